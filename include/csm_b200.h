@@ -1,0 +1,147 @@
+/*
+ * csm_b200.h -- C ABI of libcsm_b200.so: the CSM-1B frame-generation hot path of
+ * zenoran/sesameai-tts as hand-written sm_100a CUDA kernels.
+ *
+ * Boundary rules:
+ *   - plain C, POD arguments only; every pointer marked "dev" is a CUDA device pointer
+ *     (torch ``tensor.data_ptr()``), ``stream`` is a ``cudaStream_t`` passed as void*;
+ *   - the caller (PyTorch) owns every buffer: weights, workspace, inputs, outputs.  The
+ *     library owns only CUDA graphs / descriptors inside ``csm_ctx``;
+ *   - every call is stream ordered and never synchronises the device; a ctx is not thread-safe
+ *     (the reference's KV caches are mutable module state too);
+ *   - return value 0 = success, negative = error (``csm_last_error`` gives the text).  Nothing
+ *     throws or exits across the ABI.  There is NO CPU fallback: without a CUDA device every
+ *     compute call returns CSM_ERR_CUDA.
+ *
+ * Each entry point cites the reference interface (file:line under /root/reference) it replaces.
+ */
+#ifndef CSM_B200_H
+#define CSM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSM_B200_ABI_VERSION 1
+
+enum {
+  CSM_OK = 0,
+  CSM_ERR_ARG = -1,       /* bad argument / unsupported shape                     */
+  CSM_ERR_CUDA = -2,      /* CUDA runtime error (see csm_last_error)              */
+  CSM_ERR_STATE = -3,     /* e.g. caches not enabled -> Python AssertionError     */
+  CSM_ERR_OVERFLOW = -4,  /* KV cache would exceed max_seq_len                    */
+  CSM_ERR_WORKSPACE = -5  /* workspace too small                                  */
+};
+
+/* One llama3_2 stack (sesameai/models.py:10-39). head_dim = dim / heads, must be 64 or 128. */
+typedef struct csm_stack_config {
+  int32_t layers, dim, heads, kv_heads, ff;
+} csm_stack_config;
+
+/* ModelArgs + the constants hard-wired in sesameai/models.py:10-39,90-96,127. */
+typedef struct csm_config {
+  csm_stack_config backbone;   /* llama-1B:   16, 2048, 32, 8, 8192 */
+  csm_stack_config decoder;    /* llama-100M:  4, 1024,  8, 2, 8192 */
+  int32_t text_vocab;          /* 128256 */
+  int32_t audio_vocab;         /* 2051   */
+  int32_t codebooks;           /* 32     */
+  int32_t max_seq_len;         /* backbone KV slots, 2048 (models.py:17)                      */
+  float norm_eps;              /* 1e-5 */
+} csm_config;
+
+/* bf16 device pointers to one layer's parameters, torch layout ([out,in] row-major). */
+typedef struct csm_layer_weights {
+  const void *q_proj, *k_proj, *v_proj, *output_proj; /* attn.{q,k,v,output}_proj.weight */
+  const void *w1, *w2, *w3;                           /* mlp.w1 (gate), w2 (down), w3 (up) */
+  const void *sa_norm, *mlp_norm;                     /* {sa,mlp}_norm.scale               */
+} csm_layer_weights;
+
+/* All parameters of ``Model`` (sesameai/models.py:110-118), bf16, on the device. */
+typedef struct csm_weights {
+  const void *text_embeddings;   /* [text_vocab, D]                                   */
+  const void *audio_embeddings;  /* [audio_vocab*codebooks, D]                        */
+  const void *projection;        /* [Dd, D]                                           */
+  const void *codebook0_head;    /* [audio_vocab, D]                                  */
+  const void *audio_head;        /* [codebooks-1, Dd, audio_vocab]  ([in,out] per slice, models.py:118,176) */
+  const void *backbone_norm, *decoder_norm;       /* norm.scale                       */
+  const void *backbone_rope, *decoder_rope;       /* Llama3ScaledRoPE cache [max_pos, hd/2, 2] (cos,sin), bf16 */
+  int32_t backbone_rope_len, decoder_rope_len;    /* rows in the tables               */
+  const csm_layer_weights *backbone_layers;       /* host array[backbone.layers]      */
+  const csm_layer_weights *decoder_layers;        /* host array[decoder.layers]       */
+} csm_weights;
+
+typedef struct csm_ctx csm_ctx;
+
+/* ---- life cycle --------------------------------------------------------------------------- */
+
+int32_t csm_abi_version(void);
+const char *csm_last_error(void);
+
+/* Bytes of device workspace csm_create needs for ``max_batch`` streams: KV caches (GQA-compact
+ * [L][B][KV][slots][hd] bf16), packed weight copies, activation scratch.  Returns 0 on bad config. */
+size_t csm_workspace_bytes(const csm_config *cfg, int32_t max_batch);
+
+/* Replaces Model.setup_caches(max_batch_size) (sesameai/models.py:120-130; torchtune
+ * TransformerDecoder.setup_caches).  ``workspace`` is a dev buffer of >= csm_workspace_bytes,
+ * 256-byte aligned; weights are re-packed from ``w`` on ``stream`` (fused QKV, interleaved
+ * gate/up, transposed audio heads).  No causal-mask tensors are built: masks are implicit. */
+int32_t csm_create(const csm_config *cfg, const csm_weights *w, int32_t max_batch, void *workspace,
+                   size_t workspace_bytes, void *stream, csm_ctx **out);
+void csm_destroy(csm_ctx *ctx);
+
+/* Replaces Model.reset_caches() (sesameai/models.py:186-188): rewinds the backbone and decoder
+ * cache positions.  No memset is needed because attention never reads beyond the valid length. */
+int32_t csm_reset_caches(csm_ctx *ctx);
+
+/* Backbone positions currently held in the KV cache (torchtune KVCache.size). */
+int32_t csm_cache_len(const csm_ctx *ctx);
+
+/* ---- the hot path -------------------------------------------------------------------------- */
+
+/* Optional per-call extras; zero-initialise for the plain reference behaviour. */
+typedef struct csm_frame_opts {
+  const void *noise;      /* dev bf16 [codebooks, B, audio_vocab] Exp(1) draws q, or NULL -> in-kernel RNG */
+  uint64_t seed;          /* RNG seed when noise == NULL                                                   */
+  uint64_t offset;        /* RNG stream offset (frame counter) when noise == NULL                          */
+  const int32_t *forced;  /* dev [B, codebooks] teacher-forced tokens, or NULL                             */
+  void *logits_out;       /* dev bf16 [codebooks, B, audio_vocab] raw head outputs, or NULL                */
+  int32_t *sampled_out;   /* dev [B, codebooks] sampled tokens before forcing, or NULL                     */
+  int32_t no_graph;       /* 1 = launch kernels directly instead of replaying the captured CUDA graph      */
+} csm_frame_opts;
+
+/* Replaces Model.generate_frame(tokens, tokens_mask, input_pos, temperature, topk)
+ * (sesameai/models.py:132-184): embeds S frames per stream, appends S positions to the backbone
+ * KV cache, samples codebook 0 from the last position and runs the 31-step depth decoder.
+ *   tokens      dev int64 [B, S, codebooks+1]
+ *   tokens_mask dev uint8 (torch.bool) [B, S, codebooks+1]
+ *   input_pos   dev int64 [B, S]
+ *   out         dev int32 [B, codebooks]
+ * CSM_ERR_STATE if B exceeds max_batch; CSM_ERR_OVERFLOW if the cache would pass max_seq_len
+ * (torchtune KVCache.update's assert). */
+int32_t csm_generate_frame(csm_ctx *ctx, const int64_t *tokens, const uint8_t *tokens_mask,
+                           const int64_t *input_pos, int32_t B, int32_t S, float temperature, int32_t topk,
+                           const csm_frame_opts *opts, int32_t *out, void *stream);
+
+/* ---- single-kernel entry points for unit parity tests (tests/ only) ------------------------ */
+
+/* sample_topk (sesameai/models.py:77-87) on logits bf16 [B, V] with noise bf16 [B, V] -> int32 [B]. */
+int32_t csm_k_sample_topk(const void *logits, const void *noise, int32_t B, int32_t V, float temperature,
+                          int32_t topk, int32_t *out, void *stream);
+
+/* _embed_tokens + mask + sum (sesameai/models.py:155-157,193-203): -> bf16 [N, D]. */
+int32_t csm_k_embed_frames(const int64_t *tokens, const uint8_t *mask, const void *text_emb, const void *audio_emb,
+                           int32_t N, int32_t codebooks, int32_t audio_vocab, int32_t D, void *out, void *stream);
+
+/* y[N, out] = bf16(x[N, in] @ W[out, in]^T), x/W/y bf16 (nn.Linear without bias). */
+int32_t csm_k_linear(const void *x, const void *W, int32_t N, int32_t in, int32_t out, void *y, void *stream);
+
+/* torchtune RMSNorm: bf16(bf16(x * rsqrt(mean x^2 + eps)) * scale), [N, D]. */
+int32_t csm_k_rmsnorm(const void *x, const void *scale, int32_t N, int32_t D, float eps, void *y, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSM_B200_H */

@@ -1,0 +1,475 @@
+// C ABI of libcsm_b200.so (include/csm_b200.h): context, workspace carving, weight packing,
+// the generate_frame launch sequence and its CUDA-graph capture.
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <new>
+#include <vector>
+
+#include "../../include/csm_b200.h"
+#include "lm_kernels.cuh"
+
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, const char* a = "", const char* b = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+#define CU_TRY(expr)                                                                       \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) return set_err(CSM_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+extern "C" int32_t csm_abi_version(void) { return CSM_B200_ABI_VERSION; }
+extern "C" const char* csm_last_error(void) { return g_err; }
+
+// ---------------------------------------------------------------------------------------------
+static const int PREFILL_CHUNK = 8;  // prompt frames per stream per small-row pass
+
+struct StackDev {
+  csm_stack_config c;
+  int hd, slots;
+  std::vector<bf16*> wqkv, wgu;              // packed (workspace)
+  std::vector<const bf16*> wo, wd, sa, mlp;  // caller's tensors
+  const bf16* norm;
+  const bf16* rope;
+  int rope_len;
+  bf16 *kc, *vc;  // [layers][streams][kv][slots][hd]
+  size_t kv_layer_stride;
+  // activations
+  bf16 *h, *q, *att, *act;
+};
+
+struct csm_ctx {
+  csm_config cfg;
+  int max_batch, max_rows, Vp;
+  StackDev bb, dec;
+  const bf16 *text_emb, *audio_emb, *proj, *c0_head;
+  bf16* head_t;   // [C-1][Vp][Dd]
+  bf16* dec_in;   // [2B][D]
+  bf16* logits;   // [B][Vp]
+  int *row_stream, *row_pos, *row_slot;
+  FrameParams* d_params;
+  int cache_len;
+  bool enabled;
+  cudaStream_t cap_stream;
+  std::map<int, cudaGraphExec_t> graphs;  // keyed by B
+};
+
+struct Carver {
+  char* base;
+  size_t off;
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+static bool valid_stack(const csm_stack_config& s) {
+  if (s.layers < 1 || s.heads < 1 || s.kv_heads < 1 || s.dim % s.heads) return false;
+  const int hd = s.dim / s.heads;
+  return (hd == 64 || hd == 128) && s.heads % s.kv_heads == 0 && s.dim % 256 == 0 && s.ff % 256 == 0 &&
+         s.dim <= 8192 && s.ff <= 8192;
+}
+static bool valid_cfg(const csm_config* c) {
+  return c && valid_stack(c->backbone) && valid_stack(c->decoder) && c->codebooks >= 2 && c->codebooks <= 64 &&
+         c->audio_vocab >= 2 && c->audio_vocab <= SAMPLE_MAXV && c->text_vocab >= 1 && c->max_seq_len >= c->codebooks;
+}
+
+static void carve_stack(Carver& cv, StackDev& s, const csm_stack_config& c, int slots, int streams, int rows) {
+  s.c = c;
+  s.hd = c.dim / c.heads;
+  s.slots = slots;
+  const size_t qkv_rows = (size_t)(c.heads + 2 * c.kv_heads) * s.hd;
+  s.wqkv.resize(c.layers);
+  s.wgu.resize(c.layers);
+  for (int l = 0; l < c.layers; ++l) {
+    s.wqkv[l] = cv.take<bf16>(qkv_rows * c.dim);
+    s.wgu[l] = cv.take<bf16>((size_t)2 * c.ff * c.dim);
+  }
+  s.kv_layer_stride = (size_t)streams * c.kv_heads * slots * s.hd;
+  s.kc = cv.take<bf16>(s.kv_layer_stride * c.layers);
+  s.vc = cv.take<bf16>(s.kv_layer_stride * c.layers);
+  s.h = cv.take<bf16>((size_t)rows * c.dim);
+  s.q = cv.take<bf16>((size_t)rows * c.dim);
+  s.att = cv.take<bf16>((size_t)rows * c.dim);
+  s.act = cv.take<bf16>((size_t)rows * c.ff);
+}
+
+static size_t carve_all(csm_ctx* x, char* base) {
+  Carver cv{base, 0};
+  const csm_config& c = x->cfg;
+  x->max_rows = x->max_batch * PREFILL_CHUNK;
+  x->Vp = (c.audio_vocab + 7) & ~7;
+  carve_stack(cv, x->bb, c.backbone, c.max_seq_len, x->max_batch, x->max_rows);
+  carve_stack(cv, x->dec, c.decoder, c.codebooks, x->max_batch, 2 * x->max_batch);
+  x->head_t = cv.take<bf16>((size_t)(c.codebooks - 1) * x->Vp * c.decoder.dim);
+  x->dec_in = cv.take<bf16>((size_t)2 * x->max_batch * c.backbone.dim);
+  x->logits = cv.take<bf16>((size_t)x->max_batch * x->Vp);
+  x->row_stream = cv.take<int>(x->max_rows);
+  x->row_pos = cv.take<int>(x->max_rows);
+  x->row_slot = cv.take<int>(x->max_rows);
+  x->d_params = cv.take<FrameParams>(1);
+  return (cv.off + 255) & ~(size_t)255;
+}
+
+extern "C" size_t csm_workspace_bytes(const csm_config* cfg, int32_t max_batch) {
+  if (!valid_cfg(cfg) || max_batch < 1) return 0;
+  csm_ctx tmp;
+  tmp.cfg = *cfg;
+  tmp.max_batch = max_batch;
+  return carve_all(&tmp, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int NB, int EPI, bool NORM>
+static cudaError_t gemv_attr() {
+  return cudaFuncSetAttribute(k_gemv<NB, EPI, NORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8192 * 2);
+}
+template <int EPI, bool NORM>
+static cudaError_t gemv_attrs() {
+  cudaError_t e;
+  if ((e = gemv_attr<1, EPI, NORM>()) != cudaSuccess) return e;
+  if ((e = gemv_attr<2, EPI, NORM>()) != cudaSuccess) return e;
+  if ((e = gemv_attr<4, EPI, NORM>()) != cudaSuccess) return e;
+  return gemv_attr<8, EPI, NORM>();
+}
+// opt every GEMV instantiation into > 48 KB of dynamic shared memory (once per process)
+static cudaError_t init_kernel_attrs() {
+  static bool done = false;
+  if (done) return cudaSuccess;
+  cudaError_t e;
+  if ((e = gemv_attrs<EPI_PLAIN, false>()) != cudaSuccess) return e;
+  if ((e = gemv_attrs<EPI_PLAIN, true>()) != cudaSuccess) return e;
+  if ((e = gemv_attrs<EPI_RESID, false>()) != cudaSuccess) return e;
+  if ((e = gemv_attrs<EPI_SWIGLU, true>()) != cudaSuccess) return e;
+  if ((e = gemv_attrs<EPI_ROPE_KV, true>()) != cudaSuccess) return e;
+  done = true;
+  return cudaSuccess;
+}
+
+template <int NB, int EPI, bool NORM>
+static cudaError_t launch_gemv_t(const GemvArgs& a, cudaStream_t st) {
+  const int threads = 256, wpc = threads / 32;
+  const int npairs = (a.rows + 1) / 2;
+  int gx = (npairs + wpc - 1) / wpc;
+  if (gx > 148 * 8) gx = 148 * 8;
+  dim3 grid(gx, (a.N + NB - 1) / NB);
+  const size_t smem = (size_t)NB * a.K * sizeof(bf16);
+  k_gemv<NB, EPI, NORM><<<grid, threads, smem, st>>>(a);
+  return cudaGetLastError();
+}
+template <int EPI, bool NORM>
+static cudaError_t launch_gemv(const GemvArgs& a, cudaStream_t st) {
+  if (a.N <= 1) return launch_gemv_t<1, EPI, NORM>(a, st);
+  if (a.N <= 2) return launch_gemv_t<2, EPI, NORM>(a, st);
+  if (a.N <= 4) return launch_gemv_t<4, EPI, NORM>(a, st);
+  return launch_gemv_t<8, EPI, NORM>(a, st);
+}
+
+struct RowMeta {
+  const int *stream, *pos, *slot;
+  int imp_B, imp_pos;
+};
+
+// One transformer layer on N rows (torchtune TransformerSelfAttentionLayer, Appendix A.3-A.4).
+static cudaError_t run_layer(csm_ctx* x, StackDev& s, int l, int N, const RowMeta& m, cudaStream_t st) {
+  const csm_stack_config& c = s.c;
+  cudaError_t e;
+  GemvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.eps = x->cfg.norm_eps;
+  a.N = N;
+  a.row_stream = m.stream; a.row_pos = m.pos; a.row_slot = m.slot; a.imp_B = m.imp_B; a.imp_pos = m.imp_pos;
+  a.heads = c.heads; a.kv_heads = c.kv_heads; a.hd = s.hd; a.slots = s.slots;
+  bf16* kc = s.kc + s.kv_layer_stride * l;
+  bf16* vc = s.vc + s.kv_layer_stride * l;
+  // K2: sa_norm + [q;k;v] + RoPE + KV append
+  a.W = s.wqkv[l]; a.rows = (c.heads + 2 * c.kv_heads) * s.hd; a.K = c.dim;
+  a.x = s.h; a.ldx = c.dim; a.norm_scale = s.sa[l];
+  a.q_out = s.q; a.k_cache = kc; a.v_cache = vc; a.rope = s.rope;
+  if ((e = launch_gemv<EPI_ROPE_KV, true>(a, st)) != cudaSuccess) return e;
+  // K3: attention
+  {
+    dim3 grid(N, c.heads);
+    const size_t smem = (size_t)s.slots * sizeof(float);
+    const float scale = 1.0f / sqrtf((float)s.hd);
+    if (s.hd == 64)
+      k_attn_rows<64><<<grid, 128, smem, st>>>(s.q, kc, vc, m.stream, m.slot, m.imp_B, m.imp_pos, c.heads, c.kv_heads,
+                                               s.slots, scale, s.att);
+    else
+      k_attn_rows<128><<<grid, 128, smem, st>>>(s.q, kc, vc, m.stream, m.slot, m.imp_B, m.imp_pos, c.heads, c.kv_heads,
+                                                s.slots, scale, s.att);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  // K4: output_proj + residual (in place on h)
+  a.W = s.wo[l]; a.rows = c.dim; a.K = c.dim; a.x = s.att; a.ldx = c.dim;
+  a.out = s.h; a.ldo = c.dim; a.resid = s.h; a.ldr = c.dim;
+  if ((e = launch_gemv<EPI_RESID, false>(a, st)) != cudaSuccess) return e;
+  // K5: mlp_norm + interleaved gate/up + SiLU*mul
+  a.W = s.wgu[l]; a.rows = 2 * c.ff; a.K = c.dim; a.x = s.h; a.ldx = c.dim; a.norm_scale = s.mlp[l];
+  a.out = s.act; a.ldo = c.ff;
+  if ((e = launch_gemv<EPI_SWIGLU, true>(a, st)) != cudaSuccess) return e;
+  // K6: down + residual
+  a.W = s.wd[l]; a.rows = c.dim; a.K = c.ff; a.x = s.act; a.ldx = c.ff;
+  a.out = s.h; a.ldo = c.dim; a.resid = s.h; a.ldr = c.dim;
+  return launch_gemv<EPI_RESID, false>(a, st);
+}
+
+// Backbone pass over `chunk` prompt frames per stream starting at P->s0 (rows n = b*chunk + t).
+static cudaError_t backbone_pass(csm_ctx* x, int B, int chunk, cudaStream_t st) {
+  const csm_config& c = x->cfg;
+  const int N = B * chunk;
+  k_embed_pass<<<N, 256, 0, st>>>(x->d_params, x->text_emb, x->audio_emb, c.codebooks, c.audio_vocab, c.backbone.dim,
+                                  chunk, x->bb.h, x->row_stream, x->row_pos, x->row_slot);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  RowMeta m{x->row_stream, x->row_pos, x->row_slot, 0, 0};
+  for (int l = 0; l < c.backbone.layers; ++l)
+    if ((e = run_layer(x, x->bb, l, N, m, st)) != cudaSuccess) return e;
+  return cudaSuccess;
+}
+
+// Everything after the backbone layers of the LAST prompt row: final norm, codebook-0 head + sample,
+// then the 31-step depth decoder (sesameai/models.py:160-184).  Requires chunk == 1 rows (n == b).
+static cudaError_t frame_tail(csm_ctx* x, int B, cudaStream_t st) {
+  const csm_config& c = x->cfg;
+  const int D = c.backbone.dim, Dd = c.decoder.dim, V = c.audio_vocab, C = c.codebooks;
+  cudaError_t e;
+  // last_h = backbone.norm(h)  -> decoder input rows [0, B)
+  k_rmsnorm<<<B, 256, 0, st>>>(x->bb.h, D, x->bb.norm, D, c.norm_eps, x->dec_in, D);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  GemvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.eps = c.norm_eps;
+  // codebook0_head
+  a.W = x->c0_head; a.rows = V; a.K = D; a.x = x->dec_in; a.ldx = D; a.N = B; a.out = x->logits; a.ldo = x->Vp;
+  if ((e = launch_gemv<EPI_PLAIN, false>(a, st)) != cudaSuccess) return e;
+  k_sample_step<<<B, SAMPLE_THREADS, 0, st>>>(x->d_params, x->logits, x->Vp, 0, V, C, x->audio_emb, D,
+                                              x->dec_in + (size_t)B * D);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  for (int i = 1; i < C; ++i) {
+    const int N = (i == 1) ? 2 * B : B;           // first step carries [last_h, embed(c0)]
+    const int pos0 = (i == 1) ? 0 : i;
+    // projection (sesameai/models.py:173)
+    memset(&a, 0, sizeof(a));
+    a.eps = c.norm_eps;
+    a.W = x->proj; a.rows = Dd; a.K = D; a.x = x->dec_in; a.ldx = D; a.N = N; a.out = x->dec.h; a.ldo = Dd;
+    if ((e = launch_gemv<EPI_PLAIN, false>(a, st)) != cudaSuccess) return e;
+    RowMeta m{nullptr, nullptr, nullptr, B, pos0};
+    for (int l = 0; l < c.decoder.layers; ++l)
+      if ((e = run_layer(x, x->dec, l, N, m, st)) != cudaSuccess) return e;
+    // decoder.norm + audio_head[i-1] on the last position's rows
+    memset(&a, 0, sizeof(a));
+    a.eps = c.norm_eps;
+    a.W = x->head_t + (size_t)(i - 1) * x->Vp * Dd; a.rows = V; a.K = Dd;
+    a.x = x->dec.h + (size_t)(N - B) * Dd; a.ldx = Dd; a.N = B; a.norm_scale = x->dec.norm;
+    a.out = x->logits; a.ldo = x->Vp;
+    if ((e = launch_gemv<EPI_PLAIN, true>(a, st)) != cudaSuccess) return e;
+    k_sample_step<<<B, SAMPLE_THREADS, 0, st>>>(x->d_params, x->logits, x->Vp, i, V, C, x->audio_emb, D,
+                                                (i + 1 < C) ? x->dec_in : nullptr);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------
+static int pack_stack(StackDev& s, const csm_layer_weights* lw, cudaStream_t st) {
+  const csm_stack_config& c = s.c;
+  const size_t D8 = c.dim / 8;
+  const size_t qn = (size_t)c.heads * s.hd * D8, kn = (size_t)c.kv_heads * s.hd * D8;
+  s.wo.resize(c.layers); s.wd.resize(c.layers); s.sa.resize(c.layers); s.mlp.resize(c.layers);
+  for (int l = 0; l < c.layers; ++l) {
+    const csm_layer_weights& w = lw[l];
+    if (!w.q_proj || !w.k_proj || !w.v_proj || !w.output_proj || !w.w1 || !w.w2 || !w.w3 || !w.sa_norm || !w.mlp_norm)
+      return set_err(CSM_ERR_ARG, "null layer weight pointer");
+    k_copy_rows<<<256, 256, 0, st>>>((const bf16*)w.q_proj, s.wqkv[l], qn);
+    k_copy_rows<<<256, 256, 0, st>>>((const bf16*)w.k_proj, s.wqkv[l] + qn * 8, kn);
+    k_copy_rows<<<256, 256, 0, st>>>((const bf16*)w.v_proj, s.wqkv[l] + (qn + kn) * 8, kn);
+    k_interleave_rows<<<512, 256, 0, st>>>((const bf16*)w.w1, (const bf16*)w.w3, s.wgu[l], c.ff, (int)D8);
+    s.wo[l] = (const bf16*)w.output_proj; s.wd[l] = (const bf16*)w.w2;
+    s.sa[l] = (const bf16*)w.sa_norm; s.mlp[l] = (const bf16*)w.mlp_norm;
+  }
+  CU_TRY(cudaGetLastError());
+  return CSM_OK;
+}
+
+extern "C" int32_t csm_create(const csm_config* cfg, const csm_weights* w, int32_t max_batch, void* workspace,
+                              size_t workspace_bytes, void* stream, csm_ctx** out) {
+  if (!out) return set_err(CSM_ERR_ARG, "out is null");
+  *out = nullptr;
+  if (!valid_cfg(cfg)) return set_err(CSM_ERR_ARG, "unsupported csm_config (head_dim must be 64/128, dims multiples of 256)");
+  if (!w || !workspace || max_batch < 1) return set_err(CSM_ERR_ARG, "null weights/workspace or max_batch < 1");
+  int ndev = 0;
+  CU_TRY(cudaGetDeviceCount(&ndev));
+  if (ndev < 1) return set_err(CSM_ERR_CUDA, "no CUDA device (libcsm_b200 has no CPU fallback)");
+  if (((uintptr_t)workspace & 255) != 0) return set_err(CSM_ERR_ARG, "workspace must be 256-byte aligned");
+  const size_t need = csm_workspace_bytes(cfg, max_batch);
+  if (workspace_bytes < need) return set_err(CSM_ERR_WORKSPACE, "workspace too small");
+  if (!w->text_embeddings || !w->audio_embeddings || !w->projection || !w->codebook0_head || !w->audio_head ||
+      !w->backbone_norm || !w->decoder_norm || !w->backbone_rope || !w->decoder_rope || !w->backbone_layers ||
+      !w->decoder_layers)
+    return set_err(CSM_ERR_ARG, "null weight pointer");
+  if (w->backbone_rope_len < cfg->max_seq_len || w->decoder_rope_len < cfg->codebooks)
+    return set_err(CSM_ERR_ARG, "rope table shorter than the cache");
+  CU_TRY(init_kernel_attrs());
+  csm_ctx* x = new (std::nothrow) csm_ctx();
+  if (!x) return set_err(CSM_ERR_ARG, "out of host memory");
+  x->cfg = *cfg;
+  x->max_batch = max_batch;
+  carve_all(x, (char*)workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  x->text_emb = (const bf16*)w->text_embeddings;
+  x->audio_emb = (const bf16*)w->audio_embeddings;
+  x->proj = (const bf16*)w->projection;
+  x->c0_head = (const bf16*)w->codebook0_head;
+  x->bb.norm = (const bf16*)w->backbone_norm; x->bb.rope = (const bf16*)w->backbone_rope; x->bb.rope_len = w->backbone_rope_len;
+  x->dec.norm = (const bf16*)w->decoder_norm; x->dec.rope = (const bf16*)w->decoder_rope; x->dec.rope_len = w->decoder_rope_len;
+  int rc;
+  if ((rc = pack_stack(x->bb, w->backbone_layers, st)) != CSM_OK || (rc = pack_stack(x->dec, w->decoder_layers, st)) != CSM_OK) {
+    delete x;
+    return rc;
+  }
+  {
+    const int K = cfg->decoder.dim, V = cfg->audio_vocab;
+    dim3 grid((x->Vp + 31) / 32, (K + 31) / 32, cfg->codebooks - 1), block(32, 8);
+    k_transpose_heads<<<grid, block, 0, st>>>((const bf16*)w->audio_head, x->head_t, K, V, x->Vp);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&x->cap_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete x;
+    return set_err(CSM_ERR_CUDA, "csm_create: %s", cudaGetErrorString(e));
+  }
+  x->cache_len = 0;
+  x->enabled = true;
+  *out = x;
+  return CSM_OK;
+}
+
+extern "C" void csm_destroy(csm_ctx* x) {
+  if (!x) return;
+  for (auto& kv : x->graphs) cudaGraphExecDestroy(kv.second);
+  if (x->cap_stream) cudaStreamDestroy(x->cap_stream);
+  delete x;
+}
+
+extern "C" int32_t csm_reset_caches(csm_ctx* x) {
+  if (!x || !x->enabled) return set_err(CSM_ERR_STATE, "caches are not enabled");
+  x->cache_len = 0;
+  return CSM_OK;
+}
+extern "C" int32_t csm_cache_len(const csm_ctx* x) { return x ? x->cache_len : -1; }
+
+static int get_graph(csm_ctx* x, int B, cudaGraphExec_t* out) {
+  auto it = x->graphs.find(B);
+  if (it != x->graphs.end()) {
+    *out = it->second;
+    return CSM_OK;
+  }
+  cudaGraph_t g = nullptr;
+  CU_TRY(cudaStreamBeginCapture(x->cap_stream, cudaStreamCaptureModeThreadLocal));
+  cudaError_t e = backbone_pass(x, B, 1, x->cap_stream);
+  if (e == cudaSuccess) e = frame_tail(x, B, x->cap_stream);
+  cudaError_t e2 = cudaStreamEndCapture(x->cap_stream, &g);
+  if (e != cudaSuccess || e2 != cudaSuccess) {
+    if (g) cudaGraphDestroy(g);
+    return set_err(CSM_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+  }
+  cudaGraphExec_t ge = nullptr;
+  e = cudaGraphInstantiate(&ge, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return set_err(CSM_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(e));
+  x->graphs[B] = ge;
+  *out = ge;
+  return CSM_OK;
+}
+
+extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const uint8_t* tokens_mask,
+                                      const int64_t* input_pos, int32_t B, int32_t S, float temperature, int32_t topk,
+                                      const csm_frame_opts* opts, int32_t* out, void* stream) {
+  if (!x || !x->enabled) return set_err(CSM_ERR_STATE, "backbone caches are not enabled");
+  if (!tokens || !tokens_mask || !input_pos || !out || B < 1 || S < 1) return set_err(CSM_ERR_ARG, "bad tokens/mask/pos/out");
+  if (B > x->max_batch) return set_err(CSM_ERR_STATE, "batch size exceeds the batch the caches were set up for");
+  if (x->cache_len + S > x->cfg.max_seq_len) return set_err(CSM_ERR_OVERFLOW, "KV cache overflow (cache_pos + seq_len > max_seq_len)");
+  if (!(temperature > 0.f) || topk < 1) return set_err(CSM_ERR_ARG, "temperature must be > 0 and topk >= 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  FrameParams p;
+  memset(&p, 0, sizeof(p));
+  p.tokens = tokens; p.mask = tokens_mask; p.pos = input_pos; p.out = out;
+  p.temperature = temperature; p.topk = topk; p.B = B; p.S = S; p.cache_len = x->cache_len;
+  bool no_graph = false;
+  if (opts) {
+    p.noise = (const bf16*)opts->noise; p.forced = opts->forced; p.logits_out = (bf16*)opts->logits_out;
+    p.sampled_out = opts->sampled_out; p.seed = opts->seed; p.offset = opts->offset;
+    no_graph = opts->no_graph != 0;
+  }
+  // prompt rows [0, S-1): small-row passes of up to PREFILL_CHUNK frames per stream
+  for (int s0 = 0; s0 < S - 1; s0 += PREFILL_CHUNK) {
+    const int chunk = (S - 1 - s0) < PREFILL_CHUNK ? (S - 1 - s0) : PREFILL_CHUNK;
+    p.s0 = s0;
+    k_set_params<<<1, 1, 0, st>>>(x->d_params, p);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(backbone_pass(x, B, chunk, st));
+  }
+  // last row + frame tail: the captured decode graph
+  p.s0 = S - 1;
+  k_set_params<<<1, 1, 0, st>>>(x->d_params, p);
+  CU_TRY(cudaGetLastError());
+  if (no_graph) {
+    CU_TRY(backbone_pass(x, B, 1, st));
+    CU_TRY(frame_tail(x, B, st));
+  } else {
+    cudaGraphExec_t ge;
+    int rc = get_graph(x, B, &ge);
+    if (rc != CSM_OK) return rc;
+    CU_TRY(cudaGraphLaunch(ge, st));
+  }
+  x->cache_len += S;
+  return CSM_OK;
+}
+
+// ---- unit-test entry points -----------------------------------------------------------------
+extern "C" int32_t csm_k_sample_topk(const void* logits, const void* noise, int32_t B, int32_t V, float temperature,
+                                     int32_t topk, int32_t* out, void* stream) {
+  if (!logits || !out || B < 1 || V < 1 || V > SAMPLE_MAXV) return set_err(CSM_ERR_ARG, "bad sample_topk arguments");
+  k_sample_only<<<B, SAMPLE_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)logits, (const bf16*)noise, V, temperature,
+                                                                topk, out);
+  CU_TRY(cudaGetLastError());
+  return CSM_OK;
+}
+
+extern "C" int32_t csm_k_embed_frames(const int64_t* tokens, const uint8_t* mask, const void* text_emb,
+                                      const void* audio_emb, int32_t N, int32_t codebooks, int32_t audio_vocab, int32_t D,
+                                      void* out, void* stream) {
+  if (!tokens || !mask || !text_emb || !audio_emb || !out || N < 1 || D % 8) return set_err(CSM_ERR_ARG, "bad embed arguments");
+  k_embed_frames<<<N, 256, 0, (cudaStream_t)stream>>>(tokens, mask, (const bf16*)text_emb, (const bf16*)audio_emb,
+                                                      codebooks, audio_vocab, D, (bf16*)out);
+  CU_TRY(cudaGetLastError());
+  return CSM_OK;
+}
+
+extern "C" int32_t csm_k_linear(const void* xin, const void* W, int32_t N, int32_t in, int32_t outf, void* y,
+                                void* stream) {
+  if (!xin || !W || !y || N < 1 || in % 256 || in > 8192 || outf < 1) return set_err(CSM_ERR_ARG, "bad linear arguments");
+  CU_TRY(init_kernel_attrs());
+  GemvArgs a;
+  memset(&a, 0, sizeof(a));
+  a.W = (const bf16*)W; a.rows = outf; a.K = in; a.x = (const bf16*)xin; a.ldx = in; a.N = N;
+  a.out = (bf16*)y; a.ldo = outf;
+  CU_TRY((launch_gemv<EPI_PLAIN, false>(a, (cudaStream_t)stream)));
+  return CSM_OK;
+}
+
+extern "C" int32_t csm_k_rmsnorm(const void* xin, const void* scale, int32_t N, int32_t D, float eps, void* y,
+                                 void* stream) {
+  if (!xin || !scale || !y || N < 1 || D < 1) return set_err(CSM_ERR_ARG, "bad rmsnorm arguments");
+  k_rmsnorm<<<N, 256, 0, (cudaStream_t)stream>>>((const bf16*)xin, D, (const bf16*)scale, D, eps, (bf16*)y, D);
+  CU_TRY(cudaGetLastError());
+  return CSM_OK;
+}

@@ -1,0 +1,76 @@
+// Shared device helpers for libcsm_b200 (sm_100a).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef __nv_bfloat16 bf16;
+
+#define CSM_WARP 32
+
+__device__ __forceinline__ float bf2f(bf16 x) { return __bfloat162float(x); }
+__device__ __forceinline__ bf16 f2bf(float x) { return __float2bfloat16_rn(x); }
+// value after a round trip through bf16 (one of the reference's rounding points)
+__device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// two packed bf16 -> two fp32 (exact)
+__device__ __forceinline__ float bflo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bfhi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+
+// streaming 16-byte load: weights are read once per use, keep them out of L1
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide reductions through a caller-provided 33-float smem scratch; all threads get the result
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float t = (lane < nw) ? scratch[lane] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  float t = (lane < nw) ? scratch[lane] : -INFINITY;
+  t = warp_max(t);
+  return t;
+}
+
+// dot of 8 packed bf16 weights with 8 packed bf16 activations, fp32 accumulate
+__device__ __forceinline__ float dot8(const uint4& w, const uint4& x, float acc) {
+  acc = fmaf(bflo(w.x), bflo(x.x), acc);
+  acc = fmaf(bfhi(w.x), bfhi(x.x), acc);
+  acc = fmaf(bflo(w.y), bflo(x.y), acc);
+  acc = fmaf(bfhi(w.y), bfhi(x.y), acc);
+  acc = fmaf(bflo(w.z), bflo(x.z), acc);
+  acc = fmaf(bfhi(w.z), bfhi(x.z), acc);
+  acc = fmaf(bflo(w.w), bflo(x.w), acc);
+  acc = fmaf(bfhi(w.w), bfhi(x.w), acc);
+  return acc;
+}
+
+// torch F.silu on a bf16 tensor: fp32 x/(1+exp(-x)), rounded to bf16
+__device__ __forceinline__ float silu_bf(float g) { return rbf(g / (1.0f + expf(-g))); }

@@ -1,0 +1,546 @@
+// CSM-1B language-model kernels, small-row (decode / short prefill chunk) path.
+//
+// Every weight matrix is streamed from HBM exactly once per launch with 16-byte coalesced loads
+// (one warp per output-row pair, warp-shuffle reduction); the activation rows (<= 8 per launch
+// tile) sit in shared memory.  Norm, RoPE, KV append, SwiGLU and the residual add are fused into
+// the prologue / epilogue of the GEMV that produces or consumes them, at the reference's bf16
+// rounding points.
+#pragma once
+#include "common.cuh"
+
+// Per-call parameters, written by k_set_params immediately before the (captured) kernel chain.
+struct FrameParams {
+  const int64_t* tokens;   // [B, S, C+1]
+  const uint8_t* mask;     // [B, S, C+1]
+  const int64_t* pos;      // [B, S]
+  int32_t* out;            // [B, C]
+  const bf16* noise;       // [C, B, V] or null
+  const int32_t* forced;   // [B, C] or null
+  bf16* logits_out;        // [C, B, V] or null
+  int32_t* sampled_out;    // [B, C] or null
+  unsigned long long seed, offset;
+  float temperature;
+  int topk;
+  int B, S;
+  int cache_len;           // backbone positions already in the cache before this call
+  int s0;                  // first prompt row handled by the current prefill chunk
+};
+
+__global__ void k_set_params(FrameParams* dst, FrameParams v) { *dst = v; }
+
+// ---------------------------------------------------------------------------------------------
+// K1: _embed_tokens + mask-mul + sum  (sesameai/models.py:155-157,193-203)
+// h[n,:] = sum_{c<C} m_c * A[tok_c + V*c] + m_C * T[tok_C], fp32 accumulate in column order,
+// one rounding to bf16.  One CTA per frame row, 16-byte gathers.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void embed_row(const int64_t* tok, const uint8_t* msk, const bf16* text_emb,
+                                          const bf16* audio_emb, int C, int V, int D, bf16* out) {
+  for (int d8 = threadIdx.x; d8 < D / 8; d8 += blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int c = 0; c <= C; ++c) {
+      if (!msk[c]) continue;  // masked slots contribute row*0 (exact for finite weights)
+      const bf16* row = (c < C) ? audio_emb + ((size_t)tok[c] + (size_t)V * c) * D : text_emb + (size_t)tok[c] * D;
+      uint4 v = *reinterpret_cast<const uint4*>(row + d8 * 8);
+      acc[0] += bflo(v.x); acc[1] += bfhi(v.x); acc[2] += bflo(v.y); acc[3] += bfhi(v.y);
+      acc[4] += bflo(v.z); acc[5] += bfhi(v.z); acc[6] += bflo(v.w); acc[7] += bfhi(v.w);
+    }
+    __nv_bfloat162 o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
+    *reinterpret_cast<uint4*>(out + d8 * 8) = *reinterpret_cast<uint4*>(o);
+  }
+}
+
+__global__ void k_embed_frames(const int64_t* tokens, const uint8_t* mask, const bf16* text_emb,
+                               const bf16* audio_emb, int C, int V, int D, bf16* out) {
+  const int n = blockIdx.x;
+  embed_row(tokens + (size_t)n * (C + 1), mask + (size_t)n * (C + 1), text_emb, audio_emb, C, V, D,
+            out + (size_t)n * D);
+}
+
+// Backbone input rows for one pass: rows n = b*chunk + t  <->  prompt frame s = s0 + t of stream b.
+// Also emits the row metadata (stream, RoPE position, cache slot) the layer kernels use.
+__global__ void k_embed_pass(const FrameParams* __restrict__ P, const bf16* text_emb, const bf16* audio_emb, int C,
+                             int V, int D, int chunk, bf16* h, int* row_stream, int* row_pos, int* row_slot) {
+  const int n = blockIdx.x;
+  const int b = n / chunk, t = n % chunk;
+  const int s = P->s0 + t;
+  const size_t fr = (size_t)b * P->S + s;
+  embed_row(P->tokens + fr * (C + 1), P->mask + fr * (C + 1), text_emb, audio_emb, C, V, D, h + (size_t)n * D);
+  if (threadIdx.x == 0) {
+    row_stream[n] = b;
+    row_pos[n] = (int)P->pos[fr];
+    row_slot[n] = P->cache_len + s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// torchtune RMSNorm (Appendix A.3) on NB rows already resident in smem as raw bf16:
+// xn = bf16( bf16(x * rsqrt(mean(x^2)+eps)) * scale ), written back in place.
+// ---------------------------------------------------------------------------------------------
+template <int NB>
+__device__ __forceinline__ void rmsnorm_smem(bf16* xs, int K, const bf16* __restrict__ scale, float eps,
+                                             float* scratch) {
+  float inv[NB];
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
+    float ss = 0.f;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+      float v = bf2f(xs[nb * K + k]);
+      ss = fmaf(v, v, ss);
+    }
+    ss = block_sum(ss, scratch);
+    inv[nb] = 1.0f / sqrtf(ss / (float)K + eps);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float sc = bf2f(scale[k]);
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      float v = rbf(bf2f(xs[nb * K + k]) * inv[nb]);
+      xs[nb * K + k] = f2bf(v * sc);
+    }
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMV family: y[n, r] = sum_k W[r, k] * x[n, k] for NB activation rows per CTA tile.
+// One warp owns an output-row PAIR (2i, 2i+1): RoPE rotates such pairs, and the gate/up matrices
+// are interleaved so a pair is (gate_i, up_i).
+// ---------------------------------------------------------------------------------------------
+enum { EPI_PLAIN = 0, EPI_RESID = 1, EPI_SWIGLU = 2, EPI_ROPE_KV = 3 };
+
+struct GemvArgs {
+  const bf16* W;  // [rows, K] row-major
+  int rows, K;
+  const bf16* x;  // [N, ldx]
+  int ldx, N;
+  const bf16* norm_scale;  // NORM prologue
+  float eps;
+  bf16* out;  // PLAIN: [N, ldo] (rows cols); RESID: [N, ldo]; SWIGLU: [N, ldo] (rows/2 cols)
+  int ldo;
+  const bf16* resid;  // RESID: [N, ldr]
+  int ldr;
+  // EPI_ROPE_KV
+  bf16* q_out;  // [N, heads*hd]
+  bf16* k_cache;  // [streams, kv_heads, slots, hd]
+  bf16* v_cache;
+  const bf16* rope;  // [max_pos, hd/2, 2]
+  const int* row_stream;  // null -> implicit: stream = n % imp_B, pos = slot = imp_pos + n / imp_B
+  const int* row_pos;
+  const int* row_slot;
+  int imp_B, imp_pos;
+  int heads, kv_heads, hd, slots;
+};
+
+template <int NB, int EPI, bool NORM>
+__global__ void __launch_bounds__(512) k_gemv(GemvArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  bf16* xs = reinterpret_cast<bf16*>(smem_raw);
+  __shared__ float scratch[33];
+  const int K = a.K;
+  const int n0 = blockIdx.y * NB;
+
+  // stage the activation rows (zero-fill rows past N)
+  for (int i = threadIdx.x; i < NB * (K / 8); i += blockDim.x) {
+    const int nb = i / (K / 8), k8 = i % (K / 8);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (n0 + nb < a.N) v = *reinterpret_cast<const uint4*>(a.x + (size_t)(n0 + nb) * a.ldx + k8 * 8);
+    *reinterpret_cast<uint4*>(xs + nb * K + k8 * 8) = v;
+  }
+  __syncthreads();
+  if (NORM) rmsnorm_smem<NB>(xs, K, a.norm_scale, a.eps, scratch);
+
+  const int lane = threadIdx.x & 31;
+  const int warps_per_cta = blockDim.x >> 5;
+  const int npairs = (a.rows + 1) >> 1;
+  for (int p = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); p < npairs; p += gridDim.x * warps_per_cta) {
+    const int r0 = 2 * p, r1 = 2 * p + 1;
+    const bool has1 = r1 < a.rows;
+    const bf16* w0 = a.W + (size_t)r0 * K;
+    const bf16* w1 = a.W + (size_t)(has1 ? r1 : r0) * K;
+    float acc0[NB], acc1[NB];
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) acc0[nb] = acc1[nb] = 0.f;
+#pragma unroll 4
+    for (int k = lane * 8; k < K; k += 256) {
+      const uint4 a0 = ld_stream(w0 + k);
+      const uint4 a1 = ld_stream(w1 + k);
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const uint4 xv = *reinterpret_cast<const uint4*>(xs + nb * K + k);
+        acc0[nb] = dot8(a0, xv, acc0[nb]);
+        acc1[nb] = dot8(a1, xv, acc1[nb]);
+      }
+    }
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      acc0[nb] = warp_sum(acc0[nb]);
+      acc1[nb] = warp_sum(acc1[nb]);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int nb = 0; nb < NB; ++nb) {
+        const int n = n0 + nb;
+        if (n >= a.N) break;
+        const float y0 = rbf(acc0[nb]), y1 = rbf(acc1[nb]);  // nn.Linear output is bf16
+        if (EPI == EPI_PLAIN) {
+          a.out[(size_t)n * a.ldo + r0] = f2bf(y0);
+          if (has1) a.out[(size_t)n * a.ldo + r1] = f2bf(y1);
+        } else if (EPI == EPI_RESID) {
+          a.out[(size_t)n * a.ldo + r0] = f2bf(y0 + bf2f(a.resid[(size_t)n * a.ldr + r0]));
+          if (has1) a.out[(size_t)n * a.ldo + r1] = f2bf(y1 + bf2f(a.resid[(size_t)n * a.ldr + r1]));
+        } else if (EPI == EPI_SWIGLU) {
+          // pair = (gate_p, up_p):  bf16( bf16(silu(gate)) * up )
+          a.out[(size_t)n * a.ldo + p] = f2bf(silu_bf(y0) * y1);
+        } else {  // EPI_ROPE_KV
+          const int hd = a.hd, qrows = a.heads * hd, krows = a.kv_heads * hd;
+          float o0 = y0, o1 = y1;
+          const int m_stream = a.row_stream ? a.row_stream[n] : n % a.imp_B;
+          const int m_pos = a.row_stream ? a.row_pos[n] : a.imp_pos + n / a.imp_B;
+          const int m_slot = a.row_stream ? a.row_slot[n] : a.imp_pos + n / a.imp_B;
+          if (r0 < qrows + krows) {
+            const int j = (r0 % hd) >> 1;
+            const bf16* cs = a.rope + ((size_t)m_pos * (hd / 2) + j) * 2;
+            const float c = bf2f(cs[0]), s = bf2f(cs[1]);
+            // fp32, un-fused, exactly as the reference evaluates it (Appendix A.5)
+            o0 = rbf(__fsub_rn(__fmul_rn(y0, c), __fmul_rn(y1, s)));
+            o1 = rbf(__fadd_rn(__fmul_rn(y1, c), __fmul_rn(y0, s)));
+          }
+          if (r0 < qrows) {
+            a.q_out[(size_t)n * qrows + r0] = f2bf(o0);
+            a.q_out[(size_t)n * qrows + r1] = f2bf(o1);
+          } else {
+            const bool isk = r0 < qrows + krows;
+            const int rr = r0 - (isk ? qrows : qrows + krows);
+            const int kvh = rr / hd, d = rr % hd;
+            bf16* dst = (isk ? a.k_cache : a.v_cache) +
+                        (((size_t)m_stream * a.kv_heads + kvh) * a.slots + m_slot) * hd + d;
+            dst[0] = f2bf(o0);
+            dst[1] = f2bf(o1);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: attention over the GQA-compact KV cache, keys [0 .. slot] of the row's stream
+// (== the reference's bool-mask row over the zero-padded cache).
+// One CTA per (row, q-head); fp32 scores/softmax, bf16 output.
+// ---------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(128) k_attn_rows(const bf16* __restrict__ q, const bf16* __restrict__ k_cache,
+                                                   const bf16* __restrict__ v_cache, const int* __restrict__ row_stream,
+                                                   const int* __restrict__ row_slot, int imp_B, int imp_pos, int heads,
+                                                   int kv_heads, int slots, float scale, bf16* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* sc = reinterpret_cast<float*>(smem_raw);  // [slots]
+  __shared__ float scratch[33];
+  __shared__ float part[128];
+  const int n = blockIdx.x, h = blockIdx.y;
+  const int kvh = h / (heads / kv_heads);
+  const int nkeys = (row_stream ? row_slot[n] : imp_pos + n / imp_B) + 1;
+  const size_t base = ((size_t)(row_stream ? row_stream[n] : n % imp_B) * kv_heads + kvh) * slots * HD;
+  const bf16* kp = k_cache + base;
+  const bf16* vp = v_cache + base;
+
+  // q in registers (fp32)
+  float qf[HD];
+  {
+    const bf16* qr = q + ((size_t)n * heads + h) * HD;
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      uint4 v = *reinterpret_cast<const uint4*>(qr + i * 8);
+      qf[i * 8 + 0] = bflo(v.x); qf[i * 8 + 1] = bfhi(v.x); qf[i * 8 + 2] = bflo(v.y); qf[i * 8 + 3] = bfhi(v.y);
+      qf[i * 8 + 4] = bflo(v.z); qf[i * 8 + 5] = bfhi(v.z); qf[i * 8 + 6] = bflo(v.w); qf[i * 8 + 7] = bfhi(v.w);
+    }
+  }
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < nkeys; j += blockDim.x) {
+    const bf16* kr = kp + (size_t)j * HD;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) {
+      uint4 v = *reinterpret_cast<const uint4*>(kr + i * 8);
+      s = fmaf(qf[i * 8 + 0], bflo(v.x), s); s = fmaf(qf[i * 8 + 1], bfhi(v.x), s);
+      s = fmaf(qf[i * 8 + 2], bflo(v.y), s); s = fmaf(qf[i * 8 + 3], bfhi(v.y), s);
+      s = fmaf(qf[i * 8 + 4], bflo(v.z), s); s = fmaf(qf[i * 8 + 5], bfhi(v.z), s);
+      s = fmaf(qf[i * 8 + 6], bflo(v.w), s); s = fmaf(qf[i * 8 + 7], bfhi(v.w), s);
+    }
+    s *= scale;
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = block_max(mx, scratch);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < nkeys; j += blockDim.x) {
+    const float e = expf(sc[j] - mx);
+    sc[j] = e;
+    sum += e;
+  }
+  sum = block_sum(sum, scratch);  // (contains the __syncthreads that publishes sc[])
+  const float inv = 1.0f / sum;
+
+  // P.V : thread -> (key group g, dim d); groups stride over keys
+  constexpr int G = 128 / HD;  // 2 for hd 64, 1 for hd 128
+  const int g = threadIdx.x / HD, d = threadIdx.x % HD;
+  float acc = 0.f;
+  for (int j = g; j < nkeys; j += G) acc = fmaf(sc[j], bf2f(vp[(size_t)j * HD + d]), acc);
+  if (G > 1) {
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    if (g == 0) {
+#pragma unroll
+      for (int gg = 1; gg < G; ++gg) acc += part[gg * HD + d];
+    }
+  }
+  if (g == 0) out[((size_t)n * heads + h) * HD + d] = f2bf(acc * inv);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stand-alone RMSNorm (final norm of a stack): one CTA per row.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rmsnorm(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ scale,
+                                                 int D, float eps, bf16* __restrict__ y, int ldy) {
+  __shared__ float scratch[33];
+  const int n = blockIdx.x;
+  const bf16* xr = x + (size_t)n * ldx;
+  float ss = 0.f;
+  for (int k = threadIdx.x; k < D; k += blockDim.x) {
+    const float v = bf2f(xr[k]);
+    ss = fmaf(v, v, ss);
+  }
+  ss = block_sum(ss, scratch);
+  const float inv = 1.0f / sqrtf(ss / (float)D + eps);
+  for (int k = threadIdx.x; k < D; k += blockDim.x)
+    y[(size_t)n * ldy + k] = f2bf(rbf(bf2f(xr[k]) * inv) * bf2f(scale[k]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// K7/K8: sample_topk (sesameai/models.py:72-87) fused with the embedding gather that feeds the
+// next depth-decoder step.  One CTA per stream.
+//   x = bf16(logit / T); thr = k-th largest x (exact 16-bit radix select); x[x < thr] = -inf
+//   (ties with thr kept); ls = bf16(log_softmax(x)); p = bf16(softmax(ls)); r = bf16(p / q);
+//   token = first argmax(r).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bf_key(bf16 v) {
+  const uint32_t b = __bfloat16_as_ushort(v);
+  return (b & 0x8000u) ? (~b & 0xffffu) : (b | 0x8000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+  const uint32_t b = (k & 0x8000u) ? (k & 0x7fffu) : (~k & 0xffffu);
+  return __uint_as_float(b << 16);
+}
+
+// counter-based Exp(1) draw for production mode (no shared noise tensor): -log(u), u in (0,1],
+// rounded to bf16 like ``torch.empty_like(probs).exponential_(1)`` on a bf16 tensor.
+__device__ __forceinline__ float exp1_draw(unsigned long long seed, unsigned long long ctr) {
+  unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (ctr + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = ((float)(uint32_t)(z >> 40) + 1.0f) * (1.0f / 16777216.0f);
+  return fmaxf(rbf(-logf(u)), 1.1754944e-38f);
+}
+
+#define SAMPLE_THREADS 256
+#define SAMPLE_MAXV 4096
+
+// Core: returns the sampled token for one logits row (all threads return the same value).
+__device__ int sample_row(const bf16* __restrict__ logits, const bf16* __restrict__ noise, int V, float temperature,
+                          int topk, unsigned long long seed, unsigned long long ctr0, float* xs /*[V]*/,
+                          unsigned int* hist /*[256]*/, float* scratch /*[33]*/, int* iscratch /*[34]*/) {
+  const int tid = threadIdx.x;
+  // 1. temperature (IEEE division, rounded to bf16) + radix histogram of the high key byte
+  for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int i = tid; i < V; i += blockDim.x) {
+    const bf16 xb = f2bf(bf2f(logits[i]) / temperature);
+    xs[i] = bf2f(xb);
+    atomicAdd(&hist[bf_key(xb) >> 8], 1u);
+  }
+  __syncthreads();
+  // 2. k-th largest: walk the high-byte histogram from the top, then the low byte inside that bin
+  int k = topk < 1 ? 1 : (topk > V ? V : topk);
+  if (tid == 0) {
+    int cum = 0, b = 255;
+    for (; b > 0; --b) {
+      if (cum + (int)hist[b] >= k) break;
+      cum += hist[b];
+    }
+    iscratch[0] = b;
+    iscratch[1] = k - cum;  // rank inside the bin
+  }
+  __syncthreads();
+  const int hb = iscratch[0];
+  const int krem = iscratch[1];
+  __syncthreads();
+  for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (int i = tid; i < V; i += blockDim.x) {
+    const uint32_t key = bf_key(f2bf(xs[i]));
+    if ((int)(key >> 8) == hb) atomicAdd(&hist[key & 0xffu], 1u);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int cum = 0, b = 255;
+    for (; b > 0; --b) {
+      if (cum + (int)hist[b] >= krem) break;
+      cum += hist[b];
+    }
+    iscratch[2] = b;
+  }
+  __syncthreads();
+  const float thr = key_to_float(((uint32_t)hb << 8) | (uint32_t)iscratch[2]);
+  // 3. mask + log_softmax (fp32 internals, bf16 result)
+  for (int i = tid; i < V; i += blockDim.x) {
+    float v = xs[i];
+    if (v < thr) v = -INFINITY;
+    xs[i] = v;
+    mx = fmaxf(mx, v);
+  }
+  mx = block_max(mx, scratch);
+  float sum = 0.f;
+  for (int i = tid; i < V; i += blockDim.x) sum += expf(xs[i] - mx);
+  sum = block_sum(sum, scratch);
+  const float lse = logf(sum);
+  float mx2 = -INFINITY;
+  for (int i = tid; i < V; i += blockDim.x) {
+    const float ls = rbf((xs[i] - mx) - lse);
+    xs[i] = ls;
+    mx2 = fmaxf(mx2, ls);
+  }
+  mx2 = block_max(mx2, scratch);
+  // 4. softmax of the bf16 log-probs
+  float sum2 = 0.f;
+  for (int i = tid; i < V; i += blockDim.x) sum2 += expf(xs[i] - mx2);
+  sum2 = block_sum(sum2, scratch);
+  // 5. exponential race, first-index argmax
+  float best = -INFINITY;
+  int besti = 0x7fffffff;
+  for (int i = tid; i < V; i += blockDim.x) {
+    const float p = rbf(expf(xs[i] - mx2) / sum2);
+    const float q = noise ? bf2f(noise[i]) : exp1_draw(seed, ctr0 + i);
+    const float r = rbf(p / q);
+    if (r > best) {  // strided ascending i per thread -> keeps the first index on ties
+      best = r;
+      besti = i;
+    }
+  }
+  // block arg-max with smallest-index tie break
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (ob > best || (ob == best && oi < besti)) {
+      best = ob;
+      besti = oi;
+    }
+  }
+  __syncthreads();
+  if ((tid & 31) == 0) {
+    scratch[tid >> 5] = best;
+    iscratch[2 + (tid >> 5)] = besti;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    const int nw = (blockDim.x + 31) >> 5;
+    best = tid < nw ? scratch[tid] : -INFINITY;
+    besti = tid < nw ? iscratch[2 + tid] : 0x7fffffff;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ob > best || (ob == best && oi < besti)) {
+        best = ob;
+        besti = oi;
+      }
+    }
+    if (tid == 0) iscratch[0] = besti;
+  }
+  __syncthreads();
+  const int tok = iscratch[0];
+  __syncthreads();
+  return tok;
+}
+
+__global__ void __launch_bounds__(SAMPLE_THREADS) k_sample_only(const bf16* logits, const bf16* noise, int V,
+                                                                float temperature, int topk, int* out) {
+  __shared__ float xs[SAMPLE_MAXV];
+  __shared__ unsigned int hist[256];
+  __shared__ float scratch[33];
+  __shared__ int iscratch[36];
+  const int b = blockIdx.x;
+  const int tok = sample_row(logits + (size_t)b * V, noise ? noise + (size_t)b * V : nullptr, V, temperature, topk, 0,
+                             0, xs, hist, scratch, iscratch);
+  if (threadIdx.x == 0) out[b] = tok;
+}
+
+// Sampling step ``cb`` of a frame: logits [B, ldl] -> token; records it; gathers the embedding of
+// the (possibly teacher-forced) token into the depth decoder's next input row.
+__global__ void __launch_bounds__(SAMPLE_THREADS) k_sample_step(const FrameParams* __restrict__ P,
+                                                                const bf16* __restrict__ logits, int ldl, int cb,
+                                                                int V, int C, const bf16* __restrict__ audio_emb, int D,
+                                                                bf16* __restrict__ next_in /*[B, D] or null*/) {
+  __shared__ float xs[SAMPLE_MAXV];
+  __shared__ unsigned int hist[256];
+  __shared__ float scratch[33];
+  __shared__ int iscratch[36];
+  const int b = blockIdx.x, B = P->B;
+  const bf16* lrow = logits + (size_t)b * ldl;
+  if (P->logits_out) {
+    bf16* lo = P->logits_out + ((size_t)cb * B + b) * V;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) lo[i] = lrow[i];
+  }
+  const bf16* nz = P->noise ? P->noise + ((size_t)cb * B + b) * V : nullptr;
+  const unsigned long long ctr = ((P->offset * (unsigned long long)C + cb) * (unsigned long long)B + b) * 4096ull;
+  int tok = sample_row(lrow, nz, V, P->temperature, P->topk, P->seed, ctr, xs, hist, scratch, iscratch);
+  if (threadIdx.x == 0 && P->sampled_out) P->sampled_out[(size_t)b * C + cb] = tok;
+  if (P->forced) tok = P->forced[(size_t)b * C + cb];
+  if (threadIdx.x == 0) P->out[(size_t)b * C + cb] = tok;
+  if (next_in) {
+    const bf16* row = audio_emb + ((size_t)tok + (size_t)cb * V) * D;
+    for (int d8 = threadIdx.x; d8 < D / 8; d8 += blockDim.x)
+      *reinterpret_cast<uint4*>(next_in + (size_t)b * D + d8 * 8) = *reinterpret_cast<const uint4*>(row + d8 * 8);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight re-packing (csm_create): fused [q;k;v], interleaved gate/up, transposed audio heads.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_copy_rows(const bf16* src, bf16* dst, size_t n8) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x)
+    reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+}
+// dst[2r] = w1[r], dst[2r+1] = w3[r]
+__global__ void k_interleave_rows(const bf16* w1, const bf16* w3, bf16* dst, int rows, int K8) {
+  const size_t total = (size_t)rows * K8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / K8, k = i % K8;
+    reinterpret_cast<uint4*>(dst)[(2 * r) * K8 + k] = reinterpret_cast<const uint4*>(w1)[i];
+    reinterpret_cast<uint4*>(dst)[(2 * r + 1) * K8 + k] = reinterpret_cast<const uint4*>(w3)[i];
+  }
+}
+// src [S, K, V] -> dst [S, Vp, K] (rows v >= V zero)
+__global__ void k_transpose_heads(const bf16* src, bf16* dst, int K, int V, int Vp) {
+  __shared__ bf16 tile[32][33];
+  const int s = blockIdx.z;
+  const int v0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const bf16* sp = src + (size_t)s * K * V;
+  bf16* dp = dst + (size_t)s * Vp * K;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, v = v0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && v < V) ? sp[(size_t)k * V + v] : f2bf(0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int v = v0 + i, k = k0 + threadIdx.x;
+    if (v < Vp && k < K) dp[(size_t)v * K + k] = tile[threadIdx.x][i];
+  }
+}

@@ -102,7 +102,8 @@ def init_random_weights(model: torch.nn.Module, seed: int = 1234, residual_out_s
 
 
 @torch.no_grad()
-def plant_greedy_structure(model: torch.nn.Module, seed: int = 1234, logit_peak: float = 12.0) -> Dict[str, torch.Tensor]:
+def plant_greedy_structure(model: torch.nn.Module, seed: int = 1234, logit_peak: float = 12.0,
+                           c0_boost: float = 4.0) -> Dict[str, torch.Tensor]:
     """Overwrite the heads (and the text-embedding table) so every greedy argmax has
     a wide bf16 margin, while every kernel still runs on dense full-size data.
 
@@ -110,7 +111,8 @@ def plant_greedy_structure(model: torch.nn.Module, seed: int = 1234, logit_peak:
       step i is ``P @ A_{i-1}[c_{i-1}]`` (``sesameai/models.py:173,178``), so token
       ``pi_i^-1(c_{i-1})`` wins step i.
     * ``codebook0_head[j] = a * A_31[pi_0(j)]``: the backbone input of an audio frame
-      contains ``A_31[c_31]`` (``sesameai/models.py:155-157``).
+      contains ``A_31[c_31]`` (``sesameai/models.py:155-157``); the codebook-31 rows of the
+      embedding table are scaled by ``c0_boost`` so that this term dominates the 32-way sum.
     * ``text_embeddings[t] = A_31[t mod V]`` so the first frame after a text-only
       prompt is decided the same way.
     Call after ``init_random_weights(..., residual_out_scale=0.1)``.  The heads are
@@ -122,14 +124,16 @@ def plant_greedy_structure(model: torch.nn.Module, seed: int = 1234, logit_peak:
     A = sd["audio_embeddings.weight"]
     P = sd["projection.weight"]
     dev, dt = A.device, A.dtype
+    A.view(C, V, -1)[C - 1].mul_(c0_boost)
     A64 = A.detach().to("cpu", torch.float64).view(C, V, -1)
     P64 = P.detach().to("cpu", torch.float64)
     perms = {i: hash_permutation(V, seed, 0xA000 + i) for i in range(C)}
     d_bb = A64.shape[-1]
     d_dec = P64.shape[0]
 
-    # codebook 0 head: winner logit ~ a*|A_31[c]|^2 / rms(h_in) with |A|^2 ~ d_bb, rms(h_in) ~ sqrt(C)
-    a0 = logit_peak * (C ** 0.5) / d_bb
+    # codebook 0 head: winner logit ~ a*|A_31[c]|^2 / rms(h_in), |A_31|^2 ~ boost^2 d_bb,
+    # rms(h_in) ~ sqrt(C - 1 + boost^2)
+    a0 = logit_peak * ((C - 1 + c0_boost ** 2) ** 0.5) / (c0_boost ** 2 * d_bb)
     sd["codebook0_head.weight"].copy_((a0 * A64[C - 1][perms[0]]).to(dt).to(dev))
     # depth heads: winner logit ~ a*|P A|^2 / rms(P A) = a*sqrt(d_dec)*|P A|, |P A| ~ sqrt(d_dec)*rms
     head = sd["audio_head"]

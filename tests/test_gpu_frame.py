@@ -1,0 +1,120 @@
+"""End-to-end parity of Model.generate_frame on the B200 against the oracle and the golden
+vectors of the reference (north_star gates: bit-exact greedy tokens for >= 64 frames,
+teacher-forced logits max-abs <= 2e-2 and cosine >= 0.999)."""
+import pytest
+import torch
+
+import csm_oracle as orc
+from sesameai import synthetic as syn
+from helpers import build_oracle, build_product, gold_inputs, load_golden, next_inputs
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_ATOL = 2e-2  # north_star tolerance (bf16)
+COS_MIN = 0.999
+
+
+def _run_product_greedy(pm, gold, no_graph=False):
+    tok, msk, pos, noise = gold_inputs(gold, device="cuda")
+    F = gold["frames"].shape[0]
+    pm.reset_caches()
+    out = []
+    for f in range(F):
+        s = pm.generate_frame(tok, msk, pos, 1.0, 1, noise=noise[32 * f: 32 * f + 32], no_graph=no_graph)
+        out.append(s)
+        tok, msk, pos = next_inputs(s, pos)
+    return torch.stack(out).cpu()
+
+
+def _teacher_forced(pm, gold):
+    tok, msk, pos, noise = gold_inputs(gold, device="cuda")
+    F, B = gold["frames"].shape[0], gold["batch"]
+    pm.reset_caches()
+    worst, cos_min, sampled_equal, total = 0.0, 1.0, 0, 0
+    for f in range(F):
+        lg = torch.zeros(32, B, 2051, dtype=torch.bfloat16, device="cuda")
+        smp = torch.zeros(B, 32, dtype=torch.int32, device="cuda")
+        s = pm.generate_frame(tok, msk, pos, gold["temperature"], gold["topk"], noise=noise[32 * f: 32 * f + 32],
+                              forced=gold["frames"][f], logits_out=lg, sampled_out=smp)
+        assert torch.equal(s.cpu(), gold["frames"][f])
+        want = gold["logits"][f].float()
+        got = lg.cpu().float()
+        worst = max(worst, (got - want).abs().max().item())
+        for cb in range(32):
+            c = torch.nn.functional.cosine_similarity(got[cb].flatten(), want[cb].flatten(), dim=0).item()
+            cos_min = min(cos_min, c)
+        sampled_equal += int((smp.cpu() == gold["frames"][f]).sum())
+        total += smp.numel()
+        tok, msk, pos = next_inputs(s, pos)
+    return worst, cos_min, sampled_equal / total
+
+
+def test_tiny_greedy_tokens_bit_exact():
+    gold = load_golden("tiny_greedy.pt")
+    pm, _ = build_product(gold)
+    got = _run_product_greedy(pm, gold)
+    assert torch.equal(got, gold["frames"])
+    # direct launches and the captured CUDA graph agree
+    assert torch.equal(_run_product_greedy(pm, gold, no_graph=True), gold["frames"])
+
+
+def test_tiny_teacher_forced_logits():
+    gold = load_golden("tiny_teacher.pt")
+    pm, _ = build_product(gold)
+    worst, cos_min, frac = _teacher_forced(pm, gold)
+    assert worst <= LOGIT_ATOL, worst
+    assert cos_min >= COS_MIN, cos_min
+    assert frac >= 0.9  # same ids wherever the bf16 logits agree closely enough
+
+
+def test_tiny_batch_and_prefill_chunks_vs_oracle():
+    """B=3 streams, a 21-frame context prompt (3 small-row prefill passes), sampled with shared
+    noise under teacher forcing; ragged extras: prompt length not a multiple of the chunk."""
+    gold = dict(model_args=dict(backbone_flavor="tiny-bb", decoder_flavor="tiny-dec", text_vocab_size=1000,
+                                audio_vocab_size=2051, audio_num_codebooks=32),
+                weight_seed=77, planted=False, batch=3)
+    om, _ = build_oracle(gold)
+    pm, _ = build_product(gold)
+    tok, msk, pos = syn.voice_prompt(3, 2, 3, 6, 3, seed=11, text_vocab=1000)
+    noise = syn.exp_noise(32 * 3, 3, 2051, 5)
+    om.reset_caches(), pm.reset_caches()
+    tc, mc, pc = tok.cuda(), msk.cuda(), pos.cuda()
+    for f in range(3):
+        rec = {}
+        with torch.inference_mode():
+            s = om.generate_frame(tok, msk, pos, 0.9, 50, noise=noise[32 * f: 32 * f + 32], record=rec)
+        lg = torch.zeros(32, 3, 2051, dtype=torch.bfloat16, device="cuda")
+        sp = pm.generate_frame(tc, mc, pc, 0.9, 50, noise=noise[32 * f: 32 * f + 32].cuda(), forced=s, logits_out=lg)
+        assert torch.equal(sp.cpu(), s)
+        want = torch.stack(rec["logits"]).float()
+        assert (lg.cpu().float() - want).abs().max() <= LOGIT_ATOL
+        tok, msk, pos = next_inputs(s, pos)
+        tc, mc, pc = next_inputs(sp, pc)
+
+
+def test_errors_match_reference_behaviour():
+    gold = load_golden("tiny_greedy.pt")
+    pm, _ = build_product(gold, batch=1)
+    tok, msk, pos, _ = gold_inputs(gold, device="cuda")
+    with pytest.raises(ValueError):  # batch larger than the caches were set up for (torchtune KVCache.update)
+        pm.generate_frame(tok, msk, pos, 1.0, 1)
+    long_tok = torch.zeros(1, 2049, 33, dtype=torch.long, device="cuda")
+    with pytest.raises(AssertionError):  # cache_pos + seq_len > max_seq_len assert
+        pm.generate_frame(long_tok, long_tok.bool(), torch.arange(2049, device="cuda").unsqueeze(0), 1.0, 1)
+
+
+def test_csm1b_greedy_64_frames_bit_exact():
+    """Full-size CSM-1B, 64 frames x 32 codebooks greedy vs the reference's tokens."""
+    gold = load_golden("csm1b_greedy.pt")
+    assert gold["frames"].shape[0] >= 64 and gold["min_margin_ulps"] >= 8
+    pm, _ = build_product(gold)
+    got = _run_product_greedy(pm, gold)
+    assert torch.equal(got, gold["frames"])
+
+
+def test_csm1b_teacher_forced_logits():
+    gold = load_golden("csm1b_teacher.pt")
+    pm, _ = build_product(gold)
+    worst, cos_min, frac = _teacher_forced(pm, gold)
+    assert worst <= LOGIT_ATOL, worst
+    assert cos_min >= COS_MIN, cos_min

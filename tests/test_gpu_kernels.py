@@ -1,0 +1,127 @@
+"""Single-kernel parity on the B200: each CUDA kernel against the oracle's op on the same
+seeded inputs, called through the C ABI."""
+import pytest
+import torch
+
+import csm_oracle as orc
+from sesameai import _native
+from sesameai import synthetic as syn
+from helpers import load_golden
+from torchtune.modules import RMSNorm  # oracle shim
+
+pytestmark = pytest.mark.gpu
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _sample(logits, noise, temperature, topk):
+    out = torch.empty(logits.shape[0], dtype=torch.int32, device="cuda")
+    lg, nz = logits.cuda().contiguous(), noise.cuda().contiguous()
+    _native.check(_native.lib().csm_k_sample_topk(lg.data_ptr(), nz.data_ptr(), lg.shape[0], lg.shape[1],
+                                                  float(temperature), int(topk), out.data_ptr(), _stream()))
+    return out.cpu()
+
+
+def test_sample_topk_golden_cases():
+    """Known answers produced by the reference's own sample_topk (tests/golden/make_golden.py)."""
+    for case in load_golden("sample_topk_cases.pt"):
+        got = _sample(case["logits"], case["noise"], case["temperature"], case["topk"])
+        assert torch.equal(got, case["token"]), (case["temperature"], case["topk"])
+
+
+def test_sample_topk_identical_ids_given_identical_logits_and_noise():
+    """north_star: seeded sampling reproduces identical token IDs given identical logits."""
+    n_bad = 0
+    total = 0
+    for g, (scale, temperature, topk) in enumerate(
+            [(s, t, k) for s in (0.6, 3.0, 12.0) for (t, k) in ((1.0, 1), (0.7, 30), (0.9, 50), (0.8, 40), (1.0, 2051), (0.5, 3))]):
+        logits = torch.empty(64, 2051)
+        syn.hash_uniform_(logits, 31, g, scale * 3 ** 0.5)
+        logits = logits.to(torch.bfloat16)
+        q = syn.exp_noise(1, 64, 2051, 500 + g)[0]
+        want = orc.oracle_sample_topk(logits, topk, temperature, q).view(-1).to(torch.int32)
+        got = _sample(logits, q, temperature, topk)
+        n_bad += int((want != got).sum())
+        total += 64
+    assert n_bad == 0, f"{n_bad}/{total} sampled ids differ"
+
+
+def test_sample_topk_ties_and_extremes():
+    V = 2051
+    logits = torch.full((3, V), -3.0).to(torch.bfloat16)
+    logits[0, 10] = 5.0
+    logits[0, 900] = 5.0  # exact tie at the top: both survive topk=1, the race decides
+    logits[1, :] = 0.0  # all equal
+    logits[2, 17] = 80.0  # huge margin
+    q = syn.exp_noise(1, 3, V, 9)[0]
+    for k in (1, 2, 50):
+        want = orc.oracle_sample_topk(logits, k, 0.9, q).view(-1).to(torch.int32)
+        assert torch.equal(_sample(logits, q, 0.9, k), want)
+
+
+def test_embed_frames_matches_oracle():
+    args = orc.OracleArgs("tiny-bb", "tiny-dec", 500, 2051, 32)
+    orc.ARCH.update(syn.named_tiny_flavors())
+    om = orc.OracleCSM(args)
+    syn.init_random_weights(om, 3)
+    om.to(torch.bfloat16)
+    tok, msk, _ = syn.voice_prompt(2, 2, 3, 6, 2, text_vocab=500)
+    # ragged masks too: drop random codebooks
+    msk = msk & (syn.hash_ints(msk.numel(), 4, 4, 4).view_as(msk) > 0)
+    want = om.embed_frame_inputs(tok, msk)
+    N = tok.shape[0] * tok.shape[1]
+    out = torch.empty(N, 256, dtype=torch.bfloat16, device="cuda")
+    t, m = tok.cuda().contiguous(), msk.cuda().contiguous()
+    te, ae = om.text_embeddings.weight.data.cuda(), om.audio_embeddings.weight.data.cuda()
+    _native.check(_native.lib().csm_k_embed_frames(t.data_ptr(), m.data_ptr(), te.data_ptr(), ae.data_ptr(), N, 32, 2051,
+                                                   256, out.data_ptr(), _stream()))
+    got = out.cpu().view_as(want)
+    # fp32 accumulation over <= 33 bf16 rows: at most the last bf16 bit may differ with the sum order
+    assert (got.float() - want.float()).abs().max() <= 2.0 ** -6
+    assert (got != want).float().mean() < 0.01
+
+
+@pytest.mark.parametrize("N,K,M", [(1, 2048, 2048), (2, 1024, 2051), (5, 8192, 1024), (8, 256, 512), (19, 2048, 6)])
+def test_linear_matches_fp32_reference(N, K, M):
+    x = torch.empty(N, K)
+    w = torch.empty(M, K)
+    syn.hash_uniform_(x, 1, N, 1.0)
+    syn.hash_uniform_(w, 2, K, K ** -0.5)
+    xb, wb = x.to(torch.bfloat16).cuda(), w.to(torch.bfloat16).cuda()
+    y = torch.empty(N, M, dtype=torch.bfloat16, device="cuda")
+    _native.check(_native.lib().csm_k_linear(xb.data_ptr(), wb.data_ptr(), N, K, M, y.data_ptr(), _stream()))
+    ref = xb.float() @ wb.float().t()  # plain fp32 reference of the same op
+    err = (y.float() - ref).abs().max().item()
+    assert err <= 2.0 ** -8 * max(1.0, ref.abs().max().item()) * 1.01  # one bf16 rounding of an fp32 dot
+    cpu = torch.nn.functional.linear(xb.cpu().unsqueeze(0), wb.cpu()).squeeze(0)  # the oracle's op
+    assert (y.cpu().float() - cpu.float()).abs().max() <= 2.0 ** -7 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("N,D", [(1, 2048), (3, 1024), (7, 256)])
+def test_rmsnorm_matches_oracle(N, D):
+    x = torch.empty(N, D)
+    syn.hash_uniform_(x, 7, D, 4.0)
+    norm = RMSNorm(D, eps=1e-5)
+    syn.hash_uniform_(norm.scale.data, 8, D, 0.5)
+    norm.scale.data.add_(1.0)
+    norm.to(torch.bfloat16)
+    xb = x.to(torch.bfloat16)
+    want = norm(xb)
+    y = torch.empty(N, D, dtype=torch.bfloat16, device="cuda")
+    xs, sc = xb.cuda(), norm.scale.data.cuda()
+    _native.check(_native.lib().csm_k_rmsnorm(xs.data_ptr(), sc.data_ptr(), N, D, 1e-5, y.data_ptr(), _stream()))
+    got = y.cpu()
+    assert (got != want).float().mean() < 0.005  # sum-order only
+    assert (got.float() - want.float()).abs().max() <= 2.0 ** -6 * want.float().abs().max()
+
+
+def test_synthetic_fill_is_device_independent():
+    a = torch.empty(3, 1000)
+    b = torch.empty(3, 1000, device="cuda")
+    syn.hash_uniform_(a, 1234, 42, 0.0221)
+    syn.hash_uniform_(b, 1234, 42, 0.0221)
+    assert torch.equal(a, b.cpu())
+    assert torch.equal(a.to(torch.bfloat16), b.to(torch.bfloat16).cpu())
+    assert torch.equal(syn.hash_ints(100, 1, 2, 2051), syn.hash_ints(100, 1, 2, 2051, device="cuda").cpu())
