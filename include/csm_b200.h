@@ -78,6 +78,9 @@ typedef struct csm_ctx csm_ctx;
 /* ---- life cycle --------------------------------------------------------------------------- */
 
 int32_t csm_abi_version(void);
+/* Kernels this library has launched in this process so far (a CUDA-graph replay counts its
+ * kernel nodes); bench.py reports the difference over the timed region as ``gpu_launches``. */
+uint64_t csm_launch_count(void);
 const char *csm_last_error(void);
 
 /* Bytes of device workspace csm_create needs for ``max_batch`` streams: KV caches (GQA-compact

@@ -22,6 +22,11 @@ static int set_err(int code, const char* fmt, const char* a = "", const char* b 
     if (_e != cudaSuccess) return set_err(CSM_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
 
+// kernels launched by this library in this process (graph replays add their node count)
+static unsigned long long g_launches = 0;
+#define COUNT_LAUNCH() (++g_launches)
+extern "C" uint64_t csm_launch_count(void) { return g_launches; }
+
 extern "C" int32_t csm_abi_version(void) { return CSM_B200_ABI_VERSION; }
 extern "C" const char* csm_last_error(void) { return g_err; }
 
@@ -56,6 +61,7 @@ struct csm_ctx {
   bool enabled;
   cudaStream_t cap_stream;
   std::map<int, cudaGraphExec_t> graphs;  // keyed by B
+  std::map<int, unsigned long long> graph_nodes;
 };
 
 struct Carver {
@@ -161,7 +167,7 @@ static cudaError_t launch_gemv_t(const GemvArgs& a, cudaStream_t st) {
   if (gx > 148 * 8) gx = 148 * 8;
   dim3 grid(gx, (a.N + NB - 1) / NB);
   const size_t smem = (size_t)NB * a.K * sizeof(bf16);
-  k_gemv<NB, EPI, NORM><<<grid, threads, smem, st>>>(a);
+  k_gemv<NB, EPI, NORM><<<grid, threads, smem, st>>>(a); COUNT_LAUNCH();
   return cudaGetLastError();
 }
 template <int EPI, bool NORM>
@@ -199,12 +205,14 @@ static cudaError_t run_layer(csm_ctx* x, StackDev& s, int l, int N, const RowMet
     dim3 grid(N, c.heads);
     const size_t smem = (size_t)s.slots * sizeof(float);
     const float scale = 1.0f / sqrtf((float)s.hd);
-    if (s.hd == 64)
+    if (s.hd == 64) {
       k_attn_rows<64><<<grid, 128, smem, st>>>(s.q, kc, vc, m.stream, m.slot, m.imp_B, m.imp_pos, c.heads, c.kv_heads,
                                                s.slots, scale, s.att);
-    else
+    } else {
       k_attn_rows<128><<<grid, 128, smem, st>>>(s.q, kc, vc, m.stream, m.slot, m.imp_B, m.imp_pos, c.heads, c.kv_heads,
                                                 s.slots, scale, s.att);
+    }
+    COUNT_LAUNCH();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   // K4: output_proj + residual (in place on h)
@@ -226,7 +234,7 @@ static cudaError_t backbone_pass(csm_ctx* x, int B, int chunk, cudaStream_t st) 
   const csm_config& c = x->cfg;
   const int N = B * chunk;
   k_embed_pass<<<N, 256, 0, st>>>(x->d_params, x->text_emb, x->audio_emb, c.codebooks, c.audio_vocab, c.backbone.dim,
-                                  chunk, x->bb.h, x->row_stream, x->row_pos, x->row_slot);
+                                  chunk, x->bb.h, x->row_stream, x->row_pos, x->row_slot); COUNT_LAUNCH();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   RowMeta m{x->row_stream, x->row_pos, x->row_slot, 0, 0};
@@ -242,7 +250,7 @@ static cudaError_t frame_tail(csm_ctx* x, int B, cudaStream_t st) {
   const int D = c.backbone.dim, Dd = c.decoder.dim, V = c.audio_vocab, C = c.codebooks;
   cudaError_t e;
   // last_h = backbone.norm(h)  -> decoder input rows [0, B)
-  k_rmsnorm<<<B, 256, 0, st>>>(x->bb.h, D, x->bb.norm, D, c.norm_eps, x->dec_in, D);
+  k_rmsnorm<<<B, 256, 0, st>>>(x->bb.h, D, x->bb.norm, D, c.norm_eps, x->dec_in, D); COUNT_LAUNCH();
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   GemvArgs a;
   memset(&a, 0, sizeof(a));
@@ -251,7 +259,7 @@ static cudaError_t frame_tail(csm_ctx* x, int B, cudaStream_t st) {
   a.W = x->c0_head; a.rows = V; a.K = D; a.x = x->dec_in; a.ldx = D; a.N = B; a.out = x->logits; a.ldo = x->Vp;
   if ((e = launch_gemv<EPI_PLAIN, false>(a, st)) != cudaSuccess) return e;
   k_sample_step<<<B, SAMPLE_THREADS, 0, st>>>(x->d_params, x->logits, x->Vp, 0, V, C, x->audio_emb, D,
-                                              x->dec_in + (size_t)B * D);
+                                              x->dec_in + (size_t)B * D); COUNT_LAUNCH();
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   for (int i = 1; i < C; ++i) {
     const int N = (i == 1) ? 2 * B : B;           // first step carries [last_h, embed(c0)]
@@ -272,7 +280,7 @@ static cudaError_t frame_tail(csm_ctx* x, int B, cudaStream_t st) {
     a.out = x->logits; a.ldo = x->Vp;
     if ((e = launch_gemv<EPI_PLAIN, true>(a, st)) != cudaSuccess) return e;
     k_sample_step<<<B, SAMPLE_THREADS, 0, st>>>(x->d_params, x->logits, x->Vp, i, V, C, x->audio_emb, D,
-                                                (i + 1 < C) ? x->dec_in : nullptr);
+                                                (i + 1 < C) ? x->dec_in : nullptr); COUNT_LAUNCH();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   return cudaSuccess;
@@ -288,10 +296,10 @@ static int pack_stack(StackDev& s, const csm_layer_weights* lw, cudaStream_t st)
     const csm_layer_weights& w = lw[l];
     if (!w.q_proj || !w.k_proj || !w.v_proj || !w.output_proj || !w.w1 || !w.w2 || !w.w3 || !w.sa_norm || !w.mlp_norm)
       return set_err(CSM_ERR_ARG, "null layer weight pointer");
-    k_copy_rows<<<256, 256, 0, st>>>((const bf16*)w.q_proj, s.wqkv[l], qn);
-    k_copy_rows<<<256, 256, 0, st>>>((const bf16*)w.k_proj, s.wqkv[l] + qn * 8, kn);
-    k_copy_rows<<<256, 256, 0, st>>>((const bf16*)w.v_proj, s.wqkv[l] + (qn + kn) * 8, kn);
-    k_interleave_rows<<<512, 256, 0, st>>>((const bf16*)w.w1, (const bf16*)w.w3, s.wgu[l], c.ff, (int)D8);
+    k_copy_rows<<<256, 256, 0, st>>>((const bf16*)w.q_proj, s.wqkv[l], qn); COUNT_LAUNCH();
+    k_copy_rows<<<256, 256, 0, st>>>((const bf16*)w.k_proj, s.wqkv[l] + qn * 8, kn); COUNT_LAUNCH();
+    k_copy_rows<<<256, 256, 0, st>>>((const bf16*)w.v_proj, s.wqkv[l] + (qn + kn) * 8, kn); COUNT_LAUNCH();
+    k_interleave_rows<<<512, 256, 0, st>>>((const bf16*)w.w1, (const bf16*)w.w3, s.wgu[l], c.ff, (int)D8); COUNT_LAUNCH();
     s.wo[l] = (const bf16*)w.output_proj; s.wd[l] = (const bf16*)w.w2;
     s.sa[l] = (const bf16*)w.sa_norm; s.mlp[l] = (const bf16*)w.mlp_norm;
   }
@@ -338,7 +346,7 @@ extern "C" int32_t csm_create(const csm_config* cfg, const csm_weights* w, int32
   {
     const int K = cfg->decoder.dim, V = cfg->audio_vocab;
     dim3 grid((x->Vp + 31) / 32, (K + 31) / 32, cfg->codebooks - 1), block(32, 8);
-    k_transpose_heads<<<grid, block, 0, st>>>((const bf16*)w->audio_head, x->head_t, K, V, x->Vp);
+    k_transpose_heads<<<grid, block, 0, st>>>((const bf16*)w->audio_head, x->head_t, K, V, x->Vp); COUNT_LAUNCH();
   }
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&x->cap_stream, cudaStreamNonBlocking);
@@ -373,10 +381,13 @@ static int get_graph(csm_ctx* x, int B, cudaGraphExec_t* out) {
     return CSM_OK;
   }
   cudaGraph_t g = nullptr;
+  const unsigned long long before = g_launches;
   CU_TRY(cudaStreamBeginCapture(x->cap_stream, cudaStreamCaptureModeThreadLocal));
   cudaError_t e = backbone_pass(x, B, 1, x->cap_stream);
   if (e == cudaSuccess) e = frame_tail(x, B, x->cap_stream);
   cudaError_t e2 = cudaStreamEndCapture(x->cap_stream, &g);
+  x->graph_nodes[B] = g_launches - before;  // captured, not executed
+  g_launches = before;
   if (e != cudaSuccess || e2 != cudaSuccess) {
     if (g) cudaGraphDestroy(g);
     return set_err(CSM_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
@@ -413,13 +424,13 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
   for (int s0 = 0; s0 < S - 1; s0 += PREFILL_CHUNK) {
     const int chunk = (S - 1 - s0) < PREFILL_CHUNK ? (S - 1 - s0) : PREFILL_CHUNK;
     p.s0 = s0;
-    k_set_params<<<1, 1, 0, st>>>(x->d_params, p);
+    k_set_params<<<1, 1, 0, st>>>(x->d_params, p); COUNT_LAUNCH();
     CU_TRY(cudaGetLastError());
     CU_TRY(backbone_pass(x, B, chunk, st));
   }
   // last row + frame tail: the captured decode graph
   p.s0 = S - 1;
-  k_set_params<<<1, 1, 0, st>>>(x->d_params, p);
+  k_set_params<<<1, 1, 0, st>>>(x->d_params, p); COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
   if (no_graph) {
     CU_TRY(backbone_pass(x, B, 1, st));
@@ -429,6 +440,7 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
     int rc = get_graph(x, B, &ge);
     if (rc != CSM_OK) return rc;
     CU_TRY(cudaGraphLaunch(ge, st));
+    g_launches += x->graph_nodes[B];
   }
   x->cache_len += S;
   return CSM_OK;
@@ -439,7 +451,7 @@ extern "C" int32_t csm_k_sample_topk(const void* logits, const void* noise, int3
                                      int32_t topk, int32_t* out, void* stream) {
   if (!logits || !out || B < 1 || V < 1 || V > SAMPLE_MAXV) return set_err(CSM_ERR_ARG, "bad sample_topk arguments");
   k_sample_only<<<B, SAMPLE_THREADS, 0, (cudaStream_t)stream>>>((const bf16*)logits, (const bf16*)noise, V, temperature,
-                                                                topk, out);
+                                                                topk, out); COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
   return CSM_OK;
 }
@@ -449,7 +461,7 @@ extern "C" int32_t csm_k_embed_frames(const int64_t* tokens, const uint8_t* mask
                                       void* out, void* stream) {
   if (!tokens || !mask || !text_emb || !audio_emb || !out || N < 1 || D % 8) return set_err(CSM_ERR_ARG, "bad embed arguments");
   k_embed_frames<<<N, 256, 0, (cudaStream_t)stream>>>(tokens, mask, (const bf16*)text_emb, (const bf16*)audio_emb,
-                                                      codebooks, audio_vocab, D, (bf16*)out);
+                                                      codebooks, audio_vocab, D, (bf16*)out); COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
   return CSM_OK;
 }
@@ -469,7 +481,7 @@ extern "C" int32_t csm_k_linear(const void* xin, const void* W, int32_t N, int32
 extern "C" int32_t csm_k_rmsnorm(const void* xin, const void* scale, int32_t N, int32_t D, float eps, void* y,
                                  void* stream) {
   if (!xin || !scale || !y || N < 1 || D < 1) return set_err(CSM_ERR_ARG, "bad rmsnorm arguments");
-  k_rmsnorm<<<N, 256, 0, (cudaStream_t)stream>>>((const bf16*)xin, D, (const bf16*)scale, D, eps, (bf16*)y, D);
+  k_rmsnorm<<<N, 256, 0, (cudaStream_t)stream>>>((const bf16*)xin, D, (const bf16*)scale, D, eps, (bf16*)y, D); COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
   return CSM_OK;
 }

@@ -356,12 +356,15 @@ __device__ int sample_row(const bf16* __restrict__ logits, const bf16* __restric
                           int topk, unsigned long long seed, unsigned long long ctr0, float* xs /*[V]*/,
                           unsigned int* hist /*[256]*/, float* scratch /*[33]*/, int* iscratch /*[34]*/) {
   const int tid = threadIdx.x;
-  // 1. temperature (IEEE division, rounded to bf16) + radix histogram of the high key byte
+  // 1. temperature + radix histogram of the high key byte.  ``logits / temperature`` with a
+  //    Python-float divisor is evaluated by torch's CUDA div kernel as x * (1/T) in fp32
+  //    (the reference path on a GPU), then rounded to bf16.
   for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
   __syncthreads();
   float mx = -INFINITY;
+  const float inv_t = 1.0f / temperature;
   for (int i = tid; i < V; i += blockDim.x) {
-    const bf16 xb = f2bf(bf2f(logits[i]) / temperature);
+    const bf16 xb = f2bf(bf2f(logits[i]) * inv_t);
     xs[i] = bf2f(xb);
     atomicAdd(&hist[bf_key(xb) >> 8], 1u);
   }

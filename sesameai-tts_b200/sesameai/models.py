@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import weakref
 from dataclasses import dataclass
 from typing import Dict, Optional
 
@@ -130,10 +131,14 @@ class TransformerStack(nn.Module):
         self.max_seq_len = spec.max_seq_len
         self.num_heads = spec.num_heads
         self.head_dim = spec.head_dim
-        self._owner: Optional["Model"] = None
+        # weak back-reference kept out of nn.Module's attribute machinery (a plain attribute
+        # would register the owning Model as a sub-module and create a cycle)
+        self.__dict__["_owner_ref"] = None
 
     def caches_are_enabled(self) -> bool:
-        return self._owner is not None and self._owner._ctx is not None
+        ref = self.__dict__.get("_owner_ref")
+        owner = ref() if ref is not None else None
+        return owner is not None and owner._ctx is not None
 
     def forward(self, *a, **k):
         raise RuntimeError("sesameai(B200): the transformer runs inside libcsm_b200; use Model.generate_frame")
@@ -247,8 +252,8 @@ class Model(
         tri = lambda n: torch.tril(torch.ones(n, n, dtype=torch.bool, device=dev))  # noqa: E731
         self.register_buffer("backbone_causal_mask", tri(self.backbone.max_seq_len))
         self.register_buffer("decoder_causal_mask", tri(self.config.audio_num_codebooks))
-        self.backbone._owner = self
-        self.decoder._owner = self
+        self.backbone.__dict__["_owner_ref"] = weakref.ref(self)
+        self.decoder.__dict__["_owner_ref"] = weakref.ref(self)
 
     def reset_caches(self) -> None:
         if self._ctx is None:

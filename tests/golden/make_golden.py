@@ -38,6 +38,7 @@ def load_reference_models():
     spec = importlib.util.spec_from_file_location("_reference_sesameai_models", "/root/reference/sesameai/models.py")
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
+    orc.ARCH.update(syn.named_tiny_flavors())
     for name, dims in syn.named_tiny_flavors().items():
         mod.FLAVORS[name] = (lambda d=dims: tt.llama3_2(vocab_size=128_256, max_seq_len=2048, attn_dropout=0.0,
                                                           norm_eps=1e-5, rope_base=500_000, scale_factor=32, **d))
@@ -138,9 +139,29 @@ def teacher_case(mod, flavor, text_vocab, batch, prompt_frames, n_frames, temper
         mod.sample_topk = orig
     frames = torch.stack(frames)
     logits = torch.stack(rec).view(n_frames, 32, batch, 2051)
+    # "truth": the same bf16 parameter values evaluated in fp32 arithmetic, teacher-forced with the
+    # reference's tokens (oracle restatement, validated against the reference in bf16 above)
+    om = orc.OracleCSM(orc.OracleArgs(**args))
+    om.load_state_dict({k: v.float() for k, v in m.state_dict().items() if not k.endswith("causal_mask")})
+    om.setup_caches(batch)
+    om.reset_caches()
+    t32, m32, p32 = tok, msk, pos
+    truth = []
+    for f in range(n_frames):
+        r = {}
+        s = om.generate_frame(t32, m32, p32, temperature, topk, noise=noise[32 * f: 32 * f + 32].float(),
+                              forced=frames[f], record=r)
+        truth.append(torch.stack(r["logits"]))
+        t32 = torch.cat([s.long(), torch.zeros(batch, 1).long()], dim=1).unsqueeze(1)
+        m32 = torch.cat([torch.ones_like(s).bool(), torch.zeros(batch, 1).bool()], dim=1).unsqueeze(1)
+        p32 = p32[:, -1:] + 1
+    truth = torch.stack(truth)
+    ref_rms = (logits.float() - truth).pow(2).mean().sqrt().item()
     torch.save(dict(model_args=args, weight_seed=WEIGHT_SEED, input_seed=INPUT_SEED, noise_seed=NOISE_SEED,
                     planted=False, batch=batch, prompt_frames=prompt_frames, temperature=temperature, topk=topk,
-                    frames=frames.to(torch.int32), logits=logits), out_path)
+                    frames=frames.to(torch.int32), logits=logits, logits_fp32=truth.to(torch.float32),
+                    ref_rms_vs_fp32=ref_rms), out_path)
+    print(f"  bf16 reference vs fp32 arithmetic: rms {ref_rms:.5f}, max {(logits.float() - truth).abs().max():.5f}")
     print(f"{out_path}: {n_frames} frames, {time.time() - t0:.1f}s")
 
 
@@ -170,7 +191,9 @@ def main():
     what = sys.argv[1] if len(sys.argv) > 1 else "tiny"
     mod = load_reference_models()
     torch.manual_seed(0)
-    if what == "tiny":
+    if what == "teacher":
+        teacher_case(mod, ("llama-1B", "llama-100M"), 128_256, 1, 24, 3, 0.9, 50, os.path.join(HERE, "csm1b_teacher.pt"))
+    elif what == "tiny":
         sample_cases(mod, os.path.join(HERE, "sample_topk_cases.pt"))
         greedy_case(mod, ("tiny-bb", "tiny-dec"), 1000, 2, 7, 12, os.path.join(HERE, "tiny_greedy.pt"))
         teacher_case(mod, ("tiny-bb", "tiny-dec"), 1000, 2, 7, 4, 0.8, 40, os.path.join(HERE, "tiny_teacher.pt"))
