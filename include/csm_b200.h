@@ -112,8 +112,15 @@ typedef struct csm_frame_opts {
   const int32_t *forced;  /* dev [B, codebooks] teacher-forced tokens, or NULL                             */
   void *logits_out;       /* dev bf16 [codebooks, B, audio_vocab] raw head outputs, or NULL                */
   int32_t *sampled_out;   /* dev [B, codebooks] sampled tokens before forcing, or NULL                     */
-  int32_t no_graph;       /* 1 = launch kernels directly instead of replaying the captured CUDA graph      */
+  int32_t path;           /* CSM_PATH_*: which launch strategy runs the last prompt row + frame tail          */
 } csm_frame_opts;
+
+enum {
+  CSM_PATH_AUTO = 0,   /* batch 1: persistent megakernel; otherwise the captured per-op CUDA graph */
+  CSM_PATH_DIRECT = 1, /* per-op kernels launched one by one (debugging / graph-free)              */
+  CSM_PATH_GRAPH = 2,  /* per-op kernels replayed from one CUDA graph per frame                    */
+  CSM_PATH_MEGA = 3    /* one persistent kernel per frame (batch 1 only)                           */
+};
 
 /* Replaces Model.generate_frame(tokens, tokens_mask, input_pos, temperature, topk)
  * (sesameai/models.py:132-184): embeds S frames per stream, appends S positions to the backbone

@@ -9,6 +9,7 @@
 
 #include "../../include/csm_b200.h"
 #include "lm_kernels.cuh"
+#include "mega.cuh"
 
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -60,6 +61,11 @@ struct csm_ctx {
   int cache_len;
   bool enabled;
   cudaStream_t cap_stream;
+  // persistent decode megakernel (batch 1)
+  mega::Phase* d_phases;
+  mega::Sync* d_sync;
+  int n_phases, mega_grid;
+  bool mega_ok;
   std::map<int, cudaGraphExec_t> graphs;  // keyed by B
   std::map<int, unsigned long long> graph_nodes;
 };
@@ -85,6 +91,10 @@ static bool valid_stack(const csm_stack_config& s) {
 static bool valid_cfg(const csm_config* c) {
   return c && valid_stack(c->backbone) && valid_stack(c->decoder) && c->codebooks >= 2 && c->codebooks <= 64 &&
          c->audio_vocab >= 2 && c->audio_vocab <= SAMPLE_MAXV && c->text_vocab >= 1 && c->max_seq_len >= c->codebooks;
+}
+
+static int mega_phase_count(const csm_config& c) {
+  return 1 + c.backbone.layers * 5 + 2 + (c.codebooks - 1) * (1 + c.decoder.layers * 4 + 2);
 }
 
 static void carve_stack(Carver& cv, StackDev& s, const csm_stack_config& c, int slots, int streams, int rows) {
@@ -121,6 +131,8 @@ static size_t carve_all(csm_ctx* x, char* base) {
   x->row_pos = cv.take<int>(x->max_rows);
   x->row_slot = cv.take<int>(x->max_rows);
   x->d_params = cv.take<FrameParams>(1);
+  x->d_sync = cv.take<mega::Sync>(1);
+  x->d_phases = cv.take<mega::Phase>(mega_phase_count(c));
   return (cv.off + 255) & ~(size_t)255;
 }
 
@@ -286,6 +298,115 @@ static cudaError_t frame_tail(csm_ctx* x, int B, cudaStream_t st) {
   return cudaSuccess;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Megakernel phase table for one batch-1 decode frame (mega.cuh).
+static mega::Phase gemv_phase_desc(const bf16* W, int rows, int K, const bf16* xin, int ldx, int nb, int epi,
+                                   const bf16* norm_scale, float eps, bf16* out, int ldo) {
+  mega::Phase ph;
+  memset(&ph, 0, sizeof(ph));
+  ph.type = mega::PH_GEMV; ph.epi = epi; ph.norm = norm_scale != nullptr; ph.nb = nb;
+  ph.W = W; ph.rows = rows; ph.K = K;
+  ph.KC = K < 2048 ? K : 2048;
+  ph.R = mega::CHUNK_ELEMS / ph.KC;
+  ph.G = (rows + ph.R - 1) / ph.R;
+  ph.x = xin; ph.ldx = ldx; ph.norm_scale = norm_scale; ph.eps = eps; ph.out = out; ph.ldo = ldo; ph.resid = out;
+  return ph;
+}
+
+static void stack_phases(csm_ctx* x, StackDev& s, int l, int nb, int pos_mode, int pos0, bool fused_attn,
+                         std::vector<mega::Phase>& v) {
+  const csm_stack_config& c = s.c;
+  const float eps = x->cfg.norm_eps;
+  bf16* kc = s.kc + s.kv_layer_stride * l;
+  bf16* vc = s.vc + s.kv_layer_stride * l;
+  auto with_attn = [&](mega::Phase ph) {
+    ph.q = s.q; ph.kc = kc; ph.vc = vc; ph.rope = s.rope; ph.heads = c.heads; ph.kv_heads = c.kv_heads;
+    ph.hd = s.hd; ph.slots = s.slots; ph.pos_mode = pos_mode; ph.pos0 = pos0;
+    return ph;
+  };
+  v.push_back(with_attn(gemv_phase_desc(s.wqkv[l], (c.heads + 2 * c.kv_heads) * s.hd, c.dim, s.h, c.dim, nb, EPI_ROPE_KV,
+                                        s.sa[l], eps, nullptr, 0)));
+  if (!fused_attn) {
+    mega::Phase a;
+    memset(&a, 0, sizeof(a));
+    a.type = mega::PH_ATTN; a.nb = nb; a.att_out = s.att;
+    v.push_back(with_attn(a));
+  }
+  mega::Phase o = with_attn(gemv_phase_desc(s.wo[l], c.dim, c.dim, s.att, c.dim, nb, EPI_RESID, nullptr, eps, s.h, c.dim));
+  o.attn_prologue = fused_attn ? 1 : 0;
+  v.push_back(o);
+  v.push_back(gemv_phase_desc(s.wgu[l], 2 * c.ff, c.dim, s.h, c.dim, nb, EPI_SWIGLU, s.mlp[l], eps, s.act, c.ff));
+  v.push_back(gemv_phase_desc(s.wd[l], c.dim, c.ff, s.act, c.ff, nb, EPI_RESID, nullptr, eps, s.h, c.dim));
+}
+
+static void build_mega_phases(csm_ctx* x, std::vector<mega::Phase>& v) {
+  const csm_config& c = x->cfg;
+  const int D = c.backbone.dim, Dd = c.decoder.dim, V = c.audio_vocab, C = c.codebooks;
+  const float eps = c.norm_eps;
+  auto sample = [&](int cb, bf16* next_in) {
+    mega::Phase s;
+    memset(&s, 0, sizeof(s));
+    s.type = mega::PH_SAMPLE; s.cb = cb; s.V = V; s.C = C; s.D = D; s.logits = x->logits; s.ldl = x->Vp;
+    s.next_in = next_in; s.audio_emb = x->audio_emb;
+    return s;
+  };
+  mega::Phase e;
+  memset(&e, 0, sizeof(e));
+  e.type = mega::PH_EMBED; e.V = V; e.C = C; e.D = D; e.audio_emb = x->audio_emb; e.text_emb = x->text_emb; e.h_out = x->bb.h;
+  v.push_back(e);
+  for (int l = 0; l < c.backbone.layers; ++l) stack_phases(x, x->bb, l, 1, mega::POS_BACKBONE, 0, false, v);
+  mega::Phase h0 = gemv_phase_desc(x->c0_head, V, D, x->bb.h, D, 1, EPI_PLAIN, x->bb.norm, eps, x->logits, x->Vp);
+  h0.x_copy_out = x->dec_in;  // last_h = backbone.norm(h): depth-decoder input row 0
+  v.push_back(h0);
+  v.push_back(sample(0, x->dec_in + D));
+  for (int i = 1; i < C; ++i) {
+    const int nb = (i == 1) ? 2 : 1, pos0 = (i == 1) ? 0 : i;
+    v.push_back(gemv_phase_desc(x->proj, Dd, D, x->dec_in, D, nb, EPI_PLAIN, nullptr, eps, x->dec.h, Dd));
+    for (int l = 0; l < c.decoder.layers; ++l) stack_phases(x, x->dec, l, nb, mega::POS_FIXED, pos0, true, v);
+    v.push_back(gemv_phase_desc(x->head_t + (size_t)(i - 1) * x->Vp * Dd, V, Dd, x->dec.h + (size_t)(nb - 1) * Dd, Dd, 1,
+                                EPI_PLAIN, x->dec.norm, eps, x->logits, x->Vp));
+    v.push_back(sample(i, (i + 1 < C) ? x->dec_in : nullptr));
+  }
+}
+
+static int setup_mega(csm_ctx* x, cudaStream_t st) {
+  x->mega_ok = false;
+  // fused small attention needs <= 32 cached keys; scores of the backbone attention sit in the 32 KB x buffer
+  if (x->cfg.codebooks > 32 || x->cfg.max_seq_len * 4 + (mega::NCT + 128) * 4 > (int)mega::SMEM_X) return CSM_OK;
+  int dev = 0, sms = 0, coop = 0, occ = 0;
+  CU_TRY(cudaGetDevice(&dev));
+  CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CU_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  CU_TRY(cudaFuncSetAttribute(mega::k_frame_mega, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega::SMEM_BYTES));
+  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mega::k_frame_mega, mega::NTHREADS, mega::SMEM_BYTES));
+  if (!coop || occ < 1) return CSM_OK;
+  std::vector<mega::Phase> v;
+  build_mega_phases(x, v);
+  if ((int)v.size() != mega_phase_count(x->cfg)) return set_err(CSM_ERR_ARG, "internal: phase count mismatch");
+  CU_TRY(cudaMemcpyAsync(x->d_phases, v.data(), v.size() * sizeof(mega::Phase), cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemsetAsync(x->d_sync, 0, sizeof(mega::Sync), st));
+  CU_TRY(cudaStreamSynchronize(st));  // v is host stack memory
+  x->n_phases = (int)v.size();
+  x->mega_grid = sms;
+  x->mega_ok = true;
+  return CSM_OK;
+}
+
+static int launch_mega(csm_ctx* x, const FrameParams& p, cudaStream_t st) {
+  mega::k_mega_prepare<<<1, 1, 0, st>>>(x->d_params, p, x->d_sync); COUNT_LAUNCH();
+  CU_TRY(cudaGetLastError());
+  const mega::Phase* ph = x->d_phases;
+  int n = x->n_phases;
+  const FrameParams* dp = x->d_params;
+  mega::Sync* sy = x->d_sync;
+  void* args[] = {(void*)&ph, (void*)&n, (void*)&dp, (void*)&sy};
+  CU_TRY(cudaLaunchCooperativeKernel((const void*)mega::k_frame_mega, dim3(x->mega_grid), dim3(mega::NTHREADS), args,
+                                     mega::SMEM_BYTES, st));
+  COUNT_LAUNCH();
+  return CSM_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 static int pack_stack(StackDev& s, const csm_layer_weights* lw, cudaStream_t st) {
   const csm_stack_config& c = s.c;
@@ -356,6 +477,10 @@ extern "C" int32_t csm_create(const csm_config* cfg, const csm_weights* w, int32
   }
   x->cache_len = 0;
   x->enabled = true;
+  if ((rc = setup_mega(x, st)) != CSM_OK) {
+    csm_destroy(x);
+    return rc;
+  }
   *out = x;
   return CSM_OK;
 }
@@ -414,12 +539,14 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
   memset(&p, 0, sizeof(p));
   p.tokens = tokens; p.mask = tokens_mask; p.pos = input_pos; p.out = out;
   p.temperature = temperature; p.topk = topk; p.B = B; p.S = S; p.cache_len = x->cache_len;
-  bool no_graph = false;
+  int path = 0;
   if (opts) {
     p.noise = (const bf16*)opts->noise; p.forced = opts->forced; p.logits_out = (bf16*)opts->logits_out;
     p.sampled_out = opts->sampled_out; p.seed = opts->seed; p.offset = opts->offset;
-    no_graph = opts->no_graph != 0;
+    path = opts->path;
   }
+  if (path == CSM_PATH_AUTO) path = (B == 1 && x->mega_ok) ? CSM_PATH_MEGA : CSM_PATH_GRAPH;
+  if (path == CSM_PATH_MEGA && (B != 1 || !x->mega_ok)) return set_err(CSM_ERR_ARG, "megakernel path needs batch 1");
   // prompt rows [0, S-1): small-row passes of up to PREFILL_CHUNK frames per stream
   for (int s0 = 0; s0 < S - 1; s0 += PREFILL_CHUNK) {
     const int chunk = (S - 1 - s0) < PREFILL_CHUNK ? (S - 1 - s0) : PREFILL_CHUNK;
@@ -428,11 +555,17 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
     CU_TRY(cudaGetLastError());
     CU_TRY(backbone_pass(x, B, chunk, st));
   }
-  // last row + frame tail: the captured decode graph
+  // last row + frame tail: persistent megakernel (batch 1) or the captured per-op graph
   p.s0 = S - 1;
+  if (path == CSM_PATH_MEGA) {
+    int rc = launch_mega(x, p, st);
+    if (rc != CSM_OK) return rc;
+    x->cache_len += S;
+    return CSM_OK;
+  }
   k_set_params<<<1, 1, 0, st>>>(x->d_params, p); COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
-  if (no_graph) {
+  if (path == CSM_PATH_DIRECT) {
     CU_TRY(backbone_pass(x, B, 1, st));
     CU_TRY(frame_tail(x, B, st));
   } else {

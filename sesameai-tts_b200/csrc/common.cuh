@@ -37,23 +37,35 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// block-wide reductions through a caller-provided 33-float smem scratch; all threads get the result
-__device__ __forceinline__ float block_sum(float v, float* scratch) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+// Barrier among the first NT threads of the CTA on hardware barrier BAR (BAR 0 with NT ==
+// blockDim.x is __syncthreads()).  Warp-specialised kernels sync their consumer warps on BAR 1.
+template <int NT, int BAR>
+__device__ __forceinline__ void csync() {
+  asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NT) : "memory");
+}
+
+// reductions over NT threads (tid in [0, NT)) through a caller-provided 33-float smem scratch;
+// every participating thread gets the result
+template <int NT, int BAR>
+__device__ __forceinline__ float block_sum(float v, float* scratch, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int nw = NT / 32;
   v = warp_sum(v);
-  __syncthreads();
+  csync<NT, BAR>();
   if (lane == 0) scratch[warp] = v;
-  __syncthreads();
+  csync<NT, BAR>();
   float t = (lane < nw) ? scratch[lane] : 0.f;
   t = warp_sum(t);
   return t;
 }
-__device__ __forceinline__ float block_max(float v, float* scratch) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+template <int NT, int BAR>
+__device__ __forceinline__ float block_max(float v, float* scratch, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int nw = NT / 32;
   v = warp_max(v);
-  __syncthreads();
+  csync<NT, BAR>();
   if (lane == 0) scratch[warp] = v;
-  __syncthreads();
+  csync<NT, BAR>();
   float t = (lane < nw) ? scratch[lane] : -INFINITY;
   t = warp_max(t);
   return t;

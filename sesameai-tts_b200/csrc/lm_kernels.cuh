@@ -80,22 +80,22 @@ __global__ void k_embed_pass(const FrameParams* __restrict__ P, const bf16* text
 // torchtune RMSNorm (Appendix A.3) on NB rows already resident in smem as raw bf16:
 // xn = bf16( bf16(x * rsqrt(mean(x^2)+eps)) * scale ), written back in place.
 // ---------------------------------------------------------------------------------------------
-template <int NB>
+template <int NB, int NT, int BAR>
 __device__ __forceinline__ void rmsnorm_smem(bf16* xs, int K, const bf16* __restrict__ scale, float eps,
-                                             float* scratch) {
+                                             float* scratch, int tid) {
   float inv[NB];
 #pragma unroll
   for (int nb = 0; nb < NB; ++nb) {
     float ss = 0.f;
-    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    for (int k = tid; k < K; k += NT) {
       float v = bf2f(xs[nb * K + k]);
       ss = fmaf(v, v, ss);
     }
-    ss = block_sum(ss, scratch);
+    ss = block_sum<NT, BAR>(ss, scratch, tid);
     inv[nb] = 1.0f / sqrtf(ss / (float)K + eps);
   }
-  __syncthreads();
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+  csync<NT, BAR>();
+  for (int k = tid; k < K; k += NT) {
     const float sc = bf2f(scale[k]);
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
@@ -103,7 +103,7 @@ __device__ __forceinline__ void rmsnorm_smem(bf16* xs, int K, const bf16* __rest
       xs[nb * K + k] = f2bf(v * sc);
     }
   }
-  __syncthreads();
+  csync<NT, BAR>();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -137,7 +137,7 @@ struct GemvArgs {
 };
 
 template <int NB, int EPI, bool NORM>
-__global__ void __launch_bounds__(512) k_gemv(GemvArgs a) {
+__global__ void __launch_bounds__(256) k_gemv(GemvArgs a) {  // launched with exactly 256 threads
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* xs = reinterpret_cast<bf16*>(smem_raw);
   __shared__ float scratch[33];
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(512) k_gemv(GemvArgs a) {
     *reinterpret_cast<uint4*>(xs + nb * K + k8 * 8) = v;
   }
   __syncthreads();
-  if (NORM) rmsnorm_smem<NB>(xs, K, a.norm_scale, a.eps, scratch);
+  if (NORM) rmsnorm_smem<NB, 256, 0>(xs, K, a.norm_scale, a.eps, scratch, threadIdx.x);
 
   const int lane = threadIdx.x & 31;
   const int warps_per_cta = blockDim.x >> 5;
@@ -276,14 +276,14 @@ __global__ void __launch_bounds__(128) k_attn_rows(const bf16* __restrict__ q, c
     sc[j] = s;
     mx = fmaxf(mx, s);
   }
-  mx = block_max(mx, scratch);
+  mx = block_max<128, 0>(mx, scratch, threadIdx.x);
   float sum = 0.f;
   for (int j = threadIdx.x; j < nkeys; j += blockDim.x) {
     const float e = expf(sc[j] - mx);
     sc[j] = e;
     sum += e;
   }
-  sum = block_sum(sum, scratch);  // (contains the __syncthreads that publishes sc[])
+  sum = block_sum<128, 0>(sum, scratch, threadIdx.x);  // (its barrier also publishes sc[])
   const float inv = 1.0f / sum;
 
   // P.V : thread -> (key group g, dim d); groups stride over keys
@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(256) k_rmsnorm(const bf16* __restrict__ x, int
     const float v = bf2f(xr[k]);
     ss = fmaf(v, v, ss);
   }
-  ss = block_sum(ss, scratch);
+  ss = block_sum<256, 0>(ss, scratch, threadIdx.x);
   const float inv = 1.0f / sqrtf(ss / (float)D + eps);
   for (int k = threadIdx.x; k < D; k += blockDim.x)
     y[(size_t)n * ldy + k] = f2bf(rbf(bf2f(xr[k]) * inv) * bf2f(scale[k]));
@@ -352,23 +352,24 @@ __device__ __forceinline__ float exp1_draw(unsigned long long seed, unsigned lon
 #define SAMPLE_MAXV 4096
 
 // Core: returns the sampled token for one logits row (all threads return the same value).
+template <int NT, int BAR, bool CG>
 __device__ int sample_row(const bf16* __restrict__ logits, const bf16* __restrict__ noise, int V, float temperature,
                           int topk, unsigned long long seed, unsigned long long ctr0, float* xs /*[V]*/,
-                          unsigned int* hist /*[256]*/, float* scratch /*[33]*/, int* iscratch /*[34]*/) {
-  const int tid = threadIdx.x;
+                          unsigned int* hist /*[256]*/, float* scratch /*[33]*/, int* iscratch /*[36]*/, int tid) {
   // 1. temperature + radix histogram of the high key byte.  ``logits / temperature`` with a
   //    Python-float divisor is evaluated by torch's CUDA div kernel as x * (1/T) in fp32
   //    (the reference path on a GPU), then rounded to bf16.
-  for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
-  __syncthreads();
+  for (int i = tid; i < 256; i += NT) hist[i] = 0;
+  csync<NT, BAR>();
   float mx = -INFINITY;
   const float inv_t = 1.0f / temperature;
-  for (int i = tid; i < V; i += blockDim.x) {
-    const bf16 xb = f2bf(bf2f(logits[i]) * inv_t);
+  for (int i = tid; i < V; i += NT) {
+    const bf16 lg = CG ? __ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(logits) + i)) : logits[i];
+    const bf16 xb = f2bf(bf2f(lg) * inv_t);
     xs[i] = bf2f(xb);
     atomicAdd(&hist[bf_key(xb) >> 8], 1u);
   }
-  __syncthreads();
+  csync<NT, BAR>();
   // 2. k-th largest: walk the high-byte histogram from the top, then the low byte inside that bin
   int k = topk < 1 ? 1 : (topk > V ? V : topk);
   if (tid == 0) {
@@ -380,17 +381,17 @@ __device__ int sample_row(const bf16* __restrict__ logits, const bf16* __restric
     iscratch[0] = b;
     iscratch[1] = k - cum;  // rank inside the bin
   }
-  __syncthreads();
+  csync<NT, BAR>();
   const int hb = iscratch[0];
   const int krem = iscratch[1];
-  __syncthreads();
-  for (int i = tid; i < 256; i += blockDim.x) hist[i] = 0;
-  __syncthreads();
-  for (int i = tid; i < V; i += blockDim.x) {
+  csync<NT, BAR>();
+  for (int i = tid; i < 256; i += NT) hist[i] = 0;
+  csync<NT, BAR>();
+  for (int i = tid; i < V; i += NT) {
     const uint32_t key = bf_key(f2bf(xs[i]));
     if ((int)(key >> 8) == hb) atomicAdd(&hist[key & 0xffu], 1u);
   }
-  __syncthreads();
+  csync<NT, BAR>();
   if (tid == 0) {
     int cum = 0, b = 255;
     for (; b > 0; --b) {
@@ -399,35 +400,35 @@ __device__ int sample_row(const bf16* __restrict__ logits, const bf16* __restric
     }
     iscratch[2] = b;
   }
-  __syncthreads();
+  csync<NT, BAR>();
   const float thr = key_to_float(((uint32_t)hb << 8) | (uint32_t)iscratch[2]);
   // 3. mask + log_softmax (fp32 internals, bf16 result)
-  for (int i = tid; i < V; i += blockDim.x) {
+  for (int i = tid; i < V; i += NT) {
     float v = xs[i];
     if (v < thr) v = -INFINITY;
     xs[i] = v;
     mx = fmaxf(mx, v);
   }
-  mx = block_max(mx, scratch);
+  mx = block_max<NT, BAR>(mx, scratch, tid);
   float sum = 0.f;
-  for (int i = tid; i < V; i += blockDim.x) sum += expf(xs[i] - mx);
-  sum = block_sum(sum, scratch);
+  for (int i = tid; i < V; i += NT) sum += expf(xs[i] - mx);
+  sum = block_sum<NT, BAR>(sum, scratch, tid);
   const float lse = logf(sum);
   float mx2 = -INFINITY;
-  for (int i = tid; i < V; i += blockDim.x) {
+  for (int i = tid; i < V; i += NT) {
     const float ls = rbf((xs[i] - mx) - lse);
     xs[i] = ls;
     mx2 = fmaxf(mx2, ls);
   }
-  mx2 = block_max(mx2, scratch);
+  mx2 = block_max<NT, BAR>(mx2, scratch, tid);
   // 4. softmax of the bf16 log-probs
   float sum2 = 0.f;
-  for (int i = tid; i < V; i += blockDim.x) sum2 += expf(xs[i] - mx2);
-  sum2 = block_sum(sum2, scratch);
+  for (int i = tid; i < V; i += NT) sum2 += expf(xs[i] - mx2);
+  sum2 = block_sum<NT, BAR>(sum2, scratch, tid);
   // 5. exponential race, first-index argmax
   float best = -INFINITY;
   int besti = 0x7fffffff;
-  for (int i = tid; i < V; i += blockDim.x) {
+  for (int i = tid; i < V; i += NT) {
     const float p = rbf(expf(xs[i] - mx2) / sum2);
     const float q = noise ? bf2f(noise[i]) : exp1_draw(seed, ctr0 + i);
     const float r = rbf(p / q);
@@ -446,14 +447,14 @@ __device__ int sample_row(const bf16* __restrict__ logits, const bf16* __restric
       besti = oi;
     }
   }
-  __syncthreads();
+  csync<NT, BAR>();
   if ((tid & 31) == 0) {
     scratch[tid >> 5] = best;
     iscratch[2 + (tid >> 5)] = besti;
   }
-  __syncthreads();
+  csync<NT, BAR>();
   if (tid < 32) {
-    const int nw = (blockDim.x + 31) >> 5;
+    constexpr int nw = NT / 32;
     best = tid < nw ? scratch[tid] : -INFINITY;
     besti = tid < nw ? iscratch[2 + tid] : 0x7fffffff;
 #pragma unroll
@@ -467,9 +468,9 @@ __device__ int sample_row(const bf16* __restrict__ logits, const bf16* __restric
     }
     if (tid == 0) iscratch[0] = besti;
   }
-  __syncthreads();
+  csync<NT, BAR>();
   const int tok = iscratch[0];
-  __syncthreads();
+  csync<NT, BAR>();
   return tok;
 }
 
@@ -480,8 +481,8 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample_only(const bf16* logi
   __shared__ float scratch[33];
   __shared__ int iscratch[36];
   const int b = blockIdx.x;
-  const int tok = sample_row(logits + (size_t)b * V, noise ? noise + (size_t)b * V : nullptr, V, temperature, topk, 0,
-                             0, xs, hist, scratch, iscratch);
+  const int tok = sample_row<SAMPLE_THREADS, 0, false>(logits + (size_t)b * V, noise ? noise + (size_t)b * V : nullptr, V,
+                                                      temperature, topk, 0, 0, xs, hist, scratch, iscratch, threadIdx.x);
   if (threadIdx.x == 0) out[b] = tok;
 }
 
@@ -503,7 +504,8 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample_step(const FrameParam
   }
   const bf16* nz = P->noise ? P->noise + ((size_t)cb * B + b) * V : nullptr;
   const unsigned long long ctr = ((P->offset * (unsigned long long)C + cb) * (unsigned long long)B + b) * 4096ull;
-  int tok = sample_row(lrow, nz, V, P->temperature, P->topk, P->seed, ctr, xs, hist, scratch, iscratch);
+  int tok = sample_row<SAMPLE_THREADS, 0, false>(lrow, nz, V, P->temperature, P->topk, P->seed, ctr, xs, hist, scratch,
+                                                 iscratch, threadIdx.x);
   if (threadIdx.x == 0 && P->sampled_out) P->sampled_out[(size_t)b * C + cb] = tok;
   if (P->forced) tok = P->forced[(size_t)b * C + cb];
   if (threadIdx.x == 0) P->out[(size_t)b * C + cb] = tok;

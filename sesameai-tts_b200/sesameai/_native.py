@@ -12,6 +12,7 @@ from typing import Optional
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libcsm_b200.so")
 
+PATH_AUTO, PATH_DIRECT, PATH_GRAPH, PATH_MEGA = 0, 1, 2, 3
 CSM_OK, CSM_ERR_ARG, CSM_ERR_CUDA, CSM_ERR_STATE, CSM_ERR_OVERFLOW, CSM_ERR_WORKSPACE = 0, -1, -2, -3, -4, -5
 
 
@@ -62,7 +63,7 @@ class FrameOpts(C.Structure):
         ("forced", C.c_void_p),
         ("logits_out", C.c_void_p),
         ("sampled_out", C.c_void_p),
-        ("no_graph", C.c_int32),
+        ("path", C.c_int32),
     ]
 
 

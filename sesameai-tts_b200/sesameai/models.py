@@ -264,7 +264,8 @@ class Model(
     def generate_frame(self, tokens: torch.Tensor, tokens_mask: torch.Tensor, input_pos: torch.Tensor,
                        temperature: float, topk: int, *, noise: Optional[torch.Tensor] = None,
                        forced: Optional[torch.Tensor] = None, logits_out: Optional[torch.Tensor] = None,
-                       sampled_out: Optional[torch.Tensor] = None, no_graph: bool = False) -> torch.Tensor:
+                       sampled_out: Optional[torch.Tensor] = None, no_graph: bool = False,
+                       path: int = 0) -> torch.Tensor:
         """(B, S, 33) tokens/mask + (B, S) positions -> (B, 32) int32 codes, like the reference
         (``models.py:132-184``).  Keyword extras are for parity tests: shared Exp(1) ``noise``
         [32, B, V] bf16, teacher-``forced`` tokens [B, 32] int32, raw ``logits_out`` [32, B, V]."""
@@ -300,7 +301,7 @@ class Model(
         if sampled_out is not None:
             assert sampled_out.is_contiguous() and sampled_out.dtype == torch.int32
             opts.sampled_out = sampled_out.data_ptr()
-        opts.no_graph = 1 if no_graph else 0
+        opts.path = _native.PATH_DIRECT if no_graph else int(path)
         self._frame_counter += 1
         with torch.cuda.device(dev):
             rc = _native.lib().csm_generate_frame(

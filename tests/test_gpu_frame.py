@@ -137,3 +137,29 @@ def test_csm1b_teacher_forced_logits():
     assert worst[1] <= LOGIT_ATOL and worst[0] <= LOGIT_ATOL_MAX, worst
     assert cos_min >= COS_MIN, cos_min
     assert rms_truth <= 1.25 * gold["ref_rms_vs_fp32"], (rms_truth, gold["ref_rms_vs_fp32"])
+
+
+def test_megakernel_matches_per_op_path_tiny():
+    """Batch-1 decode: the persistent megakernel (default) and the per-op kernel chain produce the
+    same planted-greedy frames, and logits within bf16 noise of each other and of the oracle."""
+    from sesameai import _native
+
+    gold = load_golden("tiny_greedy.pt")
+    gold = dict(gold, batch=1)
+    pm, _ = build_product(gold, batch=1)
+    om, _ = build_oracle(gold, batch=1)
+    tok, msk, pos = syn.text_prompt(1, 9, 99, 1000)
+    noise = syn.exp_noise(32 * 6, 1, 2051, 3)
+    with torch.inference_mode():
+        want = orc.oracle_frame_loop(
+            om, tok, msk, pos, 6, 1.0, 1,
+            frame_fn=lambda i, t, m, p: om.generate_frame(t, m, p, 1.0, 1, noise=noise[32 * i: 32 * i + 32]))
+    for path in (_native.PATH_MEGA, _native.PATH_GRAPH, _native.PATH_DIRECT):
+        t, m, p = tok.cuda(), msk.cuda(), pos.cuda()
+        pm.reset_caches()
+        for i in range(6):
+            lg = torch.zeros(32, 1, 2051, dtype=torch.bfloat16, device="cuda")
+            s = pm.generate_frame(t, m, p, 1.0, 1, noise=noise[32 * i: 32 * i + 32], path=path, logits_out=lg)
+            assert torch.equal(s.cpu(), want[i]), (path, i)
+            assert torch.isfinite(lg.float()).all()
+            t, m, p = next_inputs(s, p)
