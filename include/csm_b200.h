@@ -135,6 +135,12 @@ int32_t csm_generate_frame(csm_ctx *ctx, const int64_t *tokens, const uint8_t *t
                            const int64_t *input_pos, int32_t B, int32_t S, float temperature, int32_t topk,
                            const csm_frame_opts *opts, int32_t *out, void *stream);
 
+/* Profiling aid: dev uint64 [n_phases][8] buffer that CTA 0 of the decode megakernel fills with
+ * %globaltimer stamps (phase start, work done, CTA synced, grid barrier passed, 4 phase-specific
+ * marks); NULL disables.
+ * Returns the number of phases (0 if the megakernel is unavailable). */
+int32_t csm_debug_set_trace(csm_ctx *ctx, void *dev_buffer);
+
 /* ---- single-kernel entry points for unit parity tests (tests/ only) ------------------------ */
 
 /* sample_topk (sesameai/models.py:77-87) on logits bf16 [B, V] with noise bf16 [B, V] -> int32 [B]. */

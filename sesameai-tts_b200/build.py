@@ -29,6 +29,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("CSM_NVCC_EXTRA", "").split()
     cmd = [nvcc, *flags, *(["-Xptxas", "-v"] if verbose else []), *[os.path.join(CSRC, s) for s in SOURCES], "-o", OUT]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

@@ -66,6 +66,8 @@ struct csm_ctx {
   mega::Sync* d_sync;
   int n_phases, mega_grid;
   bool mega_ok;
+  unsigned long long* trace;  // optional device buffer [n_phases][8] (csm_debug_set_trace)
+  mega::PfTable pf_table;     // weight-prefetch schedule, passed in kernel-parameter space
   std::map<int, cudaGraphExec_t> graphs;  // keyed by B
   std::map<int, unsigned long long> graph_nodes;
 };
@@ -307,7 +309,7 @@ static mega::Phase gemv_phase_desc(const bf16* W, int rows, int K, const bf16* x
   memset(&ph, 0, sizeof(ph));
   ph.type = mega::PH_GEMV; ph.epi = epi; ph.norm = norm_scale != nullptr; ph.nb = nb;
   ph.W = W; ph.rows = rows; ph.K = K;
-  ph.KC = K < 2048 ? K : 2048;
+  ph.KC = K < mega::KC_MAX ? K : mega::KC_MAX;
   ph.R = mega::CHUNK_ELEMS / ph.KC;
   ph.G = (rows + ph.R - 1) / ph.R;
   ph.x = xin; ph.ldx = ldx; ph.norm_scale = norm_scale; ph.eps = eps; ph.out = out; ph.ldo = ldo; ph.resid = out;
@@ -372,18 +374,28 @@ static void build_mega_phases(csm_ctx* x, std::vector<mega::Phase>& v) {
 
 static int setup_mega(csm_ctx* x, cudaStream_t st) {
   x->mega_ok = false;
+  x->trace = nullptr;
   // fused small attention needs <= 32 cached keys; scores of the backbone attention sit in the 32 KB x buffer
   if (x->cfg.codebooks > 32 || x->cfg.max_seq_len * 4 + (mega::NCT + 128) * 4 > (int)mega::SMEM_X) return CSM_OK;
+  if (x->dec.hd != 128 || 2 * x->cfg.decoder.dim > 2048 || x->cfg.decoder.kv_heads > 2) return CSM_OK;  // fused attention layout
+  if (x->cfg.backbone.dim > 8 * mega::NCT || x->cfg.decoder.dim > 8 * mega::NCT) return CSM_OK;  // one norm unit per thread
   int dev = 0, sms = 0, coop = 0, occ = 0;
   CU_TRY(cudaGetDevice(&dev));
   CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   CU_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   CU_TRY(cudaFuncSetAttribute(mega::k_frame_mega, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega::SMEM_BYTES));
-  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mega::k_frame_mega, mega::NTHREADS, mega::SMEM_BYTES));
+  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mega::k_frame_mega, mega::NCT, mega::SMEM_BYTES));
   if (!coop || occ < 1) return CSM_OK;
   std::vector<mega::Phase> v;
   build_mega_phases(x, v);
   if ((int)v.size() != mega_phase_count(x->cfg)) return set_err(CSM_ERR_ARG, "internal: phase count mismatch");
+  memset(&x->pf_table, 0, sizeof(x->pf_table));
+  for (const mega::Phase& ph : v) {
+    if (ph.type != mega::PH_GEMV) continue;
+    if (x->pf_table.n >= mega::MAX_GEMV) return CSM_OK;  // too deep for the parameter-space table: per-op path only
+    mega::PfDesc& d = x->pf_table.d[x->pf_table.n++];
+    d.W = ph.W; d.rows = ph.rows; d.K = ph.K; d.G = ph.G;
+  }
   CU_TRY(cudaMemcpyAsync(x->d_phases, v.data(), v.size() * sizeof(mega::Phase), cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemsetAsync(x->d_sync, 0, sizeof(mega::Sync), st));
   CU_TRY(cudaStreamSynchronize(st));  // v is host stack memory
@@ -400,8 +412,9 @@ static int launch_mega(csm_ctx* x, const FrameParams& p, cudaStream_t st) {
   int n = x->n_phases;
   const FrameParams* dp = x->d_params;
   mega::Sync* sy = x->d_sync;
-  void* args[] = {(void*)&ph, (void*)&n, (void*)&dp, (void*)&sy};
-  CU_TRY(cudaLaunchCooperativeKernel((const void*)mega::k_frame_mega, dim3(x->mega_grid), dim3(mega::NTHREADS), args,
+  unsigned long long* trc = x->trace;
+  void* args[] = {(void*)&ph, (void*)&n, (void*)&dp, (void*)&sy, (void*)&trc, (void*)&x->pf_table};
+  CU_TRY(cudaLaunchCooperativeKernel((const void*)mega::k_frame_mega, dim3(x->mega_grid), dim3(mega::NCT), args,
                                      mega::SMEM_BYTES, st));
   COUNT_LAUNCH();
   return CSM_OK;
@@ -577,6 +590,12 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
   }
   x->cache_len += S;
   return CSM_OK;
+}
+
+extern "C" int32_t csm_debug_set_trace(csm_ctx* x, void* dev_buffer) {
+  if (!x) return set_err(CSM_ERR_ARG, "null ctx");
+  x->trace = (unsigned long long*)dev_buffer;
+  return x->mega_ok ? x->n_phases : 0;
 }
 
 // ---- unit-test entry points -----------------------------------------------------------------

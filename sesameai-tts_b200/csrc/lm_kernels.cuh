@@ -83,24 +83,48 @@ __global__ void k_embed_pass(const FrameParams* __restrict__ P, const bf16* text
 template <int NB, int NT, int BAR>
 __device__ __forceinline__ void rmsnorm_smem(bf16* xs, int K, const bf16* __restrict__ scale, float eps,
                                              float* scratch, int tid) {
+  // 8-element (16-byte) units per thread; one CTA-wide reduction for all NB rows
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int nw = NT / 32;
+  float ss[NB];
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) ss[nb] = 0.f;
+  for (int u = tid; u < K / 8; u += NT) {
+#pragma unroll
+    for (int nb = 0; nb < NB; ++nb) {
+      const uint4 v = *reinterpret_cast<const uint4*>(xs + nb * K + u * 8);
+      float a;
+      a = bflo(v.x); ss[nb] = fmaf(a, a, ss[nb]); a = bfhi(v.x); ss[nb] = fmaf(a, a, ss[nb]);
+      a = bflo(v.y); ss[nb] = fmaf(a, a, ss[nb]); a = bfhi(v.y); ss[nb] = fmaf(a, a, ss[nb]);
+      a = bflo(v.z); ss[nb] = fmaf(a, a, ss[nb]); a = bfhi(v.z); ss[nb] = fmaf(a, a, ss[nb]);
+      a = bflo(v.w); ss[nb] = fmaf(a, a, ss[nb]); a = bfhi(v.w); ss[nb] = fmaf(a, a, ss[nb]);
+    }
+  }
+#pragma unroll
+  for (int nb = 0; nb < NB; ++nb) {
+    ss[nb] = warp_sum(ss[nb]);
+    if (lane == 0) scratch[nb * nw + warp] = ss[nb];
+  }
+  csync<NT, BAR>();
   float inv[NB];
 #pragma unroll
   for (int nb = 0; nb < NB; ++nb) {
-    float ss = 0.f;
-    for (int k = tid; k < K; k += NT) {
-      float v = bf2f(xs[nb * K + k]);
-      ss = fmaf(v, v, ss);
-    }
-    ss = block_sum<NT, BAR>(ss, scratch, tid);
-    inv[nb] = 1.0f / sqrtf(ss / (float)K + eps);
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < nw; ++w) t += scratch[nb * nw + w];
+    inv[nb] = 1.0f / sqrtf(t / (float)K + eps);
   }
-  csync<NT, BAR>();
-  for (int k = tid; k < K; k += NT) {
-    const float sc = bf2f(scale[k]);
+  for (int u = tid; u < K / 8; u += NT) {
+    const uint4 sc = *reinterpret_cast<const uint4*>(scale + u * 8);
 #pragma unroll
     for (int nb = 0; nb < NB; ++nb) {
-      float v = rbf(bf2f(xs[nb * K + k]) * inv[nb]);
-      xs[nb * K + k] = f2bf(v * sc);
+      uint4 v = *reinterpret_cast<const uint4*>(xs + nb * K + u * 8);
+      __nv_bfloat162 o[4];
+      o[0] = __floats2bfloat162_rn(rbf(bflo(v.x) * inv[nb]) * bflo(sc.x), rbf(bfhi(v.x) * inv[nb]) * bfhi(sc.x));
+      o[1] = __floats2bfloat162_rn(rbf(bflo(v.y) * inv[nb]) * bflo(sc.y), rbf(bfhi(v.y) * inv[nb]) * bfhi(sc.y));
+      o[2] = __floats2bfloat162_rn(rbf(bflo(v.z) * inv[nb]) * bflo(sc.z), rbf(bfhi(v.z) * inv[nb]) * bfhi(sc.z));
+      o[3] = __floats2bfloat162_rn(rbf(bflo(v.w) * inv[nb]) * bflo(sc.w), rbf(bfhi(v.w) * inv[nb]) * bfhi(sc.w));
+      *reinterpret_cast<uint4*>(xs + nb * K + u * 8) = *reinterpret_cast<uint4*>(o);
     }
   }
   csync<NT, BAR>();
@@ -140,7 +164,7 @@ template <int NB, int EPI, bool NORM>
 __global__ void __launch_bounds__(256) k_gemv(GemvArgs a) {  // launched with exactly 256 threads
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* xs = reinterpret_cast<bf16*>(smem_raw);
-  __shared__ float scratch[33];
+  __shared__ float scratch[72];
   const int K = a.K;
   const int n0 = blockIdx.y * NB;
 
@@ -351,7 +375,43 @@ __device__ __forceinline__ float exp1_draw(unsigned long long seed, unsigned lon
 #define SAMPLE_THREADS 256
 #define SAMPLE_MAXV 4096
 
-// Core: returns the sampled token for one logits row (all threads return the same value).
+// k-th largest of a 256-bin histogram, counted from the top: warp 0 scans 8 bins per lane.
+// Writes {bin, rank inside the bin} to out[0..1]; callers sync afterwards.
+__device__ __forceinline__ void hist_select_from_top(const unsigned int* hist, int k, int* out, int tid) {
+  if (tid >= 32) return;
+  const int lane = tid;
+  // lane l owns bins [255-8l-7 .. 255-8l] i.e. descending order across lanes
+  unsigned int cnt[8], tot = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    cnt[j] = hist[255 - 8 * lane - j];
+    tot += cnt[j];
+  }
+  unsigned int incl = tot;  // inclusive prefix over lanes (top bins first)
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const unsigned int excl = incl - tot;
+  const bool mine = excl < (unsigned)k && incl >= (unsigned)k;
+  const unsigned int all = __shfl_sync(0xffffffffu, incl, 31);
+  if (mine) {
+    unsigned int cum = excl;
+    int j = 0;
+    for (; j < 7; ++j) {
+      if (cum + cnt[j] >= (unsigned)k) break;
+      cum += cnt[j];
+    }
+    out[0] = 255 - 8 * lane - j;
+    out[1] = k - (int)cum;
+  } else if (lane == 31 && all < (unsigned)k) {  // fewer than k entries: everything survives
+    out[0] = 0;
+    out[1] = 1;
+  }
+}
+
+// Core: returns the sampled token for one logits row (all NT threads return the same value).
 template <int NT, int BAR, bool CG>
 __device__ int sample_row(const bf16* __restrict__ logits, const bf16* __restrict__ noise, int V, float temperature,
                           int topk, unsigned long long seed, unsigned long long ctr0, float* xs /*[V]*/,
@@ -359,85 +419,80 @@ __device__ int sample_row(const bf16* __restrict__ logits, const bf16* __restric
   // 1. temperature + radix histogram of the high key byte.  ``logits / temperature`` with a
   //    Python-float divisor is evaluated by torch's CUDA div kernel as x * (1/T) in fp32
   //    (the reference path on a GPU), then rounded to bf16.
-  for (int i = tid; i < 256; i += NT) hist[i] = 0;
-  csync<NT, BAR>();
+  const int k = topk < 1 ? 1 : (topk > V ? V : topk);
+  const bool greedy = k == 1;
+  if (!greedy) {
+    for (int i = tid; i < 256; i += NT) hist[i] = 0;
+    csync<NT, BAR>();
+  }
   float mx = -INFINITY;
   const float inv_t = 1.0f / temperature;
   for (int i = tid; i < V; i += NT) {
     const bf16 lg = CG ? __ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(logits) + i)) : logits[i];
     const bf16 xb = f2bf(bf2f(lg) * inv_t);
-    xs[i] = bf2f(xb);
-    atomicAdd(&hist[bf_key(xb) >> 8], 1u);
+    const float xv = bf2f(xb);
+    xs[i] = xv;
+    mx = fmaxf(mx, xv);
+    if (!greedy) atomicAdd(&hist[bf_key(xb) >> 8], 1u);
   }
-  csync<NT, BAR>();
-  // 2. k-th largest: walk the high-byte histogram from the top, then the low byte inside that bin
-  int k = topk < 1 ? 1 : (topk > V ? V : topk);
-  if (tid == 0) {
-    int cum = 0, b = 255;
-    for (; b > 0; --b) {
-      if (cum + (int)hist[b] >= k) break;
-      cum += hist[b];
+  mx = block_max<NT, BAR>(mx, scratch, tid);  // (its barriers also publish xs[] and hist[])
+  // 2. threshold = k-th largest value: exact 16-bit radix select (top-1 is just the max)
+  float thr = mx;
+  if (!greedy) {
+    hist_select_from_top(hist, k, iscratch, tid);
+    csync<NT, BAR>();
+    const int hb = iscratch[0];
+    const int krem = iscratch[1];
+    csync<NT, BAR>();
+    for (int i = tid; i < 256; i += NT) hist[i] = 0;
+    csync<NT, BAR>();
+    for (int i = tid; i < V; i += NT) {
+      const uint32_t key = bf_key(f2bf(xs[i]));
+      if ((int)(key >> 8) == hb) atomicAdd(&hist[key & 0xffu], 1u);
     }
-    iscratch[0] = b;
-    iscratch[1] = k - cum;  // rank inside the bin
+    csync<NT, BAR>();
+    hist_select_from_top(hist, krem, iscratch + 2, tid);
+    csync<NT, BAR>();
+    thr = key_to_float(((uint32_t)hb << 8) | (uint32_t)iscratch[2]);
   }
-  csync<NT, BAR>();
-  const int hb = iscratch[0];
-  const int krem = iscratch[1];
-  csync<NT, BAR>();
-  for (int i = tid; i < 256; i += NT) hist[i] = 0;
-  csync<NT, BAR>();
-  for (int i = tid; i < V; i += NT) {
-    const uint32_t key = bf_key(f2bf(xs[i]));
-    if ((int)(key >> 8) == hb) atomicAdd(&hist[key & 0xffu], 1u);
-  }
-  csync<NT, BAR>();
-  if (tid == 0) {
-    int cum = 0, b = 255;
-    for (; b > 0; --b) {
-      if (cum + (int)hist[b] >= krem) break;
-      cum += hist[b];
-    }
-    iscratch[2] = b;
-  }
-  csync<NT, BAR>();
-  const float thr = key_to_float(((uint32_t)hb << 8) | (uint32_t)iscratch[2]);
-  // 3. mask + log_softmax (fp32 internals, bf16 result)
-  for (int i = tid; i < V; i += NT) {
-    float v = xs[i];
-    if (v < thr) v = -INFINITY;
-    xs[i] = v;
-    mx = fmaxf(mx, v);
-  }
-  mx = block_max<NT, BAR>(mx, scratch, tid);
+  // 3. mask (ties with the threshold are kept) + log_softmax, fp32 internals, bf16 result
+  //    (non-survivors contribute exp(-inf) = 0 exactly and end with probability 0: skip their math)
   float sum = 0.f;
-  for (int i = tid; i < V; i += NT) sum += expf(xs[i] - mx);
+  for (int i = tid; i < V; i += NT) {
+    const float v = xs[i];
+    if (v < thr) xs[i] = -INFINITY;
+    else sum += expf(v - mx);
+  }
   sum = block_sum<NT, BAR>(sum, scratch, tid);
   const float lse = logf(sum);
-  float mx2 = -INFINITY;
-  for (int i = tid; i < V; i += NT) {
-    const float ls = rbf((xs[i] - mx) - lse);
-    xs[i] = ls;
-    mx2 = fmaxf(mx2, ls);
-  }
-  mx2 = block_max<NT, BAR>(mx2, scratch, tid);
-  // 4. softmax of the bf16 log-probs
+  // 4. softmax of the bf16 log-probs: their max is the entry of the largest x
+  const float mx2 = rbf((mx - mx) - lse);
   float sum2 = 0.f;
-  for (int i = tid; i < V; i += NT) sum2 += expf(xs[i] - mx2);
+  for (int i = tid; i < V; i += NT) {
+    const float v = xs[i];
+    if (v == -INFINITY) continue;
+    const float ls = rbf((v - mx) - lse);
+    xs[i] = ls;
+    sum2 += expf(ls - mx2);
+  }
   sum2 = block_sum<NT, BAR>(sum2, scratch, tid);
   // 5. exponential race, first-index argmax
   float best = -INFINITY;
   int besti = 0x7fffffff;
   for (int i = tid; i < V; i += NT) {
-    const float p = rbf(expf(xs[i] - mx2) / sum2);
-    const float q = noise ? bf2f(noise[i]) : exp1_draw(seed, ctr0 + i);
-    const float r = rbf(p / q);
+    const float v = xs[i];
+    // masked entries have p = 0 -> r = 0 (q > 0); they can only win when every r rounds to 0
+    float r = 0.f;
+    if (v != -INFINITY) {
+      const float p = rbf(expf(v - mx2) / sum2);
+      const float q = noise ? bf2f(noise[i]) : exp1_draw(seed, ctr0 + i);
+      r = rbf(p / q);
+    }
     if (r > best) {  // strided ascending i per thread -> keeps the first index on ties
       best = r;
       besti = i;
     }
   }
-  // block arg-max with smallest-index tie break
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -450,13 +505,13 @@ __device__ int sample_row(const bf16* __restrict__ logits, const bf16* __restric
   csync<NT, BAR>();
   if ((tid & 31) == 0) {
     scratch[tid >> 5] = best;
-    iscratch[2 + (tid >> 5)] = besti;
+    iscratch[4 + (tid >> 5)] = besti;
   }
   csync<NT, BAR>();
   if (tid < 32) {
     constexpr int nw = NT / 32;
     best = tid < nw ? scratch[tid] : -INFINITY;
-    besti = tid < nw ? iscratch[2 + tid] : 0x7fffffff;
+    besti = tid < nw ? iscratch[4 + tid] : 0x7fffffff;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float ob = __shfl_xor_sync(0xffffffffu, best, o);

@@ -1,65 +1,90 @@
 // Persistent decode megakernel: one audio frame (backbone step + codebook-0 sample + 31 depth-
-// decoder steps, ~670 dependent phases) in ONE launch, for one stream.
+// decoder steps, ~640 dependent phases) in ONE launch, for one stream.
 //
-// Why: at batch 1 a frame is ~800 tiny dependent GEMVs (0.3-5 us of HBM time each); launched one
+// Why: at batch 1 a frame is ~800 tiny dependent GEMVs (0.3-10 us of HBM time each); launched one
 // by one they are latency bound (v1: 17 % of the HBM roofline).  Here one CTA per SM stays
 // resident for the whole frame:
-//   * a producer warp streams this CTA's share of every weight matrix, in consumption order,
-//     through per-warp shared-memory rings with bulk async copies (cp.async.bulk + mbarrier
-//     complete_tx).  Weight addresses are data independent, so the stream runs AHEAD of the
-//     dependency chain: 148 SMs x 192 KB = 28 MB of weights (~4 us of HBM time) are in flight
-//     while grid barriers, norms, attention and sampling resolve;
-//   * 8 consumer warps each own output-row groups: dot products out of shared memory, warp
-//     shuffle reduction, fused epilogue (RoPE + KV append / residual / SwiGLU / logits) at the
-//     reference's bf16 rounding points;
-//   * phases are separated by a monotonic grid barrier (release/acquire counter in L2).
+//   * every warp streams ITS share of every weight matrix, in consumption order, through a
+//     private shared-memory ring with bulk async copies (cp.async.bulk + mbarrier complete_tx).
+//     Weight addresses are data independent, so the stream runs AHEAD of the dependency chain:
+//     148 SMs x 192 KB = 28 MB of weights (~4 us of HBM time) stay in flight while grid barriers,
+//     norms, attention and sampling resolve.  The schedule of what to fetch next comes from a
+//     compact table passed in kernel-parameter (constant) space;
+//   * the same warp computes its output-row groups out of shared memory (fp32 accumulate, warp
+//     shuffle reduction) and runs the fused epilogue (RoPE + KV append / residual / SwiGLU /
+//     logits) at the reference's bf16 rounding points, then refills the slot it just drained;
+//   * phases are separated by a monotonic grid barrier (release/acquire counter in L2); the next
+//     phase's descriptor is prefetched into shared memory while the current one computes.
 // Every spin has a trip-count cap and traps instead of hanging the GPU.
 #pragma once
 #include "lm_kernels.cuh"
 
 namespace mega {
 
-constexpr int NW = 8;                 // consumer warps
-constexpr int NCT = NW * 32;          // consumer threads
-constexpr int NTHREADS = NCT + 32;    // + one producer warp
-constexpr int SLOTS = 3;              // ring slots per consumer warp
-constexpr int CHUNK_ELEMS = 4096;     // bf16 per slot (8 KB)
+#ifndef MEGA_NW
+#define MEGA_NW 8
+#endif
+#ifndef MEGA_SLOTS
+#define MEGA_SLOTS 2
+#endif
+#ifndef MEGA_CHUNK
+#define MEGA_CHUNK 4096
+#endif
+constexpr int NW = MEGA_NW;           // warps per CTA
+constexpr int NCT = NW * 32;          // threads per CTA
+constexpr int SLOTS = MEGA_SLOTS;     // ring slots per warp
+constexpr int CHUNK_ELEMS = MEGA_CHUNK;  // bf16 per slot
+constexpr int KC_MAX = CHUNK_ELEMS / 2;  // k-extent of a chunk (a chunk holds >= 2 rows)
 constexpr int MAXNB = 2;              // activation rows per phase (depth step 1 carries 2)
 constexpr int XBUF_ELEMS = MAXNB * 8192;
-constexpr int CBAR = 1;               // named barrier of the consumer warps
+constexpr int CBAR = 0;               // all threads are consumers: plain CTA barrier
+constexpr int MAX_GEMV = 640;         // rows of the prefetch table (kernel parameter space)
 constexpr size_t SMEM_RING = (size_t)NW * SLOTS * CHUNK_ELEMS * 2;
 constexpr size_t SMEM_X = (size_t)XBUF_ELEMS * 2;
-constexpr size_t SMEM_MISC = 1024;
+constexpr size_t SMEM_MISC = 2048;
 constexpr size_t SMEM_BYTES = SMEM_RING + SMEM_X + SMEM_MISC;
 
 enum { PH_GEMV = 0, PH_EMBED = 1, PH_ATTN = 2, PH_SAMPLE = 3 };
 enum { POS_FIXED = 0, POS_BACKBONE = 1 };
 
-struct Phase {
+// Full description of a phase (global memory; staged into shared memory one phase ahead).
+struct __align__(16) Phase {
   int type, epi, norm, nb;
-  // GEMV
   const bf16* W;
-  int rows, K, R, KC, G;
+  int rows, K, R, KC, G, ldx;
   const bf16* x;  // [nb, ldx] activations in global memory
-  int ldx;
   const bf16* norm_scale;
-  float eps;
   bf16* out;
-  int ldo;
   const bf16* resid;
   bf16* x_copy_out;  // CTA 0 publishes the staged (normalised) rows here
+  float eps;
+  int ldo;
   // RoPE / KV append / attention
   bf16 *q, *kc, *vc;
   const bf16* rope;
   int heads, kv_heads, hd, slots, pos_mode, pos0;
   int attn_prologue;  // GEMV: x = attention(q, cache) computed redundantly by every CTA (<= 32 keys)
-  bf16* att_out;      // PH_ATTN: [heads*hd]
-  // sample
-  int cb, V, C, D, ldl;
+  int cb;
+  bf16* att_out;  // PH_ATTN: [heads*hd]
+  // sample / embed
+  int V, C, D, ldl;
   const bf16* logits;
   bf16* next_in;
   const bf16 *audio_emb, *text_emb;
-  bf16* h_out;  // PH_EMBED
+  bf16* h_out;
+  int pad_[2];
+};
+static_assert(sizeof(Phase) % 16 == 0, "Phase must be copyable in 16-byte units");
+
+// What the weight prefetcher needs to know about a GEMV phase.
+struct PfDesc {
+  const bf16* W;
+  int rows, K, G, pad_;
+};
+struct PfTable {
+  int n;
+  int pad_[3];
+  PfDesc d[MAX_GEMV];
 };
 
 struct Sync {
@@ -77,22 +102,8 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
 }
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -105,25 +116,39 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+// Weights are streamed with an L2 evict-first policy: they are read once per use and must not push
+// the small hot data (activations, KV cache, norm scales, RoPE tables) out of the 126 MB L2 --
+// otherwise every dependent load of a phase queues behind ~28 MB of in-flight weight traffic.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+      : "memory");
 }
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void red_release(unsigned* p, unsigned v) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void arrive_release(unsigned* p) {
+  // the fence also releases what the other threads of the CTA wrote before the CTA barrier
+  asm volatile("fence.acq_rel.gpu;\n\tred.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
 __device__ __forceinline__ uint4 ldcg16(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ float ldcg_bf(const bf16* p) {
   return bf2f(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(p))));
 }
-
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void die(Sync* sync, unsigned code) {
   atomicExch(&sync->error, code);
   __threadfence_system();
@@ -134,53 +159,55 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, Sync* 
     if (spin > (1u << 22)) die(sync, code);
 }
 
-// work distribution: group index of the i-th group owned by (cta, warp)
+// work distribution: the i-th row group owned by (cta, warp)
 __device__ __forceinline__ int group_of(int cta, int ncta, int warp, int i) { return cta + ncta * (warp + NW * i); }
 
-__device__ __forceinline__ void phase_pos(const Phase& ph, const FrameParams* P, int n, int& pos, int& slot) {
-  if (ph.pos_mode == POS_BACKBONE) {
-    pos = (int)P->pos[(size_t)n * P->S + (P->S - 1)];  // row n == stream n (batch 1: n == 0)
-    slot = P->cache_len + P->S - 1;
-  } else {
-    pos = slot = ph.pos0 + n;
+// ---- per-warp weight prefetcher -----------------------------------------------------------------------
+struct Prefetch {
+  int gi;    // index into the GEMV table
+  int i;     // group iteration inside the phase
+  int kc;    // k-chunk inside the group
+  unsigned issued;
+  bool done;
+  uint64_t policy;  // L2 cache policy of the weight stream
+};
+
+__device__ __forceinline__ void pf_seek(Prefetch& pf, const PfTable& tab, int cta, int ncta, int warp) {
+  // position on the first (phase, group) at or after (gi, i) that this warp owns
+  while (pf.gi < tab.n && group_of(cta, ncta, warp, pf.i) >= tab.d[pf.gi].G) {
+    ++pf.gi;
+    pf.i = 0;
   }
+  pf.done = pf.gi >= tab.n;
 }
 
-// ---- producer: stream this CTA's weight chunks through the per-warp rings -------------------------
-__device__ void producer(const Phase* __restrict__ phases, int nphases, bf16* ring, uint64_t* full, uint64_t* empty,
-                         Sync* sync) {
-  const int w = threadIdx.x & 31;  // lane w feeds consumer warp w
-  if (w >= NW) return;
-  const int cta = blockIdx.x, ncta = gridDim.x;
-  unsigned cnt = 0;
-  for (int p = 0; p < nphases; ++p) {
-    if (phases[p].type != PH_GEMV) continue;
-    const bf16* W = phases[p].W;
-    const int K = phases[p].K, R = phases[p].R, KC = phases[p].KC, G = phases[p].G, rows = phases[p].rows;
-    const int nkc = K / KC;
-    for (int i = 0;; ++i) {
-      const int g = group_of(cta, ncta, w, i);
-      if (g >= G) break;
-      const int r0 = g * R;
-      const int nr = min(R, rows - r0);
-      for (int kc = 0; kc < nkc; ++kc, ++cnt) {
-        const int slot = cnt % SLOTS;
-        const uint32_t par = ((cnt / SLOTS) & 1) ^ 1;
-        uint64_t* fb = &full[w * SLOTS + slot];
-        uint64_t* eb = &empty[w * SLOTS + slot];
-        for (unsigned spin = 0; !mbar_test(eb, par); ++spin)
-          if (spin > (1u << 26)) die(sync, 0x100 + w);
-        bf16* dst = ring + (size_t)(w * SLOTS + slot) * CHUNK_ELEMS;
-        if (nkc == 1) {  // rows are contiguous: one copy
-          mbar_expect_tx(fb, (uint32_t)nr * K * 2);
-          bulk_g2s(dst, W + (size_t)r0 * K, (uint32_t)nr * K * 2, fb);
-        } else {
-          mbar_expect_tx(fb, (uint32_t)nr * KC * 2);
-          for (int r = 0; r < nr; ++r)
-            bulk_g2s(dst + r * KC, W + (size_t)(r0 + r) * K + (size_t)kc * KC, (uint32_t)KC * 2, fb);
-        }
-      }
+// issue the next chunk of this warp's stream into ring slot (issued % SLOTS); whole warp calls it
+__device__ __forceinline__ void pf_issue(Prefetch& pf, const PfTable& tab, bf16* ring, uint64_t* full, int cta, int ncta,
+                                         int warp, int lane) {
+  if (pf.done) return;
+  const PfDesc& d = tab.d[pf.gi];
+  const int K = d.K, KC = K < KC_MAX ? K : KC_MAX, R = CHUNK_ELEMS / KC, nkc = K / KC;
+  const int g = group_of(cta, ncta, warp, pf.i);
+  const int r0 = g * R;
+  const int nr = min(R, d.rows - r0);
+  const int slot = pf.issued % SLOTS;
+  if (lane == 0) {
+    uint64_t* fb = &full[warp * SLOTS + slot];
+    bf16* dst = ring + (size_t)(warp * SLOTS + slot) * CHUNK_ELEMS;
+    if (nkc == 1) {  // whole rows are contiguous: one copy
+      mbar_expect_tx(fb, (uint32_t)nr * K * 2);
+      bulk_g2s(dst, d.W + (size_t)r0 * K, (uint32_t)nr * K * 2, fb, pf.policy);
+    } else {
+      mbar_expect_tx(fb, (uint32_t)nr * KC * 2);
+      for (int r = 0; r < nr; ++r)
+        bulk_g2s(dst + r * KC, d.W + (size_t)(r0 + r) * K + (size_t)pf.kc * KC, (uint32_t)KC * 2, fb, pf.policy);
     }
+  }
+  ++pf.issued;
+  if (++pf.kc == nkc) {
+    pf.kc = 0;
+    ++pf.i;
+    pf_seek(pf, tab, cta, ncta, warp);
   }
 }
 
@@ -189,70 +216,109 @@ struct Ctx {
   const FrameParams* P;
   bf16* ring;
   bf16* xs;
-  uint64_t *full, *empty;
+  uint64_t* full;
   float* scratch;  // 33 floats
-  int* iscratch;   // 36 ints
+  int* iscratch;   // 40 ints
   Sync* sync;
+  Prefetch pf;
   unsigned cnt;  // chunks consumed by this warp so far
+  unsigned long long* trp;  // fine-grained trace slots of the current phase (CTA 0, thread 0) or null
   int tid, warp, lane;
+  int bb_pos, bb_slot;  // RoPE position / cache slot of the backbone row of this frame
 };
 
+__device__ __forceinline__ void phase_pos(const Phase& ph, const Ctx& c, int n, int& pos, int& slot) {
+  if (ph.pos_mode == POS_BACKBONE) {
+    pos = c.bb_pos;
+    slot = c.bb_slot;
+  } else {
+    pos = slot = ph.pos0 + n;
+  }
+}
+
+// Operands the epilogue of a row pair needs from global memory (residual values / RoPE cos,sin).
+// They are fetched when the warp STARTS a row group, so their L2 round trip -- ~1.5 us while the
+// weight stream saturates the memory system -- overlaps the dot products instead of following them.
+struct EpiPre {
+  float a, b;
+};
+__device__ __forceinline__ EpiPre epilogue_prefetch(const Phase& ph, const Ctx& c, int r0, int n) {
+  EpiPre e;
+  e.a = e.b = 0.f;
+  if (r0 >= ph.rows || n >= ph.nb) return e;
+  if (ph.epi == EPI_RESID) {
+    e.a = ldcg_bf(ph.resid + (size_t)n * ph.ldo + r0);
+    if (r0 + 1 < ph.rows) e.b = ldcg_bf(ph.resid + (size_t)n * ph.ldo + r0 + 1);
+  } else if (ph.epi == EPI_ROPE_KV) {
+    const int hd = ph.hd;
+    if (r0 < (ph.heads + ph.kv_heads) * hd) {
+      int pos, slot;
+      phase_pos(ph, c, n, pos, slot);
+      const __nv_bfloat162 cs = *reinterpret_cast<const __nv_bfloat162*>(ph.rope + ((size_t)pos * (hd / 2) + ((r0 % hd) >> 1)) * 2);
+      e.a = __low2float(cs);
+      e.b = __high2float(cs);
+    }
+  }
+  return e;
+}
+
 // fused epilogue of one output-row pair (row r0, r0+1) for activation row n
-__device__ __forceinline__ void epilogue(const Phase& ph, const FrameParams* P, int r0, int n, float a0, float a1) {
+__device__ __forceinline__ void epilogue(const Phase& ph, const Ctx& c, int r0, int n, float a0, float a1,
+                                         const EpiPre& pre) {
   const bool has1 = r0 + 1 < ph.rows;
   const float y0 = rbf(a0), y1 = rbf(a1);
   if (ph.epi == EPI_PLAIN) {
     ph.out[(size_t)n * ph.ldo + r0] = f2bf(y0);
     if (has1) ph.out[(size_t)n * ph.ldo + r0 + 1] = f2bf(y1);
   } else if (ph.epi == EPI_RESID) {
-    const float h0 = ldcg_bf(ph.resid + (size_t)n * ph.ldo + r0);
-    const float h1 = has1 ? ldcg_bf(ph.resid + (size_t)n * ph.ldo + r0 + 1) : 0.f;
-    ph.out[(size_t)n * ph.ldo + r0] = f2bf(y0 + h0);
-    if (has1) ph.out[(size_t)n * ph.ldo + r0 + 1] = f2bf(y1 + h1);
+    ph.out[(size_t)n * ph.ldo + r0] = f2bf(y0 + pre.a);
+    if (has1) ph.out[(size_t)n * ph.ldo + r0 + 1] = f2bf(y1 + pre.b);
   } else if (ph.epi == EPI_SWIGLU) {
     ph.out[(size_t)n * ph.ldo + (r0 >> 1)] = f2bf(silu_bf(y0) * y1);
   } else {  // EPI_ROPE_KV
     const int hd = ph.hd, qrows = ph.heads * hd, krows = ph.kv_heads * hd;
     int pos, slot;
-    phase_pos(ph, P, n, pos, slot);
+    phase_pos(ph, c, n, pos, slot);
     float o0 = y0, o1 = y1;
     if (r0 < qrows + krows) {
-      const int j = (r0 % hd) >> 1;
-      const bf16* cs = ph.rope + ((size_t)pos * (hd / 2) + j) * 2;
-      const float c = bf2f(cs[0]), s = bf2f(cs[1]);
-      o0 = rbf(__fsub_rn(__fmul_rn(y0, c), __fmul_rn(y1, s)));
-      o1 = rbf(__fadd_rn(__fmul_rn(y1, c), __fmul_rn(y0, s)));
+      o0 = rbf(__fsub_rn(__fmul_rn(y0, pre.a), __fmul_rn(y1, pre.b)));
+      o1 = rbf(__fadd_rn(__fmul_rn(y1, pre.a), __fmul_rn(y0, pre.b)));
     }
     if (r0 < qrows) {
-      ph.q[(size_t)n * qrows + r0] = f2bf(o0);
-      ph.q[(size_t)n * qrows + r0 + 1] = f2bf(o1);
+      *reinterpret_cast<__nv_bfloat162*>(ph.q + (size_t)n * qrows + r0) = __floats2bfloat162_rn(o0, o1);
     } else {
       const bool isk = r0 < qrows + krows;
       const int rr = r0 - (isk ? qrows : qrows + krows);
       const int kvh = rr / hd, d = rr % hd;
       bf16* dst = (isk ? ph.kc : ph.vc) + ((size_t)kvh * ph.slots + slot) * hd + d;  // stream 0
-      dst[0] = f2bf(o0);
-      dst[1] = f2bf(o1);
+      *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(o0, o1);
     }
   }
 }
 
+// One warp, one row group (R rows x K) at a time: R*NB accumulators, the group's chunk(s) come from
+// this warp's ring; after the shuffle reduction lane (pair, n) runs that pair's epilogue.
 template <int R, int NB>
-__device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c) {
+__device__ __noinline__ void gemv_groups(const Phase& ph, Ctx& c, const PfTable& tab) {
   const int cta = blockIdx.x, ncta = gridDim.x;
   const int K = ph.K, KC = ph.KC, nkc = K / KC;
   for (int i = 0;; ++i) {
     const int g = group_of(cta, ncta, c.warp, i);
     if (g >= ph.G) break;
+    const int my_pr = c.lane % (R / 2), my_n = c.lane / (R / 2);
+    const bool epi_lane = c.lane < (R / 2) * NB;
+    EpiPre pre;
+    pre.a = pre.b = 0.f;
+    if (epi_lane) pre = epilogue_prefetch(ph, c, g * R + 2 * my_pr, my_n);
     float acc[R][NB];
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int n = 0; n < NB; ++n) acc[r][n] = 0.f;
-    for (int kc = 0; kc < nkc; ++kc, ++c.cnt) {
+    for (int kc = 0; kc < nkc; ++kc) {
       const int slot = c.cnt % SLOTS;
-      const uint32_t par = (c.cnt / SLOTS) & 1;
-      mbar_wait(&c.full[c.warp * SLOTS + slot], par, c.sync, 0x200 + c.warp);
+      mbar_wait(&c.full[c.warp * SLOTS + slot], (c.cnt / SLOTS) & 1, c.sync, 0x200 + c.warp);
+      if (c.trp && i == 0 && kc == 0 && !ph.attn_prologue) c.trp[1] = gtimer();
       const bf16* chunk = c.ring + (size_t)(c.warp * SLOTS + slot) * CHUNK_ELEMS;
       const bf16* xk = c.xs + (size_t)kc * KC;
 #pragma unroll 2
@@ -268,9 +334,11 @@ __device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c) {
         }
       }
       __syncwarp();
-      if (c.lane == 0) mbar_arrive(&c.empty[c.warp * SLOTS + slot]);
+      ++c.cnt;
+      if (c.trp && i == 0 && kc == 0 && !ph.attn_prologue) c.trp[2] = gtimer();
+      // the slot is drained: refill it with the chunk SLOTS ahead in this warp's stream
+      pf_issue(c.pf, tab, c.ring, c.full, cta, ncta, c.warp, c.lane);
     }
-    // reduce, then lane (pair, n) runs that pair's epilogue
     float y0 = 0.f, y1 = 0.f;
 #pragma unroll
     for (int r = 0; r < R / 2; ++r)
@@ -283,120 +351,217 @@ __device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c) {
           y1 = s1;
         }
       }
-    if (c.lane < (R / 2) * NB) {
-      const int pr = c.lane % (R / 2), n = c.lane / (R / 2);
-      const int r0 = g * R + 2 * pr;
-      if (r0 < ph.rows && n < ph.nb) epilogue(ph, c.P, r0, n, y0, y1);
+    if (epi_lane) {
+      const int r0 = g * R + 2 * my_pr;
+      if (r0 < ph.rows && my_n < ph.nb) epilogue(ph, c, r0, my_n, y0, y1, pre);
     }
   }
 }
 
-// attention over <= 32 cached keys for every (row, head), redundantly in every CTA, straight into
-// the activation buffer of the output projection (depth decoder: 32 slots per stream)
-__device__ void attn_small_into_x(const Phase& ph, Ctx& c) {
-  const int hd = ph.hd, heads = ph.heads, grp = heads / ph.kv_heads;
-  const float scale = 1.0f / sqrtf((float)hd);
-  const int dims = hd / 32;  // output dims per lane (2 or 4)
-  for (int item = c.warp; item < ph.nb * heads; item += NW) {
-    const int n = item / heads, h = item % heads, kvh = h / grp;
-    int pos, slot;
-    phase_pos(ph, c.P, n, pos, slot);
-    const int nkeys = slot + 1;
-    const bf16* kp = ph.kc + (size_t)kvh * ph.slots * hd;
-    const bf16* vp = ph.vc + (size_t)kvh * ph.slots * hd;
-    const bf16* qr = ph.q + ((size_t)n * heads + h) * hd;
-    float s = -INFINITY;
-    if (c.lane < nkeys) {
-      const bf16* kr = kp + (size_t)c.lane * hd;
-      float a = 0.f;
-      for (int i = 0; i < hd / 8; ++i) {
-        const uint4 kv = ldcg16(kr + i * 8);
-        const uint4 qv = ldcg16(qr + i * 8);
-        a = dot8(kv, qv, a);
+// Attention over <= 32 cached keys for every (row, head), redundantly in every CTA, straight into
+// the activation buffer of the output projection (depth decoder: 32 slots per stream, head_dim 128).
+//   xs layout (bf16 elements): [0, nb*dim) output rows | [2048, +nb*dim) q | [4096, +kv*keys*136) K
+//   rows padded to 136 (conflict-free 16-byte reads with lane == key) | partial scores (fp32).
+//   A warp owns (row, head, half of the head dims): partial q.k over its 64 dims with lane == key,
+//   halves summed through shared memory, softmax by shuffles, then P.V for its 64 output dims with
+//   lane == 2 dims.  The V loads are issued first so their L2 round trip overlaps everything else.
+__device__ __noinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
+  constexpr int HD = 128, KS = HD + 8, QOFF = 2048, KOFF = 4096;
+  const int heads = ph.heads, kvn = ph.kv_heads, grp = heads / kvn, nb = ph.nb;
+  const int nkmax = ph.pos0 + nb;  // keys visible to the last row
+  float* part = reinterpret_cast<float*>(c.xs + KOFF + kvn * 32 * KS);  // [nb*heads][2][32]
+  const int nitems = nb * heads * 2;
+  // V for this warp's first item: 32 x 4-byte loads in flight from here on
+  uint32_t vreg[32];
+  {
+    const int item = c.warp < nitems ? c.warp : 0;
+    const int n = item / (heads * 2), h = (item >> 1) % heads, half = item & 1, kvh = h / grp;
+    const int nkeys = ph.pos0 + n + 1;
+    const bf16* vp = ph.vc + (size_t)kvh * ph.slots * HD + half * 64 + c.lane * 2;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) vreg[j] = __ldcg(reinterpret_cast<const uint32_t*>(vp + (j < nkeys ? j : 0) * HD));
+  }
+  {  // stage q and the K rows with 16-byte loads
+    const int qunits = nb * heads * (HD / 8), kunits = kvn * nkmax * (HD / 8), total = qunits + kunits;
+    constexpr int MAXIT = (2 * 8 * 16 + 2 * 32 * 16 + NCT - 1) / NCT;  // nb<=2, heads<=8, kv<=2, keys<=32
+    uint4 v[MAXIT];
+    int dst[MAXIT];
+#pragma unroll
+    for (int t = 0; t < MAXIT; ++t) {
+      const int u = c.tid + t * NCT;
+      dst[t] = -1;
+      if (u < qunits) {
+        v[t] = ldcg16(ph.q + u * 8);
+        dst[t] = QOFF + u * 8;
+      } else if (u < total) {
+        const int ku = u - qunits, row = ku >> 4, i = ku & 15;
+        const int kvh = row / nkmax, j = row - kvh * nkmax;
+        v[t] = ldcg16(ph.kc + (kvh * ph.slots + j) * HD + i * 8);
+        dst[t] = KOFF + row * KS + i * 8;
       }
-      s = a * scale;
     }
-    const float mx = warp_max(s);
-    const float e = (c.lane < nkeys) ? expf(s - mx) : 0.f;
-    const float sum = warp_sum(e);
-    float o[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int j = 0; j < nkeys; ++j) {
-      const float pj = __shfl_sync(0xffffffffu, e, j);
-      const bf16* vr = vp + (size_t)j * hd + c.lane * dims;
-      if (dims == 4) {
-        const uint2 v = __ldcg(reinterpret_cast<const uint2*>(vr));
-        o[0] = fmaf(pj, bflo(v.x), o[0]); o[1] = fmaf(pj, bfhi(v.x), o[1]);
-        o[2] = fmaf(pj, bflo(v.y), o[2]); o[3] = fmaf(pj, bfhi(v.y), o[3]);
-      } else {
-        const uint32_t v = __ldcg(reinterpret_cast<const uint32_t*>(vr));
-        o[0] = fmaf(pj, bflo(v), o[0]); o[1] = fmaf(pj, bfhi(v), o[1]);
-      }
-    }
-    const float inv = 1.0f / sum;
-    bf16* dst = c.xs + (size_t)n * ph.K + h * hd + c.lane * dims;
-    for (int d = 0; d < dims; ++d) dst[d] = f2bf(o[d] * inv);
+#pragma unroll
+    for (int t = 0; t < MAXIT; ++t)
+      if (dst[t] >= 0) *reinterpret_cast<uint4*>(c.xs + dst[t]) = v[t];
   }
   csync<NCT, CBAR>();
+  if (c.trp) c.trp[1] = gtimer();
+  const float scale = 0.08838834764831845f;  // 1/sqrt(128)
+  for (int it0 = 0; it0 < nitems; it0 += NW) {
+    const int item = it0 + c.warp;
+    if (item < nitems) {
+      const int n = item / (heads * 2), h = (item >> 1) % heads, half = item & 1, kvh = h / grp;
+      const int nkeys = ph.pos0 + n + 1;
+      const bool own = c.lane < nkeys;
+      const bf16* kr = c.xs + KOFF + (kvh * nkmax + (own ? c.lane : 0)) * KS + half * 64;
+      const bf16* qr = c.xs + QOFF + (n * heads + h) * HD + half * 64;
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        a = dot8(*reinterpret_cast<const uint4*>(kr + i * 8), *reinterpret_cast<const uint4*>(qr + i * 8), a);
+      part[item * 32 + c.lane] = a;
+    }
+    csync<NCT, CBAR>();
+    if (c.trp && it0 == 0) c.trp[2] = gtimer();
+    if (item < nitems) {
+      const int n = item / (heads * 2), h = (item >> 1) % heads, half = item & 1;
+      const int nkeys = ph.pos0 + n + 1;
+      const bool own = c.lane < nkeys;
+      const float sc = own ? (part[(item & ~1) * 32 + c.lane] + part[(item | 1) * 32 + c.lane]) * scale : -INFINITY;
+      const float mx = warp_max(sc);
+      const float e = own ? expf(sc - mx) : 0.f;
+      const float inv = 1.0f / warp_sum(e);
+      if (it0 > 0) {  // later items (nb == 2): their V rows were not prefetched
+        const int kvh = h / grp;
+        const bf16* vp = ph.vc + (size_t)kvh * ph.slots * HD + half * 64 + c.lane * 2;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) vreg[j] = __ldcg(reinterpret_cast<const uint32_t*>(vp + (j < nkeys ? j : 0) * HD));
+      }
+      float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, e, j);  // 0 beyond nkeys
+        o0 = fmaf(pj, bflo(vreg[j]), o0);
+        o1 = fmaf(pj, bfhi(vreg[j]), o1);
+      }
+      *reinterpret_cast<__nv_bfloat162*>(c.xs + n * ph.K + h * HD + half * 64 + c.lane * 2) =
+          __floats2bfloat162_rn(o0 * inv, o1 * inv);
+    }
+    if (c.trp && it0 == 0) c.trp[3] = gtimer();
+    csync<NCT, CBAR>();
+  }
+}
+
+__device__ __forceinline__ float sumsq8(const uint4& v) {
+  float s = 0.f, a;
+  a = bflo(v.x); s = fmaf(a, a, s); a = bfhi(v.x); s = fmaf(a, a, s);
+  a = bflo(v.y); s = fmaf(a, a, s); a = bfhi(v.y); s = fmaf(a, a, s);
+  a = bflo(v.z); s = fmaf(a, a, s); a = bfhi(v.z); s = fmaf(a, a, s);
+  a = bflo(v.w); s = fmaf(a, a, s); a = bfhi(v.w); s = fmaf(a, a, s);
+  return s;
+}
+// torchtune RMSNorm on 8 elements: bf16( bf16(x * inv) * scale )
+__device__ __forceinline__ uint4 norm8(const uint4& v, float inv, const uint4& sc) {
+  __nv_bfloat162 o[4];
+  o[0] = __floats2bfloat162_rn(rbf(bflo(v.x) * inv) * bflo(sc.x), rbf(bfhi(v.x) * inv) * bfhi(sc.x));
+  o[1] = __floats2bfloat162_rn(rbf(bflo(v.y) * inv) * bflo(sc.y), rbf(bfhi(v.y) * inv) * bfhi(sc.y));
+  o[2] = __floats2bfloat162_rn(rbf(bflo(v.z) * inv) * bflo(sc.z), rbf(bfhi(v.z) * inv) * bfhi(sc.z));
+  o[3] = __floats2bfloat162_rn(rbf(bflo(v.w) * inv) * bflo(sc.w), rbf(bfhi(v.w) * inv) * bfhi(sc.w));
+  return *reinterpret_cast<uint4*>(o);
 }
 
 // stage the phase's activation rows into shared memory (+ RMSNorm prologue)
-__device__ void stage_x(const Phase& ph, Ctx& c) {
+__device__ __noinline__ void stage_x(const Phase& ph, Ctx& c) {
   if (ph.attn_prologue) {
     attn_small_into_x(ph, c);
     return;
   }
   const int K = ph.K, nb = ph.nb;
-  for (int i = c.tid; i < nb * (K / 8); i += NCT) {
-    const int n = i / (K / 8), k8 = i % (K / 8);
-    *reinterpret_cast<uint4*>(c.xs + (size_t)n * K + k8 * 8) = ldcg16(ph.x + (size_t)n * ph.ldx + k8 * 8);
+  if (ph.norm) {
+    // K <= 2048 for every normed phase: one 16-byte unit per thread; x and scale loads together
+    const int k8 = c.tid;
+    const bool on = k8 < K / 8;
+    uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0, sc = x0;
+    if (on) {
+      x0 = ldcg16(ph.x + k8 * 8);
+      if (nb == 2) x1 = ldcg16(ph.x + ph.ldx + k8 * 8);
+      sc = *reinterpret_cast<const uint4*>(ph.norm_scale + k8 * 8);
+    }
+    float s0 = sumsq8(x0), s1 = sumsq8(x1);
+    s0 = warp_sum(s0);
+    s1 = warp_sum(s1);
+    if (c.lane == 0) {
+      c.scratch[c.warp] = s0;
+      c.scratch[NW + c.warp] = s1;
+    }
+    csync<NCT, CBAR>();
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      t0 += c.scratch[w];
+      t1 += c.scratch[NW + w];
+    }
+    if (on) {
+      *reinterpret_cast<uint4*>(c.xs + k8 * 8) = norm8(x0, 1.0f / sqrtf(t0 / (float)K + ph.eps), sc);
+      if (nb == 2) *reinterpret_cast<uint4*>(c.xs + K + k8 * 8) = norm8(x1, 1.0f / sqrtf(t1 / (float)K + ph.eps), sc);
+    }
+  } else {
+    constexpr int MAXIT = 8192 / 8 / NCT;
+    uint4 v0[MAXIT], v1[MAXIT];
+#pragma unroll
+    for (int t = 0; t < MAXIT; ++t) {
+      const int k8 = c.tid + t * NCT;
+      if (k8 < K / 8) {
+        v0[t] = ldcg16(ph.x + k8 * 8);
+        if (nb == 2) v1[t] = ldcg16(ph.x + ph.ldx + k8 * 8);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < MAXIT; ++t) {
+      const int k8 = c.tid + t * NCT;
+      if (k8 < K / 8) {
+        *reinterpret_cast<uint4*>(c.xs + k8 * 8) = v0[t];
+        if (nb == 2) *reinterpret_cast<uint4*>(c.xs + K + k8 * 8) = v1[t];
+      }
+    }
   }
   csync<NCT, CBAR>();
-  if (ph.norm) {
-    if (nb == 1) rmsnorm_smem<1, NCT, CBAR>(c.xs, K, ph.norm_scale, ph.eps, c.scratch, c.tid);
-    else rmsnorm_smem<2, NCT, CBAR>(c.xs, K, ph.norm_scale, ph.eps, c.scratch, c.tid);
-  }
   if (ph.x_copy_out && blockIdx.x == 0) {
-    for (int i = c.tid; i < nb * (K / 8); i += NCT) {
-      const int n = i / (K / 8), k8 = i % (K / 8);
-      *reinterpret_cast<uint4*>(ph.x_copy_out + (size_t)n * K + k8 * 8) =
-          *reinterpret_cast<const uint4*>(c.xs + (size_t)n * K + k8 * 8);
-    }
+    for (int k8 = c.tid; k8 < nb * (K / 8); k8 += NCT)
+      *reinterpret_cast<uint4*>(ph.x_copy_out + k8 * 8) = *reinterpret_cast<const uint4*>(c.xs + k8 * 8);
   }
 }
 
-__device__ void gemv_phase(const Phase& ph, Ctx& c) {
+__device__ __forceinline__ void gemv_phase(const Phase& ph, Ctx& c, const PfTable& tab) {
   stage_x(ph, c);
+  if (c.trp) c.trp[0] = gtimer();
   if (ph.nb == 1) {
-    switch (ph.R) {
-      case 2: gemv_groups<2, 1>(ph, c); break;
-      case 4: gemv_groups<4, 1>(ph, c); break;
-      case 8: gemv_groups<8, 1>(ph, c); break;
-      default: gemv_groups<16, 1>(ph, c); break;
-    }
+    if (ph.R == 2) gemv_groups<2, 1>(ph, c, tab);
+    else if (ph.R == 4) gemv_groups<4, 1>(ph, c, tab);
+    else if (ph.R == 8) gemv_groups<8, 1>(ph, c, tab);
+    else gemv_groups<16, 1>(ph, c, tab);
   } else {
-    switch (ph.R) {
-      case 2: gemv_groups<2, 2>(ph, c); break;
-      case 4: gemv_groups<4, 2>(ph, c); break;
-      case 8: gemv_groups<8, 2>(ph, c); break;
-      default: gemv_groups<16, 2>(ph, c); break;
-    }
+    if (ph.R == 2) gemv_groups<2, 2>(ph, c, tab);
+    else if (ph.R == 4) gemv_groups<4, 2>(ph, c, tab);
+    else if (ph.R == 8) gemv_groups<8, 2>(ph, c, tab);
+    else gemv_groups<16, 2>(ph, c, tab);
   }
 }
 
 // backbone attention: CTA h < heads owns q-head h over keys [0 .. slot]
-__device__ void attn_phase(const Phase& ph, Ctx& c) {
+__device__ __noinline__ void attn_phase(const Phase& ph, Ctx& c) {
   const int h = blockIdx.x;
   if (h >= ph.heads) return;
   const int hd = ph.hd;
   int pos, slot;
-  phase_pos(ph, c.P, 0, pos, slot);
+  phase_pos(ph, c, 0, pos, slot);
   const int nkeys = slot + 1;
   const int kvh = h / (ph.heads / ph.kv_heads);
   const bf16* kp = ph.kc + (size_t)kvh * ph.slots * hd;
   const bf16* vp = ph.vc + (size_t)kvh * ph.slots * hd;
-  float* sc = reinterpret_cast<float*>(c.xs);      // [slots] scores (<= 8 KB)
-  float* part = sc + ph.slots;                      // [NCT] partial outputs
-  float* qs = part + NCT;                           // [hd]
+  float* sc = reinterpret_cast<float*>(c.xs);  // [slots] scores (<= 8 KB)
+  float* part = sc + ph.slots;                  // [NCT] partial outputs
+  float* qs = part + NCT;                       // [hd]
   const float scale = 1.0f / sqrtf((float)hd);
   for (int d = c.tid; d < hd; d += NCT) qs[d] = ldcg_bf(ph.q + (size_t)h * hd + d);
   csync<NCT, CBAR>();
@@ -427,7 +592,15 @@ __device__ void attn_phase(const Phase& ph, Ctx& c) {
   const int G = NCT / hd;  // key groups
   const int g = c.tid / hd, d = c.tid % hd;
   float acc = 0.f;
-  for (int j = g; j < nkeys; j += G) acc = fmaf(sc[j], ldcg_bf(vp + (size_t)j * hd + d), acc);
+  int j = g;
+  for (; j + 7 * G < nkeys; j += 8 * G) {  // 8 independent loads in flight
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = ldcg_bf(vp + (size_t)(j + u * G) * hd + d);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc = fmaf(sc[j + u * G], v[u], acc);
+  }
+  for (; j < nkeys; j += G) acc = fmaf(sc[j], ldcg_bf(vp + (size_t)j * hd + d), acc);
   part[c.tid] = acc;
   csync<NCT, CBAR>();
   if (g == 0) {
@@ -436,7 +609,7 @@ __device__ void attn_phase(const Phase& ph, Ctx& c) {
   }
 }
 
-__device__ void embed_phase(const Phase& ph, Ctx& c) {
+__device__ __noinline__ void embed_phase(const Phase& ph, Ctx& c) {
   // one 16-byte unit of h per thread: unit u = cta + ncta * tid
   const FrameParams* P = c.P;
   const int u = blockIdx.x + gridDim.x * c.tid;
@@ -447,13 +620,26 @@ __device__ void embed_phase(const Phase& ph, Ctx& c) {
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int cb = 0; cb <= ph.C; ++cb) {
-    if (!msk[cb]) continue;
-    const bf16* row = (cb < ph.C) ? ph.audio_emb + ((size_t)tok[cb] + (size_t)ph.V * cb) * ph.D
-                                  : ph.text_emb + (size_t)tok[cb] * ph.D;
-    const uint4 v = *reinterpret_cast<const uint4*>(row + u * 8);
-    acc[0] += bflo(v.x); acc[1] += bfhi(v.x); acc[2] += bflo(v.y); acc[3] += bfhi(v.y);
-    acc[4] += bflo(v.z); acc[5] += bfhi(v.z); acc[6] += bflo(v.w); acc[7] += bfhi(v.w);
+  for (int c0 = 0; c0 <= ph.C; c0 += 11) {  // 11 independent gathers in flight, summed in column order
+    uint4 v[11];
+    bool on[11];
+#pragma unroll
+    for (int j = 0; j < 11; ++j) {
+      const int cb = c0 + j;
+      on[j] = cb <= ph.C && msk[cb < ph.C + 1 ? cb : 0] != 0;
+      v[j] = make_uint4(0, 0, 0, 0);
+      if (on[j]) {
+        const bf16* row = (cb < ph.C) ? ph.audio_emb + ((size_t)tok[cb] + (size_t)ph.V * cb) * ph.D
+                                      : ph.text_emb + (size_t)tok[cb] * ph.D;
+        v[j] = *reinterpret_cast<const uint4*>(row + u * 8);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 11; ++j)
+      if (on[j]) {
+        acc[0] += bflo(v[j].x); acc[1] += bfhi(v[j].x); acc[2] += bflo(v[j].y); acc[3] += bfhi(v[j].y);
+        acc[4] += bflo(v[j].z); acc[5] += bfhi(v[j].z); acc[6] += bflo(v[j].w); acc[7] += bfhi(v[j].w);
+      }
   }
   __nv_bfloat162 o[4];
 #pragma unroll
@@ -461,10 +647,10 @@ __device__ void embed_phase(const Phase& ph, Ctx& c) {
   *reinterpret_cast<uint4*>(ph.h_out + u * 8) = *reinterpret_cast<uint4*>(o);
 }
 
-__device__ void sample_phase(const Phase& ph, Ctx& c) {
+__device__ __noinline__ void sample_phase(const Phase& ph, Ctx& c) {
   if (blockIdx.x != 0) return;
   const FrameParams* P = c.P;
-  float* xs = reinterpret_cast<float*>(c.xs);                       // [4096]
+  float* xs = reinterpret_cast<float*>(c.xs);                              // [4096]
   unsigned int* hist = reinterpret_cast<unsigned int*>(xs + SAMPLE_MAXV);  // [256]
   const int V = ph.V, C = ph.C, cb = ph.cb;
   if (P->logits_out)
@@ -472,8 +658,10 @@ __device__ void sample_phase(const Phase& ph, Ctx& c) {
         reinterpret_cast<const unsigned short*>(ph.logits) + i));
   const bf16* nz = P->noise ? P->noise + (size_t)cb * V : nullptr;
   const unsigned long long ctr = ((P->offset * (unsigned long long)C + cb)) * 4096ull;
+  if (c.trp) c.trp[0] = gtimer();
   int tok = sample_row<NCT, CBAR, true>(ph.logits, nz, V, P->temperature, P->topk, P->seed, ctr, xs, hist, c.scratch,
                                         c.iscratch, c.tid);
+  if (c.trp) c.trp[1] = gtimer();
   if (c.tid == 0 && P->sampled_out) P->sampled_out[cb] = tok;
   if (P->forced) tok = P->forced[cb];
   if (c.tid == 0) P->out[cb] = tok;
@@ -485,55 +673,72 @@ __device__ void sample_phase(const Phase& ph, Ctx& c) {
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 1)
-k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* __restrict__ P, Sync* sync) {
+__global__ void __launch_bounds__(NCT, 1)
+k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* __restrict__ P, Sync* sync,
+             unsigned long long* __restrict__ trace /* optional [nphases][8] globaltimer ns of CTA 0 */,
+             const __grid_constant__ PfTable tab) {
   extern __shared__ __align__(128) unsigned char smem[];
   bf16* ring = reinterpret_cast<bf16*>(smem);
   bf16* xs = reinterpret_cast<bf16*>(smem + SMEM_RING);
   unsigned char* misc = smem + SMEM_RING + SMEM_X;
-  uint64_t* full = reinterpret_cast<uint64_t*>(misc);           // [NW*SLOTS]
-  uint64_t* empty = full + NW * SLOTS;                           // [NW*SLOTS]
-  float* scratch = reinterpret_cast<float*>(empty + NW * SLOTS);  // [33]
-  int* iscratch = reinterpret_cast<int*>(scratch + 34);           // [36]
+  Phase* phbuf = reinterpret_cast<Phase*>(misc);                           // [2] double buffer
+  uint64_t* full = reinterpret_cast<uint64_t*>(misc + 2 * sizeof(Phase));  // [NW*SLOTS]
+  float* scratch = reinterpret_cast<float*>(full + NW * SLOTS);            // [34]
+  int* iscratch = reinterpret_cast<int*>(scratch + 34);                    // [40]
+  static_assert(2 * sizeof(Phase) + NW * SLOTS * 8 + 34 * 4 + 40 * 4 <= SMEM_MISC, "misc region too small");
+  static_assert(NW <= 32, "block reductions assume <= 32 warps");
+
+  Ctx c;
+  c.P = P; c.trp = nullptr; c.ring = ring; c.xs = xs; c.full = full; c.scratch = scratch; c.iscratch = iscratch;
+  c.sync = sync; c.cnt = 0; c.tid = threadIdx.x; c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NW * SLOTS; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
-    }
+    for (int i = 0; i < NW * SLOTS; ++i) mbar_init(&full[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  constexpr int PH16 = sizeof(Phase) / 16;
+  if (c.tid < PH16) reinterpret_cast<uint4*>(&phbuf[0])[c.tid] = reinterpret_cast<const uint4*>(&phases[0])[c.tid];
+  c.bb_pos = (int)P->pos[P->S - 1];  // batch 1: stream 0, last prompt row
+  c.bb_slot = P->cache_len + P->S - 1;
   __syncthreads();
 
-  if (threadIdx.x >= NCT) {
-    producer(phases, nphases, ring, full, empty, sync);
-    return;
-  }
-  Ctx c;
-  c.P = P; c.ring = ring; c.xs = xs; c.full = full; c.empty = empty; c.scratch = scratch; c.iscratch = iscratch;
-  c.sync = sync; c.cnt = 0; c.tid = threadIdx.x; c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
+  // start this warp's weight stream: SLOTS chunks in flight from now on
+  c.pf.gi = 0; c.pf.i = 0; c.pf.kc = 0; c.pf.issued = 0; c.pf.done = false;
+  c.pf.policy = policy_evict_first();
+  pf_seek(c.pf, tab, blockIdx.x, gridDim.x, c.warp);
+  for (int s = 0; s < SLOTS; ++s) pf_issue(c.pf, tab, ring, full, blockIdx.x, gridDim.x, c.warp, c.lane);
+
   const unsigned ncta = gridDim.x;
+  const bool tr = trace != nullptr && blockIdx.x == 0 && c.tid == 0;
   for (int p = 0; p < nphases; ++p) {
-    const Phase& ph = phases[p];
+    const Phase& ph = phbuf[p & 1];
+    if (tr) {
+      trace[p * 8 + 0] = gtimer();
+      c.trp = trace + p * 8 + 4;
+    }
+    // stage the next descriptor while this phase runs (read after the barrier below)
+    if (p + 1 < nphases && c.tid < PH16)
+      reinterpret_cast<uint4*>(&phbuf[(p + 1) & 1])[c.tid] = reinterpret_cast<const uint4*>(&phases[p + 1])[c.tid];
     switch (ph.type) {
-      case PH_GEMV: gemv_phase(ph, c); break;
+      case PH_GEMV: gemv_phase(ph, c, tab); break;
       case PH_EMBED: embed_phase(ph, c); break;
       case PH_ATTN: attn_phase(ph, c); break;
       default: sample_phase(ph, c); break;
     }
+    if (tr) trace[p * 8 + 1] = gtimer();
     if (p + 1 == nphases) break;
     // grid barrier: every CTA's writes of phase p are visible before anyone starts phase p+1
     csync<NCT, CBAR>();
+    if (tr) trace[p * 8 + 2] = gtimer();
     if (c.tid == 0) {
-      __threadfence();
-      red_release(&sync->counter, 1u);
+      arrive_release(&sync->counter);
       const unsigned target = ncta * (unsigned)(p + 1);
       for (unsigned spin = 0; ld_acquire(&sync->counter) < target; ++spin)
         if (spin > (1u << 24)) die(sync, 0x300);
-      __threadfence();
     }
     csync<NCT, CBAR>();
+    if (tr) trace[p * 8 + 3] = gtimer();
   }
 }
 

@@ -89,6 +89,7 @@ PROTOTYPES = {
     "csm_cache_len": (C.c_int32, [C.c_void_p]),
     "csm_generate_frame": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
                                        C.c_int32, C.POINTER(FrameOpts), C.c_void_p, C.c_void_p]),
+    "csm_debug_set_trace": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "csm_k_sample_topk": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p,
                                       C.c_void_p]),
     "csm_k_embed_frames": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
