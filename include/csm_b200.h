@@ -135,6 +135,43 @@ int32_t csm_generate_frame(csm_ctx *ctx, const int64_t *tokens, const uint8_t *t
                            const int64_t *input_pos, int32_t B, int32_t S, float temperature, int32_t topk,
                            const csm_frame_opts *opts, int32_t *out, void *stream);
 
+/* ---- Mimi codec decode --------------------------------------------------------------------- */
+
+/* Replaces moshi's ``MimiModel.decode`` as the reference calls it through
+ * ``Generator._audio_tokenizer.decode`` (sesameai/generator.py:116,299; tts_service.py:245):
+ * codes int64 [B, K<=32, T] -> waveform fp32 [B, 1, 1920*T] at 24 kHz.  All weights are fp32 device
+ * pointers in moshi's own tensor layouts, passed as one flat array indexed by MIMI_W_*:
+ *   CODEBOOK0 + 2k     quantizer.rvq_{first|rest}...layers[..]._codebook.embedding_sum [2048,256]
+ *   CODEBOOK0 + 2k + 1 ... .cluster_usage [2048]            (k = 0 semantic, 1..31 acoustic)
+ *   RVQ_FIRST_PROJ / RVQ_REST_PROJ   output_proj.weight [512,256,1]
+ *   UPSAMPLE           upsample ConvTranspose1d weight [512,1,4] (depthwise, stride 2)
+ *   LAYER0 + 10*l + {0 in_proj_weight [1536,512], 1 out_proj.weight, 2 norm1.weight, 3 norm1.bias,
+ *                    4 norm2.weight, 5 norm2.bias, 6 linear1.weight [2048,512], 7 linear2.weight
+ *                    [512,2048], 8 layer_scale_1.scale, 9 layer_scale_2.scale}
+ *   CONV0 (+1 bias)    SEANet decoder model.0 Conv1d [1024,512,7]
+ *   STAGE0 + 6*s + {0 convtr.weight [C, C/2, 2r], 1 convtr.bias, 2 block.1 conv weight [C/4, C/2, 3],
+ *                   3 its bias, 4 block.3 conv weight [C/2, C/4, 1], 5 its bias}, r = 8,6,5,4
+ *   FINAL (+1 bias)    last Conv1d [1,64,3] */
+enum {
+  MIMI_W_CODEBOOK0 = 0,
+  MIMI_W_RVQ_FIRST_PROJ = 64,
+  MIMI_W_RVQ_REST_PROJ = 65,
+  MIMI_W_UPSAMPLE = 66,
+  MIMI_W_LAYER0 = 67,
+  MIMI_W_CONV0 = 147,
+  MIMI_W_STAGE0 = 149,
+  MIMI_W_FINAL = 173,
+  MIMI_W_COUNT = 175
+};
+typedef struct mimi_ctx mimi_ctx;
+size_t mimi_workspace_bytes(int32_t max_frames);
+/* Packs the weights (embedding = embedding_sum / clamp(cluster_usage), tap-major conv matrices)
+ * into ``workspace`` on ``stream`` and synchronises that stream once. */
+int32_t mimi_create(const void *const *weights, int32_t n_weights, int32_t max_frames, void *workspace,
+                    size_t workspace_bytes, void *stream, mimi_ctx **out);
+int32_t mimi_decode(mimi_ctx *ctx, const int64_t *codes, int32_t B, int32_t K, int32_t T, float *out, void *stream);
+void mimi_destroy(mimi_ctx *ctx);
+
 /* Profiling aid: dev uint64 [n_phases][8] buffer that CTA 0 of the decode megakernel fills with
  * %globaltimer stamps (phase start, work done, CTA synced, grid barrier passed, 4 phase-specific
  * marks); NULL disables.

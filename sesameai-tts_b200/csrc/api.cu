@@ -28,6 +28,10 @@ static unsigned long long g_launches = 0;
 #define COUNT_LAUNCH() (++g_launches)
 extern "C" uint64_t csm_launch_count(void) { return g_launches; }
 
+// shared with mimi_api.cu
+int csm_set_error(int code, const char* msg) { return set_err(code, "%s", msg); }
+void csm_count_launches(unsigned long long n) { g_launches += n; }
+
 extern "C" int32_t csm_abi_version(void) { return CSM_B200_ABI_VERSION; }
 extern "C" const char* csm_last_error(void) { return g_err; }
 

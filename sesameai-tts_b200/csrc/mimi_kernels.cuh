@@ -1,0 +1,294 @@
+// Mimi codec decode kernels (fp32, moshi 0.2.2 semantics).
+//
+// Layout: every activation is TIME-MAJOR [rows, channels] fp32 with zeroed pad rows in front, so
+//   * a causal Conv1d(k) is a plain GEMM: row t of the im2col matrix is the contiguous slice
+//     x[(t-k+1) .. t] (k*Cin floats, row stride Cin -> overlapping rows), weights packed [Cout][k][Cin];
+//   * a causal ConvTranspose1d(kernel 2s, stride s) is a plain GEMM with K = 2*Cin (rows x[q-1], x[q])
+//     and N = s*Cout: output row q holds the s upsampled time steps back to back, which IS the
+//     time-major layout of the upsampled sequence (the k-s trimmed samples are never computed);
+//   * ELU is applied when the A operand is staged, bias / GELU / LayerScale / residual in the epilogue.
+// Round 1: the GEMM is a shared-memory tiled CUDA-core SGEMM; the tcgen05 tf32 pipeline replaces it next.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mimi {
+
+enum { F_A_ELU = 1, F_GELU = 2, F_RESID = 4, F_LAYERSCALE = 8 };
+
+struct GemmArgs {
+  const float* A;
+  long long lda;
+  const float* B;  // [N, K] row-major
+  float* C;
+  long long ldc;
+  int M, N, K;
+  const float* bias;  // bias[n % bias_period] or null
+  int bias_period;
+  const float* R;  // residual [M, ldr] (may alias C)
+  long long ldr;
+  const float* scale;  // LayerScale [N]
+  int flags;
+};
+
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+__global__ void __launch_bounds__(256) k_sgemm(GemmArgs g) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int lr = tid >> 2, lc = (tid & 3) * 4;  // loader: row 0..63, k offset 0,4,8,12
+  const int ty = tid >> 4, tx = tid & 15;       // compute: 4x4 micro tile
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const bool a_ok = m0 + lr < g.M, b_ok = n0 + lr < g.N;
+  const float* ap = g.A + (long long)(m0 + lr) * g.lda + lc;
+  const float* bp = g.B + (long long)(n0 + lr) * g.K + lc;
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (a_ok) a = *reinterpret_cast<const float4*>(ap + k0);
+    if (b_ok) b = *reinterpret_cast<const float4*>(bp + k0);
+    if (g.flags & F_A_ELU) {
+      a.x = elu1(a.x); a.y = elu1(a.y); a.z = elu1(a.z); a.w = elu1(a.w);
+    }
+    __syncthreads();
+    As[lc + 0][lr] = a.x; As[lc + 1][lr] = a.y; As[lc + 2][lr] = a.z; As[lc + 3][lr] = a.w;
+    Bs[lc + 0][lr] = b.x; Bs[lc + 1][lr] = b.y; Bs[lc + 2][lr] = b.z; Bs[lc + 3][lr] = b.w;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.N) continue;
+      float v = acc[i][j];
+      if (g.bias) v += g.bias[n % g.bias_period];
+      if (g.flags & F_GELU) v = gelu_erf(v);
+      if (g.flags & F_LAYERSCALE) v *= g.scale[n];
+      if (g.flags & F_RESID) v += g.R[(long long)m * g.ldr + n];
+      g.C[(long long)m * g.ldc + n] = v;
+    }
+  }
+}
+
+// split-RVQ lookup: q[t] = [ sum over semantic codebooks | sum over acoustic codebooks ]  (2 x 256)
+// embedding = embedding_sum / clamp(cluster_usage, 1e-5) is precomputed at create time.
+__global__ void k_rvq_gather(const int64_t* __restrict__ codes /*[K, T] of this utterance*/, int K, int T,
+                             const float* __restrict__ emb /*[32][2048][256]*/, float* __restrict__ out /*[T, 512]*/) {
+  const int t = blockIdx.x;
+  const int d = threadIdx.x;  // 256 threads
+  float first = 0.f, rest = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const long long code = codes[(long long)k * T + t];
+    const float v = emb[((long long)k * 2048 + code) * 256 + d];
+    if (k == 0) first += v;
+    else rest += v;
+  }
+  out[(long long)t * 512 + d] = first;
+  out[(long long)t * 512 + 256 + d] = rest;
+}
+
+// depthwise ConvTranspose1d(k=4, s=2, groups=C), causal (trim 2 on the right):
+// y[2q + r][c] = x[q][c] * w[c][r] + x[q-1][c] * w[c][r+2]
+__global__ void k_upsample2(const float* __restrict__ x /*[T, C]*/, const float* __restrict__ w /*[C][4]*/, int T, int C,
+                            float* __restrict__ y /*[2T, C]*/) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)2 * T * C) return;
+  const int c = i % C;
+  const long long o = i / C;
+  const long long q = o >> 1;
+  const int r = o & 1;
+  float v = x[q * C + c] * w[c * 4 + r];
+  if (q > 0) v += x[(q - 1) * C + c] * w[c * 4 + r + 2];
+  y[i] = v;
+}
+
+// LayerNorm over 512 channels, one warp per row
+__global__ void __launch_bounds__(256) k_layernorm512(const float* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ b, int rows, float eps,
+                                                      float* __restrict__ y) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (long long)row * 512);
+  float4 v[4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / 512.0f);
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    var += a * a + bb * bb + c * c + d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float inv = rsqrtf(var * (1.0f / 512.0f) + eps);
+  float4* yr = reinterpret_cast<float4*>(y + (long long)row * 512);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 ww = reinterpret_cast<const float4*>(w)[lane + 32 * i];
+    const float4 bb = reinterpret_cast<const float4*>(b)[lane + 32 * i];
+    float4 o;
+    o.x = (v[i].x - mean) * inv * ww.x + bb.x;
+    o.y = (v[i].y - mean) * inv * ww.y + bb.y;
+    o.z = (v[i].z - mean) * inv * ww.z + bb.z;
+    o.w = (v[i].w - mean) * inv * ww.w + bb.w;
+    yr[lane + 32 * i] = o;
+  }
+}
+
+// interleaved RoPE (moshi apply_rope, max_period 10000) in place on the q and k thirds of qkv [L, 1536]
+__global__ void k_rope_qk(float* __restrict__ qkv, int L) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // (t, which, head, pair)
+  if (i >= (long long)L * 2 * 8 * 32) return;
+  const int pair = i & 31;
+  const int head = (i >> 5) & 7;
+  const int which = (i >> 8) & 1;
+  const long long t = i >> 9;
+  const float freq = expf((float)pair * (-9.210340371976184f * 2.0f / 64.0f));  // ln(10000)
+  float sn, cs;
+  sincosf(freq * (float)t, &sn, &cs);
+  float* p = qkv + t * 1536 + which * 512 + head * 64 + pair * 2;
+  const float xr = p[0], xi = p[1];
+  p[0] = xr * cs - xi * sn;
+  p[1] = xr * sn + xi * cs;
+}
+
+// causal attention with a `context`-key window; one warp per (query, head); qkv [L, 1536] -> out [L, 512]
+__global__ void __launch_bounds__(128) k_attn_window(const float* __restrict__ qkv, int L, int context,
+                                                     float* __restrict__ out) {
+  const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int h = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  if (t >= L) return;
+  const float scale = 0.125f;  // 1/sqrt(64)
+  float q[64];
+  {
+    const float4* qp = reinterpret_cast<const float4*>(qkv + (long long)t * 1536 + h * 64);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4 v = qp[i];
+      q[4 * i] = v.x; q[4 * i + 1] = v.y; q[4 * i + 2] = v.z; q[4 * i + 3] = v.w;
+    }
+  }
+  const int j0 = t - context + 1 > 0 ? t - context + 1 : 0;
+  float m = -INFINITY, l = 0.f, o0 = 0.f, o1 = 0.f;
+  for (int c0 = j0; c0 <= t; c0 += 32) {
+    const int key = c0 + lane;
+    float s = -INFINITY;
+    if (key <= t) {
+      const float4* kp = reinterpret_cast<const float4*>(qkv + (long long)key * 1536 + 512 + h * 64);
+      float a = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float4 v = kp[i];
+        a = fmaf(q[4 * i], v.x, a); a = fmaf(q[4 * i + 1], v.y, a);
+        a = fmaf(q[4 * i + 2], v.z, a); a = fmaf(q[4 * i + 3], v.w, a);
+      }
+      s = a * scale;
+    }
+    float cm = s;
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, of));
+    const float mn = fmaxf(m, cm);
+    const float corr = expf(m - mn);
+    const float e = key <= t ? expf(s - mn) : 0.f;
+    float cs = e;
+#pragma unroll
+    for (int of = 16; of > 0; of >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, of);
+    l = l * corr + cs;
+    o0 *= corr;
+    o1 *= corr;
+    const int nk = t - c0 + 1 < 32 ? t - c0 + 1 : 32;
+    for (int jj = 0; jj < nk; ++jj) {
+      const float p = __shfl_sync(0xffffffffu, e, jj);
+      const float2 v = *reinterpret_cast<const float2*>(qkv + (long long)(c0 + jj) * 1536 + 1024 + h * 64 + lane * 2);
+      o0 = fmaf(p, v.x, o0);
+      o1 = fmaf(p, v.y, o1);
+    }
+    m = mn;
+  }
+  const float inv = 1.0f / l;
+  *reinterpret_cast<float2*>(out + (long long)t * 512 + h * 64 + lane * 2) = make_float2(o0 * inv, o1 * inv);
+}
+
+// final causal conv 64 -> 1, k = 3, with the ELU on its input: one thread per output sample
+__global__ void k_final_conv(const float* __restrict__ x /*[L, 64], 2 zero pad rows in front*/, const float* __restrict__ w
+                             /*[3][64] tap-major*/, float bias, long long L, float* __restrict__ y) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= L) return;
+  const float4* xp = reinterpret_cast<const float4*>(x + (t - 2) * 64);
+  const float4* wp = reinterpret_cast<const float4*>(w);
+  float a = bias;
+#pragma unroll 8
+  for (int i = 0; i < 48; ++i) {
+    const float4 v = xp[i], ww = wp[i];
+    a = fmaf(elu1(v.x), ww.x, a); a = fmaf(elu1(v.y), ww.y, a);
+    a = fmaf(elu1(v.z), ww.z, a); a = fmaf(elu1(v.w), ww.w, a);
+  }
+  y[t] = a;
+}
+
+// ---- weight packing (create time) ---------------------------------------------------------------
+__global__ void k_pack_embedding(const float* __restrict__ esum, const float* __restrict__ usage, float* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // [2048][256]
+  if (i >= 2048LL * 256) return;
+  out[i] = esum[i] / fmaxf(usage[i >> 8], 1e-5f);
+}
+// Conv1d weight [Cout][Cin][k] -> [Cout][k][Cin]
+__global__ void k_pack_conv(const float* __restrict__ w, int Cout, int Cin, int k, float* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)Cout * Cin * k) return;
+  const int ci = i % Cin;
+  const int kk = (i / Cin) % k;
+  const long long co = i / ((long long)Cin * k);
+  out[i] = w[(co * Cin + ci) * k + kk];
+}
+// ConvTranspose1d weight [Cin][Cout][2s] -> B[n = r*Cout + co][K = (x[q-1] taps r+s | x[q] taps r)]
+__global__ void k_pack_convtr(const float* __restrict__ w, int Cin, int Cout, int s, float* __restrict__ out) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long total = (long long)s * Cout * 2 * Cin;
+  if (i >= total) return;
+  const int kidx = i % (2 * Cin);
+  const long long n = i / (2 * Cin);
+  const int co = n % Cout, r = n / Cout;
+  const int ci = kidx % Cin;
+  const int tap = kidx < Cin ? r + s : r;
+  out[i] = w[((long long)ci * Cout + co) * (2 * s) + tap];
+}
+// [Wf | Wr]: out[n][0..255] = Wf[n][:], out[n][256..511] = Wr[n][:]   (1x1 convs [512][256][1])
+__global__ void k_pack_rvq_proj(const float* __restrict__ wf, const float* __restrict__ wr, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 512 * 512) return;
+  const int n = i / 512, k = i % 512;
+  out[i] = k < 256 ? wf[n * 256 + k] : wr[n * 256 + k - 256];
+}
+
+}  // namespace mimi

@@ -221,3 +221,35 @@ def named_tiny_flavors() -> Dict[str, Dict[str, int]]:
         "tiny-bb": dict(num_layers=2, num_heads=4, num_kv_heads=2, embed_dim=256, intermediate_dim=512),
         "tiny-dec": dict(num_layers=2, num_heads=2, num_kv_heads=1, embed_dim=256, intermediate_dim=512),
     }
+
+
+@torch.no_grad()
+def init_mimi_weights(codec: torch.nn.Module, seed: int = 2024) -> None:
+    """Seeded random init for a Mimi codec state dict (moshi key names; works on the oracle and on
+    the product codec).  Codebooks are non-zero (moshi's defaults give all-zero embeddings), layer
+    scales are O(0.3) so the transformer visibly contributes, conv/linear weights U(+-1/sqrt(fan_in))."""
+    for name, p in sorted(codec.state_dict().items()):
+        sid = _stream_id(name)
+        if name.endswith("_initialized"):
+            p.fill_(1.0)
+        elif name.endswith("cluster_usage"):
+            hash_uniform_(p, seed, sid, 0.5)
+            p.add_(1.5)
+        elif name.endswith("embedding_sum"):
+            hash_uniform_(p, seed, sid, 1.5)
+        elif name.endswith("layer_scale_1.scale") or name.endswith("layer_scale_2.scale"):
+            hash_uniform_(p, seed, sid, 0.3)
+        elif ".norm1." in name or ".norm2." in name:
+            hash_uniform_(p, seed, sid, 0.1)
+            if name.endswith("weight"):
+                p.add_(1.0)
+        elif name.endswith("bias"):
+            hash_uniform_(p, seed, sid, 0.05)
+        elif p.dim() >= 2:
+            if "convtr" in name and "upsample" not in name:  # ConvTranspose1d [in, out, k]: fan_in = in * k / stride(=k/2)
+                fan_in = p.shape[0] * 2
+            else:
+                fan_in = p[0].numel()
+            hash_uniform_(p, seed, sid, (3.0 / fan_in) ** 0.5)
+        else:  # pragma: no cover
+            hash_uniform_(p, seed, sid, 0.02)

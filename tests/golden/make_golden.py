@@ -200,9 +200,37 @@ def main():
     elif what == "csm1b":
         greedy_case(mod, ("llama-1B", "llama-100M"), 128_256, 1, 24, 64, os.path.join(HERE, "csm1b_greedy.pt"))
         teacher_case(mod, ("llama-1B", "llama-100M"), 128_256, 1, 24, 3, 0.9, 50, os.path.join(HERE, "csm1b_teacher.pt"))
+    elif what == "mimi":
+        return
     else:
-        raise SystemExit("usage: make_golden.py [tiny|csm1b]")
+        raise SystemExit("usage: make_golden.py [tiny|csm1b|teacher|mimi]")
 
 
 if __name__ == "__main__":
     main()
+
+
+@torch.inference_mode()
+def mimi_case(out_path):
+    """Mimi decode golden: the waveform the independent ``transformers`` MimiModel port produces
+    from the seeded synthetic codec weights (moshi itself is not installable offline)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import mimi_oracle as mo
+    from test_mimi_oracle_pin_hf import map_to_hf, tf_mimi
+    from transformers import MimiConfig
+
+    om = mo.OracleMimi().eval()
+    syn.init_mimi_weights(om, 2024)
+    cfg = MimiConfig()
+    cfg._attn_implementation = "eager"
+    hf = tf_mimi.MimiModel(cfg).eval()
+    map_to_hf(om, hf)
+    B, T = 2, 20
+    codes = syn.hash_ints(B * 32 * T, 7, T, 2048).view(B, 32, T)
+    wav = hf.decode(codes)[0]
+    torch.save(dict(weight_seed=2024, B=B, T=T, code_seed=7, wav=wav.float()), out_path)
+    print(f"{out_path}: {tuple(wav.shape)}")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "mimi":
+    mimi_case(os.path.join(HERE, "mimi_decode.pt"))

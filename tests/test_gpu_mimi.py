@@ -1,0 +1,68 @@
+"""Mimi decode on the B200 vs the oracle / the golden waveform (north_star: SNR >= 40 dB)."""
+import math
+
+import pytest
+import torch
+
+import mimi_oracle as mo
+from sesameai import synthetic as syn
+from sesameai.mimi import MimiCodec
+from helpers import load_golden
+
+pytestmark = pytest.mark.gpu
+SNR_MIN_DB = 40.0  # north_star gate; an fp32 CUDA-core path lands far above it
+
+
+def snr_db(want, got):
+    return 10 * math.log10(want.double().pow(2).sum().item() / max((got.double() - want.double()).pow(2).sum().item(), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def codecs():
+    om = mo.OracleMimi().eval()
+    syn.init_mimi_weights(om, 2024)
+    pc = MimiCodec(max_frames=160)
+    pc.load_state_dict(om.state_dict())
+    pc.to("cuda")
+    return om, pc
+
+
+def test_state_dict_keys_match_oracle(codecs):
+    om, pc = codecs
+    assert sorted(om.state_dict()) == sorted(pc.state_dict())
+
+
+def test_decode_matches_golden_waveform(codecs):
+    _, pc = codecs
+    g = load_golden("mimi_decode.pt")
+    codes = syn.hash_ints(g["B"] * 32 * g["T"], g["code_seed"], g["T"], 2048).view(g["B"], 32, g["T"])
+    got = pc.decode(codes.cuda()).cpu()
+    assert got.shape == g["wav"].shape
+    assert snr_db(g["wav"], got) >= SNR_MIN_DB + 20
+
+
+@pytest.mark.parametrize("B,K,T", [(1, 32, 1), (3, 32, 7), (1, 8, 5), (1, 32, 140)])
+def test_decode_matches_oracle(codecs, B, K, T):
+    """edge cases: a single frame, ragged batch, fewer codebooks, > context-250 transformer positions"""
+    om, pc = codecs
+    codes = syn.hash_ints(B * K * T, 11, T + K, 2048).view(B, K, T)
+    with torch.inference_mode():
+        want = om.decode(codes)
+    got = pc.decode(codes.cuda()).cpu()
+    assert got.shape == (B, 1, 1920 * T)
+    assert snr_db(want, got) >= SNR_MIN_DB + 20, snr_db(want, got)
+
+
+def test_decode_is_chunk_additive_in_batch(codecs):
+    """size-independent property: decoding a batch equals decoding each utterance alone"""
+    _, pc = codecs
+    codes = syn.hash_ints(4 * 32 * 9, 3, 3, 2048).view(4, 32, 9).cuda()
+    full = pc.decode(codes)
+    for b in range(4):
+        assert torch.equal(full[b], pc.decode(codes[b : b + 1])[0])
+
+
+def test_too_many_frames_is_an_error(codecs):
+    _, pc = codecs
+    with pytest.raises(RuntimeError):
+        pc.decode(torch.zeros(1, 32, 161, dtype=torch.long, device="cuda"))

@@ -1,0 +1,89 @@
+"""Pin the Mimi decode oracle (restated moshi 0.2.2 semantics) against the independent
+``transformers`` MimiModel port in fp32: same waveform from the same weights (HF uses rotate-half
+RoPE, so q/k projection rows are permuted when mapping)."""
+import pytest
+import torch
+
+import mimi_oracle as mo
+from sesameai import synthetic as syn
+
+tf_mimi = pytest.importorskip("transformers.models.mimi.modeling_mimi")
+from transformers import MimiConfig  # noqa: E402
+
+
+def _to_rotate_half(w, heads):
+    out, inp = w.shape
+    return w.view(heads, out // heads // 2, 2, inp).transpose(1, 2).reshape(out, inp)
+
+
+def map_to_hf(om: mo.OracleMimi, hf) -> None:
+    sd = om.state_dict()
+    with torch.no_grad():
+        for name, rvq in (("semantic", "rvq_first"), ("acoustic", "rvq_rest")):
+            h = getattr(hf.quantizer, f"{name}_residual_vector_quantizer")
+            for k, layer in enumerate(h.layers):
+                layer.codebook.embed_sum.copy_(sd[f"quantizer.{rvq}.vq.layers.{k}._codebook.embedding_sum"])
+                layer.codebook.cluster_usage.copy_(sd[f"quantizer.{rvq}.vq.layers.{k}._codebook.cluster_usage"])
+                layer.codebook._embed = None
+            h.output_proj.weight.copy_(sd[f"quantizer.{rvq}.output_proj.weight"])
+        hf.upsample.conv.weight.copy_(sd["upsample.convtr.convtr.convtr.weight"])
+        for l, layer in enumerate(hf.decoder_transformer.layers):
+            pre = f"decoder_transformer.transformer.layers.{l}."
+            w = sd[pre + "self_attn.in_proj_weight"]
+            layer.self_attn.q_proj.weight.copy_(_to_rotate_half(w[:512], 8))
+            layer.self_attn.k_proj.weight.copy_(_to_rotate_half(w[512:1024], 8))
+            layer.self_attn.v_proj.weight.copy_(w[1024:])
+            layer.self_attn.o_proj.weight.copy_(sd[pre + "self_attn.out_proj.weight"])
+            layer.input_layernorm.weight.copy_(sd[pre + "norm1.weight"])
+            layer.input_layernorm.bias.copy_(sd[pre + "norm1.bias"])
+            layer.post_attention_layernorm.weight.copy_(sd[pre + "norm2.weight"])
+            layer.post_attention_layernorm.bias.copy_(sd[pre + "norm2.bias"])
+            layer.mlp.fc1.weight.copy_(sd[pre + "linear1.weight"])
+            layer.mlp.fc2.weight.copy_(sd[pre + "linear2.weight"])
+            layer.self_attn_layer_scale.scale.copy_(sd[pre + "layer_scale_1.scale"])
+            layer.mlp_layer_scale.scale.copy_(sd[pre + "layer_scale_2.scale"])
+        for i, m in enumerate(hf.decoder.layers):
+            pre = f"decoder.model.{i}."
+            if isinstance(m, tf_mimi.MimiConv1d):
+                m.conv.weight.copy_(sd[pre + "conv.conv.weight"])
+                m.conv.bias.copy_(sd[pre + "conv.conv.bias"])
+            elif isinstance(m, tf_mimi.MimiConvTranspose1d):
+                m.conv.weight.copy_(sd[pre + "convtr.convtr.weight"])
+                m.conv.bias.copy_(sd[pre + "convtr.convtr.bias"])
+            elif isinstance(m, tf_mimi.MimiResnetBlock):
+                for j in (1, 3):
+                    m.block[j].conv.weight.copy_(sd[pre + f"block.{j}.conv.conv.weight"])
+                    m.block[j].conv.bias.copy_(sd[pre + f"block.{j}.conv.conv.bias"])
+
+
+@pytest.fixture(scope="module")
+def pair():
+    om = mo.OracleMimi().eval()
+    syn.init_mimi_weights(om, 2024)
+    cfg = MimiConfig()
+    cfg._attn_implementation = "eager"
+    hf = tf_mimi.MimiModel(cfg).eval()
+    map_to_hf(om, hf)
+    return om, hf
+
+
+@torch.inference_mode()
+@pytest.mark.parametrize("B,T", [(1, 3), (2, 17), (1, 140)])  # 140 frames -> 280 transformer positions > context 250
+def test_decode_matches_hf_port(pair, B, T):
+    om, hf = pair
+    codes = syn.hash_ints(B * 32 * T, 7, T, 2048).view(B, 32, T)
+    want = hf.decode(codes)[0]
+    got = om.decode(codes)
+    assert got.shape == want.shape == (B, 1, 1920 * T)
+    err = (got - want).abs().max().item()
+    scale = want.abs().max().item()
+    assert err <= 2e-4 * max(scale, 1.0), (err, scale)
+    snr = 10 * torch.log10(want.pow(2).sum() / (got - want).pow(2).sum()).item()
+    assert snr > 80, snr
+
+
+@torch.inference_mode()
+def test_output_length_and_fewer_codebooks(pair):
+    om, _ = pair
+    codes = syn.hash_ints(1 * 8 * 5, 1, 2, 2048).view(1, 8, 5)
+    assert om.decode(codes).shape == (1, 1, 9600)
