@@ -99,7 +99,8 @@ __global__ void k_rvq_gather(const int64_t* __restrict__ codes /*[K, T] of this 
   const int d = threadIdx.x;  // 256 threads
   float first = 0.f, rest = 0.f;
   for (int k = 0; k < K; ++k) {
-    const long long code = codes[(long long)k * T + t];
+    long long code = codes[(long long)k * T + t];
+    code = code < 0 ? 0 : (code > 2047 ? 2047 : code);  // memory safety: the reference would raise on these
     const float v = emb[((long long)k * 2048 + code) * 256 + d];
     if (k == 0) first += v;
     else rest += v;
