@@ -191,6 +191,13 @@ int32_t csm_k_embed_frames(const int64_t *tokens, const uint8_t *mask, const voi
 /* y[N, out] = bf16(x[N, in] @ W[out, in]^T), x/W/y bf16 (nn.Linear without bias). */
 int32_t csm_k_linear(const void *x, const void *W, int32_t N, int32_t in, int32_t out, void *y, void *stream);
 
+/* Tensor-core path of the same op (TMA + tcgen05.mma + TMEM accumulator), used for prompt prefill:
+ * y[N, out] = bf16(x @ W^T); epi 1 adds ``resid`` [N, out] (bf16(y) + resid, like h + linear(...));
+ * epi 2 treats output columns as interleaved (gate_i, up_i) pairs and writes
+ * bf16(bf16(silu(gate)) * up) into y[N, out/2].  ``in`` must be a multiple of 64. */
+int32_t csm_k_gemm_tc(const void *x, const void *W, int32_t N, int32_t in, int32_t out, void *y, int32_t epi,
+                      const void *resid, void *stream);
+
 /* torchtune RMSNorm: bf16(bf16(x * rsqrt(mean x^2 + eps)) * scale), [N, D]. */
 int32_t csm_k_rmsnorm(const void *x, const void *scale, int32_t N, int32_t D, float eps, void *y, void *stream);
 

@@ -10,6 +10,7 @@
 #include "../../include/csm_b200.h"
 #include "lm_kernels.cuh"
 #include "mega.cuh"
+#include "gemm_tc.cuh"
 
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -600,6 +601,62 @@ extern "C" int32_t csm_debug_set_trace(csm_ctx* x, void* dev_buffer) {
   if (!x) return set_err(CSM_ERR_ARG, "null ctx");
   x->trace = (unsigned long long*)dev_buffer;
   return x->mega_ok ? x->n_phases : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 GEMM launcher: Y[rows, n_out] = X[rows, K] . W[n_out, K]^T  (gemm_tc.cuh)
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static encode_tiled_fn get_encode_tiled() {
+  static encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (encode_tiled_fn)p;
+  }
+  return fn;
+}
+static int make_map_bf16(CUtensorMap* m, const bf16* base, long long rows, long long K, long long ld, int box_rows) {
+  encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) return set_err(CSM_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(CSM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  return CSM_OK;
+}
+static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const bf16* W, int n_out, bf16* out, long long ldo,
+                          int epi, const bf16* resid, cudaStream_t st) {
+  if (K % tc::BK || rows < 1 || n_out < 1) return set_err(CSM_ERR_ARG, "gemm_tc: K must be a multiple of 64");
+  static bool attr = false;
+  if (!attr) {
+    CU_TRY(cudaFuncSetAttribute(tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
+    attr = true;
+  }
+  CUtensorMap mx, mw;
+  int rc;
+  if ((rc = make_map_bf16(&mx, X, rows, K, ldx, tc::BM)) != CSM_OK) return rc;
+  if ((rc = make_map_bf16(&mw, W, n_out, K, K, tc::BN)) != CSM_OK) return rc;
+  tc::Args a;
+  a.out = out; a.ldo = ldo; a.resid = resid ? resid : out; a.rows = rows; a.n_out = n_out; a.K = K; a.epi = epi;
+  dim3 grid((n_out + tc::BN - 1) / tc::BN, (rows + tc::BM - 1) / tc::BM);
+  tc::k_gemm_tc<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mx, mw, a); COUNT_LAUNCH();
+  CU_TRY(cudaGetLastError());
+  return CSM_OK;
+}
+
+extern "C" int32_t csm_k_gemm_tc(const void* xin, const void* W, int32_t N, int32_t in, int32_t outf, void* y, int32_t epi,
+                                 const void* resid, void* stream) {
+  if (!xin || !W || !y || N < 1 || in % 64 || outf < 1 || epi < 0 || epi > 2) return set_err(CSM_ERR_ARG, "bad gemm_tc arguments");
+  const long long ldo = epi == tc::EPI_SWIGLU_PAIRS ? outf / 2 : outf;
+  return launch_gemm_tc((const bf16*)xin, in, N, in, (const bf16*)W, outf, (bf16*)y, ldo, epi, (const bf16*)resid,
+                        (cudaStream_t)stream);
 }
 
 // ---- unit-test entry points -----------------------------------------------------------------

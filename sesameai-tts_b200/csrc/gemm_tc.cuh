@@ -1,0 +1,223 @@
+// Dense bf16 GEMM on the 5th-generation tensor cores: Y[rows, out] = X[rows, K] . W[out, K]^T
+// (both operands K-major, fp32 accumulation in TMEM, bf16 result), for the places where the hot
+// path is a real contraction: prompt prefill and batched decode.
+//
+//   warp 0      TMA producer  : cp.async.bulk.tensor.2d (128B swizzle) of a 128 x 64 X tile and a
+//                               128 x 64 W tile per stage into a 6-deep shared-memory ring
+//   warp 1      MMA issuer    : one elected lane issues tcgen05.mma.cta_group::1.kind::f16
+//                               (M128 x N128 x K16, 4 per stage) into a 128-column TMEM accumulator;
+//                               tcgen05.commit releases the stage / signals the epilogue
+//   warps 2..5  epilogue      : tcgen05.ld (32 lanes x 32 columns per warp per step) -> registers ->
+//                               fused epilogue (bf16 round, + residual, SwiGLU on interleaved
+//                               gate/up columns) -> global
+// One output tile per CTA; grid = (out/128, rows/128) -- for prefill that is thousands of CTAs,
+// several waves over the 148 SMs.  Every wait is trip-capped and traps instead of hanging.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 64, STAGES = 6;
+constexpr int UMMA_K = 16;
+constexpr int THREADS = 192;
+constexpr uint32_t STAGE_BYTES = (BM + BN) * BK * 2;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+enum { EPI_STORE = 0, EPI_ADD_RESID = 1, EPI_SWIGLU_PAIRS = 2 };
+
+struct Args {
+  bf16* out;
+  long long ldo;
+  const bf16* resid;  // EPI_ADD_RESID: [rows, ldo] (may alias out)
+  int rows, n_out, K;
+  int epi;
+};
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int c) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(c));
+}
+__device__ __forceinline__ void mbar_expect(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(s32(b)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  for (unsigned spin = 0; !mbar_try(b, parity); ++spin)
+    if (spin > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          s32(dst)),
+      "l"(map), "r"(s32(bar)), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+// shared-memory matrix descriptor: K-major tile, 128-byte swizzle, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t smem_desc(const void* p) {
+  uint64_t d = 0;
+  d |= (uint64_t)((s32(p) & 0x3FFFF) >> 4);  // start address
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset
+  d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, N and M of the tile
+__device__ __forceinline__ uint32_t instr_desc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, Args a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const int num_kb = a.K / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+  }
+  if (warp == 1) {  // one warp allocates the accumulator columns (and frees them at the end)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "n"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
+        unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
+        unsigned char* sb = sa + BM * BK * 2;
+        mbar_expect(&full[s], STAGE_BYTES);
+        tma_load_2d(sa, &map_x, &full[s], kb * BK, m0);
+        tma_load_2d(sb, &map_w, &full[s], kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(BM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(&full[s], (kb / STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
+        const unsigned char* sb = sa + BM * BK * 2;
+        const uint64_t ad = smem_desc(sa), bd = smem_desc(sb);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k)  // +32 bytes along K inside the 128-byte swizzle atom
+          umma(tmem_base, ad + (uint64_t)(k * UMMA_K * 2 >> 4), bd + (uint64_t)(k * UMMA_K * 2 >> 4), idesc, (kb | k) != 0);
+        umma_commit(&empty[s]);  // frees the stage once these MMAs have read it
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // epilogue: warp w may touch TMEM lanes [32*(w%4), +32) -> output rows m0 + that range
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    mbar_wait(acc_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < a.rows) {
+        const int n = n0 + c0;
+        if (a.epi == EPI_SWIGLU_PAIRS) {
+          // columns (2i, 2i+1) = (gate_i, up_i): bf16( bf16(silu(bf16 gate)) * bf16 up )
+          bf16* o = a.out + (long long)row * a.ldo + (n >> 1);
+#pragma unroll
+          for (int j = 0; j < 32; j += 2)
+            if (n + j + 1 < a.n_out) o[j >> 1] = f2bf(silu_bf(rbf(__uint_as_float(v[j]))) * rbf(__uint_as_float(v[j + 1])));
+        } else {
+          bf16* o = a.out + (long long)row * a.ldo + n;
+          const bf16* r = a.resid + (long long)row * a.ldo + n;
+          if (n + 32 <= a.n_out && (a.ldo & 7) == 0) {  // 4 x 16-byte stores
+#pragma unroll
+            for (int j8 = 0; j8 < 32; j8 += 8) {
+              uint4 rv = make_uint4(0, 0, 0, 0);
+              if (a.epi == EPI_ADD_RESID) rv = *reinterpret_cast<const uint4*>(r + j8);
+              const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+              __nv_bfloat162 pk[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                float y0 = rbf(__uint_as_float(v[j8 + 2 * t])), y1 = rbf(__uint_as_float(v[j8 + 2 * t + 1]));
+                if (a.epi == EPI_ADD_RESID) {
+                  y0 += bflo(rr[t]);
+                  y1 += bfhi(rr[t]);
+                }
+                pk[t] = __floats2bfloat162_rn(y0, y1);
+              }
+              *reinterpret_cast<uint4*>(o + j8) = *reinterpret_cast<uint4*>(pk);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (n + j >= a.n_out) break;
+              float y = rbf(__uint_as_float(v[j]));
+              if (a.epi == EPI_ADD_RESID) y += bf2f(r[j]);
+              o[j] = f2bf(y);
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+
+}  // namespace tc
