@@ -113,7 +113,14 @@ typedef struct csm_frame_opts {
   void *logits_out;       /* dev bf16 [codebooks, B, audio_vocab] raw head outputs, or NULL                */
   int32_t *sampled_out;   /* dev [B, codebooks] sampled tokens before forcing, or NULL                     */
   int32_t path;           /* CSM_PATH_*: which launch strategy runs the last prompt row + frame tail          */
+  int32_t prefill;        /* CSM_PREFILL_*: how prompt rows [0, S-1) are processed                            */
 } csm_frame_opts;
+
+enum {
+  CSM_PREFILL_AUTO = 0,      /* tensor cores when B*(S-1) >= 64 rows, else the small-row kernels */
+  CSM_PREFILL_SMALL_ROW = 1, /* GEMV-style kernels, 8 frames per stream per pass                 */
+  CSM_PREFILL_TENSOR = 2     /* TMA + tcgen05 GEMMs over up to 4096 rows per pass                */
+};
 
 enum {
   CSM_PATH_AUTO = 0,   /* batch 1: persistent megakernel; otherwise the captured per-op CUDA graph */

@@ -37,7 +37,9 @@ extern "C" int32_t csm_abi_version(void) { return CSM_B200_ABI_VERSION; }
 extern "C" const char* csm_last_error(void) { return g_err; }
 
 // ---------------------------------------------------------------------------------------------
-static const int PREFILL_CHUNK = 8;  // prompt frames per stream per small-row pass
+static const int PREFILL_CHUNK = 8;     // prompt frames per stream per small-row pass
+static const int PREFILL_TC_ROWS = 4096;  // rows per tensor-core prefill pass
+static const int PREFILL_TC_MIN = 64;     // prompt rows (B * (S-1)) from which the tcgen05 path is used
 
 struct StackDev {
   csm_stack_config c;
@@ -51,6 +53,7 @@ struct StackDev {
   size_t kv_layer_stride;
   // activations
   bf16 *h, *q, *att, *act;
+  bf16 *xn, *qkv;  // tensor-core prefill only (backbone)
 };
 
 struct csm_ctx {
@@ -127,9 +130,11 @@ static void carve_stack(Carver& cv, StackDev& s, const csm_stack_config& c, int 
 static size_t carve_all(csm_ctx* x, char* base) {
   Carver cv{base, 0};
   const csm_config& c = x->cfg;
-  x->max_rows = x->max_batch * PREFILL_CHUNK;
+  x->max_rows = x->max_batch * PREFILL_CHUNK > PREFILL_TC_ROWS ? x->max_batch * PREFILL_CHUNK : PREFILL_TC_ROWS;
   x->Vp = (c.audio_vocab + 7) & ~7;
   carve_stack(cv, x->bb, c.backbone, c.max_seq_len, x->max_batch, x->max_rows);
+  x->bb.xn = cv.take<bf16>((size_t)x->max_rows * c.backbone.dim);
+  x->bb.qkv = cv.take<bf16>((size_t)x->max_rows * (c.backbone.heads + 2 * c.backbone.kv_heads) * (c.backbone.dim / c.backbone.heads));
   carve_stack(cv, x->dec, c.decoder, c.codebooks, x->max_batch, 2 * x->max_batch);
   x->head_t = cv.take<bf16>((size_t)(c.codebooks - 1) * x->Vp * c.decoder.dim);
   x->dec_in = cv.take<bf16>((size_t)2 * x->max_batch * c.backbone.dim);
@@ -544,6 +549,8 @@ static int get_graph(csm_ctx* x, int B, cudaGraphExec_t* out) {
   return CSM_OK;
 }
 
+static int backbone_pass_tc(csm_ctx* x, int B, int chunk, cudaStream_t st);
+
 extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const uint8_t* tokens_mask,
                                       const int64_t* input_pos, int32_t B, int32_t S, float temperature, int32_t topk,
                                       const csm_frame_opts* opts, int32_t* out, void* stream) {
@@ -565,13 +572,23 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
   }
   if (path == CSM_PATH_AUTO) path = (B == 1 && x->mega_ok) ? CSM_PATH_MEGA : CSM_PATH_GRAPH;
   if (path == CSM_PATH_MEGA && (B != 1 || !x->mega_ok)) return set_err(CSM_ERR_ARG, "megakernel path needs batch 1");
-  // prompt rows [0, S-1): small-row passes of up to PREFILL_CHUNK frames per stream
-  for (int s0 = 0; s0 < S - 1; s0 += PREFILL_CHUNK) {
-    const int chunk = (S - 1 - s0) < PREFILL_CHUNK ? (S - 1 - s0) : PREFILL_CHUNK;
+  // prompt rows [0, S-1): tensor-core passes when there is a real contraction (>= 64 rows), else
+  // small-row passes of up to PREFILL_CHUNK frames per stream
+  int prefill_path = opts ? opts->prefill : 0;
+  if (prefill_path == CSM_PREFILL_AUTO)
+    prefill_path = ((long long)B * (S - 1) >= PREFILL_TC_MIN && x->cfg.backbone.dim % 64 == 0) ? CSM_PREFILL_TENSOR : CSM_PREFILL_SMALL_ROW;
+  const int per_pass = prefill_path == CSM_PREFILL_TENSOR ? (PREFILL_TC_ROWS / B > 0 ? PREFILL_TC_ROWS / B : 1) : PREFILL_CHUNK;
+  for (int s0 = 0; s0 < S - 1; s0 += per_pass) {
+    const int chunk = (S - 1 - s0) < per_pass ? (S - 1 - s0) : per_pass;
     p.s0 = s0;
     k_set_params<<<1, 1, 0, st>>>(x->d_params, p); COUNT_LAUNCH();
     CU_TRY(cudaGetLastError());
-    CU_TRY(backbone_pass(x, B, chunk, st));
+    if (prefill_path == CSM_PREFILL_TENSOR) {
+      int rc = backbone_pass_tc(x, B, chunk, st);
+      if (rc != CSM_OK) return rc;
+    } else {
+      CU_TRY(backbone_pass(x, B, chunk, st));
+    }
   }
   // last row + frame tail: persistent megakernel (batch 1) or the captured per-op graph
   p.s0 = S - 1;
@@ -647,6 +664,48 @@ static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const b
   a.out = out; a.ldo = ldo; a.resid = resid ? resid : out; a.rows = rows; a.n_out = n_out; a.K = K; a.epi = epi;
   dim3 grid((n_out + tc::BN - 1) / tc::BN, (rows + tc::BM - 1) / tc::BM);
   tc::k_gemm_tc<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mx, mw, a); COUNT_LAUNCH();
+  CU_TRY(cudaGetLastError());
+  return CSM_OK;
+}
+
+// Backbone pass over `chunk` prompt frames per stream on the tensor cores (rows n = b*chunk + t):
+// per layer RMSNorm -> GEMM [q;k;v] -> RoPE + KV append -> attention -> GEMM O (+res) -> RMSNorm ->
+// GEMM gate/up (SwiGLU epilogue) -> GEMM down (+res); same rounding points as the small-row path.
+static int backbone_pass_tc(csm_ctx* x, int B, int chunk, cudaStream_t st) {
+  const csm_config& c = x->cfg;
+  const csm_stack_config& k = c.backbone;
+  StackDev& s = x->bb;
+  const int N = B * chunk, D = k.dim, qkv_cols = (k.heads + 2 * k.kv_heads) * s.hd;
+  k_embed_pass<<<N, 256, 0, st>>>(x->d_params, x->text_emb, x->audio_emb, c.codebooks, c.audio_vocab, D, chunk, s.h,
+                                  x->row_stream, x->row_pos, x->row_slot); COUNT_LAUNCH();
+  CU_TRY(cudaGetLastError());
+  int rc;
+  for (int l = 0; l < k.layers; ++l) {
+    bf16* kc = s.kc + s.kv_layer_stride * l;
+    bf16* vc = s.vc + s.kv_layer_stride * l;
+    k_rmsnorm<<<N, 256, 0, st>>>(s.h, D, s.sa[l], D, c.norm_eps, s.xn, D); COUNT_LAUNCH();
+    if ((rc = launch_gemm_tc(s.xn, D, N, D, s.wqkv[l], qkv_cols, s.qkv, qkv_cols, tc::EPI_STORE, nullptr, st)) != CSM_OK) return rc;
+    k_rope_kv_rows<<<N, 256, 0, st>>>(s.qkv, s.rope, x->row_stream, x->row_pos, x->row_slot, k.heads, k.kv_heads, s.hd, s.slots,
+                                      s.q, kc, vc); COUNT_LAUNCH();
+    {
+      dim3 grid(N, k.heads);
+      const size_t smem = (size_t)s.slots * sizeof(float);
+      const float scale = 1.0f / sqrtf((float)s.hd);
+      if (s.hd == 64) {
+        k_attn_rows<64><<<grid, 128, smem, st>>>(s.q, kc, vc, x->row_stream, x->row_slot, 0, 0, k.heads, k.kv_heads, s.slots,
+                                                 scale, s.att);
+      } else {
+        k_attn_rows<128><<<grid, 128, smem, st>>>(s.q, kc, vc, x->row_stream, x->row_slot, 0, 0, k.heads, k.kv_heads, s.slots,
+                                                  scale, s.att);
+      }
+      COUNT_LAUNCH();
+    }
+    CU_TRY(cudaGetLastError());
+    if ((rc = launch_gemm_tc(s.att, D, N, D, s.wo[l], D, s.h, D, tc::EPI_ADD_RESID, s.h, st)) != CSM_OK) return rc;
+    k_rmsnorm<<<N, 256, 0, st>>>(s.h, D, s.mlp[l], D, c.norm_eps, s.xn, D); COUNT_LAUNCH();
+    if ((rc = launch_gemm_tc(s.xn, D, N, D, s.wgu[l], 2 * k.ff, s.act, k.ff, tc::EPI_SWIGLU_PAIRS, nullptr, st)) != CSM_OK) return rc;
+    if ((rc = launch_gemm_tc(s.act, k.ff, N, k.ff, s.wd[l], D, s.h, D, tc::EPI_ADD_RESID, s.h, st)) != CSM_OK) return rc;
+  }
   CU_TRY(cudaGetLastError());
   return CSM_OK;
 }

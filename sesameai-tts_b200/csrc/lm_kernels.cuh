@@ -327,6 +327,44 @@ __global__ void __launch_bounds__(128) k_attn_rows(const bf16* __restrict__ q, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row-batched RoPE + KV append for the tensor-core prefill path: qkv [N, (H+2KV)*hd] (GEMM output,
+// already rounded to bf16) -> rotated q [N, H*hd], rotated k and v into the cache at the row's slot.
+// Same arithmetic as the EPI_ROPE_KV epilogue.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rope_kv_rows(const bf16* __restrict__ qkv, const bf16* __restrict__ rope,
+                                                      const int* __restrict__ row_stream, const int* __restrict__ row_pos,
+                                                      const int* __restrict__ row_slot, int heads, int kv_heads, int hd,
+                                                      int slots, bf16* __restrict__ q_out, bf16* __restrict__ k_cache,
+                                                      bf16* __restrict__ v_cache) {
+  const int n = blockIdx.x;
+  const int qrows = heads * hd, krows = kv_heads * hd, total = qrows + 2 * krows;
+  const bf16* src = qkv + (size_t)n * total;
+  const int pos = row_pos[n], slot = row_slot[n], stream = row_stream[n];
+  for (int p = threadIdx.x; p < total / 2; p += blockDim.x) {
+    const int r0 = 2 * p;
+    const __nv_bfloat162 in = *reinterpret_cast<const __nv_bfloat162*>(src + r0);
+    const float y0 = __low2float(in), y1 = __high2float(in);
+    float o0 = y0, o1 = y1;
+    if (r0 < qrows + krows) {
+      const __nv_bfloat162 cs = *reinterpret_cast<const __nv_bfloat162*>(rope + ((size_t)pos * (hd / 2) + ((r0 % hd) >> 1)) * 2);
+      const float c = __low2float(cs), s = __high2float(cs);
+      o0 = rbf(__fsub_rn(__fmul_rn(y0, c), __fmul_rn(y1, s)));
+      o1 = rbf(__fadd_rn(__fmul_rn(y1, c), __fmul_rn(y0, s)));
+    }
+    const __nv_bfloat162 out = __floats2bfloat162_rn(o0, o1);
+    if (r0 < qrows) {
+      *reinterpret_cast<__nv_bfloat162*>(q_out + (size_t)n * qrows + r0) = out;
+    } else {
+      const bool isk = r0 < qrows + krows;
+      const int rr = r0 - (isk ? qrows : qrows + krows);
+      const int kvh = rr / hd, d = rr % hd;
+      bf16* dst = (isk ? k_cache : v_cache) + (((size_t)stream * kv_heads + kvh) * slots + slot) * hd + d;
+      *reinterpret_cast<__nv_bfloat162*>(dst) = out;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stand-alone RMSNorm (final norm of a stack): one CTA per row.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_rmsnorm(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ scale,

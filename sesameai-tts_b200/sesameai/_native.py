@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libcsm_b200.so")
 
 MIMI_W_CODEBOOK0, MIMI_W_RVQ_FIRST_PROJ, MIMI_W_RVQ_REST_PROJ, MIMI_W_UPSAMPLE = 0, 64, 65, 66
 MIMI_W_LAYER0, MIMI_W_CONV0, MIMI_W_STAGE0, MIMI_W_FINAL, MIMI_W_COUNT = 67, 147, 149, 173, 175
+PREFILL_AUTO, PREFILL_SMALL_ROW, PREFILL_TENSOR = 0, 1, 2
 PATH_AUTO, PATH_DIRECT, PATH_GRAPH, PATH_MEGA = 0, 1, 2, 3
 CSM_OK, CSM_ERR_ARG, CSM_ERR_CUDA, CSM_ERR_STATE, CSM_ERR_OVERFLOW, CSM_ERR_WORKSPACE = 0, -1, -2, -3, -4, -5
 
@@ -66,6 +67,7 @@ class FrameOpts(C.Structure):
         ("logits_out", C.c_void_p),
         ("sampled_out", C.c_void_p),
         ("path", C.c_int32),
+        ("prefill", C.c_int32),
     ]
 
 

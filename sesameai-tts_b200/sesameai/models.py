@@ -265,7 +265,7 @@ class Model(
                        temperature: float, topk: int, *, noise: Optional[torch.Tensor] = None,
                        forced: Optional[torch.Tensor] = None, logits_out: Optional[torch.Tensor] = None,
                        sampled_out: Optional[torch.Tensor] = None, no_graph: bool = False,
-                       path: int = 0) -> torch.Tensor:
+                       path: int = 0, prefill: int = 0) -> torch.Tensor:
         """(B, S, 33) tokens/mask + (B, S) positions -> (B, 32) int32 codes, like the reference
         (``models.py:132-184``).  Keyword extras are for parity tests: shared Exp(1) ``noise``
         [32, B, V] bf16, teacher-``forced`` tokens [B, 32] int32, raw ``logits_out`` [32, B, V]."""
@@ -302,6 +302,7 @@ class Model(
             assert sampled_out.is_contiguous() and sampled_out.dtype == torch.int32
             opts.sampled_out = sampled_out.data_ptr()
         opts.path = _native.PATH_DIRECT if no_graph else int(path)
+        opts.prefill = int(prefill)
         self._frame_counter += 1
         with torch.cuda.device(dev):
             rc = _native.lib().csm_generate_frame(

@@ -163,3 +163,58 @@ def test_megakernel_matches_per_op_path_tiny():
             assert torch.equal(s.cpu(), want[i]), (path, i)
             assert torch.isfinite(lg.float()).all()
             t, m, p = next_inputs(s, p)
+
+
+def test_tensor_core_prefill_matches_small_row_path_and_oracle():
+    """A 300-frame context prompt (2 streams): the TMA + tcgen05 prefill and the GEMV-style prefill
+    must lead to the same frames, and to the oracle's logits within bf16 noise."""
+    from sesameai import _native
+
+    gold = dict(model_args=dict(backbone_flavor="tiny-bb", decoder_flavor="tiny-dec", text_vocab_size=1000,
+                                audio_vocab_size=2051, audio_num_codebooks=32),
+                weight_seed=31, planted=False, batch=2)
+    om, _ = build_oracle(gold)
+    pm, _ = build_product(gold)
+    tok, msk, pos = syn.voice_prompt(2, 3, 20, 70, 30, seed=5, text_vocab=1000)
+    assert tok.shape[1] == 300
+    noise = syn.exp_noise(32, 2, 2051, 8)
+    om.reset_caches()
+    rec = {}
+    with torch.inference_mode():
+        want = om.generate_frame(tok, msk, pos, 0.9, 50, noise=noise, record=rec)
+    want_logits = torch.stack(rec["logits"]).float()
+    outs = {}
+    for mode in (_native.PREFILL_TENSOR, _native.PREFILL_SMALL_ROW):
+        pm.reset_caches()
+        lg = torch.zeros(32, 2, 2051, dtype=torch.bfloat16, device="cuda")
+        s = pm.generate_frame(tok.cuda(), msk.cuda(), pos.cuda(), 0.9, 50, noise=noise.cuda(), forced=want, logits_out=lg,
+                              prefill=mode)
+        assert torch.equal(s.cpu(), want)
+        err = (lg.cpu().float() - want_logits).abs()
+        assert err.flatten().kthvalue(int(0.9999 * err.numel())).values.item() <= LOGIT_ATOL, mode
+        assert err.max().item() <= LOGIT_ATOL_MAX, mode
+        outs[mode] = lg.cpu().float()
+    assert (outs[_native.PREFILL_TENSOR] - outs[_native.PREFILL_SMALL_ROW]).abs().max().item() <= LOGIT_ATOL_MAX
+
+
+def test_csm1b_long_prompt_prefill_runs_on_tensor_cores():
+    """Full-size model, 600-frame prompt: tensor-core prefill agrees with the small-row prefill."""
+    from sesameai import _native
+
+    gold = load_golden("csm1b_teacher.pt")
+    pm, _ = build_product(gold)
+    tok, msk, pos = syn.voice_prompt(1, 2, 40, 240, 40, seed=9)
+    assert tok.shape[1] == 600
+    noise = syn.exp_noise(32, 1, 2051, 4).cuda()
+    res = {}
+    for mode in (_native.PREFILL_TENSOR, _native.PREFILL_SMALL_ROW):
+        pm.reset_caches()
+        lg = torch.zeros(32, 1, 2051, dtype=torch.bfloat16, device="cuda")
+        forced = res[_native.PREFILL_TENSOR][0] if res else None
+        s = pm.generate_frame(tok.cuda(), msk.cuda(), pos.cuda(), 0.9, 50, noise=noise, logits_out=lg, prefill=mode,
+                              forced=forced)
+        res[mode] = (s.clone(), lg.float().cpu())
+    a, b = res[_native.PREFILL_TENSOR][1], res[_native.PREFILL_SMALL_ROW][1]
+    err = (a - b).abs()
+    assert err.flatten().kthvalue(int(0.9999 * err.numel())).values.item() <= LOGIT_ATOL
+    assert torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0).item() >= COS_MIN
