@@ -386,7 +386,7 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
   x->mega_ok = false;
   x->trace = nullptr;
   // fused small attention needs <= 32 cached keys; scores of the backbone attention sit in the 32 KB x buffer
-  if (x->cfg.codebooks > 32 || x->cfg.max_seq_len * 4 + (mega::NCT + 128) * 4 > (int)mega::SMEM_X) return CSM_OK;
+  if (x->cfg.codebooks > 32 || x->cfg.max_seq_len * 4 + (mega::NCT + 128) * 4 > 32768) return CSM_OK;
   if (x->dec.hd != 128 || 2 * x->cfg.decoder.dim > 2048 || x->cfg.decoder.kv_heads > 2) return CSM_OK;  // fused attention layout
   if (x->cfg.backbone.dim > 8 * mega::NCT || x->cfg.decoder.dim > 8 * mega::NCT) return CSM_OK;  // one norm unit per thread
   int dev = 0, sms = 0, coop = 0, occ = 0;

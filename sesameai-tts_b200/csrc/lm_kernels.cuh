@@ -465,13 +465,29 @@ __device__ int sample_row(const bf16* __restrict__ logits, const bf16* __restric
   }
   float mx = -INFINITY;
   const float inv_t = 1.0f / temperature;
-  for (int i = tid; i < V; i += NT) {
-    const bf16 lg = CG ? __ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(logits) + i)) : logits[i];
-    const bf16 xb = f2bf(bf2f(lg) * inv_t);
-    const float xv = bf2f(xb);
-    xs[i] = xv;
-    mx = fmaxf(mx, xv);
-    if (!greedy) atomicAdd(&hist[bf_key(xb) >> 8], 1u);
+  {
+    // all of this thread's logits are requested before any is used: one L2 round trip, not V/NT
+    constexpr int MAXPT = SAMPLE_MAXV / NT;
+    unsigned short raw[MAXPT];
+#pragma unroll
+    for (int t = 0; t < MAXPT; ++t) {
+      const int i = tid + t * NT;
+      raw[t] = 0;
+      if (i < V)
+        raw[t] = CG ? __ldcg(reinterpret_cast<const unsigned short*>(logits) + i)
+                    : reinterpret_cast<const unsigned short*>(logits)[i];
+    }
+#pragma unroll
+    for (int t = 0; t < MAXPT; ++t) {
+      const int i = tid + t * NT;
+      if (i < V) {
+        const bf16 xb = f2bf(bf2f(__ushort_as_bfloat16(raw[t])) * inv_t);
+        const float xv = bf2f(xb);
+        xs[i] = xv;
+        mx = fmaxf(mx, xv);
+        if (!greedy) atomicAdd(&hist[bf_key(xb) >> 8], 1u);
+      }
+    }
   }
   mx = block_max<NT, BAR>(mx, scratch, tid);  // (its barriers also publish xs[] and hist[])
   // 2. threshold = k-th largest value: exact 16-bit radix select (top-1 is just the max)

@@ -36,7 +36,7 @@ constexpr int SLOTS = MEGA_SLOTS;     // ring slots per warp
 constexpr int CHUNK_ELEMS = MEGA_CHUNK;  // bf16 per slot
 constexpr int KC_MAX = CHUNK_ELEMS / 2;  // k-extent of a chunk (a chunk holds >= 2 rows)
 constexpr int MAXNB = 2;              // activation rows per phase (depth step 1 carries 2)
-constexpr int XBUF_ELEMS = MAXNB * 8192;
+constexpr int XBUF_ELEMS = 2 * MAXNB * 8192;  // 64 KB: activation rows, or the fused attention's q / K / V staging
 constexpr int CBAR = 0;               // all threads are consumers: plain CTA barrier
 constexpr int MAX_GEMV = 640;         // rows of the prefetch table (kernel parameter space)
 constexpr size_t SMEM_RING = (size_t)NW * SLOTS * CHUNK_ELEMS * 2;
@@ -225,6 +225,10 @@ struct Ctx {
   unsigned long long* trp;  // fine-grained trace slots of the current phase (CTA 0, thread 0) or null
   int tid, warp, lane;
   int bb_pos, bb_slot;  // RoPE position / cache slot of the backbone row of this frame
+  // operands of the CURRENT phase that were fetched while the previous grid barrier was spinning
+  uint4 pre_scale;   // this thread's 16-byte unit of the RMSNorm scale
+  float pre_a, pre_b;  // epilogue operands of this lane's pair in the warp's first row group
+  bool pre_valid;
 };
 
 __device__ __forceinline__ void phase_pos(const Phase& ph, const Ctx& c, int n, int& pos, int& slot) {
@@ -309,7 +313,12 @@ __device__ __noinline__ void gemv_groups(const Phase& ph, Ctx& c, const PfTable&
     const bool epi_lane = c.lane < (R / 2) * NB;
     EpiPre pre;
     pre.a = pre.b = 0.f;
-    if (epi_lane) pre = epilogue_prefetch(ph, c, g * R + 2 * my_pr, my_n);
+    if (i == 0 && c.pre_valid) {
+      pre.a = c.pre_a;
+      pre.b = c.pre_b;
+    } else if (epi_lane) {
+      pre = epilogue_prefetch(ph, c, g * R + 2 * my_pr, my_n);
+    }
     float acc[R][NB];
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -355,55 +364,62 @@ __device__ __noinline__ void gemv_groups(const Phase& ph, Ctx& c, const PfTable&
       const int r0 = g * R + 2 * my_pr;
       if (r0 < ph.rows && my_n < ph.nb) epilogue(ph, c, r0, my_n, y0, y1, pre);
     }
+    if (c.trp && i == 0 && !ph.attn_prologue) c.trp[3] = gtimer();
   }
 }
 
 // Attention over <= 32 cached keys for every (row, head), redundantly in every CTA, straight into
 // the activation buffer of the output projection (depth decoder: 32 slots per stream, head_dim 128).
 //   xs layout (bf16 elements): [0, nb*dim) output rows | [2048, +nb*dim) q | [4096, +kv*keys*136) K
-//   rows padded to 136 (conflict-free 16-byte reads with lane == key) | partial scores (fp32).
-//   A warp owns (row, head, half of the head dims): partial q.k over its 64 dims with lane == key,
-//   halves summed through shared memory, softmax by shuffles, then P.V for its 64 output dims with
-//   lane == 2 dims.  The V loads are issued first so their L2 round trip overlaps everything else.
-__device__ __noinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
-  constexpr int HD = 128, KS = HD + 8, QOFF = 2048, KOFF = 4096;
-  const int heads = ph.heads, kvn = ph.kv_heads, grp = heads / kvn, nb = ph.nb;
-  const int nkmax = ph.pos0 + nb;  // keys visible to the last row
-  float* part = reinterpret_cast<float*>(c.xs + KOFF + kvn * 32 * KS);  // [nb*heads][2][32]
-  const int nitems = nb * heads * 2;
-  // V for this warp's first item: 32 x 4-byte loads in flight from here on
-  uint32_t vreg[32];
-  {
-    const int item = c.warp < nitems ? c.warp : 0;
-    const int n = item / (heads * 2), h = (item >> 1) % heads, half = item & 1, kvh = h / grp;
-    const int nkeys = ph.pos0 + n + 1;
-    const bf16* vp = ph.vc + (size_t)kvh * ph.slots * HD + half * 64 + c.lane * 2;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) vreg[j] = __ldcg(reinterpret_cast<const uint32_t*>(vp + (j < nkeys ? j : 0) * HD));
+//   rows padded to 136 (conflict-free 16-byte reads with lane == key) | [12800, +kv*32*128) V |
+//   partial scores (fp32).
+// Two parts.  attn_prefetch runs while the PREVIOUS phase's grid barrier is still spinning: the K/V
+// rows of earlier positions are final, so they are copied into shared memory with cp.async there and
+// their (loaded) L2 latency disappears behind the barrier.  attn_small_into_x then only fetches q and
+// the current position's K/V rows, and computes out of shared memory: a warp owns (row, head, half of
+// the head dims): partial q.k over its 64 dims with lane == key, halves summed through shared
+// memory, softmax by shuffles, P.V for its 64 output dims with lane == 2 dims.
+constexpr int A_HD = 128, A_KS = A_HD + 8, A_QOFF = 2048, A_KOFF = 4096, A_VOFF = A_KOFF + 2 * 32 * A_KS;
+constexpr int A_PARTOFF = A_VOFF + 2 * 32 * A_HD;
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+__device__ __forceinline__ void attn_prefetch(const Phase& ph, Ctx& c) {
+  const int kvn = ph.kv_heads, nold = ph.pos0;  // positions [0, pos0) were written in earlier steps
+  const int units = kvn * nold * (A_HD / 8);
+  for (int u = c.tid; u < 2 * units; u += NCT) {
+    const bool isv = u >= units;
+    const int ku = isv ? u - units : u, row = ku >> 4, i = ku & 15;
+    const int kvh = row / nold, j = row - kvh * nold;
+    const bf16* src = (isv ? ph.vc : ph.kc) + (kvh * ph.slots + j) * A_HD + i * 8;
+    bf16* dst = isv ? c.xs + A_VOFF + (kvh * 32 + j) * A_HD + i * 8 : c.xs + A_KOFF + (kvh * 32 + j) * A_KS + i * 8;
+    cp_async16(dst, src);
   }
-  {  // stage q and the K rows with 16-byte loads
-    const int qunits = nb * heads * (HD / 8), kunits = kvn * nkmax * (HD / 8), total = qunits + kunits;
-    constexpr int MAXIT = (2 * 8 * 16 + 2 * 32 * 16 + NCT - 1) / NCT;  // nb<=2, heads<=8, kv<=2, keys<=32
-    uint4 v[MAXIT];
-    int dst[MAXIT];
-#pragma unroll
-    for (int t = 0; t < MAXIT; ++t) {
-      const int u = c.tid + t * NCT;
-      dst[t] = -1;
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__device__ __noinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
+  const int heads = ph.heads, kvn = ph.kv_heads, grp = heads / kvn, nb = ph.nb;
+  float* part = reinterpret_cast<float*>(c.xs + A_PARTOFF);  // [nb*heads*2][32]
+  const int nitems = nb * heads * 2;
+  {  // q rows and the K/V rows of the positions written by the phase that just finished
+    const int qunits = nb * heads * (A_HD / 8), kunits = kvn * nb * (A_HD / 8), total = qunits + 2 * kunits;
+    for (int u = c.tid; u < total; u += NCT) {
       if (u < qunits) {
-        v[t] = ldcg16(ph.q + u * 8);
-        dst[t] = QOFF + u * 8;
-      } else if (u < total) {
-        const int ku = u - qunits, row = ku >> 4, i = ku & 15;
-        const int kvh = row / nkmax, j = row - kvh * nkmax;
-        v[t] = ldcg16(ph.kc + (kvh * ph.slots + j) * HD + i * 8);
-        dst[t] = KOFF + row * KS + i * 8;
+        *reinterpret_cast<uint4*>(c.xs + A_QOFF + u * 8) = ldcg16(ph.q + u * 8);
+      } else {
+        const bool isv = u >= qunits + kunits;
+        const int ku = u - qunits - (isv ? kunits : 0), row = ku >> 4, i = ku & 15;
+        const int kvh = row / nb, j = ph.pos0 + row - kvh * nb;
+        const uint4 v = ldcg16((isv ? ph.vc : ph.kc) + (kvh * ph.slots + j) * A_HD + i * 8);
+        if (isv) *reinterpret_cast<uint4*>(c.xs + A_VOFF + (kvh * 32 + j) * A_HD + i * 8) = v;
+        else *reinterpret_cast<uint4*>(c.xs + A_KOFF + (kvh * 32 + j) * A_KS + i * 8) = v;
       }
     }
-#pragma unroll
-    for (int t = 0; t < MAXIT; ++t)
-      if (dst[t] >= 0) *reinterpret_cast<uint4*>(c.xs + dst[t]) = v[t];
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   csync<NCT, CBAR>();
   if (c.trp) c.trp[1] = gtimer();
   const float scale = 0.08838834764831845f;  // 1/sqrt(128)
@@ -413,43 +429,44 @@ __device__ __noinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
       const int n = item / (heads * 2), h = (item >> 1) % heads, half = item & 1, kvh = h / grp;
       const int nkeys = ph.pos0 + n + 1;
       const bool own = c.lane < nkeys;
-      const bf16* kr = c.xs + KOFF + (kvh * nkmax + (own ? c.lane : 0)) * KS + half * 64;
-      const bf16* qr = c.xs + QOFF + (n * heads + h) * HD + half * 64;
-      float a = 0.f;
+      const bf16* kr = c.xs + A_KOFF + (kvh * 32 + (own ? c.lane : 0)) * A_KS + half * 64;
+      const bf16* qr = c.xs + A_QOFF + (n * heads + h) * A_HD + half * 64;
+      float a0 = 0.f, a1 = 0.f;  // two chains: the dot product is latency, not throughput, bound
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        a = dot8(*reinterpret_cast<const uint4*>(kr + i * 8), *reinterpret_cast<const uint4*>(qr + i * 8), a);
-      part[item * 32 + c.lane] = a;
+      for (int i = 0; i < 8; i += 2) {
+        a0 = dot8(*reinterpret_cast<const uint4*>(kr + i * 8), *reinterpret_cast<const uint4*>(qr + i * 8), a0);
+        a1 = dot8(*reinterpret_cast<const uint4*>(kr + i * 8 + 8), *reinterpret_cast<const uint4*>(qr + i * 8 + 8), a1);
+      }
+      part[item * 32 + c.lane] = a0 + a1;
     }
-    csync<NCT, CBAR>();
-    if (c.trp && it0 == 0) c.trp[2] = gtimer();
+  }
+  csync<NCT, CBAR>();
+  if (c.trp) c.trp[2] = gtimer();
+  for (int it0 = 0; it0 < nitems; it0 += NW) {
+    const int item = it0 + c.warp;
     if (item < nitems) {
-      const int n = item / (heads * 2), h = (item >> 1) % heads, half = item & 1;
+      const int n = item / (heads * 2), h = (item >> 1) % heads, half = item & 1, kvh = h / grp;
       const int nkeys = ph.pos0 + n + 1;
       const bool own = c.lane < nkeys;
       const float sc = own ? (part[(item & ~1) * 32 + c.lane] + part[(item | 1) * 32 + c.lane]) * scale : -INFINITY;
       const float mx = warp_max(sc);
       const float e = own ? expf(sc - mx) : 0.f;
       const float inv = 1.0f / warp_sum(e);
-      if (it0 > 0) {  // later items (nb == 2): their V rows were not prefetched
-        const int kvh = h / grp;
-        const bf16* vp = ph.vc + (size_t)kvh * ph.slots * HD + half * 64 + c.lane * 2;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) vreg[j] = __ldcg(reinterpret_cast<const uint32_t*>(vp + (j < nkeys ? j : 0) * HD));
-      }
-      float o0 = 0.f, o1 = 0.f;
+      const bf16* vp = c.xs + A_VOFF + kvh * 32 * A_HD + half * 64 + c.lane * 2;
+      float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};  // 4 independent chains
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const float pj = __shfl_sync(0xffffffffu, e, j);  // 0 beyond nkeys
-        o0 = fmaf(pj, bflo(vreg[j]), o0);
-        o1 = fmaf(pj, bfhi(vreg[j]), o1);
+        const float pj = __shfl_sync(0xffffffffu, e, j);  // 0 for j >= nkeys
+        const uint32_t v = j < nkeys ? *reinterpret_cast<const uint32_t*>(vp + j * A_HD) : 0u;  // rows past nkeys are stale
+        o0[j & 3] = fmaf(pj, bflo(v), o0[j & 3]);
+        o1[j & 3] = fmaf(pj, bfhi(v), o1[j & 3]);
       }
-      *reinterpret_cast<__nv_bfloat162*>(c.xs + n * ph.K + h * HD + half * 64 + c.lane * 2) =
-          __floats2bfloat162_rn(o0 * inv, o1 * inv);
+      *reinterpret_cast<__nv_bfloat162*>(c.xs + n * ph.K + h * A_HD + half * 64 + c.lane * 2) =
+          __floats2bfloat162_rn(((o0[0] + o0[1]) + (o0[2] + o0[3])) * inv, ((o1[0] + o1[1]) + (o1[2] + o1[3])) * inv);
     }
-    if (c.trp && it0 == 0) c.trp[3] = gtimer();
-    csync<NCT, CBAR>();
   }
+  if (c.trp) c.trp[3] = gtimer();
+  csync<NCT, CBAR>();
 }
 
 __device__ __forceinline__ float sumsq8(const uint4& v) {
@@ -485,7 +502,7 @@ __device__ __noinline__ void stage_x(const Phase& ph, Ctx& c) {
     if (on) {
       x0 = ldcg16(ph.x + k8 * 8);
       if (nb == 2) x1 = ldcg16(ph.x + ph.ldx + k8 * 8);
-      sc = *reinterpret_cast<const uint4*>(ph.norm_scale + k8 * 8);
+      sc = c.pre_valid ? c.pre_scale : *reinterpret_cast<const uint4*>(ph.norm_scale + k8 * 8);
     }
     float s0 = sumsq8(x0), s1 = sumsq8(x1);
     s0 = warp_sum(s0);
@@ -691,6 +708,7 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
   Ctx c;
   c.P = P; c.trp = nullptr; c.ring = ring; c.xs = xs; c.full = full; c.scratch = scratch; c.iscratch = iscratch;
   c.sync = sync; c.cnt = 0; c.tid = threadIdx.x; c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
+  c.pre_valid = false; c.pre_a = c.pre_b = 0.f; c.pre_scale = make_uint4(0, 0, 0, 0);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NW * SLOTS; ++i) mbar_init(&full[i], 1);
@@ -731,8 +749,28 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
     // grid barrier: every CTA's writes of phase p are visible before anyone starts phase p+1
     csync<NCT, CBAR>();
     if (tr) trace[p * 8 + 2] = gtimer();
+    if (c.tid == 0) arrive_release(&sync->counter);
+    {
+      // While the barrier resolves: fetch what phase p+1 needs that is already final -- the norm
+      // scale and the epilogue operands (residual values from two phases ago, RoPE cos/sin) of this
+      // warp's first row group.  Their L2 round trip then overlaps the barrier instead of following it.
+      const Phase& nx = phbuf[(p + 1) & 1];
+      c.pre_valid = false;
+      if (nx.type == PH_GEMV && nx.attn_prologue) attn_prefetch(nx, c);
+      if (nx.type == PH_GEMV) {
+        c.pre_valid = true;
+        if (nx.norm && c.tid < nx.K / 8) c.pre_scale = *reinterpret_cast<const uint4*>(nx.norm_scale + c.tid * 8);
+        const int g = group_of(blockIdx.x, gridDim.x, c.warp, 0);
+        const int hp = nx.R / 2;
+        c.pre_a = c.pre_b = 0.f;
+        if (g < nx.G && c.lane < hp * nx.nb) {
+          const EpiPre e = epilogue_prefetch(nx, c, g * nx.R + 2 * (c.lane % hp), c.lane / hp);
+          c.pre_a = e.a;
+          c.pre_b = e.b;
+        }
+      }
+    }
     if (c.tid == 0) {
-      arrive_release(&sync->counter);
       const unsigned target = ncta * (unsigned)(p + 1);
       for (unsigned spin = 0; ld_acquire(&sync->counter) < target; ++spin)
         if (spin > (1u << 24)) die(sync, 0x300);
