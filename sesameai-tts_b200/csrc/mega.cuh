@@ -303,7 +303,7 @@ __device__ __forceinline__ void epilogue(const Phase& ph, const Ctx& c, int r0, 
 // One warp, one row group (R rows x K) at a time: R*NB accumulators, the group's chunk(s) come from
 // this warp's ring; after the shuffle reduction lane (pair, n) runs that pair's epilogue.
 template <int R, int NB>
-__device__ __noinline__ void gemv_groups(const Phase& ph, Ctx& c, const PfTable& tab) {
+__device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c, const PfTable& tab) {
   const int cta = blockIdx.x, ncta = gridDim.x;
   const int K = ph.K, KC = ph.KC, nkc = K / KC;
   for (int i = 0;; ++i) {
@@ -400,7 +400,7 @@ __device__ __forceinline__ void attn_prefetch(const Phase& ph, Ctx& c) {
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-__device__ __noinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
+__device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
   const int heads = ph.heads, kvn = ph.kv_heads, grp = heads / kvn, nb = ph.nb;
   float* part = reinterpret_cast<float*>(c.xs + A_PARTOFF);  // [nb*heads*2][32]
   const int nitems = nb * heads * 2;
@@ -488,7 +488,7 @@ __device__ __forceinline__ uint4 norm8(const uint4& v, float inv, const uint4& s
 }
 
 // stage the phase's activation rows into shared memory (+ RMSNorm prologue)
-__device__ __noinline__ void stage_x(const Phase& ph, Ctx& c) {
+__device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
   if (ph.attn_prologue) {
     attn_small_into_x(ph, c);
     return;
@@ -566,7 +566,7 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, Ctx& c, const PfTabl
 }
 
 // backbone attention: CTA h < heads owns q-head h over keys [0 .. slot]
-__device__ __noinline__ void attn_phase(const Phase& ph, Ctx& c) {
+__device__ __forceinline__ void attn_phase(const Phase& ph, Ctx& c) {
   const int h = blockIdx.x;
   if (h >= ph.heads) return;
   const int hd = ph.hd;
@@ -626,7 +626,7 @@ __device__ __noinline__ void attn_phase(const Phase& ph, Ctx& c) {
   }
 }
 
-__device__ __noinline__ void embed_phase(const Phase& ph, Ctx& c) {
+__device__ __forceinline__ void embed_phase(const Phase& ph, Ctx& c) {
   // one 16-byte unit of h per thread: unit u = cta + ncta * tid
   const FrameParams* P = c.P;
   const int u = blockIdx.x + gridDim.x * c.tid;
@@ -664,7 +664,7 @@ __device__ __noinline__ void embed_phase(const Phase& ph, Ctx& c) {
   *reinterpret_cast<uint4*>(ph.h_out + u * 8) = *reinterpret_cast<uint4*>(o);
 }
 
-__device__ __noinline__ void sample_phase(const Phase& ph, Ctx& c) {
+__device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
   if (blockIdx.x != 0) return;
   const FrameParams* P = c.P;
   float* xs = reinterpret_cast<float*>(c.xs);                              // [4096]
