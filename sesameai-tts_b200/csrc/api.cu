@@ -403,6 +403,7 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
   for (const mega::Phase& ph : v) {
     if (ph.type != mega::PH_GEMV) continue;
     if (x->pf_table.n >= mega::MAX_GEMV) return CSM_OK;  // too deep for the parameter-space table: per-op path only
+    if (ph.K > mega::KC_MAX && ((ph.G + sms - 1) / sms) * (ph.K / mega::KC_MAX) > mega::MAX_SPLIT_TASKS) return CSM_OK;
     mega::PfDesc& d = x->pf_table.d[x->pf_table.n++];
     d.W = ph.W; d.rows = ph.rows; d.K = ph.K; d.G = ph.G;
   }

@@ -490,6 +490,28 @@ __device__ int sample_row(const bf16* __restrict__ logits, const bf16* __restric
     }
   }
   mx = block_max<NT, BAR>(mx, scratch, tid);  // (its barriers also publish xs[] and hist[])
+  // greedy short cut: topk == 1 with a UNIQUE maximum leaves one survivor, whose probability is
+  // exactly 1 (log_softmax -> 0, softmax -> 1) while every masked entry scores 0: the race cannot
+  // change the winner, so the token is the arg-max.  (Ties at the maximum take the general path:
+  // the reference resolves them by the Exp(1) race)
+  if (greedy) {
+    float cnt = 0.f;
+    int first = -1;
+    for (int i = tid; i < V; i += NT)
+      if (xs[i] == mx) {
+        cnt += 1.f;
+        if (first < 0) first = i;
+      }
+    cnt = block_sum<NT, BAR>(cnt, scratch, tid);
+    if (cnt == 1.f) {
+      if (first >= 0) iscratch[0] = first;
+      csync<NT, BAR>();
+      const int tok = iscratch[0];
+      csync<NT, BAR>();
+      return tok;
+    }
+    csync<NT, BAR>();
+  }
   // 2. threshold = k-th largest value: exact 16-bit radix select (top-1 is just the max)
   float thr = mx;
   if (!greedy) {

@@ -30,18 +30,23 @@ namespace mega {
 #ifndef MEGA_CHUNK
 #define MEGA_CHUNK 4096
 #endif
+#ifndef MEGA_L2_AHEAD
+#define MEGA_L2_AHEAD 0  /* measured: an extra L2 prefetch stage slows the stream (5.15 vs 4.3 ms/frame) */
+#endif
 constexpr int NW = MEGA_NW;           // warps per CTA
 constexpr int NCT = NW * 32;          // threads per CTA
 constexpr int SLOTS = MEGA_SLOTS;     // ring slots per warp
 constexpr int CHUNK_ELEMS = MEGA_CHUNK;  // bf16 per slot
 constexpr int KC_MAX = CHUNK_ELEMS / 2;  // k-extent of a chunk (a chunk holds >= 2 rows)
+constexpr int L2_AHEAD = MEGA_L2_AHEAD;  // chunks per warp that are pulled into L2 ahead of the smem ring
 constexpr int MAXNB = 2;              // activation rows per phase (depth step 1 carries 2)
 constexpr int XBUF_ELEMS = 2 * MAXNB * 8192;  // 64 KB: activation rows, or the fused attention's q / K / V staging
 constexpr int CBAR = 0;               // all threads are consumers: plain CTA barrier
 constexpr int MAX_GEMV = 640;         // rows of the prefetch table (kernel parameter space)
 constexpr size_t SMEM_RING = (size_t)NW * SLOTS * CHUNK_ELEMS * 2;
 constexpr size_t SMEM_X = (size_t)XBUF_ELEMS * 2;
-constexpr size_t SMEM_MISC = 2048;
+constexpr size_t SMEM_MISC = 4096;
+constexpr int MAX_SPLIT_TASKS = 128;  // (row group, k-chunk) tasks per CTA in a split-K phase
 constexpr size_t SMEM_BYTES = SMEM_RING + SMEM_X + SMEM_MISC;
 
 enum { PH_GEMV = 0, PH_EMBED = 1, PH_ATTN = 2, PH_SAMPLE = 3 };
@@ -131,6 +136,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
       : "memory");
 }
+// Second, deeper stage of the weight stream: pull a chunk into the 126 MB L2 well before its turn
+// in the shared-memory ring.  HBM then keeps streaming while every CTA sits in a latency chain
+// (barrier, activation load, epilogue), and the ring refills at L2 speed.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -163,22 +174,44 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, Sync* 
 __device__ __forceinline__ int group_of(int cta, int ncta, int warp, int i) { return cta + ncta * (warp + NW * i); }
 
 // ---- per-warp weight prefetcher -----------------------------------------------------------------------
+// A phase's work is cut into tasks (row group j of this CTA, k-chunk kc), numbered u = j*nkc + kc and
+// dealt round-robin to the warps (u = warp, warp + NW, ...).  For K <= KC_MAX a task is a whole row
+// group; for the down projections (K = 8192) the k-chunks of one row pair go to different warps, so
+// all warps stream in parallel and the partial sums meet in shared memory.
 struct Prefetch {
-  int gi;    // index into the GEMV table
-  int i;     // group iteration inside the phase
-  int kc;    // k-chunk inside the group
+  int gi;  // index into the GEMV table
+  int u;   // task index inside the phase
   unsigned issued;
   bool done;
   uint64_t policy;  // L2 cache policy of the weight stream
 };
 
+__device__ __forceinline__ int nkc_of(int K) { return K <= KC_MAX ? 1 : K / KC_MAX; }
+
 __device__ __forceinline__ void pf_seek(Prefetch& pf, const PfTable& tab, int cta, int ncta, int warp) {
-  // position on the first (phase, group) at or after (gi, i) that this warp owns
-  while (pf.gi < tab.n && group_of(cta, ncta, warp, pf.i) >= tab.d[pf.gi].G) {
+  // position on the first (phase, task) at or after (gi, u) that this warp owns
+  while (pf.gi < tab.n && cta + ncta * (pf.u / nkc_of(tab.d[pf.gi].K)) >= tab.d[pf.gi].G) {
     ++pf.gi;
-    pf.i = 0;
+    pf.u = warp;
   }
   pf.done = pf.gi >= tab.n;
+}
+
+// L2 prefetch of the chunk the cursor points at, then advance (no shared-memory slot involved)
+__device__ __forceinline__ void pf_issue_l2(Prefetch& pf, const PfTable& tab, int cta, int ncta, int warp, int lane) {
+  if (pf.done) return;
+  const PfDesc& d = tab.d[pf.gi];
+  const int K = d.K, KC = K < KC_MAX ? K : KC_MAX, R = CHUNK_ELEMS / KC, nkc = K / KC;
+  const int j = pf.u / nkc, kc = pf.u - j * nkc;
+  const int r0 = (cta + ncta * j) * R;
+  const int nr = min(R, d.rows - r0);
+  if (nkc == 1) {
+    if (lane == 0) bulk_prefetch_l2(d.W + (size_t)r0 * K, (uint32_t)nr * K * 2);
+  } else if (lane < nr) {
+    bulk_prefetch_l2(d.W + (size_t)(r0 + lane) * K + (size_t)kc * KC, (uint32_t)KC * 2);
+  }
+  pf.u += NW;
+  pf_seek(pf, tab, cta, ncta, warp);
 }
 
 // issue the next chunk of this warp's stream into ring slot (issued % SLOTS); whole warp calls it
@@ -187,8 +220,8 @@ __device__ __forceinline__ void pf_issue(Prefetch& pf, const PfTable& tab, bf16*
   if (pf.done) return;
   const PfDesc& d = tab.d[pf.gi];
   const int K = d.K, KC = K < KC_MAX ? K : KC_MAX, R = CHUNK_ELEMS / KC, nkc = K / KC;
-  const int g = group_of(cta, ncta, warp, pf.i);
-  const int r0 = g * R;
+  const int j = pf.u / nkc, kc = pf.u - j * nkc;
+  const int r0 = (cta + ncta * j) * R;
   const int nr = min(R, d.rows - r0);
   const int slot = pf.issued % SLOTS;
   if (lane == 0) {
@@ -200,15 +233,12 @@ __device__ __forceinline__ void pf_issue(Prefetch& pf, const PfTable& tab, bf16*
     } else {
       mbar_expect_tx(fb, (uint32_t)nr * KC * 2);
       for (int r = 0; r < nr; ++r)
-        bulk_g2s(dst + r * KC, d.W + (size_t)(r0 + r) * K + (size_t)pf.kc * KC, (uint32_t)KC * 2, fb, pf.policy);
+        bulk_g2s(dst + r * KC, d.W + (size_t)(r0 + r) * K + (size_t)kc * KC, (uint32_t)KC * 2, fb, pf.policy);
     }
   }
   ++pf.issued;
-  if (++pf.kc == nkc) {
-    pf.kc = 0;
-    ++pf.i;
-    pf_seek(pf, tab, cta, ncta, warp);
-  }
+  pf.u += NW;
+  pf_seek(pf, tab, cta, ncta, warp);
 }
 
 // ---- consumer pieces ---------------------------------------------------------------------------------
@@ -218,9 +248,11 @@ struct Ctx {
   bf16* xs;
   uint64_t* full;
   float* scratch;  // 33 floats
+  float* psum;     // [MAX_SPLIT_TASKS][4] split-K partial sums
   int* iscratch;   // 40 ints
   Sync* sync;
-  Prefetch pf;
+  Prefetch pf;   // shared-memory ring cursor
+  Prefetch pf2;  // L2 prefetch cursor, L2_AHEAD chunks further down the same stream
   unsigned cnt;  // chunks consumed by this warp so far
   unsigned long long* trp;  // fine-grained trace slots of the current phase (CTA 0, thread 0) or null
   int tid, warp, lane;
@@ -300,71 +332,145 @@ __device__ __forceinline__ void epilogue(const Phase& ph, const Ctx& c, int r0, 
   }
 }
 
-// One warp, one row group (R rows x K) at a time: R*NB accumulators, the group's chunk(s) come from
-// this warp's ring; after the shuffle reduction lane (pair, n) runs that pair's epilogue.
+// dot products of one ring chunk ([R][KC] weights) with the staged activations
+template <int R, int NB>
+__device__ __forceinline__ void chunk_dot(const bf16* chunk, const bf16* xk, int K, int KC, int lane, float (&acc)[R][NB]) {
+  // two independent accumulator sets (even / odd 256-element blocks): the FMA chains, not the
+  // shared-memory bandwidth, bound this loop with only two warps per scheduler
+  float acc2[R][NB];
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int n = 0; n < NB; ++n) acc2[r][n] = 0.f;
+  for (int k = lane * 8; k < KC; k += 512) {
+    uint4 xa[NB], xb[NB];
+#pragma unroll
+    for (int n = 0; n < NB; ++n) {
+      xa[n] = *reinterpret_cast<const uint4*>(xk + (size_t)n * K + k);
+      xb[n] = *reinterpret_cast<const uint4*>(xk + (size_t)n * K + k + 256);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const uint4 wa = *reinterpret_cast<const uint4*>(chunk + r * KC + k);
+      const uint4 wb = *reinterpret_cast<const uint4*>(chunk + r * KC + k + 256);
+#pragma unroll
+      for (int n = 0; n < NB; ++n) {
+        acc[r][n] = dot8(wa, xa[n], acc[r][n]);
+        acc2[r][n] = dot8(wb, xb[n], acc2[r][n]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int n = 0; n < NB; ++n) acc[r][n] += acc2[r][n];
+}
+
+// The warp's tasks of this phase: chunks come from its ring; after the shuffle reduction lane
+// (pair, n) runs that pair's epilogue (K <= KC_MAX), or the partial sums go to shared memory and a
+// post pass adds the k-chunks in a fixed order and runs the epilogue (split-K phases).
 template <int R, int NB>
 __device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c, const PfTable& tab) {
   const int cta = blockIdx.x, ncta = gridDim.x;
   const int K = ph.K, KC = ph.KC, nkc = K / KC;
-  for (int i = 0;; ++i) {
-    const int g = group_of(cta, ncta, c.warp, i);
-    if (g >= ph.G) break;
-    const int my_pr = c.lane % (R / 2), my_n = c.lane / (R / 2);
-    const bool epi_lane = c.lane < (R / 2) * NB;
-    EpiPre pre;
-    pre.a = pre.b = 0.f;
-    if (i == 0 && c.pre_valid) {
-      pre.a = c.pre_a;
-      pre.b = c.pre_b;
-    } else if (epi_lane) {
-      pre = epilogue_prefetch(ph, c, g * R + 2 * my_pr, my_n);
-    }
-    float acc[R][NB];
+  const int my_pr = c.lane % (R / 2), my_n = c.lane / (R / 2);
+  const bool epi_lane = c.lane < (R / 2) * NB;
+  if (nkc == 1) {
+    for (int i = 0;; ++i) {
+      const int g = cta + ncta * (c.warp + NW * i);
+      if (g >= ph.G) break;
+      EpiPre pre;
+      pre.a = pre.b = 0.f;
+      if (i == 0 && c.pre_valid) {
+        pre.a = c.pre_a;
+        pre.b = c.pre_b;
+      } else if (epi_lane) {
+        pre = epilogue_prefetch(ph, c, g * R + 2 * my_pr, my_n);
+      }
+      float acc[R][NB];
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+      for (int r = 0; r < R; ++r)
 #pragma unroll
-      for (int n = 0; n < NB; ++n) acc[r][n] = 0.f;
-    for (int kc = 0; kc < nkc; ++kc) {
+        for (int n = 0; n < NB; ++n) acc[r][n] = 0.f;
       const int slot = c.cnt % SLOTS;
       mbar_wait(&c.full[c.warp * SLOTS + slot], (c.cnt / SLOTS) & 1, c.sync, 0x200 + c.warp);
-      if (c.trp && i == 0 && kc == 0 && !ph.attn_prologue) c.trp[1] = gtimer();
-      const bf16* chunk = c.ring + (size_t)(c.warp * SLOTS + slot) * CHUNK_ELEMS;
-      const bf16* xk = c.xs + (size_t)kc * KC;
-#pragma unroll 2
-      for (int k = c.lane * 8; k < KC; k += 256) {
-        uint4 xv[NB];
-#pragma unroll
-        for (int n = 0; n < NB; ++n) xv[n] = *reinterpret_cast<const uint4*>(xk + (size_t)n * K + k);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const uint4 wv = *reinterpret_cast<const uint4*>(chunk + r * KC + k);
-#pragma unroll
-          for (int n = 0; n < NB; ++n) acc[r][n] = dot8(wv, xv[n], acc[r][n]);
-        }
-      }
+      if (c.trp && i == 0 && !ph.attn_prologue) c.trp[1] = gtimer();
+      chunk_dot<R, NB>(c.ring + (size_t)(c.warp * SLOTS + slot) * CHUNK_ELEMS, c.xs, K, KC, c.lane, acc);
       __syncwarp();
       ++c.cnt;
-      if (c.trp && i == 0 && kc == 0 && !ph.attn_prologue) c.trp[2] = gtimer();
+      if (c.trp && i == 0 && !ph.attn_prologue) c.trp[2] = gtimer();
       // the slot is drained: refill it with the chunk SLOTS ahead in this warp's stream
       pf_issue(c.pf, tab, c.ring, c.full, cta, ncta, c.warp, c.lane);
-    }
-    float y0 = 0.f, y1 = 0.f;
+      if (L2_AHEAD > 0) pf_issue_l2(c.pf2, tab, cta, ncta, c.warp, c.lane);
+      float y0 = 0.f, y1 = 0.f;
 #pragma unroll
-    for (int r = 0; r < R / 2; ++r)
+      for (int r = 0; r < R / 2; ++r)
 #pragma unroll
-      for (int n = 0; n < NB; ++n) {
-        const float s0 = warp_sum(acc[2 * r][n]);
-        const float s1 = warp_sum(acc[2 * r + 1][n]);
-        if (c.lane == r + n * (R / 2)) {
-          y0 = s0;
-          y1 = s1;
+        for (int n = 0; n < NB; ++n) {
+          const float s0 = warp_sum(acc[2 * r][n]);
+          const float s1 = warp_sum(acc[2 * r + 1][n]);
+          if (c.lane == r + n * (R / 2)) {
+            y0 = s0;
+            y1 = s1;
+          }
         }
+      if (epi_lane) {
+        const int r0 = g * R + 2 * my_pr;
+        if (r0 < ph.rows && my_n < ph.nb) epilogue(ph, c, r0, my_n, y0, y1, pre);
       }
-    if (epi_lane) {
-      const int r0 = g * R + 2 * my_pr;
-      if (r0 < ph.rows && my_n < ph.nb) epilogue(ph, c, r0, my_n, y0, y1, pre);
+      if (c.trp && i == 0 && !ph.attn_prologue) c.trp[3] = gtimer();
     }
-    if (c.trp && i == 0 && !ph.attn_prologue) c.trp[3] = gtimer();
+  } else {
+    // split K: post-pass item t = (row group j of this CTA, pair, activation row)
+    const int ngroups = ph.G > cta ? (ph.G - cta + ncta - 1) / ncta : 0;
+    const int per_group = (R / 2) * ph.nb;
+    const int items = ngroups * per_group;
+    int pj = 0, pr0 = 0, pn = 0;
+    EpiPre pre;
+    pre.a = pre.b = 0.f;
+    if (c.tid < items) {
+      pj = c.tid / per_group;
+      const int rem = c.tid - pj * per_group;
+      pn = rem / (R / 2);
+      pr0 = (cta + ncta * pj) * R + 2 * (rem % (R / 2));
+      pre = epilogue_prefetch(ph, c, pr0, pn);
+    }
+    for (int u = c.warp;; u += NW) {
+      const int j = u / nkc, kc = u - j * nkc;
+      if (cta + ncta * j >= ph.G) break;
+      float acc[R][NB];
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int n = 0; n < NB; ++n) acc[r][n] = 0.f;
+      const int slot = c.cnt % SLOTS;
+      mbar_wait(&c.full[c.warp * SLOTS + slot], (c.cnt / SLOTS) & 1, c.sync, 0x200 + c.warp);
+      if (c.trp && u == c.warp) c.trp[1] = gtimer();
+      chunk_dot<R, NB>(c.ring + (size_t)(c.warp * SLOTS + slot) * CHUNK_ELEMS, c.xs + (size_t)kc * KC, K, KC, c.lane, acc);
+      __syncwarp();
+      ++c.cnt;
+      if (c.trp && u == c.warp) c.trp[2] = gtimer();
+      pf_issue(c.pf, tab, c.ring, c.full, cta, ncta, c.warp, c.lane);
+      if (L2_AHEAD > 0) pf_issue_l2(c.pf2, tab, cta, ncta, c.warp, c.lane);
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int n = 0; n < NB; ++n) {
+          const float sr = warp_sum(acc[r][n]);
+          if (c.lane == r * NB + n) c.psum[(u * R + r) * MAXNB + n] = sr;
+        }
+    }
+    csync<NCT, CBAR>();
+    if (c.trp) c.trp[3] = gtimer();
+    if (c.tid < items) {
+      const int pr = (pr0 - (cta + ncta * pj) * R);  // row inside the group (even)
+      float y0 = 0.f, y1 = 0.f;
+      for (int kc = 0; kc < nkc; ++kc) {  // fixed order -> deterministic rounding
+        y0 += c.psum[((pj * nkc + kc) * R + pr) * MAXNB + pn];
+        y1 += c.psum[((pj * nkc + kc) * R + pr + 1) * MAXNB + pn];
+      }
+      epilogue(ph, c, pr0, pn, y0, y1, pre);
+    }
   }
 }
 
@@ -702,11 +808,13 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
   uint64_t* full = reinterpret_cast<uint64_t*>(misc + 2 * sizeof(Phase));  // [NW*SLOTS]
   float* scratch = reinterpret_cast<float*>(full + NW * SLOTS);            // [34]
   int* iscratch = reinterpret_cast<int*>(scratch + 34);                    // [40]
-  static_assert(2 * sizeof(Phase) + NW * SLOTS * 8 + 34 * 4 + 40 * 4 <= SMEM_MISC, "misc region too small");
+  float* psum = reinterpret_cast<float*>(iscratch + 40);                   // [MAX_SPLIT_TASKS * 2 * MAXNB]
+  static_assert(2 * sizeof(Phase) + NW * SLOTS * 8 + 34 * 4 + 40 * 4 + MAX_SPLIT_TASKS * 2 * MAXNB * 4 <= SMEM_MISC,
+                "misc region too small");
   static_assert(NW <= 32, "block reductions assume <= 32 warps");
 
   Ctx c;
-  c.P = P; c.trp = nullptr; c.ring = ring; c.xs = xs; c.full = full; c.scratch = scratch; c.iscratch = iscratch;
+  c.P = P; c.trp = nullptr; c.ring = ring; c.xs = xs; c.full = full; c.scratch = scratch; c.iscratch = iscratch; c.psum = psum;
   c.sync = sync; c.cnt = 0; c.tid = threadIdx.x; c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
   c.pre_valid = false; c.pre_a = c.pre_b = 0.f; c.pre_scale = make_uint4(0, 0, 0, 0);
 
@@ -722,10 +830,12 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
   __syncthreads();
 
   // start this warp's weight stream: SLOTS chunks in flight from now on
-  c.pf.gi = 0; c.pf.i = 0; c.pf.kc = 0; c.pf.issued = 0; c.pf.done = false;
+  c.pf.gi = 0; c.pf.u = c.warp; c.pf.issued = 0; c.pf.done = false;
   c.pf.policy = policy_evict_first();
   pf_seek(c.pf, tab, blockIdx.x, gridDim.x, c.warp);
   for (int s = 0; s < SLOTS; ++s) pf_issue(c.pf, tab, ring, full, blockIdx.x, gridDim.x, c.warp, c.lane);
+  c.pf2 = c.pf;  // continues where the ring cursor stands, then stays L2_AHEAD chunks in front
+  for (int s = 0; s < L2_AHEAD; ++s) pf_issue_l2(c.pf2, tab, blockIdx.x, gridDim.x, c.warp, c.lane);
 
   const unsigned ncta = gridDim.x;
   const bool tr = trace != nullptr && blockIdx.x == 0 && c.tid == 0;
