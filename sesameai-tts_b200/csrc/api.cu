@@ -29,6 +29,9 @@ static unsigned long long g_launches = 0;
 #define COUNT_LAUNCH() (++g_launches)
 extern "C" uint64_t csm_launch_count(void) { return g_launches; }
 
+static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const bf16* W, int n_out, bf16* out, long long ldo,
+                          int epi, const bf16* resid, cudaStream_t st);
+
 // shared with mimi_api.cu
 int csm_set_error(int code, const char* msg) { return set_err(code, "%s", msg); }
 void csm_count_launches(unsigned long long n) { g_launches += n; }
@@ -62,6 +65,8 @@ struct csm_ctx {
   StackDev bb, dec;
   const bf16 *text_emb, *audio_emb, *proj, *c0_head;
   bf16* head_t;   // [C-1][Vp][Dd]
+  bf16* head0_proj;  // stacked [codebook0_head (Vp rows) ; projection (Dd rows)] x D
+  bf16* proj_table;  // projection(audio_embeddings[cb*V + tok]) for cb < C-1: [(C-1)*V][Dd]
   bf16* dec_in;   // [2B][D]
   bf16* logits;   // [B][Vp]
   int *row_stream, *row_pos, *row_slot;
@@ -104,7 +109,7 @@ static bool valid_cfg(const csm_config* c) {
 }
 
 static int mega_phase_count(const csm_config& c) {
-  return 1 + c.backbone.layers * 5 + 2 + (c.codebooks - 1) * (1 + c.decoder.layers * 4 + 2);
+  return 1 + c.backbone.layers * 5 + 2 + (c.codebooks - 1) * (c.decoder.layers * 4 + 2);
 }
 
 static void carve_stack(Carver& cv, StackDev& s, const csm_stack_config& c, int slots, int streams, int rows) {
@@ -137,6 +142,8 @@ static size_t carve_all(csm_ctx* x, char* base) {
   x->bb.qkv = cv.take<bf16>((size_t)x->max_rows * (c.backbone.heads + 2 * c.backbone.kv_heads) * (c.backbone.dim / c.backbone.heads));
   carve_stack(cv, x->dec, c.decoder, c.codebooks, x->max_batch, 2 * x->max_batch);
   x->head_t = cv.take<bf16>((size_t)(c.codebooks - 1) * x->Vp * c.decoder.dim);
+  x->head0_proj = cv.take<bf16>((size_t)(x->Vp + c.decoder.dim) * c.backbone.dim);
+  x->proj_table = cv.take<bf16>((size_t)(c.codebooks - 1) * c.audio_vocab * c.decoder.dim);
   x->dec_in = cv.take<bf16>((size_t)2 * x->max_batch * c.backbone.dim);
   x->logits = cv.take<bf16>((size_t)x->max_batch * x->Vp);
   x->row_stream = cv.take<int>(x->max_rows);
@@ -360,7 +367,7 @@ static void build_mega_phases(csm_ctx* x, std::vector<mega::Phase>& v) {
     mega::Phase s;
     memset(&s, 0, sizeof(s));
     s.type = mega::PH_SAMPLE; s.cb = cb; s.V = V; s.C = C; s.D = D; s.logits = x->logits; s.ldl = x->Vp;
-    s.next_in = next_in; s.audio_emb = x->audio_emb;
+    s.next_in = next_in; s.audio_emb = x->audio_emb; s.next_table = x->proj_table; s.next_ld = Dd;
     return s;
   };
   mega::Phase e;
@@ -368,17 +375,18 @@ static void build_mega_phases(csm_ctx* x, std::vector<mega::Phase>& v) {
   e.type = mega::PH_EMBED; e.V = V; e.C = C; e.D = D; e.audio_emb = x->audio_emb; e.text_emb = x->text_emb; e.h_out = x->bb.h;
   v.push_back(e);
   for (int l = 0; l < c.backbone.layers; ++l) stack_phases(x, x->bb, l, 1, mega::POS_BACKBONE, 0, false, v);
-  mega::Phase h0 = gemv_phase_desc(x->c0_head, V, D, x->bb.h, D, 1, EPI_PLAIN, x->bb.norm, eps, x->logits, x->Vp);
-  h0.x_copy_out = x->dec_in;  // last_h = backbone.norm(h): depth-decoder input row 0
+  // one phase: logits of codebook 0 AND projection(last_h) (depth-decoder row 0), from the stacked matrix;
+  // every later decoder input is a row of the projection(embedding) table, so no projection phase remains
+  mega::Phase h0 = gemv_phase_desc(x->head0_proj, x->Vp + Dd, D, x->bb.h, D, 1, EPI_PLAIN, x->bb.norm, eps, x->logits, x->Vp);
+  h0.out2 = x->dec.h; h0.split_row = x->Vp;
   v.push_back(h0);
-  v.push_back(sample(0, x->dec_in + D));
+  v.push_back(sample(0, x->dec.h + Dd));
   for (int i = 1; i < C; ++i) {
     const int nb = (i == 1) ? 2 : 1, pos0 = (i == 1) ? 0 : i;
-    v.push_back(gemv_phase_desc(x->proj, Dd, D, x->dec_in, D, nb, EPI_PLAIN, nullptr, eps, x->dec.h, Dd));
     for (int l = 0; l < c.decoder.layers; ++l) stack_phases(x, x->dec, l, nb, mega::POS_FIXED, pos0, true, v);
     v.push_back(gemv_phase_desc(x->head_t + (size_t)(i - 1) * x->Vp * Dd, V, Dd, x->dec.h + (size_t)(nb - 1) * Dd, Dd, 1,
                                 EPI_PLAIN, x->dec.norm, eps, x->logits, x->Vp));
-    v.push_back(sample(i, (i + 1 < C) ? x->dec_in : nullptr));
+    v.push_back(sample(i, (i + 1 < C) ? x->dec.h : nullptr));
   }
 }
 
@@ -492,6 +500,23 @@ extern "C" int32_t csm_create(const csm_config* cfg, const csm_weights* w, int32
     const int K = cfg->decoder.dim, V = cfg->audio_vocab;
     dim3 grid((x->Vp + 31) / 32, (K + 31) / 32, cfg->codebooks - 1), block(32, 8);
     k_transpose_heads<<<grid, block, 0, st>>>((const bf16*)w->audio_head, x->head_t, K, V, x->Vp); COUNT_LAUNCH();
+  }
+  {
+    // stacked [codebook0_head ; projection] (the workspace is not zeroed: clear the pad rows)
+    const size_t D8 = cfg->backbone.dim / 8;
+    cudaMemsetAsync(x->head0_proj, 0, (size_t)(x->Vp + cfg->decoder.dim) * cfg->backbone.dim * sizeof(bf16), st);
+    k_copy_rows<<<256, 256, 0, st>>>(x->c0_head, x->head0_proj, (size_t)cfg->audio_vocab * D8); COUNT_LAUNCH();
+    k_copy_rows<<<256, 256, 0, st>>>(x->proj, x->head0_proj + (size_t)x->Vp * cfg->backbone.dim, (size_t)cfg->decoder.dim * D8);
+    COUNT_LAUNCH();
+    // projection(embedding) table on the tensor cores: [(C-1)*V, D] x [Dd, D]^T
+    if (cfg->backbone.dim % 64 == 0) {
+      rc = launch_gemm_tc(x->audio_emb, cfg->backbone.dim, (cfg->codebooks - 1) * cfg->audio_vocab, cfg->backbone.dim, x->proj,
+                          cfg->decoder.dim, x->proj_table, cfg->decoder.dim, tc::EPI_STORE, nullptr, st);
+      if (rc != CSM_OK) {
+        delete x;
+        return rc;
+      }
+    }
   }
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&x->cap_stream, cudaStreamNonBlocking);

@@ -77,7 +77,12 @@ struct __align__(16) Phase {
   bf16* next_in;
   const bf16 *audio_emb, *text_emb;
   bf16* h_out;
-  int pad_[2];
+  // PLAIN epilogue with two destinations: rows >= split_row go to out2[row - split_row] (stacked
+  // [codebook0_head; projection] matrix: logits and the depth decoder's position-0 input in one phase)
+  bf16* out2;
+  int split_row;
+  int next_ld;  // SAMPLE: row length of the gather table feeding next_in
+  const bf16* next_table;  // SAMPLE: projection(embedding) table [(codebooks-1)*V][Dd], or null -> audio_emb rows
 };
 static_assert(sizeof(Phase) % 16 == 0, "Phase must be copyable in 16-byte units");
 
@@ -304,8 +309,13 @@ __device__ __forceinline__ void epilogue(const Phase& ph, const Ctx& c, int r0, 
   const bool has1 = r0 + 1 < ph.rows;
   const float y0 = rbf(a0), y1 = rbf(a1);
   if (ph.epi == EPI_PLAIN) {
-    ph.out[(size_t)n * ph.ldo + r0] = f2bf(y0);
-    if (has1) ph.out[(size_t)n * ph.ldo + r0 + 1] = f2bf(y1);
+    if (ph.out2 && r0 >= ph.split_row) {
+      ph.out2[r0 - ph.split_row] = f2bf(y0);
+      if (has1) ph.out2[r0 + 1 - ph.split_row] = f2bf(y1);
+    } else {
+      ph.out[(size_t)n * ph.ldo + r0] = f2bf(y0);
+      if (has1) ph.out[(size_t)n * ph.ldo + r0 + 1] = f2bf(y1);
+    }
   } else if (ph.epi == EPI_RESID) {
     ph.out[(size_t)n * ph.ldo + r0] = f2bf(y0 + pre.a);
     if (has1) ph.out[(size_t)n * ph.ldo + r0 + 1] = f2bf(y1 + pre.b);
@@ -343,16 +353,18 @@ __device__ __forceinline__ void chunk_dot(const bf16* chunk, const bf16* xk, int
 #pragma unroll
     for (int n = 0; n < NB; ++n) acc2[r][n] = 0.f;
   for (int k = lane * 8; k < KC; k += 512) {
+    const bool two = k + 256 < KC;  // KC is a multiple of 256, not necessarily of 512
+    const int k2 = two ? k + 256 : k;
     uint4 xa[NB], xb[NB];
 #pragma unroll
     for (int n = 0; n < NB; ++n) {
       xa[n] = *reinterpret_cast<const uint4*>(xk + (size_t)n * K + k);
-      xb[n] = *reinterpret_cast<const uint4*>(xk + (size_t)n * K + k + 256);
+      xb[n] = two ? *reinterpret_cast<const uint4*>(xk + (size_t)n * K + k2) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const uint4 wa = *reinterpret_cast<const uint4*>(chunk + r * KC + k);
-      const uint4 wb = *reinterpret_cast<const uint4*>(chunk + r * KC + k + 256);
+      const uint4 wb = *reinterpret_cast<const uint4*>(chunk + r * KC + k2);
 #pragma unroll
       for (int n = 0; n < NB; ++n) {
         acc[r][n] = dot8(wa, xa[n], acc[r][n]);
@@ -789,8 +801,10 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
   if (P->forced) tok = P->forced[cb];
   if (c.tid == 0) P->out[cb] = tok;
   if (ph.next_in) {
-    const bf16* row = ph.audio_emb + ((size_t)tok + (size_t)cb * V) * ph.D;
-    for (int d8 = c.tid; d8 < ph.D / 8; d8 += NCT)
+    // next depth-decoder input: projection(embed_audio(cb, tok)) read from the table built at setup
+    const int ld = ph.next_table ? ph.next_ld : ph.D;
+    const bf16* row = (ph.next_table ? ph.next_table : ph.audio_emb) + ((size_t)tok + (size_t)cb * V) * ld;
+    for (int d8 = c.tid; d8 < ld / 8; d8 += NCT)
       *reinterpret_cast<uint4*>(ph.next_in + d8 * 8) = *reinterpret_cast<const uint4*>(row + d8 * 8);
   }
 }

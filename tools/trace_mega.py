@@ -36,7 +36,6 @@ for l in range(16):
     kinds += ["bb.qkv", "bb.attn", "bb.o", "bb.gu", "bb.down"]
 kinds += ["c0head", "sample"]
 for i in range(1, 32):
-    kinds += ["proj"]
     for l in range(4):
         kinds += ["d.qkv", "d.o+attn", "d.gu", "d.down"]
     kinds += ["d.head", "sample"]
