@@ -43,6 +43,7 @@ extern "C" const char* csm_last_error(void) { return g_err; }
 static const int PREFILL_CHUNK = 8;     // prompt frames per stream per small-row pass
 static const int PREFILL_TC_ROWS = 4096;  // rows per tensor-core prefill pass
 static const int PREFILL_TC_MIN = 64;     // prompt rows (B * (S-1)) from which the tcgen05 path is used
+static const int DECODE_TC_MIN = 16;      // streams from which a decode step runs on the tcgen05 GEMM
 
 struct StackDev {
   csm_stack_config c;
@@ -84,6 +85,9 @@ struct csm_ctx {
   std::map<int, cudaGraphExec_t> graphs;  // keyed by B
   std::map<int, unsigned long long> graph_nodes;
 };
+
+static int backbone_pass_tc(csm_ctx* x, int B, int chunk, cudaStream_t st);
+static int frame_tail_tc(csm_ctx* x, int B, cudaStream_t st);
 
 struct Carver {
   char* base;
@@ -141,6 +145,8 @@ static size_t carve_all(csm_ctx* x, char* base) {
   x->bb.xn = cv.take<bf16>((size_t)x->max_rows * c.backbone.dim);
   x->bb.qkv = cv.take<bf16>((size_t)x->max_rows * (c.backbone.heads + 2 * c.backbone.kv_heads) * (c.backbone.dim / c.backbone.heads));
   carve_stack(cv, x->dec, c.decoder, c.codebooks, x->max_batch, 2 * x->max_batch);
+  x->dec.xn = cv.take<bf16>((size_t)2 * x->max_batch * c.decoder.dim);
+  x->dec.qkv = cv.take<bf16>((size_t)2 * x->max_batch * (c.decoder.heads + 2 * c.decoder.kv_heads) * (c.decoder.dim / c.decoder.heads));
   x->head_t = cv.take<bf16>((size_t)(c.codebooks - 1) * x->Vp * c.decoder.dim);
   x->head0_proj = cv.take<bf16>((size_t)(x->Vp + c.decoder.dim) * c.backbone.dim);
   x->proj_table = cv.take<bf16>((size_t)(c.codebooks - 1) * c.audio_vocab * c.decoder.dim);
@@ -557,9 +563,20 @@ static int get_graph(csm_ctx* x, int B, cudaGraphExec_t* out) {
   cudaGraph_t g = nullptr;
   const unsigned long long before = g_launches;
   CU_TRY(cudaStreamBeginCapture(x->cap_stream, cudaStreamCaptureModeThreadLocal));
-  cudaError_t e = backbone_pass(x, B, 1, x->cap_stream);
-  if (e == cudaSuccess) e = frame_tail(x, B, x->cap_stream);
+  cudaError_t e = cudaSuccess;
+  int rc_tc = CSM_OK;
+  if (B >= DECODE_TC_MIN && x->cfg.backbone.dim % 64 == 0 && x->cfg.decoder.dim % 64 == 0) {
+    rc_tc = backbone_pass_tc(x, B, 1, x->cap_stream);
+    if (rc_tc == CSM_OK) rc_tc = frame_tail_tc(x, B, x->cap_stream);
+  } else {
+    e = backbone_pass(x, B, 1, x->cap_stream);
+    if (e == cudaSuccess) e = frame_tail(x, B, x->cap_stream);
+  }
   cudaError_t e2 = cudaStreamEndCapture(x->cap_stream, &g);
+  if (rc_tc != CSM_OK) {
+    if (g) cudaGraphDestroy(g);
+    return rc_tc;
+  }
   x->graph_nodes[B] = g_launches - before;  // captured, not executed
   g_launches = before;
   if (e != cudaSuccess || e2 != cudaSuccess) {
@@ -575,7 +592,6 @@ static int get_graph(csm_ctx* x, int B, cudaGraphExec_t* out) {
   return CSM_OK;
 }
 
-static int backbone_pass_tc(csm_ctx* x, int B, int chunk, cudaStream_t st);
 
 extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const uint8_t* tokens_mask,
                                       const int64_t* input_pos, int32_t B, int32_t S, float temperature, int32_t topk,
@@ -627,8 +643,14 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
   k_set_params<<<1, 1, 0, st>>>(x->d_params, p); COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
   if (path == CSM_PATH_DIRECT) {
-    CU_TRY(backbone_pass(x, B, 1, st));
-    CU_TRY(frame_tail(x, B, st));
+    if (B >= DECODE_TC_MIN && x->cfg.backbone.dim % 64 == 0 && x->cfg.decoder.dim % 64 == 0) {
+      int rc = backbone_pass_tc(x, B, 1, st);
+      if (rc == CSM_OK) rc = frame_tail_tc(x, B, st);
+      if (rc != CSM_OK) return rc;
+    } else {
+      CU_TRY(backbone_pass(x, B, 1, st));
+      CU_TRY(frame_tail(x, B, st));
+    }
   } else {
     cudaGraphExec_t ge;
     int rc = get_graph(x, B, &ge);
@@ -694,45 +716,78 @@ static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const b
   return CSM_OK;
 }
 
-// Backbone pass over `chunk` prompt frames per stream on the tensor cores (rows n = b*chunk + t):
-// per layer RMSNorm -> GEMM [q;k;v] -> RoPE + KV append -> attention -> GEMM O (+res) -> RMSNorm ->
-// GEMM gate/up (SwiGLU epilogue) -> GEMM down (+res); same rounding points as the small-row path.
-static int backbone_pass_tc(csm_ctx* x, int B, int chunk, cudaStream_t st) {
-  const csm_config& c = x->cfg;
-  const csm_stack_config& k = c.backbone;
-  StackDev& s = x->bb;
-  const int N = B * chunk, D = k.dim, qkv_cols = (k.heads + 2 * k.kv_heads) * s.hd;
-  k_embed_pass<<<N, 256, 0, st>>>(x->d_params, x->text_emb, x->audio_emb, c.codebooks, c.audio_vocab, D, chunk, s.h,
-                                  x->row_stream, x->row_pos, x->row_slot); COUNT_LAUNCH();
-  CU_TRY(cudaGetLastError());
+// All layers of one stack on N rows with the tcgen05 GEMM: per layer RMSNorm -> GEMM [q;k;v] -> RoPE +
+// KV append -> attention -> GEMM O (+res) -> RMSNorm -> GEMM gate/up (SwiGLU epilogue) -> GEMM down
+// (+res); same rounding points as the small-row path.
+static int stack_pass_tc(csm_ctx* x, StackDev& s, int N, const RowMeta& m, cudaStream_t st) {
+  const csm_stack_config& k = s.c;
+  const int D = k.dim, qkv_cols = (k.heads + 2 * k.kv_heads) * s.hd;
+  const float eps = x->cfg.norm_eps;
   int rc;
   for (int l = 0; l < k.layers; ++l) {
     bf16* kc = s.kc + s.kv_layer_stride * l;
     bf16* vc = s.vc + s.kv_layer_stride * l;
-    k_rmsnorm<<<N, 256, 0, st>>>(s.h, D, s.sa[l], D, c.norm_eps, s.xn, D); COUNT_LAUNCH();
+    k_rmsnorm<<<N, 256, 0, st>>>(s.h, D, s.sa[l], D, eps, s.xn, D); COUNT_LAUNCH();
     if ((rc = launch_gemm_tc(s.xn, D, N, D, s.wqkv[l], qkv_cols, s.qkv, qkv_cols, tc::EPI_STORE, nullptr, st)) != CSM_OK) return rc;
-    k_rope_kv_rows<<<N, 256, 0, st>>>(s.qkv, s.rope, x->row_stream, x->row_pos, x->row_slot, k.heads, k.kv_heads, s.hd, s.slots,
-                                      s.q, kc, vc); COUNT_LAUNCH();
+    k_rope_kv_rows<<<N, 256, 0, st>>>(s.qkv, s.rope, m.stream, m.pos, m.slot, m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.hd,
+                                      s.slots, s.q, kc, vc); COUNT_LAUNCH();
     {
       dim3 grid(N, k.heads);
       const size_t smem = (size_t)s.slots * sizeof(float);
       const float scale = 1.0f / sqrtf((float)s.hd);
       if (s.hd == 64) {
-        k_attn_rows<64><<<grid, 128, smem, st>>>(s.q, kc, vc, x->row_stream, x->row_slot, 0, 0, k.heads, k.kv_heads, s.slots,
+        k_attn_rows<64><<<grid, 128, smem, st>>>(s.q, kc, vc, m.stream, m.slot, m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.slots,
                                                  scale, s.att);
       } else {
-        k_attn_rows<128><<<grid, 128, smem, st>>>(s.q, kc, vc, x->row_stream, x->row_slot, 0, 0, k.heads, k.kv_heads, s.slots,
+        k_attn_rows<128><<<grid, 128, smem, st>>>(s.q, kc, vc, m.stream, m.slot, m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.slots,
                                                   scale, s.att);
       }
       COUNT_LAUNCH();
     }
     CU_TRY(cudaGetLastError());
     if ((rc = launch_gemm_tc(s.att, D, N, D, s.wo[l], D, s.h, D, tc::EPI_ADD_RESID, s.h, st)) != CSM_OK) return rc;
-    k_rmsnorm<<<N, 256, 0, st>>>(s.h, D, s.mlp[l], D, c.norm_eps, s.xn, D); COUNT_LAUNCH();
+    k_rmsnorm<<<N, 256, 0, st>>>(s.h, D, s.mlp[l], D, eps, s.xn, D); COUNT_LAUNCH();
     if ((rc = launch_gemm_tc(s.xn, D, N, D, s.wgu[l], 2 * k.ff, s.act, k.ff, tc::EPI_SWIGLU_PAIRS, nullptr, st)) != CSM_OK) return rc;
     if ((rc = launch_gemm_tc(s.act, k.ff, N, k.ff, s.wd[l], D, s.h, D, tc::EPI_ADD_RESID, s.h, st)) != CSM_OK) return rc;
   }
   CU_TRY(cudaGetLastError());
+  return CSM_OK;
+}
+
+// Backbone pass over `chunk` frames per stream on the tensor cores (rows n = b*chunk + t).
+static int backbone_pass_tc(csm_ctx* x, int B, int chunk, cudaStream_t st) {
+  const csm_config& c = x->cfg;
+  const int N = B * chunk;
+  k_embed_pass<<<N, 256, 0, st>>>(x->d_params, x->text_emb, x->audio_emb, c.codebooks, c.audio_vocab, c.backbone.dim, chunk,
+                                  x->bb.h, x->row_stream, x->row_pos, x->row_slot); COUNT_LAUNCH();
+  CU_TRY(cudaGetLastError());
+  RowMeta m{x->row_stream, x->row_pos, x->row_slot, 0, 0};
+  return stack_pass_tc(x, x->bb, N, m, st);
+}
+
+// frame_tail for many streams (B >= DECODE_TC_MIN): every linear layer is a tcgen05 GEMM over the B
+// (or 2B) rows, the depth decoder's inputs after step 1 come from the projection(embedding) table.
+static int frame_tail_tc(csm_ctx* x, int B, cudaStream_t st) {
+  const csm_config& c = x->cfg;
+  const int D = c.backbone.dim, Dd = c.decoder.dim, V = c.audio_vocab, C = c.codebooks;
+  int rc;
+  k_rmsnorm<<<B, 256, 0, st>>>(x->bb.h, D, x->bb.norm, D, c.norm_eps, x->dec_in, D); COUNT_LAUNCH();  // last_h
+  if ((rc = launch_gemm_tc(x->dec_in, D, B, D, x->c0_head, V, x->logits, x->Vp, tc::EPI_STORE, nullptr, st)) != CSM_OK) return rc;
+  if ((rc = launch_gemm_tc(x->dec_in, D, B, D, x->proj, Dd, x->dec.h, Dd, tc::EPI_STORE, nullptr, st)) != CSM_OK) return rc;
+  k_sample_step<<<B, SAMPLE_THREADS, 0, st>>>(x->d_params, x->logits, x->Vp, 0, V, C, x->proj_table, Dd,
+                                              x->dec.h + (size_t)B * Dd); COUNT_LAUNCH();
+  CU_TRY(cudaGetLastError());
+  for (int i = 1; i < C; ++i) {
+    const int N = (i == 1) ? 2 * B : B, pos0 = (i == 1) ? 0 : i;
+    RowMeta m{nullptr, nullptr, nullptr, B, pos0};
+    if ((rc = stack_pass_tc(x, x->dec, N, m, st)) != CSM_OK) return rc;
+    k_rmsnorm<<<B, 256, 0, st>>>(x->dec.h + (size_t)(N - B) * Dd, Dd, x->dec.norm, Dd, c.norm_eps, x->dec.xn, Dd); COUNT_LAUNCH();
+    if ((rc = launch_gemm_tc(x->dec.xn, Dd, B, Dd, x->head_t + (size_t)(i - 1) * x->Vp * Dd, V, x->logits, x->Vp, tc::EPI_STORE,
+                             nullptr, st)) != CSM_OK) return rc;
+    k_sample_step<<<B, SAMPLE_THREADS, 0, st>>>(x->d_params, x->logits, x->Vp, i, V, C, x->proj_table, Dd,
+                                                (i + 1 < C) ? x->dec.h : nullptr); COUNT_LAUNCH();
+    CU_TRY(cudaGetLastError());
+  }
   return CSM_OK;
 }
 

@@ -333,13 +333,15 @@ __global__ void __launch_bounds__(128) k_attn_rows(const bf16* __restrict__ q, c
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_rope_kv_rows(const bf16* __restrict__ qkv, const bf16* __restrict__ rope,
                                                       const int* __restrict__ row_stream, const int* __restrict__ row_pos,
-                                                      const int* __restrict__ row_slot, int heads, int kv_heads, int hd,
-                                                      int slots, bf16* __restrict__ q_out, bf16* __restrict__ k_cache,
-                                                      bf16* __restrict__ v_cache) {
+                                                      const int* __restrict__ row_slot, int imp_B, int imp_pos, int heads,
+                                                      int kv_heads, int hd, int slots, bf16* __restrict__ q_out,
+                                                      bf16* __restrict__ k_cache, bf16* __restrict__ v_cache) {
   const int n = blockIdx.x;
   const int qrows = heads * hd, krows = kv_heads * hd, total = qrows + 2 * krows;
   const bf16* src = qkv + (size_t)n * total;
-  const int pos = row_pos[n], slot = row_slot[n], stream = row_stream[n];
+  const int pos = row_stream ? row_pos[n] : imp_pos + n / imp_B;
+  const int slot = row_stream ? row_slot[n] : imp_pos + n / imp_B;
+  const int stream = row_stream ? row_stream[n] : n % imp_B;
   for (int p = threadIdx.x; p < total / 2; p += blockDim.x) {
     const int r0 = 2 * p;
     const __nv_bfloat162 in = *reinterpret_cast<const __nv_bfloat162*>(src + r0);
@@ -623,6 +625,7 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample_step(const FrameParam
                                                                 const bf16* __restrict__ logits, int ldl, int cb,
                                                                 int V, int C, const bf16* __restrict__ audio_emb, int D,
                                                                 bf16* __restrict__ next_in /*[B, D] or null*/) {
+  // ``audio_emb``/``D`` may also be the projection(embedding) table and its row length
   __shared__ float xs[SAMPLE_MAXV];
   __shared__ unsigned int hist[256];
   __shared__ float scratch[33];

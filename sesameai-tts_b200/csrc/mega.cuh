@@ -572,12 +572,15 @@ __device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
       const float inv = 1.0f / warp_sum(e);
       const bf16* vp = c.xs + A_VOFF + kvh * 32 * A_HD + half * 64 + c.lane * 2;
       float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};  // 4 independent chains
+      for (int j0 = 0; j0 < nkeys; j0 += 4) {  // only the visible keys, 4 independent chains
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float pj = __shfl_sync(0xffffffffu, e, j);  // 0 for j >= nkeys
-        const uint32_t v = j < nkeys ? *reinterpret_cast<const uint32_t*>(vp + j * A_HD) : 0u;  // rows past nkeys are stale
-        o0[j & 3] = fmaf(pj, bflo(v), o0[j & 3]);
-        o1[j & 3] = fmaf(pj, bfhi(v), o1[j & 3]);
+        for (int t = 0; t < 4; ++t) {
+          const int j = j0 + t;
+          const float pj = __shfl_sync(0xffffffffu, e, j & 31);  // 0 for j >= nkeys
+          const uint32_t v = j < nkeys ? *reinterpret_cast<const uint32_t*>(vp + j * A_HD) : 0u;  // rows past nkeys are stale
+          o0[t] = fmaf(pj, bflo(v), o0[t]);
+          o1[t] = fmaf(pj, bfhi(v), o1[t]);
+        }
       }
       *reinterpret_cast<__nv_bfloat162*>(c.xs + n * ph.K + h * A_HD + half * 64 + c.lane * 2) =
           __floats2bfloat162_rn(((o0[0] + o0[1]) + (o0[2] + o0[3])) * inv, ((o1[0] + o1[1]) + (o1[2] + o1[3])) * inv);

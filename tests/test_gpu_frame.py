@@ -218,3 +218,32 @@ def test_csm1b_long_prompt_prefill_runs_on_tensor_cores():
     err = (a - b).abs()
     assert err.flatten().kthvalue(int(0.9999 * err.numel())).values.item() <= LOGIT_ATOL
     assert torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0).item() >= COS_MIN
+
+
+def test_batched_decode_on_tensor_cores_matches_oracle():
+    """B = 16 streams take the tcgen05 GEMM decode path (graph of TMA/UMMA GEMMs + row kernels):
+    teacher-forced logits against the oracle, and the graph replay equals direct launches."""
+    from sesameai import _native
+
+    gold = dict(model_args=dict(backbone_flavor="tiny-bb", decoder_flavor="tiny-dec", text_vocab_size=1000,
+                                audio_vocab_size=2051, audio_num_codebooks=32),
+                weight_seed=55, planted=False, batch=16)
+    om, _ = build_oracle(gold)
+    pm, _ = build_product(gold)
+    tok, msk, pos = syn.text_prompt(16, 5, 21, 1000)
+    noise = syn.exp_noise(32 * 2, 16, 2051, 6)
+    om.reset_caches(), pm.reset_caches()
+    tc_, mc, pc = tok.cuda(), msk.cuda(), pos.cuda()
+    for f in range(2):
+        rec = {}
+        with torch.inference_mode():
+            s = om.generate_frame(tok, msk, pos, 0.8, 40, noise=noise[32 * f: 32 * f + 32], record=rec)
+        lg = torch.zeros(32, 16, 2051, dtype=torch.bfloat16, device="cuda")
+        sp = pm.generate_frame(tc_, mc, pc, 0.8, 40, noise=noise[32 * f: 32 * f + 32].cuda(), forced=s, logits_out=lg,
+                               path=_native.PATH_GRAPH if f else _native.PATH_DIRECT)
+        assert torch.equal(sp.cpu(), s)
+        err = (lg.cpu().float() - torch.stack(rec["logits"]).float()).abs()
+        assert err.flatten().kthvalue(int(0.9999 * err.numel())).values.item() <= LOGIT_ATOL
+        assert err.max().item() <= LOGIT_ATOL_MAX
+        tok, msk, pos = next_inputs(s, pos)
+        tc_, mc, pc = next_inputs(sp, pc)
