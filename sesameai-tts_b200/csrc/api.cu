@@ -334,6 +334,9 @@ static mega::Phase gemv_phase_desc(const bf16* W, int rows, int K, const bf16* x
   ph.W = W; ph.rows = rows; ph.K = K;
   ph.KC = K < mega::KC_MAX ? K : mega::KC_MAX;
   ph.R = mega::CHUNK_ELEMS / ph.KC;
+  // latency-bound small phases: half-size chunks (down to row pairs) so that more warps share the
+  // rows and the per-CTA imbalance shrinks; streaming phases keep full 8 KB chunks
+  while (ph.R > 2 && (rows + ph.R - 1) / ph.R < 148 * mega::NW) ph.R /= 2;
   ph.G = (rows + ph.R - 1) / ph.R;
   ph.x = xin; ph.ldx = ldx; ph.norm_scale = norm_scale; ph.eps = eps; ph.out = out; ph.ldo = ldo; ph.resid = out;
   return ph;
@@ -419,7 +422,7 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
     if (x->pf_table.n >= mega::MAX_GEMV) return CSM_OK;  // too deep for the parameter-space table: per-op path only
     if (ph.K > mega::KC_MAX && ((ph.G + sms - 1) / sms) * (ph.K / mega::KC_MAX) > mega::MAX_SPLIT_TASKS) return CSM_OK;
     mega::PfDesc& d = x->pf_table.d[x->pf_table.n++];
-    d.W = ph.W; d.rows = ph.rows; d.K = ph.K; d.G = ph.G;
+    d.W = ph.W; d.rows = ph.rows; d.K = ph.K; d.G = ph.G; d.R = ph.R;
   }
   CU_TRY(cudaMemcpyAsync(x->d_phases, v.data(), v.size() * sizeof(mega::Phase), cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemsetAsync(x->d_sync, 0, sizeof(mega::Sync), st));

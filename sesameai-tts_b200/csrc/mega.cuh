@@ -89,7 +89,7 @@ static_assert(sizeof(Phase) % 16 == 0, "Phase must be copyable in 16-byte units"
 // What the weight prefetcher needs to know about a GEMV phase.
 struct PfDesc {
   const bf16* W;
-  int rows, K, G, pad_;
+  int rows, K, G, R;  // R rows per chunk (small phases use half-size chunks so more warps share them)
 };
 struct PfTable {
   int n;
@@ -206,7 +206,7 @@ __device__ __forceinline__ void pf_seek(Prefetch& pf, const PfTable& tab, int ct
 __device__ __forceinline__ void pf_issue_l2(Prefetch& pf, const PfTable& tab, int cta, int ncta, int warp, int lane) {
   if (pf.done) return;
   const PfDesc& d = tab.d[pf.gi];
-  const int K = d.K, KC = K < KC_MAX ? K : KC_MAX, R = CHUNK_ELEMS / KC, nkc = K / KC;
+  const int K = d.K, KC = K < KC_MAX ? K : KC_MAX, R = d.R, nkc = K / KC;
   const int j = pf.u / nkc, kc = pf.u - j * nkc;
   const int r0 = (cta + ncta * j) * R;
   const int nr = min(R, d.rows - r0);
@@ -224,7 +224,7 @@ __device__ __forceinline__ void pf_issue(Prefetch& pf, const PfTable& tab, bf16*
                                          int warp, int lane) {
   if (pf.done) return;
   const PfDesc& d = tab.d[pf.gi];
-  const int K = d.K, KC = K < KC_MAX ? K : KC_MAX, R = CHUNK_ELEMS / KC, nkc = K / KC;
+  const int K = d.K, KC = K < KC_MAX ? K : KC_MAX, R = d.R, nkc = K / KC;
   const int j = pf.u / nkc, kc = pf.u - j * nkc;
   const int r0 = (cta + ncta * j) * R;
   const int nr = min(R, d.rows - r0);

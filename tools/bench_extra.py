@@ -32,7 +32,7 @@ def ev_time(fn, reps=3, warm=1):
 
 
 # ---- prefill: S-frame voice prompt, tensor-core path vs small-row path ---------------------------
-for B in (1, 8):
+for B in (1, 8, 32):
     model = bench.build_product(dev, B)
     tok, msk, pos = syn.voice_prompt(B, 4, 64, 320, 32, seed=3, device=dev)  # 1568 frames (BASELINE config 3 prompt)
     S = tok.shape[1]
@@ -43,7 +43,7 @@ for B in (1, 8):
     flop = B * (2 * 973_146_112 * S + 2 * S * S * 2048 * 16 / 2)
     out[f"prefill_B{B}_S{S}"] = {"ms_tensor_core": t_tc, "tokens_per_s": B * S / t_tc * 1e3,
                                   "tflops": flop / t_tc / 1e9, "frac_of_bf16_peak": flop / t_tc / 1e9 / peaks.get("bf16_tflops_sustained", 1384.0)}
-    if B == 1:
+    if B == 1 and "--small-row" in sys.argv:
         out[f"prefill_B{B}_S{S}"]["ms_small_row"] = ev_time(lambda: run(_native.PREFILL_SMALL_ROW), reps=1, warm=0)
     # ---- batched decode (graph path for B > 1) ------------------------------------------------------
     t = torch.zeros(B, 1, 33, dtype=torch.int64, device=dev)
