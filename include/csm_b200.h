@@ -168,7 +168,22 @@ enum {
   MIMI_W_CONV0 = 147,
   MIMI_W_STAGE0 = 149,
   MIMI_W_FINAL = 173,
-  MIMI_W_COUNT = 175
+  /* encode side (moshi ``MimiModel.encode``, reference sesameai/generator.py:86):
+   *   ENC_CONV0 (+1 bias)  encoder.model.0 Conv1d [64,1,7]
+   *   ENC_STAGE0 + 6*s + {0 block.1 conv weight [C/2,C,3], 1 bias, 2 block.3 conv weight [C,C/2,1], 3 bias,
+   *                       4 strided conv weight [2C, C, 2r], 5 bias}, C = 64,128,256,512, r = 4,5,6,8
+   *   ENC_FINAL (+1 bias)  encoder.model.14 Conv1d [512,1024,3]
+   *   ENC_LAYER0 + 10*l    encoder_transformer layers, same 10 tensors as LAYER0
+   *   DOWNSAMPLE           downsample Conv1d weight [512,512,4] (stride 2, replicate padding, no bias)
+   *   RVQ_FIRST_INPROJ / RVQ_REST_INPROJ   input_proj.weight [256,512,1] */
+  MIMI_W_ENC_CONV0 = 175,
+  MIMI_W_ENC_STAGE0 = 177,
+  MIMI_W_ENC_FINAL = 201,
+  MIMI_W_ENC_LAYER0 = 203,
+  MIMI_W_DOWNSAMPLE = 283,
+  MIMI_W_RVQ_FIRST_INPROJ = 284,
+  MIMI_W_RVQ_REST_INPROJ = 285,
+  MIMI_W_COUNT = 286
 };
 typedef struct mimi_ctx mimi_ctx;
 size_t mimi_workspace_bytes(int32_t max_frames);
@@ -177,6 +192,10 @@ size_t mimi_workspace_bytes(int32_t max_frames);
 int32_t mimi_create(const void *const *weights, int32_t n_weights, int32_t max_frames, void *workspace,
                     size_t workspace_bytes, void *stream, mimi_ctx **out);
 int32_t mimi_decode(mimi_ctx *ctx, const int64_t *codes, int32_t B, int32_t K, int32_t T, float *out, void *stream);
+/* Replaces moshi's ``MimiModel.encode`` (reference sesameai/generator.py:86: voice-prompt audio ->
+ * codes): wav fp32 [B, L] at 24 kHz (zero-padded on the right to whole 1920-sample frames) ->
+ * codes int64 [B, K, ceil(L/1920)], K <= 32 codebooks (nearest centroid per residual layer). */
+int32_t mimi_encode(mimi_ctx *ctx, const float *wav, int32_t B, int64_t L, int32_t K, int64_t *codes, void *stream);
 void mimi_destroy(mimi_ctx *ctx);
 
 /* Profiling aid: dev uint64 [n_phases][8] buffer that CTA 0 of the decode megakernel fills with

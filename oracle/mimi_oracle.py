@@ -160,6 +160,7 @@ class OracleMimi(nn.Module):
         model.append(conv(N_FILTERS, 1, 3))
         self.decoder.model = nn.ModuleList(model)
         self.num_codebooks = N_Q
+        self._build_encoder()
 
     def set_num_codebooks(self, n: int) -> None:
         self.num_codebooks = n
@@ -215,5 +216,88 @@ class OracleMimi(nn.Module):
         emb = self.transformer(emb)
         return self.seanet(emb)
 
-    def encode(self, wav: torch.Tensor) -> torch.Tensor:  # pragma: no cover
-        raise NotImplementedError("Mimi encode is a 'next' row (SURVEY.md 8f); only decode is restated")
+    # -- encode (reference call site sesameai/generator.py:86) ---------------
+    def _build_encoder(self) -> None:
+        """SEANet encoder (ratios reversed 4,5,6,8), encoder transformer, stride-2 downsample."""
+
+        def conv(cin, cout, k, stride=1, bias=True):
+            m = nn.Module()
+            m.conv = nn.Module()
+            m.conv.conv = nn.Conv1d(cin, cout, k, stride=stride, bias=bias)
+            return m
+
+        model: List[nn.Module] = [conv(1, N_FILTERS, 7)]
+        ch = N_FILTERS
+        for r in reversed(RATIOS):
+            res = nn.Module()
+            res.block = nn.ModuleList([nn.ELU(), conv(ch, ch // 2, 3), nn.ELU(), conv(ch // 2, ch, 1)])
+            model += [res, nn.ELU(), conv(ch, 2 * ch, 2 * r, stride=r)]
+            ch *= 2
+        model += [nn.ELU(), conv(ch, DIM, 3)]
+        self.encoder = nn.Module()
+        self.encoder.model = nn.ModuleList(model)
+        self.encoder_transformer = nn.Module()
+        self.encoder_transformer.transformer = nn.Module()
+        self.encoder_transformer.transformer.layers = nn.ModuleList([_TLayer() for _ in range(TR_LAYERS)])
+        self.downsample = nn.Module()
+        self.downsample.conv = nn.Module()
+        self.downsample.conv.conv = nn.Module()
+        self.downsample.conv.conv.conv = nn.Conv1d(DIM, DIM, 4, stride=2, bias=False)
+
+    def seanet_encode(self, x: torch.Tensor) -> torch.Tensor:
+        mods = self.encoder.model
+
+        def sconv(x, m, stride=1):  # causal strided conv: left pad k - stride zeros
+            c = m.conv.conv
+            return F.conv1d(F.pad(x, (c.kernel_size[0] - stride, 0)), c.weight, c.bias, stride=stride)
+
+        x = sconv(x, mods[0])
+        i = 1
+        for r in reversed(RATIOS):
+            blk = mods[i].block
+            y = sconv(F.elu(x), blk[1])
+            y = sconv(F.elu(y), blk[3])
+            x = x + y
+            x = sconv(F.elu(x), mods[i + 2], stride=r)
+            i += 3
+        return sconv(F.elu(x), mods[i + 1])
+
+    def _transformer_layers(self, x: torch.Tensor, layers) -> torch.Tensor:
+        saved = self.decoder_transformer.transformer.layers
+        self.decoder_transformer.transformer.layers = layers
+        try:
+            return self.transformer(x)
+        finally:
+            self.decoder_transformer.transformer.layers = saved
+
+    @staticmethod
+    def _rvq_encode(rvq: "_RVQ", x: torch.Tensor, n_q: int) -> torch.Tensor:
+        """moshi ResidualVectorQuantization.encode: nearest centroid (cdist + argmin) per layer on the
+        running residual of the input projection."""
+        res = rvq.input_proj(x).transpose(1, 2)  # [B, T, 256]
+        out = []
+        for k in range(n_q):
+            emb = rvq.vq.layers[k]._codebook.embedding
+            idx = torch.cdist(res.reshape(1, -1, Q_DIM), emb[None], p=2)[0].argmin(dim=-1).view(res.shape[:2])
+            out.append(idx)
+            res = res - F.embedding(idx, emb)
+        return torch.stack(out, dim=1)  # [B, n_q, T]
+
+    @torch.no_grad()
+    def encode(self, wav: torch.Tensor) -> torch.Tensor:
+        """wav [B, 1, L] fp32 at 24 kHz -> codes [B, num_codebooks, ceil(L / 1920)] int64 (moshi
+        ``MimiModel.encode``; the waveform is zero-padded on the right to a whole number of frames)."""
+        if not hasattr(self, "encoder"):
+            raise RuntimeError("call _build_encoder() before loading encoder weights")
+        L = wav.shape[-1]
+        pad = (-L) % 1920
+        x = F.pad(wav, (0, pad)) if pad else wav
+        emb = self.seanet_encode(x)
+        emb = self._transformer_layers(emb, self.encoder_transformer.transformer.layers)
+        ds = self.downsample.conv.conv.conv
+        emb = F.conv1d(F.pad(emb, (2, 0), mode="replicate"), ds.weight, None, stride=2)
+        nq = self.num_codebooks
+        first = self._rvq_encode(self.quantizer.rvq_first, emb, 1)
+        if nq > 1:
+            return torch.cat([first, self._rvq_encode(self.quantizer.rvq_rest, emb, nq - 1)], dim=1)
+        return first

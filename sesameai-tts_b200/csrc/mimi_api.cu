@@ -46,6 +46,8 @@ struct mimi_ctx {
   float final_bias;
   // activations (per utterance)
   float *q512, *e, *xs, *xn, *qkv, *att, *ff, *c0, *u[4], *r[4];
+  // encode side
+  float *enc_res1[4], *enc_down[4], *enc_final, *dsw, *enorm, *wavbuf, *p1, *p2, *dots;
   size_t pad_rows_bytes;
 };
 
@@ -62,6 +64,22 @@ static size_t mimi_carve(mimi_ctx* x, char* base) {
     ch /= 2;
   }
   x->finalw = cv.take(3 * 64);
+  {
+    int ech = 64;
+    const int eratio[4] = {4, 5, 6, 8};
+    for (int s = 0; s < 4; ++s) {
+      x->enc_res1[s] = cv.take((size_t)(ech / 2) * 3 * ech);
+      x->enc_down[s] = cv.take((size_t)(2 * ech) * 2 * eratio[s] * ech);
+      ech *= 2;
+    }
+    x->enc_final = cv.take((size_t)512 * 3 * 1024);
+    x->dsw = cv.take((size_t)512 * 4 * 512);
+    x->enorm = cv.take((size_t)32 * 2048);
+    x->wavbuf = cv.take(T * 1920 + 64);
+    x->p1 = cv.take(T * 256);
+    x->p2 = cv.take(T * 256);
+    x->dots = cv.take(T * 2048);
+  }
   x->q512 = cv.take(T * 512);
   x->e = cv.take(T * 512);
   x->xs = cv.take((L + PAD) * 512);
@@ -139,7 +157,21 @@ extern "C" int32_t mimi_create(const void* const* weights, int32_t n_weights, in
     ch /= 2;
   }
   mimi::k_pack_conv<<<1, 256, 0, st>>>(x->w[MIMI_W_FINAL], 1, 64, 3, x->finalw);
-  csm_count_launches(32 + 3 + 8 + 1);
+  {
+    int ech = 64;
+    const int eratio[4] = {4, 5, 6, 8};
+    for (int s = 0; s < 4; ++s) {
+      const float* const* sw = &x->w[MIMI_W_ENC_STAGE0 + 6 * s];
+      const long long n1 = (long long)(ech / 2) * ech * 3, n2 = (long long)(2 * ech) * ech * 2 * eratio[s];
+      mimi::k_pack_conv<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(sw[0], ech / 2, ech, 3, x->enc_res1[s]);
+      mimi::k_pack_conv<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(sw[4], 2 * ech, ech, 2 * eratio[s], x->enc_down[s]);
+      ech *= 2;
+    }
+    mimi::k_pack_conv<<<(512 * 1024 * 3 + 255) / 256, 256, 0, st>>>(x->w[MIMI_W_ENC_FINAL], 512, 1024, 3, x->enc_final);
+    mimi::k_pack_conv<<<(512 * 512 * 4 + 255) / 256, 256, 0, st>>>(x->w[MIMI_W_DOWNSAMPLE], 512, 512, 4, x->dsw);
+    mimi::k_row_sumsq256<<<32 * 2048 / 8, 256, 0, st>>>(x->emb, 32LL * 2048, x->enorm);
+  }
+  csm_count_launches(32 + 3 + 8 + 1 + 11);
   e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaMemcpyAsync(&x->final_bias, x->w[MIMI_W_FINAL + 1], sizeof(float), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -149,6 +181,81 @@ extern "C" int32_t mimi_create(const void* const* weights, int32_t n_weights, in
 }
 
 extern "C" void mimi_destroy(mimi_ctx* x) { delete x; }
+
+// 8-layer causal transformer (context 250) in place on xs [L, 512]; lw0 = first of the 80 layer tensors
+static int mimi_transformer(mimi_ctx* x, float* xs, long long L, int w_layer0, cudaStream_t st) {
+  using namespace mimi;
+  for (int l = 0; l < 8; ++l) {
+    const float* const* lw = &x->w[w_layer0 + 10 * l];
+    k_layernorm512<<<(unsigned)((L + 7) / 8), 256, 0, st>>>(xs, lw[2], lw[3], (int)L, 1e-5f, x->xn);
+    MCU_TRY(gemm(st, x->xn, 512, lw[0], x->qkv, 1536, L, 1536, 512, nullptr, 0, 0));
+    k_rope_qk<<<(unsigned)((L * 512 + 255) / 256), 256, 0, st>>>(x->qkv, (int)L);
+    k_attn_window<<<dim3((unsigned)((L + 3) / 4), 8), 128, 0, st>>>(x->qkv, (int)L, 250, x->att);
+    MCU_TRY(gemm(st, x->att, 512, lw[1], xs, 512, L, 512, 512, nullptr, 0, F_LAYERSCALE | F_RESID, xs, 512, lw[8]));
+    k_layernorm512<<<(unsigned)((L + 7) / 8), 256, 0, st>>>(xs, lw[4], lw[5], (int)L, 1e-5f, x->xn);
+    MCU_TRY(gemm(st, x->xn, 512, lw[6], x->ff, 2048, L, 2048, 512, nullptr, 0, F_GELU));
+    MCU_TRY(gemm(st, x->ff, 2048, lw[7], xs, 512, L, 512, 2048, nullptr, 0, F_LAYERSCALE | F_RESID, xs, 512, lw[9]));
+    csm_count_launches(4);
+  }
+  MCU_TRY(cudaGetLastError());
+  return CSM_OK;
+}
+
+extern "C" int32_t mimi_encode(mimi_ctx* x, const float* wav, int32_t B, int64_t Lin, int32_t K, int64_t* codes, void* stream) {
+  if (!x) return csm_set_error(CSM_ERR_STATE, "mimi_encode: null context");
+  if (!wav || !codes || B < 1 || Lin < 1 || K < 1 || K > 32) return csm_set_error(CSM_ERR_ARG, "mimi_encode: bad arguments");
+  const long long T = (Lin + 1919) / 1920, Lp = T * 1920;
+  if (T > x->max_frames) return csm_set_error(CSM_ERR_OVERFLOW, "mimi_encode: more frames than the codec was created for");
+  cudaStream_t st = (cudaStream_t)stream;
+  using namespace mimi;
+  const int eratio[4] = {4, 5, 6, 8};
+  for (int b = 0; b < B; ++b) {
+    // waveform, zero-padded to whole frames, 8 zero samples in front (causal k = 7)
+    float* wv = x->wavbuf + 8;
+    MCU_TRY(cudaMemsetAsync(x->wavbuf, 0, (size_t)(Lp + 8) * sizeof(float), st));
+    MCU_TRY(cudaMemcpyAsync(wv, wav + (size_t)b * Lin, (size_t)Lin * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    // SEANet encoder, mirrored onto the decoder's activation buffers (same shapes in reverse order)
+    float* cur = x->u[3] + (size_t)PAD * 64;  // [Lp, 64]
+    k_enc_conv0<<<(unsigned)((Lp * 64 + 255) / 256), 256, 0, st>>>(wv, x->w[MIMI_W_ENC_CONV0], x->w[MIMI_W_ENC_CONV0 + 1], Lp, cur);
+    csm_count_launches(1);
+    long long rows = Lp;
+    int ch = 64;
+    for (int s = 0; s < 4; ++s) {
+      const float* const* sw = &x->w[MIMI_W_ENC_STAGE0 + 6 * s];
+      float* hid = x->r[3 - s];  // [rows, ch/2]
+      MCU_TRY(gemm(st, cur - 2 * ch, ch, x->enc_res1[s], hid, ch / 2, rows, ch / 2, 3 * ch, sw[1], ch / 2, F_A_ELU));
+      MCU_TRY(gemm(st, hid, ch / 2, sw[2], cur, ch, rows, ch, ch / 2, sw[3], ch, F_A_ELU | F_RESID, cur, ch));
+      const int r = eratio[s];
+      float* nxt = (s < 3 ? x->u[2 - s] + (size_t)PAD * 2 * ch : x->c0 + (size_t)PAD * 1024);  // [rows/r, 2ch]
+      MCU_TRY(gemm(st, cur - (size_t)r * ch, (long long)r * ch, x->enc_down[s], nxt, 2 * ch, rows / r, 2 * ch, 2 * r * ch, sw[5],
+                   2 * ch, F_A_ELU));
+      rows /= r;
+      cur = nxt;
+      ch *= 2;
+    }
+    const long long L2 = rows;  // = 2T
+    float* xs = x->xs + (size_t)PAD * 512;
+    MCU_TRY(gemm(st, cur - 2 * 1024, 1024, x->enc_final, xs, 512, L2, 512, 3 * 1024, x->w[MIMI_W_ENC_FINAL + 1], 512, F_A_ELU));
+    int rc = mimi_transformer(x, xs, L2, MIMI_W_ENC_LAYER0, st);
+    if (rc != CSM_OK) return rc;
+    // stride-2 downsample with replicate padding
+    k_pad_rows<<<2, 256, 0, st>>>(xs, 512, 1);
+    MCU_TRY(gemm(st, xs - 2 * 512, 1024, x->dsw, x->e, 512, T, 512, 4 * 512, nullptr, 0, 0));
+    k_pad_rows<<<2, 256, 0, st>>>(xs, 512, 0);
+    // split RVQ: semantic codebook on its own projection, acoustic codebooks on theirs
+    MCU_TRY(gemm(st, x->e, 512, x->w[MIMI_W_RVQ_FIRST_INPROJ], x->p1, 256, T, 256, 512, nullptr, 0, 0));
+    MCU_TRY(gemm(st, x->e, 512, x->w[MIMI_W_RVQ_REST_INPROJ], x->p2, 256, T, 256, 512, nullptr, 0, 0));
+    for (int k = 0; k < K; ++k) {
+      float* res = k == 0 ? x->p1 : x->p2;
+      const float* emb = x->emb + (size_t)k * 2048 * 256;
+      MCU_TRY(gemm(st, res, 256, emb, x->dots, 2048, T, 2048, 256, nullptr, 0, 0));
+      k_rvq_argmin<<<(unsigned)T, 256, 0, st>>>(x->dots, x->enorm + (size_t)k * 2048, emb, res, codes + ((size_t)b * K + k) * T);
+    }
+    csm_count_launches(2 + K);
+    MCU_TRY(cudaGetLastError());
+  }
+  return CSM_OK;
+}
 
 extern "C" int32_t mimi_decode(mimi_ctx* x, const int64_t* codes, int32_t B, int32_t K, int32_t T, float* out, void* stream) {
   if (!x) return csm_set_error(CSM_ERR_STATE, "mimi_decode: null context");
@@ -165,17 +272,9 @@ extern "C" int32_t mimi_decode(mimi_ctx* x, const int64_t* codes, int32_t B, int
     float* xs = x->xs + (size_t)PAD * 512;
     k_upsample2<<<(unsigned)((L * 512 + 255) / 256), 256, 0, st>>>(x->e, x->w[MIMI_W_UPSAMPLE], T, 512, xs);
     csm_count_launches(2);
-    for (int l = 0; l < 8; ++l) {
-      const float* const* lw = &x->w[MIMI_W_LAYER0 + 10 * l];
-      k_layernorm512<<<(unsigned)((L + 7) / 8), 256, 0, st>>>(xs, lw[2], lw[3], (int)L, 1e-5f, x->xn);
-      MCU_TRY(gemm(st, x->xn, 512, lw[0], x->qkv, 1536, L, 1536, 512, nullptr, 0, 0));
-      k_rope_qk<<<(unsigned)((L * 512 + 255) / 256), 256, 0, st>>>(x->qkv, (int)L);
-      k_attn_window<<<dim3((unsigned)((L + 3) / 4), 8), 128, 0, st>>>(x->qkv, (int)L, 250, x->att);
-      MCU_TRY(gemm(st, x->att, 512, lw[1], xs, 512, L, 512, 512, nullptr, 0, F_LAYERSCALE | F_RESID, xs, 512, lw[8]));
-      k_layernorm512<<<(unsigned)((L + 7) / 8), 256, 0, st>>>(xs, lw[4], lw[5], (int)L, 1e-5f, x->xn);
-      MCU_TRY(gemm(st, x->xn, 512, lw[6], x->ff, 2048, L, 2048, 512, nullptr, 0, F_GELU));
-      MCU_TRY(gemm(st, x->ff, 2048, lw[7], xs, 512, L, 512, 2048, nullptr, 0, F_LAYERSCALE | F_RESID, xs, 512, lw[9]));
-      csm_count_launches(4);
+    {
+      int rc = mimi_transformer(x, xs, L, MIMI_W_LAYER0, st);
+      if (rc != CSM_OK) return rc;
     }
     // SEANet decoder
     float* c0 = x->c0 + (size_t)PAD * 1024;

@@ -257,6 +257,86 @@ __global__ void k_final_conv(const float* __restrict__ x /*[L, 64], 2 zero pad r
   y[t] = a;
 }
 
+// ---- encode side --------------------------------------------------------------------------------
+// first encoder conv: 1 -> 64 channels, k = 7, causal; x is the waveform with >= 6 zero samples in front
+__global__ void k_enc_conv0(const float* __restrict__ x, const float* __restrict__ w /*[64][7]*/, const float* __restrict__ b,
+                            long long L, float* __restrict__ y /*[L, 64]*/) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= L * 64) return;
+  const int co = i & 63;
+  const long long t = i >> 6;
+  float a = b[co];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) a = fmaf(w[co * 7 + k], x[t - 6 + k], a);
+  y[i] = a;
+}
+// replicate padding for the stride-2 downsample: rows -1 and -2 of xs become copies of row 0 (mode 1),
+// or are cleared again afterwards (mode 0) because the decoder expects zero pad rows there
+__global__ void k_pad_rows(float* __restrict__ xs, int C, int mode) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float v = mode ? xs[c] : 0.f;
+  xs[c - C] = v;
+  xs[c - 2 * C] = v;
+}
+// |e_j|^2 of every codebook entry
+__global__ void k_row_sumsq256(const float* __restrict__ emb, long long rows, float* __restrict__ out) {
+  const long long r = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int d = lane; d < 256; d += 32) {
+    const float v = emb[r * 256 + d];
+    s = fmaf(v, v, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[r] = s;
+}
+// nearest centroid of one RVQ layer: argmin_j(|e_j|^2 - 2 x.e_j) (first index on ties, as torch.argmin),
+// writes the code and subtracts the chosen centroid from the running residual
+__global__ void __launch_bounds__(256) k_rvq_argmin(const float* __restrict__ dots /*[T, 2048]*/,
+                                                    const float* __restrict__ enorm /*[2048]*/,
+                                                    const float* __restrict__ emb /*[2048, 256]*/, float* __restrict__ res
+                                                    /*[T, 256]*/, int64_t* __restrict__ codes /*[T]*/) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float best = INFINITY;
+  int bi = 0x7fffffff;
+  for (int j = tid; j < 2048; j += 256) {
+    const float d = enorm[j] - 2.0f * dots[(long long)t * 2048 + j];
+    if (d < best) {
+      best = d;
+      bi = j;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob < best || (ob == best && oi < bi)) {
+      best = ob;
+      bi = oi;
+    }
+  }
+  if (lane == 0) {
+    sv[warp] = best;
+    si[warp] = bi;
+  }
+  __syncthreads();
+  best = sv[0];
+  bi = si[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w)
+    if (sv[w] < best || (sv[w] == best && si[w] < bi)) {
+      best = sv[w];
+      bi = si[w];
+    }
+  if (tid == 0) codes[t] = bi;
+  res[(long long)t * 256 + tid] -= emb[(long long)bi * 256 + tid];
+}
+
 // ---- weight packing (create time) ---------------------------------------------------------------
 __global__ void k_pack_embedding(const float* __restrict__ esum, const float* __restrict__ usage, float* __restrict__ out) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // [2048][256]

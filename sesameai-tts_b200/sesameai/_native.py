@@ -13,7 +13,7 @@ _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libcsm_b200.so")
 
 MIMI_W_CODEBOOK0, MIMI_W_RVQ_FIRST_PROJ, MIMI_W_RVQ_REST_PROJ, MIMI_W_UPSAMPLE = 0, 64, 65, 66
-MIMI_W_LAYER0, MIMI_W_CONV0, MIMI_W_STAGE0, MIMI_W_FINAL, MIMI_W_COUNT = 67, 147, 149, 173, 175
+MIMI_W_LAYER0, MIMI_W_CONV0, MIMI_W_STAGE0, MIMI_W_FINAL, MIMI_W_COUNT = 67, 147, 149, 173, 286
 PREFILL_AUTO, PREFILL_SMALL_ROW, PREFILL_TENSOR = 0, 1, 2
 PATH_AUTO, PATH_DIRECT, PATH_GRAPH, PATH_MEGA = 0, 1, 2, 3
 CSM_OK, CSM_ERR_ARG, CSM_ERR_CUDA, CSM_ERR_STATE, CSM_ERR_OVERFLOW, CSM_ERR_WORKSPACE = 0, -1, -2, -3, -4, -5
@@ -97,6 +97,7 @@ PROTOTYPES = {
     "mimi_create": (C.c_int32, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p,
                                 C.POINTER(C.c_void_p)]),
     "mimi_decode": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mimi_encode": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "mimi_destroy": (None, [C.c_void_p]),
     "csm_debug_set_trace": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "csm_k_sample_topk": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p,

@@ -4,8 +4,8 @@
 the ``kyutai/moshiko`` tokenizer checkpoint load as they are; the arithmetic runs in
 libcsm_b200.so (``mimi_decode``).  No PyTorch / CPU execution path exists here.
 
-``encode`` (voice-prompt audio -> codes) is the next row of the scope table and is
-not implemented: callers that pass context audio get a clear error instead of a silent fallback.
+``encode`` (voice-prompt audio -> codes) runs in the same library
+(``mimi_encode``): SEANet encoder, encoder transformer, stride-2 downsample, split-RVQ search.
 """
 from __future__ import annotations
 
@@ -24,13 +24,39 @@ MIMI_NAME = "tokenizer-e351c8d8-checkpoint125.safetensors"
 _RATIOS = (8, 6, 5, 4)
 
 
-def _conv(cin: int, cout: int, k: int) -> nn.Module:
+def _conv(cin: int, cout: int, k: int, bias: bool = True) -> nn.Module:
     m = nn.Module()
     m.conv = nn.Module()
     m.conv.conv = nn.Module()
     m.conv.conv.weight = nn.Parameter(torch.empty(cout, cin, k))
-    m.conv.conv.bias = nn.Parameter(torch.empty(cout))
+    if bias:
+        m.conv.conv.bias = nn.Parameter(torch.empty(cout))
     return m
+
+
+def _transformer_layers() -> nn.ModuleList:
+    layers = []
+    for _ in range(8):
+        l = nn.Module()
+        l.self_attn = nn.Module()
+        l.self_attn.in_proj_weight = nn.Parameter(torch.empty(1536, 512))
+        l.self_attn.out_proj = nn.Module()
+        l.self_attn.out_proj.weight = nn.Parameter(torch.empty(512, 512))
+        for nm in ("norm1", "norm2"):
+            n = nn.Module()
+            n.weight = nn.Parameter(torch.ones(512))
+            n.bias = nn.Parameter(torch.zeros(512))
+            setattr(l, nm, n)
+        l.linear1 = nn.Module()
+        l.linear1.weight = nn.Parameter(torch.empty(2048, 512))
+        l.linear2 = nn.Module()
+        l.linear2.weight = nn.Parameter(torch.empty(512, 2048))
+        for nm in ("layer_scale_1", "layer_scale_2"):
+            sc = nn.Module()
+            sc.scale = nn.Parameter(torch.full((512,), 0.01))
+            setattr(l, nm, sc)
+        layers.append(l)
+    return nn.ModuleList(layers)
 
 
 def _convtr(cin: int, cout: int, k: int) -> nn.Module:
@@ -82,28 +108,7 @@ class MimiCodec(nn.Module):
         self.upsample.convtr.convtr.convtr.weight = nn.Parameter(torch.empty(512, 1, 4))
         self.decoder_transformer = nn.Module()
         self.decoder_transformer.transformer = nn.Module()
-        layers = []
-        for _ in range(8):
-            l = nn.Module()
-            l.self_attn = nn.Module()
-            l.self_attn.in_proj_weight = nn.Parameter(torch.empty(1536, 512))
-            l.self_attn.out_proj = nn.Module()
-            l.self_attn.out_proj.weight = nn.Parameter(torch.empty(512, 512))
-            for nm in ("norm1", "norm2"):
-                n = nn.Module()
-                n.weight = nn.Parameter(torch.ones(512))
-                n.bias = nn.Parameter(torch.zeros(512))
-                setattr(l, nm, n)
-            l.linear1 = nn.Module()
-            l.linear1.weight = nn.Parameter(torch.empty(2048, 512))
-            l.linear2 = nn.Module()
-            l.linear2.weight = nn.Parameter(torch.empty(512, 2048))
-            for nm in ("layer_scale_1", "layer_scale_2"):
-                s = nn.Module()
-                s.scale = nn.Parameter(torch.full((512,), 0.01))
-                setattr(l, nm, s)
-            layers.append(l)
-        self.decoder_transformer.transformer.layers = nn.ModuleList(layers)
+        self.decoder_transformer.transformer.layers = _transformer_layers()
         self.decoder = nn.Module()
         model: List[nn.Module] = [_conv(512, 1024, 7)]
         ch = 1024
@@ -117,6 +122,22 @@ class MimiCodec(nn.Module):
         model.append(nn.Identity())
         model.append(_conv(64, 1, 3))
         self.decoder.model = nn.ModuleList(model)
+        # encode side: SEANet encoder (ratios reversed), encoder transformer, stride-2 downsample
+        enc: List[nn.Module] = [_conv(1, 64, 7)]
+        ch = 64
+        for r in reversed(_RATIOS):
+            res = nn.Module()
+            res.block = nn.ModuleList([nn.Identity(), _conv(ch, ch // 2, 3), nn.Identity(), _conv(ch // 2, ch, 1)])
+            enc += [res, nn.Identity(), _conv(ch, 2 * ch, 2 * r)]
+            ch *= 2
+        enc += [nn.Identity(), _conv(ch, 512, 3)]
+        self.encoder = nn.Module()
+        self.encoder.model = nn.ModuleList(enc)
+        self.encoder_transformer = nn.Module()
+        self.encoder_transformer.transformer = nn.Module()
+        self.encoder_transformer.transformer.layers = _transformer_layers()
+        self.downsample = nn.Module()
+        self.downsample.conv = _conv(512, 512, 4, bias=False)
         self._ctx: Optional[int] = None
         self._keep: Dict[str, object] = {}
 
@@ -146,6 +167,21 @@ class MimiCodec(nn.Module):
                   sd[f"decoder.model.{i + 1}.block.1.conv.conv.weight"], sd[f"decoder.model.{i + 1}.block.1.conv.conv.bias"],
                   sd[f"decoder.model.{i + 1}.block.3.conv.conv.weight"], sd[f"decoder.model.{i + 1}.block.3.conv.conv.bias"]]
         w += [sd["decoder.model.14.conv.conv.weight"], sd["decoder.model.14.conv.conv.bias"]]
+        # encode side, in MIMI_W_ENC_* order
+        w += [sd["encoder.model.0.conv.conv.weight"], sd["encoder.model.0.conv.conv.bias"]]
+        for s in range(4):
+            i = 1 + 3 * s
+            w += [sd[f"encoder.model.{i}.block.1.conv.conv.weight"], sd[f"encoder.model.{i}.block.1.conv.conv.bias"],
+                  sd[f"encoder.model.{i}.block.3.conv.conv.weight"], sd[f"encoder.model.{i}.block.3.conv.conv.bias"],
+                  sd[f"encoder.model.{i + 2}.conv.conv.weight"], sd[f"encoder.model.{i + 2}.conv.conv.bias"]]
+        w += [sd["encoder.model.14.conv.conv.weight"], sd["encoder.model.14.conv.conv.bias"]]
+        for l in range(8):
+            pre = f"encoder_transformer.transformer.layers.{l}."
+            w += [sd[pre + n] for n in ("self_attn.in_proj_weight", "self_attn.out_proj.weight", "norm1.weight", "norm1.bias",
+                                        "norm2.weight", "norm2.bias", "linear1.weight", "linear2.weight",
+                                        "layer_scale_1.scale", "layer_scale_2.scale")]
+        w += [sd["downsample.conv.conv.conv.weight"], sd["quantizer.rvq_first.input_proj.weight"],
+              sd["quantizer.rvq_rest.input_proj.weight"]]
         assert len(w) == _native.MIMI_W_COUNT
         return w
 
@@ -197,14 +233,26 @@ class MimiCodec(nn.Module):
         return out
 
     def encode(self, wav: torch.Tensor) -> torch.Tensor:
-        raise NotImplementedError(
-            "sesameai(B200): Mimi encode (voice-prompt audio -> codes) is not part of this release's hot path "
-            "(SURVEY.md 8f 'next'); pass pre-tokenised context or run the reference encoder")
+        """wav [B, 1, L] fp32 at 24 kHz -> codes [B, num_codebooks, ceil(L/1920)] int64, as moshi's
+        ``MimiModel.encode`` (reference ``generator.py:86``)."""
+        if wav.dim() != 3 or wav.shape[1] != 1:
+            raise ValueError("wav must be [B, 1, L]")
+        if self._ctx is None:
+            self.prepare()
+        dev = next(self.parameters()).device
+        w = wav.to(device=dev, dtype=torch.float32).contiguous()
+        B, _, L = w.shape
+        T = (L + 1919) // 1920
+        codes = torch.empty(B, self.num_codebooks, T, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            _native.check(_native.lib().mimi_encode(self._ctx, w.data_ptr(), B, L, self.num_codebooks, codes.data_ptr(),
+                                                    torch.cuda.current_stream(dev).cuda_stream))
+        w.record_stream(torch.cuda.current_stream(dev))
+        return codes
 
 
 def get_mimi(filename: Optional[str], device="cuda", max_frames: int = 1200) -> MimiCodec:
-    """Counterpart of moshi ``loaders.get_mimi``: build the codec and load a safetensors checkpoint
-    (decode-side tensors; encoder tensors in the file are ignored)."""
+    """Counterpart of moshi ``loaders.get_mimi``: build the codec and load a safetensors checkpoint."""
     codec = MimiCodec(max_frames=max_frames)
     if filename is not None:
         from safetensors.torch import load_file
@@ -213,7 +261,7 @@ def get_mimi(filename: Optional[str], device="cuda", max_frames: int = 1200) -> 
         own = codec.state_dict()
         missing = [k for k in own if k not in sd]
         if missing:
-            raise RuntimeError(f"Mimi checkpoint lacks decode tensors: {missing[:4]} ...")
+            raise RuntimeError(f"Mimi checkpoint lacks tensors: {missing[:4]} ...")
         codec.load_state_dict({k: sd[k].float() for k in own})
     codec.to(device=device, dtype=torch.float32)
     return codec

@@ -105,7 +105,27 @@ def test_reference_service_loop_runs_unchanged(rig):
     assert audio.shape == (5 * 1920,) and torch.isfinite(audio).all()
 
 
-def test_context_audio_needs_encode(rig):
-    _, _, gen = rig
-    with pytest.raises(NotImplementedError):
-        gen.generate("hi", 0, [Segment(speaker=0, text="ctx", audio=torch.zeros(24000))], max_audio_length_ms=400)
+def test_generate_with_voice_prompt_context(rig):
+    """Context segments carry audio: Generator._tokenize_segment runs Mimi encode on the GPU and the
+    prompt gets text frames + audio frames + the all-zero EOS frame (reference generator.py:78-109)."""
+    om, omimi, gen = rig
+    wav = torch.empty(24000)
+    syn.hash_uniform_(wav, 12, 1, 0.4)
+    seg = Segment(speaker=0, text="ctx", audio=wav)
+    tok, msk = gen._tokenize_segment(seg)
+    n_text = len(FakeTokenizer().encode("[0]ctx"))
+    n_audio = 13 + 1  # ceil(24000 / 1920) frames + EOS frame
+    assert tok.shape == (n_text + n_audio, 33) and msk.shape == tok.shape
+    assert msk[:n_text, -1].all() and not msk[:n_text, :-1].any()
+    assert msk[n_text:, :-1].all() and not msk[n_text:, -1].any()
+    assert int(tok[-1].abs().sum()) == 0  # EOS frame
+    with torch.inference_mode():
+        want = omimi.encode(wav.view(1, 1, -1))[0].t()
+    assert (tok[n_text:-1, :-1].cpu() == want).float().mean().item() >= 0.97
+    real_decode = gen._audio_tokenizer.decode
+    gen._audio_tokenizer.decode = lambda codes: real_decode(codes % 2048)
+    try:
+        audio = gen.generate("hi", 0, [seg], max_audio_length_ms=400, temperature=0.9, topk=50)
+    finally:
+        gen._audio_tokenizer.decode = real_decode
+    assert audio.shape == (5 * 1920,) and torch.isfinite(audio).all()
