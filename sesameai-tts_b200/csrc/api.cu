@@ -58,6 +58,9 @@ struct StackDev {
   // activations
   bf16 *h, *q, *att, *act;
   bf16 *xn, *qkv;  // tensor-core prefill only (backbone)
+  // megakernel: fragment-major packed matrices and tagged activation words
+  std::vector<bf16*> fqkv, fo, fgu, fd;
+  uint32_t *t_h, *t_q, *t_kv, *t_att, *t_act;
 };
 
 struct csm_ctx {
@@ -66,7 +69,12 @@ struct csm_ctx {
   StackDev bb, dec;
   const bf16 *text_emb, *audio_emb, *proj, *c0_head;
   bf16* head_t;   // [C-1][Vp][Dd]
-  bf16* head0_proj;  // stacked [codebook0_head (Vp rows) ; projection (Dd rows)] x D
+  bf16* f_head0;  // fragment-major stacked [codebook0_head (Vf rows) ; projection (Dd rows)] x D
+  bf16* f_heads;  // fragment-major audio heads [C-1][Vf][Dd]
+  int Vf;         // audio vocab rounded up to 16 rows (fragment-major row groups)
+  uint32_t* t_logits;  // tagged logits [Vf]
+  char* tagged_base;   // all tagged words live in [tagged_base, tagged_base + tagged_bytes): zeroed at create
+  size_t tagged_bytes;
   bf16* proj_table;  // projection(audio_embeddings[cb*V + tok]) for cb < C-1: [(C-1)*V][Dd]
   bf16* dec_in;   // [2B][D]
   bf16* logits;   // [B][Vp]
@@ -82,6 +90,7 @@ struct csm_ctx {
   bool mega_ok;
   unsigned long long* trace;  // optional device buffer [n_phases][8] (csm_debug_set_trace)
   mega::PfTable pf_table;     // weight-prefetch schedule, passed in kernel-parameter space
+  int mega_Rbb[4], mega_Rdec[4], mega_Rh0, mega_Rh;  // row-group heights (mega_pick_R): [qkv, o, gate/up, down] per stack, stacked head, audio heads
   std::map<int, cudaGraphExec_t> graphs;  // keyed by B
   std::map<int, unsigned long long> graph_nodes;
 };
@@ -134,6 +143,22 @@ static void carve_stack(Carver& cv, StackDev& s, const csm_stack_config& c, int 
   s.q = cv.take<bf16>((size_t)rows * c.dim);
   s.att = cv.take<bf16>((size_t)rows * c.dim);
   s.act = cv.take<bf16>((size_t)rows * c.ff);
+  s.fqkv.resize(c.layers); s.fo.resize(c.layers); s.fgu.resize(c.layers); s.fd.resize(c.layers);
+  for (int l = 0; l < c.layers; ++l) {
+    s.fqkv[l] = cv.take<bf16>(qkv_rows * c.dim);
+    s.fo[l] = cv.take<bf16>((size_t)c.dim * c.dim);
+    s.fgu[l] = cv.take<bf16>((size_t)2 * c.ff * c.dim);
+    s.fd[l] = cv.take<bf16>((size_t)c.dim * c.ff);
+  }
+}
+static void carve_tagged(Carver& cv, StackDev& s) {
+  const csm_stack_config& c = s.c;
+  const size_t krows = (size_t)c.kv_heads * s.hd;
+  s.t_h = cv.take<uint32_t>((size_t)2 * c.dim);
+  s.t_q = cv.take<uint32_t>((size_t)2 * c.dim);
+  s.t_kv = cv.take<uint32_t>((size_t)2 * 2 * krows);
+  s.t_att = cv.take<uint32_t>((size_t)2 * c.dim);
+  s.t_act = cv.take<uint32_t>((size_t)2 * c.ff);
 }
 
 static size_t carve_all(csm_ctx* x, char* base) {
@@ -148,7 +173,9 @@ static size_t carve_all(csm_ctx* x, char* base) {
   x->dec.xn = cv.take<bf16>((size_t)2 * x->max_batch * c.decoder.dim);
   x->dec.qkv = cv.take<bf16>((size_t)2 * x->max_batch * (c.decoder.heads + 2 * c.decoder.kv_heads) * (c.decoder.dim / c.decoder.heads));
   x->head_t = cv.take<bf16>((size_t)(c.codebooks - 1) * x->Vp * c.decoder.dim);
-  x->head0_proj = cv.take<bf16>((size_t)(x->Vp + c.decoder.dim) * c.backbone.dim);
+  x->Vf = (c.audio_vocab + 15) & ~15;
+  x->f_head0 = cv.take<bf16>((size_t)(x->Vf + c.decoder.dim) * c.backbone.dim);
+  x->f_heads = cv.take<bf16>((size_t)(c.codebooks - 1) * x->Vf * c.decoder.dim);
   x->proj_table = cv.take<bf16>((size_t)(c.codebooks - 1) * c.audio_vocab * c.decoder.dim);
   x->dec_in = cv.take<bf16>((size_t)2 * x->max_batch * c.backbone.dim);
   x->logits = cv.take<bf16>((size_t)x->max_batch * x->Vp);
@@ -158,6 +185,14 @@ static size_t carve_all(csm_ctx* x, char* base) {
   x->d_params = cv.take<FrameParams>(1);
   x->d_sync = cv.take<mega::Sync>(1);
   x->d_phases = cv.take<mega::Phase>(mega_phase_count(c));
+  cv.off = (cv.off + 255) & ~(size_t)255;
+  const size_t t0 = cv.off;
+  carve_tagged(cv, x->bb);
+  carve_tagged(cv, x->dec);
+  x->t_logits = cv.take<uint32_t>((size_t)x->Vf);
+  cv.off = (cv.off + 255) & ~(size_t)255;
+  x->tagged_base = base ? base + t0 : nullptr;
+  x->tagged_bytes = cv.off - t0;
   return (cv.off + 255) & ~(size_t)255;
 }
 
@@ -326,86 +361,158 @@ static cudaError_t frame_tail(csm_ctx* x, int B, cudaStream_t st) {
 
 // ---------------------------------------------------------------------------------------------
 // Megakernel phase table for one batch-1 decode frame (mega.cuh).
-static mega::Phase gemv_phase_desc(const bf16* W, int rows, int K, const bf16* xin, int ldx, int nb, int epi,
-                                   const bf16* norm_scale, float eps, bf16* out, int ldo) {
+
+// Row-group height of a fragment-major matrix: the R in {8, 16} that gives the busiest CTA the fewest
+// rows (ties -> 16: half as many mma instructions and epilogue items).
+static int mega_pick_R(int rows, int ncta) {
+  const int g16 = (rows + 15) / 16, g8 = (rows + 7) / 8;
+  const int m16 = ((g16 + ncta - 1) / ncta) * 16, m8 = ((g8 + ncta - 1) / ncta) * 8;
+  return m8 < m16 ? 8 : 16;
+}
+
+// Fragment-major re-pack (see mega.cuh): dst[group][k block of 32][R*64 bytes]; rows >= src_rows are zero.
+__global__ void k_pack_frag(const bf16* __restrict__ src, int src_rows, int K, int R, bf16* __restrict__ dst) {
+  const size_t KB = K / 32, upb = (size_t)R * 4;  // 16-byte units per block
+  const size_t groups = (src_rows + R - 1) / R, total = groups * KB * upb;
+  for (size_t u = blockIdx.x * (size_t)blockDim.x + threadIdx.x; u < total; u += (size_t)gridDim.x * blockDim.x) {
+    const size_t blk = u / upb;
+    const int w = (int)(u % upb);
+    const size_t g = blk / KB, kb = blk % KB;
+    int row, L;
+    if (R == 16) {
+      const int h = w >> 5;
+      L = w & 31;
+      row = (int)g * 16 + 2 * (L >> 2) + h;
+    } else {
+      L = w;
+      row = (int)g * 8 + (L >> 2);
+    }
+    const size_t k = kb * 32 + (size_t)(L & 3) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (row < src_rows) v = *reinterpret_cast<const uint4*>(src + (size_t)row * K + k);
+    reinterpret_cast<uint4*>(dst)[u] = v;
+  }
+}
+static void pack_frag(const bf16* src, int rows, int K, int R, bf16* dst, cudaStream_t st) {
+  k_pack_frag<<<1024, 256, 0, st>>>(src, rows, K, R, dst); COUNT_LAUNCH();
+}
+
+struct MegaBuild {
+  std::vector<mega::Phase> v;
+  int ncta;
+  int rot;  // CTA that receives the next phase's first row group (round-robin continues across phases)
+};
+
+static mega::Phase gemv_phase_desc(MegaBuild& mb, const bf16* Wf, int rows, int K, int R, const uint32_t* t_x, int ldx, int nb,
+                                   int epi, const bf16* norm_scale, float eps, uint32_t* t_out, int ldo) {
   mega::Phase ph;
   memset(&ph, 0, sizeof(ph));
   ph.type = mega::PH_GEMV; ph.epi = epi; ph.norm = norm_scale != nullptr; ph.nb = nb;
-  ph.W = W; ph.rows = rows; ph.K = K;
-  ph.KC = K < mega::KC_MAX ? K : mega::KC_MAX;
-  ph.R = mega::CHUNK_ELEMS / ph.KC;
-  // latency-bound small phases: half-size chunks (down to row pairs) so that more warps share the
-  // rows and the per-CTA imbalance shrinks; streaming phases keep full 8 KB chunks
-  while (ph.R > 2 && (rows + ph.R - 1) / ph.R < 148 * mega::NW) ph.R /= 2;
-  ph.G = (rows + ph.R - 1) / ph.R;
-  ph.x = xin; ph.ldx = ldx; ph.norm_scale = norm_scale; ph.eps = eps; ph.out = out; ph.ldo = ldo; ph.resid = out;
+  ph.W = Wf; ph.rows = rows; ph.K = K; ph.R = R;
+  ph.G = (rows + R - 1) / R;
+  ph.rot = mb.rot; ph.gq = ph.G / mb.ncta; ph.gr = ph.G % mb.ncta;
+  mb.rot = (mb.rot + ph.gr) % mb.ncta;
+  ph.t_x = t_x; ph.ldx = ldx; ph.norm_scale = norm_scale; ph.eps = eps; ph.t_out = t_out; ph.ldo = ldo;
   return ph;
 }
 
-static void stack_phases(csm_ctx* x, StackDev& s, int l, int nb, int pos_mode, int pos0, bool fused_attn,
-                         std::vector<mega::Phase>& v) {
+// src[n]: index of the phase that last wrote row n of the stack's residual stream (updated here)
+static void stack_phases(csm_ctx* x, StackDev& s, const int* R4, int l, int nb, int pos_mode, int pos0, bool fused_attn,
+                         MegaBuild& mb, int* src) {
   const csm_stack_config& c = s.c;
   const float eps = x->cfg.norm_eps;
   bf16* kc = s.kc + s.kv_layer_stride * l;
   bf16* vc = s.vc + s.kv_layer_stride * l;
   auto with_attn = [&](mega::Phase ph) {
-    ph.q = s.q; ph.kc = kc; ph.vc = vc; ph.rope = s.rope; ph.heads = c.heads; ph.kv_heads = c.kv_heads;
+    ph.t_q = s.t_q; ph.t_kv = s.t_kv; ph.kc = kc; ph.vc = vc; ph.rope = s.rope; ph.heads = c.heads; ph.kv_heads = c.kv_heads;
     ph.hd = s.hd; ph.slots = s.slots; ph.pos_mode = pos_mode; ph.pos0 = pos0;
     return ph;
   };
-  v.push_back(with_attn(gemv_phase_desc(s.wqkv[l], (c.heads + 2 * c.kv_heads) * s.hd, c.dim, s.h, c.dim, nb, EPI_ROPE_KV,
-                                        s.sa[l], eps, nullptr, 0)));
+  mega::Phase q = with_attn(gemv_phase_desc(mb, s.fqkv[l], (c.heads + 2 * c.kv_heads) * s.hd, c.dim, R4[0], s.t_h, c.dim, nb,
+                                            EPI_ROPE_KV, s.sa[l], eps, nullptr, 0));
+  q.x_src[0] = src[0]; q.x_src[1] = src[1];
+  const int iq = (int)mb.v.size();
+  mb.v.push_back(q);
+  int iatt = -1;
   if (!fused_attn) {
     mega::Phase a;
     memset(&a, 0, sizeof(a));
-    a.type = mega::PH_ATTN; a.nb = nb; a.att_out = s.att;
-    v.push_back(with_attn(a));
+    a.type = mega::PH_ATTN; a.nb = nb; a.t_out = s.t_att;
+    a = with_attn(a);
+    a.q_src = iq;
+    iatt = (int)mb.v.size();
+    mb.v.push_back(a);
   }
-  mega::Phase o = with_attn(gemv_phase_desc(s.wo[l], c.dim, c.dim, s.att, c.dim, nb, EPI_RESID, nullptr, eps, s.h, c.dim));
+  mega::Phase o = with_attn(gemv_phase_desc(mb, s.fo[l], c.dim, c.dim, R4[1], s.t_att, c.dim, nb, EPI_RESID, nullptr, eps,
+                                            s.t_h, c.dim));
   o.attn_prologue = fused_attn ? 1 : 0;
-  v.push_back(o);
-  v.push_back(gemv_phase_desc(s.wgu[l], 2 * c.ff, c.dim, s.h, c.dim, nb, EPI_SWIGLU, s.mlp[l], eps, s.act, c.ff));
-  v.push_back(gemv_phase_desc(s.wd[l], c.dim, c.ff, s.act, c.ff, nb, EPI_RESID, nullptr, eps, s.h, c.dim));
+  o.q_src = iq;
+  o.x_src[0] = o.x_src[1] = iatt;
+  o.resid_src[0] = src[0]; o.resid_src[1] = src[1];
+  src[0] = src[1] = (int)mb.v.size();
+  mb.v.push_back(o);
+  mega::Phase g = gemv_phase_desc(mb, s.fgu[l], 2 * c.ff, c.dim, R4[2], s.t_h, c.dim, nb, EPI_SWIGLU, s.mlp[l], eps, s.t_act, c.ff);
+  g.x_src[0] = g.x_src[1] = src[0];
+  const int ig = (int)mb.v.size();
+  mb.v.push_back(g);
+  mega::Phase d = gemv_phase_desc(mb, s.fd[l], c.dim, c.ff, R4[3], s.t_act, c.ff, nb, EPI_RESID, nullptr, eps, s.t_h, c.dim);
+  d.x_src[0] = d.x_src[1] = ig;
+  d.resid_src[0] = d.resid_src[1] = src[0];
+  src[0] = src[1] = (int)mb.v.size();
+  mb.v.push_back(d);
 }
 
-static void build_mega_phases(csm_ctx* x, std::vector<mega::Phase>& v) {
+static void build_mega_phases(csm_ctx* x, MegaBuild& mb) {
   const csm_config& c = x->cfg;
   const int D = c.backbone.dim, Dd = c.decoder.dim, V = c.audio_vocab, C = c.codebooks;
   const float eps = c.norm_eps;
-  auto sample = [&](int cb, bf16* next_in) {
+  auto sample = [&](int cb, int logits_src, uint32_t* t_next) {
     mega::Phase s;
     memset(&s, 0, sizeof(s));
-    s.type = mega::PH_SAMPLE; s.cb = cb; s.V = V; s.C = C; s.D = D; s.logits = x->logits; s.ldl = x->Vp;
-    s.next_in = next_in; s.audio_emb = x->audio_emb; s.next_table = x->proj_table; s.next_ld = Dd;
+    s.type = mega::PH_SAMPLE; s.cb = cb; s.V = V; s.C = C; s.D = D; s.t_logits = x->t_logits; s.logits_src = logits_src;
+    s.t_next = t_next; s.next_table = x->proj_table; s.next_ld = Dd;
     return s;
   };
   mega::Phase e;
   memset(&e, 0, sizeof(e));
-  e.type = mega::PH_EMBED; e.V = V; e.C = C; e.D = D; e.audio_emb = x->audio_emb; e.text_emb = x->text_emb; e.h_out = x->bb.h;
-  v.push_back(e);
-  for (int l = 0; l < c.backbone.layers; ++l) stack_phases(x, x->bb, l, 1, mega::POS_BACKBONE, 0, false, v);
+  e.type = mega::PH_EMBED; e.V = V; e.C = C; e.D = D; e.audio_emb = x->audio_emb; e.text_emb = x->text_emb; e.t_out = x->bb.t_h;
+  mb.v.push_back(e);
+  int src[2] = {0, 0};
+  for (int l = 0; l < c.backbone.layers; ++l) stack_phases(x, x->bb, x->mega_Rbb, l, 1, mega::POS_BACKBONE, 0, false, mb, src);
   // one phase: logits of codebook 0 AND projection(last_h) (depth-decoder row 0), from the stacked matrix;
   // every later decoder input is a row of the projection(embedding) table, so no projection phase remains
-  mega::Phase h0 = gemv_phase_desc(x->head0_proj, x->Vp + Dd, D, x->bb.h, D, 1, EPI_PLAIN, x->bb.norm, eps, x->logits, x->Vp);
-  h0.out2 = x->dec.h; h0.split_row = x->Vp;
-  v.push_back(h0);
-  v.push_back(sample(0, x->dec.h + Dd));
+  mega::Phase h0 = gemv_phase_desc(mb, x->f_head0, x->Vf + Dd, D, x->mega_Rh0, x->bb.t_h, D, 1, EPI_PLAIN, x->bb.norm, eps,
+                                   x->t_logits, x->Vf);
+  h0.x_src[0] = h0.x_src[1] = src[0];
+  h0.t_out2 = x->dec.t_h; h0.split_row = x->Vf;
+  const int ih0 = (int)mb.v.size();
+  mb.v.push_back(h0);
+  const int is0 = (int)mb.v.size();
+  mb.v.push_back(sample(0, ih0, x->dec.t_h + Dd));
+  int dsrc[2] = {ih0, is0};
   for (int i = 1; i < C; ++i) {
     const int nb = (i == 1) ? 2 : 1, pos0 = (i == 1) ? 0 : i;
-    for (int l = 0; l < c.decoder.layers; ++l) stack_phases(x, x->dec, l, nb, mega::POS_FIXED, pos0, true, v);
-    v.push_back(gemv_phase_desc(x->head_t + (size_t)(i - 1) * x->Vp * Dd, V, Dd, x->dec.h + (size_t)(nb - 1) * Dd, Dd, 1,
-                                EPI_PLAIN, x->dec.norm, eps, x->logits, x->Vp));
-    v.push_back(sample(i, (i + 1 < C) ? x->dec.h : nullptr));
+    for (int l = 0; l < c.decoder.layers; ++l) stack_phases(x, x->dec, x->mega_Rdec, l, nb, mega::POS_FIXED, pos0, true, mb, dsrc);
+    mega::Phase h = gemv_phase_desc(mb, x->f_heads + (size_t)(i - 1) * x->Vf * Dd, x->Vf, Dd, x->mega_Rh,
+                                    x->dec.t_h + (size_t)(nb - 1) * Dd, Dd, 1, EPI_PLAIN, x->dec.norm, eps, x->t_logits, x->Vf);
+    h.x_src[0] = h.x_src[1] = dsrc[nb - 1];
+    const int ih = (int)mb.v.size();
+    mb.v.push_back(h);
+    const int is = (int)mb.v.size();
+    mb.v.push_back(sample(i, ih, (i + 1 < C) ? x->dec.t_h : nullptr));
+    dsrc[0] = is;
   }
 }
 
 static int setup_mega(csm_ctx* x, cudaStream_t st) {
   x->mega_ok = false;
   x->trace = nullptr;
-  // fused small attention needs <= 32 cached keys; scores of the backbone attention sit in the 32 KB x buffer
-  if (x->cfg.codebooks > 32 || x->cfg.max_seq_len * 4 + (mega::NCT + 128) * 4 > 32768) return CSM_OK;
-  if (x->dec.hd != 128 || 2 * x->cfg.decoder.dim > 2048 || x->cfg.decoder.kv_heads > 2) return CSM_OK;  // fused attention layout
-  if (x->cfg.backbone.dim > 8 * mega::NCT || x->cfg.decoder.dim > 8 * mega::NCT) return CSM_OK;  // one norm unit per thread
+  const csm_config& c = x->cfg;
+  // fused small attention needs <= 32 cached keys; scores of the backbone attention sit in the x buffer
+  if (c.codebooks > 32 || c.max_seq_len * 4 + (mega::NCT + 3 * 128) * 4 > 32768) return CSM_OK;
+  if (x->dec.hd != 128 || 2 * c.decoder.dim > 2048 || c.decoder.kv_heads > 2) return CSM_OK;  // fused attention layout
+  if (c.backbone.dim > 8 * mega::NCT || c.decoder.dim > 8 * mega::NCT) return CSM_OK;  // one norm unit per thread
+  if (mega_phase_count(c) > 2046) return CSM_OK;  // 11-bit phase tags
   int dev = 0, sms = 0, coop = 0, occ = 0;
   CU_TRY(cudaGetDevice(&dev));
   CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -413,16 +520,51 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
   CU_TRY(cudaFuncSetAttribute(mega::k_frame_mega, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega::SMEM_BYTES));
   CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mega::k_frame_mega, mega::NCT, mega::SMEM_BYTES));
   if (!coop || occ < 1) return CSM_OK;
-  std::vector<mega::Phase> v;
-  build_mega_phases(x, v);
+  // fragment-major copies of every matrix the frame touches
+  const int D = c.backbone.dim, Dd = c.decoder.dim;
+  auto pick_stack = [&](const StackDev& s, int* r4) {
+    r4[0] = mega_pick_R((s.c.heads + 2 * s.c.kv_heads) * s.hd, sms);
+    r4[1] = mega_pick_R(s.c.dim, sms);
+    r4[2] = mega_pick_R(2 * s.c.ff, sms);
+    r4[3] = mega_pick_R(s.c.dim, sms);
+  };
+  pick_stack(x->bb, x->mega_Rbb);
+  pick_stack(x->dec, x->mega_Rdec);
+  x->mega_Rh0 = mega_pick_R(x->Vf + Dd, sms);
+  x->mega_Rh = mega_pick_R(x->Vf, sms);
+  auto pack_stack_frag = [&](StackDev& s, const int* r4) {
+    for (int l = 0; l < s.c.layers; ++l) {
+      pack_frag(s.wqkv[l], (s.c.heads + 2 * s.c.kv_heads) * s.hd, s.c.dim, r4[0], s.fqkv[l], st);
+      pack_frag(s.wo[l], s.c.dim, s.c.dim, r4[1], s.fo[l], st);
+      pack_frag(s.wgu[l], 2 * s.c.ff, s.c.dim, r4[2], s.fgu[l], st);
+      pack_frag(s.wd[l], s.c.dim, s.c.ff, r4[3], s.fd[l], st);
+    }
+  };
+  pack_stack_frag(x->bb, x->mega_Rbb);
+  pack_stack_frag(x->dec, x->mega_Rdec);
+  CU_TRY(cudaMemsetAsync(x->f_head0, 0, (size_t)(x->Vf + Dd) * D * sizeof(bf16), st));
+  pack_frag(x->c0_head, c.audio_vocab, D, x->mega_Rh0, x->f_head0, st);
+  pack_frag(x->proj, Dd, D, x->mega_Rh0, x->f_head0 + (size_t)x->Vf * D, st);
+  CU_TRY(cudaMemsetAsync(x->f_heads, 0, (size_t)(c.codebooks - 1) * x->Vf * Dd * sizeof(bf16), st));
+  for (int i = 0; i + 1 < c.codebooks; ++i)
+    pack_frag(x->head_t + (size_t)i * x->Vp * Dd, c.audio_vocab, Dd, x->mega_Rh, x->f_heads + (size_t)i * x->Vf * Dd, st);
+  CU_TRY(cudaMemsetAsync(x->tagged_base, 0, x->tagged_bytes, st));  // stale tags of an earlier context must never match
+  CU_TRY(cudaGetLastError());
+
+  MegaBuild mb;
+  mb.ncta = sms;
+  mb.rot = 0;
+  build_mega_phases(x, mb);
+  std::vector<mega::Phase>& v = mb.v;
   if ((int)v.size() != mega_phase_count(x->cfg)) return set_err(CSM_ERR_ARG, "internal: phase count mismatch");
   memset(&x->pf_table, 0, sizeof(x->pf_table));
   for (const mega::Phase& ph : v) {
     if (ph.type != mega::PH_GEMV) continue;
     if (x->pf_table.n >= mega::MAX_GEMV) return CSM_OK;  // too deep for the parameter-space table: per-op path only
-    if (ph.K > mega::KC_MAX && ((ph.G + sms - 1) / sms) * (ph.K / mega::KC_MAX) > mega::MAX_SPLIT_TASKS) return CSM_OK;
+    if ((ph.G + sms - 1) / sms > mega::MAX_LOCAL_GROUPS) return CSM_OK;
+    if (ph.K % (32 * mega::NW) != 0) return CSM_OK;
     mega::PfDesc& d = x->pf_table.d[x->pf_table.n++];
-    d.W = ph.W; d.rows = ph.rows; d.K = ph.K; d.G = ph.G; d.R = ph.R;
+    d.W = ph.W; d.G = ph.G; d.rot = ph.rot; d.group_bytes = ph.R * ph.K * 2;
   }
   CU_TRY(cudaMemcpyAsync(x->d_phases, v.data(), v.size() * sizeof(mega::Phase), cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemsetAsync(x->d_sync, 0, sizeof(mega::Sync), st));
@@ -511,12 +653,6 @@ extern "C" int32_t csm_create(const csm_config* cfg, const csm_weights* w, int32
     k_transpose_heads<<<grid, block, 0, st>>>((const bf16*)w->audio_head, x->head_t, K, V, x->Vp); COUNT_LAUNCH();
   }
   {
-    // stacked [codebook0_head ; projection] (the workspace is not zeroed: clear the pad rows)
-    const size_t D8 = cfg->backbone.dim / 8;
-    cudaMemsetAsync(x->head0_proj, 0, (size_t)(x->Vp + cfg->decoder.dim) * cfg->backbone.dim * sizeof(bf16), st);
-    k_copy_rows<<<256, 256, 0, st>>>(x->c0_head, x->head0_proj, (size_t)cfg->audio_vocab * D8); COUNT_LAUNCH();
-    k_copy_rows<<<256, 256, 0, st>>>(x->proj, x->head0_proj + (size_t)x->Vp * cfg->backbone.dim, (size_t)cfg->decoder.dim * D8);
-    COUNT_LAUNCH();
     // projection(embedding) table on the tensor cores: [(C-1)*V, D] x [Dd, D]^T
     if (cfg->backbone.dim % 64 == 0) {
       rc = launch_gemm_tc(x->audio_emb, cfg->backbone.dim, (cfg->codebooks - 1) * cfg->audio_vocab, cfg->backbone.dim, x->proj,

@@ -1,95 +1,97 @@
 // Persistent decode megakernel: one audio frame (backbone step + codebook-0 sample + 31 depth-
 // decoder steps, ~640 dependent phases) in ONE launch, for one stream.
 //
-// Why: at batch 1 a frame is ~800 tiny dependent GEMVs (0.3-10 us of HBM time each); launched one
-// by one they are latency bound (v1: 17 % of the HBM roofline).  Here one CTA per SM stays
-// resident for the whole frame:
-//   * every warp streams ITS share of every weight matrix, in consumption order, through a
-//     private shared-memory ring with bulk async copies (cp.async.bulk + mbarrier complete_tx).
-//     Weight addresses are data independent, so the stream runs AHEAD of the dependency chain:
-//     148 SMs x 192 KB = 28 MB of weights (~4 us of HBM time) stay in flight while grid barriers,
-//     norms, attention and sampling resolve.  The schedule of what to fetch next comes from a
-//     compact table passed in kernel-parameter (constant) space;
-//   * the same warp computes its output-row groups out of shared memory (fp32 accumulate, warp
-//     shuffle reduction) and runs the fused epilogue (RoPE + KV append / residual / SwiGLU /
-//     logits) at the reference's bf16 rounding points, then refills the slot it just drained;
-//   * phases are separated by a monotonic grid barrier (release/acquire counter in L2); the next
-//     phase's descriptor is prefetched into shared memory while the current one computes.
+// Why: at batch 1 a frame is ~640 tiny dependent GEMVs (0.3-10 us of HBM time each); launched one by
+// one, or separated by grid barriers, they are latency bound.  Here one CTA per SM stays resident for
+// the whole frame and three things keep the dependency chain short:
+//   * WEIGHT STREAM.  Every warp streams ITS share of every weight matrix, in consumption order,
+//     through a private shared-memory ring with bulk async copies (cp.async.bulk + mbarrier
+//     complete_tx).  Weight addresses are data independent, so the stream runs AHEAD of the
+//     dependency chain: 148 SMs x 128 KB of weights stay in flight while activations resolve.  The
+//     fetch schedule is a compact table in kernel-parameter (constant) space.
+//   * FRAGMENT-MAJOR WEIGHTS + TENSOR-CORE DOT.  The matrices are re-packed once at setup into
+//     [row group of R=8/16][32-wide k block][lane][16 B] order: a chunk is one contiguous bulk copy,
+//     each lane reads its mma.m16n8k16 A fragment with one conflict-free LDS.128, and the dot products
+//     of a 16-row group with the (<= 2) activation rows are HMMA instructions whose accumulator
+//     already holds finished sums -- no unpack/FMA chains and no shuffle reductions.  All 8 warps of a
+//     CTA split the K extent of a row group, partial sums meet in shared memory in a fixed order.
+//   * TAGGED ACTIVATIONS INSTEAD OF GRID BARRIERS.  Every vector one phase hands to the next travels
+//     as 32-bit words {tag16 | bf16}; the tag names the producing phase and frame.  A consumer
+//     re-loads a word until its tag is the expected one: the data is its own ready flag, a phase
+//     boundary costs one L2 round trip, and CTAs without work in a phase run ahead.
 // Every spin has a trip-count cap and traps instead of hanging the GPU.
 #pragma once
 #include "lm_kernels.cuh"
 
 namespace mega {
 
-#ifndef MEGA_NW
-#define MEGA_NW 8
-#endif
-#ifndef MEGA_SLOTS
-#define MEGA_SLOTS 2
-#endif
-#ifndef MEGA_CHUNK
-#define MEGA_CHUNK 4096
-#endif
-#ifndef MEGA_L2_AHEAD
-#define MEGA_L2_AHEAD 0  /* measured: an extra L2 prefetch stage slows the stream (5.15 vs 4.3 ms/frame) */
-#endif
-constexpr int NW = MEGA_NW;           // warps per CTA
+constexpr int NW = 8;                 // warps per CTA
 constexpr int NCT = NW * 32;          // threads per CTA
-constexpr int SLOTS = MEGA_SLOTS;     // ring slots per warp
-constexpr int CHUNK_ELEMS = MEGA_CHUNK;  // bf16 per slot
-constexpr int KC_MAX = CHUNK_ELEMS / 2;  // k-extent of a chunk (a chunk holds >= 2 rows)
-constexpr int L2_AHEAD = MEGA_L2_AHEAD;  // chunks per warp that are pulled into L2 ahead of the smem ring
+#ifndef MEGA_SLOTS
+#define MEGA_SLOTS 4
+#endif
+#ifndef MEGA_SLOT_BYTES
+#define MEGA_SLOT_BYTES 4096
+#endif
+constexpr int SLOTS = MEGA_SLOTS;            // ring slots per warp
+constexpr int SLOT_BYTES = MEGA_SLOT_BYTES;  // bytes per slot (a chunk never exceeds it)
 constexpr int MAXNB = 2;              // activation rows per phase (depth step 1 carries 2)
 constexpr int XBUF_ELEMS = 2 * MAXNB * 8192;  // 64 KB: activation rows, or the fused attention's q / K / V staging
-constexpr int CBAR = 0;               // all threads are consumers: plain CTA barrier
+constexpr int CBAR = 0;               // all threads take part in CTA barriers
 constexpr int MAX_GEMV = 640;         // rows of the prefetch table (kernel parameter space)
-constexpr size_t SMEM_RING = (size_t)NW * SLOTS * CHUNK_ELEMS * 2;
+constexpr int MAX_LOCAL_GROUPS = 8;   // row groups one CTA owns in one phase
+constexpr size_t SMEM_RING = (size_t)NW * SLOTS * SLOT_BYTES;
 constexpr size_t SMEM_X = (size_t)XBUF_ELEMS * 2;
-constexpr size_t SMEM_MISC = 4096;
-constexpr int MAX_SPLIT_TASKS = 128;  // (row group, k-chunk) tasks per CTA in a split-K phase
-constexpr size_t SMEM_BYTES = SMEM_RING + SMEM_X + SMEM_MISC;
+constexpr size_t SMEM_PSUM = (size_t)MAX_LOCAL_GROUPS * NW * 16 * MAXNB * 4;
+constexpr size_t SMEM_MISC = 2048;
+constexpr size_t SMEM_BYTES = SMEM_RING + SMEM_X + SMEM_PSUM + SMEM_MISC;
 
 enum { PH_GEMV = 0, PH_EMBED = 1, PH_ATTN = 2, PH_SAMPLE = 3 };
 enum { POS_FIXED = 0, POS_BACKBONE = 1 };
 
 // Full description of a phase (global memory; staged into shared memory one phase ahead).
+// t_* pointers address TAGGED words; *_src = index of the phase that produced the words consumed.
 struct __align__(16) Phase {
   int type, epi, norm, nb;
+  // GEMV: W is fragment-major packed, G groups of R rows, group g belongs to CTA (g + rot) % ncta
   const bf16* W;
-  int rows, K, R, KC, G, ldx;
-  const bf16* x;  // [nb, ldx] activations in global memory
+  int rows, K, R, G;
+  int rot, gq, gr;  // gq = G / ncta, gr = G % ncta
+  int ldx;
+  const uint32_t* t_x;  // input rows [nb][ldx]
+  int x_src[2];
   const bf16* norm_scale;
-  bf16* out;
-  const bf16* resid;
-  bf16* x_copy_out;  // CTA 0 publishes the staged (normalised) rows here
   float eps;
   int ldo;
-  // RoPE / KV append / attention
-  bf16 *q, *kc, *vc;
-  const bf16* rope;
-  int heads, kv_heads, hd, slots, pos_mode, pos0;
-  int attn_prologue;  // GEMV: x = attention(q, cache) computed redundantly by every CTA (<= 32 keys)
-  int cb;
-  bf16* att_out;  // PH_ATTN: [heads*hd]
-  // sample / embed
-  int V, C, D, ldl;
-  const bf16* logits;
-  bf16* next_in;
-  const bf16 *audio_emb, *text_emb;
-  bf16* h_out;
-  // PLAIN epilogue with two destinations: rows >= split_row go to out2[row - split_row] (stacked
-  // [codebook0_head; projection] matrix: logits and the depth decoder's position-0 input in one phase)
-  bf16* out2;
+  uint32_t* t_out;   // output rows [nb][ldo]; EPI_RESID: the residual stream, updated in place
+  uint32_t* t_out2;  // EPI_PLAIN with two destinations: rows >= split_row go to t_out2[row - split_row]
   int split_row;
-  int next_ld;  // SAMPLE: row length of the gather table feeding next_in
-  const bf16* next_table;  // SAMPLE: projection(embedding) table [(codebooks-1)*V][Dd], or null -> audio_emb rows
+  int resid_src[2];
+  int attn_prologue;  // GEMV: x = attention(q, cache) computed redundantly by every CTA (<= 32 keys)
+  // RoPE / KV append / attention
+  uint32_t* t_q;   // [nb][heads*hd]
+  uint32_t* t_kv;  // K and V rows of the positions written by the QKV phase: [nb][2][kv_heads*hd]
+  int q_src;
+  int heads, kv_heads, hd, slots, pos_mode, pos0;
+  bf16 *kc, *vc;  // plain bf16 cache (later steps / frames)
+  const bf16* rope;
+  // sample / embed
+  int V, C, D, cb;
+  const uint32_t* t_logits;
+  int logits_src;
+  int next_ld;             // SAMPLE: row length of the gather table feeding t_next
+  uint32_t* t_next;        // SAMPLE: next depth-decoder input row
+  const bf16* next_table;  // SAMPLE: projection(embedding) table [(codebooks-1)*V][next_ld]
+  const bf16 *audio_emb, *text_emb;
 };
 static_assert(sizeof(Phase) % 16 == 0, "Phase must be copyable in 16-byte units");
 
 // What the weight prefetcher needs to know about a GEMV phase.
 struct PfDesc {
   const bf16* W;
-  int rows, K, G, R;  // R rows per chunk (small phases use half-size chunks so more warps share them)
+  int G, rot;
+  int group_bytes;  // R * K * 2
+  int pad_;
 };
 struct PfTable {
   int n;
@@ -98,13 +100,13 @@ struct PfTable {
 };
 
 struct Sync {
-  unsigned int counter;  // grid barrier arrivals, zeroed by k_mega_prepare before every frame
+  unsigned int seq;  // frame counter (tag salt), bumped by k_mega_prepare
   unsigned int error;
 };
 
 __global__ void k_mega_prepare(FrameParams* dst, FrameParams v, Sync* sync) {
   *dst = v;
-  sync->counter = 0;
+  sync->seq += 1;
 }
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -127,8 +129,7 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Weights are streamed with an L2 evict-first policy: they are read once per use and must not push
-// the small hot data (activations, KV cache, norm scales, RoPE tables) out of the 126 MB L2 --
-// otherwise every dependent load of a phase queues behind ~28 MB of in-flight weight traffic.
+// the small hot data (tagged activations, KV cache, norm scales, RoPE tables) out of the 126 MB L2.
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
@@ -140,21 +141,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
           smem_u32(dst)),
       "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
       : "memory");
-}
-// Second, deeper stage of the weight stream: pull a chunk into the 126 MB L2 well before its turn
-// in the shared-memory ring.  HBM then keeps streaming while every CTA sits in a latency chain
-// (barrier, activation load, epilogue), and the ring refills at L2 speed.
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void arrive_release(unsigned* p) {
-  // the fence also releases what the other threads of the CTA wrote before the CTA barrier
-  asm volatile("fence.acq_rel.gpu;\n\tred.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
 __device__ __forceinline__ uint4 ldcg16(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ float ldcg_bf(const bf16* p) {
@@ -174,98 +160,146 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, Sync* 
   for (unsigned spin = 0; !mbar_try(bar, parity); ++spin)
     if (spin > (1u << 22)) die(sync, code);
 }
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// D += A(16x16, row) * B(16x8, col), bf16 operands, fp32 accumulate (HMMA.16816.F32.BF16)
+__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 
-// work distribution: the i-th row group owned by (cta, warp)
-__device__ __forceinline__ int group_of(int cta, int ncta, int warp, int i) { return cta + ncta * (warp + NW * i); }
+// ---- tagged activations ------------------------------------------------------------------------------
+// Buffer reuse is safe without further synchronisation: seeing ANY word of phase p implies that its
+// producer had staged the complete output of phase p-1, hence that every phase <= p-1 is complete;
+// a buffer written in phase p is never rewritten before phase p+2.
+__device__ __forceinline__ uint32_t tag_of(unsigned seq, int phase) {
+  return ((uint32_t)(((seq & 31u) << 11) | (unsigned)(phase + 1))) << 16;
+}
+__device__ __forceinline__ uint32_t tword(uint32_t tag, float v) { return tag | (uint32_t)__bfloat16_as_ushort(f2bf(v)); }
+__device__ __forceinline__ uint32_t tword_raw(uint32_t tag, uint32_t bf) { return tag | (bf & 0xffffu); }
+__device__ __forceinline__ uint4 ldv4(const uint32_t* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 ldv2(const uint32_t* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ldv1(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stv4(uint32_t* p, const uint4& v) { __stcg(reinterpret_cast<uint4*>(p), v); }
+__device__ __forceinline__ void stv2(uint32_t* p, const uint2& v) { __stcg(reinterpret_cast<uint2*>(p), v); }
+__device__ __forceinline__ bool fresh4(const uint4& v, uint32_t tag) {
+  return ((((v.x ^ tag) | (v.y ^ tag)) | ((v.z ^ tag) | (v.w ^ tag))) & 0xffff0000u) == 0;
+}
+__device__ __forceinline__ uint4 poll4(const uint32_t* p, uint32_t tag, uint4 v, Sync* sync) {
+  for (unsigned spin = 0; !fresh4(v, tag); ++spin) {
+    if (spin > (1u << 22)) die(sync, 0x400);
+    v = ldv4(p);
+  }
+  return v;
+}
+__device__ __forceinline__ uint2 poll2(const uint32_t* p, uint32_t tag, Sync* sync) {
+  uint2 v = ldv2(p);
+  for (unsigned spin = 0; (((v.x ^ tag) | (v.y ^ tag)) & 0xffff0000u) != 0; ++spin) {
+    if (spin > (1u << 22)) die(sync, 0x401);
+    v = ldv2(p);
+  }
+  return v;
+}
+__device__ __forceinline__ uint32_t poll1(const uint32_t* p, uint32_t tag, Sync* sync) {
+  uint32_t v = ldv1(p);
+  for (unsigned spin = 0; ((v ^ tag) & 0xffff0000u) != 0; ++spin) {
+    if (spin > (1u << 22)) die(sync, 0x402);
+    v = ldv1(p);
+  }
+  return v;
+}
+// four tagged words -> four packed bf16 (the low halves)
+__device__ __forceinline__ uint2 strip4(const uint4& v) {
+  return make_uint2((v.x & 0xffffu) | (v.y << 16), (v.z & 0xffffu) | (v.w << 16));
+}
+__device__ __forceinline__ float tval(uint32_t w) { return __uint_as_float(w << 16); }
 
 // ---- per-warp weight prefetcher -----------------------------------------------------------------------
-// A phase's work is cut into tasks (row group j of this CTA, k-chunk kc), numbered u = j*nkc + kc and
-// dealt round-robin to the warps (u = warp, warp + NW, ...).  For K <= KC_MAX a task is a whole row
-// group; for the down projections (K = 8192) the k-chunks of one row pair go to different warps, so
-// all warps stream in parallel and the partial sums meet in shared memory.
+// A phase's row group g belongs to CTA (g + rot) % ncta; all NW warps of that CTA split its K extent:
+// warp w owns the contiguous slice [w/NW, (w+1)/NW) of the group's fragment-major bytes, cut into
+// chunks of <= SLOT_BYTES.  The warp's stream is: phases in order, its CTA's groups in order, chunks
+// in order -- exactly the order in which gemv_phase consumes them.
 struct Prefetch {
   int gi;  // index into the GEMV table
-  int u;   // task index inside the phase
+  int j;   // local group index inside the phase
+  int c;   // chunk index inside the task
   unsigned issued;
   bool done;
-  uint64_t policy;  // L2 cache policy of the weight stream
+  uint64_t policy;
 };
 
-__device__ __forceinline__ int nkc_of(int K) { return K <= KC_MAX ? 1 : K / KC_MAX; }
+__device__ __forceinline__ int local_cta(int cta, int ncta, int rot) {
+  const int cl = cta - rot;
+  return cl < 0 ? cl + ncta : cl;
+}
 
-__device__ __forceinline__ void pf_seek(Prefetch& pf, const PfTable& tab, int cta, int ncta, int warp) {
-  // position on the first (phase, task) at or after (gi, u) that this warp owns
-  while (pf.gi < tab.n && cta + ncta * (pf.u / nkc_of(tab.d[pf.gi].K)) >= tab.d[pf.gi].G) {
+__device__ __forceinline__ void pf_seek(Prefetch& pf, const PfTable& tab, int cta, int ncta) {
+  while (pf.gi < tab.n && local_cta(cta, ncta, tab.d[pf.gi].rot) + ncta * pf.j >= tab.d[pf.gi].G) {
     ++pf.gi;
-    pf.u = warp;
+    pf.j = 0;
+    pf.c = 0;
   }
   pf.done = pf.gi >= tab.n;
 }
 
-// L2 prefetch of the chunk the cursor points at, then advance (no shared-memory slot involved)
-__device__ __forceinline__ void pf_issue_l2(Prefetch& pf, const PfTable& tab, int cta, int ncta, int warp, int lane) {
-  if (pf.done) return;
-  const PfDesc& d = tab.d[pf.gi];
-  const int K = d.K, KC = K < KC_MAX ? K : KC_MAX, R = d.R, nkc = K / KC;
-  const int j = pf.u / nkc, kc = pf.u - j * nkc;
-  const int r0 = (cta + ncta * j) * R;
-  const int nr = min(R, d.rows - r0);
-  if (nkc == 1) {
-    if (lane == 0) bulk_prefetch_l2(d.W + (size_t)r0 * K, (uint32_t)nr * K * 2);
-  } else if (lane < nr) {
-    bulk_prefetch_l2(d.W + (size_t)(r0 + lane) * K + (size_t)kc * KC, (uint32_t)KC * 2);
-  }
-  pf.u += NW;
-  pf_seek(pf, tab, cta, ncta, warp);
-}
-
 // issue the next chunk of this warp's stream into ring slot (issued % SLOTS); whole warp calls it
-__device__ __forceinline__ void pf_issue(Prefetch& pf, const PfTable& tab, bf16* ring, uint64_t* full, int cta, int ncta,
-                                         int warp, int lane) {
+__device__ __forceinline__ void pf_issue(Prefetch& pf, const PfTable& tab, unsigned char* ring, uint64_t* full, int cta,
+                                         int ncta, int warp, int lane) {
   if (pf.done) return;
   const PfDesc& d = tab.d[pf.gi];
-  const int K = d.K, KC = K < KC_MAX ? K : KC_MAX, R = d.R, nkc = K / KC;
-  const int j = pf.u / nkc, kc = pf.u - j * nkc;
-  const int r0 = (cta + ncta * j) * R;
-  const int nr = min(R, d.rows - r0);
+  const int tb = d.group_bytes / NW;
+  const int chunk = tb < SLOT_BYTES ? tb : SLOT_BYTES;
+  const int g = local_cta(cta, ncta, d.rot) + ncta * pf.j;
   const int slot = pf.issued % SLOTS;
   if (lane == 0) {
     uint64_t* fb = &full[warp * SLOTS + slot];
-    bf16* dst = ring + (size_t)(warp * SLOTS + slot) * CHUNK_ELEMS;
-    if (nkc == 1) {  // whole rows are contiguous: one copy
-      mbar_expect_tx(fb, (uint32_t)nr * K * 2);
-      bulk_g2s(dst, d.W + (size_t)r0 * K, (uint32_t)nr * K * 2, fb, pf.policy);
-    } else {
-      mbar_expect_tx(fb, (uint32_t)nr * KC * 2);
-      for (int r = 0; r < nr; ++r)
-        bulk_g2s(dst + r * KC, d.W + (size_t)(r0 + r) * K + (size_t)kc * KC, (uint32_t)KC * 2, fb, pf.policy);
-    }
+    const unsigned char* src =
+        reinterpret_cast<const unsigned char*>(d.W) + (size_t)g * d.group_bytes + (size_t)warp * tb + (size_t)pf.c * chunk;
+    mbar_expect_tx(fb, (uint32_t)chunk);
+    bulk_g2s(ring + (size_t)(warp * SLOTS + slot) * SLOT_BYTES, src, (uint32_t)chunk, fb, pf.policy);
   }
   ++pf.issued;
-  pf.u += NW;
-  pf_seek(pf, tab, cta, ncta, warp);
+  ++pf.c;
+  if (pf.c * chunk >= tb) {
+    pf.c = 0;
+    ++pf.j;
+    pf_seek(pf, tab, cta, ncta);
+  }
 }
 
 // ---- consumer pieces ---------------------------------------------------------------------------------
 struct Ctx {
   const FrameParams* P;
-  bf16* ring;
+  unsigned char* ring;
   bf16* xs;
   uint64_t* full;
-  float* scratch;  // 33 floats
-  float* psum;     // [MAX_SPLIT_TASKS][4] split-K partial sums
+  float* scratch;  // 34 floats
+  float* psum;     // [MAX_LOCAL_GROUPS][NW][16][MAXNB] split-K partial sums
   int* iscratch;   // 40 ints
   Sync* sync;
-  Prefetch pf;   // shared-memory ring cursor
-  Prefetch pf2;  // L2 prefetch cursor, L2_AHEAD chunks further down the same stream
+  Prefetch pf;
   unsigned cnt;  // chunks consumed by this warp so far
-  unsigned long long* trp;  // fine-grained trace slots of the current phase (CTA 0, thread 0) or null
+  unsigned long long* trp;  // trace slots of the current phase (CTA 0, thread 0) or null
   int tid, warp, lane;
   int bb_pos, bb_slot;  // RoPE position / cache slot of the backbone row of this frame
-  // operands of the CURRENT phase that were fetched while the previous grid barrier was spinning
-  uint4 pre_scale;   // this thread's 16-byte unit of the RMSNorm scale
-  float pre_a, pre_b;  // epilogue operands of this lane's pair in the warp's first row group
-  bool pre_valid;
+  unsigned seq;         // frame counter (tag salt)
+  uint32_t tag;         // tag of the words the current phase produces
 };
 
 __device__ __forceinline__ void phase_pos(const Phase& ph, const Ctx& c, int n, int& pos, int& slot) {
@@ -278,18 +312,17 @@ __device__ __forceinline__ void phase_pos(const Phase& ph, const Ctx& c, int n, 
 }
 
 // Operands the epilogue of a row pair needs from global memory (residual values / RoPE cos,sin).
-// They are fetched when the warp STARTS a row group, so their L2 round trip -- ~1.5 us while the
-// weight stream saturates the memory system -- overlaps the dot products instead of following them.
+// They are requested at the START of the phase, so their L2 round trip overlaps the hand-off.
 struct EpiPre {
   float a, b;
 };
 __device__ __forceinline__ EpiPre epilogue_prefetch(const Phase& ph, const Ctx& c, int r0, int n) {
   EpiPre e;
   e.a = e.b = 0.f;
-  if (r0 >= ph.rows || n >= ph.nb) return e;
   if (ph.epi == EPI_RESID) {
-    e.a = ldcg_bf(ph.resid + (size_t)n * ph.ldo + r0);
-    if (r0 + 1 < ph.rows) e.b = ldcg_bf(ph.resid + (size_t)n * ph.ldo + r0 + 1);
+    const uint2 w = poll2(ph.t_out + (size_t)n * ph.ldo + r0, tag_of(c.seq, ph.resid_src[n]), c.sync);
+    e.a = tval(w.x);
+    e.b = tval(w.y);
   } else if (ph.epi == EPI_ROPE_KV) {
     const int hd = ph.hd;
     if (r0 < (ph.heads + ph.kv_heads) * hd) {
@@ -304,23 +337,16 @@ __device__ __forceinline__ EpiPre epilogue_prefetch(const Phase& ph, const Ctx& 
 }
 
 // fused epilogue of one output-row pair (row r0, r0+1) for activation row n
-__device__ __forceinline__ void epilogue(const Phase& ph, const Ctx& c, int r0, int n, float a0, float a1,
-                                         const EpiPre& pre) {
-  const bool has1 = r0 + 1 < ph.rows;
+__device__ __forceinline__ void epilogue(const Phase& ph, const Ctx& c, int r0, int n, float a0, float a1, const EpiPre& pre) {
   const float y0 = rbf(a0), y1 = rbf(a1);
+  const uint32_t tag = c.tag;
   if (ph.epi == EPI_PLAIN) {
-    if (ph.out2 && r0 >= ph.split_row) {
-      ph.out2[r0 - ph.split_row] = f2bf(y0);
-      if (has1) ph.out2[r0 + 1 - ph.split_row] = f2bf(y1);
-    } else {
-      ph.out[(size_t)n * ph.ldo + r0] = f2bf(y0);
-      if (has1) ph.out[(size_t)n * ph.ldo + r0 + 1] = f2bf(y1);
-    }
+    uint32_t* dst = (ph.t_out2 && r0 >= ph.split_row) ? ph.t_out2 + (r0 - ph.split_row) : ph.t_out + (size_t)n * ph.ldo + r0;
+    stv2(dst, make_uint2(tword(tag, y0), tword(tag, y1)));
   } else if (ph.epi == EPI_RESID) {
-    ph.out[(size_t)n * ph.ldo + r0] = f2bf(y0 + pre.a);
-    if (has1) ph.out[(size_t)n * ph.ldo + r0 + 1] = f2bf(y1 + pre.b);
+    stv2(ph.t_out + (size_t)n * ph.ldo + r0, make_uint2(tword(tag, y0 + pre.a), tword(tag, y1 + pre.b)));
   } else if (ph.epi == EPI_SWIGLU) {
-    ph.out[(size_t)n * ph.ldo + (r0 >> 1)] = f2bf(silu_bf(y0) * y1);
+    __stcg(ph.t_out + (size_t)n * ph.ldo + (r0 >> 1), tword(tag, silu_bf(y0) * y1));
   } else {  // EPI_ROPE_KV
     const int hd = ph.hd, qrows = ph.heads * hd, krows = ph.kv_heads * hd;
     int pos, slot;
@@ -331,158 +357,116 @@ __device__ __forceinline__ void epilogue(const Phase& ph, const Ctx& c, int r0, 
       o1 = rbf(__fadd_rn(__fmul_rn(y1, pre.a), __fmul_rn(y0, pre.b)));
     }
     if (r0 < qrows) {
-      *reinterpret_cast<__nv_bfloat162*>(ph.q + (size_t)n * qrows + r0) = __floats2bfloat162_rn(o0, o1);
+      stv2(ph.t_q + (size_t)n * qrows + r0, make_uint2(tword(tag, o0), tword(tag, o1)));
     } else {
       const bool isk = r0 < qrows + krows;
       const int rr = r0 - (isk ? qrows : qrows + krows);
       const int kvh = rr / hd, d = rr % hd;
+      // this step's consumers read the tagged copy; the cache keeps plain bf16 for later steps / frames
+      stv2(ph.t_kv + ((size_t)n * 2 + (isk ? 0 : 1)) * krows + rr, make_uint2(tword(tag, o0), tword(tag, o1)));
       bf16* dst = (isk ? ph.kc : ph.vc) + ((size_t)kvh * ph.slots + slot) * hd + d;  // stream 0
       *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(o0, o1);
     }
   }
 }
 
-// dot products of one ring chunk ([R][KC] weights) with the staged activations
-template <int R, int NB>
-__device__ __forceinline__ void chunk_dot(const bf16* chunk, const bf16* xk, int K, int KC, int lane, float (&acc)[R][NB]) {
-  // two independent accumulator sets (even / odd 256-element blocks): the FMA chains, not the
-  // shared-memory bandwidth, bound this loop with only two warps per scheduler
-  float acc2[R][NB];
-#pragma unroll
-  for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int n = 0; n < NB; ++n) acc2[r][n] = 0.f;
-  for (int k = lane * 8; k < KC; k += 512) {
-    const bool two = k + 256 < KC;  // KC is a multiple of 256, not necessarily of 512
-    const int k2 = two ? k + 256 : k;
-    uint4 xa[NB], xb[NB];
-#pragma unroll
-    for (int n = 0; n < NB; ++n) {
-      xa[n] = *reinterpret_cast<const uint4*>(xk + (size_t)n * K + k);
-      xb[n] = two ? *reinterpret_cast<const uint4*>(xk + (size_t)n * K + k2) : make_uint4(0, 0, 0, 0);
+// One ring chunk ([nblk] fragment-major blocks of R rows x 32 k) times the staged activation rows.
+// A = weights (16 rows; R == 8 leaves the upper 8 rows zero), B = activations (column n = row n of x).
+// k is permuted consistently in both operands so that every lane fetches 8 consecutive k with one
+// 16-byte load: logical k {2q,2q+1 | 2q+8,2q+9} of the first / second mma <-> physical q*8 + {0,1 | 2,3} / {4,5 | 6,7}.
+template <int R>
+__device__ __forceinline__ void chunk_mma(const unsigned char* chunk, int nblk, const bf16* xk, int K, int nb, int lane,
+                                          float (&acc)[4][4]) {
+  const int g = lane >> 2, q = lane & 3;
+  const bool xl = g < nb;
+  const bf16* xp = xk + (size_t)g * K + q * 8;
+  const unsigned char* wp = chunk + lane * 16;
+  constexpr int BLK = R * 64;
+  int b = 0;
+  for (; b + 1 < nblk; b += 2) {
+    const uint4 w0 = *reinterpret_cast<const uint4*>(wp + (size_t)b * BLK);
+    const uint4 w2 = *reinterpret_cast<const uint4*>(wp + (size_t)(b + 1) * BLK);
+    uint4 w1 = make_uint4(0, 0, 0, 0), w3 = w1;
+    if (R == 16) {
+      w1 = *reinterpret_cast<const uint4*>(wp + (size_t)b * BLK + 512);
+      w3 = *reinterpret_cast<const uint4*>(wp + (size_t)(b + 1) * BLK + 512);
     }
+    uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0;
+    if (xl) {
+      x0 = *reinterpret_cast<const uint4*>(xp + b * 32);
+      x1 = *reinterpret_cast<const uint4*>(xp + (b + 1) * 32);
+    }
+    mma16816(acc[0], w0.x, w1.x, w0.y, w1.y, x0.x, x0.y);
+    mma16816(acc[1], w0.z, w1.z, w0.w, w1.w, x0.z, x0.w);
+    mma16816(acc[2], w2.x, w3.x, w2.y, w3.y, x1.x, x1.y);
+    mma16816(acc[3], w2.z, w3.z, w2.w, w3.w, x1.z, x1.w);
+  }
+  if (b < nblk) {
+    const uint4 w0 = *reinterpret_cast<const uint4*>(wp + (size_t)b * BLK);
+    uint4 w1 = make_uint4(0, 0, 0, 0);
+    if (R == 16) w1 = *reinterpret_cast<const uint4*>(wp + (size_t)b * BLK + 512);
+    uint4 x0 = make_uint4(0, 0, 0, 0);
+    if (xl) x0 = *reinterpret_cast<const uint4*>(xp + b * 32);
+    mma16816(acc[0], w0.x, w1.x, w0.y, w1.y, x0.x, x0.y);
+    mma16816(acc[1], w0.z, w1.z, w0.w, w1.w, x0.z, x0.w);
+  }
+}
+
+// The CTA's row groups of this phase.  Warp w streams slice w of every group through its ring, the
+// partial sums meet in shared memory, and one thread per (group, row pair, activation row) adds them
+// in a fixed order and runs the fused epilogue.
+template <int R>
+__device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c, const PfTable& tab, int cl, int ngl, int j_item,
+                                            int pair, int n_item, bool item_on, const EpiPre& pre) {
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  const int K = ph.K;
+  const int tb = R * K * 2 / NW;  // bytes of a warp's slice
+  const int chunk = tb < SLOT_BYTES ? tb : SLOT_BYTES;
+  const int nch = tb / chunk;
+  const int kchunk = chunk / (R * 2);  // k extent of a chunk
+  const int nblk = chunk / (R * 64);
+  const int g = c.lane >> 2, q = c.lane & 3;
+  for (int j = 0; j < ngl; ++j) {
+    float acc[4][4];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const uint4 wa = *reinterpret_cast<const uint4*>(chunk + r * KC + k);
-      const uint4 wb = *reinterpret_cast<const uint4*>(chunk + r * KC + k2);
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int n = 0; n < NB; ++n) {
-        acc[r][n] = dot8(wa, xa[n], acc[r][n]);
-        acc2[r][n] = dot8(wb, xb[n], acc2[r][n]);
+      for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+    for (int ch = 0; ch < nch; ++ch) {
+      const int slot = c.cnt % SLOTS;
+      mbar_wait(&c.full[c.warp * SLOTS + slot], (c.cnt / SLOTS) & 1, c.sync, 0x200 + c.warp);
+      chunk_mma<R>(c.ring + (size_t)(c.warp * SLOTS + slot) * SLOT_BYTES, nblk, c.xs + c.warp * (K / NW) + ch * kchunk, K,
+                   ph.nb, c.lane, acc);
+      __syncwarp();
+      ++c.cnt;
+      // the slot is drained: refill it with the chunk SLOTS ahead in this warp's stream
+      pf_issue(c.pf, tab, c.ring, c.full, cta, ncta, c.warp, c.lane);
+    }
+    if (q == 0) {
+      // accumulator rows: lane group g holds A rows g and g+8 <-> group rows 2g, 2g+1 (R == 16) or g (R == 8)
+      float* ps = c.psum + ((size_t)(j * NW + c.warp) * 16) * MAXNB;
+      const float s0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+      const float s1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+      if (R == 16) {
+        const float s2 = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]);
+        const float s3 = (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]);
+        *reinterpret_cast<float4*>(ps + (2 * g) * MAXNB) = make_float4(s0, s1, s2, s3);
+      } else {
+        *reinterpret_cast<float2*>(ps + g * MAXNB) = make_float2(s0, s1);
       }
     }
   }
+  csync<NCT, CBAR>();
+  if (c.trp) c.trp[2] = gtimer();
+  if (item_on) {
+    const float* ps = c.psum + ((size_t)(j_item * NW) * 16 + 2 * pair) * MAXNB + n_item;
+    float y0 = 0.f, y1 = 0.f;
 #pragma unroll
-  for (int r = 0; r < R; ++r)
-#pragma unroll
-    for (int n = 0; n < NB; ++n) acc[r][n] += acc2[r][n];
-}
-
-// The warp's tasks of this phase: chunks come from its ring; after the shuffle reduction lane
-// (pair, n) runs that pair's epilogue (K <= KC_MAX), or the partial sums go to shared memory and a
-// post pass adds the k-chunks in a fixed order and runs the epilogue (split-K phases).
-template <int R, int NB>
-__device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c, const PfTable& tab) {
-  const int cta = blockIdx.x, ncta = gridDim.x;
-  const int K = ph.K, KC = ph.KC, nkc = K / KC;
-  const int my_pr = c.lane % (R / 2), my_n = c.lane / (R / 2);
-  const bool epi_lane = c.lane < (R / 2) * NB;
-  if (nkc == 1) {
-    for (int i = 0;; ++i) {
-      const int g = cta + ncta * (c.warp + NW * i);
-      if (g >= ph.G) break;
-      EpiPre pre;
-      pre.a = pre.b = 0.f;
-      if (i == 0 && c.pre_valid) {
-        pre.a = c.pre_a;
-        pre.b = c.pre_b;
-      } else if (epi_lane) {
-        pre = epilogue_prefetch(ph, c, g * R + 2 * my_pr, my_n);
-      }
-      float acc[R][NB];
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int n = 0; n < NB; ++n) acc[r][n] = 0.f;
-      const int slot = c.cnt % SLOTS;
-      mbar_wait(&c.full[c.warp * SLOTS + slot], (c.cnt / SLOTS) & 1, c.sync, 0x200 + c.warp);
-      if (c.trp && i == 0 && !ph.attn_prologue) c.trp[1] = gtimer();
-      chunk_dot<R, NB>(c.ring + (size_t)(c.warp * SLOTS + slot) * CHUNK_ELEMS, c.xs, K, KC, c.lane, acc);
-      __syncwarp();
-      ++c.cnt;
-      if (c.trp && i == 0 && !ph.attn_prologue) c.trp[2] = gtimer();
-      // the slot is drained: refill it with the chunk SLOTS ahead in this warp's stream
-      pf_issue(c.pf, tab, c.ring, c.full, cta, ncta, c.warp, c.lane);
-      if (L2_AHEAD > 0) pf_issue_l2(c.pf2, tab, cta, ncta, c.warp, c.lane);
-      float y0 = 0.f, y1 = 0.f;
-#pragma unroll
-      for (int r = 0; r < R / 2; ++r)
-#pragma unroll
-        for (int n = 0; n < NB; ++n) {
-          const float s0 = warp_sum(acc[2 * r][n]);
-          const float s1 = warp_sum(acc[2 * r + 1][n]);
-          if (c.lane == r + n * (R / 2)) {
-            y0 = s0;
-            y1 = s1;
-          }
-        }
-      if (epi_lane) {
-        const int r0 = g * R + 2 * my_pr;
-        if (r0 < ph.rows && my_n < ph.nb) epilogue(ph, c, r0, my_n, y0, y1, pre);
-      }
-      if (c.trp && i == 0 && !ph.attn_prologue) c.trp[3] = gtimer();
+    for (int w = 0; w < NW; ++w) {  // fixed order -> deterministic rounding
+      y0 += ps[(size_t)w * 16 * MAXNB];
+      y1 += ps[(size_t)w * 16 * MAXNB + MAXNB];
     }
-  } else {
-    // split K: post-pass item t = (row group j of this CTA, pair, activation row)
-    const int ngroups = ph.G > cta ? (ph.G - cta + ncta - 1) / ncta : 0;
-    const int per_group = (R / 2) * ph.nb;
-    const int items = ngroups * per_group;
-    int pj = 0, pr0 = 0, pn = 0;
-    EpiPre pre;
-    pre.a = pre.b = 0.f;
-    if (c.tid < items) {
-      pj = c.tid / per_group;
-      const int rem = c.tid - pj * per_group;
-      pn = rem / (R / 2);
-      pr0 = (cta + ncta * pj) * R + 2 * (rem % (R / 2));
-      pre = epilogue_prefetch(ph, c, pr0, pn);
-    }
-    for (int u = c.warp;; u += NW) {
-      const int j = u / nkc, kc = u - j * nkc;
-      if (cta + ncta * j >= ph.G) break;
-      float acc[R][NB];
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int n = 0; n < NB; ++n) acc[r][n] = 0.f;
-      const int slot = c.cnt % SLOTS;
-      mbar_wait(&c.full[c.warp * SLOTS + slot], (c.cnt / SLOTS) & 1, c.sync, 0x200 + c.warp);
-      if (c.trp && u == c.warp) c.trp[1] = gtimer();
-      chunk_dot<R, NB>(c.ring + (size_t)(c.warp * SLOTS + slot) * CHUNK_ELEMS, c.xs + (size_t)kc * KC, K, KC, c.lane, acc);
-      __syncwarp();
-      ++c.cnt;
-      if (c.trp && u == c.warp) c.trp[2] = gtimer();
-      pf_issue(c.pf, tab, c.ring, c.full, cta, ncta, c.warp, c.lane);
-      if (L2_AHEAD > 0) pf_issue_l2(c.pf2, tab, cta, ncta, c.warp, c.lane);
-#pragma unroll
-      for (int r = 0; r < R; ++r)
-#pragma unroll
-        for (int n = 0; n < NB; ++n) {
-          const float sr = warp_sum(acc[r][n]);
-          if (c.lane == r * NB + n) c.psum[(u * R + r) * MAXNB + n] = sr;
-        }
-    }
-    csync<NCT, CBAR>();
-    if (c.trp) c.trp[3] = gtimer();
-    if (c.tid < items) {
-      const int pr = (pr0 - (cta + ncta * pj) * R);  // row inside the group (even)
-      float y0 = 0.f, y1 = 0.f;
-      for (int kc = 0; kc < nkc; ++kc) {  // fixed order -> deterministic rounding
-        y0 += c.psum[((pj * nkc + kc) * R + pr) * MAXNB + pn];
-        y1 += c.psum[((pj * nkc + kc) * R + pr + 1) * MAXNB + pn];
-      }
-      epilogue(ph, c, pr0, pn, y0, y1, pre);
-    }
+    epilogue(ph, c, (cl + ncta * j_item) * R + 2 * pair, n_item, y0, y1, pre);
   }
 }
 
@@ -491,18 +475,14 @@ __device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c, const PfTab
 //   xs layout (bf16 elements): [0, nb*dim) output rows | [2048, +nb*dim) q | [4096, +kv*keys*136) K
 //   rows padded to 136 (conflict-free 16-byte reads with lane == key) | [12800, +kv*32*128) V |
 //   partial scores (fp32).
-// Two parts.  attn_prefetch runs while the PREVIOUS phase's grid barrier is still spinning: the K/V
-// rows of earlier positions are final, so they are copied into shared memory with cp.async there and
-// their (loaded) L2 latency disappears behind the barrier.  attn_small_into_x then only fetches q and
-// the current position's K/V rows, and computes out of shared memory: a warp owns (row, head, half of
-// the head dims): partial q.k over its 64 dims with lane == key, halves summed through shared
-// memory, softmax by shuffles, P.V for its 64 output dims with lane == 2 dims.
+// Two parts.  attn_prefetch runs right after the PREVIOUS phase ends: the K/V rows of earlier
+// positions are final, so they are copied into shared memory with cp.async while this CTA waits for
+// the q words.  attn_small_into_x then polls q and the current positions' K/V (tagged words of the
+// QKV phase) and computes out of shared memory: a warp owns (row, head, half of the head dims):
+// partial q.k over its 64 dims with lane == key, halves summed through shared memory, softmax by
+// shuffles, P.V for its 64 output dims with lane == 2 dims.
 constexpr int A_HD = 128, A_KS = A_HD + 8, A_QOFF = 2048, A_KOFF = 4096, A_VOFF = A_KOFF + 2 * 32 * A_KS;
 constexpr int A_PARTOFF = A_VOFF + 2 * 32 * A_HD;
-
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
 
 __device__ __forceinline__ void attn_prefetch(const Phase& ph, Ctx& c) {
   const int kvn = ph.kv_heads, nold = ph.pos0;  // positions [0, pos0) were written in earlier steps
@@ -522,24 +502,39 @@ __device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
   const int heads = ph.heads, kvn = ph.kv_heads, grp = heads / kvn, nb = ph.nb;
   float* part = reinterpret_cast<float*>(c.xs + A_PARTOFF);  // [nb*heads*2][32]
   const int nitems = nb * heads * 2;
-  {  // q rows and the K/V rows of the positions written by the phase that just finished
-    const int qunits = nb * heads * (A_HD / 8), kunits = kvn * nb * (A_HD / 8), total = qunits + 2 * kunits;
-    for (int u = c.tid; u < total; u += NCT) {
-      if (u < qunits) {
-        *reinterpret_cast<uint4*>(c.xs + A_QOFF + u * 8) = ldcg16(ph.q + u * 8);
-      } else {
-        const bool isv = u >= qunits + kunits;
-        const int ku = u - qunits - (isv ? kunits : 0), row = ku >> 4, i = ku & 15;
-        const int kvh = row / nb, j = ph.pos0 + row - kvh * nb;
-        const uint4 v = ldcg16((isv ? ph.vc : ph.kc) + (kvh * ph.slots + j) * A_HD + i * 8);
-        if (isv) *reinterpret_cast<uint4*>(c.xs + A_VOFF + (kvh * 32 + j) * A_HD + i * 8) = v;
-        else *reinterpret_cast<uint4*>(c.xs + A_KOFF + (kvh * 32 + j) * A_KS + i * 8) = v;
+  {  // q rows and the K/V rows of the positions written by the phase that just finished (tagged words)
+    const uint32_t tag = tag_of(c.seq, ph.q_src);
+    const int krows = kvn * A_HD;
+    const int qunits = nb * heads * (A_HD / 4), kunits = nb * 2 * krows / 4, total = qunits + kunits;
+    for (int u0 = 0; u0 < total; u0 += 4 * NCT) {
+      uint4 v[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int u = u0 + t * NCT + c.tid;
+        if (u < total) v[t] = ldv4(u < qunits ? ph.t_q + u * 4 : ph.t_kv + (u - qunits) * 4);
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int u = u0 + t * NCT + c.tid;
+        if (u < total) {
+          if (u < qunits) {
+            v[t] = poll4(ph.t_q + u * 4, tag, v[t], c.sync);
+            *reinterpret_cast<uint2*>(c.xs + A_QOFF + u * 4) = strip4(v[t]);
+          } else {
+            const int e = (u - qunits) * 4;  // element in [nb][2][krows]
+            v[t] = poll4(ph.t_kv + e, tag, v[t], c.sync);
+            const int n = e / (2 * krows), r = e - n * 2 * krows;
+            const bool isv = r >= krows;
+            const int rr = isv ? r - krows : r, kvh = rr / A_HD, d = rr % A_HD, j = ph.pos0 + n;
+            bf16* dst = isv ? c.xs + A_VOFF + (kvh * 32 + j) * A_HD + d : c.xs + A_KOFF + (kvh * 32 + j) * A_KS + d;
+            *reinterpret_cast<uint2*>(dst) = strip4(v[t]);
+          }
+        }
       }
     }
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   csync<NCT, CBAR>();
-  if (c.trp) c.trp[1] = gtimer();
   const float scale = 0.08838834764831845f;  // 1/sqrt(128)
   for (int it0 = 0; it0 < nitems; it0 += NW) {
     const int item = it0 + c.warp;
@@ -559,7 +554,6 @@ __device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
     }
   }
   csync<NCT, CBAR>();
-  if (c.trp) c.trp[2] = gtimer();
   for (int it0 = 0; it0 < nitems; it0 += NW) {
     const int item = it0 + c.warp;
     if (item < nitems) {
@@ -572,7 +566,7 @@ __device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
       const float inv = 1.0f / warp_sum(e);
       const bf16* vp = c.xs + A_VOFF + kvh * 32 * A_HD + half * 64 + c.lane * 2;
       float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};  // 4 independent chains
-      for (int j0 = 0; j0 < nkeys; j0 += 4) {  // only the visible keys, 4 independent chains
+      for (int j0 = 0; j0 < nkeys; j0 += 4) {  // only the visible keys
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           const int j = j0 + t;
@@ -586,46 +580,55 @@ __device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
           __floats2bfloat162_rn(((o0[0] + o0[1]) + (o0[2] + o0[3])) * inv, ((o1[0] + o1[1]) + (o1[2] + o1[3])) * inv);
     }
   }
-  if (c.trp) c.trp[3] = gtimer();
   csync<NCT, CBAR>();
 }
 
-__device__ __forceinline__ float sumsq8(const uint4& v) {
+__device__ __forceinline__ float sumsq4(const uint4& v) {
   float s = 0.f, a;
-  a = bflo(v.x); s = fmaf(a, a, s); a = bfhi(v.x); s = fmaf(a, a, s);
-  a = bflo(v.y); s = fmaf(a, a, s); a = bfhi(v.y); s = fmaf(a, a, s);
-  a = bflo(v.z); s = fmaf(a, a, s); a = bfhi(v.z); s = fmaf(a, a, s);
-  a = bflo(v.w); s = fmaf(a, a, s); a = bfhi(v.w); s = fmaf(a, a, s);
+  a = tval(v.x); s = fmaf(a, a, s);
+  a = tval(v.y); s = fmaf(a, a, s);
+  a = tval(v.z); s = fmaf(a, a, s);
+  a = tval(v.w); s = fmaf(a, a, s);
   return s;
 }
-// torchtune RMSNorm on 8 elements: bf16( bf16(x * inv) * scale )
-__device__ __forceinline__ uint4 norm8(const uint4& v, float inv, const uint4& sc) {
-  __nv_bfloat162 o[4];
-  o[0] = __floats2bfloat162_rn(rbf(bflo(v.x) * inv) * bflo(sc.x), rbf(bfhi(v.x) * inv) * bfhi(sc.x));
-  o[1] = __floats2bfloat162_rn(rbf(bflo(v.y) * inv) * bflo(sc.y), rbf(bfhi(v.y) * inv) * bfhi(sc.y));
-  o[2] = __floats2bfloat162_rn(rbf(bflo(v.z) * inv) * bflo(sc.z), rbf(bfhi(v.z) * inv) * bfhi(sc.z));
-  o[3] = __floats2bfloat162_rn(rbf(bflo(v.w) * inv) * bflo(sc.w), rbf(bfhi(v.w) * inv) * bfhi(sc.w));
-  return *reinterpret_cast<uint4*>(o);
+// torchtune RMSNorm on 4 tagged elements: bf16( bf16(x * inv) * scale ), packed
+__device__ __forceinline__ uint2 norm4(const uint4& v, float inv, uint32_t sc01, uint32_t sc23) {
+  __nv_bfloat162 o[2];
+  o[0] = __floats2bfloat162_rn(rbf(tval(v.x) * inv) * bflo(sc01), rbf(tval(v.y) * inv) * bfhi(sc01));
+  o[1] = __floats2bfloat162_rn(rbf(tval(v.z) * inv) * bflo(sc23), rbf(tval(v.w) * inv) * bfhi(sc23));
+  return *reinterpret_cast<uint2*>(o);
 }
 
-// stage the phase's activation rows into shared memory (+ RMSNorm prologue)
+// stage the phase's activation rows into shared memory (+ RMSNorm prologue): poll the tagged words
 __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
   if (ph.attn_prologue) {
     attn_small_into_x(ph, c);
     return;
   }
   const int K = ph.K, nb = ph.nb;
+  const uint32_t tag0 = tag_of(c.seq, ph.x_src[0]), tag1 = tag_of(c.seq, ph.x_src[1]);
   if (ph.norm) {
-    // K <= 2048 for every normed phase: one 16-byte unit per thread; x and scale loads together
+    // K <= 2048 for every normed phase: one 8-element unit per thread
     const int k8 = c.tid;
     const bool on = k8 < K / 8;
-    uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0, sc = x0;
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0, sc = a0;
     if (on) {
-      x0 = ldcg16(ph.x + k8 * 8);
-      if (nb == 2) x1 = ldcg16(ph.x + ph.ldx + k8 * 8);
-      sc = c.pre_valid ? c.pre_scale : *reinterpret_cast<const uint4*>(ph.norm_scale + k8 * 8);
+      const uint32_t* p0 = ph.t_x + k8 * 8;
+      a0 = ldv4(p0);
+      a1 = ldv4(p0 + 4);
+      if (nb == 2) {
+        b0 = ldv4(p0 + ph.ldx);
+        b1 = ldv4(p0 + ph.ldx + 4);
+      }
+      sc = *reinterpret_cast<const uint4*>(ph.norm_scale + k8 * 8);
+      a0 = poll4(p0, tag0, a0, c.sync);
+      a1 = poll4(p0 + 4, tag0, a1, c.sync);
+      if (nb == 2) {
+        b0 = poll4(p0 + ph.ldx, tag1, b0, c.sync);
+        b1 = poll4(p0 + ph.ldx + 4, tag1, b1, c.sync);
+      }
     }
-    float s0 = sumsq8(x0), s1 = sumsq8(x1);
+    float s0 = sumsq4(a0) + sumsq4(a1), s1 = sumsq4(b0) + sumsq4(b1);
     s0 = warp_sum(s0);
     s1 = warp_sum(s1);
     if (c.lane == 0) {
@@ -640,53 +643,66 @@ __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
       t1 += c.scratch[NW + w];
     }
     if (on) {
-      *reinterpret_cast<uint4*>(c.xs + k8 * 8) = norm8(x0, 1.0f / sqrtf(t0 / (float)K + ph.eps), sc);
-      if (nb == 2) *reinterpret_cast<uint4*>(c.xs + K + k8 * 8) = norm8(x1, 1.0f / sqrtf(t1 / (float)K + ph.eps), sc);
-    }
-  } else {
-    constexpr int MAXIT = 8192 / 8 / NCT;
-    uint4 v0[MAXIT], v1[MAXIT];
-#pragma unroll
-    for (int t = 0; t < MAXIT; ++t) {
-      const int k8 = c.tid + t * NCT;
-      if (k8 < K / 8) {
-        v0[t] = ldcg16(ph.x + k8 * 8);
-        if (nb == 2) v1[t] = ldcg16(ph.x + ph.ldx + k8 * 8);
+      const float i0 = 1.0f / sqrtf(t0 / (float)K + ph.eps);
+      const uint2 lo = norm4(a0, i0, sc.x, sc.y), hi = norm4(a1, i0, sc.z, sc.w);
+      *reinterpret_cast<uint4*>(c.xs + k8 * 8) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+      if (nb == 2) {
+        const float i1 = 1.0f / sqrtf(t1 / (float)K + ph.eps);
+        const uint2 lo1 = norm4(b0, i1, sc.x, sc.y), hi1 = norm4(b1, i1, sc.z, sc.w);
+        *reinterpret_cast<uint4*>(c.xs + K + k8 * 8) = make_uint4(lo1.x, lo1.y, hi1.x, hi1.y);
       }
     }
+  } else {
+    // 4-word units, 8 in flight per thread
+    const int upr = K / 4, total = nb * upr;
+    for (int u0 = 0; u0 < total; u0 += 8 * NCT) {
+      uint4 v[8];
 #pragma unroll
-    for (int t = 0; t < MAXIT; ++t) {
-      const int k8 = c.tid + t * NCT;
-      if (k8 < K / 8) {
-        *reinterpret_cast<uint4*>(c.xs + k8 * 8) = v0[t];
-        if (nb == 2) *reinterpret_cast<uint4*>(c.xs + K + k8 * 8) = v1[t];
+      for (int t = 0; t < 8; ++t) {
+        const int u = u0 + t * NCT + c.tid;
+        if (u < total) {
+          const int n = u >= upr ? 1 : 0, k4 = u - n * upr;
+          v[t] = ldv4(ph.t_x + (size_t)n * ph.ldx + k4 * 4);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int u = u0 + t * NCT + c.tid;
+        if (u < total) {
+          const int n = u >= upr ? 1 : 0, k4 = u - n * upr;
+          v[t] = poll4(ph.t_x + (size_t)n * ph.ldx + k4 * 4, n ? tag1 : tag0, v[t], c.sync);
+          *reinterpret_cast<uint2*>(c.xs + (size_t)n * K + k4 * 4) = strip4(v[t]);
+        }
       }
     }
   }
   csync<NCT, CBAR>();
-  if (ph.x_copy_out && blockIdx.x == 0) {
-    for (int k8 = c.tid; k8 < nb * (K / 8); k8 += NCT)
-      *reinterpret_cast<uint4*>(ph.x_copy_out + k8 * 8) = *reinterpret_cast<const uint4*>(c.xs + k8 * 8);
-  }
 }
 
 __device__ __forceinline__ void gemv_phase(const Phase& ph, Ctx& c, const PfTable& tab) {
+  const int ncta = gridDim.x;
+  const int cl = local_cta(blockIdx.x, ncta, ph.rot);
+  const int ngl = ph.gq + (cl < ph.gr ? 1 : 0);
+  if (ngl == 0) return;  // nothing to do here: run ahead
+  // epilogue item of this thread: (local group, row pair, activation row)
+  const int R = ph.R;
+  const int ipg_shift = R == 16 ? 4 : 3;  // items per group = (R / 2) pairs x 2 activation rows
+  const int j_item = c.tid >> ipg_shift, rem = c.tid & ((1 << ipg_shift) - 1);
+  const int pair = rem >> 1, n_item = rem & 1;
+  const int r0 = (cl + ncta * j_item) * R + 2 * pair;
+  const bool item_on = j_item < ngl && n_item < ph.nb && r0 < ph.rows;
+  EpiPre pre;
+  pre.a = pre.b = 0.f;
+  if (item_on) pre = epilogue_prefetch(ph, c, r0, n_item);
   stage_x(ph, c);
-  if (c.trp) c.trp[0] = gtimer();
-  if (ph.nb == 1) {
-    if (ph.R == 2) gemv_groups<2, 1>(ph, c, tab);
-    else if (ph.R == 4) gemv_groups<4, 1>(ph, c, tab);
-    else if (ph.R == 8) gemv_groups<8, 1>(ph, c, tab);
-    else gemv_groups<16, 1>(ph, c, tab);
-  } else {
-    if (ph.R == 2) gemv_groups<2, 2>(ph, c, tab);
-    else if (ph.R == 4) gemv_groups<4, 2>(ph, c, tab);
-    else if (ph.R == 8) gemv_groups<8, 2>(ph, c, tab);
-    else gemv_groups<16, 2>(ph, c, tab);
-  }
+  if (c.trp) c.trp[1] = gtimer();
+  if (R == 16) gemv_groups<16>(ph, c, tab, cl, ngl, j_item, pair, n_item, item_on, pre);
+  else gemv_groups<8>(ph, c, tab, cl, ngl, j_item, pair, n_item, item_on, pre);
+  if (ph.epi == EPI_ROPE_KV) __threadfence();  // plain cache rows: ordered before this CTA's later tagged words
 }
 
-// backbone attention: CTA h < heads owns q-head h over keys [0 .. slot]
+// backbone attention: CTA h < heads owns q-head h over keys [0 .. slot]; the current position's K/V
+// come from the QKV phase's tagged words, earlier positions from the cache (previous launches)
 __device__ __forceinline__ void attn_phase(const Phase& ph, Ctx& c) {
   const int h = blockIdx.x;
   if (h >= ph.heads) return;
@@ -695,25 +711,38 @@ __device__ __forceinline__ void attn_phase(const Phase& ph, Ctx& c) {
   phase_pos(ph, c, 0, pos, slot);
   const int nkeys = slot + 1;
   const int kvh = h / (ph.heads / ph.kv_heads);
+  const int krows = ph.kv_heads * hd;
   const bf16* kp = ph.kc + (size_t)kvh * ph.slots * hd;
   const bf16* vp = ph.vc + (size_t)kvh * ph.slots * hd;
   float* sc = reinterpret_cast<float*>(c.xs);  // [slots] scores (<= 8 KB)
   float* part = sc + ph.slots;                  // [NCT] partial outputs
   float* qs = part + NCT;                       // [hd]
+  float* kcur = qs + hd;                        // [hd]
+  float* vcur = kcur + hd;                      // [hd]
   const float scale = 1.0f / sqrtf((float)hd);
-  for (int d = c.tid; d < hd; d += NCT) qs[d] = ldcg_bf(ph.q + (size_t)h * hd + d);
+  const uint32_t tag = tag_of(c.seq, ph.q_src);
+  for (int d = c.tid; d < 3 * hd; d += NCT) {
+    const int which = d / hd, dd = d - which * hd;
+    const uint32_t* src = which == 0 ? ph.t_q + (size_t)h * hd + dd
+                                     : ph.t_kv + (size_t)(which - 1) * krows + (size_t)kvh * hd + dd;
+    qs[d] = tval(poll1(src, tag, c.sync));  // qs, kcur, vcur are contiguous
+  }
   csync<NCT, CBAR>();
   float mx = -INFINITY;
   for (int j = c.tid; j < nkeys; j += NCT) {
-    const bf16* kr = kp + (size_t)j * hd;
     float s = 0.f;
-    for (int i = 0; i < hd / 8; ++i) {
-      const uint4 v = ldcg16(kr + i * 8);
-      const float* q8 = qs + i * 8;
-      s = fmaf(q8[0], bflo(v.x), s); s = fmaf(q8[1], bfhi(v.x), s);
-      s = fmaf(q8[2], bflo(v.y), s); s = fmaf(q8[3], bfhi(v.y), s);
-      s = fmaf(q8[4], bflo(v.z), s); s = fmaf(q8[5], bfhi(v.z), s);
-      s = fmaf(q8[6], bflo(v.w), s); s = fmaf(q8[7], bfhi(v.w), s);
+    if (j == slot) {
+      for (int i = 0; i < hd; ++i) s = fmaf(qs[i], kcur[i], s);
+    } else {
+      const bf16* kr = kp + (size_t)j * hd;
+      for (int i = 0; i < hd / 8; ++i) {
+        const uint4 v = ldcg16(kr + i * 8);
+        const float* q8 = qs + i * 8;
+        s = fmaf(q8[0], bflo(v.x), s); s = fmaf(q8[1], bfhi(v.x), s);
+        s = fmaf(q8[2], bflo(v.y), s); s = fmaf(q8[3], bfhi(v.y), s);
+        s = fmaf(q8[4], bflo(v.z), s); s = fmaf(q8[5], bfhi(v.z), s);
+        s = fmaf(q8[6], bflo(v.w), s); s = fmaf(q8[7], bfhi(v.w), s);
+      }
     }
     s *= scale;
     sc[j] = s;
@@ -729,26 +758,28 @@ __device__ __forceinline__ void attn_phase(const Phase& ph, Ctx& c) {
   sum = block_sum<NCT, CBAR>(sum, c.scratch, c.tid);
   const int G = NCT / hd;  // key groups
   const int g = c.tid / hd, d = c.tid % hd;
+  const int nold = nkeys - 1;  // keys in the cache
   float acc = 0.f;
   int j = g;
-  for (; j + 7 * G < nkeys; j += 8 * G) {  // 8 independent loads in flight
+  for (; j + 7 * G < nold; j += 8 * G) {  // 8 independent loads in flight
     float v[8];
 #pragma unroll
     for (int u = 0; u < 8; ++u) v[u] = ldcg_bf(vp + (size_t)(j + u * G) * hd + d);
 #pragma unroll
     for (int u = 0; u < 8; ++u) acc = fmaf(sc[j + u * G], v[u], acc);
   }
-  for (; j < nkeys; j += G) acc = fmaf(sc[j], ldcg_bf(vp + (size_t)j * hd + d), acc);
+  for (; j < nold; j += G) acc = fmaf(sc[j], ldcg_bf(vp + (size_t)j * hd + d), acc);
+  if (g == 0) acc = fmaf(sc[slot], vcur[d], acc);
   part[c.tid] = acc;
   csync<NCT, CBAR>();
   if (g == 0) {
     for (int gg = 1; gg < G; ++gg) acc += part[gg * hd + d];
-    ph.att_out[(size_t)h * hd + d] = f2bf(acc * (1.0f / sum));
+    __stcg(ph.t_out + (size_t)h * hd + d, tword(c.tag, acc * (1.0f / sum)));
   }
 }
 
 __device__ __forceinline__ void embed_phase(const Phase& ph, Ctx& c) {
-  // one 16-byte unit of h per thread: unit u = cta + ncta * tid
+  // one 8-element unit of h per thread: unit u = cta + ncta * tid
   const FrameParams* P = c.P;
   const int u = blockIdx.x + gridDim.x * c.tid;
   if (u >= ph.D / 8) return;
@@ -779,10 +810,9 @@ __device__ __forceinline__ void embed_phase(const Phase& ph, Ctx& c) {
         acc[4] += bflo(v[j].z); acc[5] += bfhi(v[j].z); acc[6] += bflo(v[j].w); acc[7] += bfhi(v[j].w);
       }
   }
-  __nv_bfloat162 o[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) o[i] = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]);
-  *reinterpret_cast<uint4*>(ph.h_out + u * 8) = *reinterpret_cast<uint4*>(o);
+  const uint32_t tag = c.tag;
+  stv4(ph.t_out + u * 8, make_uint4(tword(tag, acc[0]), tword(tag, acc[1]), tword(tag, acc[2]), tword(tag, acc[3])));
+  stv4(ph.t_out + u * 8 + 4, make_uint4(tword(tag, acc[4]), tword(tag, acc[5]), tword(tag, acc[6]), tword(tag, acc[7])));
 }
 
 __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
@@ -790,50 +820,74 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
   const FrameParams* P = c.P;
   float* xs = reinterpret_cast<float*>(c.xs);                              // [4096]
   unsigned int* hist = reinterpret_cast<unsigned int*>(xs + SAMPLE_MAXV);  // [256]
+  bf16* lg = reinterpret_cast<bf16*>(hist + 256);                          // [V] logits of this step
   const int V = ph.V, C = ph.C, cb = ph.cb;
+  {
+    const uint32_t tag = tag_of(c.seq, ph.logits_src);
+    constexpr int MAXPT = SAMPLE_MAXV / NCT;
+    uint32_t w[MAXPT];
+#pragma unroll
+    for (int t = 0; t < MAXPT; ++t) {
+      const int i = c.tid + t * NCT;
+      if (i < V) w[t] = ldv1(ph.t_logits + i);
+    }
+#pragma unroll
+    for (int t = 0; t < MAXPT; ++t) {
+      const int i = c.tid + t * NCT;
+      if (i < V) {
+        for (unsigned spin = 0; ((w[t] ^ tag) & 0xffff0000u) != 0; ++spin) {
+          if (spin > (1u << 22)) die(c.sync, 0x403);
+          w[t] = ldv1(ph.t_logits + i);
+        }
+        lg[i] = __ushort_as_bfloat16((unsigned short)(w[t] & 0xffffu));
+      }
+    }
+  }
+  csync<NCT, CBAR>();
+  if (c.trp) c.trp[1] = gtimer();
   if (P->logits_out)
-    for (int i = c.tid; i < V; i += NCT) P->logits_out[(size_t)cb * V + i] = __ushort_as_bfloat16(__ldcg(
-        reinterpret_cast<const unsigned short*>(ph.logits) + i));
+    for (int i = c.tid; i < V; i += NCT) P->logits_out[(size_t)cb * V + i] = lg[i];
   const bf16* nz = P->noise ? P->noise + (size_t)cb * V : nullptr;
   const unsigned long long ctr = ((P->offset * (unsigned long long)C + cb)) * 4096ull;
-  if (c.trp) c.trp[0] = gtimer();
-  int tok = sample_row<NCT, CBAR, true>(ph.logits, nz, V, P->temperature, P->topk, P->seed, ctr, xs, hist, c.scratch,
-                                        c.iscratch, c.tid);
-  if (c.trp) c.trp[1] = gtimer();
+  int tok = sample_row<NCT, CBAR, false>(lg, nz, V, P->temperature, P->topk, P->seed, ctr, xs, hist, c.scratch, c.iscratch,
+                                         c.tid);
+  if (c.trp) c.trp[2] = gtimer();
   if (c.tid == 0 && P->sampled_out) P->sampled_out[cb] = tok;
   if (P->forced) tok = P->forced[cb];
   if (c.tid == 0) P->out[cb] = tok;
-  if (ph.next_in) {
+  if (ph.t_next) {
     // next depth-decoder input: projection(embed_audio(cb, tok)) read from the table built at setup
-    const int ld = ph.next_table ? ph.next_ld : ph.D;
-    const bf16* row = (ph.next_table ? ph.next_table : ph.audio_emb) + ((size_t)tok + (size_t)cb * V) * ld;
-    for (int d8 = c.tid; d8 < ld / 8; d8 += NCT)
-      *reinterpret_cast<uint4*>(ph.next_in + d8 * 8) = *reinterpret_cast<const uint4*>(row + d8 * 8);
+    const int ld = ph.next_ld;
+    const bf16* row = ph.next_table + ((size_t)tok + (size_t)cb * V) * ld;
+    const uint32_t tag = c.tag;
+    for (int d4 = c.tid; d4 < ld / 4; d4 += NCT) {
+      const uint2 v = *reinterpret_cast<const uint2*>(row + d4 * 4);
+      stv4(ph.t_next + d4 * 4, make_uint4(tword_raw(tag, v.x), tword_raw(tag, v.x >> 16), tword_raw(tag, v.y),
+                                          tword_raw(tag, v.y >> 16)));
+    }
   }
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NCT, 1)
 k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* __restrict__ P, Sync* sync,
-             unsigned long long* __restrict__ trace /* optional [nphases][8] globaltimer ns of CTA 0 */,
+             unsigned long long* __restrict__ trace /* optional [nphases][4] globaltimer ns of CTA 0 */,
              const __grid_constant__ PfTable tab) {
   extern __shared__ __align__(128) unsigned char smem[];
-  bf16* ring = reinterpret_cast<bf16*>(smem);
+  unsigned char* ring = smem;
   bf16* xs = reinterpret_cast<bf16*>(smem + SMEM_RING);
-  unsigned char* misc = smem + SMEM_RING + SMEM_X;
+  float* psum = reinterpret_cast<float*>(smem + SMEM_RING + SMEM_X);
+  unsigned char* misc = smem + SMEM_RING + SMEM_X + SMEM_PSUM;
   Phase* phbuf = reinterpret_cast<Phase*>(misc);                           // [2] double buffer
   uint64_t* full = reinterpret_cast<uint64_t*>(misc + 2 * sizeof(Phase));  // [NW*SLOTS]
   float* scratch = reinterpret_cast<float*>(full + NW * SLOTS);            // [34]
   int* iscratch = reinterpret_cast<int*>(scratch + 34);                    // [40]
-  float* psum = reinterpret_cast<float*>(iscratch + 40);                   // [MAX_SPLIT_TASKS * 2 * MAXNB]
-  static_assert(2 * sizeof(Phase) + NW * SLOTS * 8 + 34 * 4 + 40 * 4 + MAX_SPLIT_TASKS * 2 * MAXNB * 4 <= SMEM_MISC,
-                "misc region too small");
-  static_assert(NW <= 32, "block reductions assume <= 32 warps");
+  static_assert(2 * sizeof(Phase) + NW * SLOTS * 8 + 34 * 4 + 40 * 4 <= SMEM_MISC, "misc region too small");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
   Ctx c;
   c.P = P; c.trp = nullptr; c.ring = ring; c.xs = xs; c.full = full; c.scratch = scratch; c.iscratch = iscratch; c.psum = psum;
   c.sync = sync; c.cnt = 0; c.tid = threadIdx.x; c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
-  c.pre_valid = false; c.pre_a = c.pre_b = 0.f; c.pre_scale = make_uint4(0, 0, 0, 0);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NW * SLOTS; ++i) mbar_init(&full[i], 1);
@@ -844,25 +898,25 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
   if (c.tid < PH16) reinterpret_cast<uint4*>(&phbuf[0])[c.tid] = reinterpret_cast<const uint4*>(&phases[0])[c.tid];
   c.bb_pos = (int)P->pos[P->S - 1];  // batch 1: stream 0, last prompt row
   c.bb_slot = P->cache_len + P->S - 1;
+  c.seq = sync->seq;
   __syncthreads();
 
   // start this warp's weight stream: SLOTS chunks in flight from now on
-  c.pf.gi = 0; c.pf.u = c.warp; c.pf.issued = 0; c.pf.done = false;
+  c.pf.gi = 0; c.pf.j = 0; c.pf.c = 0; c.pf.issued = 0; c.pf.done = false;
   c.pf.policy = policy_evict_first();
-  pf_seek(c.pf, tab, blockIdx.x, gridDim.x, c.warp);
+  pf_seek(c.pf, tab, blockIdx.x, gridDim.x);
   for (int s = 0; s < SLOTS; ++s) pf_issue(c.pf, tab, ring, full, blockIdx.x, gridDim.x, c.warp, c.lane);
-  c.pf2 = c.pf;  // continues where the ring cursor stands, then stays L2_AHEAD chunks in front
-  for (int s = 0; s < L2_AHEAD; ++s) pf_issue_l2(c.pf2, tab, blockIdx.x, gridDim.x, c.warp, c.lane);
 
-  const unsigned ncta = gridDim.x;
   const bool tr = trace != nullptr && blockIdx.x == 0 && c.tid == 0;
   for (int p = 0; p < nphases; ++p) {
     const Phase& ph = phbuf[p & 1];
+    c.tag = tag_of(c.seq, p);
     if (tr) {
-      trace[p * 8 + 0] = gtimer();
-      c.trp = trace + p * 8 + 4;
+      c.trp = trace + p * 4;
+      c.trp[0] = gtimer();
+      c.trp[1] = c.trp[2] = 0;
     }
-    // stage the next descriptor while this phase runs (read after the barrier below)
+    // stage the next descriptor while this phase runs (read after the CTA barrier below)
     if (p + 1 < nphases && c.tid < PH16)
       reinterpret_cast<uint4*>(&phbuf[(p + 1) & 1])[c.tid] = reinterpret_cast<const uint4*>(&phases[p + 1])[c.tid];
     switch (ph.type) {
@@ -871,39 +925,16 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
       case PH_ATTN: attn_phase(ph, c); break;
       default: sample_phase(ph, c); break;
     }
-    if (tr) trace[p * 8 + 1] = gtimer();
-    if (p + 1 == nphases) break;
-    // grid barrier: every CTA's writes of phase p are visible before anyone starts phase p+1
+    if (tr) c.trp[3] = gtimer();
+    // end of phase inside the CTA: shared activations / partial sums may be overwritten from here on
     csync<NCT, CBAR>();
-    if (tr) trace[p * 8 + 2] = gtimer();
-    if (c.tid == 0) arrive_release(&sync->counter);
-    {
-      // While the barrier resolves: fetch what phase p+1 needs that is already final -- the norm
-      // scale and the epilogue operands (residual values from two phases ago, RoPE cos/sin) of this
-      // warp's first row group.  Their L2 round trip then overlaps the barrier instead of following it.
+    if (p + 1 < nphases) {
       const Phase& nx = phbuf[(p + 1) & 1];
-      c.pre_valid = false;
-      if (nx.type == PH_GEMV && nx.attn_prologue) attn_prefetch(nx, c);
-      if (nx.type == PH_GEMV) {
-        c.pre_valid = true;
-        if (nx.norm && c.tid < nx.K / 8) c.pre_scale = *reinterpret_cast<const uint4*>(nx.norm_scale + c.tid * 8);
-        const int g = group_of(blockIdx.x, gridDim.x, c.warp, 0);
-        const int hp = nx.R / 2;
-        c.pre_a = c.pre_b = 0.f;
-        if (g < nx.G && c.lane < hp * nx.nb) {
-          const EpiPre e = epilogue_prefetch(nx, c, g * nx.R + 2 * (c.lane % hp), c.lane / hp);
-          c.pre_a = e.a;
-          c.pre_b = e.b;
-        }
+      if (nx.type == PH_GEMV && nx.attn_prologue) {
+        const int cl = local_cta(blockIdx.x, gridDim.x, nx.rot);
+        if (nx.gq + (cl < nx.gr ? 1 : 0) > 0) attn_prefetch(nx, c);
       }
     }
-    if (c.tid == 0) {
-      const unsigned target = ncta * (unsigned)(p + 1);
-      for (unsigned spin = 0; ld_acquire(&sync->counter) < target; ++spin)
-        if (spin > (1u << 24)) die(sync, 0x300);
-    }
-    csync<NCT, CBAR>();
-    if (tr) trace[p * 8 + 3] = gtimer();
   }
 }
 

@@ -15,7 +15,7 @@ from sesameai import _native, synthetic as syn
 model = bench.build_product(torch.device("cuda", 0), 1)
 L = _native.lib()
 nph = L.csm_debug_set_trace(model._ctx, None)
-buf = torch.zeros(nph, 8, dtype=torch.int64, device="cuda")
+buf = torch.zeros(nph, 4, dtype=torch.int64, device="cuda")
 tok, msk, pos = syn.text_prompt(1, 32, 4321, device="cuda")
 model.reset_caches()
 s = model.generate_frame(tok, msk, pos, 1.0, 1)
@@ -40,26 +40,16 @@ for i in range(1, 32):
         kinds += ["d.qkv", "d.o+attn", "d.gu", "d.down"]
     kinds += ["d.head", "sample"]
 assert len(kinds) == nph, (len(kinds), nph)
-agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0])
-fine = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0, 0.0])
-for i, k in enumerate(kinds[:-1]):
+agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0, 0.0])
+for i, k in enumerate(kinds):
     a = agg[k]
     a[0] += 1
-    a[1] += (tr[i, 1] - tr[i, 0]) / 1e3   # work
-    a[2] += (tr[i, 2] - tr[i, 1]) / 1e3   # CTA-local sync
-    a[3] += (tr[i, 3] - tr[i, 2]) / 1e3   # grid barrier (arrive + wait for slowest CTA)
-    f = fine[k]
-    f[0] += 1
-    for j in range(4):
-        if tr[i, 4 + j] > 0:
-            f[1 + j] += (tr[i, 4 + j] - tr[i, 0]) / 1e3
-print(f"frame total {(tr[-1,1]-tr[0,0])/1e3:.1f} us over {nph} phases")
-print(f"{'phase':10s} {'n':>4s} {'work us':>9s} {'csync us':>9s} {'grid us':>9s}   (avg per phase)")
-tot = [0, 0, 0]
+    nxt = tr[i + 1, 0] if i + 1 < nph else tr[i, 3]
+    a[1] += (nxt - tr[i, 0]) / 1e3                                    # whole phase (start -> next start)
+    if tr[i, 1] > 0: a[2] += (tr[i, 1] - tr[i, 0]) / 1e3              # inputs staged (hand-off wait + norm / attention)
+    if tr[i, 2] > 0 and tr[i, 1] > 0: a[3] += (tr[i, 2] - tr[i, 1]) / 1e3  # weight chunks + mma (gemv) / sampling
+    if tr[i, 2] > 0: a[4] += (tr[i, 3] - tr[i, 2]) / 1e3              # partial-sum pass + epilogue
+print(f"frame total {(tr[-1,3]-tr[0,0])/1e3:.1f} us over {nph} phases (CTA 0 timeline)")
+print(f"{'phase':10s} {'n':>4s} {'total us':>9s} {'staged':>9s} {'stream':>9s} {'epilogue':>9s}   (avg per phase)")
 for k, a in agg.items():
-    print(f"{k:10s} {a[0]:4d} {a[1]/a[0]:9.2f} {a[2]/a[0]:9.2f} {a[3]/a[0]:9.2f}   total {sum(a[1:]):8.1f}")
-    for j in range(3): tot[j] += a[1 + j]
-print("totals us: work %.1f csync %.1f grid %.1f" % tuple(tot))
-print("fine marks (avg us since phase start): gemv: x staged / first chunk landed / first chunk done / refill issued; sample: start / sampled")
-for k, f in fine.items():
-    print(f"{k:10s} " + " ".join(f"{f[1+j]/f[0]:8.2f}" for j in range(4)))
+    print(f"{k:10s} {a[0]:4d} {a[1]/a[0]:9.2f} {a[2]/a[0]:9.2f} {a[3]/a[0]:9.2f} {a[4]/a[0]:9.2f}   total {a[1]:8.1f}")
