@@ -61,6 +61,7 @@ struct StackDev {
   // megakernel: fragment-major packed matrices and tagged activation words
   std::vector<bf16*> fqkv, fo, fgu, fd;
   uint32_t *t_h, *t_q, *t_kv, *t_att, *t_act;
+  int rs_h, rs_q, rs_kv, rs_att, rs_act;  // words between the mega::REP copies of each tagged vector
 };
 
 struct csm_ctx {
@@ -151,14 +152,20 @@ static void carve_stack(Carver& cv, StackDev& s, const csm_stack_config& c, int 
     s.fd[l] = cv.take<bf16>((size_t)c.dim * c.ff);
   }
 }
+// REP copies of a tagged vector of n words, (n + pad) words apart
+static uint32_t* take_rep(Carver& cv, size_t n, int* rs) {
+  const size_t stride = ((n + 63) & ~(size_t)63) + 64;
+  *rs = (int)stride;
+  return cv.take<uint32_t>(stride * mega::REP);
+}
 static void carve_tagged(Carver& cv, StackDev& s) {
   const csm_stack_config& c = s.c;
   const size_t krows = (size_t)c.kv_heads * s.hd;
-  s.t_h = cv.take<uint32_t>((size_t)2 * c.dim);
-  s.t_q = cv.take<uint32_t>((size_t)2 * c.dim);
-  s.t_kv = cv.take<uint32_t>((size_t)2 * 2 * krows);
-  s.t_att = cv.take<uint32_t>((size_t)2 * c.dim);
-  s.t_act = cv.take<uint32_t>((size_t)2 * c.ff);
+  s.t_h = take_rep(cv, (size_t)2 * c.dim, &s.rs_h);
+  s.t_q = take_rep(cv, (size_t)2 * c.dim, &s.rs_q);
+  s.t_kv = take_rep(cv, (size_t)2 * 2 * krows, &s.rs_kv);
+  s.t_att = take_rep(cv, (size_t)2 * c.dim, &s.rs_att);
+  s.t_act = take_rep(cv, (size_t)2 * c.ff, &s.rs_act);
 }
 
 static size_t carve_all(csm_ctx* x, char* base) {
@@ -412,6 +419,12 @@ static mega::Phase gemv_phase_desc(MegaBuild& mb, const bf16* Wf, int rows, int 
   ph.G = (rows + R - 1) / R;
   ph.rot = mb.rot; ph.gq = ph.G / mb.ncta; ph.gr = ph.G % mb.ncta;
   mb.rot = (mb.rot + ph.gr) % mb.ncta;
+  ph.tb = R * K * 2 / mega::NW;
+  ph.chunk = ph.tb < mega::SLOT_BYTES ? ph.tb : mega::SLOT_BYTES;
+  ph.nch = ph.tb / ph.chunk;
+  ph.kchunk = ph.chunk / (R * 2);
+  ph.nblk = ph.chunk / (R * 64);
+  ph.inv_K = (K & (K - 1)) == 0 ? 1.0f / (float)K : 0.f;
   ph.t_x = t_x; ph.ldx = ldx; ph.norm_scale = norm_scale; ph.eps = eps; ph.t_out = t_out; ph.ldo = ldo;
   return ph;
 }
@@ -424,20 +437,21 @@ static void stack_phases(csm_ctx* x, StackDev& s, const int* R4, int l, int nb, 
   bf16* kc = s.kc + s.kv_layer_stride * l;
   bf16* vc = s.vc + s.kv_layer_stride * l;
   auto with_attn = [&](mega::Phase ph) {
-    ph.t_q = s.t_q; ph.t_kv = s.t_kv; ph.kc = kc; ph.vc = vc; ph.rope = s.rope; ph.heads = c.heads; ph.kv_heads = c.kv_heads;
-    ph.hd = s.hd; ph.slots = s.slots; ph.pos_mode = pos_mode; ph.pos0 = pos0;
+    ph.t_q = s.t_q; ph.t_kv = s.t_kv; ph.q_rs = s.rs_q; ph.kv_rs = s.rs_kv; ph.kc = kc; ph.vc = vc; ph.rope = s.rope; ph.heads = c.heads; ph.kv_heads = c.kv_heads;
+    ph.hd = s.hd; ph.hd_shift = s.hd == 128 ? 7 : 6; ph.slots = s.slots; ph.pos_mode = pos_mode; ph.pos0 = pos0;
     return ph;
   };
   mega::Phase q = with_attn(gemv_phase_desc(mb, s.fqkv[l], (c.heads + 2 * c.kv_heads) * s.hd, c.dim, R4[0], s.t_h, c.dim, nb,
                                             EPI_ROPE_KV, s.sa[l], eps, nullptr, 0));
   q.x_src[0] = src[0]; q.x_src[1] = src[1];
+  q.x_rs = s.rs_h;
   const int iq = (int)mb.v.size();
   mb.v.push_back(q);
   int iatt = -1;
   if (!fused_attn) {
     mega::Phase a;
     memset(&a, 0, sizeof(a));
-    a.type = mega::PH_ATTN; a.nb = nb; a.t_out = s.t_att;
+    a.type = mega::PH_ATTN; a.nb = nb; a.t_out = s.t_att; a.out_rs = s.rs_att;
     a = with_attn(a);
     a.q_src = iq;
     iatt = (int)mb.v.size();
@@ -446,6 +460,7 @@ static void stack_phases(csm_ctx* x, StackDev& s, const int* R4, int l, int nb, 
   mega::Phase o = with_attn(gemv_phase_desc(mb, s.fo[l], c.dim, c.dim, R4[1], s.t_att, c.dim, nb, EPI_RESID, nullptr, eps,
                                             s.t_h, c.dim));
   o.attn_prologue = fused_attn ? 1 : 0;
+  o.x_rs = s.rs_att; o.out_rs = s.rs_h;
   o.q_src = iq;
   o.x_src[0] = o.x_src[1] = iatt;
   o.resid_src[0] = src[0]; o.resid_src[1] = src[1];
@@ -453,10 +468,12 @@ static void stack_phases(csm_ctx* x, StackDev& s, const int* R4, int l, int nb, 
   mb.v.push_back(o);
   mega::Phase g = gemv_phase_desc(mb, s.fgu[l], 2 * c.ff, c.dim, R4[2], s.t_h, c.dim, nb, EPI_SWIGLU, s.mlp[l], eps, s.t_act, c.ff);
   g.x_src[0] = g.x_src[1] = src[0];
+  g.x_rs = s.rs_h; g.out_rs = s.rs_act;
   const int ig = (int)mb.v.size();
   mb.v.push_back(g);
   mega::Phase d = gemv_phase_desc(mb, s.fd[l], c.dim, c.ff, R4[3], s.t_act, c.ff, nb, EPI_RESID, nullptr, eps, s.t_h, c.dim);
   d.x_src[0] = d.x_src[1] = ig;
+  d.x_rs = s.rs_act; d.out_rs = s.rs_h;
   d.resid_src[0] = d.resid_src[1] = src[0];
   src[0] = src[1] = (int)mb.v.size();
   mb.v.push_back(d);
@@ -470,12 +487,12 @@ static void build_mega_phases(csm_ctx* x, MegaBuild& mb) {
     mega::Phase s;
     memset(&s, 0, sizeof(s));
     s.type = mega::PH_SAMPLE; s.cb = cb; s.V = V; s.C = C; s.D = D; s.t_logits = x->t_logits; s.logits_src = logits_src;
-    s.t_next = t_next; s.next_table = x->proj_table; s.next_ld = Dd;
+    s.t_next = t_next; s.next_rs = x->dec.rs_h; s.next_table = x->proj_table; s.next_ld = Dd;
     return s;
   };
   mega::Phase e;
   memset(&e, 0, sizeof(e));
-  e.type = mega::PH_EMBED; e.V = V; e.C = C; e.D = D; e.audio_emb = x->audio_emb; e.text_emb = x->text_emb; e.t_out = x->bb.t_h;
+  e.type = mega::PH_EMBED; e.V = V; e.C = C; e.D = D; e.audio_emb = x->audio_emb; e.text_emb = x->text_emb; e.t_out = x->bb.t_h; e.out_rs = x->bb.rs_h;
   mb.v.push_back(e);
   int src[2] = {0, 0};
   for (int l = 0; l < c.backbone.layers; ++l) stack_phases(x, x->bb, x->mega_Rbb, l, 1, mega::POS_BACKBONE, 0, false, mb, src);
@@ -485,6 +502,7 @@ static void build_mega_phases(csm_ctx* x, MegaBuild& mb) {
                                    x->t_logits, x->Vf);
   h0.x_src[0] = h0.x_src[1] = src[0];
   h0.t_out2 = x->dec.t_h; h0.split_row = x->Vf;
+  h0.x_rs = x->bb.rs_h; h0.out_rs = 0; h0.out2_rs = x->dec.rs_h;
   const int ih0 = (int)mb.v.size();
   mb.v.push_back(h0);
   const int is0 = (int)mb.v.size();
@@ -496,6 +514,7 @@ static void build_mega_phases(csm_ctx* x, MegaBuild& mb) {
     mega::Phase h = gemv_phase_desc(mb, x->f_heads + (size_t)(i - 1) * x->Vf * Dd, x->Vf, Dd, x->mega_Rh,
                                     x->dec.t_h + (size_t)(nb - 1) * Dd, Dd, 1, EPI_PLAIN, x->dec.norm, eps, x->t_logits, x->Vf);
     h.x_src[0] = h.x_src[1] = dsrc[nb - 1];
+    h.x_rs = x->dec.rs_h; h.out_rs = 0;
     const int ih = (int)mb.v.size();
     mb.v.push_back(h);
     const int is = (int)mb.v.size();
@@ -518,7 +537,7 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
   CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   CU_TRY(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   CU_TRY(cudaFuncSetAttribute(mega::k_frame_mega, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mega::SMEM_BYTES));
-  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mega::k_frame_mega, mega::NCT, mega::SMEM_BYTES));
+  CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mega::k_frame_mega, mega::NTHREADS, mega::SMEM_BYTES));
   if (!coop || occ < 1) return CSM_OK;
   // fragment-major copies of every matrix the frame touches
   const int D = c.backbone.dim, Dd = c.decoder.dim;
@@ -565,6 +584,8 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
     if (ph.K % (32 * mega::NW) != 0) return CSM_OK;
     mega::PfDesc& d = x->pf_table.d[x->pf_table.n++];
     d.W = ph.W; d.G = ph.G; d.rot = ph.rot; d.group_bytes = ph.R * ph.K * 2;
+    if (ph.tb % ph.chunk != 0 || ph.chunk % (ph.R * 64) != 0) return CSM_OK;  // slices must be whole chunks of whole blocks
+    d.chunk_nch = ph.chunk | (ph.nch << 16);
   }
   CU_TRY(cudaMemcpyAsync(x->d_phases, v.data(), v.size() * sizeof(mega::Phase), cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemsetAsync(x->d_sync, 0, sizeof(mega::Sync), st));
@@ -584,7 +605,7 @@ static int launch_mega(csm_ctx* x, const FrameParams& p, cudaStream_t st) {
   mega::Sync* sy = x->d_sync;
   unsigned long long* trc = x->trace;
   void* args[] = {(void*)&ph, (void*)&n, (void*)&dp, (void*)&sy, (void*)&trc, (void*)&x->pf_table};
-  CU_TRY(cudaLaunchCooperativeKernel((const void*)mega::k_frame_mega, dim3(x->mega_grid), dim3(mega::NCT), args,
+  CU_TRY(cudaLaunchCooperativeKernel((const void*)mega::k_frame_mega, dim3(x->mega_grid), dim3(mega::NTHREADS), args,
                                      mega::SMEM_BYTES, st));
   COUNT_LAUNCH();
   return CSM_OK;

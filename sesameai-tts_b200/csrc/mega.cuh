@@ -26,7 +26,8 @@
 namespace mega {
 
 constexpr int NW = 8;                 // warps per CTA
-constexpr int NCT = NW * 32;          // threads per CTA
+constexpr int NCT = NW * 32;          // consumer threads per CTA
+constexpr int NTHREADS = NCT + 32;    // + one producer warp that feeds the weight rings
 #ifndef MEGA_SLOTS
 #define MEGA_SLOTS 4
 #endif
@@ -35,16 +36,21 @@ constexpr int NCT = NW * 32;          // threads per CTA
 #endif
 constexpr int SLOTS = MEGA_SLOTS;            // ring slots per warp
 constexpr int SLOT_BYTES = MEGA_SLOT_BYTES;  // bytes per slot (a chunk never exceeds it)
+#ifndef MEGA_REP
+#define MEGA_REP 1  /* measured: 1, 4 and 8 copies hand off equally fast; the mechanism stays */
+#endif
+constexpr int REP = MEGA_REP;         // copies of every broadcast activation vector (spreads the readers over L2 slices)
 constexpr int MAXNB = 2;              // activation rows per phase (depth step 1 carries 2)
 constexpr int XBUF_ELEMS = 2 * MAXNB * 8192;  // 64 KB: activation rows, or the fused attention's q / K / V staging
-constexpr int CBAR = 0;               // all threads take part in CTA barriers
+constexpr int CBAR = 1;               // consumer warps synchronise on named barrier 1 (the producer warp never joins)
 constexpr int MAX_GEMV = 640;         // rows of the prefetch table (kernel parameter space)
 constexpr int MAX_LOCAL_GROUPS = 8;   // row groups one CTA owns in one phase
 constexpr size_t SMEM_RING = (size_t)NW * SLOTS * SLOT_BYTES;
 constexpr size_t SMEM_X = (size_t)XBUF_ELEMS * 2;
 constexpr size_t SMEM_PSUM = (size_t)MAX_LOCAL_GROUPS * NW * 16 * MAXNB * 4;
 constexpr size_t SMEM_MISC = 2048;
-constexpr size_t SMEM_BYTES = SMEM_RING + SMEM_X + SMEM_PSUM + SMEM_MISC;
+constexpr size_t SMEM_TAB = (size_t)MAX_GEMV * 24 + 16;  // copy of the prefetch table
+constexpr size_t SMEM_BYTES = SMEM_RING + SMEM_X + SMEM_PSUM + SMEM_MISC + SMEM_TAB;
 
 enum { PH_GEMV = 0, PH_EMBED = 1, PH_ATTN = 2, PH_SAMPLE = 3 };
 enum { POS_FIXED = 0, POS_BACKBONE = 1 };
@@ -57,6 +63,9 @@ struct __align__(16) Phase {
   const bf16* W;
   int rows, K, R, G;
   int rot, gq, gr;  // gq = G / ncta, gr = G % ncta
+  int tb, chunk, nch, kchunk, nblk;  // bytes of a warp's slice of a group, bytes / count / k extent / blocks of its chunks
+  int hd_shift;  // log2(hd)
+  float inv_K;   // 1/K when K is a power of two (exact), else 0
   int ldx;
   const uint32_t* t_x;  // input rows [nb][ldx]
   int x_src[2];
@@ -83,6 +92,9 @@ struct __align__(16) Phase {
   uint32_t* t_next;        // SAMPLE: next depth-decoder input row
   const bf16* next_table;  // SAMPLE: projection(embedding) table [(codebooks-1)*V][next_ld]
   const bf16 *audio_emb, *text_emb;
+  // distance in words between the REP copies of the tagged vectors (0: single copy)
+  int x_rs, out_rs, out2_rs, q_rs, kv_rs, next_rs;
+  int pad_[3];
 };
 static_assert(sizeof(Phase) % 16 == 0, "Phase must be copyable in 16-byte units");
 
@@ -91,8 +103,9 @@ struct PfDesc {
   const bf16* W;
   int G, rot;
   int group_bytes;  // R * K * 2
-  int pad_;
+  int chunk_nch;    // chunk bytes | chunks per warp slice << 16
 };
+static_assert(sizeof(PfDesc) == 24, "PfDesc layout");
 struct PfTable {
   int n;
   int pad_[3];
@@ -151,7 +164,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void die(Sync* sync, unsigned code) {
+__device__ __noinline__ void die(Sync* sync, unsigned code) {
   atomicExch(&sync->error, code);
   __threadfence_system();
   __trap();
@@ -229,71 +242,77 @@ __device__ __forceinline__ uint2 strip4(const uint4& v) {
   return make_uint2((v.x & 0xffffu) | (v.y << 16), (v.z & 0xffffu) | (v.w << 16));
 }
 __device__ __forceinline__ float tval(uint32_t w) { return __uint_as_float(w << 16); }
+// store to every copy of a broadcast vector (rs = distance between copies in words, 0 = single copy)
+__device__ __forceinline__ void rep_st1(uint32_t* p, int rs, uint32_t v) {
+#pragma unroll
+  for (int r = 0; r < REP; ++r)
+    if (r == 0 || rs) __stcg(p + (size_t)r * rs, v);
+}
+__device__ __forceinline__ void rep_st2(uint32_t* p, int rs, const uint2& v) {
+#pragma unroll
+  for (int r = 0; r < REP; ++r)
+    if (r == 0 || rs) stv2(p + (size_t)r * rs, v);
+}
+__device__ __forceinline__ void rep_st4(uint32_t* p, int rs, const uint4& v) {
+#pragma unroll
+  for (int r = 0; r < REP; ++r)
+    if (r == 0 || rs) stv4(p + (size_t)r * rs, v);
+}
+// the copy this CTA reads
+__device__ __forceinline__ const uint32_t* my_copy(const uint32_t* p, int rs) { return p + (size_t)(blockIdx.x % REP) * rs; }
 
-// ---- per-warp weight prefetcher -----------------------------------------------------------------------
-// A phase's row group g belongs to CTA (g + rot) % ncta; all NW warps of that CTA split its K extent:
-// warp w owns the contiguous slice [w/NW, (w+1)/NW) of the group's fragment-major bytes, cut into
-// chunks of <= SLOT_BYTES.  The warp's stream is: phases in order, its CTA's groups in order, chunks
-// in order -- exactly the order in which gemv_phase consumes them.
-struct Prefetch {
-  int gi;  // index into the GEMV table
-  int j;   // local group index inside the phase
-  int c;   // chunk index inside the task
-  unsigned issued;
-  bool done;
-  uint64_t policy;
-};
-
+// ---- weight stream: one producer warp per CTA -------------------------------------------------------
+// A phase's row group g belongs to CTA (g + rot) % ncta; all NW consumer warps of that CTA split its
+// K extent: warp w owns the contiguous slice [w/NW, (w+1)/NW) of the group's fragment-major bytes, cut
+// into chunks of <= SLOT_BYTES.  Every consumer warp has a private ring of SLOTS slots with a full
+// (complete_tx) and an empty (consumer lane 0 arrives) mbarrier per slot.  The producer warp walks
+// the frame's schedule -- phases in order, the CTA's groups in order, chunks in order, exactly the
+// order in which gemv_groups consumes -- and lane w issues warp w's chunk as soon as the slot it goes
+// to has been drained.  Consumers never compute addresses or touch the schedule: their inner loop is
+// wait(full) -> LDS + HMMA -> arrive(empty).
 __device__ __forceinline__ int local_cta(int cta, int ncta, int rot) {
   const int cl = cta - rot;
   return cl < 0 ? cl + ncta : cl;
 }
-
-__device__ __forceinline__ void pf_seek(Prefetch& pf, const PfTable& tab, int cta, int ncta) {
-  while (pf.gi < tab.n && local_cta(cta, ncta, tab.d[pf.gi].rot) + ncta * pf.j >= tab.d[pf.gi].G) {
-    ++pf.gi;
-    pf.j = 0;
-    pf.c = 0;
-  }
-  pf.done = pf.gi >= tab.n;
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// issue the next chunk of this warp's stream into ring slot (issued % SLOTS); whole warp calls it
-__device__ __forceinline__ void pf_issue(Prefetch& pf, const PfTable& tab, unsigned char* ring, uint64_t* full, int cta,
-                                         int ncta, int warp, int lane) {
-  if (pf.done) return;
-  const PfDesc& d = tab.d[pf.gi];
-  const int tb = d.group_bytes / NW;
-  const int chunk = tb < SLOT_BYTES ? tb : SLOT_BYTES;
-  const int g = local_cta(cta, ncta, d.rot) + ncta * pf.j;
-  const int slot = pf.issued % SLOTS;
-  if (lane == 0) {
-    uint64_t* fb = &full[warp * SLOTS + slot];
-    const unsigned char* src =
-        reinterpret_cast<const unsigned char*>(d.W) + (size_t)g * d.group_bytes + (size_t)warp * tb + (size_t)pf.c * chunk;
-    mbar_expect_tx(fb, (uint32_t)chunk);
-    bulk_g2s(ring + (size_t)(warp * SLOTS + slot) * SLOT_BYTES, src, (uint32_t)chunk, fb, pf.policy);
-  }
-  ++pf.issued;
-  ++pf.c;
-  if (pf.c * chunk >= tb) {
-    pf.c = 0;
-    ++pf.j;
-    pf_seek(pf, tab, cta, ncta);
+__device__ __forceinline__ void producer_loop(const PfDesc* tab, int ntab, unsigned char* ring, uint64_t* full, uint64_t* empty,
+                                              Sync* sync, int lane) {
+  const int cta = blockIdx.x, ncta = gridDim.x;
+  const uint64_t policy = policy_evict_first();
+  unsigned issued = 0;
+  for (int gi = 0; gi < ntab; ++gi) {
+    const PfDesc d = tab[gi];
+    const int chunk = d.chunk_nch & 0xffff, nch = d.chunk_nch >> 16;
+    const int tb = chunk * nch;
+    for (int g = local_cta(cta, ncta, d.rot); g < d.G; g += ncta) {
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(d.W) + (size_t)g * d.group_bytes + (size_t)lane * tb;
+      for (int ch = 0; ch < nch; ++ch, ++issued) {
+        const int slot = issued % SLOTS;
+        if (lane < NW) {
+          mbar_wait(&empty[lane * SLOTS + slot], ((issued / SLOTS) & 1) ^ 1, sync, 0x100 + lane);
+          uint64_t* fb = &full[lane * SLOTS + slot];
+          mbar_expect_tx(fb, (uint32_t)chunk);
+          bulk_g2s(ring + (size_t)(lane * SLOTS + slot) * SLOT_BYTES, src + (size_t)ch * chunk, (uint32_t)chunk, fb, policy);
+        }
+      }
+    }
   }
 }
 
+#define CK(i) do { if (c.trp) c.trp[i] = clock64(); } while (0)
 // ---- consumer pieces ---------------------------------------------------------------------------------
 struct Ctx {
   const FrameParams* P;
   unsigned char* ring;
   bf16* xs;
-  uint64_t* full;
+  uint64_t *full, *empty;
   float* scratch;  // 34 floats
   float* psum;     // [MAX_LOCAL_GROUPS][NW][16][MAXNB] split-K partial sums
   int* iscratch;   // 40 ints
   Sync* sync;
-  Prefetch pf;
   unsigned cnt;  // chunks consumed by this warp so far
   unsigned long long* trp;  // trace slots of the current phase (CTA 0, thread 0) or null
   int tid, warp, lane;
@@ -320,7 +339,7 @@ __device__ __forceinline__ EpiPre epilogue_prefetch(const Phase& ph, const Ctx& 
   EpiPre e;
   e.a = e.b = 0.f;
   if (ph.epi == EPI_RESID) {
-    const uint2 w = poll2(ph.t_out + (size_t)n * ph.ldo + r0, tag_of(c.seq, ph.resid_src[n]), c.sync);
+    const uint2 w = poll2(my_copy(ph.t_out, ph.out_rs) + (size_t)n * ph.ldo + r0, tag_of(c.seq, ph.resid_src[n]), c.sync);
     e.a = tval(w.x);
     e.b = tval(w.y);
   } else if (ph.epi == EPI_ROPE_KV) {
@@ -328,7 +347,7 @@ __device__ __forceinline__ EpiPre epilogue_prefetch(const Phase& ph, const Ctx& 
     if (r0 < (ph.heads + ph.kv_heads) * hd) {
       int pos, slot;
       phase_pos(ph, c, n, pos, slot);
-      const __nv_bfloat162 cs = *reinterpret_cast<const __nv_bfloat162*>(ph.rope + ((size_t)pos * (hd / 2) + ((r0 % hd) >> 1)) * 2);
+      const __nv_bfloat162 cs = *reinterpret_cast<const __nv_bfloat162*>(ph.rope + ((size_t)pos * (hd / 2) + ((r0 & (hd - 1)) >> 1)) * 2);
       e.a = __low2float(cs);
       e.b = __high2float(cs);
     }
@@ -341,12 +360,13 @@ __device__ __forceinline__ void epilogue(const Phase& ph, const Ctx& c, int r0, 
   const float y0 = rbf(a0), y1 = rbf(a1);
   const uint32_t tag = c.tag;
   if (ph.epi == EPI_PLAIN) {
-    uint32_t* dst = (ph.t_out2 && r0 >= ph.split_row) ? ph.t_out2 + (r0 - ph.split_row) : ph.t_out + (size_t)n * ph.ldo + r0;
-    stv2(dst, make_uint2(tword(tag, y0), tword(tag, y1)));
+    const bool second = ph.t_out2 && r0 >= ph.split_row;
+    uint32_t* dst = second ? ph.t_out2 + (r0 - ph.split_row) : ph.t_out + (size_t)n * ph.ldo + r0;
+    rep_st2(dst, second ? ph.out2_rs : ph.out_rs, make_uint2(tword(tag, y0), tword(tag, y1)));
   } else if (ph.epi == EPI_RESID) {
-    stv2(ph.t_out + (size_t)n * ph.ldo + r0, make_uint2(tword(tag, y0 + pre.a), tword(tag, y1 + pre.b)));
+    rep_st2(ph.t_out + (size_t)n * ph.ldo + r0, ph.out_rs, make_uint2(tword(tag, y0 + pre.a), tword(tag, y1 + pre.b)));
   } else if (ph.epi == EPI_SWIGLU) {
-    __stcg(ph.t_out + (size_t)n * ph.ldo + (r0 >> 1), tword(tag, silu_bf(y0) * y1));
+    rep_st1(ph.t_out + (size_t)n * ph.ldo + (r0 >> 1), ph.out_rs, tword(tag, silu_bf(y0) * y1));
   } else {  // EPI_ROPE_KV
     const int hd = ph.hd, qrows = ph.heads * hd, krows = ph.kv_heads * hd;
     int pos, slot;
@@ -357,107 +377,97 @@ __device__ __forceinline__ void epilogue(const Phase& ph, const Ctx& c, int r0, 
       o1 = rbf(__fadd_rn(__fmul_rn(y1, pre.a), __fmul_rn(y0, pre.b)));
     }
     if (r0 < qrows) {
-      stv2(ph.t_q + (size_t)n * qrows + r0, make_uint2(tword(tag, o0), tword(tag, o1)));
+      rep_st2(ph.t_q + (size_t)n * qrows + r0, ph.q_rs, make_uint2(tword(tag, o0), tword(tag, o1)));
     } else {
       const bool isk = r0 < qrows + krows;
       const int rr = r0 - (isk ? qrows : qrows + krows);
-      const int kvh = rr / hd, d = rr % hd;
+      const int kvh = rr >> ph.hd_shift, d = rr & (hd - 1);
       // this step's consumers read the tagged copy; the cache keeps plain bf16 for later steps / frames
-      stv2(ph.t_kv + ((size_t)n * 2 + (isk ? 0 : 1)) * krows + rr, make_uint2(tword(tag, o0), tword(tag, o1)));
+      rep_st2(ph.t_kv + ((size_t)n * 2 + (isk ? 0 : 1)) * krows + rr, ph.kv_rs, make_uint2(tword(tag, o0), tword(tag, o1)));
       bf16* dst = (isk ? ph.kc : ph.vc) + ((size_t)kvh * ph.slots + slot) * hd + d;  // stream 0
       *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(o0, o1);
     }
   }
 }
 
-// One ring chunk ([nblk] fragment-major blocks of R rows x 32 k) times the staged activation rows.
-// A = weights (16 rows; R == 8 leaves the upper 8 rows zero), B = activations (column n = row n of x).
-// k is permuted consistently in both operands so that every lane fetches 8 consecutive k with one
-// 16-byte load: logical k {2q,2q+1 | 2q+8,2q+9} of the first / second mma <-> physical q*8 + {0,1 | 2,3} / {4,5 | 6,7}.
-template <int R>
-__device__ __forceinline__ void chunk_mma(const unsigned char* chunk, int nblk, const bf16* xk, int K, int nb, int lane,
-                                          float (&acc)[4][4]) {
-  const int g = lane >> 2, q = lane & 3;
-  const bool xl = g < nb;
-  const bf16* xp = xk + (size_t)g * K + q * 8;
-  const unsigned char* wp = chunk + lane * 16;
-  constexpr int BLK = R * 64;
-  int b = 0;
-  for (; b + 1 < nblk; b += 2) {
-    const uint4 w0 = *reinterpret_cast<const uint4*>(wp + (size_t)b * BLK);
-    const uint4 w2 = *reinterpret_cast<const uint4*>(wp + (size_t)(b + 1) * BLK);
-    uint4 w1 = make_uint4(0, 0, 0, 0), w3 = w1;
-    if (R == 16) {
-      w1 = *reinterpret_cast<const uint4*>(wp + (size_t)b * BLK + 512);
-      w3 = *reinterpret_cast<const uint4*>(wp + (size_t)(b + 1) * BLK + 512);
-    }
-    uint4 x0 = make_uint4(0, 0, 0, 0), x1 = x0;
-    if (xl) {
-      x0 = *reinterpret_cast<const uint4*>(xp + b * 32);
-      x1 = *reinterpret_cast<const uint4*>(xp + (b + 1) * 32);
-    }
-    mma16816(acc[0], w0.x, w1.x, w0.y, w1.y, x0.x, x0.y);
-    mma16816(acc[1], w0.z, w1.z, w0.w, w1.w, x0.z, x0.w);
-    mma16816(acc[2], w2.x, w3.x, w2.y, w3.y, x1.x, x1.y);
-    mma16816(acc[3], w2.z, w3.z, w2.w, w3.w, x1.z, x1.w);
-  }
-  if (b < nblk) {
-    const uint4 w0 = *reinterpret_cast<const uint4*>(wp + (size_t)b * BLK);
-    uint4 w1 = make_uint4(0, 0, 0, 0);
-    if (R == 16) w1 = *reinterpret_cast<const uint4*>(wp + (size_t)b * BLK + 512);
-    uint4 x0 = make_uint4(0, 0, 0, 0);
-    if (xl) x0 = *reinterpret_cast<const uint4*>(xp + b * 32);
-    mma16816(acc[0], w0.x, w1.x, w0.y, w1.y, x0.x, x0.y);
-    mma16816(acc[1], w0.z, w1.z, w0.w, w1.w, x0.z, x0.w);
-  }
-}
-
-// The CTA's row groups of this phase.  Warp w streams slice w of every group through its ring, the
-// partial sums meet in shared memory, and one thread per (group, row pair, activation row) adds them
-// in a fixed order and runs the fused epilogue.
-template <int R>
-__device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c, const PfTable& tab, int cl, int ngl, int j_item,
+// The CTA's row groups of this phase.  Warp w streams slice w of every group through its ring:
+// a chunk is [nblk] fragment-major blocks of R rows x 32 k.  A = weights (16 rows; R == 8 leaves the
+// upper 8 rows zero), B = activations (column n = row n of x).  k is permuted consistently in both
+// operands so that every lane fetches 8 consecutive k with one 16-byte load: logical k
+// {2q,2q+1 | 2q+8,2q+9} of the first / second mma <-> physical q*8 + {0,1 | 2,3} / {4,5 | 6,7}.
+// The partial sums of the 8 warps meet in shared memory, and one thread per (group, row pair,
+// activation row) adds them in a fixed order and runs the fused epilogue.
+// ONE copy of this code serves every GEMV phase (R is a run-time value): the ~640 phases of a frame
+// must stay inside the 32 KB instruction cache, a miss is an L2 round trip in the dependency chain.
+__device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c, int cl, int ngl, int j_item,
                                             int pair, int n_item, bool item_on, const EpiPre& pre) {
-  const int cta = blockIdx.x, ncta = gridDim.x;
-  const int K = ph.K;
-  const int tb = R * K * 2 / NW;  // bytes of a warp's slice
-  const int chunk = tb < SLOT_BYTES ? tb : SLOT_BYTES;
-  const int nch = tb / chunk;
-  const int kchunk = chunk / (R * 2);  // k extent of a chunk
-  const int nblk = chunk / (R * 64);
+  const int ncta = gridDim.x;
+  const int K = ph.K, R = ph.R;
+  const bool r16 = R == 16;
+  const int nch = ph.nch, kchunk = ph.kchunk, nblk = ph.nblk;
+  const int blk = R * 64;
   const int g = c.lane >> 2, q = c.lane & 3;
-  for (int j = 0; j < ngl; ++j) {
-    float acc[4][4];
+  const bool xl = g < ph.nb;
+  const bf16* xw = c.xs + c.warp * (K / NW) + (size_t)g * K + q * 8;
+  const int ntask = ngl * nch;
+  float acc[4][4];
+  int j = 0, ch = 0;
+  for (int t = 0; t < ntask; ++t) {
+    if (ch == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
-    for (int ch = 0; ch < nch; ++ch) {
-      const int slot = c.cnt % SLOTS;
-      mbar_wait(&c.full[c.warp * SLOTS + slot], (c.cnt / SLOTS) & 1, c.sync, 0x200 + c.warp);
-      chunk_mma<R>(c.ring + (size_t)(c.warp * SLOTS + slot) * SLOT_BYTES, nblk, c.xs + c.warp * (K / NW) + ch * kchunk, K,
-                   ph.nb, c.lane, acc);
-      __syncwarp();
-      ++c.cnt;
-      // the slot is drained: refill it with the chunk SLOTS ahead in this warp's stream
-      pf_issue(c.pf, tab, c.ring, c.full, cta, ncta, c.warp, c.lane);
+        for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
     }
-    if (q == 0) {
-      // accumulator rows: lane group g holds A rows g and g+8 <-> group rows 2g, 2g+1 (R == 16) or g (R == 8)
-      float* ps = c.psum + ((size_t)(j * NW + c.warp) * 16) * MAXNB;
-      const float s0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
-      const float s1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
-      if (R == 16) {
-        const float s2 = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]);
-        const float s3 = (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]);
-        *reinterpret_cast<float4*>(ps + (2 * g) * MAXNB) = make_float4(s0, s1, s2, s3);
-      } else {
-        *reinterpret_cast<float2*>(ps + g * MAXNB) = make_float2(s0, s1);
+    const int slot = c.cnt % SLOTS;
+    if (t == 0) CK(9);
+    mbar_wait(&c.full[c.warp * SLOTS + slot], (c.cnt / SLOTS) & 1, c.sync, 0x200 + c.warp);
+    if (t == 0) CK(10);
+    {
+      const unsigned char* wp = c.ring + (size_t)(c.warp * SLOTS + slot) * SLOT_BYTES + c.lane * 16;
+      const bf16* xp = xw + ch * kchunk;
+      const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+      for (int b = 0; b < nblk; b += 2) {
+        const bool two = b + 1 < nblk;
+        const uint4 w0 = *reinterpret_cast<const uint4*>(wp + (size_t)b * blk);
+        const uint4 w2 = two ? *reinterpret_cast<const uint4*>(wp + (size_t)(b + 1) * blk) : z;
+        const uint4 w1 = r16 ? *reinterpret_cast<const uint4*>(wp + (size_t)b * blk + 512) : z;
+        const uint4 w3 = (r16 && two) ? *reinterpret_cast<const uint4*>(wp + (size_t)(b + 1) * blk + 512) : z;
+        const uint4 x0 = xl ? *reinterpret_cast<const uint4*>(xp + b * 32) : z;
+        const uint4 x1 = (xl && two) ? *reinterpret_cast<const uint4*>(xp + (b + 1) * 32) : z;
+        mma16816(acc[0], w0.x, w1.x, w0.y, w1.y, x0.x, x0.y);
+        mma16816(acc[1], w0.z, w1.z, w0.w, w1.w, x0.z, x0.w);
+        mma16816(acc[2], w2.x, w3.x, w2.y, w3.y, x1.x, x1.y);
+        mma16816(acc[3], w2.z, w3.z, w2.w, w3.w, x1.z, x1.w);
       }
     }
+    __syncwarp();
+    if (c.lane == 0) mbar_arrive(&c.empty[c.warp * SLOTS + slot]);  // the slot is drained: the producer may refill it
+    if (t == 0) CK(11);
+    ++c.cnt;
+    if (++ch == nch) {
+      if (q == 0) {
+        // accumulator rows: lane group g holds A rows g and g+8 <-> group rows 2g, 2g+1 (R == 16) or g (R == 8)
+        float* ps = c.psum + ((size_t)(j * NW + c.warp) * 16) * MAXNB;
+        const float s0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+        const float s1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+        if (r16) {
+          const float s2 = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]);
+          const float s3 = (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]);
+          *reinterpret_cast<float4*>(ps + (2 * g) * MAXNB) = make_float4(s0, s1, s2, s3);
+        } else {
+          *reinterpret_cast<float2*>(ps + g * MAXNB) = make_float2(s0, s1);
+        }
+      }
+      ch = 0;
+      ++j;
+    }
   }
+  CK(12);
   csync<NCT, CBAR>();
   if (c.trp) c.trp[2] = gtimer();
+  CK(13);
   if (item_on) {
     const float* ps = c.psum + ((size_t)(j_item * NW) * 16 + 2 * pair) * MAXNB + n_item;
     float y0 = 0.f, y1 = 0.f;
@@ -468,6 +478,7 @@ __device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c, const PfTab
     }
     epilogue(ph, c, (cl + ncta * j_item) * R + 2 * pair, n_item, y0, y1, pre);
   }
+  CK(14);
 }
 
 // Attention over <= 32 cached keys for every (row, head), redundantly in every CTA, straight into
@@ -506,24 +517,33 @@ __device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
     const uint32_t tag = tag_of(c.seq, ph.q_src);
     const int krows = kvn * A_HD;
     const int qunits = nb * heads * (A_HD / 4), kunits = nb * 2 * krows / 4, total = qunits + kunits;
+    const uint32_t* tq = my_copy(ph.t_q, ph.q_rs);
+    const uint32_t* tkv = my_copy(ph.t_kv, ph.kv_rs);
+    // one lane per warp watches the warp's first unit; everybody loads once it is fresh
+    if (c.lane == 0 && c.warp * 32 < total) {
+      const int u = c.warp * 32;
+      const uint32_t* p = u < qunits ? tq + u * 4 : tkv + (u - qunits) * 4;
+      poll4(p, tag, ldv4(p), c.sync);
+    }
+    __syncwarp();
     for (int u0 = 0; u0 < total; u0 += 4 * NCT) {
       uint4 v[4];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const int u = u0 + t * NCT + c.tid;
-        if (u < total) v[t] = ldv4(u < qunits ? ph.t_q + u * 4 : ph.t_kv + (u - qunits) * 4);
+        if (u < total) v[t] = ldv4(u < qunits ? tq + u * 4 : tkv + (u - qunits) * 4);
       }
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const int u = u0 + t * NCT + c.tid;
         if (u < total) {
           if (u < qunits) {
-            v[t] = poll4(ph.t_q + u * 4, tag, v[t], c.sync);
+            v[t] = poll4(tq + u * 4, tag, v[t], c.sync);
             *reinterpret_cast<uint2*>(c.xs + A_QOFF + u * 4) = strip4(v[t]);
           } else {
             const int e = (u - qunits) * 4;  // element in [nb][2][krows]
-            v[t] = poll4(ph.t_kv + e, tag, v[t], c.sync);
-            const int n = e / (2 * krows), r = e - n * 2 * krows;
+            v[t] = poll4(tkv + e, tag, v[t], c.sync);
+            const int n = e >= 2 * krows ? 1 : 0, r = e - n * 2 * krows;
             const bool isv = r >= krows;
             const int rr = isv ? r - krows : r, kvh = rr / A_HD, d = rr % A_HD, j = ph.pos0 + n;
             bf16* dst = isv ? c.xs + A_VOFF + (kvh * 32 + j) * A_HD + d : c.xs + A_KOFF + (kvh * 32 + j) * A_KS + d;
@@ -599,7 +619,9 @@ __device__ __forceinline__ uint2 norm4(const uint4& v, float inv, uint32_t sc01,
   return *reinterpret_cast<uint2*>(o);
 }
 
-// stage the phase's activation rows into shared memory (+ RMSNorm prologue): poll the tagged words
+// stage the phase's activation rows into shared memory (+ RMSNorm prologue): poll the tagged words.
+// Thread t owns the 4-word units t, t + NCT, ...; normed phases (K <= 2048, so <= 4 units per
+// thread) keep them in registers across the sum-of-squares reduction.
 __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
   if (ph.attn_prologue) {
     attn_small_into_x(ph, c);
@@ -607,34 +629,48 @@ __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
   }
   const int K = ph.K, nb = ph.nb;
   const uint32_t tag0 = tag_of(c.seq, ph.x_src[0]), tag1 = tag_of(c.seq, ph.x_src[1]);
-  if (ph.norm) {
-    // K <= 2048 for every normed phase: one 8-element unit per thread
-    const int k8 = c.tid;
-    const bool on = k8 < K / 8;
-    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0, b0 = a0, b1 = a0, sc = a0;
-    if (on) {
-      const uint32_t* p0 = ph.t_x + k8 * 8;
-      a0 = ldv4(p0);
-      a1 = ldv4(p0 + 4);
-      if (nb == 2) {
-        b0 = ldv4(p0 + ph.ldx);
-        b1 = ldv4(p0 + ph.ldx + 4);
-      }
-      sc = *reinterpret_cast<const uint4*>(ph.norm_scale + k8 * 8);
-      a0 = poll4(p0, tag0, a0, c.sync);
-      a1 = poll4(p0 + 4, tag0, a1, c.sync);
-      if (nb == 2) {
-        b0 = poll4(p0 + ph.ldx, tag1, b0, c.sync);
-        b1 = poll4(p0 + ph.ldx + 4, tag1, b1, c.sync);
+  const uint32_t* tx = my_copy(ph.t_x, ph.x_rs);
+  const bool norm = ph.norm != 0;
+  const int upr = K / 4, total = nb * upr;
+  uint4 v[4];
+  uint2 sc[4];
+  float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll 1
+  for (int u0 = 0; u0 < total; u0 += 4 * NCT) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int u = u0 + t * NCT + c.tid;
+      if (u < total) {
+        const int n = u >= upr ? 1 : 0, k4 = u - n * upr;
+        v[t] = ldv4(tx + (size_t)n * ph.ldx + k4 * 4);
+        if (norm) sc[t] = *reinterpret_cast<const uint2*>(ph.norm_scale + k4 * 4);
       }
     }
-    float s0 = sumsq4(a0) + sumsq4(a1), s1 = sumsq4(b0) + sumsq4(b1);
-    s0 = warp_sum(s0);
-    s1 = warp_sum(s1);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int u = u0 + t * NCT + c.tid;
+      if (u < total) {
+        const int n = u >= upr ? 1 : 0, k4 = u - n * upr;
+        v[t] = poll4(tx + (size_t)n * ph.ldx + k4 * 4, n ? tag1 : tag0, v[t], c.sync);
+        if (norm) {
+          const float s = sumsq4(v[t]);
+          if (n) ss1 += s;
+          else ss0 += s;
+        } else {
+          *reinterpret_cast<uint2*>(c.xs + (size_t)n * K + k4 * 4) = strip4(v[t]);
+        }
+      }
+    }
+  }
+  CK(6);
+  if (norm) {
+    ss0 = warp_sum(ss0);
+    ss1 = warp_sum(ss1);
     if (c.lane == 0) {
-      c.scratch[c.warp] = s0;
-      c.scratch[NW + c.warp] = s1;
+      c.scratch[c.warp] = ss0;
+      c.scratch[NW + c.warp] = ss1;
     }
+    CK(7);
     csync<NCT, CBAR>();
     float t0 = 0.f, t1 = 0.f;
 #pragma unroll
@@ -642,44 +678,23 @@ __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
       t0 += c.scratch[w];
       t1 += c.scratch[NW + w];
     }
-    if (on) {
-      const float i0 = 1.0f / sqrtf(t0 / (float)K + ph.eps);
-      const uint2 lo = norm4(a0, i0, sc.x, sc.y), hi = norm4(a1, i0, sc.z, sc.w);
-      *reinterpret_cast<uint4*>(c.xs + k8 * 8) = make_uint4(lo.x, lo.y, hi.x, hi.y);
-      if (nb == 2) {
-        const float i1 = 1.0f / sqrtf(t1 / (float)K + ph.eps);
-        const uint2 lo1 = norm4(b0, i1, sc.x, sc.y), hi1 = norm4(b1, i1, sc.z, sc.w);
-        *reinterpret_cast<uint4*>(c.xs + K + k8 * 8) = make_uint4(lo1.x, lo1.y, hi1.x, hi1.y);
-      }
-    }
-  } else {
-    // 4-word units, 8 in flight per thread
-    const int upr = K / 4, total = nb * upr;
-    for (int u0 = 0; u0 < total; u0 += 8 * NCT) {
-      uint4 v[8];
+    const float ik = ph.inv_K;  // exact when K is a power of two
+    const float i0 = 1.0f / sqrtf((ik != 0.f ? t0 * ik : t0 / (float)K) + ph.eps);
+    const float i1 = nb == 2 ? 1.0f / sqrtf((ik != 0.f ? t1 * ik : t1 / (float)K) + ph.eps) : 0.f;
+    CK(8);
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int u = u0 + t * NCT + c.tid;
-        if (u < total) {
-          const int n = u >= upr ? 1 : 0, k4 = u - n * upr;
-          v[t] = ldv4(ph.t_x + (size_t)n * ph.ldx + k4 * 4);
-        }
-      }
-#pragma unroll
-      for (int t = 0; t < 8; ++t) {
-        const int u = u0 + t * NCT + c.tid;
-        if (u < total) {
-          const int n = u >= upr ? 1 : 0, k4 = u - n * upr;
-          v[t] = poll4(ph.t_x + (size_t)n * ph.ldx + k4 * 4, n ? tag1 : tag0, v[t], c.sync);
-          *reinterpret_cast<uint2*>(c.xs + (size_t)n * K + k4 * 4) = strip4(v[t]);
-        }
+    for (int t = 0; t < 4; ++t) {
+      const int u = t * NCT + c.tid;
+      if (u < total) {
+        const int n = u >= upr ? 1 : 0, k4 = u - n * upr;
+        *reinterpret_cast<uint2*>(c.xs + (size_t)n * K + k4 * 4) = norm4(v[t], n ? i1 : i0, sc[t].x, sc[t].y);
       }
     }
   }
   csync<NCT, CBAR>();
 }
 
-__device__ __forceinline__ void gemv_phase(const Phase& ph, Ctx& c, const PfTable& tab) {
+__device__ __forceinline__ void gemv_phase(const Phase& ph, Ctx& c) {
   const int ncta = gridDim.x;
   const int cl = local_cta(blockIdx.x, ncta, ph.rot);
   const int ngl = ph.gq + (cl < ph.gr ? 1 : 0);
@@ -694,11 +709,10 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, Ctx& c, const PfTabl
   EpiPre pre;
   pre.a = pre.b = 0.f;
   if (item_on) pre = epilogue_prefetch(ph, c, r0, n_item);
+  CK(5);
   stage_x(ph, c);
   if (c.trp) c.trp[1] = gtimer();
-  if (R == 16) gemv_groups<16>(ph, c, tab, cl, ngl, j_item, pair, n_item, item_on, pre);
-  else gemv_groups<8>(ph, c, tab, cl, ngl, j_item, pair, n_item, item_on, pre);
-  if (ph.epi == EPI_ROPE_KV) __threadfence();  // plain cache rows: ordered before this CTA's later tagged words
+  gemv_groups(ph, c, cl, ngl, j_item, pair, n_item, item_on, pre);
 }
 
 // backbone attention: CTA h < heads owns q-head h over keys [0 .. slot]; the current position's K/V
@@ -723,8 +737,8 @@ __device__ __forceinline__ void attn_phase(const Phase& ph, Ctx& c) {
   const uint32_t tag = tag_of(c.seq, ph.q_src);
   for (int d = c.tid; d < 3 * hd; d += NCT) {
     const int which = d / hd, dd = d - which * hd;
-    const uint32_t* src = which == 0 ? ph.t_q + (size_t)h * hd + dd
-                                     : ph.t_kv + (size_t)(which - 1) * krows + (size_t)kvh * hd + dd;
+    const uint32_t* src = which == 0 ? my_copy(ph.t_q, ph.q_rs) + (size_t)h * hd + dd
+                                     : my_copy(ph.t_kv, ph.kv_rs) + (size_t)(which - 1) * krows + (size_t)kvh * hd + dd;
     qs[d] = tval(poll1(src, tag, c.sync));  // qs, kcur, vcur are contiguous
   }
   csync<NCT, CBAR>();
@@ -774,7 +788,7 @@ __device__ __forceinline__ void attn_phase(const Phase& ph, Ctx& c) {
   csync<NCT, CBAR>();
   if (g == 0) {
     for (int gg = 1; gg < G; ++gg) acc += part[gg * hd + d];
-    __stcg(ph.t_out + (size_t)h * hd + d, tword(c.tag, acc * (1.0f / sum)));
+    rep_st1(ph.t_out + (size_t)h * hd + d, ph.out_rs, tword(c.tag, acc * (1.0f / sum)));
   }
 }
 
@@ -811,9 +825,11 @@ __device__ __forceinline__ void embed_phase(const Phase& ph, Ctx& c) {
       }
   }
   const uint32_t tag = c.tag;
-  stv4(ph.t_out + u * 8, make_uint4(tword(tag, acc[0]), tword(tag, acc[1]), tword(tag, acc[2]), tword(tag, acc[3])));
-  stv4(ph.t_out + u * 8 + 4, make_uint4(tword(tag, acc[4]), tword(tag, acc[5]), tword(tag, acc[6]), tword(tag, acc[7])));
+  rep_st4(ph.t_out + u * 8, ph.out_rs, make_uint4(tword(tag, acc[0]), tword(tag, acc[1]), tword(tag, acc[2]), tword(tag, acc[3])));
+  rep_st4(ph.t_out + u * 8 + 4, ph.out_rs, make_uint4(tword(tag, acc[4]), tword(tag, acc[5]), tword(tag, acc[6]), tword(tag, acc[7])));
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
   if (blockIdx.x != 0) return;
@@ -822,6 +838,10 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
   unsigned int* hist = reinterpret_cast<unsigned int*>(xs + SAMPLE_MAXV);  // [256]
   bf16* lg = reinterpret_cast<bf16*>(hist + 256);                          // [V] logits of this step
   const int V = ph.V, C = ph.C, cb = ph.cb;
+  const bool fast = P->topk == 1 && !P->forced;  // greedy: arg-max straight from the polled registers
+  const float inv_t = 1.0f / P->temperature;
+  float best = -INFINITY;
+  int besti = 0x7fffffff, bestn = 0;
   {
     const uint32_t tag = tag_of(c.seq, ph.logits_src);
     constexpr int MAXPT = SAMPLE_MAXV / NCT;
@@ -840,17 +860,56 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
           w[t] = ldv1(ph.t_logits + i);
         }
         lg[i] = __ushort_as_bfloat16((unsigned short)(w[t] & 0xffffu));
+        const float xv = rbf(tval(w[t]) * inv_t);  // the value sample_row compares (x * (1/T) rounded to bf16)
+        if (xv > best) { best = xv; besti = i; bestn = 1; }
+        else if (xv == best) ++bestn;
       }
     }
   }
-  csync<NCT, CBAR>();
   if (c.trp) c.trp[1] = gtimer();
+  int tok = -1;
+  if (fast) {
+    // warp arg-max (first index on ties, tie count), then the 8 warp results through shared memory
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      const int on = __shfl_xor_sync(0xffffffffu, bestn, o);
+      if (ob > best) { best = ob; besti = oi; bestn = on; }
+      else if (ob == best) { bestn += on; besti = min(besti, oi); }
+    }
+    if (c.lane == 0) {
+      c.scratch[c.warp] = best;
+      c.iscratch[c.warp] = besti;
+      c.iscratch[NW + c.warp] = bestn;
+      // speculation: start pulling this warp's candidate row of the gather table towards L2
+      if (ph.t_next) {
+        const char* row = reinterpret_cast<const char*>(ph.next_table + ((size_t)besti + (size_t)cb * V) * ph.next_ld);
+        for (int o = 0; o < ph.next_ld * 2; o += 128) prefetch_l2(row + o);
+      }
+    }
+    csync<NCT, CBAR>();
+    float b = c.scratch[0];
+    int bi = c.iscratch[0], bn = c.iscratch[NW];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) {
+      const float ob = c.scratch[w];
+      const int oi = c.iscratch[w], on = c.iscratch[NW + w];
+      if (ob > b) { b = ob; bi = oi; bn = on; }
+      else if (ob == b) { bn += on; bi = min(bi, oi); }
+    }
+    // a UNIQUE maximum is the token (probability exactly 1, see sample_row); ties take the general path
+    if (bn == 1) tok = bi;
+  }
+  csync<NCT, CBAR>();  // lg[] complete; scratch reads done
   if (P->logits_out)
     for (int i = c.tid; i < V; i += NCT) P->logits_out[(size_t)cb * V + i] = lg[i];
-  const bf16* nz = P->noise ? P->noise + (size_t)cb * V : nullptr;
-  const unsigned long long ctr = ((P->offset * (unsigned long long)C + cb)) * 4096ull;
-  int tok = sample_row<NCT, CBAR, false>(lg, nz, V, P->temperature, P->topk, P->seed, ctr, xs, hist, c.scratch, c.iscratch,
-                                         c.tid);
+  if (tok < 0) {
+    const bf16* nz = P->noise ? P->noise + (size_t)cb * V : nullptr;
+    const unsigned long long ctr = ((P->offset * (unsigned long long)C + cb)) * 4096ull;
+    tok = sample_row<NCT, CBAR, false>(lg, nz, V, P->temperature, P->topk, P->seed, ctr, xs, hist, c.scratch, c.iscratch,
+                                       c.tid);
+  }
   if (c.trp) c.trp[2] = gtimer();
   if (c.tid == 0 && P->sampled_out) P->sampled_out[cb] = tok;
   if (P->forced) tok = P->forced[cb];
@@ -862,16 +921,16 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
     const uint32_t tag = c.tag;
     for (int d4 = c.tid; d4 < ld / 4; d4 += NCT) {
       const uint2 v = *reinterpret_cast<const uint2*>(row + d4 * 4);
-      stv4(ph.t_next + d4 * 4, make_uint4(tword_raw(tag, v.x), tword_raw(tag, v.x >> 16), tword_raw(tag, v.y),
-                                          tword_raw(tag, v.y >> 16)));
+      rep_st4(ph.t_next + d4 * 4, ph.next_rs, make_uint4(tword_raw(tag, v.x), tword_raw(tag, v.x >> 16), tword_raw(tag, v.y),
+                                                          tword_raw(tag, v.y >> 16)));
     }
   }
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NCT, 1)
+__global__ void __launch_bounds__(NTHREADS, 1)
 k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* __restrict__ P, Sync* sync,
-             unsigned long long* __restrict__ trace /* optional [nphases][4] globaltimer ns of CTA 0 */,
+             unsigned long long* __restrict__ trace /* optional [ncta][nphases][16]: 4 globaltimer ns + 12 clock64 marks, thread 0 of every CTA */,
              const __grid_constant__ PfTable tab) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* ring = smem;
@@ -880,52 +939,68 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
   unsigned char* misc = smem + SMEM_RING + SMEM_X + SMEM_PSUM;
   Phase* phbuf = reinterpret_cast<Phase*>(misc);                           // [2] double buffer
   uint64_t* full = reinterpret_cast<uint64_t*>(misc + 2 * sizeof(Phase));  // [NW*SLOTS]
-  float* scratch = reinterpret_cast<float*>(full + NW * SLOTS);            // [34]
+  uint64_t* empty = full + NW * SLOTS;                                     // [NW*SLOTS]
+  float* scratch = reinterpret_cast<float*>(empty + NW * SLOTS);           // [34]
   int* iscratch = reinterpret_cast<int*>(scratch + 34);                    // [40]
-  static_assert(2 * sizeof(Phase) + NW * SLOTS * 8 + 34 * 4 + 40 * 4 <= SMEM_MISC, "misc region too small");
+  static_assert(2 * sizeof(Phase) + 2 * NW * SLOTS * 8 + 34 * 4 + 40 * 4 <= SMEM_MISC, "misc region too small");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-
-  Ctx c;
-  c.P = P; c.trp = nullptr; c.ring = ring; c.xs = xs; c.full = full; c.scratch = scratch; c.iscratch = iscratch; c.psum = psum;
-  c.sync = sync; c.cnt = 0; c.tid = threadIdx.x; c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
-
+  PfDesc* stab = reinterpret_cast<PfDesc*>(misc + SMEM_MISC);  // [tab.n]: shared-memory copy of the schedule
+  {
+    const uint2* src = reinterpret_cast<const uint2*>(tab.d);
+    uint2* dst = reinterpret_cast<uint2*>(stab);
+    for (int i = threadIdx.x; i < tab.n * 3; i += NTHREADS) dst[i] = src[i];
+  }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NW * SLOTS; ++i) mbar_init(&full[i], 1);
+    for (int i = 0; i < 2 * NW * SLOTS; ++i) mbar_init(&full[i], 1);  // full[] and empty[] are contiguous
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   constexpr int PH16 = sizeof(Phase) / 16;
-  if (c.tid < PH16) reinterpret_cast<uint4*>(&phbuf[0])[c.tid] = reinterpret_cast<const uint4*>(&phases[0])[c.tid];
+  if (threadIdx.x < PH16)
+    reinterpret_cast<uint4*>(&phbuf[0])[threadIdx.x] = reinterpret_cast<const uint4*>(&phases[0])[threadIdx.x];
+  __syncthreads();
+
+  if (threadIdx.x >= NCT) {  // producer warp: feeds the eight weight rings for the whole frame, then retires
+    producer_loop(stab, tab.n, ring, full, empty, sync, threadIdx.x - NCT);
+    return;
+  }
+
+  Ctx c;
+  c.P = P; c.trp = nullptr; c.ring = ring; c.xs = xs; c.full = full; c.empty = empty; c.scratch = scratch; c.iscratch = iscratch;
+  c.psum = psum; c.sync = sync; c.cnt = 0; c.tid = threadIdx.x; c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
   c.bb_pos = (int)P->pos[P->S - 1];  // batch 1: stream 0, last prompt row
   c.bb_slot = P->cache_len + P->S - 1;
   c.seq = sync->seq;
-  __syncthreads();
 
-  // start this warp's weight stream: SLOTS chunks in flight from now on
-  c.pf.gi = 0; c.pf.j = 0; c.pf.c = 0; c.pf.issued = 0; c.pf.done = false;
-  c.pf.policy = policy_evict_first();
-  pf_seek(c.pf, tab, blockIdx.x, gridDim.x);
-  for (int s = 0; s < SLOTS; ++s) pf_issue(c.pf, tab, ring, full, blockIdx.x, gridDim.x, c.warp, c.lane);
-
-  const bool tr = trace != nullptr && blockIdx.x == 0 && c.tid == 0;
+  const bool tr = trace != nullptr && c.tid == 0;
   for (int p = 0; p < nphases; ++p) {
     const Phase& ph = phbuf[p & 1];
     c.tag = tag_of(c.seq, p);
     if (tr) {
-      c.trp = trace + p * 4;
+      c.trp = trace + ((size_t)blockIdx.x * nphases + p) * 16;
       c.trp[0] = gtimer();
       c.trp[1] = c.trp[2] = 0;
+      c.trp[4] = clock64();
     }
-    // stage the next descriptor while this phase runs (read after the CTA barrier below)
+    // stage the next descriptor while this phase runs (asynchronously: nobody waits for the load here)
     if (p + 1 < nphases && c.tid < PH16)
-      reinterpret_cast<uint4*>(&phbuf[(p + 1) & 1])[c.tid] = reinterpret_cast<const uint4*>(&phases[p + 1])[c.tid];
+      cp_async16(reinterpret_cast<uint4*>(&phbuf[(p + 1) & 1]) + c.tid, reinterpret_cast<const uint4*>(&phases[p + 1]) + c.tid);
+    asm volatile("cp.async.commit_group;" ::: "memory");
     switch (ph.type) {
-      case PH_GEMV: gemv_phase(ph, c, tab); break;
+      case PH_GEMV: gemv_phase(ph, c); break;
       case PH_EMBED: embed_phase(ph, c); break;
       case PH_ATTN: attn_phase(ph, c); break;
       default: sample_phase(ph, c); break;
     }
-    if (tr) c.trp[3] = gtimer();
+    if (tr) {
+      c.trp[3] = gtimer();
+      c.trp[15] = clock64();
+    }
+#ifndef MEGA_NO_KV_FENCE
+    // plain cache rows written by a QKV epilogue: ordered before this CTA's later tagged words
+    if (ph.type == PH_GEMV && ph.epi == EPI_ROPE_KV) __threadfence();
+#endif
+    asm volatile("cp.async.wait_all;" ::: "memory");  // the next descriptor has landed
     // end of phase inside the CTA: shared activations / partial sums may be overwritten from here on
     csync<NCT, CBAR>();
     if (p + 1 < nphases) {

@@ -10,7 +10,7 @@ import os
 from typing import Optional
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libcsm_b200.so")
+LIB_PATH = os.environ.get("CSM_B200_LIB") or os.path.join(_PKG_ROOT, "lib", "libcsm_b200.so")  # env: kernel-variant experiments
 
 MIMI_W_CODEBOOK0, MIMI_W_RVQ_FIRST_PROJ, MIMI_W_RVQ_REST_PROJ, MIMI_W_UPSAMPLE = 0, 64, 65, 66
 MIMI_W_LAYER0, MIMI_W_CONV0, MIMI_W_STAGE0, MIMI_W_FINAL, MIMI_W_COUNT = 67, 147, 149, 173, 286
