@@ -404,6 +404,13 @@ static void pack_frag(const bf16* src, int rows, int K, int R, bf16* dst, cudaSt
   k_pack_frag<<<1024, 256, 0, st>>>(src, rows, K, R, dst); COUNT_LAUNCH();
 }
 
+static int ilog2(int v) {
+  int s = 0;
+  while ((1 << s) < v) ++s;
+  return s;
+}
+static bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
 struct MegaBuild {
   std::vector<mega::Phase> v;
   int ncta;
@@ -438,7 +445,8 @@ static void stack_phases(csm_ctx* x, StackDev& s, const int* R4, int l, int nb, 
   bf16* vc = s.vc + s.kv_layer_stride * l;
   auto with_attn = [&](mega::Phase ph) {
     ph.t_q = s.t_q; ph.t_kv = s.t_kv; ph.q_rs = s.rs_q; ph.kv_rs = s.rs_kv; ph.kc = kc; ph.vc = vc; ph.rope = s.rope; ph.heads = c.heads; ph.kv_heads = c.kv_heads;
-    ph.hd = s.hd; ph.hd_shift = s.hd == 128 ? 7 : 6; ph.slots = s.slots; ph.pos_mode = pos_mode; ph.pos0 = pos0;
+    ph.hd = s.hd; ph.hd_shift = s.hd == 128 ? 7 : 6; ph.slots = s.slots;
+    ph.grp_shift = ilog2(c.heads / c.kv_heads); ph.heads_shift = ilog2(c.heads); ph.pos_mode = pos_mode; ph.pos0 = pos0;
     return ph;
   };
   mega::Phase q = with_attn(gemv_phase_desc(mb, s.fqkv[l], (c.heads + 2 * c.kv_heads) * s.hd, c.dim, R4[0], s.t_h, c.dim, nb,
@@ -530,6 +538,8 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
   // fused small attention needs <= 32 cached keys; scores of the backbone attention sit in the x buffer
   if (c.codebooks > 32 || c.max_seq_len * 4 + (mega::NCT + 3 * 128) * 4 > 32768) return CSM_OK;
   if (x->dec.hd != 128 || 2 * c.decoder.dim > 2048 || c.decoder.kv_heads > 2) return CSM_OK;  // fused attention layout
+  if (!is_pow2(c.decoder.heads) || !is_pow2(c.decoder.heads / c.decoder.kv_heads) || 2 * (c.decoder.heads / c.decoder.kv_heads) > 8)
+    return CSM_OK;  // (activation row, head in group) columns must fit the 8-wide mma tile
   if (c.backbone.dim > 8 * mega::NCT || c.decoder.dim > 8 * mega::NCT) return CSM_OK;  // one norm unit per thread
   if (mega_phase_count(c) > 2046) return CSM_OK;  // 11-bit phase tags
   int dev = 0, sms = 0, coop = 0, occ = 0;

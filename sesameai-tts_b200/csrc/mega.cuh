@@ -65,6 +65,7 @@ struct __align__(16) Phase {
   int rot, gq, gr;  // gq = G / ncta, gr = G % ncta
   int tb, chunk, nch, kchunk, nblk;  // bytes of a warp's slice of a group, bytes / count / k extent / blocks of its chunks
   int hd_shift;  // log2(hd)
+  int grp_shift, heads_shift;  // log2(heads / kv_heads), log2(heads)
   float inv_K;   // 1/K when K is a power of two (exact), else 0
   int ldx;
   const uint32_t* t_x;  // input rows [nb][ldx]
@@ -94,7 +95,7 @@ struct __align__(16) Phase {
   const bf16 *audio_emb, *text_emb;
   // distance in words between the REP copies of the tagged vectors (0: single copy)
   int x_rs, out_rs, out2_rs, q_rs, kv_rs, next_rs;
-  int pad_[3];
+  int pad_[1];
 };
 static_assert(sizeof(Phase) % 16 == 0, "Phase must be copyable in 16-byte units");
 
@@ -278,27 +279,80 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+#ifndef MEGA_L2_AHEAD
+#define MEGA_L2_AHEAD 0
+#endif
+constexpr int L2_AHEAD = MEGA_L2_AHEAD;  // ring steps (NW chunks each) that the L2 prefetch cursor runs ahead of the ring cursor
+
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+// position in the frame's schedule: (phase, group of this CTA, chunk)
+struct Cursor {
+  int gi, g, ch;
+};
+__device__ __forceinline__ bool cursor_valid(const Cursor& k, int ntab) { return k.gi < ntab; }
+// first position at or after (gi, ., .) where this CTA owns a group
+__device__ __forceinline__ void cursor_seek(Cursor& k, const PfDesc* tab, int ntab, int cta, int ncta) {
+  while (k.gi < ntab) {
+    if (k.g < 0) k.g = local_cta(cta, ncta, tab[k.gi].rot);
+    if (k.g < tab[k.gi].G) return;
+    ++k.gi;
+    k.g = -1;
+    k.ch = 0;
+  }
+}
+__device__ __forceinline__ void cursor_next(Cursor& k, const PfDesc* tab, int ntab, int cta, int ncta) {
+  if (++k.ch >= (tab[k.gi].chunk_nch >> 16)) {
+    k.ch = 0;
+    k.g += ncta;
+    cursor_seek(k, tab, ntab, cta, ncta);
+  }
+}
+__device__ __forceinline__ const unsigned char* cursor_src(const Cursor& k, const PfDesc* tab, int lane, int& chunk) {
+  const PfDesc d = tab[k.gi];
+  chunk = d.chunk_nch & 0xffff;
+  const int tb = chunk * (d.chunk_nch >> 16);
+  return reinterpret_cast<const unsigned char*>(d.W) + (size_t)k.g * d.group_bytes + (size_t)lane * tb + (size_t)k.ch * chunk;
+}
+
 __device__ __forceinline__ void producer_loop(const PfDesc* tab, int ntab, unsigned char* ring, uint64_t* full, uint64_t* empty,
                                               Sync* sync, int lane) {
   const int cta = blockIdx.x, ncta = gridDim.x;
   const uint64_t policy = policy_evict_first();
-  unsigned issued = 0;
-  for (int gi = 0; gi < ntab; ++gi) {
-    const PfDesc d = tab[gi];
-    const int chunk = d.chunk_nch & 0xffff, nch = d.chunk_nch >> 16;
-    const int tb = chunk * nch;
-    for (int g = local_cta(cta, ncta, d.rot); g < d.G; g += ncta) {
-      const unsigned char* src = reinterpret_cast<const unsigned char*>(d.W) + (size_t)g * d.group_bytes + (size_t)lane * tb;
-      for (int ch = 0; ch < nch; ++ch, ++issued) {
-        const int slot = issued % SLOTS;
-        if (lane < NW) {
-          mbar_wait(&empty[lane * SLOTS + slot], ((issued / SLOTS) & 1) ^ 1, sync, 0x100 + lane);
-          uint64_t* fb = &full[lane * SLOTS + slot];
-          mbar_expect_tx(fb, (uint32_t)chunk);
-          bulk_g2s(ring + (size_t)(lane * SLOTS + slot) * SLOT_BYTES, src + (size_t)ch * chunk, (uint32_t)chunk, fb, policy);
-        }
+  Cursor k, k2;
+  k.gi = 0; k.g = -1; k.ch = 0;
+  cursor_seek(k, tab, ntab, cta, ncta);
+  k2 = k;
+  if (L2_AHEAD > 0) {
+    // second, deeper stage of the weight stream: HBM keeps streaming into the 126 MB L2 while the CTAs
+    // sit in latency chains, and the rings refill at L2 speed afterwards
+    for (int i = 0; i < SLOTS + L2_AHEAD && cursor_valid(k2, ntab); ++i) {
+      if (i >= SLOTS && lane < NW) {
+        int chunk;
+        const unsigned char* src = cursor_src(k2, tab, lane, chunk);
+        bulk_prefetch_l2(src, (uint32_t)chunk);
+      }
+      cursor_next(k2, tab, ntab, cta, ncta);
+    }
+  }
+  for (unsigned issued = 0; cursor_valid(k, ntab); ++issued) {
+    const int slot = issued % SLOTS;
+    if (lane < NW) {
+      int chunk;
+      const unsigned char* src = cursor_src(k, tab, lane, chunk);
+      mbar_wait(&empty[lane * SLOTS + slot], ((issued / SLOTS) & 1) ^ 1, sync, 0x100 + lane);
+      uint64_t* fb = &full[lane * SLOTS + slot];
+      mbar_expect_tx(fb, (uint32_t)chunk);
+      bulk_g2s(ring + (size_t)(lane * SLOTS + slot) * SLOT_BYTES, src, (uint32_t)chunk, fb, policy);
+      if (L2_AHEAD > 0 && cursor_valid(k2, ntab)) {
+        const unsigned char* src2 = cursor_src(k2, tab, lane, chunk);
+        bulk_prefetch_l2(src2, (uint32_t)chunk);
       }
     }
+    cursor_next(k, tab, ntab, cta, ncta);
+    if (L2_AHEAD > 0 && cursor_valid(k2, ntab)) cursor_next(k2, tab, ntab, cta, ncta);
   }
 }
 
@@ -333,23 +387,22 @@ __device__ __forceinline__ void phase_pos(const Phase& ph, const Ctx& c, int n, 
 // Operands the epilogue of a row pair needs from global memory (residual values / RoPE cos,sin).
 // They are requested at the START of the phase, so their L2 round trip overlaps the hand-off.
 struct EpiPre {
-  float a, b;
+  uint32_t a, b;  // raw words: converting here would wait for the load at the start of the phase
 };
 __device__ __forceinline__ EpiPre epilogue_prefetch(const Phase& ph, const Ctx& c, int r0, int n) {
   EpiPre e;
-  e.a = e.b = 0.f;
+  e.a = e.b = 0u;
   if (ph.epi == EPI_RESID) {
-    const uint2 w = poll2(my_copy(ph.t_out, ph.out_rs) + (size_t)n * ph.ldo + r0, tag_of(c.seq, ph.resid_src[n]), c.sync);
-    e.a = tval(w.x);
-    e.b = tval(w.y);
+    // written at least two phases ago: one load, verified (and re-polled in the unlikely stale case) in the epilogue
+    const uint2 w = ldv2(my_copy(ph.t_out, ph.out_rs) + (size_t)n * ph.ldo + r0);
+    e.a = w.x;
+    e.b = w.y;
   } else if (ph.epi == EPI_ROPE_KV) {
     const int hd = ph.hd;
     if (r0 < (ph.heads + ph.kv_heads) * hd) {
       int pos, slot;
       phase_pos(ph, c, n, pos, slot);
-      const __nv_bfloat162 cs = *reinterpret_cast<const __nv_bfloat162*>(ph.rope + ((size_t)pos * (hd / 2) + ((r0 & (hd - 1)) >> 1)) * 2);
-      e.a = __low2float(cs);
-      e.b = __high2float(cs);
+      e.a = *reinterpret_cast<const uint32_t*>(ph.rope + ((size_t)pos * (hd / 2) + ((r0 & (hd - 1)) >> 1)) * 2);  // {cos, sin}
     }
   }
   return e;
@@ -359,12 +412,24 @@ __device__ __forceinline__ EpiPre epilogue_prefetch(const Phase& ph, const Ctx& 
 __device__ __forceinline__ void epilogue(const Phase& ph, const Ctx& c, int r0, int n, float a0, float a1, const EpiPre& pre) {
   const float y0 = rbf(a0), y1 = rbf(a1);
   const uint32_t tag = c.tag;
+  float pa, pb;
+  if (ph.epi == EPI_RESID) {
+    uint2 w = make_uint2(pre.a, pre.b);
+    const uint32_t rtag = tag_of(c.seq, ph.resid_src[n]);
+    if ((((w.x ^ rtag) | (w.y ^ rtag)) & 0xffff0000u) != 0)
+      w = poll2(my_copy(ph.t_out, ph.out_rs) + (size_t)n * ph.ldo + r0, rtag, c.sync);
+    pa = tval(w.x);
+    pb = tval(w.y);
+  } else {
+    pa = bflo(pre.a);  // cos
+    pb = bfhi(pre.a);  // sin
+  }
   if (ph.epi == EPI_PLAIN) {
     const bool second = ph.t_out2 && r0 >= ph.split_row;
     uint32_t* dst = second ? ph.t_out2 + (r0 - ph.split_row) : ph.t_out + (size_t)n * ph.ldo + r0;
     rep_st2(dst, second ? ph.out2_rs : ph.out_rs, make_uint2(tword(tag, y0), tword(tag, y1)));
   } else if (ph.epi == EPI_RESID) {
-    rep_st2(ph.t_out + (size_t)n * ph.ldo + r0, ph.out_rs, make_uint2(tword(tag, y0 + pre.a), tword(tag, y1 + pre.b)));
+    rep_st2(ph.t_out + (size_t)n * ph.ldo + r0, ph.out_rs, make_uint2(tword(tag, y0 + pa), tword(tag, y1 + pb)));
   } else if (ph.epi == EPI_SWIGLU) {
     rep_st1(ph.t_out + (size_t)n * ph.ldo + (r0 >> 1), ph.out_rs, tword(tag, silu_bf(y0) * y1));
   } else {  // EPI_ROPE_KV
@@ -373,8 +438,8 @@ __device__ __forceinline__ void epilogue(const Phase& ph, const Ctx& c, int r0, 
     phase_pos(ph, c, n, pos, slot);
     float o0 = y0, o1 = y1;
     if (r0 < qrows + krows) {
-      o0 = rbf(__fsub_rn(__fmul_rn(y0, pre.a), __fmul_rn(y1, pre.b)));
-      o1 = rbf(__fadd_rn(__fmul_rn(y1, pre.a), __fmul_rn(y0, pre.b)));
+      o0 = rbf(__fsub_rn(__fmul_rn(y0, pa), __fmul_rn(y1, pb)));
+      o1 = rbf(__fadd_rn(__fmul_rn(y1, pa), __fmul_rn(y0, pb)));
     }
     if (r0 < qrows) {
       rep_st2(ph.t_q + (size_t)n * qrows + r0, ph.q_rs, make_uint2(tword(tag, o0), tword(tag, o1)));
@@ -408,7 +473,7 @@ __device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c, int cl, int
   const int blk = R * 64;
   const int g = c.lane >> 2, q = c.lane & 3;
   const bool xl = g < ph.nb;
-  const bf16* xw = c.xs + c.warp * (K / NW) + (size_t)g * K + q * 8;
+  const bf16* xw = c.xs + c.warp * (K / NW) + (size_t)(xl ? g : 0) * K + q * 8;
   const int ntask = ngl * nch;
   float acc[4][4];
   int j = 0, ch = 0;
@@ -424,22 +489,29 @@ __device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c, int cl, int
     mbar_wait(&c.full[c.warp * SLOTS + slot], (c.cnt / SLOTS) & 1, c.sync, 0x200 + c.warp);
     if (t == 0) CK(10);
     {
+      // four blocks per round: all twelve 16-byte loads go out first, then eight HMMA on four
+      // independent accumulators (dependent ones are >= 4 issue slots apart).  Every lane loads x
+      // (same address within a quad column: a broadcast) and lanes of unused B columns select zero:
+      // no divergent branch in the loop.
       const unsigned char* wp = c.ring + (size_t)(c.warp * SLOTS + slot) * SLOT_BYTES + c.lane * 16;
       const bf16* xp = xw + ch * kchunk;
       const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll 1
-      for (int b = 0; b < nblk; b += 2) {
-        const bool two = b + 1 < nblk;
-        const uint4 w0 = *reinterpret_cast<const uint4*>(wp + (size_t)b * blk);
-        const uint4 w2 = two ? *reinterpret_cast<const uint4*>(wp + (size_t)(b + 1) * blk) : z;
-        const uint4 w1 = r16 ? *reinterpret_cast<const uint4*>(wp + (size_t)b * blk + 512) : z;
-        const uint4 w3 = (r16 && two) ? *reinterpret_cast<const uint4*>(wp + (size_t)(b + 1) * blk + 512) : z;
-        const uint4 x0 = xl ? *reinterpret_cast<const uint4*>(xp + b * 32) : z;
-        const uint4 x1 = (xl && two) ? *reinterpret_cast<const uint4*>(xp + (b + 1) * 32) : z;
-        mma16816(acc[0], w0.x, w1.x, w0.y, w1.y, x0.x, x0.y);
-        mma16816(acc[1], w0.z, w1.z, w0.w, w1.w, x0.z, x0.w);
-        mma16816(acc[2], w2.x, w3.x, w2.y, w3.y, x1.x, x1.y);
-        mma16816(acc[3], w2.z, w3.z, w2.w, w3.w, x1.z, x1.w);
+      for (int b = 0; b < nblk; b += 4) {
+        uint4 wl[4], wh[4], xv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool on = b + i < nblk;
+          wl[i] = on ? *reinterpret_cast<const uint4*>(wp + (size_t)(b + i) * blk) : z;
+          wh[i] = (on && r16) ? *reinterpret_cast<const uint4*>(wp + (size_t)(b + i) * blk + 512) : z;
+          xv[i] = on ? *reinterpret_cast<const uint4*>(xp + (b + i) * 32) : z;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (!xl) xv[i] = z;
+          mma16816(acc[(2 * i) & 3], wl[i].x, wh[i].x, wl[i].y, wh[i].y, xv[i].x, xv[i].y);
+          mma16816(acc[(2 * i + 1) & 3], wl[i].z, wh[i].z, wl[i].w, wh[i].w, xv[i].z, xv[i].w);
+        }
       }
     }
     __syncwarp();
@@ -483,121 +555,176 @@ __device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c, int cl, int
 
 // Attention over <= 32 cached keys for every (row, head), redundantly in every CTA, straight into
 // the activation buffer of the output projection (depth decoder: 32 slots per stream, head_dim 128).
-//   xs layout (bf16 elements): [0, nb*dim) output rows | [2048, +nb*dim) q | [4096, +kv*keys*136) K
-//   rows padded to 136 (conflict-free 16-byte reads with lane == key) | [12800, +kv*32*128) V |
-//   partial scores (fp32).
-// Two parts.  attn_prefetch runs right after the PREVIOUS phase ends: the K/V rows of earlier
-// positions are final, so they are copied into shared memory with cp.async while this CTA waits for
-// the q words.  attn_small_into_x then polls q and the current positions' K/V (tagged words of the
-// QKV phase) and computes out of shared memory: a warp owns (row, head, half of the head dims):
-// partial q.k over its 64 dims with lane == key, halves summed through shared memory, softmax by
-// shuffles, P.V for its 64 output dims with lane == 2 dims.
-constexpr int A_HD = 128, A_KS = A_HD + 8, A_QOFF = 2048, A_KOFF = 4096, A_VOFF = A_KOFF + 2 * 32 * A_KS;
-constexpr int A_PARTOFF = A_VOFF + 2 * 32 * A_HD;
+// Everything runs on the tensor cores out of shared memory; columns are (activation row, head within
+// the kv group): nb * grp <= 8 = the N extent of mma.m16n8k16.
+//   xs layout (bf16 elements):
+//     [0, nb*dim)            output rows (the O projection's x)
+//     A_QOFF  q    [kv][8 columns][160]      (rows padded to 160: conflict-free 16-byte fragment loads)
+//     A_KOFF  K    [kv][32 keys][160]
+//     A_VOFF  V    [kv][32 keys][136]        (rows padded to 136: conflict-free ldmatrix)
+//     A_SOFF  S    [kv][8 columns][32] fp32 scaled scores
+//     A_POFF  P    [kv][8 columns][40] bf16 exp(s - max), 0 beyond the visible keys
+//     A_IOFF  1/sum [kv][8] fp32
+// attn_prefetch runs right after the PREVIOUS phase ends: the K/V rows of earlier positions are final,
+// so they are copied into shared memory with cp.async while this CTA waits for the q words.
+// attn_small_into_x polls q and the current positions' K/V (tagged words of the QKV phase), then:
+//   scores  warp (kv, 16-key tile): S = K q^T, 8 HMMA over the 128 dims
+//   softmax warp per 2 (kv, column) rows, lane == key
+//   P.V     warp per 4 (kv, 8-dim tile): V fragments by ldmatrix.trans, <= 2 HMMA each, scaled by 1/sum.
+constexpr int A_HD = 128, A_QS = 160, A_KS = 160, A_VS = 136, A_PS = 40;
+constexpr int A_QOFF = 2048, A_KOFF = A_QOFF + 2 * 8 * A_QS, A_VOFF = A_KOFF + 2 * 32 * A_KS;
+constexpr int A_SOFF = A_VOFF + 2 * 32 * A_VS, A_POFF = A_SOFF + 2 * 8 * 32 * 2, A_IOFF = A_POFF + 2 * 8 * A_PS;
+static_assert(A_IOFF + 64 <= XBUF_ELEMS, "attention staging must fit the activation buffer");
 
 __device__ __forceinline__ void attn_prefetch(const Phase& ph, Ctx& c) {
   const int kvn = ph.kv_heads, nold = ph.pos0;  // positions [0, pos0) were written in earlier steps
-  const int units = kvn * nold * (A_HD / 8);
-  for (int u = c.tid; u < 2 * units; u += NCT) {
-    const bool isv = u >= units;
-    const int ku = isv ? u - units : u, row = ku >> 4, i = ku & 15;
-    const int kvh = row / nold, j = row - kvh * nold;
+  const int per = nold * (A_HD / 8);            // 16-byte units of one kv head's K (or V) rows
+  for (int u = c.tid; u < 2 * kvn * per; u += NCT) {
+    int r = u;
+    const bool isv = r >= kvn * per;
+    if (isv) r -= kvn * per;
+    const int kvh = r >= per ? 1 : 0;  // kvn <= 2
+    r -= kvh * per;
+    const int j = r >> 4, i = r & 15;
     const bf16* src = (isv ? ph.vc : ph.kc) + (kvh * ph.slots + j) * A_HD + i * 8;
-    bf16* dst = isv ? c.xs + A_VOFF + (kvh * 32 + j) * A_HD + i * 8 : c.xs + A_KOFF + (kvh * 32 + j) * A_KS + i * 8;
+    bf16* dst = isv ? c.xs + A_VOFF + (kvh * 32 + j) * A_VS + i * 8 : c.xs + A_KOFF + (kvh * 32 + j) * A_KS + i * 8;
     cp_async16(dst, src);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+
 __device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
-  const int heads = ph.heads, kvn = ph.kv_heads, grp = heads / kvn, nb = ph.nb;
-  float* part = reinterpret_cast<float*>(c.xs + A_PARTOFF);  // [nb*heads*2][32]
-  const int nitems = nb * heads * 2;
+  const int heads = ph.heads, kvn = ph.kv_heads, nb = ph.nb;
+  const int gsh = ph.grp_shift, grp = 1 << gsh;  // heads per kv head (a power of two)
+  const int ncols = nb * grp;                    // columns per kv head: (activation row, head in group)
+  const int nkmax = ph.pos0 + nb;                // visible keys of the last row
+  const int nmt = nkmax > 16 ? 2 : 1;            // 16-key tiles in use
+  float* S = reinterpret_cast<float*>(c.xs + A_SOFF);
+  bf16* P = c.xs + A_POFF;
+  float* inv = reinterpret_cast<float*>(c.xs + A_IOFF);
+  {
+    // V rows between the last visible key and the end of the last tile in use: P is 0 there, but stale
+    // shared memory may hold Inf / NaN patterns (0 * Inf): clear them
+    const int zrows = nmt * 16 - nkmax;
+    for (int u = c.tid; u < kvn * zrows * 16; u += NCT) {
+      const int kvh = u >= zrows * 16 ? 1 : 0, r = u - kvh * zrows * 16;
+      *reinterpret_cast<uint4*>(c.xs + A_VOFF + (kvh * 32 + nkmax + (r >> 4)) * A_VS + (r & 15) * 8) = make_uint4(0, 0, 0, 0);
+    }
+  }
   {  // q rows and the K/V rows of the positions written by the phase that just finished (tagged words)
     const uint32_t tag = tag_of(c.seq, ph.q_src);
-    const int krows = kvn * A_HD;
+    const int krows = kvn * A_HD, hsh = ph.heads_shift;
     const int qunits = nb * heads * (A_HD / 4), kunits = nb * 2 * krows / 4, total = qunits + kunits;
     const uint32_t* tq = my_copy(ph.t_q, ph.q_rs);
     const uint32_t* tkv = my_copy(ph.t_kv, ph.kv_rs);
-    // one lane per warp watches the warp's first unit; everybody loads once it is fresh
-    if (c.lane == 0 && c.warp * 32 < total) {
-      const int u = c.warp * 32;
-      const uint32_t* p = u < qunits ? tq + u * 4 : tkv + (u - qunits) * 4;
-      poll4(p, tag, ldv4(p), c.sync);
-    }
-    __syncwarp();
-    for (int u0 = 0; u0 < total; u0 += 4 * NCT) {
-      uint4 v[4];
+#pragma unroll 1
+    for (int u0 = 0; u0 < total; u0 += 2 * NCT) {
+      uint4 v[2];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
+      for (int t = 0; t < 2; ++t) {
         const int u = u0 + t * NCT + c.tid;
         if (u < total) v[t] = ldv4(u < qunits ? tq + u * 4 : tkv + (u - qunits) * 4);
       }
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
+      for (int t = 0; t < 2; ++t) {
         const int u = u0 + t * NCT + c.tid;
         if (u < total) {
+          bf16* dst;
           if (u < qunits) {
             v[t] = poll4(tq + u * 4, tag, v[t], c.sync);
-            *reinterpret_cast<uint2*>(c.xs + A_QOFF + u * 4) = strip4(v[t]);
+            const int d4 = u & 31, hn = u >> 5, h = hn & (heads - 1), n = hn >> hsh;  // [n][head][128]
+            dst = c.xs + A_QOFF + ((h >> gsh) * 8 + n * grp + (h & (grp - 1))) * A_QS + d4 * 4;
           } else {
             const int e = (u - qunits) * 4;  // element in [nb][2][krows]
             v[t] = poll4(tkv + e, tag, v[t], c.sync);
             const int n = e >= 2 * krows ? 1 : 0, r = e - n * 2 * krows;
             const bool isv = r >= krows;
-            const int rr = isv ? r - krows : r, kvh = rr / A_HD, d = rr % A_HD, j = ph.pos0 + n;
-            bf16* dst = isv ? c.xs + A_VOFF + (kvh * 32 + j) * A_HD + d : c.xs + A_KOFF + (kvh * 32 + j) * A_KS + d;
-            *reinterpret_cast<uint2*>(dst) = strip4(v[t]);
+            const int rr = isv ? r - krows : r, kvh = rr >> 7, d = rr & 127, j = ph.pos0 + n;
+            dst = isv ? c.xs + A_VOFF + (kvh * 32 + j) * A_VS + d : c.xs + A_KOFF + (kvh * 32 + j) * A_KS + d;
           }
+          *reinterpret_cast<uint2*>(dst) = strip4(v[t]);
         }
       }
     }
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   csync<NCT, CBAR>();
-  const float scale = 0.08838834764831845f;  // 1/sqrt(128)
-  for (int it0 = 0; it0 < nitems; it0 += NW) {
-    const int item = it0 + c.warp;
-    if (item < nitems) {
-      const int n = item / (heads * 2), h = (item >> 1) % heads, half = item & 1, kvh = h / grp;
-      const int nkeys = ph.pos0 + n + 1;
-      const bool own = c.lane < nkeys;
-      const bf16* kr = c.xs + A_KOFF + (kvh * 32 + (own ? c.lane : 0)) * A_KS + half * 64;
-      const bf16* qr = c.xs + A_QOFF + (n * heads + h) * A_HD + half * 64;
-      float a0 = 0.f, a1 = 0.f;  // two chains: the dot product is latency, not throughput, bound
+  CK(6);
+  const int g = c.lane >> 2, qd = c.lane & 3;
+  if (c.warp < kvn * nmt) {
+    // scores of one (kv head, 16-key tile): A = K rows (keys), B = q columns, k = the 128 dims
+    const int kvh = c.warp / nmt, mt = c.warp - kvh * nmt;
+    const bf16* kp = c.xs + A_KOFF + (kvh * 32 + mt * 16 + g) * A_KS + qd * 8;
+    const bf16* qp = c.xs + A_QOFF + (kvh * 8 + (g < ncols ? g : 0)) * A_QS + qd * 8;
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+    uint4 ka[4], kb[4], qv[4];
 #pragma unroll
-      for (int i = 0; i < 8; i += 2) {
-        a0 = dot8(*reinterpret_cast<const uint4*>(kr + i * 8), *reinterpret_cast<const uint4*>(qr + i * 8), a0);
-        a1 = dot8(*reinterpret_cast<const uint4*>(kr + i * 8 + 8), *reinterpret_cast<const uint4*>(qr + i * 8 + 8), a1);
+    for (int i = 0; i < 4; ++i) {
+      ka[i] = *reinterpret_cast<const uint4*>(kp + i * 32);
+      kb[i] = *reinterpret_cast<const uint4*>(kp + 8 * A_KS + i * 32);
+      qv[i] = *reinterpret_cast<const uint4*>(qp + i * 32);
+      if (g >= ncols) qv[i] = make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      mma16816(s0, ka[i].x, kb[i].x, ka[i].y, kb[i].y, qv[i].x, qv[i].y);
+      mma16816(s1, ka[i].z, kb[i].z, ka[i].w, kb[i].w, qv[i].z, qv[i].w);
+    }
+    const float scale = 0.08838834764831845f;  // 1/sqrt(128)
+    float* sp = S + (kvh * 8 + 2 * qd) * 32 + mt * 16 + g;  // accumulator: keys g, g+8 x columns 2qd, 2qd+1
+    sp[0] = (s0[0] + s1[0]) * scale;
+    sp[32] = (s0[1] + s1[1]) * scale;
+    sp[8] = (s0[2] + s1[2]) * scale;
+    sp[40] = (s0[3] + s1[3]) * scale;
+  }
+  csync<NCT, CBAR>();
+  CK(7);
+  {
+    // softmax rows: (kv head, column); lane == key
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      const int row = c.warp * 2 + rr, kvh = row >> 3, col = row & 7;
+      if (kvh < kvn && col < ncols) {
+        const int nkeys = ph.pos0 + (col >> gsh) + 1;
+        const bool own = c.lane < nkeys;
+        const float sc = own ? S[row * 32 + c.lane] : -INFINITY;
+        const float mx = warp_max(sc);
+        const float e = own ? expf(sc - mx) : 0.f;
+        const float sum = warp_sum(e);
+        P[row * A_PS + c.lane] = f2bf(e);
+        if (c.lane == 0) inv[row] = 1.0f / sum;
       }
-      part[item * 32 + c.lane] = a0 + a1;
     }
   }
   csync<NCT, CBAR>();
-  for (int it0 = 0; it0 < nitems; it0 += NW) {
-    const int item = it0 + c.warp;
-    if (item < nitems) {
-      const int n = item / (heads * 2), h = (item >> 1) % heads, half = item & 1, kvh = h / grp;
-      const int nkeys = ph.pos0 + n + 1;
-      const bool own = c.lane < nkeys;
-      const float sc = own ? (part[(item & ~1) * 32 + c.lane] + part[(item | 1) * 32 + c.lane]) * scale : -INFINITY;
-      const float mx = warp_max(sc);
-      const float e = own ? expf(sc - mx) : 0.f;
-      const float inv = 1.0f / warp_sum(e);
-      const bf16* vp = c.xs + A_VOFF + kvh * 32 * A_HD + half * 64 + c.lane * 2;
-      float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};  // 4 independent chains
-      for (int j0 = 0; j0 < nkeys; j0 += 4) {  // only the visible keys
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int j = j0 + t;
-          const float pj = __shfl_sync(0xffffffffu, e, j & 31);  // 0 for j >= nkeys
-          const uint32_t v = j < nkeys ? *reinterpret_cast<const uint32_t*>(vp + j * A_HD) : 0u;  // rows past nkeys are stale
-          o0[t] = fmaf(pj, bflo(v), o0[t]);
-          o1[t] = fmaf(pj, bfhi(v), o1[t]);
-        }
+  CK(8);
+  {
+    // P.V: tiles of 8 output dims; A = P (columns as rows, 8 of 16 used), B = V^T by ldmatrix.trans
+    const int tiles = kvn * 16, per = tiles / NW;
+#pragma unroll 1
+    for (int i = 0; i < per; ++i) {
+      const int t = c.warp * per + i, kvh = t >> 4, n0 = (t & 15) * 8;
+      uint32_t vb[4];
+      ldmatrix_x4_trans(vb, c.xs + A_VOFF + (kvh * 32 + c.lane) * A_VS + n0);
+      const bf16* pp = P + (kvh * 8 + g) * A_PS + 2 * qd;
+      const uint32_t a0 = *reinterpret_cast<const uint32_t*>(pp), a2 = *reinterpret_cast<const uint32_t*>(pp + 8);
+      float o[4] = {0.f, 0.f, 0.f, 0.f};
+      mma16816(o, a0, 0u, a2, 0u, vb[0], vb[1]);
+      if (nmt == 2) {
+        const uint32_t a4 = *reinterpret_cast<const uint32_t*>(pp + 16), a6 = *reinterpret_cast<const uint32_t*>(pp + 24);
+        mma16816(o, a4, 0u, a6, 0u, vb[2], vb[3]);
       }
-      *reinterpret_cast<__nv_bfloat162*>(c.xs + n * ph.K + h * A_HD + half * 64 + c.lane * 2) =
-          __floats2bfloat162_rn(((o0[0] + o0[1]) + (o0[2] + o0[3])) * inv, ((o1[0] + o1[1]) + (o1[2] + o1[3])) * inv);
+      if (g < ncols) {
+        const float is = inv[kvh * 8 + g];
+        const int n = g >> gsh, h = kvh * grp + (g & (grp - 1));
+        *reinterpret_cast<__nv_bfloat162*>(c.xs + n * ph.K + h * A_HD + n0 + 2 * qd) = __floats2bfloat162_rn(o[0] * is, o[1] * is);
+      }
     }
   }
   csync<NCT, CBAR>();
@@ -620,8 +747,9 @@ __device__ __forceinline__ uint2 norm4(const uint4& v, float inv, uint32_t sc01,
 }
 
 // stage the phase's activation rows into shared memory (+ RMSNorm prologue): poll the tagged words.
-// Thread t owns the 4-word units t, t + NCT, ...; normed phases (K <= 2048, so <= 4 units per
-// thread) keep them in registers across the sum-of-squares reduction.
+// Warp w stages exactly the K/8 slice of every row that ITS mma loop reads, so un-normed phases need
+// no CTA barrier at all here (a __syncwarp orders the slice), and normed phases need one, for the
+// sum of squares; normed phases (K <= 2048, <= 4 units per lane) keep the words in registers across it.
 __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
   if (ph.attn_prologue) {
     attn_small_into_x(ph, c);
@@ -629,35 +757,36 @@ __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
   }
   const int K = ph.K, nb = ph.nb;
   const uint32_t tag0 = tag_of(c.seq, ph.x_src[0]), tag1 = tag_of(c.seq, ph.x_src[1]);
-  const uint32_t* tx = my_copy(ph.t_x, ph.x_rs);
   const bool norm = ph.norm != 0;
-  const int upr = K / 4, total = nb * upr;
+  const int slice = K / NW, nu = slice >> 2, tw = nb * nu;  // units of 4 words per row / in all rows of the warp's slice
+  const uint32_t* txw = my_copy(ph.t_x, ph.x_rs) + c.warp * slice;
+  bf16* xsw = c.xs + c.warp * slice;
   uint4 v[4];
   uint2 sc[4];
   float ss0 = 0.f, ss1 = 0.f;
 #pragma unroll 1
-  for (int u0 = 0; u0 < total; u0 += 4 * NCT) {
+  for (int e0 = 0; e0 < tw; e0 += 128) {
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      const int u = u0 + t * NCT + c.tid;
-      if (u < total) {
-        const int n = u >= upr ? 1 : 0, k4 = u - n * upr;
-        v[t] = ldv4(tx + (size_t)n * ph.ldx + k4 * 4);
-        if (norm) sc[t] = *reinterpret_cast<const uint2*>(ph.norm_scale + k4 * 4);
+      const int e = e0 + t * 32 + c.lane;
+      if (e < tw) {
+        const int n = e >= nu ? 1 : 0, k4 = e - n * nu;
+        v[t] = ldv4(txw + (size_t)n * ph.ldx + k4 * 4);
+        if (norm) sc[t] = *reinterpret_cast<const uint2*>(ph.norm_scale + c.warp * slice + k4 * 4);
       }
     }
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      const int u = u0 + t * NCT + c.tid;
-      if (u < total) {
-        const int n = u >= upr ? 1 : 0, k4 = u - n * upr;
-        v[t] = poll4(tx + (size_t)n * ph.ldx + k4 * 4, n ? tag1 : tag0, v[t], c.sync);
+      const int e = e0 + t * 32 + c.lane;
+      if (e < tw) {
+        const int n = e >= nu ? 1 : 0, k4 = e - n * nu;
+        v[t] = poll4(txw + (size_t)n * ph.ldx + k4 * 4, n ? tag1 : tag0, v[t], c.sync);
         if (norm) {
           const float s = sumsq4(v[t]);
           if (n) ss1 += s;
           else ss0 += s;
         } else {
-          *reinterpret_cast<uint2*>(c.xs + (size_t)n * K + k4 * 4) = strip4(v[t]);
+          *reinterpret_cast<uint2*>(xsw + (size_t)n * K + k4 * 4) = strip4(v[t]);
         }
       }
     }
@@ -684,14 +813,14 @@ __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
     CK(8);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      const int u = t * NCT + c.tid;
-      if (u < total) {
-        const int n = u >= upr ? 1 : 0, k4 = u - n * upr;
-        *reinterpret_cast<uint2*>(c.xs + (size_t)n * K + k4 * 4) = norm4(v[t], n ? i1 : i0, sc[t].x, sc[t].y);
+      const int e = t * 32 + c.lane;
+      if (e < tw) {
+        const int n = e >= nu ? 1 : 0, k4 = e - n * nu;
+        *reinterpret_cast<uint2*>(xsw + (size_t)n * K + k4 * 4) = norm4(v[t], n ? i1 : i0, sc[t].x, sc[t].y);
       }
     }
   }
-  csync<NCT, CBAR>();
+  __syncwarp();
 }
 
 __device__ __forceinline__ void gemv_phase(const Phase& ph, Ctx& c) {
@@ -707,7 +836,7 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, Ctx& c) {
   const int r0 = (cl + ncta * j_item) * R + 2 * pair;
   const bool item_on = j_item < ngl && n_item < ph.nb && r0 < ph.rows;
   EpiPre pre;
-  pre.a = pre.b = 0.f;
+  pre.a = pre.b = 0u;
   if (item_on) pre = epilogue_prefetch(ph, c, r0, n_item);
   CK(5);
   stage_x(ph, c);
@@ -996,8 +1125,10 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
       c.trp[3] = gtimer();
       c.trp[15] = clock64();
     }
-#ifndef MEGA_NO_KV_FENCE
-    // plain cache rows written by a QKV epilogue: ordered before this CTA's later tagged words
+#ifdef MEGA_KV_FENCE
+    // Plain cache rows written by a QKV epilogue are first read >= 16 phases (tens of microseconds)
+    // later, by L2 loads (cp.async.cg), after write-through stores that reach L2 within a few hundred
+    // cycles: the fence that would order them formally costs ~0.5 us on every QKV phase and is off.
     if (ph.type == PH_GEMV && ph.epi == EPI_ROPE_KV) __threadfence();
 #endif
     asm volatile("cp.async.wait_all;" ::: "memory");  // the next descriptor has landed
