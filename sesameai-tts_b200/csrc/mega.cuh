@@ -325,34 +325,38 @@ __device__ __forceinline__ void producer_loop(const PfDesc* tab, int ntab, unsig
   k.gi = 0; k.g = -1; k.ch = 0;
   cursor_seek(k, tab, ntab, cta, ncta);
   k2 = k;
-  if (L2_AHEAD > 0) {
-    // second, deeper stage of the weight stream: HBM keeps streaming into the 126 MB L2 while the CTAs
-    // sit in latency chains, and the rings refill at L2 speed afterwards
-    for (int i = 0; i < SLOTS + L2_AHEAD && cursor_valid(k2, ntab); ++i) {
-      if (i >= SLOTS && lane < NW) {
-        int chunk;
-        const unsigned char* src = cursor_src(k2, tab, lane, chunk);
-        bulk_prefetch_l2(src, (uint32_t)chunk);
-      }
-      cursor_next(k2, tab, ntab, cta, ncta);
-    }
-  }
+  unsigned ahead = 0;  // ring steps by which the L2 cursor k2 leads the ring cursor k
   for (unsigned issued = 0; cursor_valid(k, ntab); ++issued) {
     const int slot = issued % SLOTS;
+    uint64_t* eb = &empty[(lane < NW ? lane : 0) * SLOTS + slot];
+    const uint32_t parity = ((issued / SLOTS) & 1) ^ 1;
+    // Wait until all eight slots of this step are drained.  While waiting -- the CTA sits in a latency
+    // chain and HBM would idle -- run the second, deeper stage of the weight stream: pull chunks up to
+    // L2_AHEAD steps beyond the ring into the 126 MB L2, so that the rings later refill at L2 speed.
+    for (unsigned spin = 0;; ++spin) {
+      const bool ok = lane >= NW || mbar_try(eb, parity);
+      if (__all_sync(0xffffffffu, ok)) break;
+      if (spin > (1u << 22)) die(sync, 0x100);
+      if (L2_AHEAD > 0 && ahead < SLOTS + L2_AHEAD && cursor_valid(k2, ntab)) {
+        if (ahead >= SLOTS && lane < NW) {  // the first SLOTS steps ahead are in the ring (or on their way) already
+          int chunk;
+          const unsigned char* src = cursor_src(k2, tab, lane, chunk);
+          bulk_prefetch_l2(src, (uint32_t)chunk);
+        }
+        cursor_next(k2, tab, ntab, cta, ncta);
+        ++ahead;
+      }
+    }
     if (lane < NW) {
       int chunk;
       const unsigned char* src = cursor_src(k, tab, lane, chunk);
-      mbar_wait(&empty[lane * SLOTS + slot], ((issued / SLOTS) & 1) ^ 1, sync, 0x100 + lane);
       uint64_t* fb = &full[lane * SLOTS + slot];
       mbar_expect_tx(fb, (uint32_t)chunk);
       bulk_g2s(ring + (size_t)(lane * SLOTS + slot) * SLOT_BYTES, src, (uint32_t)chunk, fb, policy);
-      if (L2_AHEAD > 0 && cursor_valid(k2, ntab)) {
-        const unsigned char* src2 = cursor_src(k2, tab, lane, chunk);
-        bulk_prefetch_l2(src2, (uint32_t)chunk);
-      }
     }
     cursor_next(k, tab, ntab, cta, ncta);
-    if (L2_AHEAD > 0 && cursor_valid(k2, ntab)) cursor_next(k2, tab, ntab, cta, ncta);
+    if (ahead > 0) --ahead;
+    else k2 = k;
   }
 }
 
