@@ -377,7 +377,8 @@ static int mega_pick_R(int rows, int ncta) {
   return m8 < m16 ? 8 : 16;
 }
 
-// Fragment-major re-pack (see mega.cuh): dst[group][k block of 32][R*64 bytes]; rows >= src_rows are zero.
+// Fragment-major re-pack (see mega.cuh): dst[group of R rows][k block of 32][R/8 sub-blocks][lane][16 B],
+// lane = 4 * (row within the 8-row sub-block) + (8-element k segment); rows >= src_rows are zero.
 __global__ void k_pack_frag(const bf16* __restrict__ src, int src_rows, int K, int R, bf16* __restrict__ dst) {
   const size_t KB = K / 32, upb = (size_t)R * 4;  // 16-byte units per block
   const size_t groups = (src_rows + R - 1) / R, total = groups * KB * upb;
@@ -385,15 +386,8 @@ __global__ void k_pack_frag(const bf16* __restrict__ src, int src_rows, int K, i
     const size_t blk = u / upb;
     const int w = (int)(u % upb);
     const size_t g = blk / KB, kb = blk % KB;
-    int row, L;
-    if (R == 16) {
-      const int h = w >> 5;
-      L = w & 31;
-      row = (int)g * 16 + 2 * (L >> 2) + h;
-    } else {
-      L = w;
-      row = (int)g * 8 + (L >> 2);
-    }
+    const int sub = w >> 5, L = w & 31;
+    const int row = (int)g * R + sub * 8 + (L >> 2);
     const size_t k = kb * 32 + (size_t)(L & 3) * 8;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (row < src_rows) v = *reinterpret_cast<const uint4*>(src + (size_t)row * K + k);

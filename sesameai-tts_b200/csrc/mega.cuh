@@ -222,6 +222,16 @@ __device__ __forceinline__ uint4 poll4(const uint32_t* p, uint32_t tag, uint4 v,
   }
   return v;
 }
+// two adjacent units at once: both re-loads are in flight together (no second round trip)
+__device__ __forceinline__ void poll8(const uint32_t* p, uint32_t tag, uint4& lo, uint4& hi, Sync* sync) {
+  for (unsigned spin = 0;; ++spin) {
+    const bool f0 = fresh4(lo, tag), f1 = fresh4(hi, tag);
+    if (f0 && f1) return;
+    if (spin > (1u << 22)) die(sync, 0x404);
+    if (!f0) lo = ldv4(p);
+    if (!f1) hi = ldv4(p + 4);
+  }
+}
 __device__ __forceinline__ uint2 poll2(const uint32_t* p, uint32_t tag, Sync* sync) {
   uint2 v = ldv2(p);
   for (unsigned spin = 0; (((v.x ^ tag) | (v.y ^ tag)) & 0xffff0000u) != 0; ++spin) {
@@ -459,62 +469,87 @@ __device__ __forceinline__ void epilogue(const Phase& ph, const Ctx& c, int r0, 
   }
 }
 
-// The CTA's row groups of this phase.  Warp w streams slice w of every group through its ring:
-// a chunk is [nblk] fragment-major blocks of R rows x 32 k.  A = weights (16 rows; R == 8 leaves the
-// upper 8 rows zero), B = activations (column n = row n of x).  k is permuted consistently in both
-// operands so that every lane fetches 8 consecutive k with one 16-byte load: logical k
-// {2q,2q+1 | 2q+8,2q+9} of the first / second mma <-> physical q*8 + {0,1 | 2,3} / {4,5 | 6,7}.
+// The CTA's row groups of this phase.  Warp w streams slice w of every group through its ring: a
+// chunk is [nblk] fragment-major blocks of R rows x 32 k, each made of R/8 sub-blocks [lane][16 B] =
+// W[8-row sub-block row lane/4][k = (lane%4)*8 .. +8].
+// Tensor-core mapping (mma.m16n8k16, D[m][n] = sum_k A[m][k] B[k][n]): B = weights (n = the 8 rows of
+// a sub-block), A = activations (m = activation row).  One 16-byte load per lane is a complete
+// operand, no register shuffling:
+//   * B: the lane's 8 consecutive k are the pairs P0..P3; HMMA "lo" takes (b0,b1) = (P0,P1), HMMA "hi"
+//     takes (P2,P3);
+//   * A: x is staged in shared memory with the pairs of every 8-group in the order (P0,P2,P1,P3), so
+//     the loaded quad (a0,a1,a2,a3) = (xP0,xP2,xP1,xP3) serves BOTH: in "lo" the rows 0-7 operands
+//     (a0,a2) = (xP0,xP1) meet (P0,P1) and accumulator rows 0-7 are right; in "hi" the rows 8-15
+//     operands (a1,a3) = (xP2,xP3) meet (P2,P3) and accumulator rows 8-15 are right.  The other halves
+//     are garbage and never read; lanes of unused activation rows load row 0 and only feed accumulator
+//     columns nobody reads.  y[act row g][sub-block row 2q+e] = lo[e] + hi[2+e] in lane (g, q).
 // The partial sums of the 8 warps meet in shared memory, and one thread per (group, row pair,
 // activation row) adds them in a fixed order and runs the fused epilogue.
 // ONE copy of this code serves every GEMV phase (R is a run-time value): the ~640 phases of a frame
-// must stay inside the 32 KB instruction cache, a miss is an L2 round trip in the dependency chain.
+// should stay inside the instruction cache, a miss is an L2 round trip in the dependency chain.
+__device__ __forceinline__ void mma_x(float (&d)[4], const uint4& x, uint32_t b0, uint32_t b1) {
+  mma16816(d, x.x, x.y, x.z, x.w, b0, b1);
+}
+
 __device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c, int cl, int ngl, int j_item,
                                             int pair, int n_item, bool item_on, const EpiPre& pre) {
   const int ncta = gridDim.x;
   const int K = ph.K, R = ph.R;
   const bool r16 = R == 16;
   const int nch = ph.nch, kchunk = ph.kchunk, nblk = ph.nblk;
-  const int blk = R * 64;
   const int g = c.lane >> 2, q = c.lane & 3;
-  const bool xl = g < ph.nb;
-  const bf16* xw = c.xs + c.warp * (K / NW) + (size_t)(xl ? g : 0) * K + q * 8;
+  const bf16* xw = c.xs + c.warp * (K / NW) + (size_t)(g < ph.nb ? g : 0) * K + q * 8;
   const int ntask = ngl * nch;
-  float acc[4][4];
+  float acc[2][2][4];  // [sub-block (R == 16) or block parity (R == 8)][lo / hi][fragment]
   int j = 0, ch = 0;
   for (int t = 0; t < ntask; ++t) {
     if (ch == 0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[i][e] = 0.f;
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[i][m][e] = 0.f;
     }
     const int slot = c.cnt % SLOTS;
     if (t == 0) CK(9);
     mbar_wait(&c.full[c.warp * SLOTS + slot], (c.cnt / SLOTS) & 1, c.sync, 0x200 + c.warp);
     if (t == 0) CK(10);
     {
-      // four blocks per round: all twelve 16-byte loads go out first, then eight HMMA on four
-      // independent accumulators (dependent ones are >= 4 issue slots apart).  Every lane loads x
-      // (same address within a quad column: a broadcast) and lanes of unused B columns select zero:
-      // no divergent branch in the loop.
       const unsigned char* wp = c.ring + (size_t)(c.warp * SLOTS + slot) * SLOT_BYTES + c.lane * 16;
       const bf16* xp = xw + ch * kchunk;
       const uint4 z = make_uint4(0, 0, 0, 0);
+      if (r16) {
 #pragma unroll 1
-      for (int b = 0; b < nblk; b += 4) {
-        uint4 wl[4], wh[4], xv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const bool on = b + i < nblk;
-          wl[i] = on ? *reinterpret_cast<const uint4*>(wp + (size_t)(b + i) * blk) : z;
-          wh[i] = (on && r16) ? *reinterpret_cast<const uint4*>(wp + (size_t)(b + i) * blk + 512) : z;
-          xv[i] = on ? *reinterpret_cast<const uint4*>(xp + (b + i) * 32) : z;
+        for (int b = 0; b < nblk; b += 2) {
+          const bool two = b + 1 < nblk;
+          const uint4 x0 = *reinterpret_cast<const uint4*>(xp + b * 32);
+          const uint4 wa = *reinterpret_cast<const uint4*>(wp + b * 1024);
+          const uint4 wb = *reinterpret_cast<const uint4*>(wp + b * 1024 + 512);
+          const uint4 x1 = two ? *reinterpret_cast<const uint4*>(xp + b * 32 + 32) : x0;
+          const uint4 wc = two ? *reinterpret_cast<const uint4*>(wp + b * 1024 + 1024) : z;
+          const uint4 wd = two ? *reinterpret_cast<const uint4*>(wp + b * 1024 + 1536) : z;
+          mma_x(acc[0][0], x0, wa.x, wa.y);
+          mma_x(acc[0][1], x0, wa.z, wa.w);
+          mma_x(acc[1][0], x0, wb.x, wb.y);
+          mma_x(acc[1][1], x0, wb.z, wb.w);
+          mma_x(acc[0][0], x1, wc.x, wc.y);
+          mma_x(acc[0][1], x1, wc.z, wc.w);
+          mma_x(acc[1][0], x1, wd.x, wd.y);
+          mma_x(acc[1][1], x1, wd.z, wd.w);
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (!xl) xv[i] = z;
-          mma16816(acc[(2 * i) & 3], wl[i].x, wh[i].x, wl[i].y, wh[i].y, xv[i].x, xv[i].y);
-          mma16816(acc[(2 * i + 1) & 3], wl[i].z, wh[i].z, wl[i].w, wh[i].w, xv[i].z, xv[i].w);
+      } else {
+#pragma unroll 1
+        for (int b = 0; b < nblk; b += 2) {
+          const bool two = b + 1 < nblk;
+          const uint4 x0 = *reinterpret_cast<const uint4*>(xp + b * 32);
+          const uint4 wa = *reinterpret_cast<const uint4*>(wp + b * 512);
+          const uint4 x1 = two ? *reinterpret_cast<const uint4*>(xp + b * 32 + 32) : x0;
+          const uint4 wc = two ? *reinterpret_cast<const uint4*>(wp + b * 512 + 512) : z;
+          mma_x(acc[0][0], x0, wa.x, wa.y);
+          mma_x(acc[0][1], x0, wa.z, wa.w);
+          mma_x(acc[1][0], x1, wc.x, wc.y);
+          mma_x(acc[1][1], x1, wc.z, wc.w);
         }
       }
     }
@@ -523,17 +558,17 @@ __device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c, int cl, int
     if (t == 0) CK(11);
     ++c.cnt;
     if (++ch == nch) {
-      if (q == 0) {
-        // accumulator rows: lane group g holds A rows g and g+8 <-> group rows 2g, 2g+1 (R == 16) or g (R == 8)
-        float* ps = c.psum + ((size_t)(j * NW + c.warp) * 16) * MAXNB;
-        const float s0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
-        const float s1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+      if (g < MAXNB) {
+        // lane (g, q): activation row g, rows 2q, 2q+1 of each 8-row sub-block
+        float* ps = c.psum + ((size_t)(j * NW + c.warp) * 16 + 2 * q) * MAXNB + g;
         if (r16) {
-          const float s2 = (acc[0][2] + acc[1][2]) + (acc[2][2] + acc[3][2]);
-          const float s3 = (acc[0][3] + acc[1][3]) + (acc[2][3] + acc[3][3]);
-          *reinterpret_cast<float4*>(ps + (2 * g) * MAXNB) = make_float4(s0, s1, s2, s3);
+          ps[0] = acc[0][0][0] + acc[0][1][2];
+          ps[MAXNB] = acc[0][0][1] + acc[0][1][3];
+          ps[8 * MAXNB] = acc[1][0][0] + acc[1][1][2];
+          ps[9 * MAXNB] = acc[1][0][1] + acc[1][1][3];
         } else {
-          *reinterpret_cast<float2*>(ps + g * MAXNB) = make_float2(s0, s1);
+          ps[0] = (acc[0][0][0] + acc[0][1][2]) + (acc[1][0][0] + acc[1][1][2]);
+          ps[MAXNB] = (acc[0][0][1] + acc[0][1][3]) + (acc[1][0][1] + acc[1][1][3]);
         }
       }
       ch = 0;
@@ -727,7 +762,8 @@ __device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
       if (g < ncols) {
         const float is = inv[kvh * 8 + g];
         const int n = g >> gsh, h = kvh * grp + (g & (grp - 1));
-        *reinterpret_cast<__nv_bfloat162*>(c.xs + n * ph.K + h * A_HD + n0 + 2 * qd) = __floats2bfloat162_rn(o[0] * is, o[1] * is);
+        const int ps = qd == 1 ? 2 : (qd == 2 ? 1 : qd);  // the O projection reads x with the pairs of an 8-group as (P0,P2,P1,P3)
+        *reinterpret_cast<__nv_bfloat162*>(c.xs + n * ph.K + h * A_HD + n0 + 2 * ps) = __floats2bfloat162_rn(o[0] * is, o[1] * is);
       }
     }
   }
@@ -754,6 +790,14 @@ __device__ __forceinline__ uint2 norm4(const uint4& v, float inv, uint32_t sc01,
 // Warp w stages exactly the K/8 slice of every row that ITS mma loop reads, so un-normed phases need
 // no CTA barrier at all here (a __syncwarp orders the slice), and normed phases need one, for the
 // sum of squares; normed phases (K <= 2048, <= 4 units per lane) keep the words in registers across it.
+// A unit is 4 elements = two pairs; the pairs of every 8-group are stored in the order (P0,P2,P1,P3)
+// the mma loop expects: unit 2i (P0,P1) -> pair slots 0 and 2, unit 2i+1 (P2,P3) -> slots 1 and 3.
+__device__ __forceinline__ void store_unit(bf16* row, int k4, const uint2& pr) {
+  uint32_t* d = reinterpret_cast<uint32_t*>(row + (k4 >> 1) * 8) + (k4 & 1);
+  d[0] = pr.x;
+  d[2] = pr.y;
+}
+
 __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
   if (ph.attn_prologue) {
     attn_small_into_x(ph, c);
@@ -765,7 +809,7 @@ __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
   const int slice = K / NW, nu = slice >> 2, tw = nb * nu;  // units of 4 words per row / in all rows of the warp's slice
   const uint32_t* txw = my_copy(ph.t_x, ph.x_rs) + c.warp * slice;
   bf16* xsw = c.xs + c.warp * slice;
-  uint4 v[4];
+  uint4 v[4];  // (measured: eight units in flight per lane spill and are slower)
   uint2 sc[4];
   float ss0 = 0.f, ss1 = 0.f;
 #pragma unroll 1
@@ -790,7 +834,7 @@ __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
           if (n) ss1 += s;
           else ss0 += s;
         } else {
-          *reinterpret_cast<uint2*>(xsw + (size_t)n * K + k4 * 4) = strip4(v[t]);
+          store_unit(xsw + (size_t)n * K, k4, strip4(v[t]));
         }
       }
     }
@@ -820,7 +864,7 @@ __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
       const int e = t * 32 + c.lane;
       if (e < tw) {
         const int n = e >= nu ? 1 : 0, k4 = e - n * nu;
-        *reinterpret_cast<uint2*>(xsw + (size_t)n * K + k4 * 4) = norm4(v[t], n ? i1 : i0, sc[t].x, sc[t].y);
+        store_unit(xsw + (size_t)n * K, k4, norm4(v[t], n ? i1 : i0, sc[t].x, sc[t].y));
       }
     }
   }
