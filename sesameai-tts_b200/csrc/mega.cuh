@@ -142,6 +142,17 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {  // non-blocking probe
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Weights are streamed with an L2 evict-first policy: they are read once per use and must not push
 // the small hot data (tagged activations, KV cache, norm scales, RoPE tables) out of the 126 MB L2.
 __device__ __forceinline__ uint64_t policy_evict_first() {
@@ -290,7 +301,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 
 #ifndef MEGA_L2_AHEAD
-#define MEGA_L2_AHEAD 0
+#define MEGA_L2_AHEAD 6  /* measured: 3.16 (off) -> 3.09 ms/frame with 6 steps, 3.12 with 12 */
 #endif
 constexpr int L2_AHEAD = MEGA_L2_AHEAD;  // ring steps (NW chunks each) that the L2 prefetch cursor runs ahead of the ring cursor
 
@@ -344,9 +355,10 @@ __device__ __forceinline__ void producer_loop(const PfDesc* tab, int ntab, unsig
     // chain and HBM would idle -- run the second, deeper stage of the weight stream: pull chunks up to
     // L2_AHEAD steps beyond the ring into the 126 MB L2, so that the rings later refill at L2 speed.
     for (unsigned spin = 0;; ++spin) {
-      const bool ok = lane >= NW || mbar_try(eb, parity);
+      // (with the L2 stage on, probe without suspending so that the prefetches really go out while waiting)
+      const bool ok = lane >= NW || (L2_AHEAD > 0 ? mbar_test(eb, parity) : mbar_try(eb, parity));
       if (__all_sync(0xffffffffu, ok)) break;
-      if (spin > (1u << 22)) die(sync, 0x100);
+      if (spin > (1u << 26)) die(sync, 0x100);
       if (L2_AHEAD > 0 && ahead < SLOTS + L2_AHEAD && cursor_valid(k2, ntab)) {
         if (ahead >= SLOTS && lane < NW) {  // the first SLOTS steps ahead are in the ring (or on their way) already
           int chunk;

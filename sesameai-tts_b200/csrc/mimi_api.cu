@@ -1,5 +1,7 @@
 // C ABI of the Mimi decode path (include/csm_b200.h, mimi_* entry points).
 #include <stdio.h>
+#include <stdlib.h>
+#include <stdint.h>
 #include <string.h>
 
 #include <new>
@@ -106,14 +108,30 @@ extern "C" size_t mimi_workspace_bytes(int32_t max_frames) {
   return mimi_carve(&tmp, nullptr);
 }
 
+// GEMM dispatch: TF32 tensor cores when K is a whole number of 32-wide tiles and rows are 16-byte
+// aligned (every Mimi shape is); precise = 3xTF32 (encode side), else single-pass TF32.
+// MIMI_GEMM env (debug): "fp32" forces the CUDA-core SGEMM, "tf32x3" forces the split everywhere.
+static int g_gemm_mode = -1;  // 0 auto, 1 fp32, 2 tf32x3
+static bool g_precise = false;
 static cudaError_t gemm(cudaStream_t st, const float* A, long long lda, const float* B, float* C, long long ldc, long long M,
                         int N, int K, const float* bias, int bias_period, int flags, const float* R = nullptr,
                         long long ldr = 0, const float* scale = nullptr) {
+  if (g_gemm_mode < 0) {
+    const char* e = getenv("MIMI_GEMM");
+    g_gemm_mode = !e ? 0 : (!strcmp(e, "fp32") ? 1 : (!strcmp(e, "tf32x3") ? 2 : 0));
+  }
   mimi::GemmArgs g;
   g.A = A; g.lda = lda; g.B = B; g.C = C; g.ldc = ldc; g.M = (int)M; g.N = N; g.K = K;
   g.bias = bias; g.bias_period = bias_period > 0 ? bias_period : 1; g.R = R; g.ldr = ldr; g.scale = scale; g.flags = flags;
-  dim3 grid((N + mimi::BN - 1) / mimi::BN, (unsigned)((M + mimi::BM - 1) / mimi::BM));
-  mimi::k_sgemm<<<grid, 256, 0, st>>>(g);
+  const bool tc_ok = g_gemm_mode != 1 && K % mimi::TBK == 0 && lda % 4 == 0 && (((uintptr_t)A | (uintptr_t)B) & 15) == 0;
+  if (tc_ok) {
+    dim3 grid((N + mimi::TBN - 1) / mimi::TBN, (unsigned)((M + mimi::TBM - 1) / mimi::TBM));
+    if (g_precise || g_gemm_mode == 2) mimi::k_tgemm<3><<<grid, 256, 0, st>>>(g);
+    else mimi::k_tgemm<1><<<grid, 256, 0, st>>>(g);
+  } else {
+    dim3 grid((N + mimi::BN - 1) / mimi::BN, (unsigned)((M + mimi::BM - 1) / mimi::BM));
+    mimi::k_sgemm<<<grid, 256, 0, st>>>(g);
+  }
   csm_count_launches(1);
   return cudaGetLastError();
 }
@@ -208,6 +226,10 @@ extern "C" int32_t mimi_encode(mimi_ctx* x, const float* wav, int32_t B, int64_t
   if (T > x->max_frames) return csm_set_error(CSM_ERR_OVERFLOW, "mimi_encode: more frames than the codec was created for");
   cudaStream_t st = (cudaStream_t)stream;
   using namespace mimi;
+  struct Precise {  // the nearest-centroid search amplifies rounding: 3xTF32 products on the encode side
+    Precise() { g_precise = true; }
+    ~Precise() { g_precise = false; }
+  } precise_scope;
   const int eratio[4] = {4, 5, 6, 8};
   for (int b = 0; b < B; ++b) {
     // waveform, zero-padded to whole frames, 8 zero samples in front (causal k = 7)

@@ -7,7 +7,8 @@
 //     and N = s*Cout: output row q holds the s upsampled time steps back to back, which IS the
 //     time-major layout of the upsampled sequence (the k-s trimmed samples are never computed);
 //   * ELU is applied when the A operand is staged, bias / GELU / LayerScale / residual in the epilogue.
-// Round 1: the GEMM is a shared-memory tiled CUDA-core SGEMM; the tcgen05 tf32 pipeline replaces it next.
+// GEMMs: k_tgemm (TF32 tensor cores, mma.sync, fp32 accumulate; 3xTF32 split on the encode side where a
+// nearest-centroid search consumes the result) with k_sgemm (CUDA cores) for shapes it does not take.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -89,6 +90,131 @@ __global__ void __launch_bounds__(256) k_sgemm(GemmArgs g) {
       g.C[(long long)m * g.ldc + n] = v;
     }
   }
+}
+
+// ---- tensor-core GEMM (TF32 mma.sync, fp32 accumulate) -------------------------------------------
+// Same contract as k_sgemm.  CTA tile 128 x 64 x 32, 8 warps as 4 (M) x 2 (N), warp tile 32 x 32 =
+// 2 x 4 mma.m16n8k8 tiles; the next k-tile is fetched into registers while the current one is
+// multiplied (one shared-memory stage, padded rows: conflict-free fragment loads).
+// PASSES == 1: operands rounded to TF32 (10-bit mantissa).  PASSES == 3: the 3xTF32 split
+// a = hi + lo, a*b ~ hi*hi + hi*lo + lo*hi: fp32-grade products at a third of the tensor rate (used
+// where a nearest-centroid search consumes the result).
+constexpr int TBM = 128, TBN = 64, TBK = 32, TPAD = 4;
+
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int PASSES>
+__global__ void __launch_bounds__(256) k_tgemm(GemmArgs g) {
+  __shared__ __align__(16) float As[TBM][TBK + TPAD];
+  __shared__ __align__(16) float Bs[TBN][TBK + TPAD];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gq = lane >> 2, q = lane & 3;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  const long long m0 = (long long)blockIdx.y * TBM;
+  const int n0 = blockIdx.x * TBN;
+  // loaders: A tile 128 x 32 floats = 1024 float4 (4 per thread), B tile 64 x 32 = 512 float4 (2 per thread)
+  const int lrow = tid >> 3, lk = (tid & 7) * 4;  // row 0..31 (+32 per step), k offset 0..28
+  float4 pa[4], pb[2];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long m = m0 + lrow + 32 * i;
+      pa[i] = m < g.M ? *reinterpret_cast<const float4*>(g.A + m * g.lda + k0 + lk) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int n = n0 + lrow + 32 * i;
+      pb[i] = n < g.N ? *reinterpret_cast<const float4*>(g.B + (long long)n * g.K + k0 + lk) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+  const bool elu = (g.flags & F_A_ELU) != 0;
+  fetch(0);
+  for (int k0 = 0; k0 < g.K; k0 += TBK) {
+    __syncthreads();  // the previous tile has been consumed
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 a = pa[i];
+      if (elu) {
+        a.x = elu1(a.x); a.y = elu1(a.y); a.z = elu1(a.z); a.w = elu1(a.w);
+      }
+      *reinterpret_cast<float4*>(&As[lrow + 32 * i][lk]) = a;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) *reinterpret_cast<float4*>(&Bs[lrow + 32 * i][lk]) = pb[i];
+    __syncthreads();
+    if (k0 + TBK < g.K) fetch(k0 + TBK);
+#pragma unroll
+    for (int kk = 0; kk < TBK; kk += 8) {
+      uint32_t ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float* ap = &As[wm + 16 * i + gq][kk + q];
+        const float v[4] = {ap[0], ap[8 * (TBK + TPAD)], ap[4], ap[8 * (TBK + TPAD) + 4]};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          ah[i][e] = f2tf32(v[e]);
+          if (PASSES == 3) al[i][e] = f2tf32(v[e] - __uint_as_float(ah[i][e]));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float* bp = &Bs[wn + 8 * j + gq][kk + q];
+        const float v[2] = {bp[0], bp[4]};
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          bh[j][e] = f2tf32(v[e]);
+          if (PASSES == 3) bl[j][e] = f2tf32(v[e] - __uint_as_float(bh[j][e]));
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (PASSES == 3) {
+            mma_tf32(acc[i][j], al[i], bh[j]);
+            mma_tf32(acc[i][j], ah[i], bl[j]);
+          }
+          mma_tf32(acc[i][j], ah[i], bh[j]);
+        }
+    }
+  }
+  // epilogue: accumulator (i, j): rows wm + 16 i + gq (+8), columns wn + 8 j + 2 q (+1)
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long m = m0 + wm + 16 * i + gq + 8 * h;
+      if (m >= g.M) continue;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int n = n0 + wn + 8 * j + 2 * q + e;
+          if (n >= g.N) continue;
+          float v = acc[i][j][2 * h + e];
+          if (g.bias) v += g.bias[n % g.bias_period];
+          if (g.flags & F_GELU) v = gelu_erf(v);
+          if (g.flags & F_LAYERSCALE) v *= g.scale[n];
+          if (g.flags & F_RESID) v += g.R[m * g.ldr + n];
+          g.C[m * g.ldc + n] = v;
+        }
+    }
 }
 
 // split-RVQ lookup: q[t] = [ sum over semantic codebooks | sum over acoustic codebooks ]  (2 x 256)

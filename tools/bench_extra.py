@@ -32,7 +32,8 @@ def ev_time(fn, reps=3, warm=1):
 
 
 # ---- prefill: S-frame voice prompt, tensor-core path vs small-row path ---------------------------
-for B in (1, 8, 32):
+ONLY = os.environ.get("BENCH_EXTRA_ONLY", "")  # "mimi": skip the language-model part
+for B in (() if ONLY == "mimi" else (1, 8, 32)):
     model = bench.build_product(dev, B)
     tok, msk, pos = syn.voice_prompt(B, 4, 64, 320, 32, seed=3, device=dev)  # 1568 frames (BASELINE config 3 prompt)
     S = tok.shape[1]
