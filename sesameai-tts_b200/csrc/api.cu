@@ -1,6 +1,7 @@
 // C ABI of libcsm_b200.so (include/csm_b200.h): context, workspace carving, weight packing,
 // the generate_frame launch sequence and its CUDA-graph capture.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -91,6 +92,7 @@ struct csm_ctx {
   bool mega_ok;
   unsigned long long* trace;  // optional device buffer [n_phases][8] (csm_debug_set_trace)
   mega::PfTable pf_table;     // weight-prefetch schedule, passed in kernel-parameter space
+  unsigned mega_keep;  // depth-decoder matrices loaded with the L2 evict-last policy: 4 bits per layer (qkv, o, gate/up, down)
   int mega_Rbb[4], mega_Rdec[4], mega_Rh0, mega_Rh;  // row-group heights (mega_pick_R): [qkv, o, gate/up, down] per stack, stacked head, audio heads
   std::map<int, cudaGraphExec_t> graphs;  // keyed by B
   std::map<int, unsigned long long> graph_nodes;
@@ -377,8 +379,10 @@ static int mega_pick_R(int rows, int ncta) {
   return m8 < m16 ? 8 : 16;
 }
 
-// Fragment-major re-pack (see mega.cuh): dst[group of R rows][k block of 32][R/8 sub-blocks][lane][16 B],
-// lane = 4 * (row within the 8-row sub-block) + (8-element k segment); rows >= src_rows are zero.
+// Fragment-major re-pack (see mega.cuh, gemv_groups); rows >= src_rows are zero.
+//   R == 8 : dst[group][k block of 32][lane][16 B] = W[8G + lane/4][32 kb + 8 (lane%4) .. +8]        (B operand)
+//   R == 16: dst[group][k block][half h][lane][16 B] = { W[16G + 2g][k0], W[16G + 2g + 1][k0], W[16G + 2g][k0 + 2],
+//            W[16G + 2g + 1][k0 + 2] } (pairs of bf16), g = lane/4, k0 = 32 kb + 8 (lane%4) + 4 h      (A operand)
 __global__ void k_pack_frag(const bf16* __restrict__ src, int src_rows, int K, int R, bf16* __restrict__ dst) {
   const size_t KB = K / 32, upb = (size_t)R * 4;  // 16-byte units per block
   const size_t groups = (src_rows + R - 1) / R, total = groups * KB * upb;
@@ -386,11 +390,21 @@ __global__ void k_pack_frag(const bf16* __restrict__ src, int src_rows, int K, i
     const size_t blk = u / upb;
     const int w = (int)(u % upb);
     const size_t g = blk / KB, kb = blk % KB;
-    const int sub = w >> 5, L = w & 31;
-    const int row = (int)g * R + sub * 8 + (L >> 2);
-    const size_t k = kb * 32 + (size_t)(L & 3) * 8;
+    const int L = w & 31;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (row < src_rows) v = *reinterpret_cast<const uint4*>(src + (size_t)row * K + k);
+    if (R == 16) {
+      const int h = w >> 5;
+      const int r0 = (int)g * 16 + 2 * (L >> 2);
+      const size_t k0 = kb * 32 + (size_t)(L & 3) * 8 + 4 * h;
+      const uint32_t* a = reinterpret_cast<const uint32_t*>(src + (size_t)r0 * K + k0);
+      const uint32_t* b = reinterpret_cast<const uint32_t*>(src + (size_t)(r0 + 1) * K + k0);
+      if (r0 < src_rows) { v.x = a[0]; v.z = a[1]; }
+      if (r0 + 1 < src_rows) { v.y = b[0]; v.w = b[1]; }
+    } else {
+      const int row = (int)g * 8 + (L >> 2);
+      const size_t k = kb * 32 + (size_t)(L & 3) * 8;
+      if (row < src_rows) v = *reinterpret_cast<const uint4*>(src + (size_t)row * K + k);
+    }
     reinterpret_cast<uint4*>(dst)[u] = v;
   }
 }
@@ -432,7 +446,7 @@ static mega::Phase gemv_phase_desc(MegaBuild& mb, const bf16* Wf, int rows, int 
 
 // src[n]: index of the phase that last wrote row n of the stack's residual stream (updated here)
 static void stack_phases(csm_ctx* x, StackDev& s, const int* R4, int l, int nb, int pos_mode, int pos0, bool fused_attn,
-                         MegaBuild& mb, int* src) {
+                         MegaBuild& mb, int* src, int keep_mask = 0 /* bit 0 qkv, 1 o, 2 gate/up, 3 down: L2 evict-last */) {
   const csm_stack_config& c = s.c;
   const float eps = x->cfg.norm_eps;
   bf16* kc = s.kc + s.kv_layer_stride * l;
@@ -447,6 +461,7 @@ static void stack_phases(csm_ctx* x, StackDev& s, const int* R4, int l, int nb, 
                                             EPI_ROPE_KV, s.sa[l], eps, nullptr, 0));
   q.x_src[0] = src[0]; q.x_src[1] = src[1];
   q.x_rs = s.rs_h;
+  q.keep = keep_mask & 1;
   const int iq = (int)mb.v.size();
   mb.v.push_back(q);
   int iatt = -1;
@@ -463,6 +478,7 @@ static void stack_phases(csm_ctx* x, StackDev& s, const int* R4, int l, int nb, 
                                             s.t_h, c.dim));
   o.attn_prologue = fused_attn ? 1 : 0;
   o.x_rs = s.rs_att; o.out_rs = s.rs_h;
+  o.keep = (keep_mask >> 1) & 1;
   o.q_src = iq;
   o.x_src[0] = o.x_src[1] = iatt;
   o.resid_src[0] = src[0]; o.resid_src[1] = src[1];
@@ -471,11 +487,13 @@ static void stack_phases(csm_ctx* x, StackDev& s, const int* R4, int l, int nb, 
   mega::Phase g = gemv_phase_desc(mb, s.fgu[l], 2 * c.ff, c.dim, R4[2], s.t_h, c.dim, nb, EPI_SWIGLU, s.mlp[l], eps, s.t_act, c.ff);
   g.x_src[0] = g.x_src[1] = src[0];
   g.x_rs = s.rs_h; g.out_rs = s.rs_act;
+  g.keep = (keep_mask >> 2) & 1;
   const int ig = (int)mb.v.size();
   mb.v.push_back(g);
   mega::Phase d = gemv_phase_desc(mb, s.fd[l], c.dim, c.ff, R4[3], s.t_act, c.ff, nb, EPI_RESID, nullptr, eps, s.t_h, c.dim);
   d.x_src[0] = d.x_src[1] = ig;
   d.x_rs = s.rs_act; d.out_rs = s.rs_h;
+  d.keep = (keep_mask >> 3) & 1;
   d.resid_src[0] = d.resid_src[1] = src[0];
   src[0] = src[1] = (int)mb.v.size();
   mb.v.push_back(d);
@@ -512,7 +530,8 @@ static void build_mega_phases(csm_ctx* x, MegaBuild& mb) {
   int dsrc[2] = {ih0, is0};
   for (int i = 1; i < C; ++i) {
     const int nb = (i == 1) ? 2 : 1, pos0 = (i == 1) ? 0 : i;
-    for (int l = 0; l < c.decoder.layers; ++l) stack_phases(x, x->dec, x->mega_Rdec, l, nb, mega::POS_FIXED, pos0, true, mb, dsrc);
+    for (int l = 0; l < c.decoder.layers; ++l)
+      stack_phases(x, x->dec, x->mega_Rdec, l, nb, mega::POS_FIXED, pos0, true, mb, dsrc, (x->mega_keep >> (4 * (l & 7))) & 15);
     mega::Phase h = gemv_phase_desc(mb, x->f_heads + (size_t)(i - 1) * x->Vf * Dd, x->Vf, Dd, x->mega_Rh,
                                     x->dec.t_h + (size_t)(nb - 1) * Dd, Dd, 1, EPI_PLAIN, x->dec.norm, eps, x->t_logits, x->Vf);
     h.x_src[0] = h.x_src[1] = dsrc[nb - 1];
@@ -574,6 +593,11 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
   CU_TRY(cudaMemsetAsync(x->tagged_base, 0, x->tagged_bytes, st));  // stale tags of an earlier context must never match
   CU_TRY(cudaGetLastError());
 
+  // Which depth-decoder matrices stay in L2 across the 31 codebook steps (see mega.cuh, producer_loop).
+  // Default: the down and O projections of every layer and QKV (75 MB of the 222 MB); CSM_MEGA_KEEP=<hex>
+  // overrides it for experiments (4 bits per layer: 1 qkv, 2 o, 4 gate/up, 8 down).
+  x->mega_keep = 0xBBBBBBBBu;
+  if (const char* e = getenv("CSM_MEGA_KEEP")) x->mega_keep = (unsigned)strtoul(e, nullptr, 16);
   MegaBuild mb;
   mb.ncta = sms;
   mb.rot = 0;
@@ -589,7 +613,7 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
     mega::PfDesc& d = x->pf_table.d[x->pf_table.n++];
     d.W = ph.W; d.G = ph.G; d.rot = ph.rot; d.group_bytes = ph.R * ph.K * 2;
     if (ph.tb % ph.chunk != 0 || ph.chunk % (ph.R * 64) != 0) return CSM_OK;  // slices must be whole chunks of whole blocks
-    d.chunk_nch = ph.chunk | (ph.nch << 16);
+    d.chunk_nch = ph.chunk | (ph.nch << 16) | (ph.keep ? (1 << 30) : 0);
   }
   CU_TRY(cudaMemcpyAsync(x->d_phases, v.data(), v.size() * sizeof(mega::Phase), cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemsetAsync(x->d_sync, 0, sizeof(mega::Sync), st));

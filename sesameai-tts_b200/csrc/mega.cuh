@@ -95,7 +95,7 @@ struct __align__(16) Phase {
   const bf16 *audio_emb, *text_emb;
   // distance in words between the REP copies of the tagged vectors (0: single copy)
   int x_rs, out_rs, out2_rs, q_rs, kv_rs, next_rs;
-  int pad_[1];
+  int keep;  // this matrix is loaded with the L2 evict-last policy
 };
 static_assert(sizeof(Phase) % 16 == 0, "Phase must be copyable in 16-byte units");
 
@@ -104,7 +104,7 @@ struct PfDesc {
   const bf16* W;
   int G, rot;
   int group_bytes;  // R * K * 2
-  int chunk_nch;    // chunk bytes | chunks per warp slice << 16
+  int chunk_nch;    // chunk bytes | chunks per warp slice << 16 | (keep in L2: evict-last) << 30
 };
 static_assert(sizeof(PfDesc) == 24, "PfDesc layout");
 struct PfTable {
@@ -305,8 +305,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 #endif
 constexpr int L2_AHEAD = MEGA_L2_AHEAD;  // ring steps (NW chunks each) that the L2 prefetch cursor runs ahead of the ring cursor
 
-__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src), "r"(bytes), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
 }
 
 // position in the frame's schedule: (phase, group of this CTA, chunk)
@@ -325,23 +330,27 @@ __device__ __forceinline__ void cursor_seek(Cursor& k, const PfDesc* tab, int nt
   }
 }
 __device__ __forceinline__ void cursor_next(Cursor& k, const PfDesc* tab, int ntab, int cta, int ncta) {
-  if (++k.ch >= (tab[k.gi].chunk_nch >> 16)) {
+  if (++k.ch >= ((tab[k.gi].chunk_nch >> 16) & 0xff)) {
     k.ch = 0;
     k.g += ncta;
     cursor_seek(k, tab, ntab, cta, ncta);
   }
 }
-__device__ __forceinline__ const unsigned char* cursor_src(const Cursor& k, const PfDesc* tab, int lane, int& chunk) {
+__device__ __forceinline__ const unsigned char* cursor_src(const Cursor& k, const PfDesc* tab, int lane, int& chunk, bool& keep) {
   const PfDesc d = tab[k.gi];
   chunk = d.chunk_nch & 0xffff;
-  const int tb = chunk * (d.chunk_nch >> 16);
+  keep = (d.chunk_nch >> 30) & 1;
+  const int tb = chunk * ((d.chunk_nch >> 16) & 0xff);
   return reinterpret_cast<const unsigned char*>(d.W) + (size_t)k.g * d.group_bytes + (size_t)lane * tb + (size_t)k.ch * chunk;
 }
 
 __device__ __forceinline__ void producer_loop(const PfDesc* tab, int ntab, unsigned char* ring, uint64_t* full, uint64_t* empty,
                                               Sync* sync, int lane) {
   const int cta = blockIdx.x, ncta = gridDim.x;
-  const uint64_t policy = policy_evict_first();
+  // Weights that are used once per frame stream through L2 evict-first.  The depth decoder's 222 MB are
+  // used 31 times per frame: the matrices marked "keep" are loaded evict-last, so that part of them
+  // survives in the 126 MB L2 from one codebook step to the next and never touches HBM again.
+  const uint64_t pol_first = policy_evict_first(), pol_last = policy_evict_last();
   Cursor k, k2;
   k.gi = 0; k.g = -1; k.ch = 0;
   cursor_seek(k, tab, ntab, cta, ncta);
@@ -362,8 +371,9 @@ __device__ __forceinline__ void producer_loop(const PfDesc* tab, int ntab, unsig
       if (L2_AHEAD > 0 && ahead < SLOTS + L2_AHEAD && cursor_valid(k2, ntab)) {
         if (ahead >= SLOTS && lane < NW) {  // the first SLOTS steps ahead are in the ring (or on their way) already
           int chunk;
-          const unsigned char* src = cursor_src(k2, tab, lane, chunk);
-          bulk_prefetch_l2(src, (uint32_t)chunk);
+          bool keep;
+          const unsigned char* src = cursor_src(k2, tab, lane, chunk, keep);
+          bulk_prefetch_l2(src, (uint32_t)chunk, keep ? pol_last : pol_first);
         }
         cursor_next(k2, tab, ntab, cta, ncta);
         ++ahead;
@@ -371,10 +381,11 @@ __device__ __forceinline__ void producer_loop(const PfDesc* tab, int ntab, unsig
     }
     if (lane < NW) {
       int chunk;
-      const unsigned char* src = cursor_src(k, tab, lane, chunk);
+      bool keep;
+      const unsigned char* src = cursor_src(k, tab, lane, chunk, keep);
       uint64_t* fb = &full[lane * SLOTS + slot];
       mbar_expect_tx(fb, (uint32_t)chunk);
-      bulk_g2s(ring + (size_t)(lane * SLOTS + slot) * SLOT_BYTES, src, (uint32_t)chunk, fb, policy);
+      bulk_g2s(ring + (size_t)(lane * SLOTS + slot) * SLOT_BYTES, src, (uint32_t)chunk, fb, keep ? pol_last : pol_first);
     }
     cursor_next(k, tab, ntab, cta, ncta);
     if (ahead > 0) --ahead;
@@ -532,23 +543,26 @@ __device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c, int cl, int
       const bf16* xp = xw + ch * kchunk;
       const uint4 z = make_uint4(0, 0, 0, 0);
       if (r16) {
+        // 16-row groups: weights are the A operand.  A block is [lo / hi half][lane][16 B]; the lane's
+        // quad is (W[2g][Pa], W[2g+1][Pa], W[2g][Pb], W[2g+1][Pb]) with (Pa,Pb) = the pairs (P0,P1) of its
+        // 8 consecutive k in the lo half and (P2,P3) in the hi half -- exactly (a0,a1,a2,a3).  x is the
+        // B operand, staged in natural order: one 16-byte load = (b0,b1) of the lo and of the hi HMMA.
+        // Four blocks per round: twelve loads go out first, then eight HMMA on four accumulators.
 #pragma unroll 1
-        for (int b = 0; b < nblk; b += 2) {
-          const bool two = b + 1 < nblk;
-          const uint4 x0 = *reinterpret_cast<const uint4*>(xp + b * 32);
-          const uint4 wa = *reinterpret_cast<const uint4*>(wp + b * 1024);
-          const uint4 wb = *reinterpret_cast<const uint4*>(wp + b * 1024 + 512);
-          const uint4 x1 = two ? *reinterpret_cast<const uint4*>(xp + b * 32 + 32) : x0;
-          const uint4 wc = two ? *reinterpret_cast<const uint4*>(wp + b * 1024 + 1024) : z;
-          const uint4 wd = two ? *reinterpret_cast<const uint4*>(wp + b * 1024 + 1536) : z;
-          mma_x(acc[0][0], x0, wa.x, wa.y);
-          mma_x(acc[0][1], x0, wa.z, wa.w);
-          mma_x(acc[1][0], x0, wb.x, wb.y);
-          mma_x(acc[1][1], x0, wb.z, wb.w);
-          mma_x(acc[0][0], x1, wc.x, wc.y);
-          mma_x(acc[0][1], x1, wc.z, wc.w);
-          mma_x(acc[1][0], x1, wd.x, wd.y);
-          mma_x(acc[1][1], x1, wd.z, wd.w);
+        for (int b = 0; b < nblk; b += 4) {
+          uint4 wl[4], wh[4], xv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const bool on = b + i < nblk;
+            wl[i] = on ? *reinterpret_cast<const uint4*>(wp + (b + i) * 1024) : z;
+            wh[i] = on ? *reinterpret_cast<const uint4*>(wp + (b + i) * 1024 + 512) : z;
+            xv[i] = *reinterpret_cast<const uint4*>(xp + (on ? b + i : b) * 32);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            mma16816(acc[i & 1][0], wl[i].x, wl[i].y, wl[i].z, wl[i].w, xv[i].x, xv[i].y);
+            mma16816(acc[i & 1][1], wh[i].x, wh[i].y, wh[i].z, wh[i].w, xv[i].z, xv[i].w);
+          }
         }
       } else {
 #pragma unroll 1
@@ -570,15 +584,20 @@ __device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c, int cl, int
     if (t == 0) CK(11);
     ++c.cnt;
     if (++ch == nch) {
-      if (g < MAXNB) {
-        // lane (g, q): activation row g, rows 2q, 2q+1 of each 8-row sub-block
+      if (r16) {
+        // accumulator of lane (g, 0): rows 2g (c0,c1) and 2g+1 (c2,c3) x activation rows 0,1
+        if (q == 0) {
+          float4 o;
+          o.x = (acc[0][0][0] + acc[0][1][0]) + (acc[1][0][0] + acc[1][1][0]);
+          o.y = (acc[0][0][1] + acc[0][1][1]) + (acc[1][0][1] + acc[1][1][1]);
+          o.z = (acc[0][0][2] + acc[0][1][2]) + (acc[1][0][2] + acc[1][1][2]);
+          o.w = (acc[0][0][3] + acc[0][1][3]) + (acc[1][0][3] + acc[1][1][3]);
+          *reinterpret_cast<float4*>(c.psum + ((size_t)(j * NW + c.warp) * 16 + 2 * g) * MAXNB) = o;
+        }
+      } else if (g < MAXNB) {
+        // lane (g, q): activation row g, rows 2q, 2q+1 of the 8-row group
         float* ps = c.psum + ((size_t)(j * NW + c.warp) * 16 + 2 * q) * MAXNB + g;
-        if (r16) {
-          ps[0] = acc[0][0][0] + acc[0][1][2];
-          ps[MAXNB] = acc[0][0][1] + acc[0][1][3];
-          ps[8 * MAXNB] = acc[1][0][0] + acc[1][1][2];
-          ps[9 * MAXNB] = acc[1][0][1] + acc[1][1][3];
-        } else {
+        {
           ps[0] = (acc[0][0][0] + acc[0][1][2]) + (acc[1][0][0] + acc[1][1][2]);
           ps[MAXNB] = (acc[0][0][1] + acc[0][1][3]) + (acc[1][0][1] + acc[1][1][3]);
         }
@@ -774,7 +793,8 @@ __device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
       if (g < ncols) {
         const float is = inv[kvh * 8 + g];
         const int n = g >> gsh, h = kvh * grp + (g & (grp - 1));
-        const int ps = qd == 1 ? 2 : (qd == 2 ? 1 : qd);  // the O projection reads x with the pairs of an 8-group as (P0,P2,P1,P3)
+        // an 8-row-group O projection reads x with the pairs of an 8-group as (P0,P2,P1,P3), a 16-row one in natural order
+        const int ps = ph.R == 16 ? qd : (qd == 1 ? 2 : (qd == 2 ? 1 : qd));
         *reinterpret_cast<__nv_bfloat162*>(c.xs + n * ph.K + h * A_HD + n0 + 2 * ps) = __floats2bfloat162_rn(o[0] * is, o[1] * is);
       }
     }
@@ -804,10 +824,14 @@ __device__ __forceinline__ uint2 norm4(const uint4& v, float inv, uint32_t sc01,
 // sum of squares; normed phases (K <= 2048, <= 4 units per lane) keep the words in registers across it.
 // A unit is 4 elements = two pairs; the pairs of every 8-group are stored in the order (P0,P2,P1,P3)
 // the mma loop expects: unit 2i (P0,P1) -> pair slots 0 and 2, unit 2i+1 (P2,P3) -> slots 1 and 3.
-__device__ __forceinline__ void store_unit(bf16* row, int k4, const uint2& pr) {
-  uint32_t* d = reinterpret_cast<uint32_t*>(row + (k4 >> 1) * 8) + (k4 & 1);
-  d[0] = pr.x;
-  d[2] = pr.y;
+__device__ __forceinline__ void store_unit(bf16* row, int k4, const uint2& pr, bool natural) {
+  if (natural) {  // 16-row groups read x as the B operand, in natural order
+    *reinterpret_cast<uint2*>(row + k4 * 4) = pr;
+  } else {
+    uint32_t* d = reinterpret_cast<uint32_t*>(row + (k4 >> 1) * 8) + (k4 & 1);
+    d[0] = pr.x;
+    d[2] = pr.y;
+  }
 }
 
 __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
@@ -817,7 +841,7 @@ __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
   }
   const int K = ph.K, nb = ph.nb;
   const uint32_t tag0 = tag_of(c.seq, ph.x_src[0]), tag1 = tag_of(c.seq, ph.x_src[1]);
-  const bool norm = ph.norm != 0;
+  const bool norm = ph.norm != 0, natural = ph.R == 16;
   const int slice = K / NW, nu = slice >> 2, tw = nb * nu;  // units of 4 words per row / in all rows of the warp's slice
   const uint32_t* txw = my_copy(ph.t_x, ph.x_rs) + c.warp * slice;
   bf16* xsw = c.xs + c.warp * slice;
@@ -846,7 +870,7 @@ __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
           if (n) ss1 += s;
           else ss0 += s;
         } else {
-          store_unit(xsw + (size_t)n * K, k4, strip4(v[t]));
+          store_unit(xsw + (size_t)n * K, k4, strip4(v[t]), natural);
         }
       }
     }
@@ -876,7 +900,7 @@ __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
       const int e = t * 32 + c.lane;
       if (e < tw) {
         const int n = e >= nu ? 1 : 0, k4 = e - n * nu;
-        store_unit(xsw + (size_t)n * K, k4, norm4(v[t], n ? i1 : i0, sc[t].x, sc[t].y));
+        store_unit(xsw + (size_t)n * K, k4, norm4(v[t], n ? i1 : i0, sc[t].x, sc[t].y), natural);
       }
     }
   }
