@@ -262,6 +262,7 @@ static cudaError_t launch_gemv(const GemvArgs& a, cudaStream_t st) {
 struct RowMeta {
   const int *stream, *pos, *slot;
   int imp_B, imp_pos;
+  int chunk;  // prompt passes: rows n = b * chunk + t (0: not a prompt pass)
 };
 
 // One transformer layer on N rows (torchtune TransformerSelfAttentionLayer, Appendix A.3-A.4).
@@ -923,7 +924,11 @@ static int stack_pass_tc(csm_ctx* x, StackDev& s, int N, const RowMeta& m, cudaS
       dim3 grid(N, k.heads);
       const size_t smem = (size_t)s.slots * sizeof(float);
       const float scale = 1.0f / sqrtf((float)s.hd);
-      if (s.hd == 64) {
+      if (s.hd == 64 && m.chunk >= 16 && m.stream) {
+        // prompt rows: tiled tensor-core attention, one CTA per (64 rows of a stream, q-head)
+        dim3 fgrid((m.chunk + 63) / 64, k.heads, N / m.chunk);
+        k_attn_flash64<<<fgrid, 128, 0, st>>>(s.q, kc, vc, m.slot, m.chunk, k.heads, k.kv_heads, s.slots, scale, s.att);
+      } else if (s.hd == 64) {
         k_attn_rows<64><<<grid, 128, smem, st>>>(s.q, kc, vc, m.stream, m.slot, m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.slots,
                                                  scale, s.att);
       } else {
@@ -949,7 +954,7 @@ static int backbone_pass_tc(csm_ctx* x, int B, int chunk, cudaStream_t st) {
   k_embed_pass<<<N, 256, 0, st>>>(x->d_params, x->text_emb, x->audio_emb, c.codebooks, c.audio_vocab, c.backbone.dim, chunk,
                                   x->bb.h, x->row_stream, x->row_pos, x->row_slot); COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
-  RowMeta m{x->row_stream, x->row_pos, x->row_slot, 0, 0};
+  RowMeta m{x->row_stream, x->row_pos, x->row_slot, 0, 0, chunk};
   return stack_pass_tc(x, x->bb, N, m, st);
 }
 

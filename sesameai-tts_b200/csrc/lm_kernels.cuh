@@ -327,6 +327,177 @@ __global__ void __launch_bounds__(128) k_attn_rows(const bf16* __restrict__ q, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// K3 (prompt prefill): tiled causal attention on the tensor cores, head_dim 64.
+// One CTA = 64 consecutive prompt rows of one stream x one q-head; 4 warps x 16 rows.  Key tiles of
+// 64 cache rows are double-buffered in shared memory with cp.async; S = Q K^T and O += P V are
+// mma.m16n8k16 (K fragments by ldmatrix, V fragments by ldmatrix.trans), the softmax is the online
+// (running max / running sum) form in fp32 registers, P is rounded to bf16 for the second product.
+// Rows: n = b * chunk + t, cache slot row_slot[n] (ascending in t), keys [0 .. slot] of stream b.
+// ---------------------------------------------------------------------------------------------
+constexpr int FA_LD = 72;  // padded row length (bf16) of the 64 x 64 tiles: conflict-free ldmatrix
+
+__device__ __forceinline__ void fa_ldm4(uint32_t (&r)[4], const bf16* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void fa_ldm4t(uint32_t (&r)[4], const bf16* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void fa_mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void fa_cp16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ uint32_t fa_pack(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(128) k_attn_flash64(const bf16* __restrict__ q, const bf16* __restrict__ k_cache,
+                                                      const bf16* __restrict__ v_cache, const int* __restrict__ row_slot, int chunk,
+                                                      int heads, int kv_heads, int slots, float scale, bf16* __restrict__ out) {
+  __shared__ __align__(16) bf16 Qs[64 * FA_LD];
+  __shared__ __align__(16) bf16 Ks[2][64 * FA_LD];
+  __shared__ __align__(16) bf16 Vs[2][64 * FA_LD];
+  const int b = blockIdx.z, h = blockIdx.y, t0 = blockIdx.x * 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, qd = lane & 3;
+  const int kvh = h / (heads / kv_heads);
+  const int nrows = min(64, chunk - t0);          // valid rows of this tile
+  const size_t n0 = (size_t)b * chunk + t0;       // first row
+  const bf16* kp = k_cache + ((size_t)b * kv_heads + kvh) * slots * 64;
+  const bf16* vp = v_cache + ((size_t)b * kv_heads + kvh) * slots * 64;
+  const int slot_last = row_slot[n0 + nrows - 1];
+  const int nkt = slot_last / 64 + 1;
+
+  auto load_kv = [&](int kt, int buf) {
+    for (int u = tid; u < 64 * 8; u += 128) {  // 64 rows x 8 units of 16 bytes, for K and for V
+      const int r = u >> 3, c8 = (u & 7) * 8;
+      const int key = kt * 64 + r;
+      if (key <= slot_last) {
+        fa_cp16(&Ks[buf][r * FA_LD + c8], kp + (size_t)key * 64 + c8);
+        fa_cp16(&Vs[buf][r * FA_LD + c8], vp + (size_t)key * 64 + c8);
+      } else {  // never-written cache rows may hold Inf / NaN patterns: P is 0 there, but 0 * Inf is not
+        *reinterpret_cast<uint4*>(&Ks[buf][r * FA_LD + c8]) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(&Vs[buf][r * FA_LD + c8]) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load_kv(0, 0);
+  for (int u = tid; u < 64 * 8; u += 128) {
+    const int r = u >> 3, c8 = (u & 7) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < nrows) v = *reinterpret_cast<const uint4*>(q + ((n0 + r) * heads + h) * 64 + c8);
+    *reinterpret_cast<uint4*>(&Qs[r * FA_LD + c8]) = v;
+  }
+  __syncthreads();
+  uint32_t qa[4][4];  // A fragments of this warp's 16 rows, 4 k-steps of 16 dims
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk)
+    fa_ldm4(qa[kk], &Qs[(warp * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * FA_LD + kk * 16 + (lane >> 4) * 8]);
+  const int r_lo = warp * 16 + g, r_hi = r_lo + 8;
+  const int slot_lo = r_lo < nrows ? row_slot[n0 + r_lo] : 0, slot_hi = r_hi < nrows ? row_slot[n0 + r_hi] : 0;
+  float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+  float o[8][4];
+#pragma unroll
+  for (int d = 0; d < 8; ++d)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[d][e] = 0.f;
+  const float sl2 = scale * 1.4426950408889634f;  // scores in log2 units: exp(x) = exp2(x log2 e)
+
+  for (int kt = 0; kt < nkt; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nkt) load_kv(kt + 1, buf ^ 1);
+    if (kt + 1 < nkt) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    // S = Q K^T for 64 keys: 8 n-tiles x 4 k-steps
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[j][e] = 0.f;
+#pragma unroll
+      for (int kk2 = 0; kk2 < 2; ++kk2) {
+        uint32_t kb[4];  // (b0, b1) of k-step 2 kk2 and of k-step 2 kk2 + 1
+        fa_ldm4(kb, &Ks[buf][(j * 8 + (lane & 7)) * FA_LD + kk2 * 32 + (lane >> 3) * 8]);
+        fa_mma(s[j], qa[2 * kk2], kb[0], kb[1]);
+        fa_mma(s[j], qa[2 * kk2 + 1], kb[2], kb[3]);
+      }
+    }
+    // causal mask + running max
+    const int key0 = kt * 64 + 2 * qd;
+    float mx_lo = m_lo, mx_hi = m_hi;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int key = key0 + j * 8 + e;
+        s[j][e] = key <= slot_lo ? s[j][e] * sl2 : -INFINITY;
+        s[j][2 + e] = key <= slot_hi ? s[j][2 + e] * sl2 : -INFINITY;
+        mx_lo = fmaxf(mx_lo, s[j][e]);
+        mx_hi = fmaxf(mx_hi, s[j][2 + e]);
+      }
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+    // key 0 is visible to every row, so the running max is finite from the first tile on
+    const float c_lo = exp2f(m_lo - mx_lo), c_hi = exp2f(m_hi - mx_hi);
+    m_lo = mx_lo;
+    m_hi = mx_hi;
+    float ps_lo = 0.f, ps_hi = 0.f;
+    uint32_t pa[4][4];  // P as A fragments: k-step t = keys 16 t .. 16 t + 15 = n-tiles 2t, 2t+1
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = exp2f(s[j][0] - m_lo), p1 = exp2f(s[j][1] - m_lo);
+      const float p2 = exp2f(s[j][2] - m_hi), p3 = exp2f(s[j][3] - m_hi);
+      ps_lo += p0 + p1;
+      ps_hi += p2 + p3;
+      pa[j >> 1][(j & 1) * 2] = fa_pack(p0, p1);
+      pa[j >> 1][(j & 1) * 2 + 1] = fa_pack(p2, p3);
+    }
+    l_lo = l_lo * c_lo + ps_lo;
+    l_hi = l_hi * c_hi + ps_hi;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      o[d][0] *= c_lo; o[d][1] *= c_lo;
+      o[d][2] *= c_hi; o[d][3] *= c_hi;
+    }
+    // O += P V: 8 n-tiles of 8 dims x 4 k-steps of 16 keys
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+#pragma unroll
+      for (int d2 = 0; d2 < 4; ++d2) {
+        uint32_t vb[4];  // (b0, b1) of dims 16 d2 .. +7 and of dims 16 d2 + 8 .. +15
+        fa_ldm4t(vb, &Vs[buf][(t * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * FA_LD + d2 * 16 + (lane >> 4) * 8]);
+        fa_mma(o[2 * d2], pa[t], vb[0], vb[1]);
+        fa_mma(o[2 * d2 + 1], pa[t], vb[2], vb[3]);
+      }
+    __syncthreads();  // the buffer is free for the load after next
+  }
+  // the row sums live spread over the four lanes of a quad
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+  const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) {
+    if (r_lo < nrows)
+      *reinterpret_cast<uint32_t*>(out + ((n0 + r_lo) * heads + h) * 64 + d * 8 + 2 * qd) = fa_pack(o[d][0] * i_lo, o[d][1] * i_lo);
+    if (r_hi < nrows)
+      *reinterpret_cast<uint32_t*>(out + ((n0 + r_hi) * heads + h) * 64 + d * 8 + 2 * qd) = fa_pack(o[d][2] * i_hi, o[d][3] * i_hi);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Row-batched RoPE + KV append for the tensor-core prefill path: qkv [N, (H+2KV)*hd] (GEMM output,
 // already rounded to bf16) -> rotated q [N, H*hd], rotated k and v into the cache at the row's slot.
 // Same arithmetic as the EPI_ROPE_KV epilogue.
