@@ -595,9 +595,10 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
   CU_TRY(cudaGetLastError());
 
   // Which depth-decoder matrices stay in L2 across the 31 codebook steps (see mega.cuh, producer_loop).
-  // Default: the down and O projections of every layer and QKV (75 MB of the 222 MB); CSM_MEGA_KEEP=<hex>
-  // overrides it for experiments (4 bits per layer: 1 qkv, 2 o, 4 gate/up, 8 down).
-  x->mega_keep = 0xBBBBBBBBu;
+  // Measured (profiles/r1_mega_l2_keep.txt): no subset helps -- the stream phases are bound by the per-chunk
+  // consumer loop and the hand-off chain, not by HBM bandwidth -- so the default is none; CSM_MEGA_KEEP=<hex>
+  // sets it for experiments (4 bits per layer: 1 qkv, 2 o, 4 gate/up, 8 down).
+  x->mega_keep = 0;
   if (const char* e = getenv("CSM_MEGA_KEEP")) x->mega_keep = (unsigned)strtoul(e, nullptr, 16);
   MegaBuild mb;
   mb.ncta = sms;
