@@ -224,6 +224,13 @@ int32_t csm_k_linear(const void *x, const void *W, int32_t N, int32_t in, int32_
 int32_t csm_k_gemm_tc(const void *x, const void *W, int32_t N, int32_t in, int32_t out, void *y, int32_t epi,
                       const void *resid, void *stream);
 
+/* Prompt attention (head_dim 64) on the tensor cores, the kernel behind the tensor-core prefill
+ * (replaces the per-row scaled_dot_product_attention of torchtune's MultiHeadAttention for prompt rows):
+ * q [B*chunk, heads*64] (row n = b*chunk + t), caches [B, kv_heads, slots, 64], row_slot[n] = cache slot of row
+ * n (ascending in t); row n attends to slots [0 .. row_slot[n]] of stream b; out [B*chunk, heads*64], bf16. */
+int32_t csm_k_attn_prefill(const void *q, const void *k_cache, const void *v_cache, const int32_t *row_slot, int32_t B,
+                           int32_t chunk, int32_t heads, int32_t kv_heads, int32_t slots, void *out, void *stream);
+
 /* torchtune RMSNorm: bf16(bf16(x * rsqrt(mean x^2 + eps)) * scale), [N, D]. */
 int32_t csm_k_rmsnorm(const void *x, const void *scale, int32_t N, int32_t D, float eps, void *y, void *stream);
 

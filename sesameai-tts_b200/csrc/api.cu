@@ -550,7 +550,7 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
   x->trace = nullptr;
   const csm_config& c = x->cfg;
   // fused small attention needs <= 32 cached keys; scores of the backbone attention sit in the x buffer
-  if (c.codebooks > 32 || c.max_seq_len * 4 + (mega::NCT + 3 * 128) * 4 > 32768) return CSM_OK;
+  if (c.codebooks > 32 || c.max_seq_len * 4 + (8 * mega::NCT + 3 * 128) * 4 > 65536) return CSM_OK;
   if (x->dec.hd != 128 || 2 * c.decoder.dim > 2048 || c.decoder.kv_heads > 2) return CSM_OK;  // fused attention layout
   if (!is_pow2(c.decoder.heads) || !is_pow2(c.decoder.heads / c.decoder.kv_heads) || 2 * (c.decoder.heads / c.decoder.kv_heads) > 8)
     return CSM_OK;  // (activation row, head in group) columns must fit the 8-wide mma tile
@@ -991,6 +991,19 @@ extern "C" int32_t csm_k_gemm_tc(const void* xin, const void* W, int32_t N, int3
   const long long ldo = epi == tc::EPI_SWIGLU_PAIRS ? outf / 2 : outf;
   return launch_gemm_tc((const bf16*)xin, in, N, in, (const bf16*)W, outf, (bf16*)y, ldo, epi, (const bf16*)resid,
                         (cudaStream_t)stream);
+}
+
+extern "C" int32_t csm_k_attn_prefill(const void* q, const void* k_cache, const void* v_cache, const int32_t* row_slot, int32_t B,
+                                      int32_t chunk, int32_t heads, int32_t kv_heads, int32_t slots, void* out, void* stream) {
+  if (!q || !k_cache || !v_cache || !row_slot || !out || B < 1 || chunk < 1 || heads < 1 || kv_heads < 1 || heads % kv_heads ||
+      slots < 1)
+    return set_err(CSM_ERR_ARG, "bad attn_prefill arguments");
+  dim3 grid((chunk + 63) / 64, heads, B);
+  k_attn_flash64<<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache, row_slot, chunk,
+                                                         heads, kv_heads, slots, 0.125f, (bf16*)out);
+  COUNT_LAUNCH();
+  CU_TRY(cudaGetLastError());
+  return CSM_OK;
 }
 
 // ---- unit-test entry points -----------------------------------------------------------------

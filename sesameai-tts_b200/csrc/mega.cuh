@@ -894,8 +894,9 @@ __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
       t1 += c.scratch[NW + w];
     }
     const float ik = ph.inv_K;  // exact when K is a power of two
-    const float i0 = 1.0f / sqrtf((ik != 0.f ? t0 * ik : t0 / (float)K) + ph.eps);
-    const float i1 = nb == 2 ? 1.0f / sqrtf((ik != 0.f ? t1 * ik : t1 / (float)K) + ph.eps) : 0.f;
+    // torch.rsqrt on a GPU is rsqrtf (<= 2 ulp), which is also ~50 instructions shorter than 1 / sqrtf in this chain
+    const float i0 = rsqrtf((ik != 0.f ? t0 * ik : t0 / (float)K) + ph.eps);
+    const float i1 = nb == 2 ? rsqrtf((ik != 0.f ? t1 * ik : t1 / (float)K) + ph.eps) : 0.f;
     CK(8);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -944,8 +945,8 @@ __device__ __forceinline__ void attn_phase(const Phase& ph, Ctx& c) {
   const bf16* kp = ph.kc + (size_t)kvh * ph.slots * hd;
   const bf16* vp = ph.vc + (size_t)kvh * ph.slots * hd;
   float* sc = reinterpret_cast<float*>(c.xs);  // [slots] scores (<= 8 KB)
-  float* part = sc + ph.slots;                  // [NCT] partial outputs
-  float* qs = part + NCT;                       // [hd]
+  float* part = sc + ((ph.slots + 3) & ~3);      // [NCT / (hd/8)][hd] = 8 NCT partial outputs (16-byte aligned)
+  float* qs = part + 8 * NCT;                   // [hd]
   float* kcur = qs + hd;                        // [hd]
   float* vcur = kcur + hd;                      // [hd]
   const float scale = 1.0f / sqrtf((float)hd);
@@ -985,25 +986,48 @@ __device__ __forceinline__ void attn_phase(const Phase& ph, Ctx& c) {
     sum += e;
   }
   sum = block_sum<NCT, CBAR>(sum, c.scratch, c.tid);
-  const int G = NCT / hd;  // key groups
-  const int g = c.tid / hd, d = c.tid % hd;
+  // P.V: 8 dims (one 16-byte load) per thread, hd/8 threads per key row, NCT / (hd/8) key groups:
+  // a context of a few hundred keys is one batch of loads in flight per thread
+  const int tpr = hd >> 3, ngroups = NCT / tpr;
+  const int kg = c.tid / tpr, d8 = (c.tid - kg * tpr) * 8;
   const int nold = nkeys - 1;  // keys in the cache
-  float acc = 0.f;
-  int j = g;
-  for (; j + 7 * G < nold; j += 8 * G) {  // 8 independent loads in flight
-    float v[8];
+  float acc[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = ldcg_bf(vp + (size_t)(j + u * G) * hd + d);
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  int j = kg;
+  for (; j + 3 * ngroups < nold; j += 4 * ngroups) {
+    uint4 v[4];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) acc = fmaf(sc[j + u * G], v[u], acc);
+    for (int u = 0; u < 4; ++u) v[u] = ldcg16(vp + (size_t)(j + u * ngroups) * hd + d8);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float p = sc[j + u * ngroups];
+      acc[0] = fmaf(p, bflo(v[u].x), acc[0]); acc[1] = fmaf(p, bfhi(v[u].x), acc[1]);
+      acc[2] = fmaf(p, bflo(v[u].y), acc[2]); acc[3] = fmaf(p, bfhi(v[u].y), acc[3]);
+      acc[4] = fmaf(p, bflo(v[u].z), acc[4]); acc[5] = fmaf(p, bfhi(v[u].z), acc[5]);
+      acc[6] = fmaf(p, bflo(v[u].w), acc[6]); acc[7] = fmaf(p, bfhi(v[u].w), acc[7]);
+    }
   }
-  for (; j < nold; j += G) acc = fmaf(sc[j], ldcg_bf(vp + (size_t)j * hd + d), acc);
-  if (g == 0) acc = fmaf(sc[slot], vcur[d], acc);
-  part[c.tid] = acc;
+  for (; j < nold; j += ngroups) {
+    const uint4 v = ldcg16(vp + (size_t)j * hd + d8);
+    const float p = sc[j];
+    acc[0] = fmaf(p, bflo(v.x), acc[0]); acc[1] = fmaf(p, bfhi(v.x), acc[1]);
+    acc[2] = fmaf(p, bflo(v.y), acc[2]); acc[3] = fmaf(p, bfhi(v.y), acc[3]);
+    acc[4] = fmaf(p, bflo(v.z), acc[4]); acc[5] = fmaf(p, bfhi(v.z), acc[5]);
+    acc[6] = fmaf(p, bflo(v.w), acc[6]); acc[7] = fmaf(p, bfhi(v.w), acc[7]);
+  }
+  if (kg == 0) {
+    const float p = sc[slot];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vcur[d8 + e], acc[e]);
+  }
+  *reinterpret_cast<float4*>(part + kg * hd + d8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  *reinterpret_cast<float4*>(part + kg * hd + d8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
   csync<NCT, CBAR>();
-  if (g == 0) {
-    for (int gg = 1; gg < G; ++gg) acc += part[gg * hd + d];
-    rep_st1(ph.t_out + (size_t)h * hd + d, ph.out_rs, tword(c.tag, acc * (1.0f / sum)));
+  if (c.tid < hd) {
+    float o = 0.f;
+    for (int gg = 0; gg < ngroups; ++gg) o += part[gg * hd + c.tid];  // fixed order
+    rep_st1(ph.t_out + (size_t)h * hd + c.tid, ph.out_rs, tword(c.tag, o * (1.0f / sum)));
   }
 }
 
@@ -1058,26 +1082,32 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
   float best = -INFINITY;
   int besti = 0x7fffffff, bestn = 0;
   {
+    // the head phase wrote every word below the 16-row padded vocabulary: poll whole 4-word units
     const uint32_t tag = tag_of(c.seq, ph.logits_src);
-    constexpr int MAXPT = SAMPLE_MAXV / NCT;
-    uint32_t w[MAXPT];
+    constexpr int MAXU = SAMPLE_MAXV / 4 / NCT;
+    const int nunits = (V + 3) >> 2;
+    uint4 w[MAXU];
 #pragma unroll
-    for (int t = 0; t < MAXPT; ++t) {
-      const int i = c.tid + t * NCT;
-      if (i < V) w[t] = ldv1(ph.t_logits + i);
+    for (int t = 0; t < MAXU; ++t) {
+      const int u = c.tid + t * NCT;
+      if (u < nunits) w[t] = ldv4(ph.t_logits + u * 4);
     }
 #pragma unroll
-    for (int t = 0; t < MAXPT; ++t) {
-      const int i = c.tid + t * NCT;
-      if (i < V) {
-        for (unsigned spin = 0; ((w[t] ^ tag) & 0xffff0000u) != 0; ++spin) {
-          if (spin > (1u << 22)) die(c.sync, 0x403);
-          w[t] = ldv1(ph.t_logits + i);
+    for (int t = 0; t < MAXU; ++t) {
+      const int u = c.tid + t * NCT;
+      if (u < nunits) {
+        w[t] = poll4(ph.t_logits + u * 4, tag, w[t], c.sync);
+        const uint32_t ww[4] = {w[t].x, w[t].y, w[t].z, w[t].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = u * 4 + e;
+          if (i < V) {
+            lg[i] = __ushort_as_bfloat16((unsigned short)(ww[e] & 0xffffu));
+            const float xv = rbf(tval(ww[e]) * inv_t);  // the value sample_row compares (x * (1/T) rounded to bf16)
+            if (xv > best) { best = xv; besti = i; bestn = 1; }
+            else if (xv == best) ++bestn;
+          }
         }
-        lg[i] = __ushort_as_bfloat16((unsigned short)(w[t] & 0xffffu));
-        const float xv = rbf(tval(w[t]) * inv_t);  // the value sample_row compares (x * (1/T) rounded to bf16)
-        if (xv > best) { best = xv; besti = i; bestn = 1; }
-        else if (xv == best) ++bestn;
       }
     }
   }
