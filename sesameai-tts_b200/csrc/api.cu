@@ -550,7 +550,7 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
   x->trace = nullptr;
   const csm_config& c = x->cfg;
   // fused small attention needs <= 32 cached keys; scores of the backbone attention sit in the x buffer
-  if (c.codebooks > 32 || c.max_seq_len * 4 + (8 * mega::NCT + 3 * 128) * 4 > 65536) return CSM_OK;
+  if (c.codebooks > 32 || c.max_seq_len * 4 + (8 * mega::NCT + 3 * 128) * 4 > mega::XBUF_ELEMS * 2) return CSM_OK;
   if (x->dec.hd != 128 || 2 * c.decoder.dim > 2048 || c.decoder.kv_heads > 2) return CSM_OK;  // fused attention layout
   if (!is_pow2(c.decoder.heads) || !is_pow2(c.decoder.heads / c.decoder.kv_heads) || 2 * (c.decoder.heads / c.decoder.kv_heads) > 8)
     return CSM_OK;  // (activation row, head in group) columns must fit the 8-wide mma tile
@@ -600,6 +600,12 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
   // sets it for experiments (4 bits per layer: 1 qkv, 2 o, 4 gate/up, 8 down).
   x->mega_keep = 0;
   if (const char* e = getenv("CSM_MEGA_KEEP")) x->mega_keep = (unsigned)strtoul(e, nullptr, 16);
+  if (x->mega_keep) {
+    // evict-last lines only persist inside the L2 set-aside: open it as far as the device allows
+    int persist_max = 0;
+    CU_TRY(cudaDeviceGetAttribute(&persist_max, cudaDevAttrMaxPersistingL2CacheSize, dev));
+    if (persist_max > 0) CU_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)persist_max));
+  }
   MegaBuild mb;
   mb.ncta = sms;
   mb.rot = 0;

@@ -41,7 +41,7 @@ constexpr int SLOT_BYTES = MEGA_SLOT_BYTES;  // bytes per slot (a chunk never ex
 #endif
 constexpr int REP = MEGA_REP;         // copies of every broadcast activation vector (spreads the readers over L2 slices)
 constexpr int MAXNB = 2;              // activation rows per phase (depth step 1 carries 2)
-constexpr int XBUF_ELEMS = 2 * MAXNB * 8192;  // 64 KB: activation rows, or the fused attention's q / K / V staging
+constexpr int XBUF_ELEMS = 25600;  // 50 KB: activation rows (<= 2 x 8192), or the fused attention's q / K / V staging (A_IOFF + 64)
 constexpr int CBAR = 1;               // consumer warps synchronise on named barrier 1 (the producer warp never joins)
 constexpr int MAX_GEMV = 640;         // rows of the prefetch table (kernel parameter space)
 constexpr int MAX_LOCAL_GROUPS = 8;   // row groups one CTA owns in one phase
@@ -49,8 +49,7 @@ constexpr size_t SMEM_RING = (size_t)NW * SLOTS * SLOT_BYTES;
 constexpr size_t SMEM_X = (size_t)XBUF_ELEMS * 2;
 constexpr size_t SMEM_PSUM = (size_t)MAX_LOCAL_GROUPS * NW * 16 * MAXNB * 4;
 constexpr size_t SMEM_MISC = 2048;
-constexpr size_t SMEM_TAB = (size_t)MAX_GEMV * 24 + 16;  // copy of the prefetch table
-constexpr size_t SMEM_BYTES = SMEM_RING + SMEM_X + SMEM_PSUM + SMEM_MISC + SMEM_TAB;
+constexpr size_t SMEM_BYTES = SMEM_RING + SMEM_X + SMEM_PSUM + SMEM_MISC;
 
 enum { PH_GEMV = 0, PH_EMBED = 1, PH_ATTN = 2, PH_SAMPLE = 3 };
 enum { POS_FIXED = 0, POS_BACKBONE = 1 };
@@ -1189,12 +1188,6 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
   int* iscratch = reinterpret_cast<int*>(scratch + 34);                    // [40]
   static_assert(2 * sizeof(Phase) + 2 * NW * SLOTS * 8 + 34 * 4 + 40 * 4 <= SMEM_MISC, "misc region too small");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-  PfDesc* stab = reinterpret_cast<PfDesc*>(misc + SMEM_MISC);  // [tab.n]: shared-memory copy of the schedule
-  {
-    const uint2* src = reinterpret_cast<const uint2*>(tab.d);
-    uint2* dst = reinterpret_cast<uint2*>(stab);
-    for (int i = threadIdx.x; i < tab.n * 3; i += NTHREADS) dst[i] = src[i];
-  }
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2 * NW * SLOTS; ++i) mbar_init(&full[i], 1);  // full[] and empty[] are contiguous
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1206,7 +1199,7 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
   __syncthreads();
 
   if (threadIdx.x >= NCT) {  // producer warp: feeds the eight weight rings for the whole frame, then retires
-    producer_loop(stab, tab.n, ring, full, empty, sync, threadIdx.x - NCT);
+    producer_loop(tab.d, tab.n, ring, full, empty, sync, threadIdx.x - NCT);  // the schedule is read from parameter space: only this warp walks it
     return;
   }
 
