@@ -12,6 +12,7 @@
 #include "lm_kernels.cuh"
 #include "mega.cuh"
 #include "gemm_tc.cuh"
+#include "skinny.cuh"
 
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
@@ -45,6 +46,7 @@ static const int PREFILL_CHUNK = 8;     // prompt frames per stream per small-ro
 static const int PREFILL_TC_ROWS = 4096;  // rows per tensor-core prefill pass
 static const int PREFILL_TC_MIN = 64;     // prompt rows (B * (S-1)) from which the tcgen05 path is used
 static const int DECODE_TC_MIN = 16;      // streams from which a decode step runs on the tcgen05 GEMM
+static const int SKINNY_MAX_ROWS = 64;    // rows up to which a linear layer runs on the skinny fragment-major GEMM
 
 struct StackDev {
   csm_stack_config c;
@@ -90,6 +92,7 @@ struct csm_ctx {
   mega::Sync* d_sync;
   int n_phases, mega_grid;
   bool mega_ok;
+  bool frag_ok;  // the fragment-major packed matrices exist (setup_mega): the skinny batched-decode GEMM can run
   unsigned long long* trace;  // optional device buffer [n_phases][8] (csm_debug_set_trace)
   mega::PfTable pf_table;     // weight-prefetch schedule, passed in kernel-parameter space
   unsigned mega_keep;  // depth-decoder matrices loaded with the L2 evict-last policy: 4 bits per layer (qkv, o, gate/up, down)
@@ -547,6 +550,7 @@ static void build_mega_phases(csm_ctx* x, MegaBuild& mb) {
 
 static int setup_mega(csm_ctx* x, cudaStream_t st) {
   x->mega_ok = false;
+  x->frag_ok = false;
   x->trace = nullptr;
   const csm_config& c = x->cfg;
   // fused small attention needs <= 32 cached keys; scores of the backbone attention sit in the x buffer
@@ -593,6 +597,7 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
     pack_frag(x->head_t + (size_t)i * x->Vp * Dd, c.audio_vocab, Dd, x->mega_Rh, x->f_heads + (size_t)i * x->Vf * Dd, st);
   CU_TRY(cudaMemsetAsync(x->tagged_base, 0, x->tagged_bytes, st));  // stale tags of an earlier context must never match
   CU_TRY(cudaGetLastError());
+  x->frag_ok = true;
 
   // Which depth-decoder matrices stay in L2 across the 31 codebook steps (see mega.cuh, producer_loop).
   // Measured (profiles/r1_mega_l2_keep.txt): no subset helps -- the stream phases are bound by the per-chunk
@@ -750,6 +755,13 @@ extern "C" int32_t csm_reset_caches(csm_ctx* x) {
 }
 extern "C" int32_t csm_cache_len(const csm_ctx* x) { return x ? x->cache_len : -1; }
 
+// decode steps run row-batched (RMSNorm / linear / RoPE kernels over all streams) from 16 streams on the
+// tcgen05 GEMM, and from 2 streams when the skinny GEMM has its fragment-major weights
+static bool rows_path(const csm_ctx* x, int B) {
+  if (x->cfg.backbone.dim % 64 || x->cfg.decoder.dim % 64) return false;
+  return B >= DECODE_TC_MIN || (x->frag_ok && B >= 2 && 2 * B <= SKINNY_MAX_ROWS);
+}
+
 static int get_graph(csm_ctx* x, int B, cudaGraphExec_t* out) {
   auto it = x->graphs.find(B);
   if (it != x->graphs.end()) {
@@ -761,7 +773,7 @@ static int get_graph(csm_ctx* x, int B, cudaGraphExec_t* out) {
   CU_TRY(cudaStreamBeginCapture(x->cap_stream, cudaStreamCaptureModeThreadLocal));
   cudaError_t e = cudaSuccess;
   int rc_tc = CSM_OK;
-  if (B >= DECODE_TC_MIN && x->cfg.backbone.dim % 64 == 0 && x->cfg.decoder.dim % 64 == 0) {
+  if (rows_path(x, B)) {
     rc_tc = backbone_pass_tc(x, B, 1, x->cap_stream);
     if (rc_tc == CSM_OK) rc_tc = frame_tail_tc(x, B, x->cap_stream);
   } else {
@@ -839,7 +851,7 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
   k_set_params<<<1, 1, 0, st>>>(x->d_params, p); COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
   if (path == CSM_PATH_DIRECT) {
-    if (B >= DECODE_TC_MIN && x->cfg.backbone.dim % 64 == 0 && x->cfg.decoder.dim % 64 == 0) {
+    if (rows_path(x, B)) {
       int rc = backbone_pass_tc(x, B, 1, st);
       if (rc == CSM_OK) rc = frame_tail_tc(x, B, st);
       if (rc != CSM_OK) return rc;
@@ -912,6 +924,47 @@ static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const b
   return CSM_OK;
 }
 
+// Batched decode (<= 64 rows): one CTA per fragment-major row group (skinny.cuh).  n_out = valid rows.
+template <bool NORM>
+static void launch_skinny_t(const sk::Args& a, cudaStream_t st) {
+  if (a.N <= 8) sk::k_skinny<1, NORM><<<a.G, 256, 0, st>>>(a);
+  else if (a.N <= 16) sk::k_skinny<2, NORM><<<a.G, 256, 0, st>>>(a);
+  else if (a.N <= 32) sk::k_skinny<4, NORM><<<a.G, 256, 0, st>>>(a);
+  else sk::k_skinny<8, NORM><<<a.G, 256, 0, st>>>(a);
+}
+// norm_scale != null: X holds the un-normalised rows and the kernel applies torchtune's RMSNorm on the fly
+static int launch_skinny(const bf16* Wf, int R, const bf16* X, long long ldx, int N, int K, int n_out, bf16* out, long long ldo,
+                         int epi, const bf16* resid, cudaStream_t st, const bf16* norm_scale = nullptr, float eps = 0.f) {
+  sk::Args a;
+  a.Wf = Wf; a.R = R; a.K = K; a.n_out = n_out; a.G = (n_out + R - 1) / R; a.X = X; a.ldx = ldx; a.N = N; a.out = out; a.ldo = ldo;
+  a.resid = resid ? resid : out; a.epi = epi; a.norm_scale = norm_scale; a.eps = eps;
+  if (norm_scale) launch_skinny_t<true>(a, st);
+  else launch_skinny_t<false>(a, st);
+  COUNT_LAUNCH();
+  CU_TRY(cudaGetLastError());
+  return CSM_OK;
+}
+// a linear layer of the row-batched path: skinny kernel for few rows, tcgen05 GEMM otherwise
+static bool skinny_ok(const csm_ctx* x, const bf16* Wf, int N, int K) {
+  return x->frag_ok && Wf && N <= SKINNY_MAX_ROWS && K % 256 == 0;
+}
+static int linear_rows(csm_ctx* x, const bf16* W, const bf16* Wf, int R, const bf16* X, long long ldx, int N, int K, int n_out,
+                       bf16* out, long long ldo, int epi, const bf16* resid, cudaStream_t st) {
+  if (skinny_ok(x, Wf, N, K)) return launch_skinny(Wf, R, X, ldx, N, K, n_out, out, ldo, epi, resid, st);
+  return launch_gemm_tc(X, ldx, N, K, W, n_out, out, ldo, epi, resid, st);
+}
+// RMSNorm(H rows) followed by a linear layer: fused into the skinny kernel for few rows, else k_rmsnorm into
+// ``xn`` (skipped when ``xn_ready``: an earlier call of the same pair normalised already) and the tcgen05 GEMM
+static int norm_linear_rows(csm_ctx* x, const bf16* H, const bf16* scale, float eps, bf16* xn, bool xn_ready, const bf16* W,
+                            const bf16* Wf, int R, int N, int K, int n_out, bf16* out, long long ldo, int epi, cudaStream_t st) {
+  // (every CTA normalises all rows itself: cheaper than a launch up to 16 rows, measured slower at 32)
+  if (skinny_ok(x, Wf, N, K) && N <= 16) return launch_skinny(Wf, R, H, K, N, K, n_out, out, ldo, epi, nullptr, st, scale, eps);
+  if (!xn_ready) {
+    k_rmsnorm<<<N, 256, 0, st>>>(H, K, scale, K, eps, xn, K); COUNT_LAUNCH();
+  }
+  return linear_rows(x, W, Wf, R, xn, K, N, K, n_out, out, ldo, epi, nullptr, st);
+}
+
 // All layers of one stack on N rows with the tcgen05 GEMM: per layer RMSNorm -> GEMM [q;k;v] -> RoPE +
 // KV append -> attention -> GEMM O (+res) -> RMSNorm -> GEMM gate/up (SwiGLU epilogue) -> GEMM down
 // (+res); same rounding points as the small-row path.
@@ -919,12 +972,13 @@ static int stack_pass_tc(csm_ctx* x, StackDev& s, int N, const RowMeta& m, cudaS
   const csm_stack_config& k = s.c;
   const int D = k.dim, qkv_cols = (k.heads + 2 * k.kv_heads) * s.hd;
   const float eps = x->cfg.norm_eps;
+  const int* R4 = (&s == &x->bb) ? x->mega_Rbb : x->mega_Rdec;  // row-group heights of the fragment-major copies
   int rc;
   for (int l = 0; l < k.layers; ++l) {
     bf16* kc = s.kc + s.kv_layer_stride * l;
     bf16* vc = s.vc + s.kv_layer_stride * l;
-    k_rmsnorm<<<N, 256, 0, st>>>(s.h, D, s.sa[l], D, eps, s.xn, D); COUNT_LAUNCH();
-    if ((rc = launch_gemm_tc(s.xn, D, N, D, s.wqkv[l], qkv_cols, s.qkv, qkv_cols, tc::EPI_STORE, nullptr, st)) != CSM_OK) return rc;
+    if ((rc = norm_linear_rows(x, s.h, s.sa[l], eps, s.xn, false, s.wqkv[l], s.fqkv[l], R4[0], N, D, qkv_cols, s.qkv, qkv_cols,
+                               tc::EPI_STORE, st)) != CSM_OK) return rc;
     k_rope_kv_rows<<<N, 256, 0, st>>>(s.qkv, s.rope, m.stream, m.pos, m.slot, m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.hd,
                                       s.slots, s.q, kc, vc); COUNT_LAUNCH();
     {
@@ -945,10 +999,10 @@ static int stack_pass_tc(csm_ctx* x, StackDev& s, int N, const RowMeta& m, cudaS
       COUNT_LAUNCH();
     }
     CU_TRY(cudaGetLastError());
-    if ((rc = launch_gemm_tc(s.att, D, N, D, s.wo[l], D, s.h, D, tc::EPI_ADD_RESID, s.h, st)) != CSM_OK) return rc;
-    k_rmsnorm<<<N, 256, 0, st>>>(s.h, D, s.mlp[l], D, eps, s.xn, D); COUNT_LAUNCH();
-    if ((rc = launch_gemm_tc(s.xn, D, N, D, s.wgu[l], 2 * k.ff, s.act, k.ff, tc::EPI_SWIGLU_PAIRS, nullptr, st)) != CSM_OK) return rc;
-    if ((rc = launch_gemm_tc(s.act, k.ff, N, k.ff, s.wd[l], D, s.h, D, tc::EPI_ADD_RESID, s.h, st)) != CSM_OK) return rc;
+    if ((rc = linear_rows(x, s.wo[l], s.fo[l], R4[1], s.att, D, N, D, D, s.h, D, tc::EPI_ADD_RESID, s.h, st)) != CSM_OK) return rc;
+    if ((rc = norm_linear_rows(x, s.h, s.mlp[l], eps, s.xn, false, s.wgu[l], s.fgu[l], R4[2], N, D, 2 * k.ff, s.act, k.ff,
+                               tc::EPI_SWIGLU_PAIRS, st)) != CSM_OK) return rc;
+    if ((rc = linear_rows(x, s.wd[l], s.fd[l], R4[3], s.act, k.ff, N, k.ff, D, s.h, D, tc::EPI_ADD_RESID, s.h, st)) != CSM_OK) return rc;
   }
   CU_TRY(cudaGetLastError());
   return CSM_OK;
@@ -971,9 +1025,12 @@ static int frame_tail_tc(csm_ctx* x, int B, cudaStream_t st) {
   const csm_config& c = x->cfg;
   const int D = c.backbone.dim, Dd = c.decoder.dim, V = c.audio_vocab, C = c.codebooks;
   int rc;
-  k_rmsnorm<<<B, 256, 0, st>>>(x->bb.h, D, x->bb.norm, D, c.norm_eps, x->dec_in, D); COUNT_LAUNCH();  // last_h
-  if ((rc = launch_gemm_tc(x->dec_in, D, B, D, x->c0_head, V, x->logits, x->Vp, tc::EPI_STORE, nullptr, st)) != CSM_OK) return rc;
-  if ((rc = launch_gemm_tc(x->dec_in, D, B, D, x->proj, Dd, x->dec.h, Dd, tc::EPI_STORE, nullptr, st)) != CSM_OK) return rc;
+  // last_h = backbone.norm(h) feeds the codebook-0 head and the projection (the fragment-major copy stacks
+  // [codebook0_head padded to Vf rows ; projection]: two row-group ranges of it)
+  if ((rc = norm_linear_rows(x, x->bb.h, x->bb.norm, c.norm_eps, x->dec_in, false, x->c0_head, x->f_head0, x->mega_Rh0, B, D, V,
+                             x->logits, x->Vp, tc::EPI_STORE, st)) != CSM_OK) return rc;
+  if ((rc = norm_linear_rows(x, x->bb.h, x->bb.norm, c.norm_eps, x->dec_in, true, x->proj, x->f_head0 + (size_t)x->Vf * D, x->mega_Rh0, B,
+                             D, Dd, x->dec.h, Dd, tc::EPI_STORE, st)) != CSM_OK) return rc;
   k_sample_step<<<B, SAMPLE_THREADS, 0, st>>>(x->d_params, x->logits, x->Vp, 0, V, C, x->proj_table, Dd,
                                               x->dec.h + (size_t)B * Dd); COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
@@ -981,9 +1038,9 @@ static int frame_tail_tc(csm_ctx* x, int B, cudaStream_t st) {
     const int N = (i == 1) ? 2 * B : B, pos0 = (i == 1) ? 0 : i;
     RowMeta m{nullptr, nullptr, nullptr, B, pos0};
     if ((rc = stack_pass_tc(x, x->dec, N, m, st)) != CSM_OK) return rc;
-    k_rmsnorm<<<B, 256, 0, st>>>(x->dec.h + (size_t)(N - B) * Dd, Dd, x->dec.norm, Dd, c.norm_eps, x->dec.xn, Dd); COUNT_LAUNCH();
-    if ((rc = launch_gemm_tc(x->dec.xn, Dd, B, Dd, x->head_t + (size_t)(i - 1) * x->Vp * Dd, V, x->logits, x->Vp, tc::EPI_STORE,
-                             nullptr, st)) != CSM_OK) return rc;
+    if ((rc = norm_linear_rows(x, x->dec.h + (size_t)(N - B) * Dd, x->dec.norm, c.norm_eps, x->dec.xn, false,
+                               x->head_t + (size_t)(i - 1) * x->Vp * Dd, x->f_heads + (size_t)(i - 1) * x->Vf * Dd, x->mega_Rh, B, Dd, V,
+                               x->logits, x->Vp, tc::EPI_STORE, st)) != CSM_OK) return rc;
     k_sample_step<<<B, SAMPLE_THREADS, 0, st>>>(x->d_params, x->logits, x->Vp, i, V, C, x->proj_table, Dd,
                                                 (i + 1 < C) ? x->dec.h : nullptr); COUNT_LAUNCH();
     CU_TRY(cudaGetLastError());
