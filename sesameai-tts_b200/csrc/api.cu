@@ -934,8 +934,11 @@ static void launch_skinny_t(const sk::Args& a, cudaStream_t st) {
 }
 // norm_scale != null: X holds the un-normalised rows and the kernel applies torchtune's RMSNorm on the fly
 static int launch_skinny(const bf16* Wf, int R, const bf16* X, long long ldx, int N, int K, int n_out, bf16* out, long long ldo,
-                         int epi, const bf16* resid, cudaStream_t st, const bf16* norm_scale = nullptr, float eps = 0.f) {
+                         int epi, const bf16* resid, cudaStream_t st, const bf16* norm_scale = nullptr, float eps = 0.f,
+                         const sk::Args* rope_kv = nullptr) {
   sk::Args a;
+  memset(&a, 0, sizeof(a));
+  if (rope_kv) a = *rope_kv;  // the RoPE / KV-append fields of the fused [q;k;v] projection
   a.Wf = Wf; a.R = R; a.K = K; a.n_out = n_out; a.G = (n_out + R - 1) / R; a.X = X; a.ldx = ldx; a.N = N; a.out = out; a.ldo = ldo;
   a.resid = resid ? resid : out; a.epi = epi; a.norm_scale = norm_scale; a.eps = eps;
   if (norm_scale) launch_skinny_t<true>(a, st);
@@ -977,10 +980,24 @@ static int stack_pass_tc(csm_ctx* x, StackDev& s, int N, const RowMeta& m, cudaS
   for (int l = 0; l < k.layers; ++l) {
     bf16* kc = s.kc + s.kv_layer_stride * l;
     bf16* vc = s.vc + s.kv_layer_stride * l;
-    if ((rc = norm_linear_rows(x, s.h, s.sa[l], eps, s.xn, false, s.wqkv[l], s.fqkv[l], R4[0], N, D, qkv_cols, s.qkv, qkv_cols,
-                               tc::EPI_STORE, st)) != CSM_OK) return rc;
-    k_rope_kv_rows<<<N, 256, 0, st>>>(s.qkv, s.rope, m.stream, m.pos, m.slot, m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.hd,
-                                      s.slots, s.q, kc, vc); COUNT_LAUNCH();
+    if (skinny_ok(x, s.fqkv[l], N, D)) {
+      // few rows: RMSNorm (up to 16 rows), [q;k;v], RoPE and the KV append in ONE skinny launch
+      sk::Args ra;
+      memset(&ra, 0, sizeof(ra));
+      ra.rope = s.rope; ra.row_stream = m.stream; ra.row_pos = m.pos; ra.row_slot = m.slot; ra.imp_B = m.imp_B; ra.imp_pos = m.imp_pos;
+      ra.heads = k.heads; ra.kv_heads = k.kv_heads; ra.hd = s.hd; ra.slots = s.slots; ra.k_cache = kc; ra.v_cache = vc;
+      const bool fuse_norm = N <= 16;
+      if (!fuse_norm) {
+        k_rmsnorm<<<N, 256, 0, st>>>(s.h, D, s.sa[l], D, eps, s.xn, D); COUNT_LAUNCH();
+      }
+      if ((rc = launch_skinny(s.fqkv[l], R4[0], fuse_norm ? s.h : s.xn, D, N, D, qkv_cols, s.q, 0, sk::EPI_ROPE_KV, nullptr, st,
+                              fuse_norm ? s.sa[l] : nullptr, eps, &ra)) != CSM_OK) return rc;
+    } else {
+      if ((rc = norm_linear_rows(x, s.h, s.sa[l], eps, s.xn, false, s.wqkv[l], s.fqkv[l], R4[0], N, D, qkv_cols, s.qkv, qkv_cols,
+                                 tc::EPI_STORE, st)) != CSM_OK) return rc;
+      k_rope_kv_rows<<<N, 256, 0, st>>>(s.qkv, s.rope, m.stream, m.pos, m.slot, m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.hd,
+                                        s.slots, s.q, kc, vc); COUNT_LAUNCH();
+    }
     {
       dim3 grid(N, k.heads);
       const size_t smem = (size_t)s.slots * sizeof(float);

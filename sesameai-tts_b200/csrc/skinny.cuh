@@ -11,7 +11,7 @@
 
 namespace sk {
 
-enum { EPI_STORE = 0, EPI_ADD_RESID = 1, EPI_SWIGLU_PAIRS = 2 };
+enum { EPI_STORE = 0, EPI_ADD_RESID = 1, EPI_SWIGLU_PAIRS = 2, EPI_ROPE_KV = 3 };
 
 struct Args {
   const bf16* Wf;  // fragment-major packed [G][K/32][R*64 bytes]
@@ -25,6 +25,12 @@ struct Args {
   int epi;
   const bf16* norm_scale;  // NORM: X rows are RMS-normalised on the fly, bf16(bf16(x * inv) * scale) like k_rmsnorm
   float eps;
+  // EPI_ROPE_KV (the fused [q;k;v] projection): same arithmetic as k_rope_kv_rows -- rotate q and k row pairs,
+  // q -> out [N, heads*hd], k / v -> the cache at the row's slot
+  const bf16* rope;
+  const int *row_stream, *row_pos, *row_slot;  // null: stream n % imp_B, position = slot = imp_pos + n / imp_B
+  int imp_B, imp_pos, heads, kv_heads, hd, slots;
+  bf16 *k_cache, *v_cache;
 };
 
 __device__ __forceinline__ float sk_sumsq8(const uint4& v) {
@@ -154,7 +160,29 @@ __global__ void __launch_bounds__(256) k_skinny(Args a) {
     if (r0 >= a.n_out) continue;
     y0 = rbf(y0);
     y1 = rbf(y1);
-    if (a.epi == EPI_SWIGLU_PAIRS) {
+    if (a.epi == EPI_ROPE_KV) {
+      const int hd = a.hd, qrows = a.heads * hd, krows = a.kv_heads * hd;
+      const int pos = a.row_stream ? a.row_pos[n] : a.imp_pos + n / a.imp_B;
+      const int slot = a.row_stream ? a.row_slot[n] : a.imp_pos + n / a.imp_B;
+      const int stream = a.row_stream ? a.row_stream[n] : n % a.imp_B;
+      float o0 = y0, o1 = y1;
+      if (r0 < qrows + krows) {
+        const __nv_bfloat162 cs = *reinterpret_cast<const __nv_bfloat162*>(a.rope + ((size_t)pos * (hd / 2) + ((r0 % hd) >> 1)) * 2);
+        const float c = __low2float(cs), sn = __high2float(cs);
+        o0 = rbf(__fsub_rn(__fmul_rn(y0, c), __fmul_rn(y1, sn)));
+        o1 = rbf(__fadd_rn(__fmul_rn(y1, c), __fmul_rn(y0, sn)));
+      }
+      const __nv_bfloat162 ov = __floats2bfloat162_rn(o0, o1);
+      if (r0 < qrows) {
+        *reinterpret_cast<__nv_bfloat162*>(a.out + (size_t)n * qrows + r0) = ov;
+      } else {
+        const bool isk = r0 < qrows + krows;
+        const int rr = r0 - (isk ? qrows : qrows + krows);
+        const int kvh = rr / hd, d = rr % hd;
+        bf16* dst = (isk ? a.k_cache : a.v_cache) + (((size_t)stream * a.kv_heads + kvh) * a.slots + slot) * hd + d;
+        *reinterpret_cast<__nv_bfloat162*>(dst) = ov;
+      }
+    } else if (a.epi == EPI_SWIGLU_PAIRS) {
       a.out[(size_t)n * a.ldo + (r0 >> 1)] = f2bf(silu_bf(y0) * y1);
     } else {
       bf16* o = a.out + (size_t)n * a.ldo + r0;
