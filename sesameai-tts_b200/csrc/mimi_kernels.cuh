@@ -151,7 +151,14 @@ __global__ void __launch_bounds__(256) k_tgemm(GemmArgs g) {
     for (int i = 0; i < 4; ++i) {
       float4 a = pa[i];
       if (elu) {
-        a.x = elu1(a.x); a.y = elu1(a.y); a.z = elu1(a.z); a.w = elu1(a.w);
+        // single-pass TF32 keeps 10 mantissa bits: exp(x) - 1 from the fast exponential (absolute error ~1e-7)
+        // is far inside that, and expm1f was the dominant cost of the skinny SEANet GEMMs
+        if (PASSES == 1) {
+          a.x = a.x > 0.f ? a.x : __expf(a.x) - 1.f; a.y = a.y > 0.f ? a.y : __expf(a.y) - 1.f;
+          a.z = a.z > 0.f ? a.z : __expf(a.z) - 1.f; a.w = a.w > 0.f ? a.w : __expf(a.w) - 1.f;
+        } else {
+          a.x = elu1(a.x); a.y = elu1(a.y); a.z = elu1(a.z); a.w = elu1(a.w);
+        }
       }
       *reinterpret_cast<float4*>(&As[lrow + 32 * i][lk]) = a;
     }
