@@ -702,18 +702,29 @@ __device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
         const int u = u0 + t * NCT + c.tid;
         if (u < total) v[t] = ldv4(u < qunits ? tq + u * 4 : tkv + (u - qunits) * 4);
       }
+      for (unsigned spin = 0;; ++spin) {  // both units together (see stage_x)
+        bool ok = true;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int u = u0 + t * NCT + c.tid;
+          if (u < total && !fresh4(v[t], tag)) {
+            v[t] = ldv4(u < qunits ? tq + u * 4 : tkv + (u - qunits) * 4);
+            ok = false;
+          }
+        }
+        if (ok) break;
+        if (spin > (1u << 22)) die(c.sync, 0x406);
+      }
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const int u = u0 + t * NCT + c.tid;
         if (u < total) {
           bf16* dst;
           if (u < qunits) {
-            v[t] = poll4(tq + u * 4, tag, v[t], c.sync);
             const int d4 = u & 31, hn = u >> 5, h = hn & (heads - 1), n = hn >> hsh;  // [n][head][128]
             dst = c.xs + A_QOFF + ((h >> gsh) * 8 + n * grp + (h & (grp - 1))) * A_QS + d4 * 4;
           } else {
             const int e = (u - qunits) * 4;  // element in [nb][2][krows]
-            v[t] = poll4(tkv + e, tag, v[t], c.sync);
             const int n = e >= 2 * krows ? 1 : 0, r = e - n * 2 * krows;
             const bool isv = r >= krows;
             const int rr = isv ? r - krows : r, kvh = rr >> 7, d = rr & 127, j = ph.pos0 + n;
@@ -860,12 +871,29 @@ __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
         if (norm) sc[t] = *reinterpret_cast<const uint2*>(ph.norm_scale + c.warp * slice + k4 * 4);
       }
     }
+    // all units of the batch are polled TOGETHER: one round trip per round for every stale unit, not one
+    // after the other (a lane that waits for data would otherwise pay a round trip per unit after it lands)
+    for (unsigned spin = 0;; ++spin) {
+      bool ok = true;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int e = e0 + t * 32 + c.lane;
+        if (e < tw) {
+          const int n = e >= nu ? 1 : 0, k4 = e - n * nu;
+          if (!fresh4(v[t], n ? tag1 : tag0)) {
+            v[t] = ldv4(txw + (size_t)n * ph.ldx + k4 * 4);
+            ok = false;
+          }
+        }
+      }
+      if (ok) break;
+      if (spin > (1u << 22)) die(c.sync, 0x405);
+    }
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int e = e0 + t * 32 + c.lane;
       if (e < tw) {
         const int n = e >= nu ? 1 : 0, k4 = e - n * nu;
-        v[t] = poll4(txw + (size_t)n * ph.ldx + k4 * 4, n ? tag1 : tag0, v[t], c.sync);
         if (norm) {
           const float s = sumsq4(v[t]);
           if (n) ss1 += s;
@@ -1091,11 +1119,23 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
       const int u = c.tid + t * NCT;
       if (u < nunits) w[t] = ldv4(ph.t_logits + u * 4);
     }
+    for (unsigned spin = 0;; ++spin) {  // all units together (see stage_x)
+      bool ok = true;
+#pragma unroll
+      for (int t = 0; t < MAXU; ++t) {
+        const int u = c.tid + t * NCT;
+        if (u < nunits && !fresh4(w[t], tag)) {
+          w[t] = ldv4(ph.t_logits + u * 4);
+          ok = false;
+        }
+      }
+      if (ok) break;
+      if (spin > (1u << 22)) die(c.sync, 0x407);
+    }
 #pragma unroll
     for (int t = 0; t < MAXU; ++t) {
       const int u = c.tid + t * NCT;
       if (u < nunits) {
-        w[t] = poll4(ph.t_logits + u * 4, tag, w[t], c.sync);
         const uint32_t ww[4] = {w[t].x, w[t].y, w[t].z, w[t].w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
