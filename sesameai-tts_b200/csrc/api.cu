@@ -80,6 +80,8 @@ struct csm_ctx {
   char* tagged_base;   // all tagged words live in [tagged_base, tagged_base + tagged_bytes): zeroed at create
   size_t tagged_bytes;
   bf16* proj_table;  // projection(audio_embeddings[cb*V + tok]) for cb < C-1: [(C-1)*V][Dd]
+  bf16* qkv_table;   // first decoder layer's RoPE'd [q;k;v] of proj_table rows (position cb + 1): [(C-1)*V][qkv cols]
+  bool qkv_table_ok;
   bf16* dec_in;   // [2B][D]
   bf16* logits;   // [B][Vp]
   int *row_stream, *row_pos, *row_slot;
@@ -127,8 +129,9 @@ static bool valid_cfg(const csm_config* c) {
          c->audio_vocab >= 2 && c->audio_vocab <= SAMPLE_MAXV && c->text_vocab >= 1 && c->max_seq_len >= c->codebooks;
 }
 
-static int mega_phase_count(const csm_config& c) {
-  return 1 + c.backbone.layers * 5 + 2 + (c.codebooks - 1) * (c.decoder.layers * 4 + 2);
+// (with the first-layer [q;k;v] table the steps after the first one have no QKV phase in layer 0)
+static int mega_phase_count(const csm_config& c, bool qkv_table = false) {
+  return 1 + c.backbone.layers * 5 + 2 + (c.codebooks - 1) * (c.decoder.layers * 4 + 2) - (qkv_table ? c.codebooks - 2 : 0);
 }
 
 static void carve_stack(Carver& cv, StackDev& s, const csm_stack_config& c, int slots, int streams, int rows) {
@@ -189,6 +192,7 @@ static size_t carve_all(csm_ctx* x, char* base) {
   x->f_head0 = cv.take<bf16>((size_t)(x->Vf + c.decoder.dim) * c.backbone.dim);
   x->f_heads = cv.take<bf16>((size_t)(c.codebooks - 1) * x->Vf * c.decoder.dim);
   x->proj_table = cv.take<bf16>((size_t)(c.codebooks - 1) * c.audio_vocab * c.decoder.dim);
+  x->qkv_table = cv.take<bf16>((size_t)(c.codebooks - 1) * c.audio_vocab * (c.decoder.heads + 2 * c.decoder.kv_heads) * (c.decoder.dim / c.decoder.heads));
   x->dec_in = cv.take<bf16>((size_t)2 * x->max_batch * c.backbone.dim);
   x->logits = cv.take<bf16>((size_t)x->max_batch * x->Vp);
   x->row_stream = cv.take<int>(x->max_rows);
@@ -412,6 +416,22 @@ __global__ void k_pack_frag(const bf16* __restrict__ src, int src_rows, int K, i
     reinterpret_cast<uint4*>(dst)[u] = v;
   }
 }
+// RoPE at one fixed position on rows of [q;k;v] (in place; same arithmetic as the EPI_ROPE_KV epilogue)
+__global__ void __launch_bounds__(256) k_rope_table(bf16* __restrict__ qkv, const bf16* __restrict__ rope, int pos, int heads,
+                                                    int kv_heads, int hd) {
+  const int total = (heads + 2 * kv_heads) * hd, rot = (heads + kv_heads) * hd;
+  bf16* row = qkv + (size_t)blockIdx.x * total;
+  for (int p = threadIdx.x; p < rot / 2; p += blockDim.x) {
+    const int r0 = 2 * p;
+    const __nv_bfloat162 in = *reinterpret_cast<const __nv_bfloat162*>(row + r0);
+    const float y0 = __low2float(in), y1 = __high2float(in);
+    const __nv_bfloat162 cs = *reinterpret_cast<const __nv_bfloat162*>(rope + ((size_t)pos * (hd / 2) + ((r0 % hd) >> 1)) * 2);
+    const float c = __low2float(cs), s = __high2float(cs);
+    *reinterpret_cast<__nv_bfloat162*>(row + r0) = __floats2bfloat162_rn(rbf(__fsub_rn(__fmul_rn(y0, c), __fmul_rn(y1, s))),
+                                                                         rbf(__fadd_rn(__fmul_rn(y1, c), __fmul_rn(y0, s))));
+  }
+}
+
 static void pack_frag(const bf16* src, int rows, int K, int R, bf16* dst, cudaStream_t st) {
   k_pack_frag<<<1024, 256, 0, st>>>(src, rows, K, R, dst); COUNT_LAUNCH();
 }
@@ -450,7 +470,8 @@ static mega::Phase gemv_phase_desc(MegaBuild& mb, const bf16* Wf, int rows, int 
 
 // src[n]: index of the phase that last wrote row n of the stack's residual stream (updated here)
 static void stack_phases(csm_ctx* x, StackDev& s, const int* R4, int l, int nb, int pos_mode, int pos0, bool fused_attn,
-                         MegaBuild& mb, int* src, int keep_mask = 0 /* bit 0 qkv, 1 o, 2 gate/up, 3 down: L2 evict-last */) {
+                         MegaBuild& mb, int* src, int keep_mask = 0 /* bit 0 qkv, 1 o, 2 gate/up, 3 down: L2 evict-last */,
+                         int qkv_from = -1 /* >= 0: q / k / v come from that (sample) phase's table gather, no QKV phase */) {
   const csm_stack_config& c = s.c;
   const float eps = x->cfg.norm_eps;
   bf16* kc = s.kc + s.kv_layer_stride * l;
@@ -466,8 +487,9 @@ static void stack_phases(csm_ctx* x, StackDev& s, const int* R4, int l, int nb, 
   q.x_src[0] = src[0]; q.x_src[1] = src[1];
   q.x_rs = s.rs_h;
   q.keep = keep_mask & 1;
-  const int iq = (int)mb.v.size();
-  mb.v.push_back(q);
+  int iq = (int)mb.v.size();
+  if (qkv_from >= 0) iq = qkv_from;
+  else mb.v.push_back(q);
   int iatt = -1;
   if (!fused_attn) {
     mega::Phase a;
@@ -512,6 +534,13 @@ static void build_mega_phases(csm_ctx* x, MegaBuild& mb) {
     memset(&s, 0, sizeof(s));
     s.type = mega::PH_SAMPLE; s.cb = cb; s.V = V; s.C = C; s.D = D; s.t_logits = x->t_logits; s.logits_src = logits_src;
     s.t_next = t_next; s.next_rs = x->dec.rs_h; s.next_table = x->proj_table; s.next_ld = Dd;
+    if (x->qkv_table_ok && cb >= 1 && t_next) {  // feeds step cb + 1 >= 2 (one row): first-layer q / k / v by gather
+      const StackDev& d = x->dec;
+      s.qkv_table = x->qkv_table; s.t_q = d.t_q; s.t_kv = d.t_kv; s.q_rs = d.rs_q; s.kv_rs = d.rs_kv;
+      s.kc = d.kc; s.vc = d.vc;  // layer 0
+      s.heads = d.c.heads; s.kv_heads = d.c.kv_heads; s.hd = d.hd; s.hd_shift = d.hd == 128 ? 7 : 6; s.slots = d.slots;
+      s.pos0 = cb + 1;
+    }
     return s;
   };
   mega::Phase e;
@@ -535,7 +564,8 @@ static void build_mega_phases(csm_ctx* x, MegaBuild& mb) {
   for (int i = 1; i < C; ++i) {
     const int nb = (i == 1) ? 2 : 1, pos0 = (i == 1) ? 0 : i;
     for (int l = 0; l < c.decoder.layers; ++l)
-      stack_phases(x, x->dec, x->mega_Rdec, l, nb, mega::POS_FIXED, pos0, true, mb, dsrc, (x->mega_keep >> (4 * (l & 7))) & 15);
+      stack_phases(x, x->dec, x->mega_Rdec, l, nb, mega::POS_FIXED, pos0, true, mb, dsrc, (x->mega_keep >> (4 * (l & 7))) & 15,
+                   (x->qkv_table_ok && i >= 2 && l == 0) ? dsrc[0] : -1);
     mega::Phase h = gemv_phase_desc(mb, x->f_heads + (size_t)(i - 1) * x->Vf * Dd, x->Vf, Dd, x->mega_Rh,
                                     x->dec.t_h + (size_t)(nb - 1) * Dd, Dd, 1, EPI_PLAIN, x->dec.norm, eps, x->t_logits, x->Vf);
     h.x_src[0] = h.x_src[1] = dsrc[nb - 1];
@@ -598,6 +628,24 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
   CU_TRY(cudaMemsetAsync(x->tagged_base, 0, x->tagged_bytes, st));  // stale tags of an earlier context must never match
   CU_TRY(cudaGetLastError());
   x->frag_ok = true;
+  // First decoder layer's [q;k;v] of every projection(embedding) row, RoPE applied at the position the row is used
+  // at (codebook cb's token enters the decoder at position cb + 1): rows of cb >= 1 replace a QKV phase per step.
+  x->qkv_table_ok = false;
+  if (!getenv("CSM_MEGA_NO_QKV_TABLE") && c.decoder.dim % 64 == 0 && (size_t)c.audio_vocab * Dd <= (size_t)x->max_rows * D &&
+      (c.decoder.heads + 2 * c.decoder.kv_heads) * x->dec.hd <= 3 * 4 * mega::NCT /* the sample phase gathers <= 3 units per thread */) {
+    const StackDev& d = x->dec;
+    const int qkv_cols = (d.c.heads + 2 * d.c.kv_heads) * d.hd, V = c.audio_vocab;
+    for (int cb = 1; cb + 1 < c.codebooks; ++cb) {
+      const bf16* rows = x->proj_table + (size_t)cb * V * Dd;
+      bf16* out = x->qkv_table + (size_t)cb * V * qkv_cols;
+      k_rmsnorm<<<V, 256, 0, st>>>(rows, Dd, d.sa[0], Dd, c.norm_eps, x->bb.xn, Dd); COUNT_LAUNCH();
+      int rc = launch_gemm_tc(x->bb.xn, Dd, V, Dd, d.wqkv[0], qkv_cols, out, qkv_cols, tc::EPI_STORE, nullptr, st);
+      if (rc != CSM_OK) return rc;
+      k_rope_table<<<V, 256, 0, st>>>(out, d.rope, cb + 1, d.c.heads, d.c.kv_heads, d.hd); COUNT_LAUNCH();
+    }
+    CU_TRY(cudaGetLastError());
+    x->qkv_table_ok = true;
+  }
 
   // Which depth-decoder matrices stay in L2 across the 31 codebook steps (see mega.cuh, producer_loop).
   // Measured (profiles/r1_mega_l2_keep.txt): no subset helps -- the stream phases are bound by the per-chunk
@@ -616,7 +664,7 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
   mb.rot = 0;
   build_mega_phases(x, mb);
   std::vector<mega::Phase>& v = mb.v;
-  if ((int)v.size() != mega_phase_count(x->cfg)) return set_err(CSM_ERR_ARG, "internal: phase count mismatch");
+  if ((int)v.size() != mega_phase_count(x->cfg, x->qkv_table_ok)) return set_err(CSM_ERR_ARG, "internal: phase count mismatch");
   memset(&x->pf_table, 0, sizeof(x->pf_table));
   for (const mega::Phase& ph : v) {
     if (ph.type != mega::PH_GEMV) continue;

@@ -91,10 +91,15 @@ struct __align__(16) Phase {
   int next_ld;             // SAMPLE: row length of the gather table feeding t_next
   uint32_t* t_next;        // SAMPLE: next depth-decoder input row
   const bf16* next_table;  // SAMPLE: projection(embedding) table [(codebooks-1)*V][next_ld]
+  // SAMPLE: [q;k;v] of the first decoder layer for the sampled token, RoPE applied at position cb + 1
+  // (table [(codebooks-1)*V][(heads + 2 kv_heads) * hd]); the phase then also hands q / k / v to the next step
+  // (t_q, t_kv, kc / vc at slot pos0) and that step has no QKV phase in its first layer.  Null: no table.
+  const bf16* qkv_table;
   const bf16 *audio_emb, *text_emb;
   // distance in words between the REP copies of the tagged vectors (0: single copy)
   int x_rs, out_rs, out2_rs, q_rs, kv_rs, next_rs;
   int keep;  // this matrix is loaded with the L2 evict-last policy
+  int pad_[2];
 };
 static_assert(sizeof(Phase) % 16 == 0, "Phase must be copyable in 16-byte units");
 
@@ -1170,6 +1175,11 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
       if (ph.t_next) {
         const char* row = reinterpret_cast<const char*>(ph.next_table + ((size_t)besti + (size_t)cb * V) * ph.next_ld);
         for (int o = 0; o < ph.next_ld * 2; o += 128) prefetch_l2(row + o);
+        if (ph.qkv_table) {
+          const int qb = (ph.heads + 2 * ph.kv_heads) * ph.hd * 2;  // bytes of a [q;k;v] row
+          const char* qr = reinterpret_cast<const char*>(ph.qkv_table) + ((size_t)besti + (size_t)cb * V) * qb;
+          for (int o = 0; o < qb; o += 128) prefetch_l2(qr + o);
+        }
       }
     }
     csync<NCT, CBAR>();
@@ -1199,14 +1209,50 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
   if (P->forced) tok = P->forced[cb];
   if (c.tid == 0) P->out[cb] = tok;
   if (ph.t_next) {
-    // next depth-decoder input: projection(embed_audio(cb, tok)) read from the table built at setup
+    // next depth-decoder input: projection(embed_audio(cb, tok)) read from the table built at setup, and -- when
+    // the [q;k;v] table exists -- the first layer's q / k / v of the next step, a pure function of (codebook,
+    // token) too: one more row gather instead of a GEMV phase.  All loads of both rows go out before any store
+    // (the rows are cold in HBM: one latency, not two).
     const int ld = ph.next_ld;
     const bf16* row = ph.next_table + ((size_t)tok + (size_t)cb * V) * ld;
     const uint32_t tag = c.tag;
-    for (int d4 = c.tid; d4 < ld / 4; d4 += NCT) {
-      const uint2 v = *reinterpret_cast<const uint2*>(row + d4 * 4);
-      rep_st4(ph.t_next + d4 * 4, ph.next_rs, make_uint4(tword_raw(tag, v.x), tword_raw(tag, v.x >> 16), tword_raw(tag, v.y),
-                                                          tword_raw(tag, v.y >> 16)));
+    const int hd = ph.hd, qrows = ph.heads * hd, krows = ph.kv_heads * hd;
+    const bf16* qrow = ph.qkv_table ? ph.qkv_table + ((size_t)tok + (size_t)cb * V) * (qrows + 2 * krows) : nullptr;
+    const int nh = ld / 4, nq = qrow ? (qrows + 2 * krows) / 4 : 0;  // 4-element units
+    constexpr int MAXH = 2, MAXQ = 3;  // rows up to 2048 / 3072 elements
+    uint2 hv[MAXH], qv[MAXQ];
+#pragma unroll
+    for (int t = 0; t < MAXH; ++t)
+      if (c.tid + t * NCT < nh) hv[t] = *reinterpret_cast<const uint2*>(row + (c.tid + t * NCT) * 4);
+#pragma unroll
+    for (int t = 0; t < MAXQ; ++t)
+      if (c.tid + t * NCT < nq) qv[t] = *reinterpret_cast<const uint2*>(qrow + (c.tid + t * NCT) * 4);
+#pragma unroll
+    for (int t = 0; t < MAXH; ++t) {
+      const int d4 = c.tid + t * NCT;
+      if (d4 < nh)
+        rep_st4(ph.t_next + d4 * 4, ph.next_rs, make_uint4(tword_raw(tag, hv[t].x), tword_raw(tag, hv[t].x >> 16),
+                                                            tword_raw(tag, hv[t].y), tword_raw(tag, hv[t].y >> 16)));
+    }
+    // q and the new k / v go out as tagged words for the attention of the next phase, k / v also as plain rows
+    // into the cache (slot pos0) for the later steps
+#pragma unroll
+    for (int t = 0; t < MAXQ; ++t) {
+      const int u = c.tid + t * NCT;
+      if (u < nq) {
+        const int e = u * 4;
+        const uint2 v = qv[t];
+        const uint4 w = make_uint4(tword_raw(tag, v.x), tword_raw(tag, v.x >> 16), tword_raw(tag, v.y), tword_raw(tag, v.y >> 16));
+        if (e < qrows) {
+          rep_st4(ph.t_q + e, ph.q_rs, w);
+        } else {
+          const bool isk = e < qrows + krows;
+          const int rr = e - (isk ? qrows : qrows + krows);
+          rep_st4(ph.t_kv + (isk ? 0 : krows) + rr, ph.kv_rs, w);
+          bf16* dst = (isk ? ph.kc : ph.vc) + ((size_t)(rr >> ph.hd_shift) * ph.slots + ph.pos0) * hd + (rr & (hd - 1));
+          *reinterpret_cast<uint2*>(dst) = v;
+        }
+      }
     }
   }
 }

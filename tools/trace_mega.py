@@ -36,9 +36,10 @@ kinds = ["embed"]
 for l in range(16):
     kinds += ["bb.qkv", "bb.attn", "bb.o", "bb.gu", "bb.down"]
 kinds += ["c0head", "sample"]
+qkv_table = nph == 641 - 30  # the first layer's q / k / v of steps >= 2 come from the table gather of the sample phase
 for i in range(1, 32):
     for l in range(4):
-        kinds += ["d.qkv", "d.o+attn", "d.gu", "d.down"]
+        kinds += (["d.o+attn", "d.gu", "d.down"] if (qkv_table and i >= 2 and l == 0) else ["d.qkv", "d.o+attn", "d.gu", "d.down"])
     kinds += ["d.head", "sample"]
 assert len(kinds) == nph, (len(kinds), nph)
 import numpy as np
