@@ -1,24 +1,29 @@
 // Persistent decode megakernel: one audio frame (backbone step + codebook-0 sample + 31 depth-
-// decoder steps, ~640 dependent phases) in ONE launch, for one stream.
+// decoder steps, ~610 dependent phases) in ONE launch, for one stream.
 //
-// Why: at batch 1 a frame is ~640 tiny dependent GEMVs (0.3-10 us of HBM time each); launched one by
+// Why: at batch 1 a frame is ~610 tiny dependent GEMVs (0.3-10 us of HBM time each); launched one by
 // one, or separated by grid barriers, they are latency bound.  Here one CTA per SM stays resident for
 // the whole frame and three things keep the dependency chain short:
-//   * WEIGHT STREAM.  Every warp streams ITS share of every weight matrix, in consumption order,
-//     through a private shared-memory ring with bulk async copies (cp.async.bulk + mbarrier
-//     complete_tx).  Weight addresses are data independent, so the stream runs AHEAD of the
-//     dependency chain: 148 SMs x 128 KB of weights stay in flight while activations resolve.  The
-//     fetch schedule is a compact table in kernel-parameter (constant) space.
+//   * WEIGHT STREAM.  Every consumer warp owns a shared-memory ring of 4 x 4 KB slots; a ninth,
+//     producer warp walks the frame's schedule (a table in kernel-parameter space) and issues every
+//     warp's next chunk with a bulk async copy (cp.async.bulk + mbarrier complete_tx) as soon as the
+//     slot it goes to has been drained, pulling chunks further ahead into L2 while it waits.  Weight
+//     addresses are data independent, so the stream runs AHEAD of the dependency chain: 148 SMs x
+//     128 KB of weights are in flight or landed while activations resolve.
 //   * FRAGMENT-MAJOR WEIGHTS + TENSOR-CORE DOT.  The matrices are re-packed once at setup into
 //     [row group of R=8/16][32-wide k block][lane][16 B] order: a chunk is one contiguous bulk copy,
-//     each lane reads its mma.m16n8k16 A fragment with one conflict-free LDS.128, and the dot products
-//     of a 16-row group with the (<= 2) activation rows are HMMA instructions whose accumulator
-//     already holds finished sums -- no unpack/FMA chains and no shuffle reductions.  All 8 warps of a
-//     CTA split the K extent of a row group, partial sums meet in shared memory in a fixed order.
+//     every lane reads a complete mma.m16n8k16 operand with one conflict-free LDS.128 (16-row groups:
+//     the weights are the A operand, pre-packed (a0..a3) quads; 8-row groups: the B operand), and the
+//     dot products with the (<= 2) activation rows are HMMA instructions whose accumulator already
+//     holds finished sums -- no unpack/FMA chains, no register shuffles, no shuffle reductions.  All 8
+//     warps of a CTA split the K extent of a row group, partial sums meet in shared memory in a fixed
+//     order.
 //   * TAGGED ACTIVATIONS INSTEAD OF GRID BARRIERS.  Every vector one phase hands to the next travels
 //     as 32-bit words {tag16 | bf16}; the tag names the producing phase and frame.  A consumer
 //     re-loads a word until its tag is the expected one: the data is its own ready flag, a phase
 //     boundary costs one L2 round trip, and CTAs without work in a phase run ahead.
+// Token-dependent linear maps are tables: projection(embedding) and the first decoder layer's RoPE'd
+// [q;k;v] of it are gathered by the sampling phase instead of being computed by GEMV phases.
 // Every spin has a trip-count cap and traps instead of hanging the GPU.
 #pragma once
 #include "lm_kernels.cuh"
