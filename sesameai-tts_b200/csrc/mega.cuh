@@ -1079,7 +1079,7 @@ __device__ __forceinline__ void embed_phase(const Phase& ph, Ctx& c) {
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int c0 = 0; c0 <= ph.C; c0 += 11) {  // 11 independent gathers in flight, summed in column order
+  for (int c0 = 0; c0 <= ph.C; c0 += 11) {  // 11 independent gathers in flight, summed in column order (17 spill: slower overall)
     uint4 v[11];
     bool on[11];
 #pragma unroll
@@ -1176,15 +1176,17 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
       c.scratch[c.warp] = best;
       c.iscratch[c.warp] = besti;
       c.iscratch[NW + c.warp] = bestn;
-      // speculation: start pulling this warp's candidate row of the gather table towards L2
-      if (ph.t_next) {
-        const char* row = reinterpret_cast<const char*>(ph.next_table + ((size_t)besti + (size_t)cb * V) * ph.next_ld);
-        for (int o = 0; o < ph.next_ld * 2; o += 128) prefetch_l2(row + o);
-        if (ph.qkv_table) {
-          const int qb = (ph.heads + 2 * ph.kv_heads) * ph.hd * 2;  // bytes of a [q;k;v] row
-          const char* qr = reinterpret_cast<const char*>(ph.qkv_table) + ((size_t)besti + (size_t)cb * V) * qb;
-          for (int o = 0; o < qb; o += 128) prefetch_l2(qr + o);
-        }
+    }
+    // speculation: start pulling this warp's candidate rows of the gather tables towards L2, one 128-byte
+    // line per lane (every lane holds the warp's arg-max after the butterfly)
+    if (ph.t_next) {
+      const int hb = ph.next_ld * 2;  // bytes of a projection(embedding) row
+      const char* row = reinterpret_cast<const char*>(ph.next_table) + ((size_t)besti + (size_t)cb * V) * hb;
+      for (int o = c.lane * 128; o < hb; o += 32 * 128) prefetch_l2(row + o);
+      if (ph.qkv_table) {
+        const int qb = (ph.heads + 2 * ph.kv_heads) * ph.hd * 2;  // bytes of a [q;k;v] row
+        const char* qr = reinterpret_cast<const char*>(ph.qkv_table) + ((size_t)besti + (size_t)cb * V) * qb;
+        for (int o = c.lane * 128; o < qb; o += 32 * 128) prefetch_l2(qr + o);
       }
     }
     csync<NCT, CBAR>();
