@@ -198,11 +198,24 @@ int32_t mimi_decode(mimi_ctx *ctx, const int64_t *codes, int32_t B, int32_t K, i
 int32_t mimi_encode(mimi_ctx *ctx, const float *wav, int32_t B, int64_t L, int32_t K, int64_t *codes, void *stream);
 void mimi_destroy(mimi_ctx *ctx);
 
-/* Profiling aid: dev uint64 [n_phases][8] buffer that CTA 0 of the decode megakernel fills with
- * %globaltimer stamps (phase start, work done, CTA synced, grid barrier passed, 4 phase-specific
- * marks); NULL disables.
- * Returns the number of phases (0 if the megakernel is unavailable). */
+/* Profiling aid: dev uint64 [n_ctas][n_phases][16] buffer that thread 0 of every CTA of the decode
+ * megakernel fills (4 %globaltimer stamps: phase start, inputs staged, partial sums done, end; 12
+ * clock64 marks); NULL disables.  Returns the number of phases (0 if the megakernel is unavailable). */
 int32_t csm_debug_set_trace(csm_ctx *ctx, void *dev_buffer);
+
+/* Host-only (no GPU needed): the megakernel's phase table for a configuration, with pointers taken
+ * relative to an imaginary workspace.  tests/ use it to check the invariants of the tagged hand-off
+ * statically: every consumed vector names the phase that wrote it last, and no vector is rewritten
+ * sooner than two phases after it was written. */
+typedef struct csm_phase_info {
+  int32_t type;            /* 0 GEMV, 1 embed, 2 backbone attention, 3 sample */
+  int32_t epi;             /* GEMV: 0 plain, 1 + residual (in place), 2 SwiGLU, 3 RoPE + KV append */
+  int32_t nb, K, rows, R, G, rot, ldx, ldo, split_row, attn_prologue, has_qkv_table;
+  int32_t x_src[2], resid_src[2], q_src, logits_src;
+  uint64_t t_x, t_out, t_out2, t_q, t_kv, t_logits, t_next; /* byte offsets of the tagged vectors (0: unused) */
+} csm_phase_info;
+int32_t csm_debug_phase_table(const csm_config *cfg, int32_t n_ctas, int32_t with_qkv_table, csm_phase_info *out,
+                              int32_t max_phases);
 
 /* ---- single-kernel entry points for unit parity tests (tests/ only) ------------------------ */
 

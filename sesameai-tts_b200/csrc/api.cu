@@ -918,6 +918,53 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
   return CSM_OK;
 }
 
+extern "C" int32_t csm_debug_phase_table(const csm_config* cfg, int32_t n_ctas, int32_t with_qkv_table, csm_phase_info* out,
+                                         int32_t max_phases) {
+  if (!valid_cfg(cfg) || n_ctas < 1 || !out) return set_err(CSM_ERR_ARG, "bad phase_table arguments");
+  csm_ctx x;
+  x.cfg = *cfg;
+  x.max_batch = 1;
+  char* const base = reinterpret_cast<char*>((uintptr_t)1 << 32);  // imaginary workspace: pointers are only compared
+  carve_all(&x, base);
+  for (StackDev* s : {&x.bb, &x.dec}) {
+    s->wo.assign(s->c.layers, nullptr); s->wd.assign(s->c.layers, nullptr);
+    s->sa.assign(s->c.layers, reinterpret_cast<const bf16*>(base)); s->mlp.assign(s->c.layers, reinterpret_cast<const bf16*>(base));
+    s->norm = reinterpret_cast<const bf16*>(base); s->rope = nullptr;
+  }
+  auto pick_stack = [&](const StackDev& s, int* r4) {
+    r4[0] = mega_pick_R((s.c.heads + 2 * s.c.kv_heads) * s.hd, n_ctas);
+    r4[1] = mega_pick_R(s.c.dim, n_ctas);
+    r4[2] = mega_pick_R(2 * s.c.ff, n_ctas);
+    r4[3] = mega_pick_R(s.c.dim, n_ctas);
+  };
+  pick_stack(x.bb, x.mega_Rbb);
+  pick_stack(x.dec, x.mega_Rdec);
+  x.mega_Rh0 = mega_pick_R(x.Vf + cfg->decoder.dim, n_ctas);
+  x.mega_Rh = mega_pick_R(x.Vf, n_ctas);
+  x.mega_keep = 0;
+  x.qkv_table_ok = with_qkv_table != 0;
+  x.text_emb = x.audio_emb = nullptr;
+  MegaBuild mb;
+  mb.ncta = n_ctas;
+  mb.rot = 0;
+  build_mega_phases(&x, mb);
+  const int n = (int)mb.v.size();
+  if (n != mega_phase_count(*cfg, x.qkv_table_ok)) return set_err(CSM_ERR_ARG, "internal: phase count mismatch");
+  auto off = [&](const void* p) { return p ? (uint64_t)(reinterpret_cast<const char*>(p) - base) : (uint64_t)0; };
+  for (int i = 0; i < n && i < max_phases; ++i) {
+    const mega::Phase& ph = mb.v[i];
+    csm_phase_info& o = out[i];
+    memset(&o, 0, sizeof(o));
+    o.type = ph.type; o.epi = ph.epi; o.nb = ph.nb; o.K = ph.K; o.rows = ph.rows; o.R = ph.R; o.G = ph.G; o.rot = ph.rot;
+    o.ldx = ph.ldx; o.ldo = ph.ldo; o.split_row = ph.split_row; o.attn_prologue = ph.attn_prologue; o.has_qkv_table = ph.qkv_table != nullptr;
+    o.x_src[0] = ph.x_src[0]; o.x_src[1] = ph.x_src[1]; o.resid_src[0] = ph.resid_src[0]; o.resid_src[1] = ph.resid_src[1];
+    o.q_src = ph.q_src; o.logits_src = ph.logits_src;
+    o.t_x = off(ph.t_x); o.t_out = off(ph.t_out); o.t_out2 = off(ph.t_out2); o.t_q = off(ph.t_q); o.t_kv = off(ph.t_kv);
+    o.t_logits = off(ph.t_logits); o.t_next = off(ph.t_next);
+  }
+  return n;
+}
+
 extern "C" int32_t csm_debug_set_trace(csm_ctx* x, void* dev_buffer) {
   if (!x) return set_err(CSM_ERR_ARG, "null ctx");
   x->trace = (unsigned long long*)dev_buffer;

@@ -35,6 +35,14 @@ class Config(C.Structure):
     ]
 
 
+class PhaseInfo(C.Structure):
+    """csm_phase_info (include/csm_b200.h): one row of the megakernel's phase table, host-only debug view."""
+    _fields_ = ([(n, C.c_int32) for n in ("type", "epi", "nb", "K", "rows", "R", "G", "rot", "ldx", "ldo", "split_row",
+                                           "attn_prologue", "has_qkv_table")]
+                + [("x_src", C.c_int32 * 2), ("resid_src", C.c_int32 * 2), ("q_src", C.c_int32), ("logits_src", C.c_int32)]
+                + [(n, C.c_uint64) for n in ("t_x", "t_out", "t_out2", "t_q", "t_kv", "t_logits", "t_next")])
+
+
 class LayerWeights(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in
                 ("q_proj", "k_proj", "v_proj", "output_proj", "w1", "w2", "w3", "sa_norm", "mlp_norm")]
@@ -100,6 +108,7 @@ PROTOTYPES = {
     "mimi_encode": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "mimi_destroy": (None, [C.c_void_p]),
     "csm_debug_set_trace": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "csm_debug_phase_table": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "csm_k_sample_topk": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p,
                                       C.c_void_p]),
     "csm_k_embed_frames": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,

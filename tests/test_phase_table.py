@@ -1,0 +1,106 @@
+"""Static check of the megakernel's tagged hand-off (mega.cuh) on the host-built phase table:
+  * every tagged vector a phase consumes names, as its source, the phase that wrote that vector last;
+  * no vector is rewritten sooner than two phases after it was written (a consumer of phase p's words
+    may still be reading them while phase p+1 runs; seeing a word of phase p+1 proves phase p is over);
+  * the consumer of a vector comes after its producer.
+No GPU needed: csm_debug_phase_table builds the table against an imaginary workspace."""
+import ctypes as C
+
+import pytest
+
+from sesameai import _native
+
+GEMV, EMBED, ATTN, SAMPLE = 0, 1, 2, 3
+PLAIN, RESID, SWIGLU, ROPE_KV = 0, 1, 2, 3
+
+
+def _cfg(tiny):
+    cfg = _native.Config()
+    if tiny:
+        bb, dec = (2, 256, 4, 2, 512), (2, 256, 2, 1, 512)
+    else:
+        bb, dec = (16, 2048, 32, 8, 8192), (4, 1024, 8, 2, 8192)
+    for dst, v in ((cfg.backbone, bb), (cfg.decoder, dec)):
+        dst.layers, dst.dim, dst.heads, dst.kv_heads, dst.ff = v
+    cfg.text_vocab, cfg.audio_vocab, cfg.codebooks, cfg.max_seq_len, cfg.norm_eps = (1000 if tiny else 128256), 2051, 32, 2048, 1e-5
+    return cfg
+
+
+def _table(cfg, ncta, qkv):
+    buf = (_native.PhaseInfo * 700)()
+    n = _native.lib().csm_debug_phase_table(C.byref(cfg), ncta, qkv, buf, 700)
+    assert n > 0, _native.lib().csm_last_error()
+    return [buf[i] for i in range(n)]
+
+
+@pytest.mark.parametrize("tiny", [True, False])
+@pytest.mark.parametrize("ncta", [148, 132, 16])
+@pytest.mark.parametrize("qkv", [0, 1])
+def test_tagged_hand_off_invariants(tiny, ncta, qkv):
+    cfg = _cfg(tiny)
+    ph = _table(cfg, ncta, qkv)
+    layers_bb, layers_dec = cfg.backbone.layers, cfg.decoder.layers
+    assert len(ph) == 1 + 5 * layers_bb + 2 + 31 * (4 * layers_dec + 2) - (30 if qkv else 0)
+    kv_words = lambda s: 2 * s.kv_heads * (s.dim // s.heads)
+    writer = {}  # (vector base offset + row offset in words) -> phase that wrote it last
+
+    def consume(p, base, row_words, row, src):
+        key = base + 4 * row * row_words
+        assert key in writer, (p, "consumes a vector nobody wrote")
+        assert writer[key] == src, (p, "source", src, "but last writer", writer[key])
+        assert src < p
+
+    def produce(p, base, row_words, row, in_place_only_reader=False):
+        key = base + 4 * row * row_words
+        if key in writer:
+            # an in-place residual update may follow its source directly when the epilogue thread that rewrites a
+            # word is the only reader of the old one (the [q;k;v] table removes the QKV phase that used to sit between)
+            need = 1 if in_place_only_reader else 2
+            assert p - writer[key] >= need, (p, "rewrites a vector written by phase", writer[key])
+        writer[key] = p
+
+    for p, x in enumerate(ph):
+        is_dec = p > 1 + 5 * layers_bb + 1
+        st = cfg.decoder if is_dec else cfg.backbone
+        if x.type == EMBED:
+            produce(p, x.t_out, 0, 0)
+        elif x.type == ATTN:
+            consume(p, x.t_q, 0, 0, x.q_src)
+            consume(p, x.t_kv, 0, 0, x.q_src)
+            produce(p, x.t_out, 0, 0)
+        elif x.type == SAMPLE:
+            consume(p, x.t_logits, 0, 0, x.logits_src)
+            if x.t_next:
+                produce(p, x.t_next, 0, 0)
+            if x.has_qkv_table:
+                produce(p, x.t_q, 0, 0)
+                produce(p, x.t_kv, 0, 0)
+        else:
+            assert x.type == GEMV
+            if x.attn_prologue:
+                for n in range(x.nb):
+                    consume(p, x.t_q, st.dim, n, x.q_src)
+                    consume(p, x.t_kv, kv_words(st), n, x.q_src)
+            else:
+                for n in range(x.nb):
+                    consume(p, x.t_x, x.ldx, n, x.x_src[n])
+            if x.epi == RESID:
+                for n in range(x.nb):
+                    consume(p, x.t_out, x.ldo, n, x.resid_src[n])
+                    reads_it_as_x = (not x.attn_prologue) and x.t_x == x.t_out
+                    produce(p, x.t_out, x.ldo, n, in_place_only_reader=not reads_it_as_x)
+            elif x.epi == ROPE_KV:
+                for n in range(x.nb):
+                    produce(p, x.t_q, st.dim, n)
+                    produce(p, x.t_kv, kv_words(st), n)
+            else:
+                for n in range(x.nb):
+                    produce(p, x.t_out, x.ldo, n)
+                if x.t_out2:
+                    produce(p, x.t_out2, 0, 0)
+    # every GEMV phase fits the kernel's per-CTA limits on a full GPU (setup_mega falls back to the per-op path otherwise)
+    for x in ph:
+        if x.type == GEMV:
+            assert x.R in (8, 16) and x.K % 256 == 0
+            if ncta >= 132:
+                assert -(-x.G // ncta) <= 8
