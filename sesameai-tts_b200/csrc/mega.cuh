@@ -242,16 +242,6 @@ __device__ __forceinline__ uint4 poll4(const uint32_t* p, uint32_t tag, uint4 v,
   }
   return v;
 }
-// two adjacent units at once: both re-loads are in flight together (no second round trip)
-__device__ __forceinline__ void poll8(const uint32_t* p, uint32_t tag, uint4& lo, uint4& hi, Sync* sync) {
-  for (unsigned spin = 0;; ++spin) {
-    const bool f0 = fresh4(lo, tag), f1 = fresh4(hi, tag);
-    if (f0 && f1) return;
-    if (spin > (1u << 22)) die(sync, 0x404);
-    if (!f0) lo = ldv4(p);
-    if (!f1) hi = ldv4(p + 4);
-  }
-}
 __device__ __forceinline__ uint2 poll2(const uint32_t* p, uint32_t tag, Sync* sync) {
   uint2 v = ldv2(p);
   for (unsigned spin = 0; (((v.x ^ tag) | (v.y ^ tag)) & 0xffff0000u) != 0; ++spin) {
