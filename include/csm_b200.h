@@ -102,6 +102,15 @@ int32_t csm_reset_caches(csm_ctx *ctx);
 /* Backbone positions currently held in the KV cache (torchtune KVCache.size). */
 int32_t csm_cache_len(const csm_ctx *ctx);
 
+/* Device-side errors of earlier stream-ordered calls, WITHOUT a CUDA call (the kernels mirror the code into
+ * mapped host memory): 0 = none; 0x100-0x4ff = a wait inside the decode megakernel gave up (the launch
+ * drained, its tokens are garbage, the context is still usable: reset and retry -- tts_service.py:500-514
+ * retries on any exception); 0x801 = token id outside its embedding table (the reference raises IndexError,
+ * sesameai/models.py:190-203); 0x802 = teacher-forced id out of range; 0x803 = input_pos outside the RoPE
+ * table or different from the cache position (sesameai/models.py:154,158: mask row and cache slot coincide
+ * only for sequential use).  Meaningful after the stream has been synchronised; ``clear`` resets it. */
+int32_t csm_check_error(csm_ctx *ctx, int32_t clear);
+
 /* ---- the hot path -------------------------------------------------------------------------- */
 
 /* Optional per-call extras; zero-initialise for the plain reference behaviour. */

@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <new>
 #include <vector>
@@ -27,16 +28,16 @@ static int set_err(int code, const char* fmt, const char* a = "", const char* b 
   } while (0)
 
 // kernels launched by this library in this process (graph replays add their node count)
-static unsigned long long g_launches = 0;
-#define COUNT_LAUNCH() (++g_launches)
-extern "C" uint64_t csm_launch_count(void) { return g_launches; }
+static std::atomic<unsigned long long> g_launches{0};
+#define COUNT_LAUNCH() (g_launches.fetch_add(1, std::memory_order_relaxed))
+extern "C" uint64_t csm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const bf16* W, int n_out, bf16* out, long long ldo,
                           int epi, const bf16* resid, cudaStream_t st);
 
 // shared with mimi_api.cu
 int csm_set_error(int code, const char* msg) { return set_err(code, "%s", msg); }
-void csm_count_launches(unsigned long long n) { g_launches += n; }
+void csm_count_launches(unsigned long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 extern "C" int32_t csm_abi_version(void) { return CSM_B200_ABI_VERSION; }
 extern "C" const char* csm_last_error(void) { return g_err; }
@@ -91,7 +92,8 @@ struct csm_ctx {
   cudaStream_t cap_stream;
   // persistent decode megakernel (batch 1)
   mega::Phase* d_phases;
-  mega::Sync* d_sync;
+  mega::Sync* d_sync;       // device status word (frame counter + sticky error), always initialised
+  unsigned int* h_error;    // mapped host mirror of the error word (owned by the ctx)
   int n_phases, mega_grid;
   bool mega_ok;
   bool frag_ok;  // the fragment-major packed matrices exist (setup_mega): the skinny batched-decode GEMM can run
@@ -233,17 +235,28 @@ static cudaError_t gemv_attrs() {
   if ((e = gemv_attr<4, EPI, NORM>()) != cudaSuccess) return e;
   return gemv_attr<8, EPI, NORM>();
 }
-// opt every GEMV instantiation into > 48 KB of dynamic shared memory (once per process)
+// Function attributes are per device: remember which devices have been opted in.
+static bool device_done(std::atomic<unsigned long long>& mask, bool mark) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;  // unknown: set the attribute again
+  const unsigned long long bit = 1ull << dev;
+  if (mark) {
+    mask.fetch_or(bit);
+    return true;
+  }
+  return (mask.load() & bit) != 0;
+}
+// opt every GEMV instantiation into > 48 KB of dynamic shared memory (once per device)
 static cudaError_t init_kernel_attrs() {
-  static bool done = false;
-  if (done) return cudaSuccess;
+  static std::atomic<unsigned long long> done{0};
+  if (device_done(done, false)) return cudaSuccess;
   cudaError_t e;
   if ((e = gemv_attrs<EPI_PLAIN, false>()) != cudaSuccess) return e;
   if ((e = gemv_attrs<EPI_PLAIN, true>()) != cudaSuccess) return e;
   if ((e = gemv_attrs<EPI_RESID, false>()) != cudaSuccess) return e;
   if ((e = gemv_attrs<EPI_SWIGLU, true>()) != cudaSuccess) return e;
   if ((e = gemv_attrs<EPI_ROPE_KV, true>()) != cudaSuccess) return e;
-  done = true;
+  device_done(done, true);
   return cudaSuccess;
 }
 
@@ -323,7 +336,8 @@ static cudaError_t backbone_pass(csm_ctx* x, int B, int chunk, cudaStream_t st) 
   const csm_config& c = x->cfg;
   const int N = B * chunk;
   k_embed_pass<<<N, 256, 0, st>>>(x->d_params, x->text_emb, x->audio_emb, c.codebooks, c.audio_vocab, c.backbone.dim,
-                                  chunk, x->bb.h, x->row_stream, x->row_pos, x->row_slot); COUNT_LAUNCH();
+                                  chunk, x->bb.h, x->row_stream, x->row_pos, x->row_slot, c.text_vocab, x->bb.rope_len,
+                                  x->d_sync); COUNT_LAUNCH();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   RowMeta m{x->row_stream, x->row_pos, x->row_slot, 0, 0};
@@ -348,7 +362,7 @@ static cudaError_t frame_tail(csm_ctx* x, int B, cudaStream_t st) {
   a.W = x->c0_head; a.rows = V; a.K = D; a.x = x->dec_in; a.ldx = D; a.N = B; a.out = x->logits; a.ldo = x->Vp;
   if ((e = launch_gemv<EPI_PLAIN, false>(a, st)) != cudaSuccess) return e;
   k_sample_step<<<B, SAMPLE_THREADS, 0, st>>>(x->d_params, x->logits, x->Vp, 0, V, C, x->audio_emb, D,
-                                              x->dec_in + (size_t)B * D); COUNT_LAUNCH();
+                                              x->dec_in + (size_t)B * D, x->d_sync); COUNT_LAUNCH();
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   for (int i = 1; i < C; ++i) {
     const int N = (i == 1) ? 2 * B : B;           // first step carries [last_h, embed(c0)]
@@ -369,7 +383,7 @@ static cudaError_t frame_tail(csm_ctx* x, int B, cudaStream_t st) {
     a.out = x->logits; a.ldo = x->Vp;
     if ((e = launch_gemv<EPI_PLAIN, true>(a, st)) != cudaSuccess) return e;
     k_sample_step<<<B, SAMPLE_THREADS, 0, st>>>(x->d_params, x->logits, x->Vp, i, V, C, x->audio_emb, D,
-                                                (i + 1 < C) ? x->dec_in : nullptr); COUNT_LAUNCH();
+                                                (i + 1 < C) ? x->dec_in : nullptr, x->d_sync); COUNT_LAUNCH();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   return cudaSuccess;
@@ -546,6 +560,7 @@ static void build_mega_phases(csm_ctx* x, MegaBuild& mb) {
   mega::Phase e;
   memset(&e, 0, sizeof(e));
   e.type = mega::PH_EMBED; e.V = V; e.C = C; e.D = D; e.audio_emb = x->audio_emb; e.text_emb = x->text_emb; e.t_out = x->bb.t_h; e.out_rs = x->bb.rs_h;
+  e.TV = c.text_vocab; e.rope_len = x->bb.rope_len;
   mb.v.push_back(e);
   int src[2] = {0, 0};
   for (int l = 0; l < c.backbone.layers; ++l) stack_phases(x, x->bb, x->mega_Rbb, l, 1, mega::POS_BACKBONE, 0, false, mb, src);
@@ -677,7 +692,6 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
     d.chunk_nch = ph.chunk | (ph.nch << 16) | (ph.keep ? (1 << 30) : 0);
   }
   CU_TRY(cudaMemcpyAsync(x->d_phases, v.data(), v.size() * sizeof(mega::Phase), cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaMemsetAsync(x->d_sync, 0, sizeof(mega::Sync), st));
   CU_TRY(cudaStreamSynchronize(st));  // v is host stack memory
   x->n_phases = (int)v.size();
   x->mega_grid = sms;
@@ -779,6 +793,23 @@ extern "C" int32_t csm_create(const csm_config* cfg, const csm_weights* w, int32
     delete x;
     return set_err(CSM_ERR_CUDA, "csm_create: %s", cudaGetErrorString(e));
   }
+  {
+    // status word: frame counter 0, no error, mirror in mapped host memory
+    unsigned int* dmirror = nullptr;
+    e = cudaHostAlloc((void**)&x->h_error, sizeof(unsigned int), cudaHostAllocMapped);
+    if (e == cudaSuccess) {
+      *x->h_error = 0;
+      e = cudaHostGetDevicePointer((void**)&dmirror, x->h_error, 0);
+    }
+    mega::Sync init;
+    init.seq = 0; init.error = 0; init.host_error = dmirror;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(x->d_sync, &init, sizeof(init), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // ``init`` is stack memory
+    if (e != cudaSuccess) {
+      csm_destroy(x);
+      return set_err(CSM_ERR_CUDA, "csm_create: %s", cudaGetErrorString(e));
+    }
+  }
   x->cache_len = 0;
   x->enabled = true;
   if ((rc = setup_mega(x, st)) != CSM_OK) {
@@ -793,6 +824,7 @@ extern "C" void csm_destroy(csm_ctx* x) {
   if (!x) return;
   for (auto& kv : x->graphs) cudaGraphExecDestroy(kv.second);
   if (x->cap_stream) cudaStreamDestroy(x->cap_stream);
+  if (x->h_error) cudaFreeHost(x->h_error);
   delete x;
 }
 
@@ -802,6 +834,13 @@ extern "C" int32_t csm_reset_caches(csm_ctx* x) {
   return CSM_OK;
 }
 extern "C" int32_t csm_cache_len(const csm_ctx* x) { return x ? x->cache_len : -1; }
+
+extern "C" int32_t csm_check_error(csm_ctx* x, int32_t clear) {
+  if (!x || !x->h_error) return 0;
+  const unsigned int code = *reinterpret_cast<volatile unsigned int*>(x->h_error);
+  if (code && clear) *reinterpret_cast<volatile unsigned int*>(x->h_error) = 0;
+  return (int32_t)code;
+}
 
 // decode steps run row-batched (RMSNorm / linear / RoPE kernels over all streams) from 16 streams on the
 // tcgen05 GEMM, and from 2 streams when the skinny GEMM has its fragment-major weights
@@ -817,7 +856,7 @@ static int get_graph(csm_ctx* x, int B, cudaGraphExec_t* out) {
     return CSM_OK;
   }
   cudaGraph_t g = nullptr;
-  const unsigned long long before = g_launches;
+  const unsigned long long before = g_launches.load();
   CU_TRY(cudaStreamBeginCapture(x->cap_stream, cudaStreamCaptureModeThreadLocal));
   cudaError_t e = cudaSuccess;
   int rc_tc = CSM_OK;
@@ -833,8 +872,8 @@ static int get_graph(csm_ctx* x, int B, cudaGraphExec_t* out) {
     if (g) cudaGraphDestroy(g);
     return rc_tc;
   }
-  x->graph_nodes[B] = g_launches - before;  // captured, not executed
-  g_launches = before;
+  x->graph_nodes[B] = g_launches.load() - before;  // captured, not executed
+  g_launches.store(before);
   if (e != cudaSuccess || e2 != cudaSuccess) {
     if (g) cudaGraphDestroy(g);
     return set_err(CSM_ERR_CUDA, "graph capture: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
@@ -879,7 +918,7 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
   for (int s0 = 0; s0 < S - 1; s0 += per_pass) {
     const int chunk = (S - 1 - s0) < per_pass ? (S - 1 - s0) : per_pass;
     p.s0 = s0;
-    k_set_params<<<1, 1, 0, st>>>(x->d_params, p); COUNT_LAUNCH();
+    k_set_params<<<1, 1, 0, st>>>(x->d_params, p, s0 == 0 ? x->d_sync : nullptr); COUNT_LAUNCH();
     CU_TRY(cudaGetLastError());
     if (prefill_path == CSM_PREFILL_TENSOR) {
       int rc = backbone_pass_tc(x, B, chunk, st);
@@ -896,7 +935,7 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
     x->cache_len += S;
     return CSM_OK;
   }
-  k_set_params<<<1, 1, 0, st>>>(x->d_params, p); COUNT_LAUNCH();
+  k_set_params<<<1, 1, 0, st>>>(x->d_params, p, S == 1 ? x->d_sync : nullptr); COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
   if (path == CSM_PATH_DIRECT) {
     if (rows_path(x, B)) {
@@ -912,7 +951,7 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
     int rc = get_graph(x, B, &ge);
     if (rc != CSM_OK) return rc;
     CU_TRY(cudaGraphLaunch(ge, st));
-    g_launches += x->graph_nodes[B];
+    g_launches.fetch_add(x->graph_nodes[B], std::memory_order_relaxed);
   }
   x->cache_len += S;
   return CSM_OK;
@@ -942,6 +981,7 @@ extern "C" int32_t csm_debug_phase_table(const csm_config* cfg, int32_t n_ctas, 
   x.mega_Rh0 = mega_pick_R(x.Vf + cfg->decoder.dim, n_ctas);
   x.mega_Rh = mega_pick_R(x.Vf, n_ctas);
   x.mega_keep = 0;
+  x.bb.rope_len = x.dec.rope_len = 0;
   x.qkv_table_ok = with_qkv_table != 0;
   x.text_emb = x.audio_emb = nullptr;
   MegaBuild mb;
@@ -1002,10 +1042,10 @@ static int make_map_bf16(CUtensorMap* m, const bf16* base, long long rows, long 
 static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const bf16* W, int n_out, bf16* out, long long ldo,
                           int epi, const bf16* resid, cudaStream_t st) {
   if (K % tc::BK || rows < 1 || n_out < 1) return set_err(CSM_ERR_ARG, "gemm_tc: K must be a multiple of 64");
-  static bool attr = false;
-  if (!attr) {
+  static std::atomic<unsigned long long> attr{0};
+  if (!device_done(attr, false)) {
     CU_TRY(cudaFuncSetAttribute(tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::SMEM_BYTES));
-    attr = true;
+    device_done(attr, true);
   }
   CUtensorMap mx, mw;
   int rc;
@@ -1125,7 +1165,8 @@ static int backbone_pass_tc(csm_ctx* x, int B, int chunk, cudaStream_t st) {
   const csm_config& c = x->cfg;
   const int N = B * chunk;
   k_embed_pass<<<N, 256, 0, st>>>(x->d_params, x->text_emb, x->audio_emb, c.codebooks, c.audio_vocab, c.backbone.dim, chunk,
-                                  x->bb.h, x->row_stream, x->row_pos, x->row_slot); COUNT_LAUNCH();
+                                  x->bb.h, x->row_stream, x->row_pos, x->row_slot, c.text_vocab, x->bb.rope_len, x->d_sync);
+  COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
   RowMeta m{x->row_stream, x->row_pos, x->row_slot, 0, 0, chunk};
   return stack_pass_tc(x, x->bb, N, m, st);
@@ -1144,7 +1185,7 @@ static int frame_tail_tc(csm_ctx* x, int B, cudaStream_t st) {
   if ((rc = norm_linear_rows(x, x->bb.h, x->bb.norm, c.norm_eps, x->dec_in, true, x->proj, x->f_head0 + (size_t)x->Vf * D, x->mega_Rh0, B,
                              D, Dd, x->dec.h, Dd, tc::EPI_STORE, st)) != CSM_OK) return rc;
   k_sample_step<<<B, SAMPLE_THREADS, 0, st>>>(x->d_params, x->logits, x->Vp, 0, V, C, x->proj_table, Dd,
-                                              x->dec.h + (size_t)B * Dd); COUNT_LAUNCH();
+                                              x->dec.h + (size_t)B * Dd, x->d_sync); COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
   for (int i = 1; i < C; ++i) {
     const int N = (i == 1) ? 2 * B : B, pos0 = (i == 1) ? 0 : i;
@@ -1154,7 +1195,7 @@ static int frame_tail_tc(csm_ctx* x, int B, cudaStream_t st) {
                                x->head_t + (size_t)(i - 1) * x->Vp * Dd, x->f_heads + (size_t)(i - 1) * x->Vf * Dd, x->mega_Rh, B, Dd, V,
                                x->logits, x->Vp, tc::EPI_STORE, st)) != CSM_OK) return rc;
     k_sample_step<<<B, SAMPLE_THREADS, 0, st>>>(x->d_params, x->logits, x->Vp, i, V, C, x->proj_table, Dd,
-                                                (i + 1 < C) ? x->dec.h : nullptr); COUNT_LAUNCH();
+                                                (i + 1 < C) ? x->dec.h : nullptr, x->d_sync); COUNT_LAUNCH();
     CU_TRY(cudaGetLastError());
   }
   return CSM_OK;

@@ -26,22 +26,58 @@ struct FrameParams {
   int s0;                  // first prompt row handled by the current prefill chunk
 };
 
-__global__ void k_set_params(FrameParams* dst, FrameParams v) { *dst = v; }
+struct DevStatus;
+__global__ void k_set_params(FrameParams* dst, FrameParams v, DevStatus* st_reset = nullptr);
+
+// Device-side status of a context: sticky error code of the current call, mirrored into a mapped host
+// word so that the host can look at it without a CUDA call (csm_check_error).  Codes:
+//   0x100-0x4ff  a wait of the decode megakernel gave up (trip cap): the launch drained, tokens are garbage
+//   0x801        token id outside its embedding table        (the reference raises IndexError there)
+//   0x802        teacher-forced token id outside the audio vocabulary
+//   0x803        input_pos outside the RoPE table, or != cache position (the reference's mask row / cache slot
+//                coincide only for sequential use from a reset state; anything else is rejected, not guessed)
+struct DevStatus {
+  unsigned int seq;    // frame counter of the megakernel (tag salt)
+  unsigned int error;  // first error code of this call (0 = none)
+  unsigned int* host_error;  // mapped host mirror, sticky until csm_check_error clears it
+};
+__global__ void k_set_params(FrameParams* dst, FrameParams v, DevStatus* st_reset) {
+  *dst = v;
+  if (st_reset) st_reset->error = 0;  // per call; the host mirror stays sticky until csm_check_error reads it
+}
+__device__ __noinline__ void report_error(DevStatus* st, unsigned code) {
+  if (st && atomicCAS(&st->error, 0u, code) == 0u && st->host_error) {
+    *reinterpret_cast<volatile unsigned int*>(st->host_error) = code;
+    __threadfence_system();
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // K1: _embed_tokens + mask-mul + sum  (sesameai/models.py:155-157,193-203)
 // h[n,:] = sum_{c<C} m_c * A[tok_c + V*c] + m_C * T[tok_C], fp32 accumulate in column order,
 // one rounding to bf16.  One CTA per frame row, 16-byte gathers.
 // ---------------------------------------------------------------------------------------------
+// token id of column c, range-checked (ids the reference would raise on are reported and read as 0)
+__device__ __forceinline__ size_t checked_token(const int64_t* tok, int c, int C, int V, int TV, DevStatus* st) {
+  const int64_t t = tok[c];
+  const int64_t lim = c < C ? V : TV;
+  if (t < 0 || (lim > 0 && t >= lim)) {
+    report_error(st, 0x801);
+    return 0;
+  }
+  return (size_t)t;
+}
 __device__ __forceinline__ void embed_row(const int64_t* tok, const uint8_t* msk, const bf16* text_emb,
-                                          const bf16* audio_emb, int C, int V, int D, bf16* out) {
+                                          const bf16* audio_emb, int C, int V, int D, bf16* out, int TV = 0,
+                                          DevStatus* st = nullptr) {
   for (int d8 = threadIdx.x; d8 < D / 8; d8 += blockDim.x) {
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
     for (int c = 0; c <= C; ++c) {
       if (!msk[c]) continue;  // masked slots contribute row*0 (exact for finite weights)
-      const bf16* row = (c < C) ? audio_emb + ((size_t)tok[c] + (size_t)V * c) * D : text_emb + (size_t)tok[c] * D;
+      const size_t t = checked_token(tok, c, C, V, TV, st);
+      const bf16* row = (c < C) ? audio_emb + (t + (size_t)V * c) * D : text_emb + t * D;
       uint4 v = *reinterpret_cast<const uint4*>(row + d8 * 8);
       acc[0] += bflo(v.x); acc[1] += bfhi(v.x); acc[2] += bflo(v.y); acc[3] += bfhi(v.y);
       acc[4] += bflo(v.z); acc[5] += bfhi(v.z); acc[6] += bflo(v.w); acc[7] += bfhi(v.w);
@@ -63,16 +99,25 @@ __global__ void k_embed_frames(const int64_t* tokens, const uint8_t* mask, const
 // Backbone input rows for one pass: rows n = b*chunk + t  <->  prompt frame s = s0 + t of stream b.
 // Also emits the row metadata (stream, RoPE position, cache slot) the layer kernels use.
 __global__ void k_embed_pass(const FrameParams* __restrict__ P, const bf16* text_emb, const bf16* audio_emb, int C,
-                             int V, int D, int chunk, bf16* h, int* row_stream, int* row_pos, int* row_slot) {
+                             int V, int D, int chunk, bf16* h, int* row_stream, int* row_pos, int* row_slot, int TV,
+                             int rope_len, DevStatus* st) {
   const int n = blockIdx.x;
   const int b = n / chunk, t = n % chunk;
   const int s = P->s0 + t;
   const size_t fr = (size_t)b * P->S + s;
-  embed_row(P->tokens + fr * (C + 1), P->mask + fr * (C + 1), text_emb, audio_emb, C, V, D, h + (size_t)n * D);
+  embed_row(P->tokens + fr * (C + 1), P->mask + fr * (C + 1), text_emb, audio_emb, C, V, D, h + (size_t)n * D, TV, st);
   if (threadIdx.x == 0) {
+    const int slot = P->cache_len + s;
+    int64_t pos = P->pos[fr];
+    // the key range of a row is its cache slot (key <= slot); the reference masks by input_pos: they agree
+    // exactly when input_pos == cache position, the only use the reference makes of it
+    if (pos != slot || pos < 0 || pos >= rope_len) {
+      report_error(st, 0x803);
+      pos = slot;
+    }
     row_stream[n] = b;
-    row_pos[n] = (int)P->pos[fr];
-    row_slot[n] = P->cache_len + s;
+    row_pos[n] = (int)pos;
+    row_slot[n] = slot;
   }
 }
 
@@ -795,7 +840,8 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample_only(const bf16* logi
 __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample_step(const FrameParams* __restrict__ P,
                                                                 const bf16* __restrict__ logits, int ldl, int cb,
                                                                 int V, int C, const bf16* __restrict__ audio_emb, int D,
-                                                                bf16* __restrict__ next_in /*[B, D] or null*/) {
+                                                                bf16* __restrict__ next_in /*[B, D] or null*/,
+                                                                DevStatus* st = nullptr) {
   // ``audio_emb``/``D`` may also be the projection(embedding) table and its row length
   __shared__ float xs[SAMPLE_MAXV];
   __shared__ unsigned int hist[256];
@@ -813,6 +859,10 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample_step(const FrameParam
                                                  iscratch, threadIdx.x);
   if (threadIdx.x == 0 && P->sampled_out) P->sampled_out[(size_t)b * C + cb] = tok;
   if (P->forced) tok = P->forced[(size_t)b * C + cb];
+  if ((unsigned)tok >= (unsigned)V) {  // teacher-forced id out of range
+    if (threadIdx.x == 0) report_error(st, 0x802);
+    tok = 0;
+  }
   if (threadIdx.x == 0) P->out[(size_t)b * C + cb] = tok;
   if (next_in) {
     const bf16* row = audio_emb + ((size_t)tok + (size_t)cb * V) * D;

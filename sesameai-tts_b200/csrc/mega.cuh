@@ -24,7 +24,8 @@
 //     boundary costs one L2 round trip, and CTAs without work in a phase run ahead.
 // Token-dependent linear maps are tables: projection(embedding) and the first decoder layer's RoPE'd
 // [q;k;v] of it are gathered by the sampling phase instead of being computed by GEMV phases.
-// Every spin has a trip-count cap and traps instead of hanging the GPU.
+// Every spin has a trip-count cap; a wait that gives up records an error code and lets the launch drain
+// (no __trap: the CUDA context must survive, see report_error).
 #pragma once
 #include "lm_kernels.cuh"
 
@@ -104,7 +105,8 @@ struct __align__(16) Phase {
   // distance in words between the REP copies of the tagged vectors (0: single copy)
   int x_rs, out_rs, out2_rs, q_rs, kv_rs, next_rs;
   int keep;  // this matrix is loaded with the L2 evict-last policy
-  int pad_[2];
+  int TV;    // EMBED: text vocabulary (range check of the text column)
+  int rope_len;  // EMBED: rows of the backbone RoPE table (range check of input_pos)
 };
 static_assert(sizeof(Phase) % 16 == 0, "Phase must be copyable in 16-byte units");
 
@@ -122,14 +124,12 @@ struct PfTable {
   PfDesc d[MAX_GEMV];
 };
 
-struct Sync {
-  unsigned int seq;  // frame counter (tag salt), bumped by k_mega_prepare
-  unsigned int error;
-};
+using Sync = DevStatus;  // frame counter (tag salt, bumped by k_mega_prepare) + sticky error word
 
 __global__ void k_mega_prepare(FrameParams* dst, FrameParams v, Sync* sync) {
   *dst = v;
   sync->seq += 1;
+  sync->error = 0;  // per call; the host mirror stays sticky until csm_check_error reads it
 }
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -185,14 +185,25 @@ __device__ __forceinline__ unsigned long long gtimer() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __noinline__ void die(Sync* sync, unsigned code) {
-  atomicExch(&sync->error, code);
-  __threadfence_system();
-  __trap();
+// A wait that exceeds its trip cap must not hang the GPU -- and must not __trap() either: a trap poisons
+// the CUDA context, and the reference's retry loops (tts_service.py:500-514) could never recover.  Instead
+// the first thread to give up records a sticky error code (device word + mapped host word) and from then on
+// EVERY wait of every thread returns after at most 256 more trips: the launch drains to its end with garbage
+// tokens (clamped before they index anything), the context survives, and the host raises from the code.
+__device__ __noinline__ bool give_up_slow(Sync* sync, unsigned spin, unsigned cap, unsigned code) {
+  if (*reinterpret_cast<volatile unsigned int*>(&sync->error) != 0u) return true;
+  if (spin > cap) {
+    report_error(sync, code);
+    return true;
+  }
+  return false;
+}
+__device__ __forceinline__ bool give_up(Sync* sync, unsigned spin, unsigned cap, unsigned code) {
+  return (spin & 255u) == 255u && give_up_slow(sync, spin, cap, code);
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, Sync* sync, unsigned code) {
   for (unsigned spin = 0; !mbar_try(bar, parity); ++spin)
-    if (spin > (1u << 22)) die(sync, code);
+    if (give_up(sync, spin, 1u << 22, code)) break;
 }
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
@@ -204,6 +215,23 @@ __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1
       "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// ---- ordering of the plain KV-cache rows --------------------------------------------------------------
+// The depth decoder's cache rows are written as plain bf16 (a QKV epilogue, or the sampling phase's table
+// gather) and read by OTHER CTAs in later codebook steps of the SAME launch (attn_prefetch).  The tagged
+// hand-off words do not order those plain stores, so the writing thread fences after its stores
+// (release side) and the reading CTA fences before it issues the loads (acquire side): with the chain of
+// tagged words between the two, that is release -> ... -> acquire at gpu scope.  Only the threads that wrote
+// cache rows pay for the writer fence, after their tagged stores went out, so it overlaps the hand-off
+// the CTA waits for anyway.  (The backbone cache needs none: its rows are read by the next launch.)
+#ifndef MEGA_KV_FENCE
+#define MEGA_KV_FENCE 1
+#endif
+__device__ __forceinline__ void kv_fence() {
+#if MEGA_KV_FENCE
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+#endif
 }
 
 // ---- tagged activations ------------------------------------------------------------------------------
@@ -237,7 +265,7 @@ __device__ __forceinline__ bool fresh4(const uint4& v, uint32_t tag) {
 }
 __device__ __forceinline__ uint4 poll4(const uint32_t* p, uint32_t tag, uint4 v, Sync* sync) {
   for (unsigned spin = 0; !fresh4(v, tag); ++spin) {
-    if (spin > (1u << 22)) die(sync, 0x400);
+    if (give_up(sync, spin, 1u << 22, 0x400)) break;
     v = ldv4(p);
   }
   return v;
@@ -245,7 +273,7 @@ __device__ __forceinline__ uint4 poll4(const uint32_t* p, uint32_t tag, uint4 v,
 __device__ __forceinline__ uint2 poll2(const uint32_t* p, uint32_t tag, Sync* sync) {
   uint2 v = ldv2(p);
   for (unsigned spin = 0; (((v.x ^ tag) | (v.y ^ tag)) & 0xffff0000u) != 0; ++spin) {
-    if (spin > (1u << 22)) die(sync, 0x401);
+    if (give_up(sync, spin, 1u << 22, 0x401)) break;
     v = ldv2(p);
   }
   return v;
@@ -253,7 +281,7 @@ __device__ __forceinline__ uint2 poll2(const uint32_t* p, uint32_t tag, Sync* sy
 __device__ __forceinline__ uint32_t poll1(const uint32_t* p, uint32_t tag, Sync* sync) {
   uint32_t v = ldv1(p);
   for (unsigned spin = 0; ((v ^ tag) & 0xffff0000u) != 0; ++spin) {
-    if (spin > (1u << 22)) die(sync, 0x402);
+    if (give_up(sync, spin, 1u << 22, 0x402)) break;
     v = ldv1(p);
   }
   return v;
@@ -366,7 +394,7 @@ __device__ __forceinline__ void producer_loop(const PfDesc* tab, int ntab, unsig
       // (with the L2 stage on, probe without suspending so that the prefetches really go out while waiting)
       const bool ok = lane >= NW || (L2_AHEAD > 0 ? mbar_test(eb, parity) : mbar_try(eb, parity));
       if (__all_sync(0xffffffffu, ok)) break;
-      if (spin > (1u << 26)) die(sync, 0x100);
+      if (__any_sync(0xffffffffu, give_up(sync, spin, 1u << 26, 0x100))) break;  // warp-uniform exit
       if (L2_AHEAD > 0 && ahead < SLOTS + L2_AHEAD && cursor_valid(k2, ntab)) {
         if (ahead >= SLOTS && lane < NW) {  // the first SLOTS steps ahead are in the ring (or on their way) already
           int chunk;
@@ -487,6 +515,7 @@ __device__ __forceinline__ void epilogue(const Phase& ph, const Ctx& c, int r0, 
       rep_st2(ph.t_kv + ((size_t)n * 2 + (isk ? 0 : 1)) * krows + rr, ph.kv_rs, make_uint2(tword(tag, o0), tword(tag, o1)));
       bf16* dst = (isk ? ph.kc : ph.vc) + ((size_t)kvh * ph.slots + slot) * hd + d;  // stream 0
       *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(o0, o1);
+      if (ph.pos_mode == POS_FIXED) kv_fence();  // depth decoder: read by other CTAs later in this launch
     }
   }
 }
@@ -650,6 +679,7 @@ static_assert(A_IOFF + 64 <= XBUF_ELEMS, "attention staging must fit the activat
 __device__ __forceinline__ void attn_prefetch(const Phase& ph, Ctx& c) {
   const int kvn = ph.kv_heads, nold = ph.pos0;  // positions [0, pos0) were written in earlier steps
   const int per = nold * (A_HD / 8);            // 16-byte units of one kv head's K (or V) rows
+  if (nold > 0) kv_fence();  // acquire side: this CTA has seen tagged words that follow the rows' release fences
   for (int u = c.tid; u < 2 * kvn * per; u += NCT) {
     int r = u;
     const bool isv = r >= kvn * per;
@@ -713,7 +743,7 @@ __device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
           }
         }
         if (ok) break;
-        if (spin > (1u << 22)) die(c.sync, 0x406);
+        if (give_up(c.sync, spin, 1u << 22, 0x406)) break;
       }
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
@@ -887,7 +917,7 @@ __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
         }
       }
       if (ok) break;
-      if (spin > (1u << 22)) die(c.sync, 0x405);
+      if (give_up(c.sync, spin, 1u << 22, 0x405)) break;
     }
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -1078,8 +1108,8 @@ __device__ __forceinline__ void embed_phase(const Phase& ph, Ctx& c) {
       on[j] = cb <= ph.C && msk[cb < ph.C + 1 ? cb : 0] != 0;
       v[j] = make_uint4(0, 0, 0, 0);
       if (on[j]) {
-        const bf16* row = (cb < ph.C) ? ph.audio_emb + ((size_t)tok[cb] + (size_t)ph.V * cb) * ph.D
-                                      : ph.text_emb + (size_t)tok[cb] * ph.D;
+        const size_t t = checked_token(tok, cb, ph.C, ph.V, ph.TV, c.sync);
+        const bf16* row = (cb < ph.C) ? ph.audio_emb + (t + (size_t)ph.V * cb) * ph.D : ph.text_emb + t * ph.D;
         v[j] = *reinterpret_cast<const uint4*>(row + u * 8);
       }
     }
@@ -1130,7 +1160,7 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
         }
       }
       if (ok) break;
-      if (spin > (1u << 22)) die(c.sync, 0x407);
+      if (give_up(c.sync, spin, 1u << 22, 0x407)) break;
     }
 #pragma unroll
     for (int t = 0; t < MAXU; ++t) {
@@ -1204,6 +1234,10 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
   if (c.trp) c.trp[2] = gtimer();
   if (c.tid == 0 && P->sampled_out) P->sampled_out[cb] = tok;
   if (P->forced) tok = P->forced[cb];
+  if ((unsigned)tok >= (unsigned)V) {  // a teacher-forced id out of range, or garbage logits of a draining launch
+    if (P->forced && c.tid == 0) report_error(c.sync, 0x802);
+    tok = 0;
+  }
   if (c.tid == 0) P->out[cb] = tok;
   if (ph.t_next) {
     // next depth-decoder input: projection(embed_audio(cb, tok)) read from the table built at setup, and -- when
@@ -1248,6 +1282,7 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
           rep_st4(ph.t_kv + (isk ? 0 : krows) + rr, ph.kv_rs, w);
           bf16* dst = (isk ? ph.kc : ph.vc) + ((size_t)(rr >> ph.hd_shift) * ph.slots + ph.pos0) * hd + (rr & (hd - 1));
           *reinterpret_cast<uint2*>(dst) = v;
+          kv_fence();
         }
       }
     }
@@ -1289,8 +1324,15 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
   Ctx c;
   c.P = P; c.trp = nullptr; c.ring = ring; c.xs = xs; c.full = full; c.empty = empty; c.scratch = scratch; c.iscratch = iscratch;
   c.psum = psum; c.sync = sync; c.cnt = 0; c.tid = threadIdx.x; c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
-  c.bb_pos = (int)P->pos[P->S - 1];  // batch 1: stream 0, last prompt row
   c.bb_slot = P->cache_len + P->S - 1;
+  {
+    // batch 1: stream 0, last prompt row.  Keys are masked by cache slot; the reference masks by input_pos:
+    // identical when input_pos == cache position (its only use), anything else is reported, not guessed.
+    const int64_t pos = P->pos[P->S - 1];
+    const bool bad = pos != c.bb_slot || pos >= phbuf[0].rope_len;
+    if (bad && threadIdx.x == 0 && blockIdx.x == 0) report_error(sync, 0x803);
+    c.bb_pos = bad ? c.bb_slot : (int)pos;
+  }
   c.seq = sync->seq;
 
   const bool tr = trace != nullptr && c.tid == 0;
@@ -1317,12 +1359,6 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
       c.trp[3] = gtimer();
       c.trp[15] = clock64();
     }
-#ifdef MEGA_KV_FENCE
-    // Plain cache rows written by a QKV epilogue are first read >= 16 phases (tens of microseconds)
-    // later, by L2 loads (cp.async.cg), after write-through stores that reach L2 within a few hundred
-    // cycles: the fence that would order them formally costs ~0.5 us on every QKV phase and is off.
-    if (ph.type == PH_GEMV && ph.epi == EPI_ROPE_KV) __threadfence();
-#endif
     asm volatile("cp.async.wait_all;" ::: "memory");  // the next descriptor has landed
     // end of phase inside the CTA: shared activations / partial sums may be overwritten from here on
     csync<NCT, CBAR>();

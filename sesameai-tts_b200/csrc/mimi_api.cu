@@ -111,8 +111,8 @@ extern "C" size_t mimi_workspace_bytes(int32_t max_frames) {
 // GEMM dispatch: TF32 tensor cores when K is a whole number of 32-wide tiles and rows are 16-byte
 // aligned (every Mimi shape is); precise = 3xTF32 (encode side), else single-pass TF32.
 // MIMI_GEMM env (debug): "fp32" forces the CUDA-core SGEMM, "tf32x3" forces the split everywhere.
-static int g_gemm_mode = -1;  // 0 auto, 1 fp32, 2 tf32x3
-static bool g_precise = false;
+static int g_gemm_mode = -1;  // 0 auto, 1 fp32, 2 tf32x3 (read-only after the first call)
+static thread_local bool g_precise = false;  // per calling thread: two threads may drive two codecs
 static cudaError_t gemm(cudaStream_t st, const float* A, long long lda, const float* B, float* C, long long ldc, long long M,
                         int N, int K, const float* bias, int bias_period, int flags, const float* R = nullptr,
                         long long ldr = 0, const float* scale = nullptr) {

@@ -99,6 +99,7 @@ PROTOTYPES = {
     "csm_destroy": (None, [C.c_void_p]),
     "csm_reset_caches": (C.c_int32, [C.c_void_p]),
     "csm_cache_len": (C.c_int32, [C.c_void_p]),
+    "csm_check_error": (C.c_int32, [C.c_void_p, C.c_int32]),
     "csm_generate_frame": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
                                        C.c_int32, C.POINTER(FrameOpts), C.c_void_p, C.c_void_p]),
     "mimi_workspace_bytes": (C.c_size_t, [C.c_int32]),

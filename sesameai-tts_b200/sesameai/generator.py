@@ -12,6 +12,9 @@ tokenizers (the reference downloads both from the HF hub inside ``__init__``).
 """
 from __future__ import annotations
 
+import queue
+import threading
+import time
 from dataclasses import dataclass
 from typing import Callable, Iterator, List, Optional, Tuple
 
@@ -115,7 +118,9 @@ class Generator:
         nxt_mask[..., -1] = False
         for _ in range(max_generation_len):
             sample = self._model.generate_frame(tokens, mask, pos, temperature, topk)
-            if torch.all(sample == 0):
+            eos = bool(torch.all(sample == 0))  # synchronises the stream, like the reference's ``if``
+            self._model.check_device_error()    # bad token ids / positions or a drained kernel raise here
+            if eos:
                 return  # EOS
             yield sample
             nxt_tok[0, 0, :-1] = sample[0]
@@ -152,9 +157,96 @@ class Generator:
         return self._decode_frames(samples)
 
 
+class AudioStreamWriter:
+    """Collects streamed chunks and writes them to one file (reference ``generator.py:303-327``)."""
+
+    def __init__(self, filename, sample_rate):
+        self.filename = filename
+        self.sample_rate = sample_rate
+        self.audio_chunks: List[torch.Tensor] = []
+        self.lock = threading.Lock()
+
+    def add_chunk(self, chunk):
+        with self.lock:
+            self.audio_chunks.append(chunk)
+
+    def write_file(self):
+        with self.lock:
+            if not self.audio_chunks:
+                return
+            audio = torch.cat(self.audio_chunks)
+            _save_wav(self.filename, audio.unsqueeze(0).cpu(), self.sample_rate)
+
+
+def _save_wav(filename, audio: torch.Tensor, sample_rate: int) -> None:
+    """``torchaudio.save`` as the reference calls it; without torchaudio, a 16-bit PCM file via ``wave``."""
+    try:
+        import torchaudio
+
+        torchaudio.save(filename, audio, sample_rate)
+        return
+    except ImportError:
+        pass
+    import wave
+
+    pcm = (audio.float().clamp(-1.0, 1.0) * 32767.0).round().to(torch.int16)
+    with wave.open(str(filename), "wb") as f:
+        f.setnchannels(pcm.shape[0])
+        f.setsampwidth(2)
+        f.setframerate(int(sample_rate))
+        f.writeframes(pcm.t().contiguous().numpy().tobytes())
+
+
 def load_csm_1b(device: str = "cuda") -> Generator:
     """Reference ``load_csm_1b`` (``generator.py:330-346``) minus the cuDNN / torch.compile knobs, which
     have no counterpart here: weights from the hub, bf16 on ``device``, caches for batch 1."""
     model = Model.from_pretrained("sesame/csm-1b")
     model.to(device=device, dtype=torch.bfloat16)
     return Generator(model)
+
+
+def generate_streaming_audio(generator: Generator, text: str, speaker: int, context: List[Segment], output_file: str,
+                             max_audio_length_ms: float = 90_000, temperature: float = 0.7, topk: int = 30,
+                             play_audio: bool = False):
+    """Reference ``generate_streaming_audio`` (``generator.py:349-433``): stream chunks into a file, optionally
+    playing them as they arrive (needs ``sounddevice``)."""
+    writer = AudioStreamWriter(output_file, generator.sample_rate)
+    audio_queue: "queue.Queue[torch.Tensor]" = queue.Queue()
+    stop_event = threading.Event()
+    player_thread = None
+    if play_audio:
+        try:
+            import sounddevice as sd
+
+            def audio_player():
+                while not stop_event.is_set() or not audio_queue.empty():
+                    try:
+                        chunk = audio_queue.get(timeout=0.5)
+                    except queue.Empty:
+                        continue
+                    sd.play(chunk.cpu().numpy(), generator.sample_rate)
+                    sd.wait()
+
+            player_thread = threading.Thread(target=audio_player)
+            player_thread.start()
+        except ImportError:
+            print("sounddevice library not found. Install with 'pip install sounddevice' to enable real-time playback.")
+            play_audio = False
+
+    def on_chunk_generated(chunk):
+        writer.add_chunk(chunk)
+        if play_audio:
+            audio_queue.put(chunk)
+
+    print("Generating audio in streaming mode...")
+    start_time = time.time()
+    chunk_count = 0
+    for _ in generator.generate_stream(text=text, speaker=speaker, context=context, max_audio_length_ms=max_audio_length_ms,
+                                       temperature=temperature, topk=topk, on_chunk_generated=on_chunk_generated):
+        chunk_count += 1
+        print(f"Generated chunk {chunk_count}")
+    writer.write_file()
+    if player_thread is not None:
+        stop_event.set()
+        player_thread.join()
+    print(f"Audio generation completed in {time.time() - start_time:.2f} seconds")

@@ -207,6 +207,11 @@ class Model(
         self.audio_head = nn.Parameter(torch.empty(config.audio_num_codebooks - 1, d_dec, config.audio_vocab_size))
         self._ctx: Optional[int] = None
         self._keep: Dict[str, object] = {}
+        # In-kernel sampling noise is a counter RNG keyed by (seed, frame counter, codebook, stream, index).
+        # ``seed`` is re-drawn from torch's default generator by setup_caches() and by every reset_caches()
+        # (= per utterance), so torch.manual_seed() governs the audio as it does for the reference (which
+        # draws its Exp(1) noise from torch's generator) and unseeded processes / replicas differ.
+        # Assign ``model.seed`` (after reset_caches) for a fixed stream in tests.
         self._frame_counter = 0
         self.seed = 0
 
@@ -248,6 +253,7 @@ class Model(
             _native.check(L.csm_create(ctypes.byref(cfg), ctypes.byref(w), int(max_batch_size), ws.data_ptr() + off,
                                        need, torch.cuda.current_stream(dev).cuda_stream, ctypes.byref(ctx)))
         self._ctx = ctx.value
+        self._reseed()
         self._keep = {"ws": ws, "rope_bb": rope_bb, "rope_dec": rope_dec, "w": w, "arrays": keep, "max_batch": max_batch_size}
         tri = lambda n: torch.tril(torch.ones(n, n, dtype=torch.bool, device=dev))  # noqa: E731
         self.register_buffer("backbone_causal_mask", tri(self.backbone.max_seq_len))
@@ -255,10 +261,32 @@ class Model(
         self.backbone.__dict__["_owner_ref"] = weakref.ref(self)
         self.decoder.__dict__["_owner_ref"] = weakref.ref(self)
 
+    def _reseed(self) -> None:
+        self.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        self._frame_counter = 0
+
     def reset_caches(self) -> None:
         if self._ctx is None:
             raise RuntimeError("Key value caches are not setup. Call ``setup_caches()`` first.")
         _native.check(_native.lib().csm_reset_caches(self._ctx))
+        self._reseed()
+
+    def check_device_error(self) -> None:
+        """Raise for an error that an earlier (stream-ordered, asynchronous) call hit on the device.  Costs a
+        host memory read, no CUDA call; meaningful once the stream has been synchronised (the frame loop's
+        EOS test does that).  The context stays usable: ``reset_caches()`` and retry."""
+        if self._ctx is None:
+            return
+        code = _native.lib().csm_check_error(self._ctx, 1)
+        if code == 0:
+            return
+        if code == 0x801:
+            raise IndexError("sesameai(B200): token id out of range of its embedding table")
+        if code == 0x802:
+            raise IndexError("sesameai(B200): teacher-forced token id out of range")
+        if code == 0x803:
+            raise ValueError("sesameai(B200): input_pos must continue the cache position and stay below max_seq_len")
+        raise RuntimeError(f"sesameai(B200): decode kernel gave up waiting (code {code:#x}); reset_caches() and retry")
 
     # -- the hot path ----------------------------------------------------------------------------
     def generate_frame(self, tokens: torch.Tensor, tokens_mask: torch.Tensor, input_pos: torch.Tensor,
@@ -270,6 +298,7 @@ class Model(
         (``models.py:132-184``).  Keyword extras are for parity tests: shared Exp(1) ``noise``
         [32, B, V] bf16, teacher-``forced`` tokens [B, 32] int32, raw ``logits_out`` [32, B, V]."""
         assert self._ctx is not None, "backbone caches are not enabled"
+        self.check_device_error()  # of earlier calls (free: a host memory read)
         dev = tokens.device
         if dev.type != "cuda":
             raise RuntimeError("sesameai(B200): tokens must live on the model's CUDA device")
