@@ -99,8 +99,15 @@ void csm_destroy(csm_ctx *ctx);
  * cache positions.  No memset is needed because attention never reads beyond the valid length. */
 int32_t csm_reset_caches(csm_ctx *ctx);
 
-/* Backbone positions currently held in the KV cache (torchtune KVCache.size). */
+/* Backbone positions currently held in the KV cache (torchtune KVCache.size); lane 0 of a lock-step batch. */
 int32_t csm_cache_len(const csm_ctx *ctx);
+
+/* Continuous batching (the reference loop sesameai/generator.py:283-294 serves one
+ * stream and stops at its EOS frame, models.py:160 assumes a lock-step batch): a cache lane is one stream's
+ * slice of the KV cache.  csm_lane_reset rewinds one lane (a finished stream leaves, a new one may join),
+ * csm_lane_len is the number of positions it holds. */
+int32_t csm_lane_reset(csm_ctx *ctx, int32_t lane);
+int32_t csm_lane_len(const csm_ctx *ctx, int32_t lane);
 
 /* Device-side errors of earlier stream-ordered calls, WITHOUT a CUDA call (the kernels mirror the code into
  * mapped host memory): 0 = none; 0x100-0x4ff = a wait inside the decode megakernel gave up (the launch
@@ -123,6 +130,10 @@ typedef struct csm_frame_opts {
   int32_t *sampled_out;   /* dev [B, codebooks] sampled tokens before forcing, or NULL                     */
   int32_t path;           /* CSM_PATH_*: which launch strategy runs the last prompt row + frame tail          */
   int32_t prefill;        /* CSM_PREFILL_*: how prompt rows [0, S-1) are processed                            */
+  const int32_t *lanes;   /* HOST int32 [B] (read before the call returns): KV-cache lane of each batch row, all
+                           * distinct, each < max_batch; NULL = row b on lane b (the reference's lock-step batch).
+                           * Every lane keeps its own length, so streams may join (prefill a free lane with a
+                           * B = 1 call), advance together in any subset, and leave (csm_lane_reset) per frame.   */
 } csm_frame_opts;
 
 enum {

@@ -87,7 +87,9 @@ struct csm_ctx {
   bf16* logits;   // [B][Vp]
   int *row_stream, *row_pos, *row_slot;
   FrameParams* d_params;
-  int cache_len;
+  int* d_lane_meta;            // [2 * max_batch]: row -> lane, row -> positions held (continuous batching)
+  std::vector<int> lane_len;   // positions held by every cache lane (host truth; calls are stream ordered)
+  int cache_len;               // == lane_len[0]: the reference's single counter for a lock-step batch
   bool enabled;
   cudaStream_t cap_stream;
   // persistent decode megakernel (batch 1)
@@ -201,6 +203,7 @@ static size_t carve_all(csm_ctx* x, char* base) {
   x->row_pos = cv.take<int>(x->max_rows);
   x->row_slot = cv.take<int>(x->max_rows);
   x->d_params = cv.take<FrameParams>(1);
+  x->d_lane_meta = cv.take<int>((size_t)2 * x->max_batch);
   x->d_sync = cv.take<mega::Sync>(1);
   x->d_phases = cv.take<mega::Phase>(mega_phase_count(c));
   cv.off = (cv.off + 255) & ~(size_t)255;
@@ -811,6 +814,7 @@ extern "C" int32_t csm_create(const csm_config* cfg, const csm_weights* w, int32
     }
   }
   x->cache_len = 0;
+  x->lane_len.assign(max_batch, 0);
   x->enabled = true;
   if ((rc = setup_mega(x, st)) != CSM_OK) {
     csm_destroy(x);
@@ -831,7 +835,18 @@ extern "C" void csm_destroy(csm_ctx* x) {
 extern "C" int32_t csm_reset_caches(csm_ctx* x) {
   if (!x || !x->enabled) return set_err(CSM_ERR_STATE, "caches are not enabled");
   x->cache_len = 0;
+  x->lane_len.assign(x->max_batch, 0);
   return CSM_OK;
+}
+extern "C" int32_t csm_lane_reset(csm_ctx* x, int32_t lane) {
+  if (!x || !x->enabled) return set_err(CSM_ERR_STATE, "caches are not enabled");
+  if (lane < 0 || lane >= x->max_batch) return set_err(CSM_ERR_ARG, "lane out of range");
+  x->lane_len[lane] = 0;
+  if (lane == 0) x->cache_len = 0;
+  return CSM_OK;
+}
+extern "C" int32_t csm_lane_len(const csm_ctx* x, int32_t lane) {
+  return (x && lane >= 0 && lane < x->max_batch) ? x->lane_len[lane] : -1;
 }
 extern "C" int32_t csm_cache_len(const csm_ctx* x) { return x ? x->cache_len : -1; }
 
@@ -894,13 +909,43 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
   if (!x || !x->enabled) return set_err(CSM_ERR_STATE, "backbone caches are not enabled");
   if (!tokens || !tokens_mask || !input_pos || !out || B < 1 || S < 1) return set_err(CSM_ERR_ARG, "bad tokens/mask/pos/out");
   if (B > x->max_batch) return set_err(CSM_ERR_STATE, "batch size exceeds the batch the caches were set up for");
-  if (x->cache_len + S > x->cfg.max_seq_len) return set_err(CSM_ERR_OVERFLOW, "KV cache overflow (cache_pos + seq_len > max_seq_len)");
   if (!(temperature > 0.f) || topk < 1) return set_err(CSM_ERR_ARG, "temperature must be > 0 and topk >= 1");
   cudaStream_t st = (cudaStream_t)stream;
+  // cache lanes of the batch rows: identity for the reference's lock-step batch, any distinct lanes for a
+  // continuous-batching caller; every lane keeps its own length
+  const int32_t* lanes = opts ? opts->lanes : nullptr;
+  std::vector<int> lane(B);
+  bool uniform = lanes == nullptr;
+  for (int b = 0; b < B; ++b) {
+    lane[b] = lanes ? lanes[b] : b;
+    if (lane[b] < 0 || lane[b] >= x->max_batch) return set_err(CSM_ERR_ARG, "lane out of range");
+    for (int a = 0; a < b; ++a)
+      if (lane[a] == lane[b]) return set_err(CSM_ERR_ARG, "two batch rows name the same cache lane");
+    if (x->lane_len[lane[b]] + S > x->cfg.max_seq_len)
+      return set_err(CSM_ERR_OVERFLOW, "KV cache overflow (cache_pos + seq_len > max_seq_len)");
+    if (x->lane_len[lane[b]] != x->lane_len[lane[0]]) uniform = false;
+  }
   FrameParams p;
   memset(&p, 0, sizeof(p));
   p.tokens = tokens; p.mask = tokens_mask; p.pos = input_pos; p.out = out;
-  p.temperature = temperature; p.topk = topk; p.B = B; p.S = S; p.cache_len = x->cache_len;
+  p.temperature = temperature; p.topk = topk; p.B = B; p.S = S; p.cache_len = x->lane_len[lane[0]];
+  if (!uniform) {
+    for (int off = 0; off < B; off += 256) {
+      LaneChunk ch;
+      ch.n = B - off < 256 ? B - off : 256; ch.off = off; ch.B = B;
+      for (int i = 0; i < ch.n; ++i) {
+        ch.lane[i] = lane[off + i];
+        ch.len[i] = x->lane_len[lane[off + i]];
+      }
+      k_set_lanes<<<1, 256, 0, st>>>(x->d_lane_meta, ch); COUNT_LAUNCH();
+    }
+    CU_TRY(cudaGetLastError());
+    p.lane_meta = x->d_lane_meta;
+  }
+  auto advance = [&]() {
+    for (int b = 0; b < B; ++b) x->lane_len[lane[b]] += S;
+    x->cache_len = x->lane_len[0];
+  };
   int path = 0;
   if (opts) {
     p.noise = (const bf16*)opts->noise; p.forced = opts->forced; p.logits_out = (bf16*)opts->logits_out;
@@ -932,7 +977,7 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
   if (path == CSM_PATH_MEGA) {
     int rc = launch_mega(x, p, st);
     if (rc != CSM_OK) return rc;
-    x->cache_len += S;
+    advance();
     return CSM_OK;
   }
   k_set_params<<<1, 1, 0, st>>>(x->d_params, p, S == 1 ? x->d_sync : nullptr); COUNT_LAUNCH();
@@ -953,7 +998,7 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
     CU_TRY(cudaGraphLaunch(ge, st));
     g_launches.fetch_add(x->graph_nodes[B], std::memory_order_relaxed);
   }
-  x->cache_len += S;
+  advance();
   return CSM_OK;
 }
 

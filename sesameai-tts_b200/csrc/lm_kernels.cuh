@@ -22,9 +22,27 @@ struct FrameParams {
   float temperature;
   int topk;
   int B, S;
-  int cache_len;           // backbone positions already in the cache before this call
+  int cache_len;           // backbone positions already in the cache before this call (lock-step batch: every stream)
   int s0;                  // first prompt row handled by the current prefill chunk
+  // Continuous batching: batch row b runs on cache lane lane_meta[b] which already holds lane_meta[B + b]
+  // positions.  Null: row b = lane b, every lane holds cache_len positions (the reference's lock-step batch).
+  const int* lane_meta;
 };
+__device__ __forceinline__ int row_lane(const FrameParams* P, int b) { return P->lane_meta ? P->lane_meta[b] : b; }
+__device__ __forceinline__ int row_len(const FrameParams* P, int b) { return P->lane_meta ? P->lane_meta[P->B + b] : P->cache_len; }
+
+// lane table of one call, passed in kernel-parameter space (no host buffer has to outlive the call)
+struct LaneChunk {
+  int n, off, B;
+  int lane[256], len[256];
+};
+__global__ void k_set_lanes(int* meta, LaneChunk c) {
+  const int i = threadIdx.x;
+  if (i < c.n) {
+    meta[c.off + i] = c.lane[i];
+    meta[c.B + c.off + i] = c.len[i];
+  }
+}
 
 struct DevStatus;
 __global__ void k_set_params(FrameParams* dst, FrameParams v, DevStatus* st_reset = nullptr);
@@ -107,7 +125,7 @@ __global__ void k_embed_pass(const FrameParams* __restrict__ P, const bf16* text
   const size_t fr = (size_t)b * P->S + s;
   embed_row(P->tokens + fr * (C + 1), P->mask + fr * (C + 1), text_emb, audio_emb, C, V, D, h + (size_t)n * D, TV, st);
   if (threadIdx.x == 0) {
-    const int slot = P->cache_len + s;
+    const int slot = row_len(P, b) + s;
     int64_t pos = P->pos[fr];
     // the key range of a row is its cache slot (key <= slot); the reference masks by input_pos: they agree
     // exactly when input_pos == cache position, the only use the reference makes of it
@@ -115,7 +133,7 @@ __global__ void k_embed_pass(const FrameParams* __restrict__ P, const bf16* text
       report_error(st, 0x803);
       pos = slot;
     }
-    row_stream[n] = b;
+    row_stream[n] = row_lane(P, b);
     row_pos[n] = (int)pos;
     row_slot[n] = slot;
   }

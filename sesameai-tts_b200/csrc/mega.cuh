@@ -226,12 +226,11 @@ __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1
 // cache rows pay for the writer fence, after their tagged stores went out, so it overlaps the hand-off
 // the CTA waits for anyway.  (The backbone cache needs none: its rows are read by the next launch.)
 #ifndef MEGA_KV_FENCE
-#define MEGA_KV_FENCE 1
+#define MEGA_KV_FENCE 7  /* bit 0: QKV-epilogue writers, bit 1: readers (attn_prefetch), bit 2: sampling-phase writers */
 #endif
+template <int WHO>
 __device__ __forceinline__ void kv_fence() {
-#if MEGA_KV_FENCE
-  asm volatile("fence.acq_rel.gpu;" ::: "memory");
-#endif
+  if ((MEGA_KV_FENCE) & WHO) asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
 // ---- tagged activations ------------------------------------------------------------------------------
@@ -435,6 +434,7 @@ struct Ctx {
   unsigned long long* trp;  // trace slots of the current phase (CTA 0, thread 0) or null
   int tid, warp, lane;
   int bb_pos, bb_slot;  // RoPE position / cache slot of the backbone row of this frame
+  int bb_lane;          // cache lane of the stream (continuous batching; 0 for the plain batch-1 use)
   unsigned seq;         // frame counter (tag salt)
   uint32_t tag;         // tag of the words the current phase produces
 };
@@ -513,9 +513,10 @@ __device__ __forceinline__ void epilogue(const Phase& ph, const Ctx& c, int r0, 
       const int kvh = rr >> ph.hd_shift, d = rr & (hd - 1);
       // this step's consumers read the tagged copy; the cache keeps plain bf16 for later steps / frames
       rep_st2(ph.t_kv + ((size_t)n * 2 + (isk ? 0 : 1)) * krows + rr, ph.kv_rs, make_uint2(tword(tag, o0), tword(tag, o1)));
-      bf16* dst = (isk ? ph.kc : ph.vc) + ((size_t)kvh * ph.slots + slot) * hd + d;  // stream 0
+      const int lane = ph.pos_mode == POS_BACKBONE ? c.bb_lane : 0;  // the depth decoder's cache is per-frame scratch
+      bf16* dst = (isk ? ph.kc : ph.vc) + (((size_t)lane * ph.kv_heads + kvh) * ph.slots + slot) * hd + d;
       *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(o0, o1);
-      if (ph.pos_mode == POS_FIXED) kv_fence();  // depth decoder: read by other CTAs later in this launch
+      if (ph.pos_mode == POS_FIXED) kv_fence<1>();  // depth decoder: read by other CTAs later in this launch
     }
   }
 }
@@ -679,7 +680,7 @@ static_assert(A_IOFF + 64 <= XBUF_ELEMS, "attention staging must fit the activat
 __device__ __forceinline__ void attn_prefetch(const Phase& ph, Ctx& c) {
   const int kvn = ph.kv_heads, nold = ph.pos0;  // positions [0, pos0) were written in earlier steps
   const int per = nold * (A_HD / 8);            // 16-byte units of one kv head's K (or V) rows
-  if (nold > 0) kv_fence();  // acquire side: this CTA has seen tagged words that follow the rows' release fences
+  if (nold > 0) kv_fence<2>();  // acquire side: this CTA has seen tagged words that follow the rows' release fences
   for (int u = c.tid; u < 2 * kvn * per; u += NCT) {
     int r = u;
     const bool isv = r >= kvn * per;
@@ -999,8 +1000,8 @@ __device__ __forceinline__ void attn_phase(const Phase& ph, Ctx& c) {
   const int nkeys = slot + 1;
   const int kvh = h / (ph.heads / ph.kv_heads);
   const int krows = ph.kv_heads * hd;
-  const bf16* kp = ph.kc + (size_t)kvh * ph.slots * hd;
-  const bf16* vp = ph.vc + (size_t)kvh * ph.slots * hd;
+  const bf16* kp = ph.kc + ((size_t)c.bb_lane * ph.kv_heads + kvh) * ph.slots * hd;
+  const bf16* vp = ph.vc + ((size_t)c.bb_lane * ph.kv_heads + kvh) * ph.slots * hd;
   float* sc = reinterpret_cast<float*>(c.xs);  // [slots] scores (<= 8 KB)
   float* part = sc + ((ph.slots + 3) & ~3);      // [NCT / (hd/8)][hd] = 8 NCT partial outputs (16-byte aligned)
   float* qs = part + 8 * NCT;                   // [hd]
@@ -1282,7 +1283,7 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
           rep_st4(ph.t_kv + (isk ? 0 : krows) + rr, ph.kv_rs, w);
           bf16* dst = (isk ? ph.kc : ph.vc) + ((size_t)(rr >> ph.hd_shift) * ph.slots + ph.pos0) * hd + (rr & (hd - 1));
           *reinterpret_cast<uint2*>(dst) = v;
-          kv_fence();
+          kv_fence<4>();
         }
       }
     }
@@ -1324,7 +1325,8 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
   Ctx c;
   c.P = P; c.trp = nullptr; c.ring = ring; c.xs = xs; c.full = full; c.empty = empty; c.scratch = scratch; c.iscratch = iscratch;
   c.psum = psum; c.sync = sync; c.cnt = 0; c.tid = threadIdx.x; c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
-  c.bb_slot = P->cache_len + P->S - 1;
+  c.bb_slot = row_len(P, 0) + P->S - 1;
+  c.bb_lane = row_lane(P, 0);
   {
     // batch 1: stream 0, last prompt row.  Keys are masked by cache slot; the reference masks by input_pos:
     // identical when input_pos == cache position (its only use), anything else is reported, not guessed.

@@ -76,6 +76,7 @@ class FrameOpts(C.Structure):
         ("sampled_out", C.c_void_p),
         ("path", C.c_int32),
         ("prefill", C.c_int32),
+        ("lanes", C.POINTER(C.c_int32)),
     ]
 
 
@@ -100,6 +101,8 @@ PROTOTYPES = {
     "csm_reset_caches": (C.c_int32, [C.c_void_p]),
     "csm_cache_len": (C.c_int32, [C.c_void_p]),
     "csm_check_error": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "csm_lane_reset": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "csm_lane_len": (C.c_int32, [C.c_void_p, C.c_int32]),
     "csm_generate_frame": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float,
                                        C.c_int32, C.POINTER(FrameOpts), C.c_void_p, C.c_void_p]),
     "mimi_workspace_bytes": (C.c_size_t, [C.c_int32]),

@@ -228,6 +228,20 @@ class Model(
         except Exception:
             pass
 
+    def clone_for_context(self) -> "Model":
+        """A second decode context over the SAME parameter tensors: the clone gets its own KV caches, workspace
+        and CUDA graphs from its own ``setup_caches`` (``sesameai.serving.LaneGroups`` runs several of them on
+        separate CUDA streams).  Nothing is copied except the module's bookkeeping dicts."""
+        import copy
+
+        m = copy.copy(self)
+        m._parameters = dict(self._parameters)
+        m._buffers = dict(self._buffers)
+        m._modules = dict(self._modules)
+        m._ctx = None
+        m._keep = {}
+        return m
+
     def setup_caches(self, max_batch_size: int) -> None:
         """Reference ``Model.setup_caches`` (``models.py:120-130``): allocates the KV caches (inside
         one torch-owned workspace), packs the weights for the kernels and enables generation."""
@@ -271,6 +285,15 @@ class Model(
         _native.check(_native.lib().csm_reset_caches(self._ctx))
         self._reseed()
 
+    def reset_lane(self, lane: int) -> None:
+        """Rewind one cache lane (a finished stream leaves; the lane is free for the next request)."""
+        if self._ctx is None:
+            raise RuntimeError("Key value caches are not setup. Call ``setup_caches()`` first.")
+        _native.check(_native.lib().csm_lane_reset(self._ctx, int(lane)))
+
+    def lane_len(self, lane: int) -> int:
+        return int(_native.lib().csm_lane_len(self._ctx, int(lane)))
+
     def check_device_error(self) -> None:
         """Raise for an error that an earlier (stream-ordered, asynchronous) call hit on the device.  Costs a
         host memory read, no CUDA call; meaningful once the stream has been synchronised (the frame loop's
@@ -293,10 +316,13 @@ class Model(
                        temperature: float, topk: int, *, noise: Optional[torch.Tensor] = None,
                        forced: Optional[torch.Tensor] = None, logits_out: Optional[torch.Tensor] = None,
                        sampled_out: Optional[torch.Tensor] = None, no_graph: bool = False,
-                       path: int = 0, prefill: int = 0) -> torch.Tensor:
+                       path: int = 0, prefill: int = 0, lanes=None) -> torch.Tensor:
         """(B, S, 33) tokens/mask + (B, S) positions -> (B, 32) int32 codes, like the reference
         (``models.py:132-184``).  Keyword extras are for parity tests: shared Exp(1) ``noise``
-        [32, B, V] bf16, teacher-``forced`` tokens [B, 32] int32, raw ``logits_out`` [32, B, V]."""
+        [32, B, V] bf16, teacher-``forced`` tokens [B, 32] int32, raw ``logits_out`` [32, B, V].
+        ``lanes`` (continuous batching, ``sesameai.serving``): the KV-cache lane of every batch row, distinct
+        ints below ``max_batch_size``; each lane keeps its own length, so streams join, advance in any subset and
+        leave (``reset_lane``) independently.  Default: row b on lane b, the reference's lock-step batch."""
         assert self._ctx is not None, "backbone caches are not enabled"
         self.check_device_error()  # of earlier calls (free: a host memory read)
         dev = tokens.device
@@ -332,6 +358,12 @@ class Model(
             opts.sampled_out = sampled_out.data_ptr()
         opts.path = _native.PATH_DIRECT if no_graph else int(path)
         opts.prefill = int(prefill)
+        if lanes is not None:
+            lane_list = [int(v) for v in lanes]
+            if len(lane_list) != B:
+                raise ValueError("lanes must name one cache lane per batch row")
+            lane_arr = (ctypes.c_int32 * B)(*lane_list)
+            opts.lanes = lane_arr  # host array, read before the call returns
         self._frame_counter += 1
         with torch.cuda.device(dev):
             rc = _native.lib().csm_generate_frame(

@@ -52,3 +52,16 @@ def gather_frames(local: Dict[int, torch.Tensor], n_requests: int, rank: int, wo
                 out[r] = row[2 : 2 + n * codebooks].view(n, codebooks).clone()
     assert all(o is not None for o in out)
     return out  # type: ignore[return-value]
+
+
+def serve_sharded(model, requests, rank: int, world: int, *, lanes: int, temperature: float, topk: int, groups: int = 1,
+                  device="cpu", max_frames: int = 2048, codebooks: int = 32) -> Optional[List[torch.Tensor]]:
+    """BASELINE config 5 ("N concurrent requests on 1/2/4/8 GPUs"): this rank serves its round-robin shard of
+    ``requests`` (``sesameai.serving.Request``) with continuous batching -- ``groups`` lane groups of ``lanes``
+    cache lanes each -- and the finished frames are gathered on rank 0.  No collective on the decode path."""
+    from .serving import LaneGroups
+
+    mine = [requests[i] for i in shard_requests(len(requests), rank, world)]
+    served = LaneGroups(model, groups, lanes, temperature, topk).run(mine) if mine else {}
+    local = {r.rid: served[r.rid].to(torch.int32) for r in mine}
+    return gather_frames(local, len(requests), rank, world, device=device, max_frames=max_frames, codebooks=codebooks)

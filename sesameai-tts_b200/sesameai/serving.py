@@ -1,0 +1,213 @@
+"""Continuous batching on top of ``Model.generate_frame``.
+
+The reference serves ONE stream per ``Generator.generate`` call: prompt, then one ``generate_frame`` per 80 ms
+until the all-zero EOS frame or the frame budget (``sesameai/generator.py:283-294``); its batch semantics are
+lock-step (one shared cache position, ``torch.all(sample == 0)`` over the whole batch, ``models.py:160``).
+Here every request owns a KV-cache *lane* with its own length: a queued request joins by prefilling a free lane
+(a batch-1 call), all active lanes advance together in one batched decode call per frame step, and a stream
+leaves at ITS EOS frame or budget, freeing the lane for the next request.  Per stream the frames are exactly
+what the reference loop would have produced for that request alone (same prompt layout, same EOS rule, same
+feedback of the sampled frame as the next input row).
+
+``LaneGroups`` runs several such batchers on separate CUDA streams and separate decode contexts over the same
+parameter tensors: a decode step is a chain of ~770 short dependent launches, so independent groups overlap in
+the launch gaps and latency bubbles of each other.
+"""
+from __future__ import annotations
+
+from collections import deque
+from dataclasses import dataclass, field
+from typing import Deque, Dict, Iterable, List, Optional, Sequence
+
+import torch
+
+from .models import Model
+
+
+@dataclass
+class Request:
+    """One utterance: prompt frames [S, 33] int64 + mask [S, 33] bool (``Generator._tokenize_*`` layout)."""
+
+    rid: int
+    tokens: torch.Tensor
+    mask: torch.Tensor
+    max_frames: int
+
+
+@dataclass
+class _Stream:
+    req: Request
+    lane: int
+    frames: List[torch.Tensor] = field(default_factory=list)  # device rows [32] int32
+    calls: int = 0  # generate_frame calls spent (the reference's loop counter)
+
+
+class ContinuousBatcher:
+    def __init__(self, model: Model, max_lanes: int, temperature: float, topk: int, *, setup: bool = True,
+                 stream: Optional[torch.cuda.Stream] = None):
+        self.model = model
+        self.max_lanes = int(max_lanes)
+        self.temperature, self.topk = float(temperature), int(topk)
+        if setup:
+            model.setup_caches(self.max_lanes)
+        self.device = next(model.parameters()).device
+        self.stream = stream
+        C = model.config.audio_num_codebooks
+        self._C = C
+        self._last = torch.zeros(self.max_lanes, C, dtype=torch.int32, device=self.device)  # newest frame per lane
+        self._free: List[int] = list(range(self.max_lanes - 1, -1, -1))
+        self._active: Dict[int, _Stream] = {}
+        self._pending: Deque[Request] = deque()
+        self._done: Dict[int, torch.Tensor] = {}
+        self._rows: List[int] = []
+        self._rows_dev: Optional[torch.Tensor] = None
+        self._inflight = None
+        self.steps = 0          # batched decode calls issued
+        self.row_steps = 0      # sum of their batch sizes (= frames computed by decode calls)
+        self.prefills = 0
+
+    # -- queue -------------------------------------------------------------------------------------------
+    def submit(self, req: Request) -> None:
+        self._pending.append(req)
+
+    @property
+    def idle(self) -> bool:
+        return not self._pending and not self._active and self._inflight is None
+
+    def results(self) -> Dict[int, torch.Tensor]:
+        return self._done
+
+    # -- one scheduling round: begin() launches asynchronously, end() looks at the EOS flags -------------------
+    def _ctx(self):
+        return torch.cuda.stream(self.stream) if self.stream is not None else _Null()
+
+    def _lane_len(self, lane: int) -> int:
+        return self.model.lane_len(lane)
+
+    def begin(self) -> None:
+        assert self._inflight is None
+        m = self.model
+        with self._ctx():
+            fresh: List[_Stream] = []
+            # join: prefill a free lane per queued request (the prompt's last row samples the first frame)
+            while self._pending and self._free:
+                req = self._pending.popleft()
+                lane = self._free.pop()
+                m.reset_lane(lane)
+                S = req.tokens.shape[0]
+                tok = req.tokens.to(self.device, torch.int64).unsqueeze(0)
+                msk = req.mask.to(self.device, torch.bool).unsqueeze(0)
+                pos = torch.arange(S, device=self.device).unsqueeze(0)
+                st = _Stream(req, lane)
+                s = m.generate_frame(tok, msk, pos, self.temperature, self.topk, lanes=[lane])
+                self._last[lane] = s[0]
+                st.calls = 1
+                self.prefills += 1
+                fresh.append(st)
+            # advance: one batched decode step for every stream that already holds a frame to feed back
+            rows = sorted(self._active)
+            out = None
+            if rows:
+                if rows != self._rows:
+                    self._rows = rows
+                    self._rows_dev = torch.tensor(rows, dtype=torch.long, device=self.device)
+                B = len(rows)
+                tok = torch.zeros(B, 1, self._C + 1, dtype=torch.int64, device=self.device)
+                tok[:, 0, : self._C] = self._last.index_select(0, self._rows_dev)
+                msk = torch.ones(B, 1, self._C + 1, dtype=torch.bool, device=self.device)
+                msk[:, :, -1] = False
+                pos = torch.tensor([[self._lane_len(l)] for l in rows], dtype=torch.int64, device=self.device)
+                out = m.generate_frame(tok, msk, pos, self.temperature, self.topk, lanes=rows)
+                self._last.index_copy_(0, self._rows_dev, out)
+                for l in rows:
+                    self._active[l].calls += 1
+                self.steps += 1
+                self.row_steps += B
+            for st in fresh:
+                self._active[st.lane] = st
+            lanes_now = sorted(self._active)
+            if not lanes_now:
+                return
+            idx = torch.tensor(lanes_now, dtype=torch.long, device=self.device)
+            newest = self._last.index_select(0, idx)                      # [n, C] frames sampled this round
+            eos = (newest == 0).all(dim=1).to("cpu", non_blocking=True)   # reference generator.py:285, per stream
+            ev = None
+            if self.device.type == "cuda":
+                ev = torch.cuda.Event()
+                ev.record()
+            self._inflight = (lanes_now, newest, eos, ev)
+
+    def end(self) -> None:
+        if self._inflight is None:
+            return
+        lanes_now, newest, eos, ev = self._inflight
+        self._inflight = None
+        if ev is not None:
+            ev.synchronize()
+        self.model.check_device_error()
+        for i, lane in enumerate(lanes_now):
+            st = self._active[lane]
+            finished = bool(eos[i])
+            if not finished:
+                st.frames.append(newest[i])
+                finished = st.calls >= st.req.max_frames
+            if finished:
+                C = self._C
+                self._done[st.req.rid] = (torch.stack(st.frames).cpu() if st.frames
+                                          else torch.zeros(0, C, dtype=torch.int32))
+                del self._active[lane]
+                self._free.append(lane)
+
+    def run(self, requests: Iterable[Request]) -> Dict[int, torch.Tensor]:
+        for r in requests:
+            self.submit(r)
+        while not self.idle:
+            self.begin()
+            self.end()
+        return self._done
+
+
+class _Null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+class LaneGroups:
+    """``groups`` independent ContinuousBatchers (own decode context + CUDA stream each, shared parameters);
+    requests are dealt round-robin.  All groups launch their round before any of them waits for its EOS flags."""
+
+    def __init__(self, model: Model, groups: int, lanes_per_group: int, temperature: float, topk: int):
+        self.batchers: List[ContinuousBatcher] = []
+        dev = next(model.parameters()).device
+        for g in range(groups):
+            mg = model if g == 0 else model.clone_for_context()
+            st = torch.cuda.Stream(device=dev) if groups > 1 and dev.type == "cuda" else None
+            if st is not None:
+                st.wait_stream(torch.cuda.current_stream(dev))
+            with (torch.cuda.stream(st) if st is not None else _Null()):
+                self.batchers.append(ContinuousBatcher(mg, lanes_per_group, temperature, topk, stream=st))
+
+    def run(self, requests: Sequence[Request]) -> Dict[int, torch.Tensor]:
+        for i, r in enumerate(requests):
+            self.batchers[i % len(self.batchers)].submit(r)
+        while not all(b.idle for b in self.batchers):
+            for b in self.batchers:
+                if not b.idle:
+                    b.begin()
+            for b in self.batchers:
+                b.end()
+        out: Dict[int, torch.Tensor] = {}
+        for b in self.batchers:
+            out.update(b.results())
+        return out
+
+    @property
+    def steps(self) -> int:
+        return sum(b.steps for b in self.batchers)
+
+    @property
+    def row_steps(self) -> int:
+        return sum(b.row_steps for b in self.batchers)
