@@ -211,11 +211,29 @@ size_t mimi_workspace_bytes(int32_t max_frames);
  * into ``workspace`` on ``stream`` and synchronises that stream once. */
 int32_t mimi_create(const void *const *weights, int32_t n_weights, int32_t max_frames, void *workspace,
                     size_t workspace_bytes, void *stream, mimi_ctx **out);
+/* T may exceed max_frames: the decode then runs in windows of max_frames frames that carry their causal left
+ * context (conv tails, transformer K/V of the last 249 positions), bit-identical to one pass. */
 int32_t mimi_decode(mimi_ctx *ctx, const int64_t *codes, int32_t B, int32_t K, int32_t T, float *out, void *stream);
+
+/* Stateful streaming decode.  The reference's generate_stream decodes every 10-frame
+ * buffer statelessly (sesameai/generator.py:61,111-117,189-196), so each chunk starts from silence; a
+ * mimi_stream carries the causal left context from chunk to chunk, and the concatenated chunks equal the
+ * one-shot decode of the whole utterance bit for bit.  ``state`` is a caller-owned device buffer of
+ * mimi_stream_state_bytes() bytes (256-byte aligned); one stream = one utterance at a time. */
+typedef struct mimi_stream mimi_stream;
+size_t mimi_stream_state_bytes(void);
+int32_t mimi_stream_create(mimi_ctx *ctx, void *state, size_t state_bytes, void *stream, mimi_stream **out);
+int32_t mimi_stream_reset(mimi_stream *s, void *stream);          /* start of a new utterance */
+/* codes int64 [K, T] (the next T frames of the utterance) -> out fp32 [1920*T] */
+int32_t mimi_decode_stream(mimi_stream *s, const int64_t *codes, int32_t K, int32_t T, float *out, void *stream);
+void mimi_stream_destroy(mimi_stream *s);
 /* Replaces moshi's ``MimiModel.encode`` (reference sesameai/generator.py:86: voice-prompt audio ->
  * codes): wav fp32 [B, L] at 24 kHz (zero-padded on the right to whole 1920-sample frames) ->
  * codes int64 [B, K, ceil(L/1920)], K <= 32 codebooks (nearest centroid per residual layer). */
 int32_t mimi_encode(mimi_ctx *ctx, const float *wav, int32_t B, int64_t L, int32_t K, int64_t *codes, void *stream);
+/* Test entry: the split-RVQ nearest-centroid search of mimi_encode alone, on a given 12.5 Hz latent
+ * (fp32 [T, 512] time-major, T <= max_frames) -> codes int64 [K, T]. */
+int32_t mimi_k_rvq_encode(mimi_ctx *ctx, const float *latent, int32_t T, int32_t K, int64_t *codes, void *stream);
 void mimi_destroy(mimi_ctx *ctx);
 
 /* Profiling aid: dev uint64 [n_ctas][n_phases][16] buffer that thread 0 of every CTA of the decode

@@ -284,9 +284,9 @@ class OracleMimi(nn.Module):
         return torch.stack(out, dim=1)  # [B, n_q, T]
 
     @torch.no_grad()
-    def encode(self, wav: torch.Tensor) -> torch.Tensor:
-        """wav [B, 1, L] fp32 at 24 kHz -> codes [B, num_codebooks, ceil(L / 1920)] int64 (moshi
-        ``MimiModel.encode``; the waveform is zero-padded on the right to a whole number of frames)."""
+    def encode_latent(self, wav: torch.Tensor) -> torch.Tensor:
+        """wav [B, 1, L] -> the 12.5 Hz latent [B, 512, T] the split RVQ quantises (everything of ``encode``
+        before the search)."""
         if not hasattr(self, "encoder"):
             raise RuntimeError("call _build_encoder() before loading encoder weights")
         L = wav.shape[-1]
@@ -295,9 +295,36 @@ class OracleMimi(nn.Module):
         emb = self.seanet_encode(x)
         emb = self._transformer_layers(emb, self.encoder_transformer.transformer.layers)
         ds = self.downsample.conv.conv.conv
-        emb = F.conv1d(F.pad(emb, (2, 0), mode="replicate"), ds.weight, None, stride=2)
+        return F.conv1d(F.pad(emb, (2, 0), mode="replicate"), ds.weight, None, stride=2)
+
+    @torch.no_grad()
+    def quantize_latent(self, emb: torch.Tensor) -> torch.Tensor:
+        """latent [B, 512, T] -> codes [B, num_codebooks, T] (moshi SplitResidualVectorQuantizer.encode)."""
         nq = self.num_codebooks
         first = self._rvq_encode(self.quantizer.rvq_first, emb, 1)
         if nq > 1:
             return torch.cat([first, self._rvq_encode(self.quantizer.rvq_rest, emb, nq - 1)], dim=1)
         return first
+
+    @torch.no_grad()
+    def latent_for_codes(self, codes: torch.Tensor) -> torch.Tensor:
+        """Test helper (not a moshi function): a latent [B, 512, T] whose two input projections land exactly on
+        the centroid sums of ``codes`` [B, K, T] -- least-squares solve of [W_first; W_rest] z = [e_0 ; sum_k e_k]
+        in fp64 -- so the search's decisions have the margins of the codebooks, not of encoder rounding."""
+        B, K, T = codes.shape
+        wf = self.quantizer.rvq_first.input_proj.weight[:, :, 0].double()
+        wr = self.quantizer.rvq_rest.input_proj.weight[:, :, 0].double()
+        tf = self.quantizer.rvq_first.vq.layers[0]._codebook.embedding.double()[codes[:, 0]]  # [B, T, 256]
+        tr = torch.zeros_like(tf)
+        for k in range(1, K):
+            tr = tr + self.quantizer.rvq_rest.vq.layers[k - 1]._codebook.embedding.double()[codes[:, k]]
+        A = torch.cat([wf, wr], dim=0)                      # [512, 512]
+        rhs = torch.cat([tf, tr], dim=-1).reshape(-1, 512)  # [B*T, 512]
+        z = torch.linalg.lstsq(A, rhs.t()).solution.t()     # [B*T, 512]
+        return z.reshape(B, T, 512).transpose(1, 2).float().contiguous()
+
+    @torch.no_grad()
+    def encode(self, wav: torch.Tensor) -> torch.Tensor:
+        """wav [B, 1, L] fp32 at 24 kHz -> codes [B, num_codebooks, ceil(L / 1920)] int64 (moshi
+        ``MimiModel.encode``; the waveform is zero-padded on the right to a whole number of frames)."""
+        return self.quantize_latent(self.encode_latent(wav))

@@ -50,7 +50,46 @@ struct mimi_ctx {
   float *q512, *e, *xs, *xn, *qkv, *att, *ff, *c0, *u[4], *r[4];
   // encode side
   float *enc_res1[4], *enc_down[4], *enc_final, *dsw, *enorm, *wavbuf, *p1, *p2, *dots;
-  size_t pad_rows_bytes;
+  float* own_state;  // stream state of the one-shot decode (windows of max_frames carry their left context in it)
+};
+
+// ---- streamed decode state ------------------------------------------------------------------------
+// Everything a causal chunk needs from the frames before it (device floats, caller-owned buffer):
+//   e_prev [512]            last row of the RVQ output (depthwise ConvTranspose1d k=4 s=2 reads x[q-1])
+//   kv[l]  [249][1024]      RoPE'd K | V of the last <= 249 transformer positions, per layer (window 250)
+//   xs_tail [6][512]        last 6 transformer outputs (SEANet Conv1d k=7)
+//   c0_tail [1024]          last row of conv0's output (stage-0 ConvTranspose1d reads x[q-1])
+//   per stage s: pre[s] [2][C_s] last 2 rows of the ConvTranspose1d output BEFORE the residual block adds to it
+//                           (its Conv1d k=3), post[s] [n][C_s] last row(s) after it (next stage's x[q-1]; the final
+//                           Conv1d k=3 needs n = 2)
+namespace {
+const int HIST = 249;
+struct StateLayout {
+  size_t e_prev, kv[8], xs_tail, c0_tail, pre[4], post[4], total;
+};
+StateLayout state_layout() {
+  StateLayout L;
+  size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += (n + 63) & ~(size_t)63; return r; };
+  L.e_prev = take(512);
+  for (int l = 0; l < 8; ++l) L.kv[l] = take((size_t)HIST * 1024);
+  L.xs_tail = take(6 * 512);
+  L.c0_tail = take(1024);
+  int co = 512;
+  for (int s = 0; s < 4; ++s) {
+    L.pre[s] = take(2 * (size_t)co);
+    L.post[s] = take((s == 3 ? 2 : 1) * (size_t)co);
+    co /= 2;
+  }
+  L.total = o;
+  return L;
+}
+}  // namespace
+
+struct mimi_stream {
+  mimi_ctx* x;
+  float* st;
+  long long frames;  // frames decoded so far
 };
 
 static size_t mimi_carve(mimi_ctx* x, char* base) {
@@ -86,7 +125,8 @@ static size_t mimi_carve(mimi_ctx* x, char* base) {
   x->e = cv.take(T * 512);
   x->xs = cv.take((L + PAD) * 512);
   x->xn = cv.take(L * 512);
-  x->qkv = cv.take(L * 1536);
+  x->qkv = cv.take((L + HIST + 7) * 1536);  // + carried K/V rows of a streamed decode in front
+  x->own_state = cv.take(state_layout().total);
   x->att = cv.take(L * 512);
   x->ff = cv.take(L * 2048);
   x->c0 = cv.take((L + PAD) * 1024);
@@ -115,7 +155,7 @@ static int g_gemm_mode = -1;  // 0 auto, 1 fp32, 2 tf32x3 (read-only after the f
 static thread_local bool g_precise = false;  // per calling thread: two threads may drive two codecs
 static cudaError_t gemm(cudaStream_t st, const float* A, long long lda, const float* B, float* C, long long ldc, long long M,
                         int N, int K, const float* bias, int bias_period, int flags, const float* R = nullptr,
-                        long long ldr = 0, const float* scale = nullptr) {
+                        long long ldr = 0, const float* scale = nullptr, bool fp32_fma = false) {
   if (g_gemm_mode < 0) {
     const char* e = getenv("MIMI_GEMM");
     g_gemm_mode = !e ? 0 : (!strcmp(e, "fp32") ? 1 : (!strcmp(e, "tf32x3") ? 2 : 0));
@@ -123,7 +163,9 @@ static cudaError_t gemm(cudaStream_t st, const float* A, long long lda, const fl
   mimi::GemmArgs g;
   g.A = A; g.lda = lda; g.B = B; g.C = C; g.ldc = ldc; g.M = (int)M; g.N = N; g.K = K;
   g.bias = bias; g.bias_period = bias_period > 0 ? bias_period : 1; g.R = R; g.ldr = ldr; g.scale = scale; g.flags = flags;
-  const bool tc_ok = g_gemm_mode != 1 && K % mimi::TBK == 0 && lda % 4 == 0 && (((uintptr_t)A | (uintptr_t)B) & 15) == 0;
+  // fp32_fma: true fp32 multiply-add on the CUDA cores (the split-RVQ search: an argmin over 2048 distances whose
+  // top-2 gap can be a few fp32 ulps must not see tensor-core product rounding at all)
+  const bool tc_ok = !fp32_fma && g_gemm_mode != 1 && K % mimi::TBK == 0 && lda % 4 == 0 && (((uintptr_t)A | (uintptr_t)B) & 15) == 0;
   if (tc_ok) {
     dim3 grid((N + mimi::TBN - 1) / mimi::TBN, (unsigned)((M + mimi::TBM - 1) / mimi::TBM));
     if (g_precise || g_gemm_mode == 2) mimi::k_tgemm<3><<<grid, 256, 0, st>>>(g);
@@ -200,21 +242,67 @@ extern "C" int32_t mimi_create(const void* const* weights, int32_t n_weights, in
 
 extern "C" void mimi_destroy(mimi_ctx* x) { delete x; }
 
-// 8-layer causal transformer (context 250) in place on xs [L, 512]; lw0 = first of the 80 layer tensors
-static int mimi_transformer(mimi_ctx* x, float* xs, long long L, int w_layer0, cudaStream_t st) {
+static void copy_rows(cudaStream_t st, const float* src, long long lds, float* dst, long long ldd, long long rows, int cols) {
+  if (rows <= 0) return;
+  const long long n = rows * cols;
+  mimi::k_copy_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, lds, dst, ldd, (int)rows, cols);
+  csm_count_launches(1);
+}
+
+// 8-layer causal transformer (context 250) in place on xs [L, 512]; lw0 = first of the 80 layer tensors.
+// ``kv`` (streamed decode, else null): per-layer history of the hist = min(pos0, 249) positions before this chunk
+// (pos0 = absolute position of row 0); it is read into the rows in front of the chunk's q/k/v and updated.
+static int mimi_transformer(mimi_ctx* x, float* xs, long long L, int w_layer0, cudaStream_t st, float* const* kv = nullptr,
+                            long long pos0 = 0) {
   using namespace mimi;
+  const int hist = kv ? (int)(pos0 < HIST ? pos0 : HIST) : 0;
+  float* qkv = x->qkv + (size_t)hist * 1536;  // rows of this chunk
   for (int l = 0; l < 8; ++l) {
     const float* const* lw = &x->w[w_layer0 + 10 * l];
     k_layernorm512<<<(unsigned)((L + 7) / 8), 256, 0, st>>>(xs, lw[2], lw[3], (int)L, 1e-5f, x->xn);
-    MCU_TRY(gemm(st, x->xn, 512, lw[0], x->qkv, 1536, L, 1536, 512, nullptr, 0, 0));
-    k_rope_qk<<<(unsigned)((L * 512 + 255) / 256), 256, 0, st>>>(x->qkv, (int)L);
-    k_attn_window<<<dim3((unsigned)((L + 3) / 4), 8), 128, 0, st>>>(x->qkv, (int)L, 250, x->att);
+    MCU_TRY(gemm(st, x->xn, 512, lw[0], qkv, 1536, L, 1536, 512, nullptr, 0, 0));
+    k_rope_qk<<<(unsigned)((L * 512 + 255) / 256), 256, 0, st>>>(qkv, (int)L, kv ? pos0 : 0);
+    if (kv) copy_rows(st, kv[l], 1024, x->qkv + 512, 1536, hist, 1024);
+    k_attn_window<<<dim3((unsigned)((L + 3) / 4), 8), 128, 0, st>>>(x->qkv, (int)L, 250, x->att, hist);
+    if (kv) {
+      const long long keep = hist + L < HIST ? hist + L : HIST;
+      copy_rows(st, x->qkv + (size_t)(hist + L - keep) * 1536 + 512, 1536, kv[l], 1024, keep, 1024);
+    }
     MCU_TRY(gemm(st, x->att, 512, lw[1], xs, 512, L, 512, 512, nullptr, 0, F_LAYERSCALE | F_RESID, xs, 512, lw[8]));
     k_layernorm512<<<(unsigned)((L + 7) / 8), 256, 0, st>>>(xs, lw[4], lw[5], (int)L, 1e-5f, x->xn);
     MCU_TRY(gemm(st, x->xn, 512, lw[6], x->ff, 2048, L, 2048, 512, nullptr, 0, F_GELU));
     MCU_TRY(gemm(st, x->ff, 2048, lw[7], xs, 512, L, 512, 2048, nullptr, 0, F_LAYERSCALE | F_RESID, xs, 512, lw[9]));
     csm_count_launches(4);
   }
+  MCU_TRY(cudaGetLastError());
+  return CSM_OK;
+}
+
+// the conv inputs' pad rows are zero for the encoder (it starts every utterance from silence)
+static cudaError_t zero_pads(mimi_ctx* x, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(x->xs, 0, (size_t)PAD * 512 * sizeof(float), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(x->c0, 0, (size_t)PAD * 1024 * sizeof(float), st);
+  int co = 512;
+  for (int s = 0; s < 4 && e == cudaSuccess; ++s) {
+    e = cudaMemsetAsync(x->u[s], 0, (size_t)PAD * co * sizeof(float), st);
+    co /= 2;
+  }
+  return e;
+}
+
+// split RVQ search on the latent x->e [T, 512]: the semantic codebook on its own projection, the acoustic
+// codebooks on theirs; nearest centroid per layer on the running residual (true fp32 FMA distances)
+static int rvq_search(mimi_ctx* x, int T, int K, int64_t* codes /*[K, T]*/, cudaStream_t st) {
+  using namespace mimi;
+  MCU_TRY(gemm(st, x->e, 512, x->w[MIMI_W_RVQ_FIRST_INPROJ], x->p1, 256, T, 256, 512, nullptr, 0, 0, nullptr, 0, nullptr, true));
+  MCU_TRY(gemm(st, x->e, 512, x->w[MIMI_W_RVQ_REST_INPROJ], x->p2, 256, T, 256, 512, nullptr, 0, 0, nullptr, 0, nullptr, true));
+  for (int k = 0; k < K; ++k) {
+    float* res = k == 0 ? x->p1 : x->p2;
+    const float* emb = x->emb + (size_t)k * 2048 * 256;
+    MCU_TRY(gemm(st, res, 256, emb, x->dots, 2048, T, 2048, 256, nullptr, 0, 0, nullptr, 0, nullptr, true));
+    k_rvq_argmin<<<(unsigned)T, 256, 0, st>>>(x->dots, x->enorm + (size_t)k * 2048, emb, res, codes + (size_t)k * T);
+  }
+  csm_count_launches(K);
   MCU_TRY(cudaGetLastError());
   return CSM_OK;
 }
@@ -231,6 +319,7 @@ extern "C" int32_t mimi_encode(mimi_ctx* x, const float* wav, int32_t B, int64_t
     ~Precise() { g_precise = false; }
   } precise_scope;
   const int eratio[4] = {4, 5, 6, 8};
+  MCU_TRY(zero_pads(x, st));  // a streamed decode leaves carried rows there
   for (int b = 0; b < B; ++b) {
     // waveform, zero-padded to whole frames, 8 zero samples in front (causal k = 7)
     float* wv = x->wavbuf + 8;
@@ -264,62 +353,127 @@ extern "C" int32_t mimi_encode(mimi_ctx* x, const float* wav, int32_t B, int64_t
     k_pad_rows<<<2, 256, 0, st>>>(xs, 512, 1);
     MCU_TRY(gemm(st, xs - 2 * 512, 1024, x->dsw, x->e, 512, T, 512, 4 * 512, nullptr, 0, 0));
     k_pad_rows<<<2, 256, 0, st>>>(xs, 512, 0);
-    // split RVQ: semantic codebook on its own projection, acoustic codebooks on theirs
-    MCU_TRY(gemm(st, x->e, 512, x->w[MIMI_W_RVQ_FIRST_INPROJ], x->p1, 256, T, 256, 512, nullptr, 0, 0));
-    MCU_TRY(gemm(st, x->e, 512, x->w[MIMI_W_RVQ_REST_INPROJ], x->p2, 256, T, 256, 512, nullptr, 0, 0));
-    for (int k = 0; k < K; ++k) {
-      float* res = k == 0 ? x->p1 : x->p2;
-      const float* emb = x->emb + (size_t)k * 2048 * 256;
-      MCU_TRY(gemm(st, res, 256, emb, x->dots, 2048, T, 2048, 256, nullptr, 0, 0));
-      k_rvq_argmin<<<(unsigned)T, 256, 0, st>>>(x->dots, x->enorm + (size_t)k * 2048, emb, res, codes + ((size_t)b * K + k) * T);
-    }
-    csm_count_launches(2 + K);
+    int rc2 = rvq_search(x, (int)T, K, codes + (size_t)b * K * T, st);
+    if (rc2 != CSM_OK) return rc2;
     MCU_TRY(cudaGetLastError());
   }
+  return CSM_OK;
+}
+
+// Test entry: the split-RVQ search alone on a given latent (time-major [T, 512] fp32) -> codes [K, T].
+extern "C" int32_t mimi_k_rvq_encode(mimi_ctx* x, const float* latent, int32_t T, int32_t K, int64_t* codes, void* stream) {
+  if (!x) return csm_set_error(CSM_ERR_STATE, "mimi_k_rvq_encode: null context");
+  if (!latent || !codes || T < 1 || T > x->max_frames || K < 1 || K > 32) return csm_set_error(CSM_ERR_ARG, "mimi_k_rvq_encode: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  MCU_TRY(cudaMemcpyAsync(x->e, latent, (size_t)T * 512 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return rvq_search(x, T, K, codes, st);
+}
+
+// One causal chunk of one utterance: frames [0, T) of ``codes`` ([K, ldt] layout) continue the stream whose
+// left context is ``sbuf`` (``frames_done`` frames so far; an all-zero state = the start of an utterance).
+static int decode_chunk(mimi_ctx* x, float* sbuf, long long frames_done, const int64_t* codes, int K, int T, long long ldt,
+                        float* wav, cudaStream_t st) {
+  using namespace mimi;
+  const StateLayout SL = state_layout();
+  const long long L = 2LL * T;
+  k_rvq_gather<<<T, 256, 0, st>>>(codes, K, T, ldt, x->emb, x->q512);
+  MCU_TRY(gemm(st, x->q512, 512, x->wproj, x->e, 512, T, 512, 512, nullptr, 0, 0));
+  float* xs = x->xs + (size_t)PAD * 512;
+  k_upsample2<<<(unsigned)((L * 512 + 255) / 256), 256, 0, st>>>(x->e, x->w[MIMI_W_UPSAMPLE], T, 512, xs, sbuf + SL.e_prev);
+  copy_rows(st, x->e + (size_t)(T - 1) * 512, 512, sbuf + SL.e_prev, 512, 1, 512);
+  csm_count_launches(2);
+  {
+    float* kv[8];
+    for (int l = 0; l < 8; ++l) kv[l] = sbuf + SL.kv[l];
+    int rc = mimi_transformer(x, xs, L, MIMI_W_LAYER0, st, kv, 2 * frames_done);
+    if (rc != CSM_OK) return rc;
+  }
+  // SEANet decoder.  Before a conv reads a buffer, the rows in front of it are loaded with the carried tail of
+  // the previous chunk; the new tail is saved by reading THROUGH those rows (a chunk may be shorter than the tail).
+  copy_rows(st, sbuf + SL.xs_tail, 512, xs - 6 * 512, 512, 6, 512);
+  copy_rows(st, xs + (L - 6) * 512, 512, sbuf + SL.xs_tail, 512, 6, 512);
+  float* c0 = x->c0 + (size_t)PAD * 1024;
+  MCU_TRY(gemm(st, xs - 6 * 512, 512, x->conv0, c0, 1024, L, 1024, 7 * 512, x->w[MIMI_W_CONV0 + 1], 1024, 0));
+  copy_rows(st, sbuf + SL.c0_tail, 1024, c0 - 1024, 1024, 1, 1024);
+  copy_rows(st, c0 + (L - 1) * 1024, 1024, sbuf + SL.c0_tail, 1024, 1, 1024);
+  const float* in = c0;
+  long long rows = L;
+  int ch = 1024;
+  for (int s = 0; s < 4; ++s) {
+    const float* const* sw = &x->w[MIMI_W_STAGE0 + 6 * s];
+    const int r = RATIOS[s], co = ch / 2, hid = ch / 4;
+    float* u = x->u[s] + (size_t)PAD * co;
+    // ELU -> ConvTranspose1d(ch -> ch/2, kernel 2r, stride r): rows x[q-1], x[q]
+    MCU_TRY(gemm(st, in - ch, ch, x->convtr[s], u, (long long)r * co, rows, r * co, 2 * ch, sw[1], co, F_A_ELU));
+    rows *= r;
+    // residual block: u + conv1(ELU(conv3(ELU(u)))); conv3 sees the previous chunk's last two PRE-residual rows
+    copy_rows(st, sbuf + SL.pre[s], co, u - 2 * co, co, 2, co);
+    copy_rows(st, u + (rows - 2) * co, co, sbuf + SL.pre[s], co, 2, co);
+    MCU_TRY(gemm(st, u - 2 * co, co, x->res1[s], x->r[s], hid, rows, hid, 3 * co, sw[3], hid, F_A_ELU));
+    MCU_TRY(gemm(st, x->r[s], hid, sw[4], u, co, rows, co, hid, sw[5], co, F_A_ELU | F_RESID, u, co));
+    // what follows (next ConvTranspose1d: 1 row; final Conv1d k=3: 2 rows) sees the POST-residual tail
+    const int np = s == 3 ? 2 : 1;
+    copy_rows(st, sbuf + SL.post[s], co, u - (size_t)np * co, co, np, co);
+    copy_rows(st, u + (rows - np) * co, co, sbuf + SL.post[s], co, np, co);
+    in = u;
+    ch = co;
+  }
+  k_final_conv<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(in, x->finalw, x->final_bias, rows, wav);
+  csm_count_launches(1);
+  MCU_TRY(cudaGetLastError());
   return CSM_OK;
 }
 
 extern "C" int32_t mimi_decode(mimi_ctx* x, const int64_t* codes, int32_t B, int32_t K, int32_t T, float* out, void* stream) {
   if (!x) return csm_set_error(CSM_ERR_STATE, "mimi_decode: null context");
   if (!codes || !out || B < 1 || K < 1 || K > 32 || T < 1) return csm_set_error(CSM_ERR_ARG, "mimi_decode: bad arguments");
-  if (T > x->max_frames) return csm_set_error(CSM_ERR_OVERFLOW, "mimi_decode: more frames than the codec was created for");
   cudaStream_t st = (cudaStream_t)stream;
-  const long long L = 2LL * T;
-  using namespace mimi;
+  const StateLayout SL = state_layout();
+  // any length: windows of at most max_frames frames, the causal left context carried between them
+  // (moshi's MimiModel.decode has no length limit either)
   for (int b = 0; b < B; ++b) {
-    const int64_t* cb = codes + (size_t)b * K * T;
-    float* wav = out + (size_t)b * 1920 * T;
-    k_rvq_gather<<<T, 256, 0, st>>>(cb, K, T, x->emb, x->q512);
-    MCU_TRY(gemm(st, x->q512, 512, x->wproj, x->e, 512, T, 512, 512, nullptr, 0, 0));
-    float* xs = x->xs + (size_t)PAD * 512;
-    k_upsample2<<<(unsigned)((L * 512 + 255) / 256), 256, 0, st>>>(x->e, x->w[MIMI_W_UPSAMPLE], T, 512, xs);
-    csm_count_launches(2);
-    {
-      int rc = mimi_transformer(x, xs, L, MIMI_W_LAYER0, st);
+    MCU_TRY(cudaMemsetAsync(x->own_state, 0, SL.total * sizeof(float), st));
+    for (int t0 = 0; t0 < T; t0 += x->max_frames) {
+      const int n = T - t0 < x->max_frames ? T - t0 : x->max_frames;
+      int rc = decode_chunk(x, x->own_state, t0, codes + (size_t)b * K * T + t0, K, n, T, out + (size_t)b * 1920 * T + (size_t)t0 * 1920, st);
       if (rc != CSM_OK) return rc;
     }
-    // SEANet decoder
-    float* c0 = x->c0 + (size_t)PAD * 1024;
-    MCU_TRY(gemm(st, xs - 6 * 512, 512, x->conv0, c0, 1024, L, 1024, 7 * 512, x->w[MIMI_W_CONV0 + 1], 1024, 0));
-    const float* in = c0;
-    long long rows = L;
-    int ch = 1024;
-    for (int s = 0; s < 4; ++s) {
-      const float* const* sw = &x->w[MIMI_W_STAGE0 + 6 * s];
-      const int r = RATIOS[s], co = ch / 2, hid = ch / 4;
-      float* u = x->u[s] + (size_t)PAD * co;
-      // ELU -> ConvTranspose1d(ch -> ch/2, kernel 2r, stride r): rows x[q-1], x[q]
-      MCU_TRY(gemm(st, in - ch, ch, x->convtr[s], u, (long long)r * co, rows, r * co, 2 * ch, sw[1], co, F_A_ELU));
-      rows *= r;
-      // residual block: u + conv1(ELU(conv3(ELU(u))))
-      MCU_TRY(gemm(st, u - 2 * co, co, x->res1[s], x->r[s], hid, rows, hid, 3 * co, sw[3], hid, F_A_ELU));
-      MCU_TRY(gemm(st, x->r[s], hid, sw[4], u, co, rows, co, hid, sw[5], co, F_A_ELU | F_RESID, u, co));
-      in = u;
-      ch = co;
-    }
-    k_final_conv<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(in, x->finalw, x->final_bias, rows, wav);
-    csm_count_launches(1);
-    MCU_TRY(cudaGetLastError());
+  }
+  return CSM_OK;
+}
+
+extern "C" size_t mimi_stream_state_bytes(void) { return state_layout().total * sizeof(float); }
+
+extern "C" int32_t mimi_stream_create(mimi_ctx* x, void* state, size_t state_bytes, void* stream, mimi_stream** out) {
+  if (!out) return csm_set_error(CSM_ERR_ARG, "out is null");
+  *out = nullptr;
+  if (!x) return csm_set_error(CSM_ERR_STATE, "mimi_stream_create: null context");
+  if (!state || ((uintptr_t)state & 255) || state_bytes < mimi_stream_state_bytes())
+    return csm_set_error(CSM_ERR_WORKSPACE, "mimi_stream_create: state buffer missing, misaligned or too small");
+  mimi_stream* s = new (std::nothrow) mimi_stream();
+  if (!s) return csm_set_error(CSM_ERR_ARG, "out of host memory");
+  s->x = x; s->st = (float*)state; s->frames = 0;
+  MCU_TRY(cudaMemsetAsync(state, 0, mimi_stream_state_bytes(), (cudaStream_t)stream));
+  *out = s;
+  return CSM_OK;
+}
+extern "C" int32_t mimi_stream_reset(mimi_stream* s, void* stream) {
+  if (!s) return csm_set_error(CSM_ERR_STATE, "mimi_stream_reset: null stream");
+  s->frames = 0;
+  MCU_TRY(cudaMemsetAsync(s->st, 0, mimi_stream_state_bytes(), (cudaStream_t)stream));
+  return CSM_OK;
+}
+extern "C" void mimi_stream_destroy(mimi_stream* s) { delete s; }
+
+extern "C" int32_t mimi_decode_stream(mimi_stream* s, const int64_t* codes, int32_t K, int32_t T, float* out, void* stream) {
+  if (!s) return csm_set_error(CSM_ERR_STATE, "mimi_decode_stream: null stream");
+  if (!codes || !out || K < 1 || K > 32 || T < 1) return csm_set_error(CSM_ERR_ARG, "mimi_decode_stream: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int t0 = 0; t0 < T; t0 += s->x->max_frames) {
+    const int n = T - t0 < s->x->max_frames ? T - t0 : s->x->max_frames;
+    int rc = decode_chunk(s->x, s->st, s->frames, codes + t0, K, n, T, out + (size_t)t0 * 1920, st);
+    if (rc != CSM_OK) return rc;
+    s->frames += n;
   }
   return CSM_OK;
 }

@@ -226,13 +226,13 @@ __global__ void __launch_bounds__(256) k_tgemm(GemmArgs g) {
 
 // split-RVQ lookup: q[t] = [ sum over semantic codebooks | sum over acoustic codebooks ]  (2 x 256)
 // embedding = embedding_sum / clamp(cluster_usage, 1e-5) is precomputed at create time.
-__global__ void k_rvq_gather(const int64_t* __restrict__ codes /*[K, T] of this utterance*/, int K, int T,
-                             const float* __restrict__ emb /*[32][2048][256]*/, float* __restrict__ out /*[T, 512]*/) {
+__global__ void k_rvq_gather(const int64_t* __restrict__ codes /*[K, ldt] of this utterance, frames [0, T) of it*/, int K, int T,
+                             long long ldt, const float* __restrict__ emb /*[32][2048][256]*/, float* __restrict__ out /*[T, 512]*/) {
   const int t = blockIdx.x;
   const int d = threadIdx.x;  // 256 threads
   float first = 0.f, rest = 0.f;
   for (int k = 0; k < K; ++k) {
-    long long code = codes[(long long)k * T + t];
+    long long code = codes[(long long)k * ldt + t];
     code = code < 0 ? 0 : (code > 2047 ? 2047 : code);  // memory safety: the reference would raise on these
     const float v = emb[((long long)k * 2048 + code) * 256 + d];
     if (k == 0) first += v;
@@ -244,8 +244,9 @@ __global__ void k_rvq_gather(const int64_t* __restrict__ codes /*[K, T] of this 
 
 // depthwise ConvTranspose1d(k=4, s=2, groups=C), causal (trim 2 on the right):
 // y[2q + r][c] = x[q][c] * w[c][r] + x[q-1][c] * w[c][r+2]
+// ``prev`` [C] = the row before x[0] (the last row of the previous chunk of a streamed decode; zeros at the start)
 __global__ void k_upsample2(const float* __restrict__ x /*[T, C]*/, const float* __restrict__ w /*[C][4]*/, int T, int C,
-                            float* __restrict__ y /*[2T, C]*/) {
+                            float* __restrict__ y /*[2T, C]*/, const float* __restrict__ prev) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)2 * T * C) return;
   const int c = i % C;
@@ -253,8 +254,16 @@ __global__ void k_upsample2(const float* __restrict__ x /*[T, C]*/, const float*
   const long long q = o >> 1;
   const int r = o & 1;
   float v = x[q * C + c] * w[c * 4 + r];
-  if (q > 0) v += x[(q - 1) * C + c] * w[c * 4 + r + 2];
+  v += (q > 0 ? x[(q - 1) * C + c] : prev[c]) * w[c * 4 + r + 2];
   y[i] = v;
+}
+// dst[r][c] = src[r][c] for r < rows: carries causal left context (conv pad rows, K/V history) between chunks
+__global__ void k_copy_rows(const float* __restrict__ src, long long lds, float* __restrict__ dst, long long ldd, int rows, int cols) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * cols) return;
+  const long long r = i / cols;
+  const int c = (int)(i - r * cols);
+  dst[r * ldd + c] = src[r * lds + c];
 }
 
 // LayerNorm over 512 channels, one warp per row
@@ -299,7 +308,8 @@ __global__ void __launch_bounds__(256) k_layernorm512(const float* __restrict__ 
 }
 
 // interleaved RoPE (moshi apply_rope, max_period 10000) in place on the q and k thirds of qkv [L, 1536]
-__global__ void k_rope_qk(float* __restrict__ qkv, int L) {
+// rows [0, L) of ``qkv`` are absolute positions pos0 .. pos0 + L - 1
+__global__ void k_rope_qk(float* __restrict__ qkv, int L, long long pos0) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // (t, which, head, pair)
   if (i >= (long long)L * 2 * 8 * 32) return;
   const int pair = i & 31;
@@ -308,7 +318,7 @@ __global__ void k_rope_qk(float* __restrict__ qkv, int L) {
   const long long t = i >> 9;
   const float freq = expf((float)pair * (-9.210340371976184f * 2.0f / 64.0f));  // ln(10000)
   float sn, cs;
-  sincosf(freq * (float)t, &sn, &cs);
+  sincosf(freq * (float)(pos0 + t), &sn, &cs);
   float* p = qkv + t * 1536 + which * 512 + head * 64 + pair * 2;
   const float xr = p[0], xi = p[1];
   p[0] = xr * cs - xi * sn;
@@ -316,12 +326,15 @@ __global__ void k_rope_qk(float* __restrict__ qkv, int L) {
 }
 
 // causal attention with a `context`-key window; one warp per (query, head); qkv [L, 1536] -> out [L, 512]
+// Queries are rows [hist, hist + L) of ``qkv``; rows [0, hist) hold the carried K/V of the positions before
+// this chunk (streamed decode), so row index differences are position differences.  out row = t - hist.
 __global__ void __launch_bounds__(128) k_attn_window(const float* __restrict__ qkv, int L, int context,
-                                                     float* __restrict__ out) {
-  const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+                                                     float* __restrict__ out, int hist) {
+  const int tq = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int h = blockIdx.y;
   const int lane = threadIdx.x & 31;
-  if (t >= L) return;
+  if (tq >= L) return;
+  const int t = tq + hist;
   const float scale = 0.125f;  // 1/sqrt(64)
   float q[64];
   {
@@ -370,7 +383,7 @@ __global__ void __launch_bounds__(128) k_attn_window(const float* __restrict__ q
     m = mn;
   }
   const float inv = 1.0f / l;
-  *reinterpret_cast<float2*>(out + (long long)t * 512 + h * 64 + lane * 2) = make_float2(o0 * inv, o1 * inv);
+  *reinterpret_cast<float2*>(out + (long long)tq * 512 + h * 64 + lane * 2) = make_float2(o0 * inv, o1 * inv);
 }
 
 // final causal conv 64 -> 1, k = 3, with the ELU on its input: one thread per output sample

@@ -110,7 +110,13 @@ PROTOTYPES = {
                                 C.POINTER(C.c_void_p)]),
     "mimi_decode": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "mimi_encode": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mimi_k_rvq_encode": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "mimi_destroy": (None, [C.c_void_p]),
+    "mimi_stream_state_bytes": (C.c_size_t, []),
+    "mimi_stream_create": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mimi_stream_reset": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "mimi_decode_stream": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "mimi_stream_destroy": (None, [C.c_void_p]),
     "csm_debug_set_trace": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "csm_debug_phase_table": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "csm_k_sample_topk": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p,

@@ -63,6 +63,10 @@ class Generator:
         self._audio_tokenizer = audio_tokenizer
         self.sample_rate = audio_tokenizer.sample_rate
         self._stream_buffer_size = 10  # frames per streamed chunk
+        # generate_stream decodes its chunks with a stateful Mimi stream: the causal left context (conv tails,
+        # transformer K/V) is carried over, so the concatenated chunks equal the one-shot decode of generate().
+        # False = the reference's behaviour (generator.py:111-117,189-196): every chunk decoded from silence.
+        self._stream_stateful = True
         self._n_cols = model.config.audio_num_codebooks + 1
 
     # -- prompt frames ---------------------------------------------------------------------------
@@ -133,16 +137,25 @@ class Generator:
                         temperature: float = 0.7, topk: int = 30,
                         on_chunk_generated: Optional[Callable[[torch.Tensor], None]] = None) -> Iterator[torch.Tensor]:
         buf: List[torch.Tensor] = []
+        stream = None
+        if self._stream_stateful and hasattr(self._audio_tokenizer, "streaming"):
+            stream = self._audio_tokenizer.streaming()
+
+        def decode(frames: List[torch.Tensor]) -> torch.Tensor:
+            if stream is None:
+                return self._decode_frames(frames)
+            return stream.decode(torch.stack(frames).permute(1, 2, 0)).squeeze(0).squeeze(0)
+
         for sample in self._frames(text, speaker, context, max_audio_length_ms, temperature, topk):
             buf.append(sample)
             if len(buf) >= self._stream_buffer_size:
-                chunk = self._decode_frames(buf)
+                chunk = decode(buf)
                 buf = []
                 if on_chunk_generated:
                     on_chunk_generated(chunk)
                 yield chunk
         if buf:
-            chunk = self._decode_frames(buf)
+            chunk = decode(buf)
             if on_chunk_generated:
                 on_chunk_generated(chunk)
             yield chunk

@@ -232,23 +232,95 @@ class MimiCodec(nn.Module):
         c.record_stream(torch.cuda.current_stream(dev))
         return out
 
+    def quantize_latent(self, latent: torch.Tensor) -> torch.Tensor:
+        """latent [1, 512, T] fp32 -> codes [1, num_codebooks, T]: the split-RVQ search of ``encode`` alone
+        (moshi ``SplitResidualVectorQuantizer.encode``); used by the parity tests."""
+        if latent.dim() != 3 or latent.shape[0] != 1 or latent.shape[1] != 512:
+            raise ValueError("latent must be [1, 512, T]")
+        if self._ctx is None:
+            self.prepare()
+        dev = next(self.parameters()).device
+        x = latent[0].to(device=dev, dtype=torch.float32).t().contiguous()  # time-major [T, 512]
+        T = x.shape[0]
+        codes = torch.empty(1, self.num_codebooks, T, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            _native.check(_native.lib().mimi_k_rvq_encode(self._ctx, x.data_ptr(), T, self.num_codebooks, codes.data_ptr(),
+                                                         torch.cuda.current_stream(dev).cuda_stream))
+        x.record_stream(torch.cuda.current_stream(dev))
+        return codes
+
+    def streaming(self) -> "MimiStream":
+        """A stateful decoder for ONE utterance delivered in chunks (``generate_stream``): concatenated chunk
+        outputs equal ``decode`` of the whole utterance."""
+        if self._ctx is None:
+            self.prepare()
+        return MimiStream(self)
+
     def encode(self, wav: torch.Tensor) -> torch.Tensor:
         """wav [B, 1, L] fp32 at 24 kHz -> codes [B, num_codebooks, ceil(L/1920)] int64, as moshi's
         ``MimiModel.encode`` (reference ``generator.py:86``)."""
         if wav.dim() != 3 or wav.shape[1] != 1:
             raise ValueError("wav must be [B, 1, L]")
-        if self._ctx is None:
-            self.prepare()
         dev = next(self.parameters()).device
         w = wav.to(device=dev, dtype=torch.float32).contiguous()
         B, _, L = w.shape
         T = (L + 1919) // 1920
+        if T > self.max_frames:  # moshi has no length limit: grow the workspace (decode windows instead)
+            self.max_frames = 1 << (T - 1).bit_length()
+            self._release()
+        if self._ctx is None:
+            self.prepare()
         codes = torch.empty(B, self.num_codebooks, T, dtype=torch.int64, device=dev)
         with torch.cuda.device(dev):
             _native.check(_native.lib().mimi_encode(self._ctx, w.data_ptr(), B, L, self.num_codebooks, codes.data_ptr(),
                                                     torch.cuda.current_stream(dev).cuda_stream))
         w.record_stream(torch.cuda.current_stream(dev))
         return codes
+
+
+class MimiStream:
+    """Streaming decode state of one utterance (``mimi_stream`` in include/csm_b200.h)."""
+
+    def __init__(self, codec: MimiCodec):
+        L = _native.lib()
+        self.codec = codec
+        dev = next(codec.parameters()).device
+        self.device = dev
+        need = L.mimi_stream_state_bytes()
+        with torch.cuda.device(dev):
+            self._buf = torch.empty(need + 256, dtype=torch.uint8, device=dev)
+            off = (-self._buf.data_ptr()) % 256
+            h = ctypes.c_void_p()
+            _native.check(L.mimi_stream_create(codec._ctx, self._buf.data_ptr() + off, need,
+                                               torch.cuda.current_stream(dev).cuda_stream, ctypes.byref(h)))
+        self._h = h.value
+
+    def __del__(self):  # pragma: no cover
+        try:
+            if getattr(self, "_h", None):
+                _native.lib().mimi_stream_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def reset(self) -> None:
+        with torch.cuda.device(self.device):
+            _native.check(_native.lib().mimi_stream_reset(self._h, torch.cuda.current_stream(self.device).cuda_stream))
+
+    def decode(self, codes: torch.Tensor) -> torch.Tensor:
+        """The next frames of the utterance: codes [1, K, T] (or [K, T]) -> [1, 1, 1920*T] fp32."""
+        if codes.dim() == 3:
+            if codes.shape[0] != 1:
+                raise ValueError("a MimiStream decodes one utterance")
+            codes = codes[0]
+        c = codes.to(device=self.device, dtype=torch.int64).contiguous()
+        K, T = c.shape
+        out = torch.empty(1, 1, 1920 * T, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _native.check(_native.lib().mimi_decode_stream(self._h, c.data_ptr(), K, T, out.data_ptr(),
+                                                          torch.cuda.current_stream(self.device).cuda_stream))
+        c.record_stream(torch.cuda.current_stream(self.device))
+        return out
 
 
 def get_mimi(filename: Optional[str], device="cuda", max_frames: int = 1200) -> MimiCodec:

@@ -62,17 +62,73 @@ def test_decode_is_chunk_additive_in_batch(codecs):
         assert torch.equal(full[b], pc.decode(codes[b : b + 1])[0])
 
 
-def test_too_many_frames_is_an_error(codecs):
+def test_decode_longer_than_the_workspace_runs_in_windows(codecs):
+    """moshi's decode has no length limit: beyond ``max_frames`` (160 here) the decode runs in windows that carry
+    their causal left context, and must equal the oracle's single pass (370 frames: 3 windows, > 250 positions)."""
+    om, pc = codecs
+    codes = syn.hash_ints(32 * 370, 21, 5, 2048).view(1, 32, 370)
+    with torch.inference_mode():
+        want = om.decode(codes)
+    got = pc.decode(codes.cuda()).cpu()
+    assert snr_db(want, got) >= SNR_MIN_DB + 20, snr_db(want, got)
+
+
+@pytest.mark.parametrize("chunks", [[10, 10, 10, 7], [1, 2, 1, 3, 130, 4], [160, 100, 9]])
+def test_streamed_chunks_equal_one_shot_decode_bit_for_bit(codecs, chunks):
+    """Stateful streaming decode: chunk outputs concatenated == decode of the whole utterance,
+    exactly -- including 1-frame chunks (shorter than the conv tails) and > 249 carried transformer positions."""
     _, pc = codecs
-    with pytest.raises(RuntimeError):
-        pc.decode(torch.zeros(1, 32, 161, dtype=torch.long, device="cuda"))
+    T = sum(chunks)
+    codes = syn.hash_ints(32 * T, 17, T, 2048).view(1, 32, T).cuda()
+    whole = pc.decode(codes)
+    st = pc.streaming()
+    parts, t0 = [], 0
+    for n in chunks:
+        parts.append(st.decode(codes[:, :, t0:t0 + n]))
+        t0 += n
+    assert torch.equal(torch.cat(parts, dim=-1), whole)
+    # a reset stream starts a new utterance from silence
+    st.reset()
+    assert torch.equal(st.decode(codes[:, :, :5]), pc.decode(codes[:, :, :5]))
+
+
+def test_encode_longer_than_the_workspace_grows_it():
+    pc = MimiCodec(max_frames=8)
+    om = mo.OracleMimi().eval()
+    syn.init_mimi_weights(om, 2024)
+    pc.load_state_dict(om.state_dict())
+    pc.to("cuda")
+    wav = torch.empty(1, 1, 1920 * 13)
+    syn.hash_uniform_(wav, 4, 13, 0.5)
+    got = pc.encode(wav.cuda())
+    assert got.shape == (1, 32, 13) and pc.max_frames >= 13
+
+
+def _first_mismatch_is_a_near_tie(om, wav, want, got, b, t):
+    """Both code sets agree on layers < k at frame t of utterance b and differ at layer k: recompute the oracle's
+    residual at that decision in fp64 and return the relative gap between the two candidates' distances."""
+    k = int((want[b, :, t] != got[b, :, t]).nonzero()[0])
+    with torch.inference_mode():
+        lat = om.encode_latent(wav)[b, :, t].double()  # [512] pre-quantisation latent
+    rvq = om.quantizer.rvq_first if k == 0 else om.quantizer.rvq_rest
+    res = torch.nn.functional.conv1d(lat.view(1, 512, 1), rvq.input_proj.weight.double()).view(256)
+    for j in range(1 if k > 0 else 0, k):
+        res = res - rvq.vq.layers[j - 1]._codebook.embedding[want[b, j, t]].double()
+    emb = rvq.vq.layers[k - 1 if k > 0 else 0]._codebook.embedding.double()
+    d_want = (res - emb[want[b, k, t]]).pow(2).sum().item()
+    d_got = (res - emb[got[b, k, t]]).pow(2).sum().item()
+    return k, abs(d_want - d_got) / max(d_want, 1e-30)
 
 
 @pytest.mark.parametrize("B,L", [(1, 1920 * 3), (2, 1920 * 11), (1, 1920 * 131), (1, 5000)])
 def test_encode_matches_oracle(codecs, B, L):
-    """Mimi encode (voice-prompt path): codes equal to the oracle's except where two centroids are
-    within fp32 rounding of each other (a near-tie changes the rest of that frame's residual chain).
-    Edge cases: > 250-frame transformer context, a length that is not a whole number of frames."""
+    """Mimi encode (voice-prompt path).  The codes are nearest-centroid decisions over 2048 fp32 distances; two
+    fp32 evaluations of the same encoder (different summation orders) differ by ~1e-6 relative, so a decision
+    whose top-2 distance gap is smaller than that is not defined at fp32 and the rest of that frame's residual
+    chain follows it.  Gate: every frame is either IDENTICAL to the oracle's, or its FIRST differing layer is
+    such a near-tie (gap < 1e-4 relative, recomputed in fp64 from the oracle's own residual), and the semantic
+    codebook (no chain before it) agrees on >= 99 % of frames.  Edge cases: > 250-frame transformer context, a
+    length that is not a whole number of frames."""
     om, pc = codecs
     wav = torch.empty(B, 1, L)
     syn.hash_uniform_(wav, 4, L % 977, 0.5)
@@ -81,12 +137,37 @@ def test_encode_matches_oracle(codecs, B, L):
     got = pc.encode(wav.cuda()).cpu()
     assert got.shape == want.shape == (B, 32, (L + 1919) // 1920) and got.dtype == torch.int64
     same = (got == want).float().mean().item()
-    assert same >= 0.97, same
-    assert (got[:, 0] == want[:, 0]).float().mean().item() >= 0.99  # the semantic codebook has no chain before it
-    # a mismatch must be a near-tie, not an error: decoding either code set gives the same audio quality
+    bad_frames = (got != want).any(dim=1).nonzero().tolist()
+    gaps = []
+    for b, t in bad_frames:
+        k, gap = _first_mismatch_is_a_near_tie(om, wav, want, got, b, t)
+        gaps.append((k, gap))
+        assert gap < 1e-4, (b, t, k, gap)
+    print(f"[mimi encode B={B} L={L}] codes identical: {100 * same:.2f} %, frames with a near-tie flip: {len(bad_frames)}"
+          f" of {want.shape[0] * want.shape[2]}, worst gap {max([g for _, g in gaps], default=0):.2e}")
+    assert (got[:, 0] == want[:, 0]).float().mean().item() >= 0.99
+
+
+def test_rvq_search_is_exact_on_well_separated_latents(codecs):
+    """The search itself, isolated from encoder rounding: residuals planted ON centroid sums with geometrically
+    decaying codebook scales have wide decision margins, and the codes must come back 100 % identical."""
+    om, _ = codecs
+    om2 = mo.OracleMimi().eval()
+    om2.load_state_dict(om.state_dict())
+    with torch.no_grad():  # acoustic codebook k scaled by 0.8^k: top-2 distance gaps >= 10 % at every decision (fp64 check on the CPU)
+        for k in range(31):
+            om2.quantizer.rvq_rest.vq.layers[k]._codebook.embedding_sum.mul_(0.8 ** k)
+    pc = MimiCodec(max_frames=64)
+    pc.load_state_dict(om2.state_dict())
+    pc.to("cuda")
+    T = 50
+    codes = syn.hash_ints(32 * T, 5, 9, 2048).view(1, 32, T)
     with torch.inference_mode():
-        a, b = om.decode(want), om.decode(got)
-    assert snr_db(a, b) >= 15.0 or same == 1.0
+        lat = om2.latent_for_codes(codes)             # [1, 512, T]: lands on the centroid sums of ``codes``
+        want = om2.quantize_latent(lat)               # oracle search on that latent
+    assert torch.equal(want, codes)  # the planted chain is what the oracle's search finds
+    got = pc.quantize_latent(lat.cuda()).cpu()
+    assert torch.equal(got, want)
 
 
 def test_encode_decode_round_trip_runs(codecs):
