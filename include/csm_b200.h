@@ -236,6 +236,25 @@ int32_t mimi_encode(mimi_ctx *ctx, const float *wav, int32_t B, int64_t L, int32
 int32_t mimi_k_rvq_encode(mimi_ctx *ctx, const float *latent, int32_t T, int32_t K, int64_t *codes, void *stream);
 void mimi_destroy(mimi_ctx *ctx);
 
+/* ---- waveform post-processing ------------------------------------------ */
+
+/* torchaudio.functional.resample(x, orig_freq, new_freq) with its default arguments (sinc_interp_hann,
+ * lowpass_filter_width 6, rolloff 0.99), as the reference calls it around the watermarker
+ * (sesameai/watermarking.py:35-39: 24 kHz -> 44.1 kHz -> 24 kHz; tts_service.py:254-256): x dev fp32 [n] ->
+ * y dev fp32 [csm_post_resample_len(n, ..)] = ceil(new * n / orig) samples.  ``workspace``: dev buffer of
+ * csm_post_resample_workspace_bytes (the polyphase kernel table, rebuilt per call in fp64). */
+int64_t csm_post_resample_len(int64_t n, int32_t orig_freq, int32_t new_freq);
+size_t csm_post_resample_workspace_bytes(int32_t orig_freq, int32_t new_freq);
+int32_t csm_post_resample(const float *x, int64_t n, int32_t orig_freq, int32_t new_freq, float *y, void *workspace,
+                          size_t workspace_bytes, void *stream);
+
+/* tts_service.generate_audio_segment (tts_service.py:287-306) on the device: peak-normalise
+ * (audio / max(|audio|.max(), 1e-6)), convert to 16-bit PCM (x * 32767, truncated), add start / end silence
+ * and pydub's fade_in / fade_out (per-sample linear gain from -120 dB, floor like audioop.mul; all counts in
+ * SAMPLES): audio dev fp32 [n] -> out dev int16 [start_silence + n + end_silence]; scratch4: 4 dev bytes. */
+int32_t csm_post_pcm16_segment(const float *audio, int64_t n, int64_t start_silence, int64_t end_silence, int64_t fade_in,
+                               int64_t fade_out, int16_t *out, void *scratch4, void *stream);
+
 /* Profiling aid: dev uint64 [n_ctas][n_phases][16] buffer that thread 0 of every CTA of the decode
  * megakernel fills (4 %globaltimer stamps: phase start, inputs staged, partial sums done, end; 12
  * clock64 marks); NULL disables.  Returns the number of phases (0 if the megakernel is unavailable). */

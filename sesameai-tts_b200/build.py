@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.environ.get("CSM_B200_OUT") or os.path.join(HERE, "lib", "libcsm_b200.so")
-SOURCES = ["api.cu", "mimi_api.cu"]
+SOURCES = ["api.cu", "mimi_api.cu", "post_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false",

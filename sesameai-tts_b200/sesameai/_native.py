@@ -117,6 +117,11 @@ PROTOTYPES = {
     "mimi_stream_reset": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "mimi_decode_stream": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "mimi_stream_destroy": (None, [C.c_void_p]),
+    "csm_post_resample_len": (C.c_int64, [C.c_int64, C.c_int32, C.c_int32]),
+    "csm_post_resample_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "csm_post_resample": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "csm_post_pcm16_segment": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]),
     "csm_debug_set_trace": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "csm_debug_phase_table": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]),
     "csm_k_sample_topk": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_void_p,

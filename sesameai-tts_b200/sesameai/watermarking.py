@@ -3,7 +3,8 @@
 This module only keeps ``tts_service.py``'s imports working -- ``CSM_1B_GH_WATERMARK``,
 ``load_watermarker``, ``watermark``, ``verify`` (reference ``sesameai/watermarking.py:9,20-59``) --
 by delegating to the third-party ``silentcipher`` package, imported lazily so the frame-generation
-hot path has no dependency on it.  Nothing here runs on the B200 kernels.
+hot path has no dependency on it.  Only the two sinc resamplings around the watermarker (24 kHz <-> 44.1 kHz)
+run on the B200 (``sesameai.postprocess.resample``) when the audio is a CUDA tensor.
 """
 from __future__ import annotations
 
@@ -24,9 +25,15 @@ def _silentcipher():
 
 
 def _resample(x: torch.Tensor, src: int, dst: int) -> torch.Tensor:
+    if src == dst:
+        return x
+    if x.is_cuda and x.dtype == torch.float32:  # same filter as torchaudio's default resample, on the B200
+        from .postprocess import resample
+
+        return resample(x, src, dst)
     import torchaudio
 
-    return x if src == dst else torchaudio.functional.resample(x, orig_freq=src, new_freq=dst)
+    return torchaudio.functional.resample(x, orig_freq=src, new_freq=dst)
 
 
 def load_watermarker(device: str = "cuda"):
