@@ -166,6 +166,38 @@ def teacher_case(mod, flavor, text_vocab, batch, prompt_frames, n_frames, temper
 
 
 @torch.inference_mode()
+def voice_prompt_case(mod, batch, n_frames, temperature, topk, out_path):
+    """BASELINE config 3's prompt on the full-size model: ``batch`` streams x 1568 frames (4 x (64 text + 320
+    audio frames ending in the all-zero EOS frame) + 32 text), the reference free-runs ``n_frames`` frames with
+    shared noise; tokens + logits are stored for teacher-forced comparison.  Streams are independent, so the
+    GPU tests also tile these ``batch`` prompts to larger batches (B = 32)."""
+    t0 = time.time()
+    m, args = build_reference(mod, ("llama-1B", "llama-100M"), 128_256, planted=False, batch=batch)
+    tok, msk, pos = syn.voice_prompt(batch, 4, 64, 320, 32, seed=3)
+    assert tok.shape[1] == 1568
+    noise = syn.exp_noise(32 * n_frames, batch, 2051, NOISE_SEED)
+    rec = []
+    orig = mod.sample_topk
+
+    def spy(logits, k, t):
+        rec.append(logits.detach().clone())
+        return orig(logits, k, t)
+
+    mod.sample_topk = spy
+    try:
+        with NoisePatch(mod, noise):
+            frames = orc.oracle_frame_loop(m, tok, msk, pos, n_frames, temperature, topk, stop_on_eos=False)
+    finally:
+        mod.sample_topk = orig
+    frames = torch.stack(frames)
+    logits = torch.stack(rec).view(n_frames, 32, batch, 2051)
+    torch.save(dict(model_args=args, weight_seed=WEIGHT_SEED, noise_seed=NOISE_SEED, planted=False, batch=batch,
+                    prompt=dict(segments=4, text_frames=64, audio_frames=320, tail_text_frames=32, seed=3),
+                    temperature=temperature, topk=topk, frames=frames.to(torch.int32), logits=logits), out_path)
+    print(f"{out_path}: {n_frames} frames after a 1568-frame prompt, batch {batch}, {time.time() - t0:.1f}s")
+
+
+@torch.inference_mode()
 def sample_cases(mod, out_path):
     """Known-answer vectors for sample_topk alone (reference models.py:77-87)."""
     cases = []
@@ -200,10 +232,12 @@ def main():
     elif what == "csm1b":
         greedy_case(mod, ("llama-1B", "llama-100M"), 128_256, 1, 24, 64, os.path.join(HERE, "csm1b_greedy.pt"))
         teacher_case(mod, ("llama-1B", "llama-100M"), 128_256, 1, 24, 3, 0.9, 50, os.path.join(HERE, "csm1b_teacher.pt"))
+    elif what == "voice":
+        voice_prompt_case(mod, 2, 2, 0.9, 50, os.path.join(HERE, "csm1b_voice1568.pt"))
     elif what == "mimi":
         return
     else:
-        raise SystemExit("usage: make_golden.py [tiny|csm1b|teacher|mimi]")
+        raise SystemExit("usage: make_golden.py [tiny|csm1b|teacher|voice|mimi]")
 
 
 if __name__ == "__main__":
