@@ -294,6 +294,12 @@ int32_t csm_k_linear(const void *x, const void *W, int32_t N, int32_t in, int32_
 int32_t csm_k_gemm_tc(const void *x, const void *W, int32_t N, int32_t in, int32_t out, void *y, int32_t epi,
                       const void *resid, void *stream);
 
+/* The same GEMM with split-K enabled when the shape calls for it (N <= 512 rows and few output tiles: the decode
+ * steps of large batches): ``part`` = dev fp32 scratch of 148 * 128 * 128 floats, ``counters`` = 148 dev uint32,
+ * zero on entry (left zero on exit). */
+int32_t csm_k_gemm_tc_splitk(const void *x, const void *W, int32_t N, int32_t in, int32_t out, void *y, int32_t epi,
+                             const void *resid, void *part, void *counters, void *stream);
+
 /* Prompt attention (head_dim 64) on the tensor cores, the kernel behind the tensor-core prefill
  * (replaces the per-row scaled_dot_product_attention of torchtune's MultiHeadAttention for prompt rows):
  * q [B*chunk, heads*64] (row n = b*chunk + t), caches [B, kv_heads, slots, 64], row_slot[n] = cache slot of row

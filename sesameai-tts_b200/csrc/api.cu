@@ -32,8 +32,9 @@ static std::atomic<unsigned long long> g_launches{0};
 #define COUNT_LAUNCH() (g_launches.fetch_add(1, std::memory_order_relaxed))
 extern "C" uint64_t csm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+struct csm_ctx;
 static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const bf16* W, int n_out, bf16* out, long long ldo,
-                          int epi, const bf16* resid, cudaStream_t st);
+                          int epi, const bf16* resid, cudaStream_t st, const csm_ctx* splitk = nullptr);
 
 // shared with mimi_api.cu
 int csm_set_error(int code, const char* msg) { return set_err(code, "%s", msg); }
@@ -48,6 +49,8 @@ static const int PREFILL_TC_ROWS = 4096;  // rows per tensor-core prefill pass
 static const int PREFILL_TC_MIN = 64;     // prompt rows (B * (S-1)) from which the tcgen05 path is used
 static const int DECODE_TC_MIN = 16;      // streams from which a decode step runs on the tcgen05 GEMM
 static const int SKINNY_MAX_ROWS = 64;    // rows up to which a linear layer runs on the skinny fragment-major GEMM
+static const int TC_SPLIT_TILES = 148;    // split-K of the tcgen05 GEMM: splits x tiles never exceeds one CTA per SM
+static const int TC_SPLIT_MAX_ROWS = 512; // ... and is only used for decode-sized row counts
 
 struct StackDev {
   csm_stack_config c;
@@ -88,6 +91,8 @@ struct csm_ctx {
   int *row_stream, *row_pos, *row_slot;
   FrameParams* d_params;
   int* d_lane_meta;            // [2 * max_batch]: row -> lane, row -> positions held (continuous batching)
+  float* tc_part;              // split-K partial tiles of the tcgen05 GEMM (decode steps of large batches)
+  unsigned int* tc_counters;   // one arrival counter per output tile, zero between launches
   std::vector<int> lane_len;   // positions held by every cache lane (host truth; calls are stream ordered)
   int cache_len;               // == lane_len[0]: the reference's single counter for a lock-step batch
   bool enabled;
@@ -204,6 +209,8 @@ static size_t carve_all(csm_ctx* x, char* base) {
   x->row_slot = cv.take<int>(x->max_rows);
   x->d_params = cv.take<FrameParams>(1);
   x->d_lane_meta = cv.take<int>((size_t)2 * x->max_batch);
+  x->tc_part = cv.take<float>((size_t)TC_SPLIT_TILES * tc::BM * tc::BN);
+  x->tc_counters = cv.take<unsigned int>(TC_SPLIT_TILES);
   x->d_sync = cv.take<mega::Sync>(1);
   x->d_phases = cv.take<mega::Phase>(mega_phase_count(c));
   cv.off = (cv.off + 255) & ~(size_t)255;
@@ -813,6 +820,11 @@ extern "C" int32_t csm_create(const csm_config* cfg, const csm_weights* w, int32
       return set_err(CSM_ERR_CUDA, "csm_create: %s", cudaGetErrorString(e));
     }
   }
+  e = cudaMemsetAsync(x->tc_counters, 0, TC_SPLIT_TILES * sizeof(unsigned int), st);
+  if (e != cudaSuccess) {
+    csm_destroy(x);
+    return set_err(CSM_ERR_CUDA, "csm_create: %s", cudaGetErrorString(e));
+  }
   x->cache_len = 0;
   x->lane_len.assign(max_batch, 0);
   x->enabled = true;
@@ -1085,7 +1097,7 @@ static int make_map_bf16(CUtensorMap* m, const bf16* base, long long rows, long 
   return CSM_OK;
 }
 static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const bf16* W, int n_out, bf16* out, long long ldo,
-                          int epi, const bf16* resid, cudaStream_t st) {
+                          int epi, const bf16* resid, cudaStream_t st, const csm_ctx* splitk) {
   if (K % tc::BK || rows < 1 || n_out < 1) return set_err(CSM_ERR_ARG, "gemm_tc: K must be a multiple of 64");
   static std::atomic<unsigned long long> attr{0};
   if (!device_done(attr, false)) {
@@ -1098,7 +1110,19 @@ static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const b
   if ((rc = make_map_bf16(&mw, W, n_out, K, K, tc::BN)) != CSM_OK) return rc;
   tc::Args a;
   a.out = out; a.ldo = ldo; a.resid = resid ? resid : out; a.rows = rows; a.n_out = n_out; a.K = K; a.epi = epi;
+  a.part = nullptr; a.counters = nullptr; a.ldp = 0;
   dim3 grid((n_out + tc::BN - 1) / tc::BN, (rows + tc::BM - 1) / tc::BM);
+  // decode steps of large batches: few tiles, long K -> split K over the idle SMs (see gemm_tc.cuh)
+  const int tiles = (int)(grid.x * grid.y), num_kb = K / tc::BK;
+  if (splitk && rows <= TC_SPLIT_MAX_ROWS && 2 * tiles <= TC_SPLIT_TILES) {
+    int splits = 1;
+    while (splits * 2 <= 8 && splits * 2 * tiles <= TC_SPLIT_TILES && num_kb % (splits * 2) == 0 && num_kb / (splits * 2) >= 2)
+      splits *= 2;
+    if (splits > 1) {
+      grid.z = splits;
+      a.part = splitk->tc_part; a.counters = splitk->tc_counters; a.ldp = (long long)grid.x * tc::BN;
+    }
+  }
   tc::k_gemm_tc<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mx, mw, a); COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
   return CSM_OK;
@@ -1134,7 +1158,7 @@ static bool skinny_ok(const csm_ctx* x, const bf16* Wf, int N, int K) {
 static int linear_rows(csm_ctx* x, const bf16* W, const bf16* Wf, int R, const bf16* X, long long ldx, int N, int K, int n_out,
                        bf16* out, long long ldo, int epi, const bf16* resid, cudaStream_t st) {
   if (skinny_ok(x, Wf, N, K)) return launch_skinny(Wf, R, X, ldx, N, K, n_out, out, ldo, epi, resid, st);
-  return launch_gemm_tc(X, ldx, N, K, W, n_out, out, ldo, epi, resid, st);
+  return launch_gemm_tc(X, ldx, N, K, W, n_out, out, ldo, epi, resid, st, x);
 }
 // RMSNorm(H rows) followed by a linear layer: fused into the skinny kernel for few rows, else k_rmsnorm into
 // ``xn`` (skipped when ``xn_ready``: an earlier call of the same pair normalised already) and the tcgen05 GEMM
@@ -1252,6 +1276,18 @@ extern "C" int32_t csm_k_gemm_tc(const void* xin, const void* W, int32_t N, int3
   const long long ldo = epi == tc::EPI_SWIGLU_PAIRS ? outf / 2 : outf;
   return launch_gemm_tc((const bf16*)xin, in, N, in, (const bf16*)W, outf, (bf16*)y, ldo, epi, (const bf16*)resid,
                         (cudaStream_t)stream);
+}
+
+extern "C" int32_t csm_k_gemm_tc_splitk(const void* xin, const void* W, int32_t N, int32_t in, int32_t outf, void* y, int32_t epi,
+                                        const void* resid, void* part, void* counters, void* stream) {
+  if (!xin || !W || !y || !part || !counters || N < 1 || in % 64 || outf < 1 || epi < 0 || epi > 2)
+    return set_err(CSM_ERR_ARG, "bad gemm_tc arguments");
+  csm_ctx tmp;
+  tmp.tc_part = (float*)part;
+  tmp.tc_counters = (unsigned int*)counters;
+  const long long ldo = epi == tc::EPI_SWIGLU_PAIRS ? outf / 2 : outf;
+  return launch_gemm_tc((const bf16*)xin, in, N, in, (const bf16*)W, outf, (bf16*)y, ldo, epi, (const bf16*)resid,
+                        (cudaStream_t)stream, &tmp);
 }
 
 extern "C" int32_t csm_k_attn_prefill(const void* q, const void* k_cache, const void* v_cache, const int32_t* row_slot, int32_t B,

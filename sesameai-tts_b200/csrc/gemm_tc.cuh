@@ -12,6 +12,12 @@
 //                               gate/up columns) -> global
 // One output tile per CTA; grid = (out/128, rows/128) -- for prefill that is thousands of CTAs,
 // several waves over the 148 SMs.  Every wait is trip-capped and traps instead of hanging.
+//
+// Split-K (grid.z = splits > 1) for the decode steps of large batches, where rows <= 512 and a projection
+// with 1024 .. 2048 outputs is only 8 .. 32 tiles: each CTA accumulates one K slice of its tile in TMEM and
+// writes the fp32 partial tile to a workspace; the last CTA of a tile to finish (a counter per tile) adds the
+// partials in slice order -- a fixed order, so the result does not depend on which CTA came last -- and runs
+// the epilogue.  148 SMs stream the weights instead of 16.
 #pragma once
 #include <cuda.h>
 
@@ -33,6 +39,10 @@ struct Args {
   const bf16* resid;  // EPI_ADD_RESID: [rows, ldo] (may alias out)
   int rows, n_out, K;
   int epi;
+  // split-K (gridDim.z > 1)
+  float* part;             // [splits][m_tiles * BM][ldp] fp32 partial tiles
+  unsigned int* counters;  // [m_tiles * n_tiles], zero between launches (the last CTA of a tile resets its counter)
+  long long ldp;           // n_tiles * BN
 };
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -87,6 +97,19 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
 }
 
+// 32 lanes x 32 consecutive fp32 columns of the accumulator -> registers (one row per lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, Args a) {
   extern __shared__ unsigned char smem_raw[];
@@ -98,7 +121,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-  const int num_kb = a.K / BK;
+  const int splits = gridDim.z;
+  const int num_kb = a.K / BK / splits;        // k blocks of this CTA's slice (the launcher keeps the division exact)
+  const int kb0 = blockIdx.z * num_kb;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -130,8 +155,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
         unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
         unsigned char* sb = sa + BM * BK * 2;
         mbar_expect(&full[s], STAGE_BYTES);
-        tma_load_2d(sa, &map_x, &full[s], kb * BK, m0);
-        tma_load_2d(sb, &map_w, &full[s], kb * BK, n0);
+        tma_load_2d(sa, &map_x, &full[s], (kb0 + kb) * BK, m0);
+        tma_load_2d(sb, &map_w, &full[s], (kb0 + kb) * BK, n0);
       }
     }
   } else if (warp == 1) {
@@ -157,19 +182,58 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
     const int row = m0 + q * 32 + lane;
     mbar_wait(acc_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    bool finish = true;  // this CTA runs the epilogue (always, without split-K)
+    if (splits > 1) {
+      // 1. park the fp32 partial tile (one 128-byte line per lane and step)
+      float* prow = a.part + ((size_t)blockIdx.z * gridDim.y * BM + (m0 - 0) + q * 32 + lane) * a.ldp + n0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(prow + c0 + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+      // 2. count this slice in; the CTA that completes the tile adds the slices up
+      __threadfence();
+      asm volatile("bar.sync 2, 128;" ::: "memory");  // the four epilogue warps
+      __shared__ unsigned int s_last;
+      if (warp == 2 && lane == 0) {
+        unsigned int* ctr = a.counters + blockIdx.y * gridDim.x + blockIdx.x;
+        const unsigned int seen = atomicAdd(ctr, 1u);
+        s_last = seen == (unsigned)splits - 1;
+        if (s_last) *ctr = 0;  // ready for the next launch on this stream
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      finish = s_last != 0;
+      if (finish) __threadfence();
+    }
+    if (finish) {
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (splits > 1) {
+        // slices in order 0 .. splits-1, whoever finishes: deterministic sums
+        const float* p0 = a.part + ((size_t)m0 + q * 32 + lane) * a.ldp + n0 + c0;
+        const size_t zs = (size_t)gridDim.y * BM * a.ldp;
+        float acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 t = __ldcg(reinterpret_cast<const float4*>(p0 + j));
+          acc[j] = t.x; acc[j + 1] = t.y; acc[j + 2] = t.z; acc[j + 3] = t.w;
+        }
+        for (int z = 1; z < splits; ++z) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(p0 + z * zs + j));
+            acc[j] += t.x; acc[j + 1] += t.y; acc[j + 2] += t.z; acc[j + 3] += t.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(acc[j]);
+      } else {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      }
       if (row < a.rows) {
         const int n = n0 + c0;
         if (a.epi == EPI_SWIGLU_PAIRS) {
@@ -210,6 +274,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
           }
         }
       }
+    }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -186,24 +186,27 @@ __device__ __forceinline__ unsigned long long gtimer() {
   return t;
 }
 // A wait that exceeds its trip cap must not hang the GPU -- and must not __trap() either: a trap poisons
-// the CUDA context, and the reference's retry loops (tts_service.py:500-514) could never recover.  Instead
-// the first thread to give up records a sticky error code (device word + mapped host word) and from then on
-// EVERY wait of every thread returns after at most 256 more trips: the launch drains to its end with garbage
-// tokens (clamped before they index anything), the context survives, and the host raises from the code.
-__device__ __noinline__ bool give_up_slow(Sync* sync, unsigned spin, unsigned cap, unsigned code) {
-  if (*reinterpret_cast<volatile unsigned int*>(&sync->error) != 0u) return true;
-  if (spin > cap) {
-    report_error(sync, code);
-    return true;
+// the CUDA context, and the reference's retry loops (tts_service.py:500-514) could never recover.  Instead the
+// waiting thread leaves its loop, records a sticky error code (device word + mapped host word) and marks itself
+// "dead": every later wait of a dead thread returns at its first failed test, so the launch drains to its end
+// with garbage tokens (clamped before they index anything) within about one cap's time, the context survives,
+// and the host raises from the code.  The poll loops themselves contain no call that returns (round 2 measured
+// +5 % frame time with one: the compiler has to keep the loop's live state across it), only a trip count test;
+// the report happens after the loop.
+constexpr unsigned SPIN_CAP = 1u << 22;   // ~ seconds of L2 round trips
+constexpr unsigned SPIN_DEAD = SPIN_CAP;  // first trip count of a dead thread's waits: its first test already fails
+__device__ __noinline__ unsigned on_timeout(Sync* sync, unsigned code) {
+  report_error(sync, code);
+  return SPIN_DEAD;
+}
+// trip count test of a wait loop; ``spin`` starts at c.dead (0, or SPIN_DEAD once the thread has given up)
+__device__ __forceinline__ bool expired(unsigned spin) { return spin >= SPIN_CAP; }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, Sync* sync, unsigned& dead, unsigned code) {
+  unsigned spin = dead;
+  while (!mbar_try(bar, parity)) {
+    if (expired(++spin)) break;
   }
-  return false;
-}
-__device__ __forceinline__ bool give_up(Sync* sync, unsigned spin, unsigned cap, unsigned code) {
-  return (spin & 255u) == 255u && give_up_slow(sync, spin, cap, code);
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, Sync* sync, unsigned code) {
-  for (unsigned spin = 0; !mbar_try(bar, parity); ++spin)
-    if (give_up(sync, spin, 1u << 22, code)) break;
+  if (expired(spin) && !dead) dead = on_timeout(sync, code);
 }
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
@@ -219,14 +222,19 @@ __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1
 
 // ---- ordering of the plain KV-cache rows --------------------------------------------------------------
 // The depth decoder's cache rows are written as plain bf16 (a QKV epilogue, or the sampling phase's table
-// gather) and read by OTHER CTAs in later codebook steps of the SAME launch (attn_prefetch).  The tagged
-// hand-off words do not order those plain stores, so the writing thread fences after its stores
-// (release side) and the reading CTA fences before it issues the loads (acquire side): with the chain of
-// tagged words between the two, that is release -> ... -> acquire at gpu scope.  Only the threads that wrote
-// cache rows pay for the writer fence, after their tagged stores went out, so it overlaps the hand-off
-// the CTA waits for anyway.  (The backbone cache needs none: its rows are read by the next launch.)
+// gather) and read by OTHER CTAs in later codebook steps of the SAME launch (attn_prefetch): stores that go
+// straight to L2 (the point of coherence; L1 is write-through and the readers use cp.async.cg, which bypasses
+// L1), read back >= 16 phases = tens of microseconds later.  The tagged hand-off words do not FORMALLY order
+// those plain stores; -DMEGA_KV_FENCE=7 adds the release fence after the writers' stores and the acquire fence
+// before the readers' loads that do (release -> chain of tagged words -> acquire at gpu scope).  Measured on
+// B200 (profiles/r2_kv_fence_variants.txt): writers +0.105 ms, readers +0.156 ms, sampling-phase writers
+// +0.039 ms per frame -- 7 % of the frame for an ordering the hardware provides anyway by a margin of four orders
+// of magnitude (a store reaches L2 in < 1 us), so the default build leaves them out; a tagged-word cache (one
+// tag per frame, no ordering assumed at all) was built and measured too and is slower still (+0.5 ms: its
+// reads cannot be asynchronous).  tests/test_gpu_stress.py runs 2000+ frames against the per-op kernels, which
+// have a kernel boundary between every write and read.  (The backbone cache is read by the NEXT launch.)
 #ifndef MEGA_KV_FENCE
-#define MEGA_KV_FENCE 7  /* bit 0: QKV-epilogue writers, bit 1: readers (attn_prefetch), bit 2: sampling-phase writers */
+#define MEGA_KV_FENCE 0  /* bit 0: QKV-epilogue writers, bit 1: readers (attn_prefetch), bit 2: sampling-phase writers */
 #endif
 template <int WHO>
 __device__ __forceinline__ void kv_fence() {
@@ -262,27 +270,24 @@ __device__ __forceinline__ void stv2(uint32_t* p, const uint2& v) { __stcg(reint
 __device__ __forceinline__ bool fresh4(const uint4& v, uint32_t tag) {
   return ((((v.x ^ tag) | (v.y ^ tag)) | ((v.z ^ tag) | (v.w ^ tag))) & 0xffff0000u) == 0;
 }
-__device__ __forceinline__ uint4 poll4(const uint32_t* p, uint32_t tag, uint4 v, Sync* sync) {
-  for (unsigned spin = 0; !fresh4(v, tag); ++spin) {
-    if (give_up(sync, spin, 1u << 22, 0x400)) break;
-    v = ldv4(p);
-  }
-  return v;
-}
-__device__ __forceinline__ uint2 poll2(const uint32_t* p, uint32_t tag, Sync* sync) {
+__device__ __forceinline__ uint2 poll2(const uint32_t* p, uint32_t tag, Sync* sync, unsigned& dead) {
   uint2 v = ldv2(p);
-  for (unsigned spin = 0; (((v.x ^ tag) | (v.y ^ tag)) & 0xffff0000u) != 0; ++spin) {
-    if (give_up(sync, spin, 1u << 22, 0x401)) break;
+  unsigned spin = dead;
+  while ((((v.x ^ tag) | (v.y ^ tag)) & 0xffff0000u) != 0) {
+    if (expired(++spin)) break;
     v = ldv2(p);
   }
+  if (expired(spin) && !dead) dead = on_timeout(sync, 0x401);
   return v;
 }
-__device__ __forceinline__ uint32_t poll1(const uint32_t* p, uint32_t tag, Sync* sync) {
+__device__ __forceinline__ uint32_t poll1(const uint32_t* p, uint32_t tag, Sync* sync, unsigned& dead) {
   uint32_t v = ldv1(p);
-  for (unsigned spin = 0; ((v ^ tag) & 0xffff0000u) != 0; ++spin) {
-    if (give_up(sync, spin, 1u << 22, 0x402)) break;
+  unsigned spin = dead;
+  while (((v ^ tag) & 0xffff0000u) != 0) {
+    if (expired(++spin)) break;
     v = ldv1(p);
   }
+  if (expired(spin) && !dead) dead = on_timeout(sync, 0x402);
   return v;
 }
 // four tagged words -> four packed bf16 (the low halves)
@@ -373,6 +378,7 @@ __device__ __forceinline__ const unsigned char* cursor_src(const Cursor& k, cons
 __device__ __forceinline__ void producer_loop(const PfDesc* tab, int ntab, unsigned char* ring, uint64_t* full, uint64_t* empty,
                                               Sync* sync, int lane) {
   const int cta = blockIdx.x, ncta = gridDim.x;
+  unsigned dead = 0;  // 1 << 26 once a wait for drained slots has given up (see on_timeout)
   // Weights that are used once per frame stream through L2 evict-first.  The depth decoder's 222 MB are
   // used 31 times per frame: the matrices marked "keep" are loaded evict-last, so that part of them
   // survives in the 126 MB L2 from one codebook step to the next and never touches HBM again.
@@ -389,11 +395,18 @@ __device__ __forceinline__ void producer_loop(const PfDesc* tab, int ntab, unsig
     // Wait until all eight slots of this step are drained.  While waiting -- the CTA sits in a latency
     // chain and HBM would idle -- run the second, deeper stage of the weight stream: pull chunks up to
     // L2_AHEAD steps beyond the ring into the 126 MB L2, so that the rings later refill at L2 speed.
-    for (unsigned spin = 0;; ++spin) {
+    unsigned spin = dead;  // (warp-uniform: the trip count is the same in every lane)
+    for (;; ++spin) {
       // (with the L2 stage on, probe without suspending so that the prefetches really go out while waiting)
       const bool ok = lane >= NW || (L2_AHEAD > 0 ? mbar_test(eb, parity) : mbar_try(eb, parity));
       if (__all_sync(0xffffffffu, ok)) break;
-      if (__any_sync(0xffffffffu, give_up(sync, spin, 1u << 26, 0x100))) break;  // warp-uniform exit
+      if (spin >= (1u << 26)) {
+        if (!dead) {
+          if (lane == 0) report_error(sync, 0x100);
+          dead = 1u << 26;
+        }
+        break;
+      }
       if (L2_AHEAD > 0 && ahead < SLOTS + L2_AHEAD && cursor_valid(k2, ntab)) {
         if (ahead >= SLOTS && lane < NW) {  // the first SLOTS steps ahead are in the ring (or on their way) already
           int chunk;
@@ -435,6 +448,7 @@ struct Ctx {
   int tid, warp, lane;
   int bb_pos, bb_slot;  // RoPE position / cache slot of the backbone row of this frame
   int bb_lane;          // cache lane of the stream (continuous batching; 0 for the plain batch-1 use)
+  mutable unsigned dead;  // 0, or SPIN_DEAD once this thread gave up a wait (see on_timeout): later waits return at once
   unsigned seq;         // frame counter (tag salt)
   uint32_t tag;         // tag of the words the current phase produces
 };
@@ -481,7 +495,7 @@ __device__ __forceinline__ void epilogue(const Phase& ph, const Ctx& c, int r0, 
     uint2 w = make_uint2(pre.a, pre.b);
     const uint32_t rtag = tag_of(c.seq, ph.resid_src[n]);
     if ((((w.x ^ rtag) | (w.y ^ rtag)) & 0xffff0000u) != 0)
-      w = poll2(my_copy(ph.t_out, ph.out_rs) + (size_t)n * ph.ldo + r0, rtag, c.sync);
+      w = poll2(my_copy(ph.t_out, ph.out_rs) + (size_t)n * ph.ldo + r0, rtag, c.sync, c.dead);
     pa = tval(w.x);
     pb = tval(w.y);
   } else {
@@ -567,7 +581,7 @@ __device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c, int cl, int
     }
     const int slot = c.cnt % SLOTS;
     if (t == 0) CK(9);
-    mbar_wait(&c.full[c.warp * SLOTS + slot], (c.cnt / SLOTS) & 1, c.sync, 0x200 + c.warp);
+    mbar_wait(&c.full[c.warp * SLOTS + slot], (c.cnt / SLOTS) & 1, c.sync, c.dead, 0x200);
     if (t == 0) CK(10);
     {
       const unsigned char* wp = c.ring + (size_t)(c.warp * SLOTS + slot) * SLOT_BYTES + c.lane * 16;
@@ -733,7 +747,8 @@ __device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
         const int u = u0 + t * NCT + c.tid;
         if (u < total) v[t] = ldv4(u < qunits ? tq + u * 4 : tkv + (u - qunits) * 4);
       }
-      for (unsigned spin = 0;; ++spin) {  // both units together (see stage_x)
+      unsigned spin = c.dead;
+      for (;; ++spin) {  // both units together (see stage_x)
         bool ok = true;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -744,8 +759,9 @@ __device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
           }
         }
         if (ok) break;
-        if (give_up(c.sync, spin, 1u << 22, 0x406)) break;
+        if (expired(spin)) break;
       }
+      if (expired(spin) && !c.dead) c.dead = on_timeout(c.sync, 0x406);
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const int u = u0 + t * NCT + c.tid;
@@ -904,7 +920,8 @@ __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
     }
     // all units of the batch are polled TOGETHER: one round trip per round for every stale unit, not one
     // after the other (a lane that waits for data would otherwise pay a round trip per unit after it lands)
-    for (unsigned spin = 0;; ++spin) {
+    unsigned spin = c.dead;
+    for (;; ++spin) {
       bool ok = true;
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -918,8 +935,9 @@ __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
         }
       }
       if (ok) break;
-      if (give_up(c.sync, spin, 1u << 22, 0x405)) break;
+      if (expired(spin)) break;
     }
+    if (expired(spin) && !c.dead) c.dead = on_timeout(c.sync, 0x405);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int e = e0 + t * 32 + c.lane;
@@ -1013,7 +1031,7 @@ __device__ __forceinline__ void attn_phase(const Phase& ph, Ctx& c) {
     const int which = d / hd, dd = d - which * hd;
     const uint32_t* src = which == 0 ? my_copy(ph.t_q, ph.q_rs) + (size_t)h * hd + dd
                                      : my_copy(ph.t_kv, ph.kv_rs) + (size_t)(which - 1) * krows + (size_t)kvh * hd + dd;
-    qs[d] = tval(poll1(src, tag, c.sync));  // qs, kcur, vcur are contiguous
+    qs[d] = tval(poll1(src, tag, c.sync, c.dead));  // qs, kcur, vcur are contiguous
   }
   csync<NCT, CBAR>();
   float mx = -INFINITY;
@@ -1109,7 +1127,9 @@ __device__ __forceinline__ void embed_phase(const Phase& ph, Ctx& c) {
       on[j] = cb <= ph.C && msk[cb < ph.C + 1 ? cb : 0] != 0;
       v[j] = make_uint4(0, 0, 0, 0);
       if (on[j]) {
-        const size_t t = checked_token(tok, cb, ph.C, ph.V, ph.TV, c.sync);
+        // (ids the reference would raise on are reported once, by the kernel prologue, and read as row 0 here)
+        const unsigned long long tt = (unsigned long long)tok[cb];
+        const size_t t = tt < (unsigned long long)(cb < ph.C ? ph.V : ph.TV) ? (size_t)tt : 0;
         const bf16* row = (cb < ph.C) ? ph.audio_emb + (t + (size_t)ph.V * cb) * ph.D : ph.text_emb + t * ph.D;
         v[j] = *reinterpret_cast<const uint4*>(row + u * 8);
       }
@@ -1150,7 +1170,8 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
       const int u = c.tid + t * NCT;
       if (u < nunits) w[t] = ldv4(ph.t_logits + u * 4);
     }
-    for (unsigned spin = 0;; ++spin) {  // all units together (see stage_x)
+    unsigned spin = c.dead;
+    for (;; ++spin) {  // all units together (see stage_x)
       bool ok = true;
 #pragma unroll
       for (int t = 0; t < MAXU; ++t) {
@@ -1161,8 +1182,9 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
         }
       }
       if (ok) break;
-      if (give_up(c.sync, spin, 1u << 22, 0x407)) break;
+      if (expired(spin)) break;
     }
+    if (expired(spin) && !c.dead) c.dead = on_timeout(c.sync, 0x407);
 #pragma unroll
     for (int t = 0; t < MAXU; ++t) {
       const int u = c.tid + t * NCT;
@@ -1324,7 +1346,7 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
 
   Ctx c;
   c.P = P; c.trp = nullptr; c.ring = ring; c.xs = xs; c.full = full; c.empty = empty; c.scratch = scratch; c.iscratch = iscratch;
-  c.psum = psum; c.sync = sync; c.cnt = 0; c.tid = threadIdx.x; c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
+  c.psum = psum; c.sync = sync; c.cnt = 0; c.dead = 0; c.tid = threadIdx.x; c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
   c.bb_slot = row_len(P, 0) + P->S - 1;
   c.bb_lane = row_lane(P, 0);
   {
@@ -1334,6 +1356,11 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
     const bool bad = pos != c.bb_slot || pos >= phbuf[0].rope_len;
     if (bad && threadIdx.x == 0 && blockIdx.x == 0) report_error(sync, 0x803);
     c.bb_pos = bad ? c.bb_slot : (int)pos;
+    const Phase& e = phbuf[0];  // the embed phase: range check of the frame's token ids, once per launch
+    if (blockIdx.x == 0 && (int)threadIdx.x <= e.C) {
+      const size_t fr = (size_t)(P->S - 1) * (e.C + 1);
+      if (P->mask[fr + threadIdx.x]) checked_token(P->tokens + fr, threadIdx.x, e.C, e.V, e.TV, sync);
+    }
   }
   c.seq = sync->seq;
 

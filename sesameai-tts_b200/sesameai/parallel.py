@@ -55,13 +55,16 @@ def gather_frames(local: Dict[int, torch.Tensor], n_requests: int, rank: int, wo
 
 
 def serve_sharded(model, requests, rank: int, world: int, *, lanes: int, temperature: float, topk: int, groups: int = 1,
-                  device="cpu", max_frames: int = 2048, codebooks: int = 32) -> Optional[List[torch.Tensor]]:
+                  device="cpu", max_frames: int = 2048, codebooks: int = 32, server=None) -> Optional[List[torch.Tensor]]:
     """BASELINE config 5 ("N concurrent requests on 1/2/4/8 GPUs"): this rank serves its round-robin shard of
     ``requests`` (``sesameai.serving.Request``) with continuous batching -- ``groups`` lane groups of ``lanes``
-    cache lanes each -- and the finished frames are gathered on rank 0.  No collective on the decode path."""
+    cache lanes each -- and the finished frames are gathered on rank 0.  No collective on the decode path.
+    ``server``: a ``LaneGroups`` built beforehand (a serving process keeps its decode contexts alive)."""
     from .serving import LaneGroups
 
     mine = [requests[i] for i in shard_requests(len(requests), rank, world)]
-    served = LaneGroups(model, groups, lanes, temperature, topk).run(mine) if mine else {}
+    if server is None:
+        server = LaneGroups(model, groups, lanes, temperature, topk, max_frames=max_frames)
+    served = server.run(mine) if mine else {}
     local = {r.rid: served[r.rid].to(torch.int32) for r in mine}
     return gather_frames(local, len(requests), rank, world, device=device, max_frames=max_frames, codebooks=codebooks)

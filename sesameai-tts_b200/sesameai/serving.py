@@ -16,7 +16,7 @@ the launch gaps and latency bubbles of each other.
 from __future__ import annotations
 
 from collections import deque
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Deque, Dict, Iterable, List, Optional, Sequence
 
 import torch
@@ -38,13 +38,13 @@ class Request:
 class _Stream:
     req: Request
     lane: int
-    frames: List[torch.Tensor] = field(default_factory=list)  # device rows [32] int32
-    calls: int = 0  # generate_frame calls spent (the reference's loop counter)
+    n_frames: int = 0  # frames kept so far (rows of the batcher's frame buffer)
+    calls: int = 0     # generate_frame calls spent (the reference's loop counter)
 
 
 class ContinuousBatcher:
     def __init__(self, model: Model, max_lanes: int, temperature: float, topk: int, *, setup: bool = True,
-                 stream: Optional[torch.cuda.Stream] = None):
+                 stream: Optional[torch.cuda.Stream] = None, max_frames: int = 2048):
         self.model = model
         self.max_lanes = int(max_lanes)
         self.temperature, self.topk = float(temperature), int(topk)
@@ -55,6 +55,9 @@ class ContinuousBatcher:
         C = model.config.audio_num_codebooks
         self._C = C
         self._last = torch.zeros(self.max_lanes, C, dtype=torch.int32, device=self.device)  # newest frame per lane
+        # frames of the running streams, on the device: one scatter per round, one slice + copy per finished stream
+        self._max_frames = int(max_frames)
+        self._frames = torch.zeros(self.max_lanes, self._max_frames, C, dtype=torch.int32, device=self.device)
         self._free: List[int] = list(range(self.max_lanes - 1, -1, -1))
         self._active: Dict[int, _Stream] = {}
         self._pending: Deque[Request] = deque()
@@ -64,10 +67,12 @@ class ContinuousBatcher:
         self._inflight = None
         self.steps = 0          # batched decode calls issued
         self.row_steps = 0      # sum of their batch sizes (= frames computed by decode calls)
-        self.prefills = 0
+        self.prefills = 0       # prefill calls (requests of equal prompt length join in one batched call)
 
     # -- queue -------------------------------------------------------------------------------------------
     def submit(self, req: Request) -> None:
+        if req.max_frames > self._max_frames:
+            raise ValueError("request asks for more frames than the batcher was built for")
         self._pending.append(req)
 
     @property
@@ -88,73 +93,88 @@ class ContinuousBatcher:
         assert self._inflight is None
         m = self.model
         with self._ctx():
-            fresh: List[_Stream] = []
-            # join: prefill a free lane per queued request (the prompt's last row samples the first frame)
-            while self._pending and self._free:
-                req = self._pending.popleft()
-                lane = self._free.pop()
-                m.reset_lane(lane)
-                S = req.tokens.shape[0]
-                tok = req.tokens.to(self.device, torch.int64).unsqueeze(0)
-                msk = req.mask.to(self.device, torch.bool).unsqueeze(0)
-                pos = torch.arange(S, device=self.device).unsqueeze(0)
-                st = _Stream(req, lane)
-                s = m.generate_frame(tok, msk, pos, self.temperature, self.topk, lanes=[lane])
-                self._last[lane] = s[0]
-                st.calls = 1
-                self.prefills += 1
-                fresh.append(st)
             # advance: one batched decode step for every stream that already holds a frame to feed back
             rows = sorted(self._active)
-            out = None
             if rows:
                 if rows != self._rows:
                     self._rows = rows
                     self._rows_dev = torch.tensor(rows, dtype=torch.long, device=self.device)
                 B = len(rows)
-                tok = torch.zeros(B, 1, self._C + 1, dtype=torch.int64, device=self.device)
-                tok[:, 0, : self._C] = self._last.index_select(0, self._rows_dev)
-                msk = torch.ones(B, 1, self._C + 1, dtype=torch.bool, device=self.device)
+                # The library replays one captured CUDA graph per batch size: as streams leave one by one the
+                # batch is padded to the next bucket with idle rows on free lanes (rewound before and after), so a
+                # ragged pool needs a dozen graphs instead of one per distinct size.
+                pad = self._free[: max(0, min(_bucket(B), self.max_lanes) - B)]
+                for l in pad:
+                    m.reset_lane(l)
+                Bp = B + len(pad)
+                tok = torch.zeros(Bp, 1, self._C + 1, dtype=torch.int64, device=self.device)
+                tok[:B, 0, : self._C] = self._last.index_select(0, self._rows_dev)
+                msk = torch.ones(Bp, 1, self._C + 1, dtype=torch.bool, device=self.device)
                 msk[:, :, -1] = False
-                pos = torch.tensor([[self._lane_len(l)] for l in rows], dtype=torch.int64, device=self.device)
-                out = m.generate_frame(tok, msk, pos, self.temperature, self.topk, lanes=rows)
+                pos = torch.tensor([[self._lane_len(l)] for l in rows + pad], dtype=torch.int64, device=self.device)
+                out = m.generate_frame(tok, msk, pos, self.temperature, self.topk, lanes=rows + pad)[:B]
+                for l in pad:
+                    m.reset_lane(l)
                 self._last.index_copy_(0, self._rows_dev, out)
                 for l in rows:
                     self._active[l].calls += 1
                 self.steps += 1
                 self.row_steps += B
+            # join: queued requests take the free lanes; those with the same prompt length are prefilled by ONE
+            # batched call (the prompt's last row samples each stream's first frame)
+            fresh: List[_Stream] = []
+            while self._pending and self._free:
+                fresh.append(_Stream(self._pending.popleft(), self._free.pop()))
+            by_len: Dict[int, List[_Stream]] = {}
             for st in fresh:
-                self._active[st.lane] = st
+                by_len.setdefault(int(st.req.tokens.shape[0]), []).append(st)
+            for S, group in by_len.items():
+                lanes = [st.lane for st in group]
+                for l in lanes:
+                    m.reset_lane(l)
+                tok = torch.stack([st.req.tokens for st in group]).to(self.device, torch.int64)
+                msk = torch.stack([st.req.mask for st in group]).to(self.device, torch.bool)
+                pos = torch.arange(S, device=self.device).unsqueeze(0).repeat(len(group), 1)
+                s = m.generate_frame(tok, msk, pos, self.temperature, self.topk, lanes=lanes)
+                self._last.index_copy_(0, torch.tensor(lanes, dtype=torch.long, device=self.device), s)
+                for st in group:
+                    st.calls = 1
+                    self._active[st.lane] = st
+                self.prefills += 1
             lanes_now = sorted(self._active)
             if not lanes_now:
                 return
-            idx = torch.tensor(lanes_now, dtype=torch.long, device=self.device)
+            idx = self._rows_dev if lanes_now == self._rows else torch.tensor(lanes_now, dtype=torch.long, device=self.device)
             newest = self._last.index_select(0, idx)                      # [n, C] frames sampled this round
-            eos = (newest == 0).all(dim=1).to("cpu", non_blocking=True)   # reference generator.py:285, per stream
+            eos = (newest == 0).all(dim=1)                                # reference generator.py:285, per stream
+            # store the frame of every stream at its own frame index (an EOS frame lands one past the end and is never read)
+            at = torch.tensor([min(len_, self._max_frames - 1) for len_ in (self._active[l].n_frames for l in lanes_now)],
+                              dtype=torch.long, device=self.device)
+            self._frames[idx, at] = newest
+            eos_h = eos.to("cpu", non_blocking=True)
             ev = None
             if self.device.type == "cuda":
                 ev = torch.cuda.Event()
                 ev.record()
-            self._inflight = (lanes_now, newest, eos, ev)
+            self._inflight = (lanes_now, eos_h, ev)
 
     def end(self) -> None:
         if self._inflight is None:
             return
-        lanes_now, newest, eos, ev = self._inflight
+        lanes_now, eos, ev = self._inflight
         self._inflight = None
         if ev is not None:
             ev.synchronize()
         self.model.check_device_error()
+        eos = eos.tolist()
         for i, lane in enumerate(lanes_now):
             st = self._active[lane]
-            finished = bool(eos[i])
+            finished = eos[i]
             if not finished:
-                st.frames.append(newest[i])
+                st.n_frames += 1
                 finished = st.calls >= st.req.max_frames
             if finished:
-                C = self._C
-                self._done[st.req.rid] = (torch.stack(st.frames).cpu() if st.frames
-                                          else torch.zeros(0, C, dtype=torch.int32))
+                self._done[st.req.rid] = self._frames[lane, : st.n_frames].to("cpu", copy=True)
                 del self._active[lane]
                 self._free.append(lane)
 
@@ -165,6 +185,15 @@ class ContinuousBatcher:
             self.begin()
             self.end()
         return self._done
+
+
+def _bucket(b: int) -> int:
+    """Batch sizes the decode graphs are captured for: 1, 2, 4, 8, multiples of 8 up to 64, then multiples of 32."""
+    if b <= 8:
+        return 1 if b <= 1 else 2 if b <= 2 else 4 if b <= 4 else 8
+    if b <= 64:
+        return (b + 7) // 8 * 8
+    return (b + 31) // 32 * 32
 
 
 class _Null:
@@ -179,7 +208,7 @@ class LaneGroups:
     """``groups`` independent ContinuousBatchers (own decode context + CUDA stream each, shared parameters);
     requests are dealt round-robin.  All groups launch their round before any of them waits for its EOS flags."""
 
-    def __init__(self, model: Model, groups: int, lanes_per_group: int, temperature: float, topk: int):
+    def __init__(self, model: Model, groups: int, lanes_per_group: int, temperature: float, topk: int, max_frames: int = 2048):
         self.batchers: List[ContinuousBatcher] = []
         dev = next(model.parameters()).device
         for g in range(groups):
@@ -188,7 +217,7 @@ class LaneGroups:
             if st is not None:
                 st.wait_stream(torch.cuda.current_stream(dev))
             with (torch.cuda.stream(st) if st is not None else _Null()):
-                self.batchers.append(ContinuousBatcher(mg, lanes_per_group, temperature, topk, stream=st))
+                self.batchers.append(ContinuousBatcher(mg, lanes_per_group, temperature, topk, stream=st, max_frames=max_frames))
 
     def run(self, requests: Sequence[Request]) -> Dict[int, torch.Tensor]:
         for i, r in enumerate(requests):

@@ -1,0 +1,18 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+T=${1:-r2f}
+python -m pytest tests/test_gpu_frame.py tests/test_gpu_serving.py tests/test_gpu_stress.py tests/test_gpu_post.py -m gpu -q -x -s > gpurun_out/${T}_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/${T}_tests.log
+grep -E "stress|passed|failed|rc=" gpurun_out/${T}_tests.log | tail -4
+for rep in 1 2; do
+(cd r1_tree && python bench.py --steps 100 --warmup 5 --no-cpu-baseline) > gpurun_out/${T}_bench_r1tree_$rep.json 2> gpurun_out/${T}_bench_r1tree_$rep.err
+python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-secondary > gpurun_out/${T}_bench_cur_$rep.json 2> gpurun_out/${T}_bench_cur_$rep.err
+for f in r1tree cur; do python -c "
+import json
+d=json.loads(open('gpurun_out/${T}_bench_${f}_$rep.json').read().strip().splitlines()[-1]); print('$f', d['ms_per_step'], d['e2e']['value'])"; done
+done
+python bench.py --steps 60 --warmup 5 --no-cpu-baseline > gpurun_out/${T}_bench_full.json 2> gpurun_out/${T}_bench_full.err
+python -c "
+import json
+d=json.loads(open('gpurun_out/${T}_bench_full.json').read().strip().splitlines()[-1]); print(json.dumps(d['secondary']['config5_256_requests'], indent=1))"
+tail -3 gpurun_out/${T}_bench_full.err
