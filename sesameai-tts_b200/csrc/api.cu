@@ -710,7 +710,8 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
 }
 
 static int launch_mega(csm_ctx* x, const FrameParams& p, cudaStream_t st) {
-  mega::k_mega_prepare<<<1, 1, 0, st>>>(x->d_params, p, x->d_sync); COUNT_LAUNCH();
+  mega::k_mega_prepare<<<1, 96, 0, st>>>(x->d_params, p, x->d_sync, x->cfg.codebooks, x->cfg.audio_vocab, x->cfg.text_vocab,
+                                         x->bb.rope_len); COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
   const mega::Phase* ph = x->d_phases;
   int n = x->n_phases;
@@ -1114,7 +1115,8 @@ static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const b
   dim3 grid((n_out + tc::BN - 1) / tc::BN, (rows + tc::BM - 1) / tc::BM);
   // decode steps of large batches: few tiles, long K -> split K over the idle SMs (see gemm_tc.cuh)
   const int tiles = (int)(grid.x * grid.y), num_kb = K / tc::BK;
-  if (splitk && rows <= TC_SPLIT_MAX_ROWS && 2 * tiles <= TC_SPLIT_TILES) {
+  // (only the long-K projections: with K = 1024 .. 2048 a tile is 16 .. 32 k blocks and the second pass costs more than it saves)
+  if (splitk && rows <= TC_SPLIT_MAX_ROWS && 2 * tiles <= TC_SPLIT_TILES && num_kb >= 64) {
     int splits = 1;
     while (splits * 2 <= 8 && splits * 2 * tiles <= TC_SPLIT_TILES && num_kb % (splits * 2) == 0 && num_kb / (splits * 2) >= 2)
       splits *= 2;

@@ -208,30 +208,52 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
       finish = s_last != 0;
       if (finish) __threadfence();
     }
-    if (finish) {
+    if (finish && splits > 1) {
+      // The tile's last CTA adds the slices in order 0 .. splits-1 (deterministic whoever finishes) and runs the
+      // epilogue in a COALESCED layout: a warp takes whole rows, lane l the four columns 4l .. 4l+3, four rows in
+      // flight -- the loads of all slices of a row batch go out together (the row-per-lane layout of the TMEM
+      // path would make this pass a chain of dependent L2 round trips).
+      const int et = threadIdx.x - 64;  // 0 .. 127 among the epilogue warps
+      const int ew = et >> 5;
+      const size_t zs = (size_t)gridDim.y * BM * a.ldp;
+      const int n = n0 + lane * 4;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      if (splits > 1) {
-        // slices in order 0 .. splits-1, whoever finishes: deterministic sums
-        const float* p0 = a.part + ((size_t)m0 + q * 32 + lane) * a.ldp + n0 + c0;
-        const size_t zs = (size_t)gridDim.y * BM * a.ldp;
-        float acc[32];
+      for (int r0 = ew * 32; r0 < ew * 32 + 32; r0 += 4) {
+        float4 acc[4];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 t = __ldcg(reinterpret_cast<const float4*>(p0 + j));
-          acc[j] = t.x; acc[j + 1] = t.y; acc[j + 2] = t.z; acc[j + 3] = t.w;
-        }
+        for (int i = 0; i < 4; ++i) acc[i] = __ldcg(reinterpret_cast<const float4*>(a.part + ((size_t)m0 + r0 + i) * a.ldp + n));
         for (int z = 1; z < splits; ++z) {
+          float4 t[4];
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 t = __ldcg(reinterpret_cast<const float4*>(p0 + z * zs + j));
-            acc[j] += t.x; acc[j + 1] += t.y; acc[j + 2] += t.z; acc[j + 3] += t.w;
+          for (int i = 0; i < 4; ++i) t[i] = __ldcg(reinterpret_cast<const float4*>(a.part + z * zs + ((size_t)m0 + r0 + i) * a.ldp + n));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[i].x += t[i].x; acc[i].y += t[i].y; acc[i].z += t[i].z; acc[i].w += t[i].w;
           }
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(acc[j]);
-      } else {
+        for (int i = 0; i < 4; ++i) {
+          const int rr = m0 + r0 + i;
+          if (rr >= a.rows) continue;
+          const float y[4] = {rbf(acc[i].x), rbf(acc[i].y), rbf(acc[i].z), rbf(acc[i].w)};
+          if (a.epi == EPI_SWIGLU_PAIRS) {
+            bf16* o = a.out + (long long)rr * a.ldo + (n >> 1);
+            if (n + 1 < a.n_out) o[0] = f2bf(silu_bf(y[0]) * y[1]);
+            if (n + 3 < a.n_out) o[1] = f2bf(silu_bf(y[2]) * y[3]);
+          } else {
+            bf16* o = a.out + (long long)rr * a.ldo + n;
+            const bf16* r = a.resid + (long long)rr * a.ldo + n;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (n + j < a.n_out) o[j] = f2bf(a.epi == EPI_ADD_RESID ? y[j] + bf2f(r[j]) : y[j]);
+          }
+        }
+      }
+    } else if (finish) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      {
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       }
       if (row < a.rows) {

@@ -126,10 +126,24 @@ struct PfTable {
 
 using Sync = DevStatus;  // frame counter (tag salt, bumped by k_mega_prepare) + sticky error word
 
-__global__ void k_mega_prepare(FrameParams* dst, FrameParams v, Sync* sync) {
-  *dst = v;
-  sync->seq += 1;
-  sync->error = 0;  // per call; the host mirror stays sticky until csm_check_error reads it
+// Runs before the megakernel on the same stream: publishes the call's parameters, bumps the frame counter and
+// checks the frame's inputs (token ids of the last prompt row against their tables, input_pos against the cache
+// position and the RoPE table) -- here, not in the megakernel: a returning call in its prologue cost 2 % of the
+// frame (round 2 bisect, profiles/r2_regression_bisect.txt).  The megakernel itself only clamps.
+__global__ void k_mega_prepare(FrameParams* dst, FrameParams v, Sync* sync, int C, int V, int TV, int rope_len) {
+  if (threadIdx.x == 0) {
+    *dst = v;
+    sync->seq += 1;
+    sync->error = 0;  // per call; the host mirror stays sticky until csm_check_error reads it
+  }
+  __syncthreads();
+  const size_t fr = (size_t)(v.S - 1) * (C + 1);  // batch 1: stream 0, last prompt row
+  if ((int)threadIdx.x <= C && v.mask[fr + threadIdx.x]) checked_token(v.tokens + fr, threadIdx.x, C, V, TV, sync);
+  if (threadIdx.x == 0) {
+    const int64_t pos = v.pos[v.S - 1];
+    const int slot = (v.lane_meta ? v.lane_meta[v.B] : v.cache_len) + v.S - 1;
+    if (pos != slot || pos < 0 || pos >= rope_len) report_error(sync, 0x803);
+  }
 }
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -187,26 +201,28 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 // A wait that exceeds its trip cap must not hang the GPU -- and must not __trap() either: a trap poisons
 // the CUDA context, and the reference's retry loops (tts_service.py:500-514) could never recover.  Instead the
-// waiting thread leaves its loop, records a sticky error code (device word + mapped host word) and marks itself
-// "dead": every later wait of a dead thread returns at its first failed test, so the launch drains to its end
-// with garbage tokens (clamped before they index anything) within about one cap's time, the context survives,
-// and the host raises from the code.  The poll loops themselves contain no call that returns (round 2 measured
-// +5 % frame time with one: the compiler has to keep the loop's live state across it), only a trip count test;
-// the report happens after the loop.
-constexpr unsigned SPIN_CAP = 1u << 22;   // ~ seconds of L2 round trips
-constexpr unsigned SPIN_DEAD = SPIN_CAP;  // first trip count of a dead thread's waits: its first test already fails
-__device__ __noinline__ unsigned on_timeout(Sync* sync, unsigned code) {
-  report_error(sync, code);
-  return SPIN_DEAD;
+// first wait to exceed its cap records a sticky error code (device word + mapped host word), and every wait
+// looks at that word once per 1024 trips: from then on each wait of every thread returns within a millisecond,
+// the launch drains to its end with garbage tokens (clamped before they index anything), the context
+// survives, and the host raises from the code.  Everything is inline: a call that RETURNS inside or right
+// after a poll loop makes the compiler keep the loop's live state across it (measured: +5 % and +14 % frame
+// time for the two call-based variants tried in round 2; round 1's trap was free because it never returned).
+constexpr unsigned SPIN_CAP = 1u << 22;  // ~ seconds of L2 round trips
+__device__ __forceinline__ bool give_up(Sync* sync, unsigned spin, unsigned code, unsigned cap = SPIN_CAP) {
+#ifdef MEGA_DIAG_TRAP  /* diagnosis only: round 1's behaviour, to price the soft abort */
+  if (spin > cap) __trap();
+  return false;
+#endif
+  if ((spin & 1023u) != 1023u) return false;
+  if (*reinterpret_cast<volatile unsigned int*>(&sync->error) != 0u) return true;  // somebody gave up: drain
+  if (spin < cap) return false;
+  if (atomicCAS(&sync->error, 0u, code) == 0u && sync->host_error)
+    *reinterpret_cast<volatile unsigned int*>(sync->host_error) = code;  // lands by the end of the launch at the latest
+  return true;
 }
-// trip count test of a wait loop; ``spin`` starts at c.dead (0, or SPIN_DEAD once the thread has given up)
-__device__ __forceinline__ bool expired(unsigned spin) { return spin >= SPIN_CAP; }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, Sync* sync, unsigned& dead, unsigned code) {
-  unsigned spin = dead;
-  while (!mbar_try(bar, parity)) {
-    if (expired(++spin)) break;
-  }
-  if (expired(spin) && !dead) dead = on_timeout(sync, code);
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, Sync* sync, unsigned code) {
+  for (unsigned spin = 0; !mbar_try(bar, parity); ++spin)
+    if (give_up(sync, spin, code)) break;
 }
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
@@ -270,24 +286,20 @@ __device__ __forceinline__ void stv2(uint32_t* p, const uint2& v) { __stcg(reint
 __device__ __forceinline__ bool fresh4(const uint4& v, uint32_t tag) {
   return ((((v.x ^ tag) | (v.y ^ tag)) | ((v.z ^ tag) | (v.w ^ tag))) & 0xffff0000u) == 0;
 }
-__device__ __forceinline__ uint2 poll2(const uint32_t* p, uint32_t tag, Sync* sync, unsigned& dead) {
+__device__ __forceinline__ uint2 poll2(const uint32_t* p, uint32_t tag, Sync* sync) {
   uint2 v = ldv2(p);
-  unsigned spin = dead;
-  while ((((v.x ^ tag) | (v.y ^ tag)) & 0xffff0000u) != 0) {
-    if (expired(++spin)) break;
+  for (unsigned spin = 0; (((v.x ^ tag) | (v.y ^ tag)) & 0xffff0000u) != 0; ++spin) {
+    if (give_up(sync, spin, 0x401)) break;
     v = ldv2(p);
   }
-  if (expired(spin) && !dead) dead = on_timeout(sync, 0x401);
   return v;
 }
-__device__ __forceinline__ uint32_t poll1(const uint32_t* p, uint32_t tag, Sync* sync, unsigned& dead) {
+__device__ __forceinline__ uint32_t poll1(const uint32_t* p, uint32_t tag, Sync* sync) {
   uint32_t v = ldv1(p);
-  unsigned spin = dead;
-  while (((v ^ tag) & 0xffff0000u) != 0) {
-    if (expired(++spin)) break;
+  for (unsigned spin = 0; ((v ^ tag) & 0xffff0000u) != 0; ++spin) {
+    if (give_up(sync, spin, 0x402)) break;
     v = ldv1(p);
   }
-  if (expired(spin) && !dead) dead = on_timeout(sync, 0x402);
   return v;
 }
 // four tagged words -> four packed bf16 (the low halves)
@@ -378,7 +390,6 @@ __device__ __forceinline__ const unsigned char* cursor_src(const Cursor& k, cons
 __device__ __forceinline__ void producer_loop(const PfDesc* tab, int ntab, unsigned char* ring, uint64_t* full, uint64_t* empty,
                                               Sync* sync, int lane) {
   const int cta = blockIdx.x, ncta = gridDim.x;
-  unsigned dead = 0;  // 1 << 26 once a wait for drained slots has given up (see on_timeout)
   // Weights that are used once per frame stream through L2 evict-first.  The depth decoder's 222 MB are
   // used 31 times per frame: the matrices marked "keep" are loaded evict-last, so that part of them
   // survives in the 126 MB L2 from one codebook step to the next and never touches HBM again.
@@ -395,18 +406,11 @@ __device__ __forceinline__ void producer_loop(const PfDesc* tab, int ntab, unsig
     // Wait until all eight slots of this step are drained.  While waiting -- the CTA sits in a latency
     // chain and HBM would idle -- run the second, deeper stage of the weight stream: pull chunks up to
     // L2_AHEAD steps beyond the ring into the 126 MB L2, so that the rings later refill at L2 speed.
-    unsigned spin = dead;  // (warp-uniform: the trip count is the same in every lane)
-    for (;; ++spin) {
+    for (unsigned spin = 0;; ++spin) {
       // (with the L2 stage on, probe without suspending so that the prefetches really go out while waiting)
       const bool ok = lane >= NW || (L2_AHEAD > 0 ? mbar_test(eb, parity) : mbar_try(eb, parity));
       if (__all_sync(0xffffffffu, ok)) break;
-      if (spin >= (1u << 26)) {
-        if (!dead) {
-          if (lane == 0) report_error(sync, 0x100);
-          dead = 1u << 26;
-        }
-        break;
-      }
+      if (__any_sync(0xffffffffu, give_up(sync, spin, 0x100, 1u << 26))) break;  // warp-uniform exit
       if (L2_AHEAD > 0 && ahead < SLOTS + L2_AHEAD && cursor_valid(k2, ntab)) {
         if (ahead >= SLOTS && lane < NW) {  // the first SLOTS steps ahead are in the ring (or on their way) already
           int chunk;
@@ -448,7 +452,6 @@ struct Ctx {
   int tid, warp, lane;
   int bb_pos, bb_slot;  // RoPE position / cache slot of the backbone row of this frame
   int bb_lane;          // cache lane of the stream (continuous batching; 0 for the plain batch-1 use)
-  mutable unsigned dead;  // 0, or SPIN_DEAD once this thread gave up a wait (see on_timeout): later waits return at once
   unsigned seq;         // frame counter (tag salt)
   uint32_t tag;         // tag of the words the current phase produces
 };
@@ -495,7 +498,7 @@ __device__ __forceinline__ void epilogue(const Phase& ph, const Ctx& c, int r0, 
     uint2 w = make_uint2(pre.a, pre.b);
     const uint32_t rtag = tag_of(c.seq, ph.resid_src[n]);
     if ((((w.x ^ rtag) | (w.y ^ rtag)) & 0xffff0000u) != 0)
-      w = poll2(my_copy(ph.t_out, ph.out_rs) + (size_t)n * ph.ldo + r0, rtag, c.sync, c.dead);
+      w = poll2(my_copy(ph.t_out, ph.out_rs) + (size_t)n * ph.ldo + r0, rtag, c.sync);
     pa = tval(w.x);
     pb = tval(w.y);
   } else {
@@ -581,7 +584,7 @@ __device__ __forceinline__ void gemv_groups(const Phase& ph, Ctx& c, int cl, int
     }
     const int slot = c.cnt % SLOTS;
     if (t == 0) CK(9);
-    mbar_wait(&c.full[c.warp * SLOTS + slot], (c.cnt / SLOTS) & 1, c.sync, c.dead, 0x200);
+    mbar_wait(&c.full[c.warp * SLOTS + slot], (c.cnt / SLOTS) & 1, c.sync, 0x200);
     if (t == 0) CK(10);
     {
       const unsigned char* wp = c.ring + (size_t)(c.warp * SLOTS + slot) * SLOT_BYTES + c.lane * 16;
@@ -747,8 +750,7 @@ __device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
         const int u = u0 + t * NCT + c.tid;
         if (u < total) v[t] = ldv4(u < qunits ? tq + u * 4 : tkv + (u - qunits) * 4);
       }
-      unsigned spin = c.dead;
-      for (;; ++spin) {  // both units together (see stage_x)
+      for (unsigned spin = 0;; ++spin) {  // both units together (see stage_x)
         bool ok = true;
 #pragma unroll
         for (int t = 0; t < 2; ++t) {
@@ -759,9 +761,8 @@ __device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
           }
         }
         if (ok) break;
-        if (expired(spin)) break;
+        if (give_up(c.sync, spin, 0x406)) break;
       }
-      if (expired(spin) && !c.dead) c.dead = on_timeout(c.sync, 0x406);
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         const int u = u0 + t * NCT + c.tid;
@@ -920,8 +921,7 @@ __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
     }
     // all units of the batch are polled TOGETHER: one round trip per round for every stale unit, not one
     // after the other (a lane that waits for data would otherwise pay a round trip per unit after it lands)
-    unsigned spin = c.dead;
-    for (;; ++spin) {
+    for (unsigned spin = 0;; ++spin) {
       bool ok = true;
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -935,9 +935,8 @@ __device__ __forceinline__ void stage_x(const Phase& ph, Ctx& c) {
         }
       }
       if (ok) break;
-      if (expired(spin)) break;
+      if (give_up(c.sync, spin, 0x405)) break;
     }
-    if (expired(spin) && !c.dead) c.dead = on_timeout(c.sync, 0x405);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
       const int e = e0 + t * 32 + c.lane;
@@ -1031,7 +1030,7 @@ __device__ __forceinline__ void attn_phase(const Phase& ph, Ctx& c) {
     const int which = d / hd, dd = d - which * hd;
     const uint32_t* src = which == 0 ? my_copy(ph.t_q, ph.q_rs) + (size_t)h * hd + dd
                                      : my_copy(ph.t_kv, ph.kv_rs) + (size_t)(which - 1) * krows + (size_t)kvh * hd + dd;
-    qs[d] = tval(poll1(src, tag, c.sync, c.dead));  // qs, kcur, vcur are contiguous
+    qs[d] = tval(poll1(src, tag, c.sync));  // qs, kcur, vcur are contiguous
   }
   csync<NCT, CBAR>();
   float mx = -INFINITY;
@@ -1170,8 +1169,7 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
       const int u = c.tid + t * NCT;
       if (u < nunits) w[t] = ldv4(ph.t_logits + u * 4);
     }
-    unsigned spin = c.dead;
-    for (;; ++spin) {  // all units together (see stage_x)
+    for (unsigned spin = 0;; ++spin) {  // all units together (see stage_x)
       bool ok = true;
 #pragma unroll
       for (int t = 0; t < MAXU; ++t) {
@@ -1182,9 +1180,8 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
         }
       }
       if (ok) break;
-      if (expired(spin)) break;
+      if (give_up(c.sync, spin, 0x407)) break;
     }
-    if (expired(spin) && !c.dead) c.dead = on_timeout(c.sync, 0x407);
 #pragma unroll
     for (int t = 0; t < MAXU; ++t) {
       const int u = c.tid + t * NCT;
@@ -1346,21 +1343,16 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
 
   Ctx c;
   c.P = P; c.trp = nullptr; c.ring = ring; c.xs = xs; c.full = full; c.empty = empty; c.scratch = scratch; c.iscratch = iscratch;
-  c.psum = psum; c.sync = sync; c.cnt = 0; c.dead = 0; c.tid = threadIdx.x; c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
+  c.psum = psum; c.sync = sync; c.cnt = 0; c.tid = threadIdx.x; c.warp = threadIdx.x >> 5; c.lane = threadIdx.x & 31;
   c.bb_slot = row_len(P, 0) + P->S - 1;
   c.bb_lane = row_lane(P, 0);
   {
     // batch 1: stream 0, last prompt row.  Keys are masked by cache slot; the reference masks by input_pos:
-    // identical when input_pos == cache position (its only use), anything else is reported, not guessed.
+    // identical when input_pos == cache position (its only use).  k_mega_prepare reports anything else; here
+    // the position is only clamped into the RoPE table.
     const int64_t pos = P->pos[P->S - 1];
-    const bool bad = pos != c.bb_slot || pos >= phbuf[0].rope_len;
-    if (bad && threadIdx.x == 0 && blockIdx.x == 0) report_error(sync, 0x803);
-    c.bb_pos = bad ? c.bb_slot : (int)pos;
-    const Phase& e = phbuf[0];  // the embed phase: range check of the frame's token ids, once per launch
-    if (blockIdx.x == 0 && (int)threadIdx.x <= e.C) {
-      const size_t fr = (size_t)(P->S - 1) * (e.C + 1);
-      if (P->mask[fr + threadIdx.x]) checked_token(P->tokens + fr, threadIdx.x, e.C, e.V, e.TV, sync);
-    }
+    const int lim = phbuf[0].rope_len - 1;
+    c.bb_pos = pos < 0 ? 0 : (pos > lim ? lim : (int)pos);
   }
   c.seq = sync->seq;
 
