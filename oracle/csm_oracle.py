@@ -73,11 +73,18 @@ def exp_race_argmax(probs: torch.Tensor, q: Optional[torch.Tensor]) -> torch.Ten
     return torch.argmax(probs / q, dim=-1, keepdim=True).to(dtype=torch.int)
 
 
-def oracle_sample_topk(logits: torch.Tensor, topk: int, temperature: float, q: Optional[torch.Tensor] = None):
-    """``sample_topk`` (sesameai/models.py:77-87): ties with the k-th value are kept."""
+def oracle_sample_topk(logits: torch.Tensor, topk: int, temperature: float, q: Optional[torch.Tensor] = None,
+                       autocast_cuda: bool = False):
+    """``sample_topk`` (sesameai/models.py:77-87): ties with the k-th value are kept.  ``autocast_cuda``: the
+    op dtypes of ``torch.autocast("cuda", bfloat16)`` (tts_service.py:192-194): log_softmax / softmax are on
+    autocast's fp32 list, so the probabilities and the Exp(1) race are fp32 (SURVEY.md 8c mode ii)."""
     x = logits / temperature
     kth = torch.topk(x, topk)[0][..., -1, None]
     x = x.masked_fill(x < kth, -float("Inf"))
+    if autocast_cuda:
+        x = torch.nn.functional.log_softmax(x, dim=-1, dtype=torch.float32)
+        p = torch.nn.functional.softmax(x, dim=-1, dtype=torch.float32)
+        return exp_race_argmax(p, None if q is None else q.float())
     x = torch.nn.functional.log_softmax(x, dim=-1)
     p = torch.nn.functional.softmax(x, dim=-1)
     return exp_race_argmax(p, q)
@@ -97,6 +104,17 @@ class OracleCSM(nn.Module):
         self.projection = nn.Linear(d_bb, d_dec, bias=False)
         self.codebook0_head = nn.Linear(d_bb, V, bias=False)
         self.audio_head = nn.Parameter(torch.empty(C - 1, d_dec, V))
+        # Mode (ii) of SURVEY.md 8c: the op dtypes of ``torch.autocast("cuda", dtype=bfloat16)`` around the frame
+        # loop (tts_service.py:192-194), emulated on the CPU (CPU autocast has different op lists).  What changes
+        # against the plain mode: ``sum`` is on autocast's fp32 list, so the embedding sum -- and with it the whole
+        # BACKBONE residual stream and its RMSNorm outputs -- is fp32; every linear layer (lower-precision list)
+        # rounds its input to bf16 once; log_softmax / softmax and the Exp(1) race are fp32.  The depth decoder
+        # starts from bf16 inputs and stays bf16.  The forward pre-hooks below are the "cast to bf16" of autocast's
+        # linear; they are no-ops in the plain mode, where every input is bf16 already.
+        self.autocast_cuda = False
+        for mod in self.modules():
+            if isinstance(mod, nn.Linear):
+                mod.register_forward_pre_hook(lambda m, args: (args[0].to(m.weight.dtype),) + tuple(args[1:]))
 
     # -- sesameai/models.py:120-130
     def setup_caches(self, max_batch_size: int) -> None:
@@ -120,7 +138,8 @@ class OracleCSM(nn.Module):
         aud_idx = tokens[:, :, :-1] + V * torch.arange(C, device=tokens.device)
         aud = self.audio_embeddings(aud_idx.view(-1)).reshape(tokens.size(0), tokens.size(1), C, -1)
         stacked = torch.cat([aud, txt], dim=-2)
-        return (stacked * tokens_mask.unsqueeze(-1)).sum(dim=2)
+        masked = stacked * tokens_mask.unsqueeze(-1)
+        return masked.sum(dim=2, dtype=torch.float32) if self.autocast_cuda else masked.sum(dim=2)
 
     def embed_audio(self, codebook: int, tok: torch.Tensor) -> torch.Tensor:
         return self.audio_embeddings(tok + codebook * self.config.audio_vocab_size)
@@ -147,7 +166,7 @@ class OracleCSM(nn.Module):
         last_h = h[:, -1, :]
 
         def pick(logits: torch.Tensor, i: int) -> torch.Tensor:
-            s = oracle_sample_topk(logits, topk, temperature, None if noise is None else noise[i])
+            s = oracle_sample_topk(logits, topk, temperature, None if noise is None else noise[i], self.autocast_cuda)
             if record is not None:
                 record.setdefault("logits", []).append(logits.detach().clone())
                 record.setdefault("sampled", []).append(s.detach().clone())

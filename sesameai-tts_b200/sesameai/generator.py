@@ -210,12 +210,14 @@ def _save_wav(filename, audio: torch.Tensor, sample_rate: int) -> None:
         f.writeframes(pcm.t().contiguous().numpy().tobytes())
 
 
-def load_csm_1b(device: str = "cuda") -> Generator:
-    """Reference ``load_csm_1b`` (``generator.py:330-346``) minus the cuDNN / torch.compile knobs, which
-    have no counterpart here: weights from the hub, bf16 on ``device``, caches for batch 1."""
-    model = Model.from_pretrained("sesame/csm-1b")
+def load_csm_1b(device: str = "cuda", *, model_path: str = "sesame/csm-1b", text_tokenizer=None,
+                audio_tokenizer: Optional[MimiCodec] = None) -> Generator:
+    """Reference ``load_csm_1b(device)`` (``generator.py:330-346``) minus the cuDNN / torch.compile knobs, which
+    have no counterpart here: weights through ``Model.from_pretrained`` (the hub repo, or -- keyword extras for
+    offline use -- a local directory written by ``save_pretrained``), bf16 on ``device``, caches for batch 1."""
+    model = Model.from_pretrained(model_path)
     model.to(device=device, dtype=torch.bfloat16)
-    return Generator(model)
+    return Generator(model, text_tokenizer=text_tokenizer, audio_tokenizer=audio_tokenizer)
 
 
 def generate_streaming_audio(generator: Generator, text: str, speaker: int, context: List[Segment], output_file: str,

@@ -105,6 +105,65 @@ def test_reference_service_loop_runs_unchanged(rig):
     assert audio.shape == (5 * 1920,) and torch.isfinite(audio).all()
 
 
+def test_service_loop_values_against_the_autocast_oracle(rig):
+    """VALUES of the tts_service loop: the reference runs it under autocast (oracle mode ii: fp32 backbone residual
+    stream, fp32 sampling); the kernels implement the plain mode (i) whatever the autocast state.  Teacher-forced
+    logits of the product, called inside torch.autocast like tts_service.py:192-241, against the mode-(ii) oracle:
+    the distance is the one between the two reference modes themselves (~1 bf16 ulp), measured and bounded here."""
+    from helpers import assert_logits_close, next_inputs
+
+    spec = dict(model_args=dict(backbone_flavor="tiny-bb", decoder_flavor="tiny-dec", text_vocab_size=1000,
+                                audio_vocab_size=2051, audio_num_codebooks=32), weight_seed=5, planted=False, batch=1)
+    om, _ = build_oracle(spec)
+    pm, _ = build_product(spec)
+    tok, msk, pos = syn.voice_prompt(1, 1, 4, 6, 3, seed=2, text_vocab=1000)
+    noise = syn.exp_noise(32 * 3, 1, 2051, 3)
+    om.autocast_cuda = True
+    om.reset_caches(), pm.reset_caches()
+    tc, mc, pc = tok.cuda(), msk.cuda(), pos.cuda()
+    with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
+        for f in range(3):
+            rec = {}
+            s = om.generate_frame(tok, msk, pos, 0.9, 50, noise=noise[32 * f: 32 * f + 32], record=rec)
+            lg = torch.zeros(32, 1, 2051, dtype=torch.bfloat16, device="cuda")
+            sp = pm.generate_frame(tc, mc, pc, 0.9, 50, noise=noise[32 * f: 32 * f + 32].cuda(), forced=s, logits_out=lg)
+            assert torch.equal(sp.cpu(), s)
+            assert_logits_close(lg.cpu(), torch.stack(rec["logits"]), f"service loop vs autocast oracle, frame {f}", worst=4e-2, ulps=2.0)
+            tok, msk, pos = next_inputs(s, pos)
+            tc, mc, pc = next_inputs(sp, pc)
+    om.autocast_cuda = False
+
+
+def test_generate_stream_equals_generate(rig):
+    """Stateful streaming: the chunks of generate_stream concatenated are bit-identical to generate()'s audio."""
+    _, _, gen = rig
+    codec = gen._audio_tokenizer
+
+    class Folded:  # planted tokens reach 2050; Mimi codebooks hold 2048 entries: fold like the other tests do
+        sample_rate = codec.sample_rate
+
+        def set_num_codebooks(self, n):
+            pass
+
+        def decode(self, codes):
+            return codec.decode(codes % 2048)
+
+        def streaming(self):
+            st = codec.streaming()
+            real = st.decode
+            st.decode = lambda codes: real(codes % 2048)
+            return st
+
+    gen._audio_tokenizer = Folded()
+    try:
+        chunks = list(gen.generate_stream("stream me", 0, [], max_audio_length_ms=27 * 80, temperature=1.0, topk=1))
+        whole = gen.generate("stream me", 0, [], max_audio_length_ms=27 * 80, temperature=1.0, topk=1)
+    finally:
+        gen._audio_tokenizer = codec
+    assert [c.shape[0] for c in chunks] == [19200, 19200, 7 * 1920]
+    assert torch.equal(torch.cat(chunks), whole)
+
+
 def test_generate_with_voice_prompt_context(rig):
     """Context segments carry audio: Generator._tokenize_segment runs Mimi encode on the GPU and the
     prompt gets text frames + audio frames + the all-zero EOS frame (reference generator.py:78-109)."""
