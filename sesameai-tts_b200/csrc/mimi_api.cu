@@ -8,6 +8,7 @@
 
 #include "../../include/csm_b200.h"
 #include "mimi_kernels.cuh"
+#include "mimi_tc.cuh"
 
 int csm_set_error(int code, const char* msg);  // api.cu
 void csm_count_launches(unsigned long long n);
@@ -51,6 +52,13 @@ struct mimi_ctx {
   // encode side
   float *enc_res1[4], *enc_down[4], *enc_final, *dsw, *enorm, *wavbuf, *p1, *p2, *dots;
   float* own_state;  // stream state of the one-shot decode (windows of max_frames carry their left context in it)
+  // tensor-core decode path (mimi_tc.cuh): TF32-rounded copies of the matrices used straight from the caller's
+  // tensors, the raw ConvTranspose1d outputs (residual operand) and a rounded copy of the transformer output
+  bool tc;                 // decode on tcgen05 (default) or on the mma.sync kernels (MIMI_DECODE=mma)
+  float* tr_r[8][4];       // in_proj, out_proj, linear1, linear2 per layer
+  float* res2_r[4];        // residual block's 1x1 conv per stage
+  float* u_raw[4];
+  float* xs_r;
 };
 
 // ---- streamed decode state ------------------------------------------------------------------------
@@ -127,6 +135,23 @@ static size_t mimi_carve(mimi_ctx* x, char* base) {
   x->xn = cv.take(L * 512);
   x->qkv = cv.take((L + HIST + 7) * 1536);  // + carried K/V rows of a streamed decode in front
   x->own_state = cv.take(state_layout().total);
+  for (int l = 0; l < 8; ++l) {
+    x->tr_r[l][0] = cv.take(1536 * 512);
+    x->tr_r[l][1] = cv.take(512 * 512);
+    x->tr_r[l][2] = cv.take(2048 * 512);
+    x->tr_r[l][3] = cv.take(512 * 2048);
+  }
+  x->xs_r = cv.take((L + PAD) * 512);
+  {
+    size_t rr = L;
+    int c2 = 1024;
+    for (int s = 0; s < 4; ++s) {
+      rr *= RATIOS[s];
+      x->res2_r[s] = cv.take((size_t)(c2 / 2) * (c2 / 4));
+      x->u_raw[s] = cv.take(rr * (c2 / 2));
+      c2 /= 2;
+    }
+  }
   x->att = cv.take(L * 512);
   x->ff = cv.take(L * 2048);
   x->c0 = cv.take((L + PAD) * 1024);
@@ -178,6 +203,71 @@ static cudaError_t gemm(cudaStream_t st, const float* A, long long lda, const fl
   return cudaGetLastError();
 }
 
+// ---- tcgen05 GEMM launcher (mimi_tc.cuh) ------------------------------------------------------------
+typedef CUresult (*mimi_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static mimi_encode_tiled_fn mimi_encode_tiled() {
+  static mimi_encode_tiled_fn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (mimi_encode_tiled_fn)p;
+  }
+  return fn;
+}
+// C[M, N] = A . B^T (+ epilogue), A row m = the contiguous slice of ``taps`` activation rows of ``cin`` channels
+// starting at A + m * lda (lda == cin for every Mimi conv: overlapping rows, no im2col), B [N, taps * cin] row-major.
+static int gemm_tc(cudaStream_t st, const float* A, long long lda, int cin, int taps, const float* B, long long M, int N,
+                   const mtc::Args& ep) {
+  mimi_encode_tiled_fn enc = mimi_encode_tiled();
+  if (!enc) return csm_set_error(CSM_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
+  const int K = cin * taps;
+  if (cin % mtc::BK || N % 4 || M < 1 || (((uintptr_t)A | (uintptr_t)B) & 15) || (lda * 4) % 16)
+    return csm_set_error(CSM_ERR_ARG, "mimi gemm_tc: unsupported shape");
+  static bool attr[64] = {false};
+  int dev = 0;
+  MCU_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr[dev]) {
+    MCU_TRY(cudaFuncSetAttribute(mtc::k_gemm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mtc::SMEM_BYTES));
+    if (dev >= 0 && dev < 64) attr[dev] = true;
+  }
+  CUtensorMap ma, mb;
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)cin, (cuuint64_t)taps, (cuuint64_t)M};
+    cuuint64_t gstr[2] = {(cuuint64_t)lda * 4, (cuuint64_t)lda * 4};
+    cuuint32_t box[3] = {(cuuint32_t)mtc::BK, 1, (cuuint32_t)mtc::BM};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)A, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return csm_set_error(CSM_ERR_CUDA, "cuTensorMapEncodeTiled (A, 3-d) failed");
+  }
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t gstr[1] = {(cuuint64_t)K * 4};
+    cuuint32_t box[2] = {(cuuint32_t)mtc::BK, (cuuint32_t)mtc::BN};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)B, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return csm_set_error(CSM_ERR_CUDA, "cuTensorMapEncodeTiled (B) failed");
+  }
+  mtc::Args a = ep;
+  a.M = (int)M; a.N = N; a.K = K;
+  if (a.bias_period < 1) a.bias_period = 1;
+  dim3 grid((N + mtc::BN - 1) / mtc::BN, (unsigned)((M + mtc::BM - 1) / mtc::BM));
+  mtc::k_gemm_tf32<<<grid, mtc::THREADS, mtc::SMEM_BYTES, st>>>(ma, mb, a, cin);
+  csm_count_launches(1);
+  MCU_TRY(cudaGetLastError());
+  return CSM_OK;
+}
+static mtc::Args ep_plain(float* C, long long ldc, int flags = 0, const float* bias = nullptr, int period = 1) {
+  mtc::Args e;
+  memset(&e, 0, sizeof(e));
+  e.C = C; e.ldc = ldc; e.flags = flags; e.bias = bias; e.bias_period = period;
+  return e;
+}
+
 extern "C" int32_t mimi_create(const void* const* weights, int32_t n_weights, int32_t max_frames, void* workspace,
                                size_t workspace_bytes, void* stream, mimi_ctx** out) {
   if (!out) return csm_set_error(CSM_ERR_ARG, "out is null");
@@ -218,6 +308,32 @@ extern "C" int32_t mimi_create(const void* const* weights, int32_t n_weights, in
   }
   mimi::k_pack_conv<<<1, 256, 0, st>>>(x->w[MIMI_W_FINAL], 1, 64, 3, x->finalw);
   {
+    // TF32 (round-to-nearest) copies / in-place rounding of every matrix a decode GEMM reads: the mma.sync path
+    // rounds operands when it loads fragments, the tcgen05 path truncates -- on rounded values both see the same bits
+    const char* mode = getenv("MIMI_DECODE");
+    x->tc = !(mode && !strcmp(mode, "mma"));
+    auto round_to = [&](const float* src, float* dst, long long n) {
+      mimi::k_round_copy<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n);
+      csm_count_launches(1);
+    };
+    for (int l = 0; l < 8; ++l) {
+      const float* const* lw = &x->w[MIMI_W_LAYER0 + 10 * l];
+      round_to(lw[0], x->tr_r[l][0], 1536LL * 512);
+      round_to(lw[1], x->tr_r[l][1], 512LL * 512);
+      round_to(lw[6], x->tr_r[l][2], 2048LL * 512);
+      round_to(lw[7], x->tr_r[l][3], 512LL * 2048);
+    }
+    round_to(x->wproj, x->wproj, 512LL * 512);
+    round_to(x->conv0, x->conv0, 1024LL * 7 * 512);
+    int c2 = 1024;
+    for (int s = 0; s < 4; ++s) {
+      round_to(x->convtr[s], x->convtr[s], (long long)RATIOS[s] * (c2 / 2) * 2 * c2);
+      round_to(x->res1[s], x->res1[s], (long long)(c2 / 4) * 3 * (c2 / 2));
+      round_to(x->w[MIMI_W_STAGE0 + 6 * s + 4], x->res2_r[s], (long long)(c2 / 2) * (c2 / 4));
+      c2 /= 2;
+    }
+  }
+  {
     int ech = 64;
     const int eratio[4] = {4, 5, 6, 8};
     for (int s = 0; s < 4; ++s) {
@@ -253,12 +369,35 @@ static void copy_rows(cudaStream_t st, const float* src, long long lds, float* d
 // ``kv`` (streamed decode, else null): per-layer history of the hist = min(pos0, 249) positions before this chunk
 // (pos0 = absolute position of row 0); it is read into the rows in front of the chunk's q/k/v and updated.
 static int mimi_transformer(mimi_ctx* x, float* xs, long long L, int w_layer0, cudaStream_t st, float* const* kv = nullptr,
-                            long long pos0 = 0) {
+                            long long pos0 = 0, bool tc = false) {
   using namespace mimi;
   const int hist = kv ? (int)(pos0 < HIST ? pos0 : HIST) : 0;
   float* qkv = x->qkv + (size_t)hist * 1536;  // rows of this chunk
   for (int l = 0; l < 8; ++l) {
     const float* const* lw = &x->w[w_layer0 + 10 * l];
+    if (tc) {
+      // the same layer on the tcgen05 GEMM: operands rounded to TF32 where they are produced
+      int rc;
+      k_layernorm512<<<(unsigned)((L + 7) / 8), 256, 0, st>>>(xs, lw[2], lw[3], (int)L, 1e-5f, x->xn, 1);
+      if ((rc = gemm_tc(st, x->xn, 512, 512, 1, x->tr_r[l][0], L, 1536, ep_plain(qkv, 1536))) != CSM_OK) return rc;
+      k_rope_qk<<<(unsigned)((L * 512 + 255) / 256), 256, 0, st>>>(qkv, (int)L, kv ? pos0 : 0);
+      if (kv) copy_rows(st, kv[l], 1024, x->qkv + 512, 1536, hist, 1024);
+      k_attn_window<<<dim3((unsigned)((L + 3) / 4), 8), 128, 0, st>>>(x->qkv, (int)L, 250, x->att, hist, 1);
+      if (kv) {
+        const long long keep = hist + L < HIST ? hist + L : HIST;
+        copy_rows(st, x->qkv + (size_t)(hist + L - keep) * 1536 + 512, 1536, kv[l], 1024, keep, 1024);
+      }
+      mtc::Args e1 = ep_plain(xs, 512, mtc::F_LAYERSCALE | mtc::F_RESID);
+      e1.R = xs; e1.ldr = 512; e1.scale = lw[8];
+      if ((rc = gemm_tc(st, x->att, 512, 512, 1, x->tr_r[l][1], L, 512, e1)) != CSM_OK) return rc;
+      k_layernorm512<<<(unsigned)((L + 7) / 8), 256, 0, st>>>(xs, lw[4], lw[5], (int)L, 1e-5f, x->xn, 1);
+      if ((rc = gemm_tc(st, x->xn, 512, 512, 1, x->tr_r[l][2], L, 2048, ep_plain(x->ff, 2048, mtc::F_GELU | mtc::F_ROUND))) != CSM_OK) return rc;
+      mtc::Args e2 = ep_plain(xs, 512, mtc::F_LAYERSCALE | mtc::F_RESID);
+      e2.R = xs; e2.ldr = 512; e2.scale = lw[9];
+      if ((rc = gemm_tc(st, x->ff, 2048, 2048, 1, x->tr_r[l][3], L, 512, e2)) != CSM_OK) return rc;
+      csm_count_launches(4);
+      continue;
+    }
     k_layernorm512<<<(unsigned)((L + 7) / 8), 256, 0, st>>>(xs, lw[2], lw[3], (int)L, 1e-5f, x->xn);
     MCU_TRY(gemm(st, x->xn, 512, lw[0], qkv, 1536, L, 1536, 512, nullptr, 0, 0));
     k_rope_qk<<<(unsigned)((L * 512 + 255) / 256), 256, 0, st>>>(qkv, (int)L, kv ? pos0 : 0);
@@ -371,8 +510,12 @@ extern "C" int32_t mimi_k_rvq_encode(mimi_ctx* x, const float* latent, int32_t T
 
 // One causal chunk of one utterance: frames [0, T) of ``codes`` ([K, ldt] layout) continue the stream whose
 // left context is ``sbuf`` (``frames_done`` frames so far; an all-zero state = the start of an utterance).
+static int decode_chunk_tc(mimi_ctx* x, float* sbuf, long long frames_done, const int64_t* codes, int K, int T, long long ldt,
+                           float* wav, cudaStream_t st);
+
 static int decode_chunk(mimi_ctx* x, float* sbuf, long long frames_done, const int64_t* codes, int K, int T, long long ldt,
                         float* wav, cudaStream_t st) {
+  if (x->tc) return decode_chunk_tc(x, sbuf, frames_done, codes, K, T, ldt, wav, st);
   using namespace mimi;
   const StateLayout SL = state_layout();
   const long long L = 2LL * T;
@@ -419,6 +562,70 @@ static int decode_chunk(mimi_ctx* x, float* sbuf, long long frames_done, const i
     ch = co;
   }
   k_final_conv<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(in, x->finalw, x->final_bias, rows, wav);
+  csm_count_launches(1);
+  MCU_TRY(cudaGetLastError());
+  return CSM_OK;
+}
+
+// The same chunk on the tensor cores (mimi_tc.cuh).  SEANet activations are stored the way their consumers read
+// them -- ELU applied, rounded to TF32 -- next to the raw ConvTranspose1d output the residual add needs; the
+// carried tails (stream state) hold the same representation, so a stream must not switch paths mid-utterance
+// (the path is a property of the context).
+static int decode_chunk_tc(mimi_ctx* x, float* sbuf, long long frames_done, const int64_t* codes, int K, int T, long long ldt,
+                           float* wav, cudaStream_t st) {
+  using namespace mimi;
+  const StateLayout SL = state_layout();
+  const long long L = 2LL * T;
+  int rc;
+  k_rvq_gather<<<T, 256, 0, st>>>(codes, K, T, ldt, x->emb, x->q512, 1);
+  if ((rc = gemm_tc(st, x->q512, 512, 512, 1, x->wproj, T, 512, ep_plain(x->e, 512))) != CSM_OK) return rc;
+  float* xs = x->xs + (size_t)PAD * 512;
+  k_upsample2<<<(unsigned)((L * 512 + 255) / 256), 256, 0, st>>>(x->e, x->w[MIMI_W_UPSAMPLE], T, 512, xs, sbuf + SL.e_prev);
+  copy_rows(st, x->e + (size_t)(T - 1) * 512, 512, sbuf + SL.e_prev, 512, 1, 512);
+  csm_count_launches(2);
+  {
+    float* kv[8];
+    for (int l = 0; l < 8; ++l) kv[l] = sbuf + SL.kv[l];
+    if ((rc = mimi_transformer(x, xs, L, MIMI_W_LAYER0, st, kv, 2 * frames_done, true)) != CSM_OK) return rc;
+  }
+  // conv0 reads a TF32-rounded copy of the transformer output (the residual stream itself stays fp32)
+  float* xr = x->xs_r + (size_t)PAD * 512;
+  mtc::k_round_tf32<<<(unsigned)((L * 512 + 255) / 256), 256, 0, st>>>(xs, xr, L * 512);
+  csm_count_launches(1);
+  copy_rows(st, sbuf + SL.xs_tail, 512, xr - 6 * 512, 512, 6, 512);
+  copy_rows(st, xr + (L - 6) * 512, 512, sbuf + SL.xs_tail, 512, 6, 512);
+  float* c0 = x->c0 + (size_t)PAD * 1024;  // holds ELU(conv0(..))
+  if ((rc = gemm_tc(st, xr - 6 * 512, 512, 512, 7, x->conv0, L, 1024, ep_plain(c0, 1024, mtc::F_OUT_ELU, x->w[MIMI_W_CONV0 + 1], 1024))) != CSM_OK)
+    return rc;
+  copy_rows(st, sbuf + SL.c0_tail, 1024, c0 - 1024, 1024, 1, 1024);
+  copy_rows(st, c0 + (L - 1) * 1024, 1024, sbuf + SL.c0_tail, 1024, 1, 1024);
+  const float* in = c0;
+  long long rows = L;
+  int ch = 1024;
+  for (int s = 0; s < 4; ++s) {
+    const float* const* sw = &x->w[MIMI_W_STAGE0 + 6 * s];
+    const int r = RATIOS[s], co = ch / 2, hid = ch / 4;
+    float* ue = x->u[s] + (size_t)PAD * co;  // ELU'd, rounded: what the convs read
+    float* ur = x->u_raw[s];                 // raw ConvTranspose1d output: the residual operand
+    // ConvTranspose1d(ch -> ch/2, kernel 2r, stride r) on the ELU'd input: rows x[q-1], x[q]
+    mtc::Args ec = ep_plain(ur, (long long)r * co, 0, sw[1], co);
+    ec.C2 = ue; ec.ldc2 = (long long)r * co;
+    if ((rc = gemm_tc(st, in - ch, ch, ch, 2, x->convtr[s], rows, r * co, ec)) != CSM_OK) return rc;
+    rows *= r;
+    copy_rows(st, sbuf + SL.pre[s], co, ue - 2 * co, co, 2, co);
+    copy_rows(st, ue + (rows - 2) * co, co, sbuf + SL.pre[s], co, 2, co);
+    // residual block: u + conv1(ELU(conv3(ELU(u)))), stored as ELU(..) for what follows
+    if ((rc = gemm_tc(st, ue - 2 * co, co, co, 3, x->res1[s], rows, hid, ep_plain(x->r[s], hid, mtc::F_OUT_ELU, sw[3], hid))) != CSM_OK) return rc;
+    mtc::Args er = ep_plain(ue, co, mtc::F_OUT_ELU | mtc::F_RESID, sw[5], co);
+    er.R = ur; er.ldr = co;
+    if ((rc = gemm_tc(st, x->r[s], hid, hid, 1, x->res2_r[s], rows, co, er)) != CSM_OK) return rc;
+    const int np = s == 3 ? 2 : 1;
+    copy_rows(st, sbuf + SL.post[s], co, ue - (size_t)np * co, co, np, co);
+    copy_rows(st, ue + (rows - np) * co, co, sbuf + SL.post[s], co, np, co);
+    in = ue;
+    ch = co;
+  }
+  k_final_conv<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(in, x->finalw, x->final_bias, rows, wav, 1);
   csm_count_launches(1);
   MCU_TRY(cudaGetLastError());
   return CSM_OK;

@@ -33,6 +33,14 @@ struct GemmArgs {
 };
 
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+// round-to-nearest to TF32 (10-bit mantissa): the tensor-core decode path (mimi_tc.cuh) rounds every GEMM operand
+// where it is produced, so that tcgen05's truncation of the low mantissa bits changes nothing
+__device__ __forceinline__ float rtf32(float x, int on) {
+  if (!on) return x;
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 constexpr int BM = 64, BN = 64, BK = 16;
@@ -227,7 +235,8 @@ __global__ void __launch_bounds__(256) k_tgemm(GemmArgs g) {
 // split-RVQ lookup: q[t] = [ sum over semantic codebooks | sum over acoustic codebooks ]  (2 x 256)
 // embedding = embedding_sum / clamp(cluster_usage, 1e-5) is precomputed at create time.
 __global__ void k_rvq_gather(const int64_t* __restrict__ codes /*[K, ldt] of this utterance, frames [0, T) of it*/, int K, int T,
-                             long long ldt, const float* __restrict__ emb /*[32][2048][256]*/, float* __restrict__ out /*[T, 512]*/) {
+                             long long ldt, const float* __restrict__ emb /*[32][2048][256]*/, float* __restrict__ out /*[T, 512]*/,
+                             int round = 0) {
   const int t = blockIdx.x;
   const int d = threadIdx.x;  // 256 threads
   float first = 0.f, rest = 0.f;
@@ -238,8 +247,8 @@ __global__ void k_rvq_gather(const int64_t* __restrict__ codes /*[K, ldt] of thi
     if (k == 0) first += v;
     else rest += v;
   }
-  out[(long long)t * 512 + d] = first;
-  out[(long long)t * 512 + 256 + d] = rest;
+  out[(long long)t * 512 + d] = rtf32(first, round);
+  out[(long long)t * 512 + 256 + d] = rtf32(rest, round);
 }
 
 // depthwise ConvTranspose1d(k=4, s=2, groups=C), causal (trim 2 on the right):
@@ -269,7 +278,7 @@ __global__ void k_copy_rows(const float* __restrict__ src, long long lds, float*
 // LayerNorm over 512 channels, one warp per row
 __global__ void __launch_bounds__(256) k_layernorm512(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ b, int rows, float eps,
-                                                      float* __restrict__ y) {
+                                                      float* __restrict__ y, int round = 0) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -299,10 +308,10 @@ __global__ void __launch_bounds__(256) k_layernorm512(const float* __restrict__ 
     const float4 ww = reinterpret_cast<const float4*>(w)[lane + 32 * i];
     const float4 bb = reinterpret_cast<const float4*>(b)[lane + 32 * i];
     float4 o;
-    o.x = (v[i].x - mean) * inv * ww.x + bb.x;
-    o.y = (v[i].y - mean) * inv * ww.y + bb.y;
-    o.z = (v[i].z - mean) * inv * ww.z + bb.z;
-    o.w = (v[i].w - mean) * inv * ww.w + bb.w;
+    o.x = rtf32((v[i].x - mean) * inv * ww.x + bb.x, round);
+    o.y = rtf32((v[i].y - mean) * inv * ww.y + bb.y, round);
+    o.z = rtf32((v[i].z - mean) * inv * ww.z + bb.z, round);
+    o.w = rtf32((v[i].w - mean) * inv * ww.w + bb.w, round);
     yr[lane + 32 * i] = o;
   }
 }
@@ -329,7 +338,7 @@ __global__ void k_rope_qk(float* __restrict__ qkv, int L, long long pos0) {
 // Queries are rows [hist, hist + L) of ``qkv``; rows [0, hist) hold the carried K/V of the positions before
 // this chunk (streamed decode), so row index differences are position differences.  out row = t - hist.
 __global__ void __launch_bounds__(128) k_attn_window(const float* __restrict__ qkv, int L, int context,
-                                                     float* __restrict__ out, int hist) {
+                                                     float* __restrict__ out, int hist, int round = 0) {
   const int tq = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int h = blockIdx.y;
   const int lane = threadIdx.x & 31;
@@ -383,12 +392,13 @@ __global__ void __launch_bounds__(128) k_attn_window(const float* __restrict__ q
     m = mn;
   }
   const float inv = 1.0f / l;
-  *reinterpret_cast<float2*>(out + (long long)tq * 512 + h * 64 + lane * 2) = make_float2(o0 * inv, o1 * inv);
+  *reinterpret_cast<float2*>(out + (long long)tq * 512 + h * 64 + lane * 2) = make_float2(rtf32(o0 * inv, round), rtf32(o1 * inv, round));
 }
 
 // final causal conv 64 -> 1, k = 3, with the ELU on its input: one thread per output sample
+// pre_elu: x already holds ELU(u) (the tensor-core path stores activations that way)
 __global__ void k_final_conv(const float* __restrict__ x /*[L, 64], 2 zero pad rows in front*/, const float* __restrict__ w
-                             /*[3][64] tap-major*/, float bias, long long L, float* __restrict__ y) {
+                             /*[3][64] tap-major*/, float bias, long long L, float* __restrict__ y, int pre_elu = 0) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= L) return;
   const float4* xp = reinterpret_cast<const float4*>(x + (t - 2) * 64);
@@ -397,8 +407,13 @@ __global__ void k_final_conv(const float* __restrict__ x /*[L, 64], 2 zero pad r
 #pragma unroll 8
   for (int i = 0; i < 48; ++i) {
     const float4 v = xp[i], ww = wp[i];
-    a = fmaf(elu1(v.x), ww.x, a); a = fmaf(elu1(v.y), ww.y, a);
-    a = fmaf(elu1(v.z), ww.z, a); a = fmaf(elu1(v.w), ww.w, a);
+    if (pre_elu) {
+      a = fmaf(v.x, ww.x, a); a = fmaf(v.y, ww.y, a);
+      a = fmaf(v.z, ww.z, a); a = fmaf(v.w, ww.w, a);
+    } else {
+      a = fmaf(elu1(v.x), ww.x, a); a = fmaf(elu1(v.y), ww.y, a);
+      a = fmaf(elu1(v.z), ww.z, a); a = fmaf(elu1(v.w), ww.w, a);
+    }
   }
   y[t] = a;
 }
@@ -490,6 +505,10 @@ __global__ void k_pack_embedding(const float* __restrict__ esum, const float* __
   out[i] = esum[i] / fmaxf(usage[i >> 8], 1e-5f);
 }
 // Conv1d weight [Cout][Cin][k] -> [Cout][k][Cin]
+__global__ void k_round_copy(const float* w, float* out, long long n) {  // (in place when out == w)
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = rtf32(w[i], 1);
+}
 __global__ void k_pack_conv(const float* __restrict__ w, int Cout, int Cin, int k, float* __restrict__ out) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= (long long)Cout * Cin * k) return;
