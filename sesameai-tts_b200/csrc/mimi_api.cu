@@ -231,6 +231,8 @@ static int gemm_tc(cudaStream_t st, const float* A, long long lda, int cin, int 
   MCU_TRY(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64 || !attr[dev]) {
     MCU_TRY(cudaFuncSetAttribute(mtc::k_gemm_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mtc::SMEM_BYTES));
+    MCU_TRY(cudaFuncSetAttribute(mimi::k_attn_window_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(3 * 64 * mimi::AT_LD * sizeof(float))));
     if (dev >= 0 && dev < 64) attr[dev] = true;
   }
   CUtensorMap ma, mb;
@@ -382,7 +384,11 @@ static int mimi_transformer(mimi_ctx* x, float* xs, long long L, int w_layer0, c
       if ((rc = gemm_tc(st, x->xn, 512, 512, 1, x->tr_r[l][0], L, 1536, ep_plain(qkv, 1536))) != CSM_OK) return rc;
       k_rope_qk<<<(unsigned)((L * 512 + 255) / 256), 256, 0, st>>>(qkv, (int)L, kv ? pos0 : 0);
       if (kv) copy_rows(st, kv[l], 1024, x->qkv + 512, 1536, hist, 1024);
-      k_attn_window<<<dim3((unsigned)((L + 3) / 4), 8), 128, 0, st>>>(x->qkv, (int)L, 250, x->att, hist, 1);
+      {
+        const size_t at_smem = (size_t)3 * 64 * mimi::AT_LD * sizeof(float);
+        k_attn_window_tc<<<dim3((unsigned)((L + 63) / 64), 8), 128, at_smem, st>>>(x->qkv, (int)L, 250, x->att, hist,
+                                                                                  (kv ? pos0 : 0) - hist, 1);
+      }
       if (kv) {
         const long long keep = hist + L < HIST ? hist + L : HIST;
         copy_rows(st, x->qkv + (size_t)(hist + L - keep) * 1536 + 512, 1536, kv[l], 1024, keep, 1024);

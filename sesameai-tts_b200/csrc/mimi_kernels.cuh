@@ -395,6 +395,151 @@ __global__ void __launch_bounds__(128) k_attn_window(const float* __restrict__ q
   *reinterpret_cast<float2*>(out + (long long)tq * 512 + h * 64 + lane * 2) = make_float2(rtf32(o0 * inv, round), rtf32(o1 * inv, round));
 }
 
+// ---- windowed causal attention on the tensor cores (TF32 mma.sync, fp32 accumulate) -------------------------
+// One CTA = 64 consecutive queries of one head, 4 warps x 16 query rows; key tiles of 64 rows are staged in shared
+// memory.  Key tiles are aligned to ABSOLUTE positions (tile = absolute key position / 64; ``abs0`` = absolute
+// position of buffer row 0), and every row folds the tiles it can see in ascending order with the online-softmax
+// rule, so a row's result does not depend on which rows share its CTA or on where a streamed chunk starts: the
+// chunked decode stays bit-identical to the one-shot decode.  S = Q K^T: m16n8k8, A = Q rows, B = K rows; the
+// probabilities come out of the accumulator in exactly the A-fragment slots of the second product when its k
+// slots are numbered (q, q+4) <-> keys (2q, 2q+1) of an 8-key group -- V's fragments use the same numbering.
+constexpr int AT_LD = 68;  // padded row (floats) of the 64 x 64 tiles: conflict-free fragment loads
+__device__ __forceinline__ uint32_t tf32u(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__global__ void __launch_bounds__(128) k_attn_window_tc(const float* __restrict__ qkv, int L, int context, float* __restrict__ out,
+                                                        int hist, long long abs0, int round) {
+  extern __shared__ __align__(16) float at_smem[];
+  float* Qs = at_smem;                 // [64][AT_LD]
+  float* Ks = Qs + 64 * AT_LD;
+  float* Vs = Ks + 64 * AT_LD;
+  const int h = blockIdx.y, tq0 = blockIdx.x * 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+  const int nq = min(64, L - tq0);
+  // buffer rows: queries at hist + tq0 + i; a query at buffer row t sees keys [max(t - context + 1, 0), t]
+  const int t_first = hist + tq0, t_last = t_first + nq - 1;
+  const int key_lo = max(t_first - context + 1, 0);
+  for (int u = tid; u < 64 * 16; u += 128) {
+    const int r = u >> 4, c4 = (u & 15) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < nq) v = *reinterpret_cast<const float4*>(qkv + (long long)(t_first + r) * 1536 + h * 64 + c4);
+    *reinterpret_cast<float4*>(Qs + r * AT_LD + c4) = v;
+  }
+  __syncthreads();
+  uint32_t qa[8][4];  // A fragments of this warp's 16 rows, 8 k-steps of 8 dims
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    const float* qp = Qs + (warp * 16 + g) * AT_LD + kk * 8 + q;
+    qa[kk][0] = tf32u(qp[0]);
+    qa[kk][1] = tf32u(qp[8 * AT_LD]);
+    qa[kk][2] = tf32u(qp[4]);
+    qa[kk][3] = tf32u(qp[8 * AT_LD + 4]);
+  }
+  const int t_lo = t_first + warp * 16 + g, t_hi = t_lo + 8;  // buffer rows of this lane's two query rows
+  float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+  float o[8][4];
+#pragma unroll
+  for (int d = 0; d < 8; ++d)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[d][e] = 0.f;
+  const float sl2 = 0.125f * 1.4426950408889634f;  // 1/sqrt(64), scores in log2 units
+  // absolute-aligned key tiles that intersect [key_lo, t_last]
+  const long long kt_lo = (abs0 + key_lo) >> 6, kt_hi = (abs0 + t_last) >> 6;
+  for (long long kt = kt_lo; kt <= kt_hi; ++kt) {
+    const long long row0 = kt * 64 - abs0;  // buffer row of the tile's first key (may be negative)
+    __syncthreads();                        // the previous tile has been consumed
+    for (int u = tid; u < 64 * 16; u += 128) {
+      const int r = u >> 4, c4 = (u & 15) * 4;
+      const long long key = row0 + r;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (key >= key_lo && key <= t_last) {
+        kv = *reinterpret_cast<const float4*>(qkv + key * 1536 + 512 + h * 64 + c4);
+        vv = *reinterpret_cast<const float4*>(qkv + key * 1536 + 1024 + h * 64 + c4);
+      }
+      *reinterpret_cast<float4*>(Ks + r * AT_LD + c4) = kv;
+      *reinterpret_cast<float4*>(Vs + r * AT_LD + c4) = vv;
+    }
+    __syncthreads();
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[j][e] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) {
+        const float* kp = Ks + (j * 8 + g) * AT_LD + kk * 8 + q;
+        const uint32_t b[2] = {tf32u(kp[0]), tf32u(kp[4])};
+        mma_tf32(s[j], qa[kk], b);
+      }
+    }
+    // window mask, running max
+    float mx_lo = m_lo, mx_hi = m_hi;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const long long key = row0 + j * 8 + 2 * q + e;
+        const bool ok_lo = key <= t_lo && key > (long long)t_lo - context && key >= 0 && t_lo <= t_last;
+        const bool ok_hi = key <= t_hi && key > (long long)t_hi - context && key >= 0 && t_hi <= t_last;
+        s[j][e] = ok_lo ? s[j][e] * sl2 : -INFINITY;
+        s[j][2 + e] = ok_hi ? s[j][2 + e] * sl2 : -INFINITY;
+        mx_lo = fmaxf(mx_lo, s[j][e]);
+        mx_hi = fmaxf(mx_hi, s[j][2 + e]);
+      }
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+    // a row that has not seen a key yet keeps max = -inf: its probabilities of this tile are all 0
+    const float c_lo = mx_lo == -INFINITY ? 1.f : exp2f(m_lo - mx_lo), c_hi = mx_hi == -INFINITY ? 1.f : exp2f(m_hi - mx_hi);
+    m_lo = mx_lo;
+    m_hi = mx_hi;
+    float ps_lo = 0.f, ps_hi = 0.f;
+    uint32_t pa[8][4];  // P as A fragments of the 8-key groups: (a0,a1,a2,a3) = (c0,c2,c1,c3)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = m_lo == -INFINITY ? 0.f : exp2f(s[j][0] - m_lo), p1 = m_lo == -INFINITY ? 0.f : exp2f(s[j][1] - m_lo);
+      const float p2 = m_hi == -INFINITY ? 0.f : exp2f(s[j][2] - m_hi), p3 = m_hi == -INFINITY ? 0.f : exp2f(s[j][3] - m_hi);
+      ps_lo += p0 + p1;
+      ps_hi += p2 + p3;
+      pa[j][0] = tf32u(p0); pa[j][1] = tf32u(p2); pa[j][2] = tf32u(p1); pa[j][3] = tf32u(p3);
+    }
+    l_lo = l_lo * c_lo + ps_lo;
+    l_hi = l_hi * c_hi + ps_hi;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      o[d][0] *= c_lo; o[d][1] *= c_lo;
+      o[d][2] *= c_hi; o[d][3] *= c_hi;
+    }
+    // O += P V: k slots (q, q+4) of key group j are keys (8j + 2q, 8j + 2q + 1)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        const float* vp = Vs + (j * 8 + 2 * q) * AT_LD + d * 8 + g;
+        const uint32_t b[2] = {tf32u(vp[0]), tf32u(vp[AT_LD])};
+        mma_tf32(o[d], pa[j], b);
+      }
+  }
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+  const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;
+  const int r_lo = warp * 16 + g, r_hi = r_lo + 8;
+#pragma unroll
+  for (int d = 0; d < 8; ++d) {
+    if (r_lo < nq)
+      *reinterpret_cast<float2*>(out + (long long)(tq0 + r_lo) * 512 + h * 64 + d * 8 + 2 * q) =
+          make_float2(rtf32(o[d][0] * i_lo, round), rtf32(o[d][1] * i_lo, round));
+    if (r_hi < nq)
+      *reinterpret_cast<float2*>(out + (long long)(tq0 + r_hi) * 512 + h * 64 + d * 8 + 2 * q) =
+          make_float2(rtf32(o[d][2] * i_hi, round), rtf32(o[d][3] * i_hi, round));
+  }
+}
+
 // final causal conv 64 -> 1, k = 3, with the ELU on its input: one thread per output sample
 // pre_elu: x already holds ELU(u) (the tensor-core path stores activations that way)
 __global__ void k_final_conv(const float* __restrict__ x /*[L, 64], 2 zero pad rows in front*/, const float* __restrict__ w

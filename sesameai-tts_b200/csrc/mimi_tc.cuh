@@ -181,12 +181,17 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
       umma_commit(acc_full);
     }
   } else {
-    // epilogue: warp w may touch TMEM lanes [32*(w%4), +32) -> output rows m0 + that range
+    // epilogue, two steps.  (1) warp w may touch TMEM lanes [32*(w%4), +32): each lane drains ITS row of the
+    // accumulator into a shared-memory tile (the pipeline stages are free by now).  (2) the four warps walk the
+    // tile in row-major order, four consecutive columns per lane: bias / GELU / LayerScale / residual and the
+    // stores are COALESCED -- with one row per lane a 32- or 64-column output (the SEANet tail) made every store
+    // instruction touch 32 different lines and the epilogue, not HBM, bounded those GEMMs.
     const int q = warp & 3;
-    const long long row = m0 + q * 32 + lane;
     mbar_wait(acc_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int nvalid = a.N - n0 < BN ? a.N - n0 : BN;
+    const int nvalid = a.N - n0 < BN ? a.N - n0 : BN;  // a multiple of 4 (launcher)
+    float* tile = reinterpret_cast<float*>(smem);      // [BM][TLD]
+    constexpr int TLD = BN + 4;
 #pragma unroll 1
     for (int c0 = 0; c0 < nvalid; c0 += 32) {
       uint32_t v[32];
@@ -200,38 +205,44 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
             "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < a.M) {
-        const int n = n0 + c0;
+      float* trow = tile + (size_t)(q * 32 + lane) * TLD + c0;
 #pragma unroll
-        for (int j4 = 0; j4 < 32; j4 += 4) {
-          if (n + j4 >= a.N) break;  // N is a multiple of 4 for every Mimi shape (checked by the launcher)
-          float y[4], e[4];
+      for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(trow + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    }
+    asm volatile("bar.sync 2, 128;" ::: "memory");  // the four epilogue warps
+    const int et = threadIdx.x - 64;                 // 0 .. 127
+    const int c4n = nvalid >> 2;                     // float4 columns per row
+    const int mrows = a.M - m0 < BM ? (int)(a.M - m0) : BM;
+#pragma unroll 1
+    for (int i = et; i < mrows * c4n; i += 128) {
+      const int r = i / c4n, c = (i - r * c4n) * 4;
+      const long long row = m0 + r;
+      const int n = n0 + c;
+      const float4 t = *reinterpret_cast<const float4*>(tile + (size_t)r * TLD + c);
+      float y[4] = {t.x, t.y, t.z, t.w}, e[4];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            const int nn = n + j4 + t;
-            float x = __uint_as_float(v[j4 + t]);
-            if (a.bias) x += a.bias[nn % a.bias_period];
-            if (a.flags & F_GELU) x = gelu_f(x);
-            if (a.flags & F_LAYERSCALE) x *= a.scale[nn];
-            y[t] = x;
-          }
-          if (a.flags & F_RESID) {
-            const float4 r = *reinterpret_cast<const float4*>(a.R + row * a.ldr + n + j4);
-            y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
-          }
-          if (a.C2 || (a.flags & F_OUT_ELU)) {
+      for (int k = 0; k < 4; ++k) {
+        float x = y[k];
+        if (a.bias) x += a.bias[(n + k) % a.bias_period];
+        if (a.flags & F_GELU) x = gelu_f(x);
+        if (a.flags & F_LAYERSCALE) x *= a.scale[n + k];
+        y[k] = x;
+      }
+      if (a.flags & F_RESID) {
+        const float4 rr = *reinterpret_cast<const float4*>(a.R + row * a.ldr + n);
+        y[0] += rr.x; y[1] += rr.y; y[2] += rr.z; y[3] += rr.w;
+      }
+      if (a.C2 || (a.flags & F_OUT_ELU)) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t) e[t] = round_tf32(elu_f(y[t]));
-          }
-          if (a.C2) *reinterpret_cast<float4*>(a.C2 + row * a.ldc2 + n + j4) = make_float4(e[0], e[1], e[2], e[3]);
-          if (a.C) {
-            float4 o;
-            if (a.flags & F_OUT_ELU) o = make_float4(e[0], e[1], e[2], e[3]);
-            else if (a.flags & F_ROUND) o = make_float4(round_tf32(y[0]), round_tf32(y[1]), round_tf32(y[2]), round_tf32(y[3]));
-            else o = make_float4(y[0], y[1], y[2], y[3]);
-            *reinterpret_cast<float4*>(a.C + row * a.ldc + n + j4) = o;
-          }
-        }
+        for (int k = 0; k < 4; ++k) e[k] = round_tf32(elu_f(y[k]));
+      }
+      if (a.C2) *reinterpret_cast<float4*>(a.C2 + row * a.ldc2 + n) = make_float4(e[0], e[1], e[2], e[3]);
+      if (a.C) {
+        float4 o;
+        if (a.flags & F_OUT_ELU) o = make_float4(e[0], e[1], e[2], e[3]);
+        else if (a.flags & F_ROUND) o = make_float4(round_tf32(y[0]), round_tf32(y[1]), round_tf32(y[2]), round_tf32(y[3]));
+        else o = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(a.C + row * a.ldc + n) = o;
       }
     }
   }
