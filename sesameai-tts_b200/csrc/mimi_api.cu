@@ -224,7 +224,9 @@ static int gemm_tc(cudaStream_t st, const float* A, long long lda, int cin, int 
   mimi_encode_tiled_fn enc = mimi_encode_tiled();
   if (!enc) return csm_set_error(CSM_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
   const int K = cin * taps;
-  if (cin % mtc::BK || N % 4 || M < 1 || (((uintptr_t)A | (uintptr_t)B) & 15) || (lda * 4) % 16)
+  // output width: whole 128-column tiles, or one tile of 32 / 64 columns (every Mimi shape); bias periods are multiples of 4
+  const bool n_ok = N % 128 == 0 || N == 32 || N == 64;
+  if (cin % mtc::BK || !n_ok || M < 1 || (((uintptr_t)A | (uintptr_t)B) & 15) || (lda * 4) % 16 || (ep.bias && ep.bias_period % 4))
     return csm_set_error(CSM_ERR_ARG, "mimi gemm_tc: unsupported shape");
   static bool attr[64] = {false};
   int dev = 0;
@@ -257,7 +259,11 @@ static int gemm_tc(cudaStream_t st, const float* A, long long lda, int cin, int 
   mtc::Args a = ep;
   a.M = (int)M; a.N = N; a.K = K;
   if (a.bias_period < 1) a.bias_period = 1;
-  dim3 grid((N + mtc::BN - 1) / mtc::BN, (unsigned)((M + mtc::BM - 1) / mtc::BM));
+  static int sms[64] = {0};
+  if (dev >= 0 && dev < 64 && !sms[dev]) MCU_TRY(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
+  const long long tiles = (long long)((N + mtc::BN - 1) / mtc::BN) * ((M + mtc::BM - 1) / mtc::BM);
+  const int nsm = (dev >= 0 && dev < 64 && sms[dev] > 0) ? sms[dev] : 148;
+  const unsigned grid = (unsigned)(tiles < nsm ? tiles : nsm);  // persistent: one CTA per SM walks the tiles
   mtc::k_gemm_tf32<<<grid, mtc::THREADS, mtc::SMEM_BYTES, st>>>(ma, mb, a, cin);
   csm_count_launches(1);
   MCU_TRY(cudaGetLastError());

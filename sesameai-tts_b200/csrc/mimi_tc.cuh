@@ -4,18 +4,19 @@
 // reference sesameai/generator.py:116,299).
 //
 //   warp 0      TMA producer : cp.async.bulk.tensor.3d of a 128 x 32 fp32 A tile and .2d of a 128 x 32 B tile per
-//                              stage (128-byte swizzle) into a 3-deep shared-memory ring.  The A map is THREE
+//                              stage (128-byte swizzle) into a 4-deep shared-memory ring.  The A map is THREE
 //                              dimensional {channel, tap, row} with the tap stride equal to the row stride: row m
 //                              of the implicit im2col matrix is the contiguous slice x[m .. m + taps - 1] of the
 //                              time-major activation, so a causal Conv1d(k) / ConvTranspose1d(2s, s) is a plain GEMM
 //                              over OVERLAPPING rows and no im2col buffer exists (rows beyond M read as zero)
 //   warp 1      MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::tf32 (M128 x N128 x K8, four
 //                              per stage); tcgen05.commit releases the stage / signals the epilogue
-//   warps 2..5  epilogue     : tcgen05.ld -> bias / GELU / LayerScale / residual -> fp32 stores; optionally the
+//   warps 2..9  epilogue     : tcgen05.ld -> bias / GELU / LayerScale / residual -> fp32 stores; optionally the
 //                              ELU of the result (rounded to TF32) as a second output, because the consumer of a
 //                              SEANet activation applies ELU to its input and a TMA-fed operand cannot be touched
 //                              on its way into the tensor core
-// 96 KB of shared memory and 128 TMEM columns per CTA: two CTAs per SM, one's epilogue under the other's MMAs.
+// Persistent: one CTA per SM walks the tiles; two accumulators in TMEM (2 x 128 columns) let the epilogue of one
+// tile run under the loads and MMAs of the next.
 // Operands are rounded to TF32 (round-to-nearest) where they are PRODUCED (weights at pack time, activations in
 // the producing epilogue), so the tensor core's truncation of the low mantissa bits is exact.
 #pragma once
@@ -25,11 +26,13 @@
 
 namespace mtc {
 
-constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
+constexpr int BM = 128, BN = 128, BK = 32, STAGES = 4;
 constexpr int UMMA_K = 8;
-constexpr int THREADS = 192;
+constexpr int THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
 constexpr uint32_t STAGE_BYTES = (BM + BN) * BK * 4;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int TLD = BN + 4;                                    // padded row of the epilogue staging tile
+constexpr size_t TILE_BYTES = (size_t)BM * TLD * 4;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 enum { F_GELU = 2, F_RESID = 4, F_LAYERSCALE = 8, F_OUT_ELU = 16, F_ROUND = 32 };
 
@@ -110,30 +113,44 @@ __device__ __forceinline__ float round_tf32(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
-__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
+// (the result is rounded to TF32's 10 mantissa bits right away: exp(x) - 1 from the fast exponential, absolute
+// error ~1e-7, is far inside that)
+__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// cin: channels per tap of the A operand (K = taps * cin, cin % 32 == 0)
-__global__ void __launch_bounds__(THREADS, 2)
+// cin: channels per tap of the A operand (K = taps * cin, cin % 32 == 0).
+// PERSISTENT: one CTA per SM walks the output tiles t = blockIdx.x, + gridDim.x, ... (n tile fastest, so the CTAs
+// working at the same time share their A rows in L2).  The three roles run concurrently across tiles: the TMA warp
+// is already loading tile i+1 while the MMA lane works on tile i and the epilogue warps drain tile i-1 -- the
+// accumulator is double buffered in TMEM (2 x 128 columns, acc_full / acc_empty barriers), the shared-memory ring
+// simply keeps counting k blocks across tiles.  The SEANet tail is 11 250 tiles of 6 (or 1) k blocks each: with
+// one tile per CTA the fixed cost of a CTA (barrier init, TMEM allocation, pipeline fill, drain) was the whole run time.
+__global__ void __launch_bounds__(THREADS, 1)
 k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Args a, int cin) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+  float* tile = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES);  // [BM][TLD] epilogue staging
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES + TILE_BYTES);
   uint64_t* empty = full + STAGES;
-  uint64_t* acc_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_full = empty + STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const long long m0 = (long long)blockIdx.y * BM;
   const int num_kb = a.K / BK;
+  const int n_tiles = (a.N + BN - 1) / BN;
+  const long long m_tiles = ((long long)a.M + BM - 1) / BM;
+  const long long tiles = m_tiles * n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 8);  // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -142,7 +159,7 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "n"(BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "n"(2 * BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -152,105 +169,151 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
-        unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
-        unsigned char* sb = sa + BM * BK * 4;
-        mbar_expect(&full[s], STAGE_BYTES);
-        const int k = kb * BK;
-        tma_load_3d(sa, &map_a, &full[s], k % cin, k / cin, (int)m0);
-        tma_load_2d(sb, &map_b, &full[s], k, n0);
+      unsigned kc = 0;  // k blocks issued so far, over all tiles
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int n0 = (int)(t % n_tiles) * BN;
+        const int m0 = (int)(t / n_tiles) * BM;
+        for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+          const int s = kc % STAGES;
+          mbar_wait(&empty[s], ((kc / STAGES) & 1) ^ 1);
+          unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
+          unsigned char* sb = sa + BM * BK * 4;
+          mbar_expect(&full[s], STAGE_BYTES);
+          const int k = kb * BK;
+          tma_load_3d(sa, &map_a, &full[s], k % cin, k / cin, m0);
+          tma_load_2d(sb, &map_b, &full[s], k, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = instr_desc(BM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(&full[s], (kb / STAGES) & 1);
+      unsigned kc = 0, it = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+        const unsigned buf = it & 1;
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
-        const unsigned char* sb = sa + BM * BK * 4;
-        const uint64_t ad = smem_desc(sa), bd = smem_desc(sb);
+        const uint32_t acc = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+          const int s = kc % STAGES;
+          mbar_wait(&full[s], (kc / STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
+          const unsigned char* sb = sa + BM * BK * 4;
+          const uint64_t ad = smem_desc(sa), bd = smem_desc(sb);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k)  // +32 bytes along K inside the 128-byte swizzle atom
-          umma_tf32(tmem_base, ad + (uint64_t)(k * UMMA_K * 4 >> 4), bd + (uint64_t)(k * UMMA_K * 4 >> 4), idesc, (kb | k) != 0);
-        umma_commit(&empty[s]);
+          for (int k = 0; k < BK / UMMA_K; ++k)  // +32 bytes along K inside the 128-byte swizzle atom
+            umma_tf32(acc, ad + (uint64_t)(k * UMMA_K * 4 >> 4), bd + (uint64_t)(k * UMMA_K * 4 >> 4), idesc, (kb | k) != 0);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[buf]);
       }
-      umma_commit(acc_full);
     }
   } else {
-    // epilogue, two steps.  (1) warp w may touch TMEM lanes [32*(w%4), +32): each lane drains ITS row of the
-    // accumulator into a shared-memory tile (the pipeline stages are free by now).  (2) the four warps walk the
-    // tile in row-major order, four consecutive columns per lane: bias / GELU / LayerScale / residual and the
-    // stores are COALESCED -- with one row per lane a 32- or 64-column output (the SEANet tail) made every store
-    // instruction touch 32 different lines and the epilogue, not HBM, bounded those GEMMs.
-    const int q = warp & 3;
-    mbar_wait(acc_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int nvalid = a.N - n0 < BN ? a.N - n0 : BN;  // a multiple of 4 (launcher)
-    float* tile = reinterpret_cast<float*>(smem);      // [BM][TLD]
-    constexpr int TLD = BN + 4;
+    // epilogue (8 warps), two steps per tile.  (1) warp w may touch TMEM lanes [32*(w%4), +32): the two warps of a
+    // lane quarter split the columns, each lane drains ITS row into the shared-memory tile and the accumulator goes
+    // back to the MMA lane.  (2) the warps walk the tile in row-major order, four consecutive columns per lane:
+    // bias / GELU / LayerScale / residual and the stores are COALESCED -- with one row per lane a 32- or 64-column
+    // output (the SEANet tail) made every store instruction touch 32 different lines.  The valid width of a tile is
+    // 32, 64 or 128 (launcher), so a thread keeps its column for the whole tile: no division in the loop, bias and
+    // LayerScale are loaded once per tile.  (With four warps and a division per element this step, not HBM, was the
+    // run time of the persistent kernel: one warp per scheduler hides no latency.)
+    const int q = warp & 3;           // the TMEM lane quarter is tied to the warp's index in the CTA
+    const int half = (warp - 2) >> 2; // warps 2..5 take the first half of the columns, 6..9 the second
+    const int et = threadIdx.x - 64;  // 0 .. 255
+    unsigned it = 0;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+      const int n0 = (int)(t % n_tiles) * BN;
+      const long long m0 = (t / n_tiles) * BM;
+      const unsigned buf = it & 1;
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int nvalid = a.N - n0 < BN ? a.N - n0 : BN;  // 32, 64 or 128
+      const int cper = nvalid > 32 ? nvalid >> 1 : 32;   // columns each of the quarter's two warps drains
 #pragma unroll 1
-    for (int c0 = 0; c0 < nvalid; c0 += 32) {
-      uint32_t v[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float* trow = tile + (size_t)(q * 32 + lane) * TLD + c0;
+      for (int c0 = half * cper; c0 < (half + 1) * cper && c0 < nvalid; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float* trow = tile + (size_t)(q * 32 + lane) * TLD + c0;
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(trow + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    }
-    asm volatile("bar.sync 2, 128;" ::: "memory");  // the four epilogue warps
-    const int et = threadIdx.x - 64;                 // 0 .. 127
-    const int c4n = nvalid >> 2;                     // float4 columns per row
-    const int mrows = a.M - m0 < BM ? (int)(a.M - m0) : BM;
-#pragma unroll 1
-    for (int i = et; i < mrows * c4n; i += 128) {
-      const int r = i / c4n, c = (i - r * c4n) * 4;
-      const long long row = m0 + r;
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(trow + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+      // this warp is done with the accumulator: hand it back (the MMA lane may start tile it + 2 in it)
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&acc_empty[buf])) : "memory");
+      asm volatile("bar.sync 2, 256;" ::: "memory");  // the tile is complete in shared memory
+      const int csh = nvalid == 128 ? 5 : (nvalid == 64 ? 4 : 3);  // log2(float4 columns per row)
+      const int c = (et & ((1 << csh) - 1)) * 4;                   // this thread's column for the whole tile
+      const int rstep = 256 >> csh;                                // rows covered by the 256 threads per round
+      const int mrows = a.M - m0 < BM ? (int)(a.M - m0) : BM;
       const int n = n0 + c;
-      const float4 t = *reinterpret_cast<const float4*>(tile + (size_t)r * TLD + c);
-      float y[4] = {t.x, t.y, t.z, t.w}, e[4];
+      float bv[4] = {0.f, 0.f, 0.f, 0.f}, sv[4] = {1.f, 1.f, 1.f, 1.f};
+      if (a.bias) {
+        const int bi = n % a.bias_period;  // the period is a multiple of 4: the four columns stay inside it
+        bv[0] = a.bias[bi]; bv[1] = a.bias[bi + 1]; bv[2] = a.bias[bi + 2]; bv[3] = a.bias[bi + 3];
+      }
+      if (a.flags & F_LAYERSCALE) {
+        sv[0] = a.scale[n]; sv[1] = a.scale[n + 1]; sv[2] = a.scale[n + 2]; sv[3] = a.scale[n + 3];
+      }
+#pragma unroll 1
+      for (int r0 = et >> csh; r0 < mrows; r0 += 4 * rstep) {
+        // four rows per thread per round: the residual loads of the round go out together
+        float4 rr[4];
+        if (a.flags & F_RESID) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float x = y[k];
-        if (a.bias) x += a.bias[(n + k) % a.bias_period];
-        if (a.flags & F_GELU) x = gelu_f(x);
-        if (a.flags & F_LAYERSCALE) x *= a.scale[n + k];
-        y[k] = x;
-      }
-      if (a.flags & F_RESID) {
-        const float4 rr = *reinterpret_cast<const float4*>(a.R + row * a.ldr + n);
-        y[0] += rr.x; y[1] += rr.y; y[2] += rr.z; y[3] += rr.w;
-      }
-      if (a.C2 || (a.flags & F_OUT_ELU)) {
+          for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u * rstep;
+            if (r < mrows) rr[u] = *reinterpret_cast<const float4*>(a.R + (m0 + r) * a.ldr + n);
+          }
+        }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) e[k] = round_tf32(elu_f(y[k]));
+        for (int u = 0; u < 4; ++u) {
+          const int r = r0 + u * rstep;
+          if (r >= mrows) break;
+          const long long row = m0 + r;
+          const float4 tv = *reinterpret_cast<const float4*>(tile + (size_t)r * TLD + c);
+          float y[4] = {tv.x + bv[0], tv.y + bv[1], tv.z + bv[2], tv.w + bv[3]}, e[4];
+          if (a.flags & F_GELU) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) y[k] = gelu_f(y[k]);
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) y[k] *= sv[k];
+          if (a.flags & F_RESID) {
+            y[0] += rr[u].x; y[1] += rr[u].y; y[2] += rr[u].z; y[3] += rr[u].w;
+          }
+          if (a.C2 || (a.flags & F_OUT_ELU)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) e[k] = round_tf32(elu_f(y[k]));
+          }
+          if (a.C2) *reinterpret_cast<float4*>(a.C2 + row * a.ldc2 + n) = make_float4(e[0], e[1], e[2], e[3]);
+          if (a.C) {
+            float4 o;
+            if (a.flags & F_OUT_ELU) o = make_float4(e[0], e[1], e[2], e[3]);
+            else if (a.flags & F_ROUND) o = make_float4(round_tf32(y[0]), round_tf32(y[1]), round_tf32(y[2]), round_tf32(y[3]));
+            else o = make_float4(y[0], y[1], y[2], y[3]);
+            *reinterpret_cast<float4*>(a.C + row * a.ldc + n) = o;
+          }
+        }
       }
-      if (a.C2) *reinterpret_cast<float4*>(a.C2 + row * a.ldc2 + n) = make_float4(e[0], e[1], e[2], e[3]);
-      if (a.C) {
-        float4 o;
-        if (a.flags & F_OUT_ELU) o = make_float4(e[0], e[1], e[2], e[3]);
-        else if (a.flags & F_ROUND) o = make_float4(round_tf32(y[0]), round_tf32(y[1]), round_tf32(y[2]), round_tf32(y[3]));
-        else o = make_float4(y[0], y[1], y[2], y[3]);
-        *reinterpret_cast<float4*>(a.C + row * a.ldc + n) = o;
-      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");  // the staging tile is free for the next tile
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
   }
 }
 
