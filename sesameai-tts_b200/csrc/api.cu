@@ -1129,7 +1129,23 @@ static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const b
       a.part = splitk->tc_part; a.counters = splitk->tc_counters; a.ldp = (long long)grid.x * tc::BN;
     }
   }
-  tc::k_gemm_tc<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mx, mw, a); COUNT_LAUNCH();
+  static const bool old_kernel = getenv("CSM_TC_ONE_TILE") != nullptr;  // measurement aid: round 1's one-tile-per-CTA kernel
+  if (grid.z > 1 || old_kernel) {
+    tc::k_gemm_tc<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mx, mw, a); COUNT_LAUNCH();
+  } else {
+    // persistent kernel: one CTA per SM walks the tiles
+    static std::atomic<unsigned long long> attr_p{0};
+    static int sms[64] = {0};
+    int dev = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    if (!device_done(attr_p, false)) {
+      CU_TRY(cudaFuncSetAttribute(tc::k_gemm_tc_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::P_SMEM_BYTES));
+      device_done(attr_p, true);
+    }
+    if (dev >= 0 && dev < 64 && !sms[dev]) CU_TRY(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
+    const int nsm = (dev >= 0 && dev < 64 && sms[dev] > 0) ? sms[dev] : 148;
+    tc::k_gemm_tc_p<<<tiles < nsm ? tiles : nsm, tc::P_THREADS, tc::P_SMEM_BYTES, st>>>(mx, mw, a); COUNT_LAUNCH();
+  }
   CU_TRY(cudaGetLastError());
   return CSM_OK;
 }

@@ -307,4 +307,180 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
   }
 }
 
+// ---- persistent variant (round 2): prompt prefill and every GEMM that is not split-K --------------------------
+// One CTA per SM walks the output tiles (n tile fastest: the CTAs at work share their X rows in L2).  TMA warp, MMA
+// lane and EIGHT epilogue warps run concurrently across tiles: the accumulator is double buffered in TMEM
+// (2 x 128 columns; acc_full / acc_empty barriers), the shared-memory ring keeps counting k blocks across tiles,
+// so the loads and MMAs of tile i+1 run under the epilogue of tile i.  The epilogue drains the accumulator row-per-
+// lane into a shared-memory tile and then walks it in row-major order, four columns per lane: residual loads and
+// bf16 stores are coalesced (256 bytes per warp and row) instead of 32 lines per store instruction.
+constexpr int P_STAGES = 4;
+constexpr int P_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int P_TLD = BN + 4;
+constexpr size_t P_TILE_BYTES = (size_t)BM * P_TLD * 4;
+constexpr size_t P_SMEM_BYTES = (size_t)P_STAGES * STAGE_BYTES + P_TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+__global__ void __launch_bounds__(P_THREADS, 1)
+k_gemm_tc_p(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, Args a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  float* tile = reinterpret_cast<float*>(smem + (size_t)P_STAGES * STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)P_STAGES * STAGE_BYTES + P_TILE_BYTES);
+  uint64_t* empty = full + P_STAGES;
+  uint64_t* acc_full = empty + P_STAGES;  // [2]
+  uint64_t* acc_empty = acc_full + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_kb = a.K / BK;
+  const int n_tiles = (a.n_out + BN - 1) / BN;
+  const int m_tiles = (a.rows + BM - 1) / BM;
+  const long long tiles = (long long)m_tiles * n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 8);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "n"(2 * BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      unsigned kc = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int n0 = (int)(t % n_tiles) * BN, m0 = (int)(t / n_tiles) * BM;
+        for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+          const int s = kc % P_STAGES;
+          mbar_wait(&empty[s], ((kc / P_STAGES) & 1) ^ 1);
+          unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
+          unsigned char* sb = sa + BM * BK * 2;
+          mbar_expect(&full[s], STAGE_BYTES);
+          tma_load_2d(sa, &map_x, &full[s], kb * BK, m0);
+          tma_load_2d(sb, &map_w, &full[s], kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(BM, BN);
+      unsigned kc = 0, it = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+        const unsigned buf = it & 1;
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc = tmem_base + buf * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+          const int s = kc % P_STAGES;
+          mbar_wait(&full[s], (kc / P_STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
+          const unsigned char* sb = sa + BM * BK * 2;
+          const uint64_t ad = smem_desc(sa), bd = smem_desc(sb);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma(acc, ad + (uint64_t)(k * UMMA_K * 2 >> 4), bd + (uint64_t)(k * UMMA_K * 2 >> 4), idesc, (kb | k) != 0);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&acc_full[buf]);
+      }
+    }
+  } else {
+    const int q = warp & 3;            // the TMEM lane quarter is tied to the warp's index in the CTA
+    const int half = (warp - 2) >> 2;  // warps 2..5 drain columns [0, 64), warps 6..9 columns [64, 128)
+    const int et = threadIdx.x - 64;   // 0 .. 255
+    const int c = (et & 31) * 4;       // this thread's four columns of the tile
+    unsigned it = 0;
+    for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+      const int n0 = (int)(t % n_tiles) * BN, m0 = (int)(t / n_tiles) * BM;
+      const unsigned buf = it & 1;
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+      for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        float* trow = tile + (size_t)(q * 32 + lane) * P_TLD + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(trow + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&acc_empty[buf])) : "memory");
+      asm volatile("bar.sync 2, 256;" ::: "memory");  // the tile is complete in shared memory
+      const int mrows = a.rows - m0 < BM ? a.rows - m0 : BM;
+      const int n = n0 + c;
+      const bool full4 = n + 4 <= a.n_out;
+      const bool vec = full4 && (a.ldo & 3) == 0;  // 8-byte stores / residual loads
+      if (n < a.n_out) {
+#pragma unroll 1
+        for (int r0 = et >> 5; r0 < mrows; r0 += 4 * 8) {
+          uint2 rr[4];
+          if (a.epi == EPI_ADD_RESID && vec) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int r = r0 + u * 8;
+              if (r < mrows) rr[u] = *reinterpret_cast<const uint2*>(a.resid + (long long)(m0 + r) * a.ldo + n);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u * 8;
+            if (r >= mrows) break;
+            const long long row = m0 + r;
+            const float4 tv = *reinterpret_cast<const float4*>(tile + (size_t)r * P_TLD + c);
+            const float y[4] = {rbf(tv.x), rbf(tv.y), rbf(tv.z), rbf(tv.w)};
+            if (a.epi == EPI_SWIGLU_PAIRS) {
+              // columns (2i, 2i+1) = (gate_i, up_i): bf16( bf16(silu(bf16 gate)) * bf16 up )
+              bf16* o = a.out + row * a.ldo + (n >> 1);
+              if (full4) {
+                *reinterpret_cast<__nv_bfloat162*>(o) = __floats2bfloat162_rn(silu_bf(y[0]) * y[1], silu_bf(y[2]) * y[3]);
+              } else if (n + 1 < a.n_out) {
+                o[0] = f2bf(silu_bf(y[0]) * y[1]);
+              }
+            } else if (vec) {
+              float z[4] = {y[0], y[1], y[2], y[3]};
+              if (a.epi == EPI_ADD_RESID) {
+                z[0] += bflo(rr[u].x); z[1] += bfhi(rr[u].x); z[2] += bflo(rr[u].y); z[3] += bfhi(rr[u].y);
+              }
+              __nv_bfloat162 pk[2] = {__floats2bfloat162_rn(z[0], z[1]), __floats2bfloat162_rn(z[2], z[3])};
+              *reinterpret_cast<uint2*>(a.out + row * a.ldo + n) = *reinterpret_cast<uint2*>(pk);
+            } else {
+              for (int j = 0; j < 4 && n + j < a.n_out; ++j) {
+                float z = y[j];
+                if (a.epi == EPI_ADD_RESID) z += bf2f(a.resid[row * a.ldo + n + j]);
+                a.out[row * a.ldo + n + j] = f2bf(z);
+              }
+            }
+          }
+        }
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");  // the staging tile is free for the next tile
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
+  }
+}
+
 }  // namespace tc
