@@ -9,7 +9,11 @@ dev = torch.device("cuda", 0)
 B = int(os.environ.get("PF_B", "1"))
 model = bench.build_product(dev, B)
 tok, msk, pos = syn.voice_prompt(B, 4, 64, 320, 32, seed=3, device=dev)
-for _ in range(2):
-    model.reset_caches()
-    model.generate_frame(tok, msk, pos, 0.9, 50, prefill=_native.PREFILL_TENSOR)
-    torch.cuda.synchronize()
+model.reset_caches()
+model.generate_frame(tok, msk, pos, 0.9, 50, prefill=_native.PREFILL_TENSOR)
+torch.cuda.synchronize()
+torch.cuda.profiler.start()  # ncu --profile-from-start off: one prefill + first frame
+model.reset_caches()
+model.generate_frame(tok, msk, pos, 0.9, 50, prefill=_native.PREFILL_TENSOR)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
