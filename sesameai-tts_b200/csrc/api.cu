@@ -48,7 +48,16 @@ static const int PREFILL_CHUNK = 8;     // prompt frames per stream per small-ro
 static const int PREFILL_TC_ROWS = 4096;  // rows per tensor-core prefill pass
 static const int PREFILL_TC_MIN = 64;     // prompt rows (B * (S-1)) from which the tcgen05 path is used
 static const int DECODE_TC_MIN = 16;      // streams from which a decode step runs on the tcgen05 GEMM
-static const int SKINNY_MAX_ROWS = 64;    // rows up to which a linear layer runs on the skinny fragment-major GEMM
+static int skinny_max_rows() {  // rows up to which a linear layer runs on the skinny fragment-major GEMM (CSM_SKINNY_MAX_ROWS: experiments)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CSM_SKINNY_MAX_ROWS");
+    v = e ? atoi(e) : 64;
+    if (v < 0 || v > 64) v = 64;
+  }
+  return v;
+}
+#define SKINNY_MAX_ROWS (skinny_max_rows())
 static const int TC_SPLIT_TILES = 148;    // split-K of the tcgen05 GEMM: splits x tiles never exceeds one CTA per SM
 static const int TC_SPLIT_MAX_ROWS = 512; // ... and is only used for decode-sized row counts
 
