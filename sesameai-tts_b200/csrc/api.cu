@@ -32,6 +32,26 @@ static std::atomic<unsigned long long> g_launches{0};
 #define COUNT_LAUNCH() (g_launches.fetch_add(1, std::memory_order_relaxed))
 extern "C" uint64_t csm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+// Kernel launch of the frame path: with the programmatic-serialisation attribute (common.cuh: pdl_trigger /
+// pdl_wait) the kernel may start while its predecessor on the stream drains; every kernel launched here waits
+// for that predecessor before it touches activations.  Captured into the decode graphs as programmatic edges.
+// CSM_PDL=0 launches plainly (measurement aid).
+static bool pdl_enabled() {
+  static const bool on = !(getenv("CSM_PDL") && getenv("CSM_PDL")[0] == '0');
+  return on;
+}
+template <typename... P, typename... A>
+static void launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);  // failures surface through cudaGetLastError()
+}
+
 struct csm_ctx;
 static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const bf16* W, int n_out, bf16* out, long long ldo,
                           int epi, const bf16* resid, cudaStream_t st, const csm_ctx* splitk = nullptr);
@@ -287,7 +307,7 @@ static cudaError_t launch_gemv_t(const GemvArgs& a, cudaStream_t st) {
   if (gx > 148 * 8) gx = 148 * 8;
   dim3 grid(gx, (a.N + NB - 1) / NB);
   const size_t smem = (size_t)NB * a.K * sizeof(bf16);
-  k_gemv<NB, EPI, NORM><<<grid, threads, smem, st>>>(a); COUNT_LAUNCH();
+  launch_k(k_gemv<NB, EPI, NORM>, dim3(grid), dim3(threads), smem, st, a); COUNT_LAUNCH();
   return cudaGetLastError();
 }
 template <int EPI, bool NORM>
@@ -327,10 +347,10 @@ static cudaError_t run_layer(csm_ctx* x, StackDev& s, int l, int N, const RowMet
     const size_t smem = (size_t)s.slots * sizeof(float);
     const float scale = 1.0f / sqrtf((float)s.hd);
     if (s.hd == 64) {
-      k_attn_rows<64><<<grid, 128, smem, st>>>(s.q, kc, vc, m.stream, m.slot, m.imp_B, m.imp_pos, c.heads, c.kv_heads,
+      launch_k(k_attn_rows<64>, dim3(grid), dim3(128), smem, st, s.q, kc, vc, m.stream, m.slot, m.imp_B, m.imp_pos, c.heads, c.kv_heads,
                                                s.slots, scale, s.att);
     } else {
-      k_attn_rows<128><<<grid, 128, smem, st>>>(s.q, kc, vc, m.stream, m.slot, m.imp_B, m.imp_pos, c.heads, c.kv_heads,
+      launch_k(k_attn_rows<128>, dim3(grid), dim3(128), smem, st, s.q, kc, vc, m.stream, m.slot, m.imp_B, m.imp_pos, c.heads, c.kv_heads,
                                                 s.slots, scale, s.att);
     }
     COUNT_LAUNCH();
@@ -354,7 +374,7 @@ static cudaError_t run_layer(csm_ctx* x, StackDev& s, int l, int N, const RowMet
 static cudaError_t backbone_pass(csm_ctx* x, int B, int chunk, cudaStream_t st) {
   const csm_config& c = x->cfg;
   const int N = B * chunk;
-  k_embed_pass<<<N, 256, 0, st>>>(x->d_params, x->text_emb, x->audio_emb, c.codebooks, c.audio_vocab, c.backbone.dim,
+  launch_k(k_embed_pass, dim3(N), dim3(256), 0, st, x->d_params, x->text_emb, x->audio_emb, c.codebooks, c.audio_vocab, c.backbone.dim,
                                   chunk, x->bb.h, x->row_stream, x->row_pos, x->row_slot, c.text_vocab, x->bb.rope_len,
                                   x->d_sync); COUNT_LAUNCH();
   cudaError_t e = cudaGetLastError();
@@ -372,7 +392,7 @@ static cudaError_t frame_tail(csm_ctx* x, int B, cudaStream_t st) {
   const int D = c.backbone.dim, Dd = c.decoder.dim, V = c.audio_vocab, C = c.codebooks;
   cudaError_t e;
   // last_h = backbone.norm(h)  -> decoder input rows [0, B)
-  k_rmsnorm<<<B, 256, 0, st>>>(x->bb.h, D, x->bb.norm, D, c.norm_eps, x->dec_in, D); COUNT_LAUNCH();
+  launch_k(k_rmsnorm, dim3(B), dim3(256), 0, st, x->bb.h, D, x->bb.norm, D, c.norm_eps, x->dec_in, D); COUNT_LAUNCH();
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   GemvArgs a;
   memset(&a, 0, sizeof(a));
@@ -380,7 +400,7 @@ static cudaError_t frame_tail(csm_ctx* x, int B, cudaStream_t st) {
   // codebook0_head
   a.W = x->c0_head; a.rows = V; a.K = D; a.x = x->dec_in; a.ldx = D; a.N = B; a.out = x->logits; a.ldo = x->Vp;
   if ((e = launch_gemv<EPI_PLAIN, false>(a, st)) != cudaSuccess) return e;
-  k_sample_step<<<B, SAMPLE_THREADS, 0, st>>>(x->d_params, x->logits, x->Vp, 0, V, C, x->audio_emb, D,
+  launch_k(k_sample_step, dim3(B), dim3(SAMPLE_THREADS), 0, st, x->d_params, x->logits, x->Vp, 0, V, C, x->audio_emb, D,
                                               x->dec_in + (size_t)B * D, x->d_sync); COUNT_LAUNCH();
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   for (int i = 1; i < C; ++i) {
@@ -401,7 +421,7 @@ static cudaError_t frame_tail(csm_ctx* x, int B, cudaStream_t st) {
     a.x = x->dec.h + (size_t)(N - B) * Dd; a.ldx = Dd; a.N = B; a.norm_scale = x->dec.norm;
     a.out = x->logits; a.ldo = x->Vp;
     if ((e = launch_gemv<EPI_PLAIN, true>(a, st)) != cudaSuccess) return e;
-    k_sample_step<<<B, SAMPLE_THREADS, 0, st>>>(x->d_params, x->logits, x->Vp, i, V, C, x->audio_emb, D,
+    launch_k(k_sample_step, dim3(B), dim3(SAMPLE_THREADS), 0, st, x->d_params, x->logits, x->Vp, i, V, C, x->audio_emb, D,
                                                 (i + 1 < C) ? x->dec_in : nullptr, x->d_sync); COUNT_LAUNCH();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
@@ -672,7 +692,7 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
     for (int cb = 1; cb + 1 < c.codebooks; ++cb) {
       const bf16* rows = x->proj_table + (size_t)cb * V * Dd;
       bf16* out = x->qkv_table + (size_t)cb * V * qkv_cols;
-      k_rmsnorm<<<V, 256, 0, st>>>(rows, Dd, d.sa[0], Dd, c.norm_eps, x->bb.xn, Dd); COUNT_LAUNCH();
+      launch_k(k_rmsnorm, dim3(V), dim3(256), 0, st, rows, Dd, d.sa[0], Dd, c.norm_eps, x->bb.xn, Dd); COUNT_LAUNCH();
       int rc = launch_gemm_tc(x->bb.xn, Dd, V, Dd, d.wqkv[0], qkv_cols, out, qkv_cols, tc::EPI_STORE, nullptr, st);
       if (rc != CSM_OK) return rc;
       k_rope_table<<<V, 256, 0, st>>>(out, d.rope, cb + 1, d.c.heads, d.c.kv_heads, d.hd); COUNT_LAUNCH();
@@ -985,7 +1005,7 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
   for (int s0 = 0; s0 < S - 1; s0 += per_pass) {
     const int chunk = (S - 1 - s0) < per_pass ? (S - 1 - s0) : per_pass;
     p.s0 = s0;
-    k_set_params<<<1, 1, 0, st>>>(x->d_params, p, s0 == 0 ? x->d_sync : nullptr); COUNT_LAUNCH();
+    launch_k(k_set_params, dim3(1), dim3(1), 0, st, x->d_params, p, s0 == 0 ? x->d_sync : nullptr); COUNT_LAUNCH();
     CU_TRY(cudaGetLastError());
     if (prefill_path == CSM_PREFILL_TENSOR) {
       int rc = backbone_pass_tc(x, B, chunk, st);
@@ -1002,7 +1022,7 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
     advance();
     return CSM_OK;
   }
-  k_set_params<<<1, 1, 0, st>>>(x->d_params, p, S == 1 ? x->d_sync : nullptr); COUNT_LAUNCH();
+  launch_k(k_set_params, dim3(1), dim3(1), 0, st, x->d_params, p, S == 1 ? x->d_sync : nullptr); COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
   if (path == CSM_PATH_DIRECT) {
     if (rows_path(x, B)) {
@@ -1140,7 +1160,7 @@ static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const b
   }
   static const bool old_kernel = getenv("CSM_TC_ONE_TILE") != nullptr;  // measurement aid: round 1's one-tile-per-CTA kernel
   if (grid.z > 1 || old_kernel) {
-    tc::k_gemm_tc<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(mx, mw, a); COUNT_LAUNCH();
+    launch_k(tc::k_gemm_tc, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, mx, mw, a); COUNT_LAUNCH();
   } else {
     // persistent kernel: one CTA per SM walks the tiles
     static std::atomic<unsigned long long> attr_p{0};
@@ -1153,7 +1173,7 @@ static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const b
     }
     if (dev >= 0 && dev < 64 && !sms[dev]) CU_TRY(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
     const int nsm = (dev >= 0 && dev < 64 && sms[dev] > 0) ? sms[dev] : 148;
-    tc::k_gemm_tc_p<<<tiles < nsm ? tiles : nsm, tc::P_THREADS, tc::P_SMEM_BYTES, st>>>(mx, mw, a); COUNT_LAUNCH();
+    launch_k(tc::k_gemm_tc_p, dim3(tiles < nsm ? tiles : nsm), dim3(tc::P_THREADS), tc::P_SMEM_BYTES, st, mx, mw, a); COUNT_LAUNCH();
   }
   CU_TRY(cudaGetLastError());
   return CSM_OK;
@@ -1162,10 +1182,10 @@ static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const b
 // Batched decode (<= 64 rows): one CTA per fragment-major row group (skinny.cuh).  n_out = valid rows.
 template <bool NORM>
 static void launch_skinny_t(const sk::Args& a, cudaStream_t st) {
-  if (a.N <= 8) sk::k_skinny<1, NORM><<<a.G, 256, 0, st>>>(a);
-  else if (a.N <= 16) sk::k_skinny<2, NORM><<<a.G, 256, 0, st>>>(a);
-  else if (a.N <= 32) sk::k_skinny<4, NORM><<<a.G, 256, 0, st>>>(a);
-  else sk::k_skinny<8, NORM><<<a.G, 256, 0, st>>>(a);
+  if (a.N <= 8) launch_k(sk::k_skinny<1, NORM>, dim3(a.G), dim3(256), 0, st, a);
+  else if (a.N <= 16) launch_k(sk::k_skinny<2, NORM>, dim3(a.G), dim3(256), 0, st, a);
+  else if (a.N <= 32) launch_k(sk::k_skinny<4, NORM>, dim3(a.G), dim3(256), 0, st, a);
+  else launch_k(sk::k_skinny<8, NORM>, dim3(a.G), dim3(256), 0, st, a);
 }
 // norm_scale != null: X holds the un-normalised rows and the kernel applies torchtune's RMSNorm on the fly
 static int launch_skinny(const bf16* Wf, int R, const bf16* X, long long ldx, int N, int K, int n_out, bf16* out, long long ldo,
@@ -1198,7 +1218,7 @@ static int norm_linear_rows(csm_ctx* x, const bf16* H, const bf16* scale, float 
   // (every CTA normalises all rows itself: cheaper than a launch up to 16 rows, measured slower at 32)
   if (skinny_ok(x, Wf, N, K) && N <= 16) return launch_skinny(Wf, R, H, K, N, K, n_out, out, ldo, epi, nullptr, st, scale, eps);
   if (!xn_ready) {
-    k_rmsnorm<<<N, 256, 0, st>>>(H, K, scale, K, eps, xn, K); COUNT_LAUNCH();
+    launch_k(k_rmsnorm, dim3(N), dim3(256), 0, st, H, K, scale, K, eps, xn, K); COUNT_LAUNCH();
   }
   return linear_rows(x, W, Wf, R, xn, K, N, K, n_out, out, ldo, epi, nullptr, st);
 }
@@ -1223,14 +1243,14 @@ static int stack_pass_tc(csm_ctx* x, StackDev& s, int N, const RowMeta& m, cudaS
       ra.heads = k.heads; ra.kv_heads = k.kv_heads; ra.hd = s.hd; ra.slots = s.slots; ra.k_cache = kc; ra.v_cache = vc;
       const bool fuse_norm = N <= 16;
       if (!fuse_norm) {
-        k_rmsnorm<<<N, 256, 0, st>>>(s.h, D, s.sa[l], D, eps, s.xn, D); COUNT_LAUNCH();
+        launch_k(k_rmsnorm, dim3(N), dim3(256), 0, st, s.h, D, s.sa[l], D, eps, s.xn, D); COUNT_LAUNCH();
       }
       if ((rc = launch_skinny(s.fqkv[l], R4[0], fuse_norm ? s.h : s.xn, D, N, D, qkv_cols, s.q, 0, sk::EPI_ROPE_KV, nullptr, st,
                               fuse_norm ? s.sa[l] : nullptr, eps, &ra)) != CSM_OK) return rc;
     } else {
       if ((rc = norm_linear_rows(x, s.h, s.sa[l], eps, s.xn, false, s.wqkv[l], s.fqkv[l], R4[0], N, D, qkv_cols, s.qkv, qkv_cols,
                                  tc::EPI_STORE, st)) != CSM_OK) return rc;
-      k_rope_kv_rows<<<N, 256, 0, st>>>(s.qkv, s.rope, m.stream, m.pos, m.slot, m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.hd,
+      launch_k(k_rope_kv_rows, dim3(N), dim3(256), 0, st, s.qkv, s.rope, m.stream, m.pos, m.slot, m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.hd,
                                         s.slots, s.q, kc, vc); COUNT_LAUNCH();
     }
     {
@@ -1240,12 +1260,12 @@ static int stack_pass_tc(csm_ctx* x, StackDev& s, int N, const RowMeta& m, cudaS
       if (s.hd == 64 && m.chunk >= 16 && m.stream) {
         // prompt rows: tiled tensor-core attention, one CTA per (64 rows of a stream, q-head)
         dim3 fgrid((m.chunk + 63) / 64, k.heads, N / m.chunk);
-        k_attn_flash64<<<fgrid, 128, 0, st>>>(s.q, kc, vc, m.slot, m.chunk, k.heads, k.kv_heads, s.slots, scale, s.att);
+        launch_k(k_attn_flash64, dim3(fgrid), dim3(128), 0, st, s.q, kc, vc, m.slot, m.chunk, k.heads, k.kv_heads, s.slots, scale, s.att);
       } else if (s.hd == 64) {
-        k_attn_rows<64><<<grid, 128, smem, st>>>(s.q, kc, vc, m.stream, m.slot, m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.slots,
+        launch_k(k_attn_rows<64>, dim3(grid), dim3(128), smem, st, s.q, kc, vc, m.stream, m.slot, m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.slots,
                                                  scale, s.att);
       } else {
-        k_attn_rows<128><<<grid, 128, smem, st>>>(s.q, kc, vc, m.stream, m.slot, m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.slots,
+        launch_k(k_attn_rows<128>, dim3(grid), dim3(128), smem, st, s.q, kc, vc, m.stream, m.slot, m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.slots,
                                                   scale, s.att);
       }
       COUNT_LAUNCH();
@@ -1264,7 +1284,7 @@ static int stack_pass_tc(csm_ctx* x, StackDev& s, int N, const RowMeta& m, cudaS
 static int backbone_pass_tc(csm_ctx* x, int B, int chunk, cudaStream_t st) {
   const csm_config& c = x->cfg;
   const int N = B * chunk;
-  k_embed_pass<<<N, 256, 0, st>>>(x->d_params, x->text_emb, x->audio_emb, c.codebooks, c.audio_vocab, c.backbone.dim, chunk,
+  launch_k(k_embed_pass, dim3(N), dim3(256), 0, st, x->d_params, x->text_emb, x->audio_emb, c.codebooks, c.audio_vocab, c.backbone.dim, chunk,
                                   x->bb.h, x->row_stream, x->row_pos, x->row_slot, c.text_vocab, x->bb.rope_len, x->d_sync);
   COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
@@ -1284,7 +1304,7 @@ static int frame_tail_tc(csm_ctx* x, int B, cudaStream_t st) {
                              x->logits, x->Vp, tc::EPI_STORE, st)) != CSM_OK) return rc;
   if ((rc = norm_linear_rows(x, x->bb.h, x->bb.norm, c.norm_eps, x->dec_in, true, x->proj, x->f_head0 + (size_t)x->Vf * D, x->mega_Rh0, B,
                              D, Dd, x->dec.h, Dd, tc::EPI_STORE, st)) != CSM_OK) return rc;
-  k_sample_step<<<B, SAMPLE_THREADS, 0, st>>>(x->d_params, x->logits, x->Vp, 0, V, C, x->proj_table, Dd,
+  launch_k(k_sample_step, dim3(B), dim3(SAMPLE_THREADS), 0, st, x->d_params, x->logits, x->Vp, 0, V, C, x->proj_table, Dd,
                                               x->dec.h + (size_t)B * Dd, x->d_sync); COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
   for (int i = 1; i < C; ++i) {
@@ -1294,7 +1314,7 @@ static int frame_tail_tc(csm_ctx* x, int B, cudaStream_t st) {
     if ((rc = norm_linear_rows(x, x->dec.h + (size_t)(N - B) * Dd, x->dec.norm, c.norm_eps, x->dec.xn, false,
                                x->head_t + (size_t)(i - 1) * x->Vp * Dd, x->f_heads + (size_t)(i - 1) * x->Vf * Dd, x->mega_Rh, B, Dd, V,
                                x->logits, x->Vp, tc::EPI_STORE, st)) != CSM_OK) return rc;
-    k_sample_step<<<B, SAMPLE_THREADS, 0, st>>>(x->d_params, x->logits, x->Vp, i, V, C, x->proj_table, Dd,
+    launch_k(k_sample_step, dim3(B), dim3(SAMPLE_THREADS), 0, st, x->d_params, x->logits, x->Vp, i, V, C, x->proj_table, Dd,
                                                 (i + 1 < C) ? x->dec.h : nullptr, x->d_sync); COUNT_LAUNCH();
     CU_TRY(cudaGetLastError());
   }
@@ -1328,7 +1348,7 @@ extern "C" int32_t csm_k_attn_prefill(const void* q, const void* k_cache, const 
       slots < 1)
     return set_err(CSM_ERR_ARG, "bad attn_prefill arguments");
   dim3 grid((chunk + 63) / 64, heads, B);
-  k_attn_flash64<<<grid, 128, 0, (cudaStream_t)stream>>>((const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache, row_slot, chunk,
+  launch_k(k_attn_flash64, dim3(grid), dim3(128), 0, (cudaStream_t)stream, (const bf16*)q, (const bf16*)k_cache, (const bf16*)v_cache, row_slot, chunk,
                                                          heads, kv_heads, slots, 0.125f, (bf16*)out);
   COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
@@ -1370,7 +1390,7 @@ extern "C" int32_t csm_k_linear(const void* xin, const void* W, int32_t N, int32
 extern "C" int32_t csm_k_rmsnorm(const void* xin, const void* scale, int32_t N, int32_t D, float eps, void* y,
                                  void* stream) {
   if (!xin || !scale || !y || N < 1 || D < 1) return set_err(CSM_ERR_ARG, "bad rmsnorm arguments");
-  k_rmsnorm<<<N, 256, 0, (cudaStream_t)stream>>>((const bf16*)xin, D, (const bf16*)scale, D, eps, (bf16*)y, D); COUNT_LAUNCH();
+  launch_k(k_rmsnorm, dim3(N), dim3(256), 0, (cudaStream_t)stream, (const bf16*)xin, D, (const bf16*)scale, D, eps, (bf16*)y, D); COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
   return CSM_OK;
 }

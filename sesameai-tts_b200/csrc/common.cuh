@@ -26,6 +26,19 @@ __device__ __forceinline__ uint4 ld_stream(const void* p) {
   return r;
 }
 
+// Programmatic dependent launch (the row-batched decode step is ~1100 dependent launches of a few microseconds
+// each): a kernel launched with the programmatic-serialisation attribute starts while its predecessor
+// drains.  pdl_wait() returns once the previous kernel of the stream has completed and its writes are
+// visible; pdl_trigger() lets the NEXT kernel's CTAs become resident once every CTA of this one has
+// issued it.  Rules in this library: before pdl_wait() a kernel touches only immutable data (weights,
+// tables: L2 prefetch, barrier / TMEM set-up, weight TMA boxes); EVERY thread that reads or writes
+// activations calls pdl_wait() first; and the trigger comes AFTER the wait, so at most two consecutive
+// kernels overlap and no ordering is inherited through a chain of waits.  Without the launch attribute
+// both are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -149,6 +149,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
 
   if (warp == 0) {
     if (lane == 0) {
+      pdl_wait();
+      pdl_trigger();
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
@@ -180,6 +182,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
     // epilogue: warp w may touch TMEM lanes [32*(w%4), +32) -> output rows m0 + that range
     const int q = warp & 3;
     const int row = m0 + q * 32 + lane;
+    pdl_wait();
+    pdl_trigger();
     mbar_wait(acc_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     bool finish = true;  // this CTA runs the epilogue (always, without split-K)
@@ -364,17 +368,36 @@ k_gemm_tc_p(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
 
   if (warp == 0) {
     if (lane == 0) {
-      unsigned kc = 0;
-      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const int n0 = (int)(t % n_tiles) * BN, m0 = (int)(t / n_tiles) * BM;
-        for (int kb = 0; kb < num_kb; ++kb, ++kc) {
-          const int s = kc % P_STAGES;
-          mbar_wait(&empty[s], ((kc / P_STAGES) & 1) ^ 1);
-          unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
-          unsigned char* sb = sa + BM * BK * 2;
-          mbar_expect(&full[s], STAGE_BYTES);
-          tma_load_2d(sa, &map_x, &full[s], kb * BK, m0);
-          tma_load_2d(sb, &map_w, &full[s], kb * BK, n0);
+      // Programmatic dependent launch: the W boxes of the first ring pass do not depend on the previous kernel --
+      // they are requested before pdl_wait(), the X boxes of the same stages after it (both count on full[s]).
+      const long long mine = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+      const unsigned total = (unsigned)(mine * num_kb);
+      const unsigned pre = total < (unsigned)P_STAGES ? total : (unsigned)P_STAGES;
+      for (unsigned kc = 0; kc < total; ++kc) {
+        if (kc == pre) {
+          pdl_wait();
+          pdl_trigger();
+          for (unsigned j = 0; j < pre; ++j) {
+            const long long t = blockIdx.x + (long long)(j / num_kb) * gridDim.x;
+            tma_load_2d(smem + (size_t)j * STAGE_BYTES, &map_x, &full[j], (int)(j % num_kb) * BK, (int)(t / n_tiles) * BM);
+          }
+        }
+        const long long t = blockIdx.x + (long long)(kc / num_kb) * gridDim.x;
+        const int kb = (int)(kc % num_kb), n0 = (int)(t % n_tiles) * BN, m0 = (int)(t / n_tiles) * BM;
+        const int s = kc % P_STAGES;
+        mbar_wait(&empty[s], ((kc / P_STAGES) & 1) ^ 1);
+        unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
+        unsigned char* sb = sa + BM * BK * 2;
+        mbar_expect(&full[s], STAGE_BYTES);
+        if (kc >= pre) tma_load_2d(sa, &map_x, &full[s], kb * BK, m0);
+        tma_load_2d(sb, &map_w, &full[s], kb * BK, n0);
+      }
+      if (total <= pre) {  // fewer k blocks than stages: the X boxes are still owed
+        pdl_wait();
+        pdl_trigger();
+        for (unsigned j = 0; j < total; ++j) {
+          const long long t = blockIdx.x + (long long)(j / num_kb) * gridDim.x;
+          tma_load_2d(smem + (size_t)j * STAGE_BYTES, &map_x, &full[j], (int)(j % num_kb) * BK, (int)(t / n_tiles) * BM);
         }
       }
     }
@@ -408,6 +431,8 @@ k_gemm_tc_p(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
     const int et = threadIdx.x - 64;   // 0 .. 255
     const int c = (et & 31) * 4;       // this thread's four columns of the tile
     unsigned it = 0;
+    pdl_wait();
+    pdl_trigger();
     for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
       const int n0 = (int)(t % n_tiles) * BN, m0 = (int)(t / n_tiles) * BM;
       const unsigned buf = it & 1;

@@ -60,6 +60,8 @@ struct DevStatus {
   unsigned int* host_error;  // mapped host mirror, sticky until csm_check_error clears it
 };
 __global__ void k_set_params(FrameParams* dst, FrameParams v, DevStatus* st_reset) {
+  pdl_wait();
+  pdl_trigger();
   *dst = v;
   if (st_reset) st_reset->error = 0;  // per call; the host mirror stays sticky until csm_check_error reads it
 }
@@ -119,6 +121,8 @@ __global__ void k_embed_frames(const int64_t* tokens, const uint8_t* mask, const
 __global__ void k_embed_pass(const FrameParams* __restrict__ P, const bf16* text_emb, const bf16* audio_emb, int C,
                              int V, int D, int chunk, bf16* h, int* row_stream, int* row_pos, int* row_slot, int TV,
                              int rope_len, DevStatus* st) {
+  pdl_wait();
+  pdl_trigger();
   const int n = blockIdx.x;
   const int b = n / chunk, t = n % chunk;
   const int s = P->s0 + t;
@@ -230,6 +234,8 @@ __global__ void __launch_bounds__(256) k_gemv(GemvArgs a) {  // launched with ex
   __shared__ float scratch[72];
   const int K = a.K;
   const int n0 = blockIdx.y * NB;
+  pdl_wait();
+  pdl_trigger();
 
   // stage the activation rows (zero-fill rows past N)
   for (int i = threadIdx.x; i < NB * (K / 8); i += blockDim.x) {
@@ -325,6 +331,8 @@ __global__ void __launch_bounds__(128) k_attn_rows(const bf16* __restrict__ q, c
                                                    const bf16* __restrict__ v_cache, const int* __restrict__ row_stream,
                                                    const int* __restrict__ row_slot, int imp_B, int imp_pos, int heads,
                                                    int kv_heads, int slots, float scale, bf16* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* sc = reinterpret_cast<float*>(smem_raw);  // [slots]
   __shared__ float scratch[33];
@@ -425,6 +433,8 @@ __device__ __forceinline__ uint32_t fa_pack(float lo, float hi) {
 __global__ void __launch_bounds__(128) k_attn_flash64(const bf16* __restrict__ q, const bf16* __restrict__ k_cache,
                                                       const bf16* __restrict__ v_cache, const int* __restrict__ row_slot, int chunk,
                                                       int heads, int kv_heads, int slots, float scale, bf16* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ __align__(16) bf16 Qs[64 * FA_LD];
   __shared__ __align__(16) bf16 Ks[2][64 * FA_LD];
   __shared__ __align__(16) bf16 Vs[2][64 * FA_LD];
@@ -570,6 +580,8 @@ __global__ void __launch_bounds__(256) k_rope_kv_rows(const bf16* __restrict__ q
                                                       const int* __restrict__ row_slot, int imp_B, int imp_pos, int heads,
                                                       int kv_heads, int hd, int slots, bf16* __restrict__ q_out,
                                                       bf16* __restrict__ k_cache, bf16* __restrict__ v_cache) {
+  pdl_wait();
+  pdl_trigger();
   const int n = blockIdx.x;
   const int qrows = heads * hd, krows = kv_heads * hd, total = qrows + 2 * krows;
   const bf16* src = qkv + (size_t)n * total;
@@ -605,6 +617,8 @@ __global__ void __launch_bounds__(256) k_rope_kv_rows(const bf16* __restrict__ q
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_rmsnorm(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ scale,
                                                  int D, float eps, bf16* __restrict__ y, int ldy) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float scratch[33];
   const int n = blockIdx.x;
   const bf16* xr = x + (size_t)n * ldx;
@@ -860,6 +874,8 @@ __global__ void __launch_bounds__(SAMPLE_THREADS) k_sample_step(const FrameParam
                                                                 int V, int C, const bf16* __restrict__ audio_emb, int D,
                                                                 bf16* __restrict__ next_in /*[B, D] or null*/,
                                                                 DevStatus* st = nullptr) {
+  pdl_wait();
+  pdl_trigger();
   // ``audio_emb``/``D`` may also be the projection(embedding) table and its row length
   __shared__ float xs[SAMPLE_MAXV];
   __shared__ unsigned int hist[256];

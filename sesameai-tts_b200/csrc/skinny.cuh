@@ -64,6 +64,14 @@ __global__ void __launch_bounds__(256) k_skinny(Args a) {
   const int ks = K >> 3, nblk = ks >> 5;  // this warp's k slice, in 32-wide blocks
   const unsigned char* wp = reinterpret_cast<const unsigned char*>(a.Wf) + ((size_t)grp * R * K + (size_t)warp * R * ks) * 2 + lane * 16;
   const int blk = R * 64;
+  // Programmatic dependent launch: this CTA's weight slice (R * K bf16, contiguous) does not depend on the
+  // previous kernel -- pull it into L2 while that kernel drains, then wait for the activations.
+  {
+    const unsigned char* base = reinterpret_cast<const unsigned char*>(a.Wf) + (size_t)grp * R * K * 2;
+    for (int off = tid * 128; off < R * K * 2; off += 256 * 128) prefetch_l2(base + off);
+  }
+  pdl_wait();
+  pdl_trigger();
   // x fragment rows of this lane: stream t*8 + g (clamped: rows >= N feed outputs nobody reads)
   const bf16* xp[NT];
 #pragma unroll
