@@ -81,6 +81,9 @@ int32_t csm_abi_version(void);
 /* Kernels this library has launched in this process so far (a CUDA-graph replay counts its
  * kernel nodes); bench.py reports the difference over the timed region as ``gpu_launches``. */
 uint64_t csm_launch_count(void);
+/* Test hook: launch the frame path's kernels with (1, default; env CSM_PDL=0 disables) or without (0) the programmatic
+ * dependent launch attribute.  Applies to launches and graph captures made after the call. */
+void csm_debug_set_pdl(int32_t on);
 const char *csm_last_error(void);
 
 /* Bytes of device workspace csm_create needs for ``max_batch`` streams: KV caches (GQA-compact

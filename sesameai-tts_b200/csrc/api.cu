@@ -36,10 +36,17 @@ extern "C" uint64_t csm_launch_count(void) { return g_launches.load(std::memory_
 // pdl_wait) the kernel may start while its predecessor on the stream drains; every kernel launched here waits
 // for that predecessor before it touches activations.  Captured into the decode graphs as programmatic edges.
 // CSM_PDL=0 launches plainly (measurement aid).
+static std::atomic<int> g_pdl{-1};
 static bool pdl_enabled() {
-  static const bool on = !(getenv("CSM_PDL") && getenv("CSM_PDL")[0] == '0');
-  return on;
+  int v = g_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    v = !(getenv("CSM_PDL") && getenv("CSM_PDL")[0] == '0');
+    g_pdl.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
 }
+// test hook: contexts created afterwards capture their graphs with (1) / without (0) programmatic edges
+extern "C" void csm_debug_set_pdl(int32_t on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
 template <typename... P, typename... A>
 static void launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
   cudaLaunchConfig_t cfg;

@@ -26,6 +26,7 @@ namespace {
   } while (0)
 
 const int PAD = 8;  // zero rows in front of every conv input
+const int BT_GROUP = 8;  // utterances whose transformer passes run as one batch (mimi_decode, B > 1)
 const int RATIOS[4] = {8, 6, 5, 4};
 
 struct Carver {
@@ -59,6 +60,7 @@ struct mimi_ctx {
   float* res2_r[4];        // residual block's 1x1 conv per stage
   float* u_raw[4];
   float* xs_r;
+  float* bt_xr;            // batched one-shot decode: BT_GROUP rounded transformer outputs, (L + PAD) rows each
 };
 
 // ---- streamed decode state ------------------------------------------------------------------------
@@ -142,6 +144,7 @@ static size_t mimi_carve(mimi_ctx* x, char* base) {
     x->tr_r[l][3] = cv.take(512 * 2048);
   }
   x->xs_r = cv.take((L + PAD) * 512);
+  x->bt_xr = cv.take((size_t)BT_GROUP * (L + PAD) * 512);
   {
     size_t rr = L;
     int c2 = 1024;
@@ -269,6 +272,95 @@ static int gemm_tc(cudaStream_t st, const float* A, long long lda, int cin, int 
   MCU_TRY(cudaGetLastError());
   return CSM_OK;
 }
+// The weight-resident kernel (mimi_tc.cuh: k_gemm_tf32_r) for one-tile-wide GEMMs over a small weight matrix; falls
+// back to gemm_tc when the shape does not qualify.  ``fin`` (optional) carries the fused final convolution.
+static bool g_mimi_resident = true;  // MIMI_RESIDENT=0: measurement aid
+static int gemm_tc_r(cudaStream_t st, const float* A, long long lda, int cin, int taps, const float* B, long long M, int N,
+                     const mtc::Args& ep, const mtc::RArgs* fin = nullptr) {
+  const int K = cin * taps;
+  const size_t budget = 220 * 1024;
+  const bool resid = (ep.flags & mtc::F_RESID) != 0;
+  // shared memory: weights + staging tile, then residual tiles (up to 3 in flight) and A stages (up to 8) as they fit
+  int stages = 0, nres = 0;
+  if ((N == 32 || N == 64 || N == 128) && !ep.C2 && !(ep.flags & (mtc::F_GELU | mtc::F_LAYERSCALE)) &&
+      mtc::r_smem_bytes(K, N, 2, resid ? 1 : 0) <= budget && (!fin || (N == 64 && resid && M % mtc::BM == 0))) {
+    if (resid) {
+      nres = mtc::R_MAX_RES;
+      while (nres > 1 && mtc::r_smem_bytes(K, N, 3, nres) > budget) --nres;
+    }
+    stages = mtc::R_MAX_STAGES;
+    while (stages > 2 && mtc::r_smem_bytes(K, N, stages, nres) > budget) --stages;
+  }
+  if (stages < 2 || (!g_mimi_resident && !fin)) {
+    if (fin) return csm_set_error(CSM_ERR_ARG, "mimi gemm_tc_r: the fused final conv needs the weight-resident kernel");
+    return gemm_tc(st, A, lda, cin, taps, B, M, N, ep);
+  }
+  mimi_encode_tiled_fn enc = mimi_encode_tiled();
+  if (!enc) return csm_set_error(CSM_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable");
+  if (cin % mtc::BK || M < 1 || (((uintptr_t)A | (uintptr_t)B) & 15) || (lda * 4) % 16 || (ep.bias && ep.bias_period % 4))
+    return csm_set_error(CSM_ERR_ARG, "mimi gemm_tc_r: unsupported shape");
+  typedef void (*rkern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, mtc::RArgs, int);
+  static const rkern_t kerns[7] = {mtc::k_gemm_tf32_r<32, false, false>,  mtc::k_gemm_tf32_r<64, false, false>,
+                                   mtc::k_gemm_tf32_r<128, false, false>, mtc::k_gemm_tf32_r<32, true, false>,
+                                   mtc::k_gemm_tf32_r<64, true, false>,   mtc::k_gemm_tf32_r<128, true, false>,
+                                   mtc::k_gemm_tf32_r<64, true, true>};
+  const int ki = fin ? 6 : (resid ? 3 : 0) + (N == 32 ? 0 : (N == 64 ? 1 : 2));
+  static bool attr[64] = {false};
+  static int sms[64] = {0};
+  int dev = 0;
+  MCU_TRY(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return csm_set_error(CSM_ERR_ARG, "mimi gemm_tc_r: device index out of range");
+  if (!attr[dev]) {
+    for (int i = 0; i < 7; ++i) MCU_TRY(cudaFuncSetAttribute(kerns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+    MCU_TRY(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
+    attr[dev] = true;
+  }
+  CUtensorMap ma, mb;
+  {
+    cuuint64_t gdim[3] = {(cuuint64_t)cin, (cuuint64_t)taps, (cuuint64_t)M};
+    cuuint64_t gstr[2] = {(cuuint64_t)lda * 4, (cuuint64_t)lda * 4};
+    cuuint32_t box[3] = {(cuuint32_t)mtc::BK, 1, (cuuint32_t)mtc::BM};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)A, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return csm_set_error(CSM_ERR_CUDA, "cuTensorMapEncodeTiled (A, 3-d) failed");
+  }
+  {
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t gstr[1] = {(cuuint64_t)K * 4};
+    cuuint32_t box[2] = {(cuuint32_t)mtc::BK, (cuuint32_t)N};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&mb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)B, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return csm_set_error(CSM_ERR_CUDA, "cuTensorMapEncodeTiled (B) failed");
+  }
+  CUtensorMap mr = ma;  // (unused without a residual)
+  if (resid) {
+    if (((uintptr_t)ep.R & 15) || (ep.ldr * 4) % 16) return csm_set_error(CSM_ERR_ARG, "mimi gemm_tc_r: misaligned residual");
+    cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    cuuint64_t gstr[1] = {(cuuint64_t)ep.ldr * 4};
+    cuuint32_t box[2] = {(cuuint32_t)N, (cuuint32_t)mtc::BM};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)ep.R, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return csm_set_error(CSM_ERR_CUDA, "cuTensorMapEncodeTiled (residual) failed");
+  }
+  mtc::RArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  if (fin) ra = *fin;
+  ra.e = ep;
+  ra.e.M = (int)M; ra.e.N = N; ra.e.K = K;
+  if (ra.e.bias_period < 1) ra.e.bias_period = 1;
+  ra.stages = stages;
+  ra.nres = nres;
+  const long long tiles = (M + mtc::BM - 1) / mtc::BM;
+  const int nsm = sms[dev] > 0 ? sms[dev] : 148;
+  const unsigned grid = (unsigned)(tiles < nsm ? tiles : nsm);
+  kerns[ki]<<<grid, mtc::R_THREADS, mtc::r_smem_bytes(K, N, stages, nres), st>>>(ma, mb, mr, ra, cin);
+  csm_count_launches(1);
+  MCU_TRY(cudaGetLastError());
+  return CSM_OK;
+}
 static mtc::Args ep_plain(float* C, long long ldc, int flags = 0, const float* bias = nullptr, int period = 1) {
   mtc::Args e;
   memset(&e, 0, sizeof(e));
@@ -320,6 +412,8 @@ extern "C" int32_t mimi_create(const void* const* weights, int32_t n_weights, in
     // rounds operands when it loads fragments, the tcgen05 path truncates -- on rounded values both see the same bits
     const char* mode = getenv("MIMI_DECODE");
     x->tc = !(mode && !strcmp(mode, "mma"));
+    const char* res = getenv("MIMI_RESIDENT");
+    g_mimi_resident = !(res && res[0] == '0');
     auto round_to = [&](const float* src, float* dst, long long n) {
       mimi::k_round_copy<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, n);
       csm_count_launches(1);
@@ -376,37 +470,47 @@ static void copy_rows(cudaStream_t st, const float* src, long long lds, float* d
 // 8-layer causal transformer (context 250) in place on xs [L, 512]; lw0 = first of the 80 layer tensors.
 // ``kv`` (streamed decode, else null): per-layer history of the hist = min(pos0, 249) positions before this chunk
 // (pos0 = absolute position of row 0); it is read into the rows in front of the chunk's q/k/v and updated.
+// ``sc`` / ``nutt`` (tensor-core path, one-shot): xs holds nutt utterances of L / nutt rows each and the scratch
+// buffers are the caller's; every row-wise kernel runs once over all rows, attention per utterance (grid z).
+struct TrScratch {
+  float *xn, *qkv, *att, *ff;
+};
 static int mimi_transformer(mimi_ctx* x, float* xs, long long L, int w_layer0, cudaStream_t st, float* const* kv = nullptr,
-                            long long pos0 = 0, bool tc = false) {
+                            long long pos0 = 0, bool tc = false, const TrScratch* sc = nullptr, int nutt = 1) {
   using namespace mimi;
   const int hist = kv ? (int)(pos0 < HIST ? pos0 : HIST) : 0;
-  float* qkv = x->qkv + (size_t)hist * 1536;  // rows of this chunk
+  float* const qkv0 = sc ? sc->qkv : x->qkv;
+  float* const xn = sc ? sc->xn : x->xn;
+  float* const att = sc ? sc->att : x->att;
+  float* const ff = sc ? sc->ff : x->ff;
+  const long long Lu = L / nutt;
+  float* qkv = qkv0 + (size_t)hist * 1536;  // rows of this chunk
   for (int l = 0; l < 8; ++l) {
     const float* const* lw = &x->w[w_layer0 + 10 * l];
     if (tc) {
       // the same layer on the tcgen05 GEMM: operands rounded to TF32 where they are produced
       int rc;
-      k_layernorm512<<<(unsigned)((L + 7) / 8), 256, 0, st>>>(xs, lw[2], lw[3], (int)L, 1e-5f, x->xn, 1);
-      if ((rc = gemm_tc(st, x->xn, 512, 512, 1, x->tr_r[l][0], L, 1536, ep_plain(qkv, 1536))) != CSM_OK) return rc;
-      k_rope_qk<<<(unsigned)((L * 512 + 255) / 256), 256, 0, st>>>(qkv, (int)L, kv ? pos0 : 0);
-      if (kv) copy_rows(st, kv[l], 1024, x->qkv + 512, 1536, hist, 1024);
+      k_layernorm512<<<(unsigned)((L + 7) / 8), 256, 0, st>>>(xs, lw[2], lw[3], (int)L, 1e-5f, xn, 1);
+      if ((rc = gemm_tc(st, xn, 512, 512, 1, x->tr_r[l][0], L, 1536, ep_plain(qkv, 1536))) != CSM_OK) return rc;
+      k_rope_qk<<<(unsigned)((L * 512 + 255) / 256), 256, 0, st>>>(qkv, (int)L, kv ? pos0 : 0, nutt > 1 ? (int)Lu : 0);
+      if (kv) copy_rows(st, kv[l], 1024, qkv0 + 512, 1536, hist, 1024);
       {
         const size_t at_smem = (size_t)3 * 64 * mimi::AT_LD * sizeof(float);
-        k_attn_window_tc<<<dim3((unsigned)((L + 63) / 64), 8), 128, at_smem, st>>>(x->qkv, (int)L, 250, x->att, hist,
-                                                                                  (kv ? pos0 : 0) - hist, 1);
+        k_attn_window_tc<<<dim3((unsigned)((Lu + 63) / 64), 8, (unsigned)nutt), 128, at_smem, st>>>(qkv0, (int)Lu, 250, att, hist,
+                                                                                                   (kv ? pos0 : 0) - hist, 1);
       }
       if (kv) {
         const long long keep = hist + L < HIST ? hist + L : HIST;
-        copy_rows(st, x->qkv + (size_t)(hist + L - keep) * 1536 + 512, 1536, kv[l], 1024, keep, 1024);
+        copy_rows(st, qkv0 + (size_t)(hist + L - keep) * 1536 + 512, 1536, kv[l], 1024, keep, 1024);
       }
       mtc::Args e1 = ep_plain(xs, 512, mtc::F_LAYERSCALE | mtc::F_RESID);
       e1.R = xs; e1.ldr = 512; e1.scale = lw[8];
-      if ((rc = gemm_tc(st, x->att, 512, 512, 1, x->tr_r[l][1], L, 512, e1)) != CSM_OK) return rc;
-      k_layernorm512<<<(unsigned)((L + 7) / 8), 256, 0, st>>>(xs, lw[4], lw[5], (int)L, 1e-5f, x->xn, 1);
-      if ((rc = gemm_tc(st, x->xn, 512, 512, 1, x->tr_r[l][2], L, 2048, ep_plain(x->ff, 2048, mtc::F_GELU | mtc::F_ROUND))) != CSM_OK) return rc;
+      if ((rc = gemm_tc(st, att, 512, 512, 1, x->tr_r[l][1], L, 512, e1)) != CSM_OK) return rc;
+      k_layernorm512<<<(unsigned)((L + 7) / 8), 256, 0, st>>>(xs, lw[4], lw[5], (int)L, 1e-5f, xn, 1);
+      if ((rc = gemm_tc(st, xn, 512, 512, 1, x->tr_r[l][2], L, 2048, ep_plain(ff, 2048, mtc::F_GELU | mtc::F_ROUND))) != CSM_OK) return rc;
       mtc::Args e2 = ep_plain(xs, 512, mtc::F_LAYERSCALE | mtc::F_RESID);
       e2.R = xs; e2.ldr = 512; e2.scale = lw[9];
-      if ((rc = gemm_tc(st, x->ff, 2048, 2048, 1, x->tr_r[l][3], L, 512, e2)) != CSM_OK) return rc;
+      if ((rc = gemm_tc(st, ff, 2048, 2048, 1, x->tr_r[l][3], L, 512, e2)) != CSM_OK) return rc;
       csm_count_launches(4);
       continue;
     }
@@ -524,6 +628,8 @@ extern "C" int32_t mimi_k_rvq_encode(mimi_ctx* x, const float* latent, int32_t T
 // left context is ``sbuf`` (``frames_done`` frames so far; an all-zero state = the start of an utterance).
 static int decode_chunk_tc(mimi_ctx* x, float* sbuf, long long frames_done, const int64_t* codes, int K, int T, long long ldt,
                            float* wav, cudaStream_t st);
+static int decode_front_tc(mimi_ctx* x, float* sbuf, const int64_t* codes, int K, int T, long long ldt, float* xs, cudaStream_t st);
+static int decode_seanet_tc(mimi_ctx* x, float* sbuf, float* xr, long long L, float* wav, cudaStream_t st);
 
 static int decode_chunk(mimi_ctx* x, float* sbuf, long long frames_done, const int64_t* codes, int K, int T, long long ldt,
                         float* wav, cudaStream_t st) {
@@ -585,17 +691,12 @@ static int decode_chunk(mimi_ctx* x, float* sbuf, long long frames_done, const i
 // (the path is a property of the context).
 static int decode_chunk_tc(mimi_ctx* x, float* sbuf, long long frames_done, const int64_t* codes, int K, int T, long long ldt,
                            float* wav, cudaStream_t st) {
-  using namespace mimi;
-  const StateLayout SL = state_layout();
   const long long L = 2LL * T;
   int rc;
-  k_rvq_gather<<<T, 256, 0, st>>>(codes, K, T, ldt, x->emb, x->q512, 1);
-  if ((rc = gemm_tc(st, x->q512, 512, 512, 1, x->wproj, T, 512, ep_plain(x->e, 512))) != CSM_OK) return rc;
   float* xs = x->xs + (size_t)PAD * 512;
-  k_upsample2<<<(unsigned)((L * 512 + 255) / 256), 256, 0, st>>>(x->e, x->w[MIMI_W_UPSAMPLE], T, 512, xs, sbuf + SL.e_prev);
-  copy_rows(st, x->e + (size_t)(T - 1) * 512, 512, sbuf + SL.e_prev, 512, 1, 512);
-  csm_count_launches(2);
+  if ((rc = decode_front_tc(x, sbuf, codes, K, T, ldt, xs, st)) != CSM_OK) return rc;
   {
+    const StateLayout SL = state_layout();
     float* kv[8];
     for (int l = 0; l < 8; ++l) kv[l] = sbuf + SL.kv[l];
     if ((rc = mimi_transformer(x, xs, L, MIMI_W_LAYER0, st, kv, 2 * frames_done, true)) != CSM_OK) return rc;
@@ -604,6 +705,29 @@ static int decode_chunk_tc(mimi_ctx* x, float* sbuf, long long frames_done, cons
   float* xr = x->xs_r + (size_t)PAD * 512;
   mtc::k_round_tf32<<<(unsigned)((L * 512 + 255) / 256), 256, 0, st>>>(xs, xr, L * 512);
   csm_count_launches(1);
+  return decode_seanet_tc(x, sbuf, xr, L, wav, st);
+}
+
+// codes -> RVQ sum -> projection -> depthwise ConvTranspose1d x2: the transformer's input rows xs [2T, 512]
+static int decode_front_tc(mimi_ctx* x, float* sbuf, const int64_t* codes, int K, int T, long long ldt, float* xs, cudaStream_t st) {
+  using namespace mimi;
+  const StateLayout SL = state_layout();
+  const long long L = 2LL * T;
+  int rc;
+  k_rvq_gather<<<T, 256, 0, st>>>(codes, K, T, ldt, x->emb, x->q512, 1);
+  if ((rc = gemm_tc(st, x->q512, 512, 512, 1, x->wproj, T, 512, ep_plain(x->e, 512))) != CSM_OK) return rc;
+  k_upsample2<<<(unsigned)((L * 512 + 255) / 256), 256, 0, st>>>(x->e, x->w[MIMI_W_UPSAMPLE], T, 512, xs, sbuf + SL.e_prev);
+  copy_rows(st, x->e + (size_t)(T - 1) * 512, 512, sbuf + SL.e_prev, 512, 1, 512);
+  csm_count_launches(2);
+  MCU_TRY(cudaGetLastError());
+  return CSM_OK;
+}
+
+// SEANet decoder on the TF32-rounded transformer output xr [L, 512] (>= 6 writable rows in front of it)
+static int decode_seanet_tc(mimi_ctx* x, float* sbuf, float* xr, long long L, float* wav, cudaStream_t st) {
+  using namespace mimi;
+  const StateLayout SL = state_layout();
+  int rc;
   copy_rows(st, sbuf + SL.xs_tail, 512, xr - 6 * 512, 512, 6, 512);
   copy_rows(st, xr + (L - 6) * 512, 512, sbuf + SL.xs_tail, 512, 6, 512);
   float* c0 = x->c0 + (size_t)PAD * 1024;  // holds ELU(conv0(..))
@@ -627,11 +751,23 @@ static int decode_chunk_tc(mimi_ctx* x, float* sbuf, long long frames_done, cons
     copy_rows(st, sbuf + SL.pre[s], co, ue - 2 * co, co, 2, co);
     copy_rows(st, ue + (rows - 2) * co, co, sbuf + SL.pre[s], co, 2, co);
     // residual block: u + conv1(ELU(conv3(ELU(u)))), stored as ELU(..) for what follows
-    if ((rc = gemm_tc(st, ue - 2 * co, co, co, 3, x->res1[s], rows, hid, ep_plain(x->r[s], hid, mtc::F_OUT_ELU, sw[3], hid))) != CSM_OK) return rc;
+    if ((rc = gemm_tc_r(st, ue - 2 * co, co, co, 3, x->res1[s], rows, hid, ep_plain(x->r[s], hid, mtc::F_OUT_ELU, sw[3], hid))) != CSM_OK) return rc;
     mtc::Args er = ep_plain(ue, co, mtc::F_OUT_ELU | mtc::F_RESID, sw[5], co);
     er.R = ur; er.ldr = co;
-    if ((rc = gemm_tc(st, x->r[s], hid, hid, 1, x->res2_r[s], rows, co, er)) != CSM_OK) return rc;
     const int np = s == 3 ? 2 : 1;
+    if (s == 3 && g_mimi_resident) {
+      // last stage: the final Conv1d(64 -> 1, k = 3) runs in this GEMM's epilogue; the stage's activation is not stored
+      copy_rows(st, sbuf + SL.post[s], co, ue - (size_t)np * co, co, np, co);  // rows -2, -1: the previous chunk's tail
+      MCU_TRY(cudaMemsetAsync(wav, 0, (size_t)rows * sizeof(float), st));
+      mtc::RArgs fin;
+      memset(&fin, 0, sizeof(fin));
+      fin.fw = x->finalw; fin.fb = x->final_bias; fin.wav = wav; fin.halo = ue - (size_t)np * co; fin.tail = sbuf + SL.post[s];
+      er.C = nullptr;
+      if ((rc = gemm_tc_r(st, x->r[s], hid, hid, 1, x->res2_r[s], rows, co, er, &fin)) != CSM_OK) return rc;
+      MCU_TRY(cudaGetLastError());
+      return CSM_OK;
+    }
+    if ((rc = gemm_tc_r(st, x->r[s], hid, hid, 1, x->res2_r[s], rows, co, er)) != CSM_OK) return rc;
     copy_rows(st, sbuf + SL.post[s], co, ue - (size_t)np * co, co, np, co);
     copy_rows(st, ue + (rows - np) * co, co, sbuf + SL.post[s], co, np, co);
     in = ue;
@@ -643,11 +779,53 @@ static int decode_chunk_tc(mimi_ctx* x, float* sbuf, long long frames_done, cons
   return CSM_OK;
 }
 
+// One-shot decode of several utterances (T <= max_frames): the transformer -- 8 layers of small row-wise kernels, a
+// third of a 60 s decode when run per utterance on 1500 rows -- runs ONCE over the rows of up to BT_GROUP utterances
+// (attention per utterance); front end and SEANet stay per utterance.  Row-wise kernels and per-utterance attention
+// tiles compute every row exactly as the per-utterance path does: the result is bit-identical.  The batch's scratch
+// (residual stream, xn, qkv, att, ff: 5120 floats per row) lives in the last stage's raw ConvTranspose1d buffer,
+// which is dead until the SEANet of the group's first utterance runs; the rounded outputs wait in bt_xr.
+static int decode_batch_tc(mimi_ctx* x, const int64_t* codes, int B, int K, int T, float* out, cudaStream_t st) {
+  const StateLayout SL = state_layout();
+  const long long L = 2LL * T;
+  const size_t cap = (size_t)2 * x->max_frames * 960 * 64;  // floats in u_raw[3]
+  int G = BT_GROUP;
+  while (G > 1 && (size_t)G * L * 5120 > cap) --G;
+  float* bxs = x->u_raw[3];
+  TrScratch sc;
+  sc.xn = bxs + (size_t)G * L * 512;
+  sc.qkv = sc.xn + (size_t)G * L * 512;
+  sc.att = sc.qkv + (size_t)G * L * 1536;
+  sc.ff = sc.att + (size_t)G * L * 512;
+  const size_t slot = (size_t)(2 * x->max_frames + PAD) * 512;
+  int rc;
+  for (int b0 = 0; b0 < B; b0 += G) {
+    const int g = B - b0 < G ? B - b0 : G;
+    for (int i = 0; i < g; ++i) {
+      MCU_TRY(cudaMemsetAsync(x->own_state + SL.e_prev, 0, 512 * sizeof(float), st));
+      if ((rc = decode_front_tc(x, x->own_state, codes + (size_t)(b0 + i) * K * T, K, T, T, bxs + (size_t)i * L * 512, st)) != CSM_OK) return rc;
+    }
+    if ((rc = mimi_transformer(x, bxs, (long long)g * L, MIMI_W_LAYER0, st, nullptr, 0, true, &sc, g)) != CSM_OK) return rc;
+    for (int i = 0; i < g; ++i) {
+      mtc::k_round_tf32<<<(unsigned)((L * 512 + 255) / 256), 256, 0, st>>>(bxs + (size_t)i * L * 512, x->bt_xr + i * slot + (size_t)PAD * 512, L * 512);
+      csm_count_launches(1);
+    }
+    for (int i = 0; i < g; ++i) {
+      MCU_TRY(cudaMemsetAsync(x->own_state, 0, SL.kv[0] * sizeof(float), st));  // e_prev (the K/V history is not used here)
+      MCU_TRY(cudaMemsetAsync(x->own_state + SL.xs_tail, 0, (SL.total - SL.xs_tail) * sizeof(float), st));
+      if ((rc = decode_seanet_tc(x, x->own_state, x->bt_xr + i * slot + (size_t)PAD * 512, L, out + (size_t)(b0 + i) * 1920 * T, st)) != CSM_OK) return rc;
+    }
+  }
+  return CSM_OK;
+}
+
 extern "C" int32_t mimi_decode(mimi_ctx* x, const int64_t* codes, int32_t B, int32_t K, int32_t T, float* out, void* stream) {
   if (!x) return csm_set_error(CSM_ERR_STATE, "mimi_decode: null context");
   if (!codes || !out || B < 1 || K < 1 || K > 32 || T < 1) return csm_set_error(CSM_ERR_ARG, "mimi_decode: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   const StateLayout SL = state_layout();
+  static const bool batch_on = !(getenv("MIMI_BATCH") && getenv("MIMI_BATCH")[0] == '0');  // measurement aid
+  if (x->tc && B > 1 && T <= x->max_frames && batch_on) return decode_batch_tc(x, codes, B, K, T, out, st);
   // any length: windows of at most max_frames frames, the causal left context carried between them
   // (moshi's MimiModel.decode has no length limit either)
   for (int b = 0; b < B; ++b) {

@@ -318,7 +318,8 @@ __global__ void __launch_bounds__(256) k_layernorm512(const float* __restrict__ 
 
 // interleaved RoPE (moshi apply_rope, max_period 10000) in place on the q and k thirds of qkv [L, 1536]
 // rows [0, L) of ``qkv`` are absolute positions pos0 .. pos0 + L - 1
-__global__ void k_rope_qk(float* __restrict__ qkv, int L, long long pos0) {
+// period > 0: the rows are several utterances of ``period`` rows each, every one starting at position pos0
+__global__ void k_rope_qk(float* __restrict__ qkv, int L, long long pos0, int period = 0) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // (t, which, head, pair)
   if (i >= (long long)L * 2 * 8 * 32) return;
   const int pair = i & 31;
@@ -327,7 +328,7 @@ __global__ void k_rope_qk(float* __restrict__ qkv, int L, long long pos0) {
   const long long t = i >> 9;
   const float freq = expf((float)pair * (-9.210340371976184f * 2.0f / 64.0f));  // ln(10000)
   float sn, cs;
-  sincosf(freq * (float)(pos0 + t), &sn, &cs);
+  sincosf(freq * (float)(pos0 + (period > 0 ? t % period : t)), &sn, &cs);
   float* p = qkv + t * 1536 + which * 512 + head * 64 + pair * 2;
   const float xr = p[0], xi = p[1];
   p[0] = xr * cs - xi * sn;
@@ -412,6 +413,9 @@ __device__ __forceinline__ uint32_t tf32u(float x) {
 __global__ void __launch_bounds__(128) k_attn_window_tc(const float* __restrict__ qkv, int L, int context, float* __restrict__ out,
                                                         int hist, long long abs0, int round) {
   extern __shared__ __align__(16) float at_smem[];
+  // blockIdx.z: utterance of a batched one-shot decode (hist == 0), L rows each
+  qkv += (long long)blockIdx.z * L * 1536;
+  out += (long long)blockIdx.z * L * 512;
   float* Qs = at_smem;                 // [64][AT_LD]
   float* Ks = Qs + 64 * AT_LD;
   float* Vs = Ks + 64 * AT_LD;

@@ -94,6 +94,7 @@ PROTOTYPES = {
     "csm_abi_version": (C.c_int32, []),
     "csm_last_error": (C.c_char_p, []),
     "csm_launch_count": (C.c_uint64, []),
+    "csm_debug_set_pdl": (None, [C.c_int32]),
     "csm_workspace_bytes": (C.c_size_t, [C.POINTER(Config), C.c_int32]),
     "csm_create": (C.c_int32, [C.POINTER(Config), C.POINTER(Weights), C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p,
                                C.POINTER(C.c_void_p)]),

@@ -60,6 +60,11 @@ def test_decode_is_chunk_additive_in_batch(codecs):
     full = pc.decode(codes)
     for b in range(4):
         assert torch.equal(full[b], pc.decode(codes[b : b + 1])[0])
+    # more utterances than one transformer batch holds (groups of 8 + 3), > 64 positions (several attention tiles)
+    codes = syn.hash_ints(11 * 32 * 40, 5, 7, 2048).view(11, 32, 40).cuda()
+    full = pc.decode(codes)
+    for b in range(11):
+        assert torch.equal(full[b], pc.decode(codes[b : b + 1])[0]), b
 
 
 def test_decode_longer_than_the_workspace_runs_in_windows(codecs):
