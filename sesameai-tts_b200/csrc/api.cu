@@ -1218,12 +1218,21 @@ static int linear_rows(csm_ctx* x, const bf16* W, const bf16* Wf, int R, const b
   if (skinny_ok(x, Wf, N, K)) return launch_skinny(Wf, R, X, ldx, N, K, n_out, out, ldo, epi, resid, st);
   return launch_gemm_tc(X, ldx, N, K, W, n_out, out, ldo, epi, resid, st, x);
 }
+// rows up to which the skinny kernel normalises its activation rows itself (CSM_SKINNY_NORM_ROWS: measurement aid)
+static int skinny_norm_rows() {
+  static const int n = [] {
+    const char* e = getenv("CSM_SKINNY_NORM_ROWS");
+    const int v = e ? atoi(e) : 16;
+    return v < 0 ? 0 : (v > 64 ? 64 : v);
+  }();
+  return n;
+}
 // RMSNorm(H rows) followed by a linear layer: fused into the skinny kernel for few rows, else k_rmsnorm into
 // ``xn`` (skipped when ``xn_ready``: an earlier call of the same pair normalised already) and the tcgen05 GEMM
 static int norm_linear_rows(csm_ctx* x, const bf16* H, const bf16* scale, float eps, bf16* xn, bool xn_ready, const bf16* W,
                             const bf16* Wf, int R, int N, int K, int n_out, bf16* out, long long ldo, int epi, cudaStream_t st) {
   // (every CTA normalises all rows itself: cheaper than a launch up to 16 rows, measured slower at 32)
-  if (skinny_ok(x, Wf, N, K) && N <= 16) return launch_skinny(Wf, R, H, K, N, K, n_out, out, ldo, epi, nullptr, st, scale, eps);
+  if (skinny_ok(x, Wf, N, K) && N <= skinny_norm_rows()) return launch_skinny(Wf, R, H, K, N, K, n_out, out, ldo, epi, nullptr, st, scale, eps);
   if (!xn_ready) {
     launch_k(k_rmsnorm, dim3(N), dim3(256), 0, st, H, K, scale, K, eps, xn, K); COUNT_LAUNCH();
   }
@@ -1248,7 +1257,7 @@ static int stack_pass_tc(csm_ctx* x, StackDev& s, int N, const RowMeta& m, cudaS
       memset(&ra, 0, sizeof(ra));
       ra.rope = s.rope; ra.row_stream = m.stream; ra.row_pos = m.pos; ra.row_slot = m.slot; ra.imp_B = m.imp_B; ra.imp_pos = m.imp_pos;
       ra.heads = k.heads; ra.kv_heads = k.kv_heads; ra.hd = s.hd; ra.slots = s.slots; ra.k_cache = kc; ra.v_cache = vc;
-      const bool fuse_norm = N <= 16;
+      const bool fuse_norm = N <= skinny_norm_rows();
       if (!fuse_norm) {
         launch_k(k_rmsnorm, dim3(N), dim3(256), 0, st, s.h, D, s.sa[l], D, eps, s.xn, D); COUNT_LAUNCH();
       }

@@ -282,14 +282,17 @@ static int gemm_tc_r(cudaStream_t st, const float* A, long long lda, int cin, in
   const bool resid = (ep.flags & mtc::F_RESID) != 0;
   // shared memory: weights + staging tile, then residual tiles (up to 3 in flight) and A stages (up to 8) as they fit
   int stages = 0, nres = 0;
+  // tap-shift mode: every 32-channel block of the 128 + taps - 1 activation rows of a tile is loaded once
+  static const bool shift_on = !(getenv("MIMI_TAPSHIFT") && getenv("MIMI_TAPSHIFT")[0] == '0');
+  const bool shift = shift_on && taps > 1 && taps <= 8 && lda == cin;
   if ((N == 32 || N == 64 || N == 128) && !ep.C2 && !(ep.flags & (mtc::F_GELU | mtc::F_LAYERSCALE)) &&
-      mtc::r_smem_bytes(K, N, 2, resid ? 1 : 0) <= budget && (!fin || (N == 64 && resid && M % mtc::BM == 0))) {
+      mtc::r_smem_bytes(K, N, 2, resid ? 1 : 0, shift) <= budget && (!fin || (N == 64 && resid && M % mtc::BM == 0))) {
     if (resid) {
       nres = mtc::R_MAX_RES;
-      while (nres > 1 && mtc::r_smem_bytes(K, N, 3, nres) > budget) --nres;
+      while (nres > 1 && mtc::r_smem_bytes(K, N, 3, nres, shift) > budget) --nres;
     }
     stages = mtc::R_MAX_STAGES;
-    while (stages > 2 && mtc::r_smem_bytes(K, N, stages, nres) > budget) --stages;
+    while (stages > 2 && mtc::r_smem_bytes(K, N, stages, nres, shift) > budget) --stages;
   }
   if (stages < 2 || (!g_mimi_resident && !fin)) {
     if (fin) return csm_set_error(CSM_ERR_ARG, "mimi gemm_tc_r: the fused final conv needs the weight-resident kernel");
@@ -316,7 +319,16 @@ static int gemm_tc_r(cudaStream_t st, const float* A, long long lda, int cin, in
     attr[dev] = true;
   }
   CUtensorMap ma, mb;
-  {
+  if (shift) {
+    // the activation itself, [M + taps - 1 rows, cin]: a stage = 136 rows x 32 channels starting at the tile's first row
+    cuuint64_t gdim[2] = {(cuuint64_t)cin, (cuuint64_t)(M + taps - 1)};
+    cuuint64_t gstr[1] = {(cuuint64_t)lda * 4};
+    cuuint32_t box[2] = {(cuuint32_t)mtc::BK, 136};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&ma, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)A, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return csm_set_error(CSM_ERR_CUDA, "cuTensorMapEncodeTiled (A, tap-shift) failed");
+  } else {
     cuuint64_t gdim[3] = {(cuuint64_t)cin, (cuuint64_t)taps, (cuuint64_t)M};
     cuuint64_t gstr[2] = {(cuuint64_t)lda * 4, (cuuint64_t)lda * 4};
     cuuint32_t box[3] = {(cuuint32_t)mtc::BK, 1, (cuuint32_t)mtc::BM};
@@ -353,10 +365,11 @@ static int gemm_tc_r(cudaStream_t st, const float* A, long long lda, int cin, in
   if (ra.e.bias_period < 1) ra.e.bias_period = 1;
   ra.stages = stages;
   ra.nres = nres;
+  ra.taps = shift ? taps : 0;
   const long long tiles = (M + mtc::BM - 1) / mtc::BM;
   const int nsm = sms[dev] > 0 ? sms[dev] : 148;
   const unsigned grid = (unsigned)(tiles < nsm ? tiles : nsm);
-  kerns[ki]<<<grid, mtc::R_THREADS, mtc::r_smem_bytes(K, N, stages, nres), st>>>(ma, mb, mr, ra, cin);
+  kerns[ki]<<<grid, mtc::R_THREADS, mtc::r_smem_bytes(K, N, stages, nres, shift), st>>>(ma, mb, mr, ra, cin);
   csm_count_launches(1);
   MCU_TRY(cudaGetLastError());
   return CSM_OK;

@@ -94,6 +94,14 @@ __device__ __forceinline__ uint64_t smem_desc(const void* p) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// The same for an operand that starts ``rows`` rows into a 1024-byte-aligned swizzled block: only the start address
+// moves (rows * 128 bytes).  The 128-byte swizzle is a function of the shared-memory ADDRESS (chunk index xor
+// address bits 7-9), the same function TMA applied when it wrote the block, so a row-shifted view reads the right
+// chunks.  Measured on B200: with the descriptor's base-offset field set to the row phase the product is wrong
+// (SNR 3 dB), with the field left 0 it is exact (profiles/r2_mimi.txt).
+__device__ __forceinline__ uint64_t smem_desc_rows(const void* block, int rows) {
+  return smem_desc(reinterpret_cast<const unsigned char*>(block) + rows * 128);
+}
 // instruction descriptor: D fp32, A / B TF32 (format 2), both K-major
 __device__ __forceinline__ uint32_t instr_desc(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
@@ -327,6 +335,10 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ C
 //   * the residual operand of a tile (128 x N fp32, 32 KB at N = 64) comes through TMA as well, into a ring of its
 //     own that the producer fills tiles ahead: loaded by the epilogue threads it was 16 KB in flight per SM behind
 //     a dependent HBM round trip per tile, and that -- not the tensor core, not the A stream -- was the run time;
+//   * tap-shift mode (Conv1d k = 3; ra.taps > 1): the taps of a conv read the SAME activation rows, shifted by one
+//     row each.  Instead of one A box per (tap, 32 channels) -- every row crossing L2 -> shared memory three times --
+//     a stage holds the 128 + taps - 1 rows of a 32-channel block once (map_a is then a plain 2-d map of the
+//     activation) and the MMAs of tap t read it through a descriptor that starts t rows in (smem_desc_rows);
 //   * fused final convolution (stage-3 residual conv, N = 64; fw != null): the decoder ends in Conv1d(64 -> 1,
 //     k = 3) over ELU(y).  While a thread holds four ELU'd columns of a row it forms their products with the three
 //     taps, the 16 lanes of the row add them up (xor shuffles, fixed order), and sample t of the waveform is
@@ -345,6 +357,7 @@ struct RArgs {
   Args e;             // N = the whole output width; C2 / GELU / LayerScale are not supported here
   int stages;         // depth of the A ring
   int nres;           // depth of the residual ring (0: no residual)
+  int taps;           // > 1: tap-shift mode (see k_gemm_tf32_r) with this many taps; else 0
   const float* fw;    // fused final conv: weights [3][64] tap-major, or null (needs N == 64, M % 128 == 0)
   float fb;           // its bias
   float* wav;         // [M], zero-initialised
@@ -352,8 +365,10 @@ struct RArgs {
   float* tail;        // [2][64] receives ELU'd rows M-2, M-1 (or null)
 };
 
-__host__ __device__ constexpr size_t r_smem_bytes(int K, int N, int stages, int nres) {
-  return (size_t)K * N * 4 + (size_t)stages * A_STAGE_BYTES + (size_t)BM * (N + 4) * 4 + (size_t)nres * BM * N * 4 +
+// tap-shift stage: 128 + taps - 1 (<= 136) rows of 32 channels
+constexpr uint32_t A_SHIFT_STAGE_BYTES = 136 * BK * 4;
+__host__ __device__ constexpr size_t r_smem_bytes(int K, int N, int stages, int nres, bool shift = false) {
+  return (size_t)K * N * 4 + (size_t)stages * (shift ? A_SHIFT_STAGE_BYTES : A_STAGE_BYTES) + (size_t)BM * (N + 4) * 4 + (size_t)nres * BM * N * 4 +
          3 * BM * 4 /*row sums of the fused conv*/ + 1024 /*align*/ + 256 /*barriers*/;
 }
 
@@ -382,12 +397,15 @@ k_gemm_tf32_r(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr int tld = NB + 4;
   const int stages = ra.stages, nres = RESID ? ra.nres : 0;
+  const int taps = ra.taps > 1 ? ra.taps : 0;
+  const uint32_t a_stage = taps ? A_SHIFT_STAGE_BYTES : A_STAGE_BYTES;
+  const int num_ab = taps ? cin / BK : a.K / BK;  // A stages per tile
   const int num_kb = a.K / BK;
   constexpr uint32_t b_kb_bytes = (uint32_t)NB * BK * 4;  // one k block of the weights: NB rows of 128 bytes
   constexpr uint32_t r_bytes = (uint32_t)BM * NB * 4;     // one residual tile, dense rows
   unsigned char* bres = smem;
   unsigned char* ring = bres + (size_t)num_kb * b_kb_bytes;
-  float* tile = reinterpret_cast<float*>(ring + (size_t)stages * A_STAGE_BYTES);
+  float* tile = reinterpret_cast<float*>(ring + (size_t)stages * a_stage);
   unsigned char* rring = reinterpret_cast<unsigned char*>(tile) + (size_t)BM * tld * 4;
   float* psum = reinterpret_cast<float*>(rring + (size_t)nres * r_bytes);  // [3][BM]
   uint64_t* full = reinterpret_cast<uint64_t*>(psum + 3 * BM);
@@ -448,11 +466,12 @@ k_gemm_tf32_r(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
           tma_load_2d(rring + (size_t)rs * r_bytes, &map_r, &r_full[rs], 0, m0);
           if (++rs == nres) { rs = 0; rph ^= 1; }
         }
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int ab = 0; ab < num_ab; ++ab) {
           mbar_wait(&empty[s], ph);
-          mbar_expect(&full[s], A_STAGE_BYTES);
-          const int k = kb * BK;
-          tma_load_3d(ring + (size_t)s * A_STAGE_BYTES, &map_a, &full[s], k % cin, k / cin, m0);
+          mbar_expect(&full[s], a_stage);
+          const int k = ab * BK;
+          if (taps) tma_load_2d(ring + (size_t)s * a_stage, &map_a, &full[s], k, m0);  // rows m0 .. m0 + 135 of channel block ab
+          else tma_load_3d(ring + (size_t)s * a_stage, &map_a, &full[s], k % cin, k / cin, m0);
           if (++s == stages) { s = 0; ph ^= 1; }
         }
       }
@@ -469,13 +488,23 @@ k_gemm_tf32_r(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc = tmem_base + buf * NB;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int ab = 0; ab < num_ab; ++ab) {
           mbar_wait(&full[s], ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t ad = smem_desc(ring + (size_t)s * A_STAGE_BYTES), bd = smem_desc(bres + (size_t)kb * b_kb_bytes);
+          const unsigned char* sa = ring + (size_t)s * a_stage;
+          if (taps) {
+            for (int t = 0; t < taps; ++t) {  // K index of the weights = tap * cin + channel
+              const uint64_t ad = smem_desc_rows(sa, t), bd = smem_desc(bres + (size_t)(t * num_ab + ab) * b_kb_bytes);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_tf32(acc, ad + (uint64_t)(k * UMMA_K * 4 >> 4), bd + (uint64_t)(k * UMMA_K * 4 >> 4), idesc, (kb | k) != 0);
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_tf32(acc, ad + (uint64_t)(k * UMMA_K * 4 >> 4), bd + (uint64_t)(k * UMMA_K * 4 >> 4), idesc, (ab | t | k) != 0);
+            }
+          } else {
+            const uint64_t ad = smem_desc(sa), bd = smem_desc(bres + (size_t)ab * b_kb_bytes);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_tf32(acc, ad + (uint64_t)(k * UMMA_K * 4 >> 4), bd + (uint64_t)(k * UMMA_K * 4 >> 4), idesc, (ab | k) != 0);
+          }
           umma_commit(&empty[s]);
           if (++s == stages) { s = 0; ph ^= 1; }
         }
