@@ -47,16 +47,30 @@ static bool pdl_enabled() {
 }
 // test hook: contexts created afterwards capture their graphs with (1) / without (0) programmatic edges
 extern "C" void csm_debug_set_pdl(int32_t on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
+// cluster_z > 1: the z extent of the grid is launched as one thread-block cluster (split-K through DSMEM)
 template <typename... P, typename... A>
-static void launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+static void launch_kc(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_z, A&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_z > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = 1; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = (unsigned)cluster_z;
+    ++n;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
   (void)cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);  // failures surface through cudaGetLastError()
+}
+template <typename... P, typename... A>
+static void launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  launch_kc(kern, grid, block, smem, st, 1, static_cast<A&&>(args)...);
 }
 
 struct csm_ctx;
@@ -1147,7 +1161,7 @@ static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const b
   if ((rc = make_map_bf16(&mw, W, n_out, K, K, tc::BN)) != CSM_OK) return rc;
   tc::Args a;
   a.out = out; a.ldo = ldo; a.resid = resid ? resid : out; a.rows = rows; a.n_out = n_out; a.K = K; a.epi = epi;
-  a.part = nullptr; a.counters = nullptr; a.ldp = 0;
+  a.part = nullptr; a.counters = nullptr; a.ldp = 0; a.cluster = 0;
   dim3 grid((n_out + tc::BN - 1) / tc::BN, (rows + tc::BM - 1) / tc::BM);
   // decode steps of large batches: few tiles, long K -> split K over the idle SMs (see gemm_tc.cuh)
   const int tiles = (int)(grid.x * grid.y), num_kb = K / tc::BK;
@@ -1165,9 +1179,35 @@ static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const b
       a.part = splitk->tc_part; a.counters = splitk->tc_counters; a.ldp = (long long)grid.x * tc::BN;
     }
   }
+  // Cluster split-K (default for decode-sized GEMMs): a projection of a 256-stream decode step is 16 .. 34 tiles of
+  // 16 .. 128 k blocks -- a handful of CTAs, each a chain of dependent TMA round trips (the 16-tile K = 8192 down
+  // projection took 62 us, profiles/r2_decode_B256_shapes.txt).  The k blocks of a tile are split over a thread-block
+  // cluster of 2 / 4 / 8 CTAs that add their partial tiles up through distributed shared memory.
+  static const bool cluster_on = !(getenv("CSM_TC_CLUSTER") && getenv("CSM_TC_CLUSTER")[0] == '0');
+  int cluster_z = 1;
+  // (K = 1024 projections, 16 k blocks: under ncu the cluster's fixed cost cancels the shorter k loop, in the replayed
+  //  graph splitting them too is 2-4 % faster per step at 128 / 256 streams: profiles/r2_cluster_splitk.txt)
+  static const int cluster_min_kb = getenv("CSM_TC_CLUSTER_MIN_KB") ? atoi(getenv("CSM_TC_CLUSTER_MIN_KB")) : 16;
+  if (cluster_on && grid.z == 1 && rows <= TC_SPLIT_MAX_ROWS && num_kb >= cluster_min_kb) {
+    int sp = 8;
+    while (sp > 1 && (sp * tiles > TC_SPLIT_TILES || num_kb % sp || num_kb / sp < 4)) sp >>= 1;
+    if (sp > 1) {
+      cluster_z = sp;
+      grid.z = sp;
+      a.cluster = 1;
+    }
+  }
   static const bool old_kernel = getenv("CSM_TC_ONE_TILE") != nullptr;  // measurement aid: round 1's one-tile-per-CTA kernel
-  if (grid.z > 1 || old_kernel) {
-    launch_k(tc::k_gemm_tc, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, mx, mw, a); COUNT_LAUNCH();
+  static std::atomic<int> nsm_cached{0};
+  if (!nsm_cached.load(std::memory_order_relaxed)) {
+    int dev = 0, n = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    CU_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    nsm_cached.store(n > 0 ? n : 148, std::memory_order_relaxed);
+  }
+  // (one tile per CTA also when every tile gets its own SM: its ring is six stages deep, the persistent kernel's four)
+  if (grid.z > 1 || old_kernel || tiles <= nsm_cached.load(std::memory_order_relaxed)) {
+    launch_kc(tc::k_gemm_tc, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, cluster_z, mx, mw, a); COUNT_LAUNCH();
   } else {
     // persistent kernel: one CTA per SM walks the tiles
     static std::atomic<unsigned long long> attr_p{0};
@@ -1280,6 +1320,10 @@ static int stack_pass_tc(csm_ctx* x, StackDev& s, int N, const RowMeta& m, cudaS
       } else if (s.hd == 64) {
         launch_k(k_attn_rows<64>, dim3(grid), dim3(128), smem, st, s.q, kc, vc, m.stream, m.slot, m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.slots,
                                                  scale, s.att);
+      } else if (s.hd == 128 && s.slots <= 32 && k.heads % k.kv_heads == 0 && k.heads / k.kv_heads <= 8) {
+        // depth decoder: one CTA per (row, KV head), its q-heads share the staged K / V rows
+        launch_k(k_attn_dec, dim3(N, k.kv_heads), dim3(32 * (k.heads / k.kv_heads)), 0, st, s.q, kc, vc, m.stream, m.slot, m.imp_B,
+                 m.imp_pos, k.heads, k.kv_heads, s.slots, scale, s.att);
       } else {
         launch_k(k_attn_rows<128>, dim3(grid), dim3(128), smem, st, s.q, kc, vc, m.stream, m.slot, m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.slots,
                                                   scale, s.att);

@@ -43,6 +43,7 @@ struct Args {
   float* part;             // [splits][m_tiles * BM][ldp] fp32 partial tiles
   unsigned int* counters;  // [m_tiles * n_tiles], zero between launches (the last CTA of a tile resets its counter)
   long long ldp;           // n_tiles * BN
+  int cluster;             // gridDim.z > 1 with the z extent launched as ONE thread-block cluster: slices meet through DSMEM
 };
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -109,6 +110,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+// thread-block cluster helpers (split-K through distributed shared memory)
+__device__ __forceinline__ void cluster_sync_all() {
+  __syncwarp();  // (.aligned: the warp must be converged; the TMA / MMA warps come here from single-lane branches)
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t dsmem_addr(const void* local, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(s32(local)), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ float4 dsmem_ld4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+constexpr int CK_LD = BN + 4;  // padded fp32 row of a slice's partial tile in shared memory
 
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, Args a) {
@@ -187,7 +205,22 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
     mbar_wait(acc_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     bool finish = true;  // this CTA runs the epilogue (always, without split-K)
-    if (splits > 1) {
+    if (a.cluster) {
+      // Cluster split-K: the z extent of the grid is one thread-block cluster, CTA z accumulated k slice z.  Every
+      // CTA parks its fp32 partial tile in its own shared memory (the operand ring is drained: all MMAs have
+      // completed), the cluster meets, and CTA z adds rows [z * 128 / splits, ...) of all slices in slice order
+      // through distributed shared memory -- no global partials, no counters, no last-CTA pass.
+      float* ptile = reinterpret_cast<float*>(smem);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        float* trow = ptile + (size_t)(q * 32 + lane) * CK_LD + c0;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(trow + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+      finish = false;
+    } else if (splits > 1) {
       // 1. park the fp32 partial tile (one 128-byte line per lane and step)
       float* prow = a.part + ((size_t)blockIdx.z * gridDim.y * BM + (m0 - 0) + q * 32 + lane) * a.ldp + n0;
 #pragma unroll 1
@@ -302,6 +335,42 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
       }
     }
     }
+  }
+  if (a.cluster) {
+    cluster_sync_all();  // every slice's partial tile is in its CTA's shared memory
+    if (warp >= 2) {
+      const float* ptile = reinterpret_cast<const float*>(smem);
+      const int et = threadIdx.x - 64;  // 0 .. 127
+      const int rows_per = BM / splits;
+      const int n = n0 + (et & 31) * 4;
+#pragma unroll 1
+      for (int r = (int)blockIdx.z * rows_per + (et >> 5); r < ((int)blockIdx.z + 1) * rows_per; r += 4) {
+        const float* lp = ptile + (size_t)r * CK_LD + (et & 31) * 4;  // the same offset in every CTA of the cluster
+        float4 t[8];  // all slices' loads go out together (a DSMEM round trip each), then they are added in slice order
+#pragma unroll
+        for (int z = 0; z < 8; ++z)
+          if (z < splits) t[z] = dsmem_ld4(dsmem_addr(lp, (uint32_t)z));
+        float4 acc = t[0];
+#pragma unroll
+        for (int z = 1; z < 8; ++z)
+          if (z < splits) { acc.x += t[z].x; acc.y += t[z].y; acc.z += t[z].z; acc.w += t[z].w; }
+        const int rr = m0 + r;
+        if (rr >= a.rows) continue;
+        const float y[4] = {rbf(acc.x), rbf(acc.y), rbf(acc.z), rbf(acc.w)};
+        if (a.epi == EPI_SWIGLU_PAIRS) {
+          bf16* o = a.out + (long long)rr * a.ldo + (n >> 1);
+          if (n + 1 < a.n_out) o[0] = f2bf(silu_bf(y[0]) * y[1]);
+          if (n + 3 < a.n_out) o[1] = f2bf(silu_bf(y[2]) * y[3]);
+        } else {
+          bf16* o = a.out + (long long)rr * a.ldo + n;
+          const bf16* rs = a.resid + (long long)rr * a.ldo + n;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (n + j < a.n_out) o[j] = f2bf(a.epi == EPI_ADD_RESID ? y[j] + bf2f(rs[j]) : y[j]);
+        }
+      }
+    }
+    cluster_sync_all();  // nobody leaves (or frees its shared memory) while a peer still reads it
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();

@@ -398,6 +398,70 @@ __global__ void __launch_bounds__(128) k_attn_rows(const bf16* __restrict__ q, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// K3 (depth decoder, row-batched path): head_dim 128 over a cache of <= 32 positions.  k_attn_rows spends a CTA of 128
+// threads on one (row, q-head): with <= 32 keys a quarter of them computes a 128-long dot product each from
+// scattered 16-byte loads, and 2048 such CTAs per launch took 22 us at 256 streams (12 % of the decode step).
+// Here one CTA serves a (row, KV head): the K / V rows are staged ONCE in shared memory (coalesced) for the
+// heads / kv_heads q-heads that share them, one warp per q-head: lane j scores key j (K rows padded to 130
+// bf16: conflict-free), the softmax is warp shuffles, lane l accumulates output dims 4l .. 4l+3.  Every sum runs
+// in the order k_attn_rows uses (dims ascending, keys ascending, the same shuffle tree): bit-identical output.
+// ---------------------------------------------------------------------------------------------
+constexpr int AD_LD = 130;
+__global__ void __launch_bounds__(256) k_attn_dec(const bf16* __restrict__ q, const bf16* __restrict__ k_cache,
+                                                  const bf16* __restrict__ v_cache, const int* __restrict__ row_stream,
+                                                  const int* __restrict__ row_slot, int imp_B, int imp_pos, int heads,
+                                                  int kv_heads, int slots, float scale, bf16* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ __align__(16) bf16 Ks[32 * AD_LD];
+  __shared__ __align__(16) bf16 Vs[32 * 128];
+  __shared__ float qs[8][128];
+  const int n = blockIdx.x, kvh = blockIdx.y, gq = heads / kv_heads;  // launched with 32 * gq threads, gq <= 8
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkeys = (row_stream ? row_slot[n] : imp_pos + n / imp_B) + 1;  // <= 32
+  const size_t base = ((size_t)(row_stream ? row_stream[n] : n % imp_B) * kv_heads + kvh) * slots * 128;
+  for (int u = threadIdx.x; u < nkeys * 16; u += blockDim.x) {
+    const int r = u >> 4, c8 = (u & 15) * 8;
+    const uint4 kv = *reinterpret_cast<const uint4*>(k_cache + base + (size_t)r * 128 + c8);
+    uint32_t* kd = reinterpret_cast<uint32_t*>(Ks + r * AD_LD + c8);  // (4-byte aligned: AD_LD and c8 are even)
+    kd[0] = kv.x; kd[1] = kv.y; kd[2] = kv.z; kd[3] = kv.w;
+    *reinterpret_cast<uint4*>(Vs + r * 128 + c8) = *reinterpret_cast<const uint4*>(v_cache + base + (size_t)r * 128 + c8);
+  }
+  const int h = kvh * gq + warp;
+  {
+    const uint2 v = *reinterpret_cast<const uint2*>(q + ((size_t)n * heads + h) * 128 + lane * 4);
+    qs[warp][lane * 4 + 0] = bflo(v.x); qs[warp][lane * 4 + 1] = bfhi(v.x);
+    qs[warp][lane * 4 + 2] = bflo(v.y); qs[warp][lane * 4 + 3] = bfhi(v.y);
+  }
+  __syncthreads();
+  float sc = -INFINITY;
+  if (lane < nkeys) {
+    const uint32_t* kr = reinterpret_cast<const uint32_t*>(Ks + lane * AD_LD);
+    const float* qr = qs[warp];
+    float s = 0.f;
+#pragma unroll 16
+    for (int i = 0; i < 64; ++i) {
+      const uint32_t kk = kr[i];
+      s = fmaf(qr[2 * i], bflo(kk), s);
+      s = fmaf(qr[2 * i + 1], bfhi(kk), s);
+    }
+    sc = s * scale;
+  }
+  const float mx = warp_max(sc);
+  const float e = lane < nkeys ? expf(sc - mx) : 0.f;
+  const float inv = 1.0f / warp_sum(e);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j < nkeys; ++j) {
+    const float p = __shfl_sync(0xffffffffu, e, j);
+    const uint2 v = *reinterpret_cast<const uint2*>(Vs + j * 128 + lane * 4);
+    acc[0] = fmaf(p, bflo(v.x), acc[0]); acc[1] = fmaf(p, bfhi(v.x), acc[1]);
+    acc[2] = fmaf(p, bflo(v.y), acc[2]); acc[3] = fmaf(p, bfhi(v.y), acc[3]);
+  }
+  __nv_bfloat162 o[2] = {__floats2bfloat162_rn(acc[0] * inv, acc[1] * inv), __floats2bfloat162_rn(acc[2] * inv, acc[3] * inv)};
+  *reinterpret_cast<uint2*>(out + ((size_t)n * heads + h) * 128 + lane * 4) = *reinterpret_cast<uint2*>(o);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K3 (prompt prefill): tiled causal attention on the tensor cores, head_dim 64.
 // One CTA = 64 consecutive prompt rows of one stream x one q-head; 4 warps x 16 rows.  Key tiles of
 // 64 cache rows are double-buffered in shared memory with cp.async; S = Q K^T and O += P V are
