@@ -74,8 +74,10 @@ static void launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cud
 }
 
 struct csm_ctx;
+namespace tc { struct RopeKV; }
 static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const bf16* W, int n_out, bf16* out, long long ldo,
-                          int epi, const bf16* resid, cudaStream_t st, const csm_ctx* splitk = nullptr);
+                          int epi, const bf16* resid, cudaStream_t st, const csm_ctx* splitk = nullptr,
+                          const tc::RopeKV* rk = nullptr, bool* rk_fused = nullptr);
 
 // shared with mimi_api.cu
 int csm_set_error(int code, const char* msg) { return set_err(code, "%s", msg); }
@@ -93,8 +95,8 @@ static int skinny_max_rows() {  // rows up to which a linear layer runs on the s
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("CSM_SKINNY_MAX_ROWS");
-    v = e ? atoi(e) : 64;
-    if (v < 0 || v > 64) v = 64;
+    v = e ? atoi(e) : 32;  // (33 .. 64 rows: the tcgen05 GEMM with cluster split-K is faster -- 64 streams 12.3 -> 9.3 ms per step)
+    if (v < 0 || v > 64) v = 32;
   }
   return v;
 }
@@ -1147,8 +1149,11 @@ static int make_map_bf16(CUtensorMap* m, const bf16* base, long long rows, long 
   if (r != CUDA_SUCCESS) return set_err(CSM_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   return CSM_OK;
 }
+// rk / rk_fused: the caller's RoPE + KV-append step; *rk_fused says whether this launch did it in its epilogue (only
+// the cluster split-K path can) -- otherwise the projection is in ``out`` and the caller runs k_rope_kv_rows
 static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const bf16* W, int n_out, bf16* out, long long ldo,
-                          int epi, const bf16* resid, cudaStream_t st, const csm_ctx* splitk) {
+                          int epi, const bf16* resid, cudaStream_t st, const csm_ctx* splitk, const tc::RopeKV* rk, bool* rk_fused) {
+  if (rk_fused) *rk_fused = false;
   if (K % tc::BK || rows < 1 || n_out < 1) return set_err(CSM_ERR_ARG, "gemm_tc: K must be a multiple of 64");
   static std::atomic<unsigned long long> attr{0};
   if (!device_done(attr, false)) {
@@ -1205,22 +1210,42 @@ static int launch_gemm_tc(const bf16* X, long long ldx, int rows, int K, const b
     CU_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
     nsm_cached.store(n > 0 ? n : 148, std::memory_order_relaxed);
   }
+  const int nsm = nsm_cached.load(std::memory_order_relaxed);
+  // (Tried for the 256-tile gate/up of a 256-stream step: one CTA taking two stacked tiles against one W box per
+  //  k block, 128 CTAs x 48 KB per k block -- correct, and slower than the persistent kernel: 14.4 vs 12.8 ms per step.)
+  // RoPE + KV append of the [q;k;v] projection in the GEMM epilogue (tc::EPI_ROPE_KV: the persistent kernel and the
+  // cluster split-K reduce both walk the tile four columns per thread).  Correct (the GPU suite passes with it on) and
+  // measured SLOWER than the separate k_rope_kv_rows launch in both places -- 256-stream decode step 12.7 vs 12.1 ms,
+  // 32 x 1568-frame prefill 173.6 vs 169.2 ms: scattered cache stores and index arithmetic inside the GEMM's epilogue
+  // versus a cheap, perfectly parallel kernel hidden by the dependent launch.  Off unless CSM_TC_ROPE_FUSE=1 (persistent
+  // kernel) / 2 (both).
+  static const int rope_fuse = getenv("CSM_TC_ROPE_FUSE") ? atoi(getenv("CSM_TC_ROPE_FUSE")) : 0;
+  if (rk && rk_fused && rope_fuse > 0 && epi == tc::EPI_STORE && n_out % 4 == 0 && !old_kernel && a.part == nullptr &&
+      ((a.cluster && rope_fuse > 1) || (!a.cluster && tiles > nsm))) {
+    a.rk = *rk;
+    a.epi = tc::EPI_ROPE_KV;
+    *rk_fused = true;
+  }
   // (one tile per CTA also when every tile gets its own SM: its ring is six stages deep, the persistent kernel's four)
-  if (grid.z > 1 || old_kernel || tiles <= nsm_cached.load(std::memory_order_relaxed)) {
+  if (grid.z > 1 || old_kernel || tiles <= nsm) {
     launch_kc(tc::k_gemm_tc, dim3(grid), dim3(tc::THREADS), tc::SMEM_BYTES, st, cluster_z, mx, mw, a); COUNT_LAUNCH();
   } else {
-    // persistent kernel: one CTA per SM walks the tiles
+    // persistent kernel: one CTA per SM walks the tiles; 128 x 256 tiles when the output is wide enough (CSM_TC_BN=128: off)
     static std::atomic<unsigned long long> attr_p{0};
-    static int sms[64] = {0};
-    int dev = 0;
-    CU_TRY(cudaGetDevice(&dev));
     if (!device_done(attr_p, false)) {
-      CU_TRY(cudaFuncSetAttribute(tc::k_gemm_tc_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::P_SMEM_BYTES));
+      CU_TRY(cudaFuncSetAttribute(tc::k_gemm_tc_p<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::PCfg<128>::SMEM));
+      CU_TRY(cudaFuncSetAttribute(tc::k_gemm_tc_p<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::PCfg<256>::SMEM));
       device_done(attr_p, true);
     }
-    if (dev >= 0 && dev < 64 && !sms[dev]) CU_TRY(cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev));
-    const int nsm = (dev >= 0 && dev < 64 && sms[dev] > 0) ? sms[dev] : 148;
-    launch_k(tc::k_gemm_tc_p, dim3(tiles < nsm ? tiles : nsm), dim3(tc::P_THREADS), tc::P_SMEM_BYTES, st, mx, mw, a); COUNT_LAUNCH();
+    static const bool wide_on = !(getenv("CSM_TC_BN") && atoi(getenv("CSM_TC_BN")) == 128);
+    // (prompt-sized row counts only: for the 256-tile gate/up of a 256-stream decode step the narrow tile is 1 % faster)
+    if (wide_on && n_out >= 512 && rows > TC_SPLIT_MAX_ROWS) {
+      if ((rc = make_map_bf16(&mw, W, n_out, K, K, 256)) != CSM_OK) return rc;
+      const int tiles_w = (int)(((n_out + 255) / 256) * grid.y);
+      launch_k(tc::k_gemm_tc_p<256>, dim3(tiles_w < nsm ? tiles_w : nsm), dim3(tc::P_THREADS), tc::PCfg<256>::SMEM, st, mx, mw, a); COUNT_LAUNCH();
+    } else {
+      launch_k(tc::k_gemm_tc_p<128>, dim3(tiles < nsm ? tiles : nsm), dim3(tc::P_THREADS), tc::PCfg<128>::SMEM, st, mx, mw, a); COUNT_LAUNCH();
+    }
   }
   CU_TRY(cudaGetLastError());
   return CSM_OK;
@@ -1254,9 +1279,19 @@ static bool skinny_ok(const csm_ctx* x, const bf16* Wf, int N, int K) {
   return x->frag_ok && Wf && N <= SKINNY_MAX_ROWS && K % 256 == 0;
 }
 static int linear_rows(csm_ctx* x, const bf16* W, const bf16* Wf, int R, const bf16* X, long long ldx, int N, int K, int n_out,
-                       bf16* out, long long ldo, int epi, const bf16* resid, cudaStream_t st) {
+                       bf16* out, long long ldo, int epi, const bf16* resid, cudaStream_t st, const tc::RopeKV* rk = nullptr,
+                       bool* rk_fused = nullptr) {
+  if (rk_fused) *rk_fused = false;
   if (skinny_ok(x, Wf, N, K)) return launch_skinny(Wf, R, X, ldx, N, K, n_out, out, ldo, epi, resid, st);
-  return launch_gemm_tc(X, ldx, N, K, W, n_out, out, ldo, epi, resid, st, x);
+  return launch_gemm_tc(X, ldx, N, K, W, n_out, out, ldo, epi, resid, st, x, rk, rk_fused);
+}
+// RMSNorm of N rows: a warp per row when the row fits in registers (D = 1024 / 2048, 16-byte aligned), else a CTA per row
+static void launch_rmsnorm_rows(const bf16* x, int D, const bf16* scale, float eps, bf16* y, int N, cudaStream_t st) {
+  const bool vec = ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)scale) & 15) == 0);
+  if (vec && D == 1024) launch_k(k_rmsnorm_rows<4>, dim3((N + 7) / 8), dim3(256), 0, st, x, D, scale, eps, y, D, N);
+  else if (vec && D == 2048) launch_k(k_rmsnorm_rows<8>, dim3((N + 7) / 8), dim3(256), 0, st, x, D, scale, eps, y, D, N);
+  else launch_k(k_rmsnorm, dim3(N), dim3(256), 0, st, x, D, scale, D, eps, y, D);
+  COUNT_LAUNCH();
 }
 // rows up to which the skinny kernel normalises its activation rows itself (CSM_SKINNY_NORM_ROWS: measurement aid)
 static int skinny_norm_rows() {
@@ -1270,13 +1305,15 @@ static int skinny_norm_rows() {
 // RMSNorm(H rows) followed by a linear layer: fused into the skinny kernel for few rows, else k_rmsnorm into
 // ``xn`` (skipped when ``xn_ready``: an earlier call of the same pair normalised already) and the tcgen05 GEMM
 static int norm_linear_rows(csm_ctx* x, const bf16* H, const bf16* scale, float eps, bf16* xn, bool xn_ready, const bf16* W,
-                            const bf16* Wf, int R, int N, int K, int n_out, bf16* out, long long ldo, int epi, cudaStream_t st) {
+                            const bf16* Wf, int R, int N, int K, int n_out, bf16* out, long long ldo, int epi, cudaStream_t st,
+                            const tc::RopeKV* rk = nullptr, bool* rk_fused = nullptr) {
+  if (rk_fused) *rk_fused = false;
   // (every CTA normalises all rows itself: cheaper than a launch up to 16 rows, measured slower at 32)
   if (skinny_ok(x, Wf, N, K) && N <= skinny_norm_rows()) return launch_skinny(Wf, R, H, K, N, K, n_out, out, ldo, epi, nullptr, st, scale, eps);
   if (!xn_ready) {
-    launch_k(k_rmsnorm, dim3(N), dim3(256), 0, st, H, K, scale, K, eps, xn, K); COUNT_LAUNCH();
+    launch_rmsnorm_rows(H, K, scale, eps, xn, N, st);
   }
-  return linear_rows(x, W, Wf, R, xn, K, N, K, n_out, out, ldo, epi, nullptr, st);
+  return linear_rows(x, W, Wf, R, xn, K, N, K, n_out, out, ldo, epi, nullptr, st, rk, rk_fused);
 }
 
 // All layers of one stack on N rows with the tcgen05 GEMM: per layer RMSNorm -> GEMM [q;k;v] -> RoPE +
@@ -1299,15 +1336,21 @@ static int stack_pass_tc(csm_ctx* x, StackDev& s, int N, const RowMeta& m, cudaS
       ra.heads = k.heads; ra.kv_heads = k.kv_heads; ra.hd = s.hd; ra.slots = s.slots; ra.k_cache = kc; ra.v_cache = vc;
       const bool fuse_norm = N <= skinny_norm_rows();
       if (!fuse_norm) {
-        launch_k(k_rmsnorm, dim3(N), dim3(256), 0, st, s.h, D, s.sa[l], D, eps, s.xn, D); COUNT_LAUNCH();
+        launch_rmsnorm_rows(s.h, D, s.sa[l], eps, s.xn, N, st);
       }
       if ((rc = launch_skinny(s.fqkv[l], R4[0], fuse_norm ? s.h : s.xn, D, N, D, qkv_cols, s.q, 0, sk::EPI_ROPE_KV, nullptr, st,
                               fuse_norm ? s.sa[l] : nullptr, eps, &ra)) != CSM_OK) return rc;
     } else {
+      tc::RopeKV rk;
+      rk.rope = s.rope; rk.row_stream = m.stream; rk.row_pos = m.pos; rk.row_slot = m.slot; rk.imp_B = m.imp_B; rk.imp_pos = m.imp_pos;
+      rk.heads = k.heads; rk.kv_heads = k.kv_heads; rk.hd = s.hd; rk.slots = s.slots; rk.q_out = s.q; rk.k_cache = kc; rk.v_cache = vc;
+      bool fused = false;  // decode-sized row counts: RoPE + KV append run in the projection's cluster split-K epilogue
       if ((rc = norm_linear_rows(x, s.h, s.sa[l], eps, s.xn, false, s.wqkv[l], s.fqkv[l], R4[0], N, D, qkv_cols, s.qkv, qkv_cols,
-                                 tc::EPI_STORE, st)) != CSM_OK) return rc;
-      launch_k(k_rope_kv_rows, dim3(N), dim3(256), 0, st, s.qkv, s.rope, m.stream, m.pos, m.slot, m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.hd,
-                                        s.slots, s.q, kc, vc); COUNT_LAUNCH();
+                                 tc::EPI_STORE, st, &rk, &fused)) != CSM_OK) return rc;
+      if (!fused) {
+        launch_k(k_rope_kv_rows, dim3(N), dim3(256), 0, st, s.qkv, s.rope, m.stream, m.pos, m.slot, m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.hd,
+                 s.slots, s.q, kc, vc); COUNT_LAUNCH();
+      }
     }
     {
       dim3 grid(N, k.heads);

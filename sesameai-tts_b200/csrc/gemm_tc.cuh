@@ -31,7 +31,17 @@ constexpr int THREADS = 192;
 constexpr uint32_t STAGE_BYTES = (BM + BN) * BK * 2;
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
-enum { EPI_STORE = 0, EPI_ADD_RESID = 1, EPI_SWIGLU_PAIRS = 2 };
+enum { EPI_STORE = 0, EPI_ADD_RESID = 1, EPI_SWIGLU_PAIRS = 2, EPI_ROPE_KV = 3 };
+
+// EPI_ROPE_KV (cluster split-K epilogue of the fused [q;k;v] projection only): the arithmetic of k_rope_kv_rows --
+// rotate the (even, odd) pairs of q and k with the row's position, q -> q_out [rows, heads * hd], k / v -> the cache
+// at the row's slot -- without the round trip of the projection through global memory and without the launch.
+struct RopeKV {
+  const bf16* rope;
+  const int *row_stream, *row_pos, *row_slot;  // null: stream n % imp_B, position = slot = imp_pos + n / imp_B
+  int imp_B, imp_pos, heads, kv_heads, hd, slots;
+  bf16 *q_out, *k_cache, *v_cache;
+};
 
 struct Args {
   bf16* out;
@@ -44,6 +54,7 @@ struct Args {
   unsigned int* counters;  // [m_tiles * n_tiles], zero between launches (the last CTA of a tile resets its counter)
   long long ldp;           // n_tiles * BN
   int cluster;             // gridDim.z > 1 with the z extent launched as ONE thread-block cluster: slices meet through DSMEM
+  RopeKV rk;               // EPI_ROPE_KV
 };
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -127,6 +138,38 @@ __device__ __forceinline__ float4 dsmem_ld4(uint32_t addr) {
   return v;
 }
 constexpr int CK_LD = BN + 4;  // padded fp32 row of a slice's partial tile in shared memory
+
+// EPI_ROPE_KV for four consecutive columns n .. n+3 (two (even, odd) pairs) of output row rr; y = the bf16-rounded
+// projection values.  Same arithmetic as k_rope_kv_rows / the skinny kernel's epilogue.
+__device__ __forceinline__ void rope_kv_store4(const RopeKV& k, int rr, int n, int n_out, const float (&y)[4]) {
+  const int hd = k.hd, qrows = k.heads * hd, krows = k.kv_heads * hd;
+  const int pos = k.row_stream ? k.row_pos[rr] : k.imp_pos + rr / k.imp_B;
+  const int slot = k.row_stream ? k.row_slot[rr] : k.imp_pos + rr / k.imp_B;
+  const int stream = k.row_stream ? k.row_stream[rr] : rr % k.imp_B;
+#pragma unroll
+  for (int pr = 0; pr < 2; ++pr) {
+    const int r0 = n + 2 * pr;
+    if (r0 >= n_out) break;  // (n_out is even: whole pairs)
+    const float y0 = y[2 * pr], y1 = y[2 * pr + 1];
+    float o0 = y0, o1 = y1;
+    if (r0 < qrows + krows) {
+      const __nv_bfloat162 cs = *reinterpret_cast<const __nv_bfloat162*>(k.rope + ((size_t)pos * (hd / 2) + ((r0 % hd) >> 1)) * 2);
+      const float c = __low2float(cs), sn = __high2float(cs);
+      o0 = rbf(__fsub_rn(__fmul_rn(y0, c), __fmul_rn(y1, sn)));
+      o1 = rbf(__fadd_rn(__fmul_rn(y1, c), __fmul_rn(y0, sn)));
+    }
+    const __nv_bfloat162 ov = __floats2bfloat162_rn(o0, o1);
+    if (r0 < qrows) {
+      *reinterpret_cast<__nv_bfloat162*>(k.q_out + (size_t)rr * qrows + r0) = ov;
+    } else {
+      const bool isk = r0 < qrows + krows;
+      const int rl = r0 - (isk ? qrows : qrows + krows);
+      const int kvh = rl / hd, d = rl % hd;
+      bf16* dst = (isk ? k.k_cache : k.v_cache) + (((size_t)stream * k.kv_heads + kvh) * k.slots + slot) * hd + d;
+      *reinterpret_cast<__nv_bfloat162*>(dst) = ov;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, Args a) {
@@ -357,7 +400,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
         const int rr = m0 + r;
         if (rr >= a.rows) continue;
         const float y[4] = {rbf(acc.x), rbf(acc.y), rbf(acc.z), rbf(acc.w)};
-        if (a.epi == EPI_SWIGLU_PAIRS) {
+        if (a.epi == EPI_ROPE_KV) {
+          rope_kv_store4(a.rk, rr, n, a.n_out, y);
+        } else if (a.epi == EPI_SWIGLU_PAIRS) {
           bf16* o = a.out + (long long)rr * a.ldo + (n >> 1);
           if (n + 1 < a.n_out) o[0] = f2bf(silu_bf(y[0]) * y[1]);
           if (n + 3 < a.n_out) o[1] = f2bf(silu_bf(y[2]) * y[3]);
@@ -387,14 +432,26 @@ k_gemm_tc(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUt
 // so the loads and MMAs of tile i+1 run under the epilogue of tile i.  The epilogue drains the accumulator row-per-
 // lane into a shared-memory tile and then walks it in row-major order, four columns per lane: residual loads and
 // bf16 stores are coalesced (256 bytes per warp and row) instead of 32 lines per store instruction.
-constexpr int P_STAGES = 4;
+// BNT = 256 (prompt-sized GEMMs): a 128 x 256 tile needs 48 KB of operands per 4.2 MFLOP instead of 2 x 32 KB -- the
+// 128 x 128 tile is bound by the L2 -> shared-memory path at 44-47 % tensor activity.  Three 48 KB stages, both
+// accumulators fill the 512 TMEM columns, the epilogue drains a tile in two 128-column halves through the same
+// staging tile.
 constexpr int P_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
-constexpr int P_TLD = BN + 4;
+constexpr int P_TLD = 128 + 4;
 constexpr size_t P_TILE_BYTES = (size_t)BM * P_TLD * 4;
-constexpr size_t P_SMEM_BYTES = (size_t)P_STAGES * STAGE_BYTES + P_TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+template <int BNT> struct PCfg {
+  static constexpr int STAGES = BNT == 128 ? 4 : 3;
+  static constexpr uint32_t STAGE = (BM + BNT) * BK * 2;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE + P_TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+constexpr size_t P_SMEM_BYTES = PCfg<128>::SMEM;
 
+template <int BNT>
 __global__ void __launch_bounds__(P_THREADS, 1)
 k_gemm_tc_p(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, Args a) {
+  constexpr int P_STAGES = PCfg<BNT>::STAGES;
+  constexpr uint32_t STAGE_BYTES = PCfg<BNT>::STAGE;  // (shadows the 128-wide constant of the one-tile kernel)
+  constexpr int BN = BNT;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   float* tile = reinterpret_cast<float*>(smem + (size_t)P_STAGES * STAGE_BYTES);
@@ -439,36 +496,33 @@ k_gemm_tc_p(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
     if (lane == 0) {
       // Programmatic dependent launch: the W boxes of the first ring pass do not depend on the previous kernel --
       // they are requested before pdl_wait(), the X boxes of the same stages after it (both count on full[s]).
+      // (Tile coordinates advance incrementally: a division per k block in this one thread starves the ring.)
       const long long mine = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
       const unsigned total = (unsigned)(mine * num_kb);
       const unsigned pre = total < (unsigned)P_STAGES ? total : (unsigned)P_STAGES;
-      for (unsigned kc = 0; kc < total; ++kc) {
-        if (kc == pre) {
-          pdl_wait();
-          pdl_trigger();
-          for (unsigned j = 0; j < pre; ++j) {
-            const long long t = blockIdx.x + (long long)(j / num_kb) * gridDim.x;
-            tma_load_2d(smem + (size_t)j * STAGE_BYTES, &map_x, &full[j], (int)(j % num_kb) * BK, (int)(t / n_tiles) * BM);
-          }
-        }
-        const long long t = blockIdx.x + (long long)(kc / num_kb) * gridDim.x;
-        const int kb = (int)(kc % num_kb), n0 = (int)(t % n_tiles) * BN, m0 = (int)(t / n_tiles) * BM;
-        const int s = kc % P_STAGES;
-        mbar_wait(&empty[s], ((kc / P_STAGES) & 1) ^ 1);
-        unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
-        unsigned char* sb = sa + BM * BK * 2;
-        mbar_expect(&full[s], STAGE_BYTES);
-        if (kc >= pre) tma_load_2d(sa, &map_x, &full[s], kb * BK, m0);
-        tma_load_2d(sb, &map_w, &full[s], kb * BK, n0);
-      }
-      if (total <= pre) {  // fewer k blocks than stages: the X boxes are still owed
+      auto owed_x = [&]() {  // once: wait for the previous kernel, then the X boxes of the stages filled so far
         pdl_wait();
         pdl_trigger();
-        for (unsigned j = 0; j < total; ++j) {
+        for (unsigned j = 0; j < pre; ++j) {
           const long long t = blockIdx.x + (long long)(j / num_kb) * gridDim.x;
           tma_load_2d(smem + (size_t)j * STAGE_BYTES, &map_x, &full[j], (int)(j % num_kb) * BK, (int)(t / n_tiles) * BM);
         }
+      };
+      unsigned kc = 0;
+      for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int n0 = (int)(t % n_tiles) * BN, m0 = (int)(t / n_tiles) * BM;
+        for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+          if (kc == pre) owed_x();
+          const int s = kc % P_STAGES;
+          mbar_wait(&empty[s], ((kc / P_STAGES) & 1) ^ 1);
+          unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
+          unsigned char* sb = sa + BM * BK * 2;
+          mbar_expect(&full[s], STAGE_BYTES);
+          if (kc >= pre) tma_load_2d(sa, &map_x, &full[s], kb * BK, m0);
+          tma_load_2d(sb, &map_w, &full[s], kb * BK, n0);
+        }
       }
+      if (total <= pre) owed_x();  // fewer k blocks than stages
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -507,20 +561,25 @@ k_gemm_tc_p(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
       const unsigned buf = it & 1;
       mbar_wait(&acc_full[buf], (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int mrows = a.rows - m0 < BM ? a.rows - m0 : BM;
+#pragma unroll 1
+      for (int hcol = 0; hcol < BN; hcol += 128) {  // 128 accumulator columns at a time through the staging tile
+      if (hcol) asm volatile("bar.sync 2, 256;" ::: "memory");  // the previous half has left the staging tile
 #pragma unroll 1
       for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld32(tmem_base + buf * BN + ((uint32_t)(q * 32) << 16) + (uint32_t)(hcol + c0), v);
         float* trow = tile + (size_t)(q * 32 + lane) * P_TLD + c0;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(trow + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&acc_empty[buf])) : "memory");
-      asm volatile("bar.sync 2, 256;" ::: "memory");  // the tile is complete in shared memory
-      const int mrows = a.rows - m0 < BM ? a.rows - m0 : BM;
-      const int n = n0 + c;
+      if (hcol + 128 >= BN) {  // the accumulator is drained: hand it back to the MMA lane
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(&acc_empty[buf])) : "memory");
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");  // the half tile is complete in shared memory
+      const int n = n0 + hcol + c;
       const bool full4 = n + 4 <= a.n_out;
       const bool vec = full4 && (a.ldo & 3) == 0;  // 8-byte stores / residual loads
       if (n < a.n_out) {
@@ -541,7 +600,9 @@ k_gemm_tc_p(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
             const long long row = m0 + r;
             const float4 tv = *reinterpret_cast<const float4*>(tile + (size_t)r * P_TLD + c);
             const float y[4] = {rbf(tv.x), rbf(tv.y), rbf(tv.z), rbf(tv.w)};
-            if (a.epi == EPI_SWIGLU_PAIRS) {
+            if (a.epi == EPI_ROPE_KV) {
+              rope_kv_store4(a.rk, (int)row, n, a.n_out, y);
+            } else if (a.epi == EPI_SWIGLU_PAIRS) {
               // columns (2i, 2i+1) = (gate_i, up_i): bf16( bf16(silu(bf16 gate)) * bf16 up )
               bf16* o = a.out + row * a.ldo + (n >> 1);
               if (full4) {
@@ -565,6 +626,7 @@ k_gemm_tc_p(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ C
             }
           }
         }
+      }
       }
       asm volatile("bar.sync 2, 256;" ::: "memory");  // the staging tile is free for the next tile
     }

@@ -397,6 +397,47 @@ __global__ void __launch_bounds__(128) k_attn_rows(const bf16* __restrict__ q, c
   if (g == 0) out[((size_t)n * heads + h) * HD + d] = f2bf(acc * inv);
 }
 
+// RMSNorm of the row-batched path, one WARP per row (D = 1024 / 2048: the row lives in registers, one global read,
+// no block barrier): k_rmsnorm -- a CTA per row, two passes, two block reductions -- was 6 us per launch whatever
+// the row count, 312 launches per decode step (22 % of a 32-stream step).  Same arithmetic per element
+// (bf16(bf16(x * inv) * scale)); the sum of squares is added in a different order than k_rmsnorm's.
+template <int CH>  // D = CH * 256
+__global__ void __launch_bounds__(256) k_rmsnorm_rows(const bf16* __restrict__ x, int ldx, const bf16* __restrict__ scale,
+                                                      float eps, bf16* __restrict__ y, int ldy, int N) {
+  pdl_wait();
+  pdl_trigger();
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= N) return;
+  constexpr int D = CH * 256;
+  const bf16* xr = x + (size_t)n * ldx;
+  uint4 v[CH];
+  float ss = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    v[c] = *reinterpret_cast<const uint4*>(xr + c * 256 + lane * 8);
+    const uint32_t w[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ss = fmaf(bflo(w[i]), bflo(w[i]), ss);
+      ss = fmaf(bfhi(w[i]), bfhi(w[i]), ss);
+    }
+  }
+  ss = warp_sum(ss);
+  const float inv = 1.0f / sqrtf(ss / (float)D + eps);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    const uint4 sc = *reinterpret_cast<const uint4*>(scale + c * 256 + lane * 8);
+    const uint32_t w[4] = {v[c].x, v[c].y, v[c].z, v[c].w}, g[4] = {sc.x, sc.y, sc.z, sc.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 p = __floats2bfloat162_rn(rbf(bflo(w[i]) * inv) * bflo(g[i]), rbf(bfhi(w[i]) * inv) * bfhi(g[i]));
+      o[i] = *reinterpret_cast<const uint32_t*>(&p);
+    }
+    *reinterpret_cast<uint4*>(y + (size_t)n * ldy + c * 256 + lane * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K3 (depth decoder, row-batched path): head_dim 128 over a cache of <= 32 positions.  k_attn_rows spends a CTA of 128
 // threads on one (row, q-head): with <= 32 keys a quarter of them computes a 128-long dot product each from

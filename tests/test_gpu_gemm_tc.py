@@ -26,8 +26,11 @@ def _mk(N, K, M, seed):
     return x.to(torch.bfloat16), w.to(torch.bfloat16)
 
 
+# (decode-sized row counts run cluster split-K with 2 / 4 / 8 slices; the wide shapes -- a 256-stream gate/up -- the
+#  persistent kernel with partly filled last row tiles)
 @pytest.mark.parametrize("N,K,M", [(128, 2048, 2048), (300, 1024, 1536), (50, 8192, 1024), (1000, 2048, 2051),
-                                   (1, 64, 128), (129, 256, 384), (1568, 2048, 3072)])
+                                   (1, 64, 128), (129, 256, 384), (1568, 2048, 3072), (256, 1024, 16384), (200, 512, 9600),
+                                   (384, 256, 6400)])
 def test_gemm_matches_fp32_reference(N, K, M):
     x, w = _mk(N, K, M, N + K)
     y = _run(x, w)
@@ -52,13 +55,14 @@ def test_gemm_residual_epilogue():
     assert (y.float() - ref.float()).abs().max().item() <= 2.0 ** -7 * 4
 
 
-def test_gemm_swiglu_pairs_epilogue():
-    x, w = _mk(130, 1024, 512, 6)  # 256 (gate, up) pairs interleaved
+@pytest.mark.parametrize("N,M", [(130, 512), (256, 16384)])  # cluster split-K; the persistent kernel on a 256-stream gate/up
+def test_gemm_swiglu_pairs_epilogue(N, M):
+    x, w = _mk(N, 1024, M, 6)  # M / 2 (gate, up) pairs interleaved
     y = _run(x, w, epi=2)
     lin = (x.float() @ w.float().t()).to(torch.bfloat16)
     gate, up = lin[:, 0::2], lin[:, 1::2]
     ref = (torch.nn.functional.silu(gate) * up)
-    assert y.shape == (130, 256)
+    assert y.shape == (N, M // 2)
     assert (y.float() - ref.float()).abs().max().item() <= 2.0 ** -7 * max(1.0, ref.float().abs().max().item())
 
 
