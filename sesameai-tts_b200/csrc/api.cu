@@ -49,7 +49,13 @@ static bool pdl_enabled() {
 extern "C" void csm_debug_set_pdl(int32_t on) { g_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
 // cluster_z > 1: the z extent of the grid is launched as one thread-block cluster (split-K through DSMEM)
 template <typename... P, typename... A>
+static void launch_kcd(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, dim3 cluster, A&&... args);
+template <typename... P, typename... A>
 static void launch_kc(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_z, A&&... args) {
+  launch_kcd(kern, grid, block, smem, st, dim3(1, 1, cluster_z > 1 ? cluster_z : 1), static_cast<A&&>(args)...);
+}
+template <typename... P, typename... A>
+static void launch_kcd(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, dim3 cluster, A&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -60,9 +66,9 @@ static void launch_kc(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cu
     at[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
   }
-  if (cluster_z > 1) {
+  if (cluster.x * cluster.y * cluster.z > 1) {
     at[n].id = cudaLaunchAttributeClusterDimension;
-    at[n].val.clusterDim.x = 1; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = (unsigned)cluster_z;
+    at[n].val.clusterDim.x = cluster.x; at[n].val.clusterDim.y = cluster.y; at[n].val.clusterDim.z = cluster.z;
     ++n;
   }
   cfg.attrs = at; cfg.numAttrs = n;
@@ -152,6 +158,7 @@ struct csm_ctx {
   // persistent decode megakernel (batch 1)
   mega::Phase* d_phases;
   mega::Sync* d_sync;       // device status word (frame counter + sticky error), always initialised
+  unsigned int* mega_att_part;  // tagged partials of the megakernel's split long-context attention
   unsigned int* h_error;    // mapped host mirror of the error word (owned by the ctx)
   int n_phases, mega_grid;
   bool mega_ok;
@@ -264,6 +271,7 @@ static size_t carve_all(csm_ctx* x, char* base) {
   x->tc_part = cv.take<float>((size_t)TC_SPLIT_TILES * tc::BM * tc::BN);
   x->tc_counters = cv.take<unsigned int>(TC_SPLIT_TILES);
   x->d_sync = cv.take<mega::Sync>(1);
+  x->mega_att_part = cv.take<unsigned int>((size_t)mega::ATTN_SPLITS * c.backbone.heads * mega::ATTN_PART_WORDS);
   x->d_phases = cv.take<mega::Phase>(mega_phase_count(c));
   cv.off = (cv.off + 255) & ~(size_t)255;
   const size_t t0 = cv.off;
@@ -865,7 +873,9 @@ extern "C" int32_t csm_create(const csm_config* cfg, const csm_weights* w, int32
       e = cudaHostGetDevicePointer((void**)&dmirror, x->h_error, 0);
     }
     mega::Sync init;
-    init.seq = 0; init.error = 0; init.host_error = dmirror;
+    init.seq = 0; init.error = 0; init.host_error = dmirror; init.att_part = x->mega_att_part;
+    if (e == cudaSuccess)
+      e = cudaMemsetAsync(x->mega_att_part, 0, (size_t)mega::ATTN_SPLITS * x->cfg.backbone.heads * mega::ATTN_PART_WORDS * sizeof(unsigned int), st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(x->d_sync, &init, sizeof(init), cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // ``init`` is stack memory
     if (e != cudaSuccess) {

@@ -58,6 +58,7 @@ struct DevStatus {
   unsigned int seq;    // frame counter of the megakernel (tag salt)
   unsigned int error;  // first error code of this call (0 = none)
   unsigned int* host_error;  // mapped host mirror, sticky until csm_check_error clears it
+  unsigned int* att_part;    // megakernel: tagged partial results of the split long-context attention (mega.cuh: attn_split)
 };
 __global__ void k_set_params(FrameParams* dst, FrameParams v, DevStatus* st_reset) {
   pdl_wait();

@@ -1006,14 +1006,152 @@ __device__ __forceinline__ void gemv_phase(const Phase& ph, Ctx& c) {
   gemv_groups(ph, c, cl, ngl, j_item, pair, n_item, item_on, pre);
 }
 
+// Long contexts (a voice prompt: 1568 frames): with one CTA per q-head 32 of the 148 CTAs walk the whole cache -- 29 us
+// per layer at 1568 keys, +0.47 ms per frame.  From ATTN_SPLIT_MIN keys on, the cache of a head is cut into ATTN_SPLITS
+// key ranges, one CTA each (128 CTAs): every CTA computes the softmax numerator / denominator of its range against
+// its own maximum (m, l, o[hd]: the flash-decoding partial), publishes them as tagged words -- an fp32 value is two
+// words, 16 payload bits each -- and the CTAs of range 0 combine the ranges of their head in range order
+// (deterministic) into the phase's output.  One more hand-off inside the phase, taken only on this path; a separate
+// function so that the short-context path keeps its registers and code.
+constexpr int ATTN_SPLITS = 4;
+constexpr int ATTN_SPLIT_MIN = 512;
+constexpr int ATTN_PART_WORDS = 2 * 64 + 4;  // o[64] + m + l, two words per value (head_dim 64)
+__device__ __forceinline__ void st_f32_tagged(uint32_t* p, uint32_t tag, float v) {
+  const uint32_t b = __float_as_uint(v);
+  stv2(p, make_uint2(tag | (b >> 16), tag | (b & 0xffffu)));
+}
+__device__ __forceinline__ float ld_f32_tagged(const uint32_t* p, uint32_t tag, Sync* sync) {
+  const uint32_t hi = poll1(p, tag, sync), lo = poll1(p + 1, tag, sync);
+  return __uint_as_float((hi << 16) | (lo & 0xffffu));
+}
+// (everything it needs from the kernel's context comes by value: a reference would force that struct into local memory)
+__device__ __noinline__ void attn_split(const Phase& ph, int slot, int tid, int bb_lane, unsigned seq, uint32_t otag, bf16* xs,
+                                        float* scratch, Sync* sync) {
+  const int cta = blockIdx.x;
+  if (cta >= ATTN_SPLITS * ph.heads) return;
+  const int h = cta % ph.heads, sp = cta / ph.heads;
+  constexpr int hd = 64;
+  const int nold = slot;  // keys in the cache; the current position's K / V are tagged words of the QKV phase
+  const int chunk = (nold + ATTN_SPLITS - 1) / ATTN_SPLITS;
+  const int k0 = sp * chunk < nold ? sp * chunk : nold;
+  const int k1 = k0 + chunk < nold ? k0 + chunk : nold;
+  const bool last = sp == ATTN_SPLITS - 1;  // this range also takes the current position
+  const int kvh = h / (ph.heads / ph.kv_heads);
+  const int krows = ph.kv_heads * hd;
+  const bf16* kp = ph.kc + ((size_t)bb_lane * ph.kv_heads + kvh) * ph.slots * hd;
+  const bf16* vp = ph.vc + ((size_t)bb_lane * ph.kv_heads + kvh) * ph.slots * hd;
+  float* sc = reinterpret_cast<float*>(xs);   // scores of this range: sc[j - k0], the current position at [k1 - k0]
+  float* part = sc + ((chunk + 1 + 3) & ~3);     // [NCT / 8][hd] partial outputs
+  float* qs = part + (NCT / 8) * hd;             // [hd], then kcur [hd], vcur [hd]
+  float* kcur = qs + hd;
+  float* vcur = kcur + hd;
+  const float scale = 1.0f / sqrtf((float)hd);
+  const uint32_t tag = tag_of(seq, ph.q_src);
+  for (int d = tid; d < (last ? 3 * hd : hd); d += NCT) {
+    const int which = d / hd, dd = d - which * hd;
+    const uint32_t* src = which == 0 ? my_copy(ph.t_q, ph.q_rs) + (size_t)h * hd + dd
+                                     : my_copy(ph.t_kv, ph.kv_rs) + (size_t)(which - 1) * krows + (size_t)kvh * hd + dd;
+    qs[d] = tval(poll1(src, tag, sync));
+  }
+  csync<NCT, CBAR>();
+  const int n = k1 - k0 + (last ? 1 : 0);  // scores of this range
+  float mx = -INFINITY;
+  for (int j = tid; j < n; j += NCT) {
+    float s = 0.f;
+    if (j == k1 - k0) {
+      for (int i = 0; i < hd; ++i) s = fmaf(qs[i], kcur[i], s);
+    } else {
+      const bf16* kr = kp + (size_t)(k0 + j) * hd;
+#pragma unroll
+      for (int i = 0; i < hd / 8; ++i) {
+        const uint4 v = ldcg16(kr + i * 8);
+        const float* q8 = qs + i * 8;
+        s = fmaf(q8[0], bflo(v.x), s); s = fmaf(q8[1], bfhi(v.x), s);
+        s = fmaf(q8[2], bflo(v.y), s); s = fmaf(q8[3], bfhi(v.y), s);
+        s = fmaf(q8[4], bflo(v.z), s); s = fmaf(q8[5], bfhi(v.z), s);
+        s = fmaf(q8[6], bflo(v.w), s); s = fmaf(q8[7], bfhi(v.w), s);
+      }
+    }
+    s *= scale;
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = block_max<NCT, CBAR>(mx, scratch, tid);
+  float sum = 0.f;
+  for (int j = tid; j < n; j += NCT) {
+    const float e = expf(sc[j] - mx);  // (an empty range: no iterations, mx = -inf, sum = 0)
+    sc[j] = e;
+    sum += e;
+  }
+  sum = block_sum<NCT, CBAR>(sum, scratch, tid);
+  // P.V over the cached keys of the range: 8 dims per thread, 8 threads per key row, NCT / 8 key groups
+  constexpr int tpr = hd >> 3, ngroups = NCT / tpr;
+  const int kg = tid / tpr, d8 = (tid - kg * tpr) * 8;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int j = kg; j < k1 - k0; j += ngroups) {
+    const uint4 v = ldcg16(vp + (size_t)(k0 + j) * hd + d8);
+    const float p = sc[j];
+    acc[0] = fmaf(p, bflo(v.x), acc[0]); acc[1] = fmaf(p, bfhi(v.x), acc[1]);
+    acc[2] = fmaf(p, bflo(v.y), acc[2]); acc[3] = fmaf(p, bfhi(v.y), acc[3]);
+    acc[4] = fmaf(p, bflo(v.z), acc[4]); acc[5] = fmaf(p, bfhi(v.z), acc[5]);
+    acc[6] = fmaf(p, bflo(v.w), acc[6]); acc[7] = fmaf(p, bfhi(v.w), acc[7]);
+  }
+  if (last && kg == 0) {
+    const float p = sc[k1 - k0];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vcur[d8 + e], acc[e]);
+  }
+  *reinterpret_cast<float4*>(part + kg * hd + d8) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  *reinterpret_cast<float4*>(part + kg * hd + d8 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  csync<NCT, CBAR>();
+  uint32_t* base = reinterpret_cast<uint32_t*>(sync->att_part);
+  uint32_t* mine = base + (size_t)(sp * ph.heads + h) * ATTN_PART_WORDS;
+  if (tid < hd) {
+    float o = 0.f;
+    for (int gg = 0; gg < ngroups; ++gg) o += part[gg * hd + tid];  // fixed order
+    st_f32_tagged(mine + 2 * tid, otag, o);
+  } else if (tid == hd) {
+    st_f32_tagged(mine + 2 * hd, otag, mx);
+    st_f32_tagged(mine + 2 * hd + 2, otag, sum);
+  }
+  if (sp != 0) return;
+  // range 0 combines the ranges of its head, in range order
+  if (tid < hd) {
+    float m[ATTN_SPLITS], l[ATTN_SPLITS], o[ATTN_SPLITS];
+    float M = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < ATTN_SPLITS; ++r) {
+      const uint32_t* pr = base + (size_t)(r * ph.heads + h) * ATTN_PART_WORDS;
+      o[r] = ld_f32_tagged(pr + 2 * tid, otag, sync);
+      m[r] = ld_f32_tagged(pr + 2 * hd, otag, sync);
+      l[r] = ld_f32_tagged(pr + 2 * hd + 2, otag, sync);
+      M = fmaxf(M, m[r]);
+    }
+    float L = 0.f, O = 0.f;
+#pragma unroll
+    for (int r = 0; r < ATTN_SPLITS; ++r) {
+      const float w = expf(m[r] - M);  // (an empty range: exp(-inf) = 0)
+      L = fmaf(l[r], w, L);
+      O = fmaf(o[r], w, O);
+    }
+    rep_st1(ph.t_out + (size_t)h * hd + tid, ph.out_rs, tword(otag, O * (1.0f / L)));
+  }
+}
+
 // backbone attention: CTA h < heads owns q-head h over keys [0 .. slot]; the current position's K/V
 // come from the QKV phase's tagged words, earlier positions from the cache (previous launches)
 __device__ __forceinline__ void attn_phase(const Phase& ph, Ctx& c) {
   const int h = blockIdx.x;
-  if (h >= ph.heads) return;
   const int hd = ph.hd;
   int pos, slot;
   phase_pos(ph, c, 0, pos, slot);
+  if (slot + 1 >= ATTN_SPLIT_MIN && hd == 64 && ATTN_SPLITS * ph.heads <= (int)gridDim.x) {
+    attn_split(ph, slot, c.tid, c.bb_lane, c.seq, c.tag, c.xs, c.scratch, c.sync);
+    return;
+  }
+  if (h >= ph.heads) return;
   const int nkeys = slot + 1;
   const int kvh = h / (ph.heads / ph.kv_heads);
   const int krows = ph.kv_heads * hd;
