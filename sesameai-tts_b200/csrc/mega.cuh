@@ -1090,13 +1090,31 @@ __device__ __noinline__ void attn_split(const Phase& ph, int slot, int tid, int 
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  for (int j = kg; j < k1 - k0; j += ngroups) {
-    const uint4 v = ldcg16(vp + (size_t)(k0 + j) * hd + d8);
-    const float p = sc[j];
-    acc[0] = fmaf(p, bflo(v.x), acc[0]); acc[1] = fmaf(p, bfhi(v.x), acc[1]);
-    acc[2] = fmaf(p, bflo(v.y), acc[2]); acc[3] = fmaf(p, bfhi(v.y), acc[3]);
-    acc[4] = fmaf(p, bflo(v.z), acc[4]); acc[5] = fmaf(p, bfhi(v.z), acc[5]);
-    acc[6] = fmaf(p, bflo(v.w), acc[6]); acc[7] = fmaf(p, bfhi(v.w), acc[7]);
+  {
+    const int nr = k1 - k0;
+    const bf16* vr = vp + (size_t)k0 * hd + d8;
+    int j = kg;
+    for (; j + 3 * ngroups < nr; j += 4 * ngroups) {  // four V rows in flight per thread
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ldcg16(vr + (size_t)(j + u * ngroups) * hd);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float p = sc[j + u * ngroups];
+        acc[0] = fmaf(p, bflo(v[u].x), acc[0]); acc[1] = fmaf(p, bfhi(v[u].x), acc[1]);
+        acc[2] = fmaf(p, bflo(v[u].y), acc[2]); acc[3] = fmaf(p, bfhi(v[u].y), acc[3]);
+        acc[4] = fmaf(p, bflo(v[u].z), acc[4]); acc[5] = fmaf(p, bfhi(v[u].z), acc[5]);
+        acc[6] = fmaf(p, bflo(v[u].w), acc[6]); acc[7] = fmaf(p, bfhi(v[u].w), acc[7]);
+      }
+    }
+    for (; j < nr; j += ngroups) {
+      const uint4 v = ldcg16(vr + (size_t)j * hd);
+      const float p = sc[j];
+      acc[0] = fmaf(p, bflo(v.x), acc[0]); acc[1] = fmaf(p, bfhi(v.x), acc[1]);
+      acc[2] = fmaf(p, bflo(v.y), acc[2]); acc[3] = fmaf(p, bfhi(v.y), acc[3]);
+      acc[4] = fmaf(p, bflo(v.z), acc[4]); acc[5] = fmaf(p, bfhi(v.z), acc[5]);
+      acc[6] = fmaf(p, bflo(v.w), acc[6]); acc[7] = fmaf(p, bfhi(v.w), acc[7]);
+    }
   }
   if (last && kg == 0) {
     const float p = sc[k1 - k0];
@@ -1137,6 +1155,24 @@ __device__ __noinline__ void attn_split(const Phase& ph, int slot, int tid, int 
       O = fmaf(o[r], w, O);
     }
     rep_st1(ph.t_out + (size_t)h * hd + tid, ph.out_rs, tword(otag, O * (1.0f / L)));
+  }
+}
+
+// L2 prefetch of the key range this CTA walks in the split attention phase that follows the backbone QKV phase: issued
+// when the phase BEFORE that QKV phase ends, so the cache rows (DRAM: the weights of a frame flush L2) arrive while
+// the QKV projection runs -- the range is 100 KB per CTA and a CTA keeps only 16 .. 32 KB of loads in flight.
+__device__ __noinline__ void attn_split_prefetch(const bf16* kc, const bf16* vc, int heads, int kv_heads, int slots, int slot,
+                                                 int bb_lane, int tid) {
+  const int cta = blockIdx.x;
+  if (cta >= ATTN_SPLITS * heads) return;
+  const int h = cta % heads, sp = cta / heads, kvh = h / (heads / kv_heads);
+  const int chunk = (slot + ATTN_SPLITS - 1) / ATTN_SPLITS;
+  const int k0 = sp * chunk < slot ? sp * chunk : slot;
+  const int k1 = k0 + chunk < slot ? k0 + chunk : slot;
+  const size_t base = ((size_t)bb_lane * kv_heads + kvh) * slots * 64;
+  for (int i = k0 + tid; i < k1; i += NCT) {  // one 128-byte row = one line
+    prefetch_l2(kc + base + (size_t)i * 64);
+    prefetch_l2(vc + base + (size_t)i * 64);
   }
 }
 
@@ -1526,6 +1562,9 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
       if (nx.type == PH_GEMV && nx.attn_prologue) {
         const int cl = local_cta(blockIdx.x, gridDim.x, nx.rot);
         if (nx.gq + (cl < nx.gr ? 1 : 0) > 0) attn_prefetch(nx, c);
+      } else if (nx.type == PH_GEMV && nx.epi == EPI_ROPE_KV && nx.pos_mode == POS_BACKBONE && c.bb_slot + 1 >= ATTN_SPLIT_MIN &&
+                 nx.hd == 64 && ATTN_SPLITS * nx.heads <= (int)gridDim.x) {
+        attn_split_prefetch(nx.kc, nx.vc, nx.heads, nx.kv_heads, nx.slots, c.bb_slot, c.bb_lane, c.tid);
       }
     }
   }

@@ -329,3 +329,44 @@ def test_sampling_seed_follows_torch_manual_seed():
     a, b, c = run(1), run(1), run(2)
     assert torch.equal(a, b)
     assert not torch.equal(a, c)
+
+
+def test_megakernel_split_attention_crosses_its_threshold():
+    """Backbone attention of the megakernel: one CTA per q-head below 512 keys, four key ranges per head combined in range
+    order from 512 keys on (mega.cuh: attn_split).  Eight teacher-forced decode frames after a 509-frame prompt take both
+    forms (slots 509 .. 516): logits against the oracle and against the per-op path, whose attention is one pass."""
+    gold = dict(model_args=dict(backbone_flavor="tiny-bb", decoder_flavor="tiny-dec", text_vocab_size=1000,
+                                audio_vocab_size=2051, audio_num_codebooks=32),
+                weight_seed=77, planted=False, batch=1)
+    om, _ = build_oracle(gold)
+    pm, _ = build_product(gold)
+    tok, msk, pos = syn.voice_prompt(1, 3, 20, 130, 59, seed=6, text_vocab=1000)
+    assert tok.shape[1] == 509
+    n_frames = 9
+    noise = syn.exp_noise(32 * n_frames, 1, 2051, 12)
+    om.reset_caches()
+    want, want_logits = [], []
+    t, m, p = tok, msk, pos
+    with torch.inference_mode():
+        for i in range(n_frames):
+            rec = {}
+            s = om.generate_frame(t, m, p, 0.9, 50, noise=noise[32 * i: 32 * i + 32], record=rec)
+            want.append(s)
+            want_logits.append(torch.stack(rec["logits"]).float())
+            t, m, p = next_inputs(s, p)
+    got = {}
+    for direct in (False, True):
+        pm.reset_caches()
+        t, m, p = tok.cuda(), msk.cuda(), pos.cuda()
+        out = []
+        for i in range(n_frames):
+            lg = torch.zeros(32, 1, 2051, dtype=torch.bfloat16, device="cuda")
+            s = pm.generate_frame(t, m, p, 0.9, 50, noise=noise[32 * i: 32 * i + 32].cuda(), forced=want[i].cuda(), logits_out=lg,
+                                  no_graph=direct)
+            assert torch.equal(s.cpu(), want[i]), (direct, i)
+            assert_logits_close(lg.cpu(), want_logits[i], f"509-frame prompt, frame {i}, {'per-op' if direct else 'megakernel'}")
+            out.append(lg.float().cpu())
+            t, m, p = next_inputs(s, p)
+        got[direct] = torch.stack(out)
+        pm.check_device_error()
+    assert_logits_close(got[False], got[True], "megakernel (split attention from frame 3 on) vs per-op path")
