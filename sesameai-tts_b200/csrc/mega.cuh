@@ -1158,24 +1158,6 @@ __device__ __noinline__ void attn_split(const Phase& ph, int slot, int tid, int 
   }
 }
 
-// L2 prefetch of the key range this CTA walks in the split attention phase that follows the backbone QKV phase: issued
-// when the phase BEFORE that QKV phase ends, so the cache rows (DRAM: the weights of a frame flush L2) arrive while
-// the QKV projection runs -- the range is 100 KB per CTA and a CTA keeps only 16 .. 32 KB of loads in flight.
-__device__ __noinline__ void attn_split_prefetch(const bf16* kc, const bf16* vc, int heads, int kv_heads, int slots, int slot,
-                                                 int bb_lane, int tid) {
-  const int cta = blockIdx.x;
-  if (cta >= ATTN_SPLITS * heads) return;
-  const int h = cta % heads, sp = cta / heads, kvh = h / (heads / kv_heads);
-  const int chunk = (slot + ATTN_SPLITS - 1) / ATTN_SPLITS;
-  const int k0 = sp * chunk < slot ? sp * chunk : slot;
-  const int k1 = k0 + chunk < slot ? k0 + chunk : slot;
-  const size_t base = ((size_t)bb_lane * kv_heads + kvh) * slots * 64;
-  for (int i = k0 + tid; i < k1; i += NCT) {  // one 128-byte row = one line
-    prefetch_l2(kc + base + (size_t)i * 64);
-    prefetch_l2(vc + base + (size_t)i * 64);
-  }
-}
-
 // backbone attention: CTA h < heads owns q-head h over keys [0 .. slot]; the current position's K/V
 // come from the QKV phase's tagged words, earlier positions from the cache (previous launches)
 __device__ __forceinline__ void attn_phase(const Phase& ph, Ctx& c) {
@@ -1562,9 +1544,6 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
       if (nx.type == PH_GEMV && nx.attn_prologue) {
         const int cl = local_cta(blockIdx.x, gridDim.x, nx.rot);
         if (nx.gq + (cl < nx.gr ? 1 : 0) > 0) attn_prefetch(nx, c);
-      } else if (nx.type == PH_GEMV && nx.epi == EPI_ROPE_KV && nx.pos_mode == POS_BACKBONE && c.bb_slot + 1 >= ATTN_SPLIT_MIN &&
-                 nx.hd == 64 && ATTN_SPLITS * nx.heads <= (int)gridDim.x) {
-        attn_split_prefetch(nx.kc, nx.vc, nx.heads, nx.kv_heads, nx.slots, c.bb_slot, c.bb_lane, c.tid);
       }
     }
   }
