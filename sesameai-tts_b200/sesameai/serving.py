@@ -58,6 +58,11 @@ class ContinuousBatcher:
         # frames of the running streams, on the device: one scatter per round, one slice + copy per finished stream
         self._max_frames = int(max_frames)
         self._frames = torch.zeros(self.max_lanes, self._max_frames, C, dtype=torch.int32, device=self.device)
+        # per-lane bookkeeping mirrored on the device, so that a round builds its inputs with a handful of tensor ops
+        # instead of Python loops and host -> device copies (the GPU idles while the host prepares a round)
+        self._len_dev = torch.zeros(self.max_lanes, dtype=torch.int64, device=self.device)  # cache length (= model.lane_len)
+        self._nf_dev = torch.zeros(self.max_lanes, dtype=torch.int64, device=self.device)   # frames kept
+        self._io: Dict[int, tuple] = {}  # padded batch size -> (tokens, mask) buffers
         self._free: List[int] = list(range(self.max_lanes - 1, -1, -1))
         self._active: Dict[int, _Stream] = {}
         self._pending: Deque[Request] = deque()
@@ -107,14 +112,19 @@ class ContinuousBatcher:
                 for l in pad:
                     m.reset_lane(l)
                 Bp = B + len(pad)
-                tok = torch.zeros(Bp, 1, self._C + 1, dtype=torch.int64, device=self.device)
+                if Bp not in self._io:
+                    msk = torch.ones(Bp, 1, self._C + 1, dtype=torch.bool, device=self.device)
+                    msk[:, :, -1] = False
+                    self._io[Bp] = (torch.zeros(Bp, 1, self._C + 1, dtype=torch.int64, device=self.device), msk)
+                tok, msk = self._io[Bp]
+                tok.zero_()
                 tok[:B, 0, : self._C] = self._last.index_select(0, self._rows_dev)
-                msk = torch.ones(Bp, 1, self._C + 1, dtype=torch.bool, device=self.device)
-                msk[:, :, -1] = False
-                pos = torch.tensor([[self._lane_len(l)] for l in rows + pad], dtype=torch.int64, device=self.device)
+                pos = torch.zeros(Bp, 1, dtype=torch.int64, device=self.device)  # idle rows sit on rewound lanes: position 0
+                pos[:B, 0] = self._len_dev.index_select(0, self._rows_dev)
                 out = m.generate_frame(tok, msk, pos, self.temperature, self.topk, lanes=rows + pad)[:B]
                 for l in pad:
                     m.reset_lane(l)
+                self._len_dev.index_add_(0, self._rows_dev, torch.ones_like(self._rows_dev))
                 self._last.index_copy_(0, self._rows_dev, out)
                 for l in rows:
                     self._active[l].calls += 1
@@ -136,7 +146,10 @@ class ContinuousBatcher:
                 msk = torch.stack([st.req.mask for st in group]).to(self.device, torch.bool)
                 pos = torch.arange(S, device=self.device).unsqueeze(0).repeat(len(group), 1)
                 s = m.generate_frame(tok, msk, pos, self.temperature, self.topk, lanes=lanes)
-                self._last.index_copy_(0, torch.tensor(lanes, dtype=torch.long, device=self.device), s)
+                lanes_t = torch.tensor(lanes, dtype=torch.long, device=self.device)
+                self._last.index_copy_(0, lanes_t, s)
+                self._len_dev[lanes_t] = S
+                self._nf_dev[lanes_t] = 0
                 for st in group:
                     st.calls = 1
                     self._active[st.lane] = st
@@ -148,9 +161,9 @@ class ContinuousBatcher:
             newest = self._last.index_select(0, idx)                      # [n, C] frames sampled this round
             eos = (newest == 0).all(dim=1)                                # reference generator.py:285, per stream
             # store the frame of every stream at its own frame index (an EOS frame lands one past the end and is never read)
-            at = torch.tensor([min(len_, self._max_frames - 1) for len_ in (self._active[l].n_frames for l in lanes_now)],
-                              dtype=torch.long, device=self.device)
+            at = self._nf_dev.index_select(0, idx).clamp_(max=self._max_frames - 1)
             self._frames[idx, at] = newest
+            self._nf_dev.index_add_(0, idx, (~eos).to(torch.int64))  # (the host mirror advances in end())
             eos_h = eos.to("cpu", non_blocking=True)
             ev = None
             if self.device.type == "cuda":
