@@ -10,14 +10,18 @@
 //   warps 2..5  epilogue      : tcgen05.ld (32 lanes x 32 columns per warp per step) -> registers ->
 //                               fused epilogue (bf16 round, + residual, SwiGLU on interleaved
 //                               gate/up columns) -> global
-// One output tile per CTA; grid = (out/128, rows/128) -- for prefill that is thousands of CTAs,
-// several waves over the 148 SMs.  Every wait is trip-capped and traps instead of hanging.
-//
-// Split-K (grid.z = splits > 1) for the decode steps of large batches, where rows <= 512 and a projection
-// with 1024 .. 2048 outputs is only 8 .. 32 tiles: each CTA accumulates one K slice of its tile in TMEM and
-// writes the fp32 partial tile to a workspace; the last CTA of a tile to finish (a counter per tile) adds the
-// partials in slice order -- a fixed order, so the result does not depend on which CTA came last -- and runs
-// the epilogue.  148 SMs stream the weights instead of 16.
+// Three kernels share these pieces:
+//   k_gemm_tc        one output tile per CTA (the layout above).  Serves the decode-sized GEMMs (<= 512 rows), whose
+//                    tiles all fit on the SMs at once, with CLUSTER SPLIT-K: the z extent of the grid is one
+//                    thread-block cluster of 2 / 4 / 8 CTAs, CTA z accumulates k slice z, the fp32 partial tiles meet
+//                    through distributed shared memory and are added in slice order (deterministic).  An older
+//                    split-K through global memory (partial tiles in a workspace, a counter per tile, the last CTA of
+//                    a tile adds the slices in order) remains behind CSM_TC_SPLITK.
+//   k_gemm_tc_p<128> persistent: one CTA per SM walks the tiles, two TMEM accumulators, eight epilogue warps, coalesced
+//                    epilogue through a shared-memory tile -- every GEMM with more tiles than SMs at decode row counts.
+//   k_gemm_tc_p<256> the same with 128 x 256 tiles (three 48 KB stages, all 512 TMEM columns): prompt-sized GEMMs.
+// Every wait is trip-capped and traps instead of hanging.  All three take part in programmatic dependent launch
+// (common.cuh): W boxes may be requested before griddepcontrol.wait, X boxes and the epilogue come after it.
 #pragma once
 #include <cuda.h>
 
