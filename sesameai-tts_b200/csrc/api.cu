@@ -159,6 +159,8 @@ struct csm_ctx {
   mega::Phase* d_phases;
   mega::Sync* d_sync;       // device status word (frame counter + sticky error), always initialised
   unsigned int* mega_att_part;  // tagged partials of the megakernel's split long-context attention
+  float* att_part;              // row-batched decode at long context: (o, m, l) of the key ranges (k_attn_split64)
+  bool long_ctx;                // this call's decode rows see >= ATT_LONG_MIN keys (set by csm_generate_frame)
   unsigned int* h_error;    // mapped host mirror of the error word (owned by the ctx)
   int n_phases, mega_grid;
   bool mega_ok;
@@ -272,6 +274,7 @@ static size_t carve_all(csm_ctx* x, char* base) {
   x->tc_counters = cv.take<unsigned int>(TC_SPLIT_TILES);
   x->d_sync = cv.take<mega::Sync>(1);
   x->mega_att_part = cv.take<unsigned int>((size_t)mega::ATTN_SPLITS * c.backbone.heads * mega::ATTN_PART_WORDS);
+  x->att_part = cv.take<float>((size_t)x->max_batch * c.backbone.heads * AS_SPLITS * AS_PW);
   x->d_phases = cv.take<mega::Phase>(mega_phase_count(c));
   cv.off = (cv.off + 255) & ~(size_t)255;
   const size_t t0 = cv.off;
@@ -940,7 +943,8 @@ static bool rows_path(const csm_ctx* x, int B) {
 }
 
 static int get_graph(csm_ctx* x, int B, cudaGraphExec_t* out) {
-  auto it = x->graphs.find(B);
+  const int key = B | (x->long_ctx ? 1 << 24 : 0);  // the long-context step uses other attention kernels
+  auto it = x->graphs.find(key);
   if (it != x->graphs.end()) {
     *out = it->second;
     return CSM_OK;
@@ -962,7 +966,7 @@ static int get_graph(csm_ctx* x, int B, cudaGraphExec_t* out) {
     if (g) cudaGraphDestroy(g);
     return rc_tc;
   }
-  x->graph_nodes[B] = g_launches.load() - before;  // captured, not executed
+  x->graph_nodes[key] = g_launches.load() - before;  // captured, not executed
   g_launches.store(before);
   if (e != cudaSuccess || e2 != cudaSuccess) {
     if (g) cudaGraphDestroy(g);
@@ -972,7 +976,7 @@ static int get_graph(csm_ctx* x, int B, cudaGraphExec_t* out) {
   e = cudaGraphInstantiate(&ge, g, 0);
   cudaGraphDestroy(g);
   if (e != cudaSuccess) return set_err(CSM_ERR_CUDA, "graph instantiate: %s", cudaGetErrorString(e));
-  x->graphs[B] = ge;
+  x->graphs[key] = ge;
   *out = ge;
   return CSM_OK;
 }
@@ -999,6 +1003,13 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
     if (x->lane_len[lane[b]] + S > x->cfg.max_seq_len)
       return set_err(CSM_ERR_OVERFLOW, "KV cache overflow (cache_pos + seq_len > max_seq_len)");
     if (x->lane_len[lane[b]] != x->lane_len[lane[0]]) uniform = false;
+  }
+  {
+    // decode rows at a long context (a voice prompt) take the flash-decoding attention kernels
+    static const int long_min = getenv("CSM_ATT_LONG_MIN") ? atoi(getenv("CSM_ATT_LONG_MIN")) : 256;
+    int mx = 0;
+    for (int b = 0; b < B; ++b) mx = x->lane_len[lane[b]] > mx ? x->lane_len[lane[b]] : mx;
+    x->long_ctx = long_min > 0 && mx + S >= long_min;
   }
   FrameParams p;
   memset(&p, 0, sizeof(p));
@@ -1071,7 +1082,7 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
     int rc = get_graph(x, B, &ge);
     if (rc != CSM_OK) return rc;
     CU_TRY(cudaGraphLaunch(ge, st));
-    g_launches.fetch_add(x->graph_nodes[B], std::memory_order_relaxed);
+    g_launches.fetch_add(x->graph_nodes[B | (x->long_ctx ? 1 << 24 : 0)], std::memory_order_relaxed);
   }
   advance();
   return CSM_OK;
@@ -1370,6 +1381,13 @@ static int stack_pass_tc(csm_ctx* x, StackDev& s, int N, const RowMeta& m, cudaS
         // prompt rows: tiled tensor-core attention, one CTA per (64 rows of a stream, q-head)
         dim3 fgrid((m.chunk + 63) / 64, k.heads, N / m.chunk);
         launch_k(k_attn_flash64, dim3(fgrid), dim3(128), 0, st, s.q, kc, vc, m.slot, m.chunk, k.heads, k.kv_heads, s.slots, scale, s.att);
+      } else if (s.hd == 64 && x->long_ctx && &s == &x->bb && m.chunk <= 1 && N <= x->max_batch && k.heads % k.kv_heads == 0 &&
+                 k.heads / k.kv_heads <= 8) {
+        // decode rows at a long context: key ranges over CTAs (row, KV head, range), then the ranges are combined
+        launch_k(k_attn_split64, dim3(N, k.kv_heads, AS_SPLITS), dim3(32 * (k.heads / k.kv_heads)), 0, st, s.q, kc, vc, m.stream, m.slot,
+                 m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.slots, scale, x->att_part);
+        COUNT_LAUNCH();
+        launch_k(k_attn_combine64, dim3(N, k.heads), dim3(64), 0, st, x->att_part, k.heads, s.att);
       } else if (s.hd == 64) {
         launch_k(k_attn_rows<64>, dim3(grid), dim3(128), smem, st, s.q, kc, vc, m.stream, m.slot, m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.slots,
                                                  scale, s.att);

@@ -536,6 +536,133 @@ __device__ __forceinline__ uint32_t fa_pack(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// ---------------------------------------------------------------------------------------------
+// K3 (backbone, row-batched decode at LONG context: a voice prompt): k_attn_rows gives a CTA to one (row, q-head), a thread
+// per key reading its 128-byte row by itself and a serial P.V loop over the keys -- 115 us per layer for 32 streams at
+// 1568 keys, and 8 streams are only 256 CTAs.  Flash-decoding form: a CTA serves (row, KV head, one of AS_SPLITS key
+// ranges); 32-key tiles of K and V are staged ONCE in shared memory (cp.async, double buffered, coalesced) for the
+// heads / kv_heads q-heads of the group, one warp per q-head; lane j scores key j of the tile (the words of a row are
+// walked diagonally, word (i + j) mod 32 at step i: 32 lanes, 32 banks, no padding), online softmax per warp, lane l
+// accumulates output dims 2l, 2l+1; the range's (o[64], m, l) go to ``part`` and k_attn_combine64 adds the ranges of a
+// (row, q-head) in range order.  Used from 256 keys on (host decision, a separate captured graph): below that the
+// two-pass k_attn_rows stays, so short-context results are unchanged.
+// ---------------------------------------------------------------------------------------------
+constexpr int AS_SPLITS = 8;
+constexpr int AS_PW = 66;  // floats per partial: o[64], m, l
+__global__ void __launch_bounds__(256) k_attn_split64(const bf16* __restrict__ q, const bf16* __restrict__ k_cache,
+                                                      const bf16* __restrict__ v_cache, const int* __restrict__ row_stream,
+                                                      const int* __restrict__ row_slot, int imp_B, int imp_pos, int heads,
+                                                      int kv_heads, int slots, float scale, float* __restrict__ part) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ __align__(16) bf16 Ks[2][32 * 64];
+  __shared__ __align__(16) bf16 Vs[2][32 * 64];
+  __shared__ float qs[8][64];
+  const int n = blockIdx.x, kvh = blockIdx.y, z = blockIdx.z, gq = heads / kv_heads;  // launched with 32 * gq threads, gq <= 8
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nthr = blockDim.x;
+  const int nkeys = (row_stream ? row_slot[n] : imp_pos + n / imp_B) + 1;
+  const int chunk = (((nkeys + AS_SPLITS - 1) / AS_SPLITS) + 31) & ~31;  // whole tiles per range
+  const int k0 = z * chunk, k1 = k0 + chunk < nkeys ? k0 + chunk : nkeys;
+  const int h = kvh * gq + warp;
+  float* pp = part + (((size_t)n * heads + h) * AS_SPLITS + z) * AS_PW;
+  if (k0 >= nkeys) {  // an empty range (short context): weight 0 in the combine
+    pp[2 * lane] = 0.f;
+    pp[2 * lane + 1] = 0.f;
+    if (lane == 0) {
+      pp[64] = -INFINITY;
+      pp[65] = 0.f;
+    }
+    return;
+  }
+  const size_t base = ((size_t)(row_stream ? row_stream[n] : n % imp_B) * kv_heads + kvh) * slots * 64;
+  const bf16* kp = k_cache + base;
+  const bf16* vp = v_cache + base;
+  const int ntiles = (k1 - k0 + 31) >> 5;
+  auto load_tile = [&](int t, int buf) {
+    // 32 rows x 8 units of 16 bytes for K and for V; rows past the range are zero (never-written cache rows may hold
+    // Inf / NaN patterns: their probability is 0, but 0 * Inf is not)
+    for (int u = threadIdx.x; u < 32 * 8; u += nthr) {
+      const int r = u >> 3, c8 = (u & 7) * 8, key = k0 + t * 32 + r;
+      if (key < k1) {
+        fa_cp16(&Ks[buf][r * 64 + c8], kp + (size_t)key * 64 + c8);
+        fa_cp16(&Vs[buf][r * 64 + c8], vp + (size_t)key * 64 + c8);
+      } else {
+        *reinterpret_cast<uint4*>(&Ks[buf][r * 64 + c8]) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(&Vs[buf][r * 64 + c8]) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  load_tile(0, 0);
+  {
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(q + ((size_t)n * heads + h) * 64 + lane * 2);
+    qs[warp][lane * 2] = bflo(v);
+    qs[warp][lane * 2 + 1] = bfhi(v);
+  }
+  float m = -INFINITY, l = 0.f, acc0 = 0.f, acc1 = 0.f;
+  for (int t = 0; t < ntiles; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < ntiles) {
+      load_tile(t + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();  // tile t (and, the first time, q) is visible to every warp
+    const uint32_t* kr = reinterpret_cast<const uint32_t*>(&Ks[buf][lane * 64]);
+    const float* qr = qs[warp];
+    float s = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+      const int w = (i + lane) & 31;  // diagonal walk: 32 lanes, 32 different banks
+      const uint32_t kk = kr[w];
+      s = fmaf(qr[2 * w], bflo(kk), s);
+      s = fmaf(qr[2 * w + 1], bfhi(kk), s);
+    }
+    s = (k0 + t * 32 + lane < k1) ? s * scale : -INFINITY;
+    const float m_new = fmaxf(m, warp_max(s));  // (finite: every tile holds at least one key)
+    const float corr = expf(m - m_new);         // (first tile: exp(-inf) = 0)
+    const float p = expf(s - m_new);
+    l = fmaf(l, corr, warp_sum(p));
+    acc0 *= corr;
+    acc1 *= corr;
+    m = m_new;
+    const uint32_t* vr = reinterpret_cast<const uint32_t*>(&Vs[buf][0]) + lane;
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, p, j);
+      const uint32_t vv = vr[j * 32];
+      acc0 = fmaf(pj, bflo(vv), acc0);
+      acc1 = fmaf(pj, bfhi(vv), acc1);
+    }
+    __syncthreads();  // every warp is done with tile t before its buffer is refilled (tile t + 2)
+  }
+  pp[2 * lane] = acc0;
+  pp[2 * lane + 1] = acc1;
+  if (lane == 0) {
+    pp[64] = m;
+    pp[65] = l;
+  }
+}
+// the key ranges of a (row, q-head) added in range order; one thread per output dim
+__global__ void __launch_bounds__(64) k_attn_combine64(const float* __restrict__ part, int heads, bf16* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  const int n = blockIdx.x, h = blockIdx.y, d = threadIdx.x;
+  const float* pp = part + ((size_t)n * heads + h) * AS_SPLITS * AS_PW;
+  float M = -INFINITY;
+#pragma unroll
+  for (int z = 0; z < AS_SPLITS; ++z) M = fmaxf(M, pp[z * AS_PW + 64]);
+  float L = 0.f, O = 0.f;
+#pragma unroll
+  for (int z = 0; z < AS_SPLITS; ++z) {
+    const float w = expf(pp[z * AS_PW + 64] - M);  // (an empty range: exp(-inf) = 0)
+    L = fmaf(pp[z * AS_PW + 65], w, L);
+    O = fmaf(pp[z * AS_PW + d], w, O);
+  }
+  out[((size_t)n * heads + h) * 64 + d] = f2bf(O / L);
+}
+
 __global__ void __launch_bounds__(128) k_attn_flash64(const bf16* __restrict__ q, const bf16* __restrict__ k_cache,
                                                       const bf16* __restrict__ v_cache, const int* __restrict__ row_slot, int chunk,
                                                       int heads, int kv_heads, int slots, float scale, bf16* __restrict__ out) {
