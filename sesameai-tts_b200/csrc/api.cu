@@ -159,7 +159,7 @@ struct csm_ctx {
   mega::Phase* d_phases;
   mega::Sync* d_sync;       // device status word (frame counter + sticky error), always initialised
   unsigned int* mega_att_part;  // tagged partials of the megakernel's split long-context attention
-  float* att_part;              // row-batched decode at long context: (o, m, l) of the key ranges (k_attn_split64)
+  float* att_part;              // row-batched decode at long context: (o, m, l) of the key ranges (k_attn_split64_mma)
   bool long_ctx;                // this call's decode rows see >= ATT_LONG_MIN keys (set by csm_generate_frame)
   unsigned int* h_error;    // mapped host mirror of the error word (owned by the ctx)
   int n_phases, mega_grid;
@@ -1384,8 +1384,13 @@ static int stack_pass_tc(csm_ctx* x, StackDev& s, int N, const RowMeta& m, cudaS
       } else if (s.hd == 64 && x->long_ctx && &s == &x->bb && m.chunk <= 1 && N <= x->max_batch && k.heads % k.kv_heads == 0 &&
                  k.heads / k.kv_heads <= 8) {
         // decode rows at a long context: key ranges over CTAs (row, KV head, range), then the ranges are combined
-        launch_k(k_attn_split64, dim3(N, k.kv_heads, AS_SPLITS), dim3(32 * (k.heads / k.kv_heads)), 0, st, s.q, kc, vc, m.stream, m.slot,
-                 m.imp_B, m.imp_pos, k.heads, k.kv_heads, s.slots, scale, x->att_part);
+        static std::atomic<unsigned long long> attr_am{0};
+        if (!device_done(attr_am, false)) {
+          CU_TRY(cudaFuncSetAttribute(k_attn_split64_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AM_SMEM));
+          device_done(attr_am, true);
+        }
+        launch_k(k_attn_split64_mma, dim3(N, k.kv_heads, AS_SPLITS), dim3(128), AM_SMEM, st, s.q, kc, vc, m.stream, m.slot, m.imp_B,
+                 m.imp_pos, k.heads, k.kv_heads, s.slots, scale, x->att_part);
         COUNT_LAUNCH();
         launch_k(k_attn_combine64, dim3(N, k.heads), dim3(64), 0, st, x->att_part, k.heads, s.att);
       } else if (s.hd == 64) {

@@ -537,113 +537,18 @@ __device__ __forceinline__ uint32_t fa_pack(float lo, float hi) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3 (backbone, row-batched decode at LONG context: a voice prompt): k_attn_rows gives a CTA to one (row, q-head), a thread
+// K3 (backbone, row-batched decode at LONG context: a voice prompt).  k_attn_rows gives a CTA to one (row, q-head), a thread
 // per key reading its 128-byte row by itself and a serial P.V loop over the keys -- 115 us per layer for 32 streams at
-// 1568 keys, and 8 streams are only 256 CTAs.  Flash-decoding form: a CTA serves (row, KV head, one of AS_SPLITS key
-// ranges); 32-key tiles of K and V are staged ONCE in shared memory (cp.async, double buffered, coalesced) for the
-// heads / kv_heads q-heads of the group, one warp per q-head; lane j scores key j of the tile (the words of a row are
-// walked diagonally, word (i + j) mod 32 at step i: 32 lanes, 32 banks, no padding), online softmax per warp, lane l
-// accumulates output dims 2l, 2l+1; the range's (o[64], m, l) go to ``part`` and k_attn_combine64 adds the ranges of a
-// (row, q-head) in range order.  Used from 256 keys on (host decision, a separate captured graph): below that the
-// two-pass k_attn_rows stays, so short-context results are unchanged.
+// 1568 keys, and 8 streams are only 256 CTAs.  Flash-decoding form: the keys of a (row, KV head) are cut into AS_SPLITS
+// ranges, one CTA each (k_attn_split64_mma below), whose partial (o[64], m, l) go to ``part``; k_attn_combine64 adds
+// the ranges of a (row, q-head) in range order.  Used from 256 keys on (host decision, a separate captured graph): below
+// that the two-pass k_attn_rows stays, so short-context results are unchanged.
 // ---------------------------------------------------------------------------------------------
-constexpr int AS_SPLITS = 8;
-constexpr int AS_PW = 66;  // floats per partial: o[64], m, l
-__global__ void __launch_bounds__(256) k_attn_split64(const bf16* __restrict__ q, const bf16* __restrict__ k_cache,
-                                                      const bf16* __restrict__ v_cache, const int* __restrict__ row_stream,
-                                                      const int* __restrict__ row_slot, int imp_B, int imp_pos, int heads,
-                                                      int kv_heads, int slots, float scale, float* __restrict__ part) {
-  pdl_wait();
-  pdl_trigger();
-  __shared__ __align__(16) bf16 Ks[2][32 * 64];
-  __shared__ __align__(16) bf16 Vs[2][32 * 64];
-  __shared__ float qs[8][64];
-  const int n = blockIdx.x, kvh = blockIdx.y, z = blockIdx.z, gq = heads / kv_heads;  // launched with 32 * gq threads, gq <= 8
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nthr = blockDim.x;
-  const int nkeys = (row_stream ? row_slot[n] : imp_pos + n / imp_B) + 1;
-  const int chunk = (((nkeys + AS_SPLITS - 1) / AS_SPLITS) + 31) & ~31;  // whole tiles per range
-  const int k0 = z * chunk, k1 = k0 + chunk < nkeys ? k0 + chunk : nkeys;
-  const int h = kvh * gq + warp;
-  float* pp = part + (((size_t)n * heads + h) * AS_SPLITS + z) * AS_PW;
-  if (k0 >= nkeys) {  // an empty range (short context): weight 0 in the combine
-    pp[2 * lane] = 0.f;
-    pp[2 * lane + 1] = 0.f;
-    if (lane == 0) {
-      pp[64] = -INFINITY;
-      pp[65] = 0.f;
-    }
-    return;
-  }
-  const size_t base = ((size_t)(row_stream ? row_stream[n] : n % imp_B) * kv_heads + kvh) * slots * 64;
-  const bf16* kp = k_cache + base;
-  const bf16* vp = v_cache + base;
-  const int ntiles = (k1 - k0 + 31) >> 5;
-  auto load_tile = [&](int t, int buf) {
-    // 32 rows x 8 units of 16 bytes for K and for V; rows past the range are zero (never-written cache rows may hold
-    // Inf / NaN patterns: their probability is 0, but 0 * Inf is not)
-    for (int u = threadIdx.x; u < 32 * 8; u += nthr) {
-      const int r = u >> 3, c8 = (u & 7) * 8, key = k0 + t * 32 + r;
-      if (key < k1) {
-        fa_cp16(&Ks[buf][r * 64 + c8], kp + (size_t)key * 64 + c8);
-        fa_cp16(&Vs[buf][r * 64 + c8], vp + (size_t)key * 64 + c8);
-      } else {
-        *reinterpret_cast<uint4*>(&Ks[buf][r * 64 + c8]) = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(&Vs[buf][r * 64 + c8]) = make_uint4(0, 0, 0, 0);
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  load_tile(0, 0);
-  {
-    const uint32_t v = *reinterpret_cast<const uint32_t*>(q + ((size_t)n * heads + h) * 64 + lane * 2);
-    qs[warp][lane * 2] = bflo(v);
-    qs[warp][lane * 2 + 1] = bfhi(v);
-  }
-  float m = -INFINITY, l = 0.f, acc0 = 0.f, acc1 = 0.f;
-  for (int t = 0; t < ntiles; ++t) {
-    const int buf = t & 1;
-    if (t + 1 < ntiles) {
-      load_tile(t + 1, buf ^ 1);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    __syncthreads();  // tile t (and, the first time, q) is visible to every warp
-    const uint32_t* kr = reinterpret_cast<const uint32_t*>(&Ks[buf][lane * 64]);
-    const float* qr = qs[warp];
-    float s = 0.f;
-#pragma unroll 8
-    for (int i = 0; i < 32; ++i) {
-      const int w = (i + lane) & 31;  // diagonal walk: 32 lanes, 32 different banks
-      const uint32_t kk = kr[w];
-      s = fmaf(qr[2 * w], bflo(kk), s);
-      s = fmaf(qr[2 * w + 1], bfhi(kk), s);
-    }
-    s = (k0 + t * 32 + lane < k1) ? s * scale : -INFINITY;
-    const float m_new = fmaxf(m, warp_max(s));  // (finite: every tile holds at least one key)
-    const float corr = expf(m - m_new);         // (first tile: exp(-inf) = 0)
-    const float p = expf(s - m_new);
-    l = fmaf(l, corr, warp_sum(p));
-    acc0 *= corr;
-    acc1 *= corr;
-    m = m_new;
-    const uint32_t* vr = reinterpret_cast<const uint32_t*>(&Vs[buf][0]) + lane;
-#pragma unroll 8
-    for (int j = 0; j < 32; ++j) {
-      const float pj = __shfl_sync(0xffffffffu, p, j);
-      const uint32_t vv = vr[j * 32];
-      acc0 = fmaf(pj, bflo(vv), acc0);
-      acc1 = fmaf(pj, bfhi(vv), acc1);
-    }
-    __syncthreads();  // every warp is done with tile t before its buffer is refilled (tile t + 2)
-  }
-  pp[2 * lane] = acc0;
-  pp[2 * lane + 1] = acc1;
-  if (lane == 0) {
-    pp[64] = m;
-    pp[65] = l;
-  }
-}
+#ifndef CSM_AS_SPLITS
+#define CSM_AS_SPLITS 8
+#endif
+constexpr int AS_SPLITS = CSM_AS_SPLITS;
+constexpr int AS_PW = 66;  // floats per partial: o[64], m (log2 units), l
 // the key ranges of a (row, q-head) added in range order; one thread per output dim
 __global__ void __launch_bounds__(64) k_attn_combine64(const float* __restrict__ part, int heads, bf16* __restrict__ out) {
   pdl_wait();
@@ -656,7 +561,7 @@ __global__ void __launch_bounds__(64) k_attn_combine64(const float* __restrict__
   float L = 0.f, O = 0.f;
 #pragma unroll
   for (int z = 0; z < AS_SPLITS; ++z) {
-    const float w = expf(pp[z * AS_PW + 64] - M);  // (an empty range: exp(-inf) = 0)
+    const float w = exp2f(pp[z * AS_PW + 64] - M);  // (an empty range: exp2(-inf) = 0)
     L = fmaf(pp[z * AS_PW + 65], w, L);
     O = fmaf(pp[z * AS_PW + d], w, O);
   }
@@ -800,6 +705,175 @@ __global__ void __launch_bounds__(128) k_attn_flash64(const bf16* __restrict__ q
       *reinterpret_cast<uint32_t*>(out + ((n0 + r_lo) * heads + h) * 64 + d * 8 + 2 * qd) = fa_pack(o[d][0] * i_lo, o[d][1] * i_lo);
     if (r_hi < nrows)
       *reinterpret_cast<uint32_t*>(out + ((n0 + r_hi) * heads + h) * 64 + d * 8 + 2 * qd) = fa_pack(o[d][2] * i_hi, o[d][3] * i_hi);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// One key range on the TENSOR CORES.  A CTA serves (row, KV head, key range): the q-heads of the group are the first
+// rows of ONE 16-row mma tile (the rest zero), the range is walked in passes of 256 keys staged cooperatively
+// (cp.async), warp w takes keys [64 w, 64 w + 64) of the pass with k_attn_flash64's inner loop -- S = Q K^T and
+// O += P V as mma.m16n8k16, online softmax in log2 units -- and the four warps' (o, m, l) are combined in shared
+// memory before the range's partial goes to ``part``.  (A CUDA-core version of the same decomposition -- a warp per
+// q-head, a lane per key -- was bound by its shared-memory instruction stream, a load per two multiply-adds:
+// 5.59 / 8.54 ms per step at 8 / 32 streams against 5.24 / 8.13 ms.)
+// ---------------------------------------------------------------------------------------------
+constexpr int AM_PASS = 256;  // keys per pass: 4 warps x 64
+constexpr size_t AM_SMEM = (size_t)(16 + 2 * AM_PASS) * FA_LD * sizeof(bf16);
+__global__ void __launch_bounds__(128) k_attn_split64_mma(const bf16* __restrict__ q, const bf16* __restrict__ k_cache,
+                                                          const bf16* __restrict__ v_cache, const int* __restrict__ row_stream,
+                                                          const int* __restrict__ row_slot, int imp_B, int imp_pos, int heads,
+                                                          int kv_heads, int slots, float scale, float* __restrict__ part) {
+  pdl_wait();
+  pdl_trigger();
+  extern __shared__ __align__(16) unsigned char am_raw[];
+  bf16* Qs = reinterpret_cast<bf16*>(am_raw);  // [16][FA_LD]: rows >= gq are zero
+  bf16* Ks = Qs + 16 * FA_LD;                  // [AM_PASS][FA_LD]
+  bf16* Vs = Ks + AM_PASS * FA_LD;             // [AM_PASS][FA_LD]
+  const int n = blockIdx.x, kvh = blockIdx.y, z = blockIdx.z, gq = heads / kv_heads;  // gq <= 8
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, qd = lane & 3;
+  const int nkeys = (row_stream ? row_slot[n] : imp_pos + n / imp_B) + 1;
+  const int chunk = (((nkeys + AS_SPLITS - 1) / AS_SPLITS) + 63) & ~63;  // whole 64-key tiles per range
+  const int k0 = z * chunk, k1 = k0 + chunk < nkeys ? k0 + chunk : nkeys;
+  const int h0 = kvh * gq;
+  if (k0 >= nkeys) {  // an empty range: weight 0 in the combine
+    for (int i = tid; i < gq * AS_PW; i += 128) {
+      const int r = i / AS_PW, d = i - r * AS_PW;
+      part[(((size_t)n * heads + h0 + r) * AS_SPLITS + z) * AS_PW + d] = d == 64 ? -INFINITY : 0.f;
+    }
+    return;
+  }
+  const size_t base = ((size_t)(row_stream ? row_stream[n] : n % imp_B) * kv_heads + kvh) * slots * 64;
+  const bf16* kp = k_cache + base;
+  const bf16* vp = v_cache + base;
+  for (int u = tid; u < 16 * 8; u += 128) {
+    const int r = u >> 3, c8 = (u & 7) * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (r < gq) v = *reinterpret_cast<const uint4*>(q + ((size_t)n * heads + h0 + r) * 64 + c8);
+    *reinterpret_cast<uint4*>(&Qs[r * FA_LD + c8]) = v;
+  }
+  float m_lo = -INFINITY, l_lo = 0.f;
+  float o[8][4];
+#pragma unroll
+  for (int d = 0; d < 8; ++d)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[d][e] = 0.f;
+  const float sl2 = scale * 1.4426950408889634f;  // scores in log2 units
+  uint32_t qa[4][4];
+  bool have_q = false;
+  for (int kb = k0; kb < k1; kb += AM_PASS) {
+    // stage the pass: 256 rows x 8 units of 16 bytes for K and for V; rows past the range are zero
+    for (int u = tid; u < AM_PASS * 8; u += 128) {
+      const int r = u >> 3, c8 = (u & 7) * 8, key = kb + r;
+      if (key < k1) {
+        fa_cp16(&Ks[r * FA_LD + c8], kp + (size_t)key * 64 + c8);
+        fa_cp16(&Vs[r * FA_LD + c8], vp + (size_t)key * 64 + c8);
+      } else {
+        *reinterpret_cast<uint4*>(&Ks[r * FA_LD + c8]) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(&Vs[r * FA_LD + c8]) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (!have_q) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        fa_ldm4(qa[kk], &Qs[(((lane >> 3) & 1) * 8 + (lane & 7)) * FA_LD + kk * 16 + (lane >> 4) * 8]);
+      have_q = true;
+    }
+    const int tk0 = kb + warp * 64;  // this warp's 64 keys of the pass
+    if (tk0 < k1) {
+      const bf16* Kt = Ks + warp * 64 * FA_LD;
+      const bf16* Vt = Vs + warp * 64 * FA_LD;
+      float sc[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sc[j][e] = 0.f;
+#pragma unroll
+        for (int kk2 = 0; kk2 < 2; ++kk2) {
+          uint32_t kf[4];
+          fa_ldm4(kf, &Kt[(j * 8 + (lane & 7)) * FA_LD + kk2 * 32 + (lane >> 3) * 8]);
+          fa_mma(sc[j], qa[2 * kk2], kf[0], kf[1]);
+          fa_mma(sc[j], qa[2 * kk2 + 1], kf[2], kf[3]);
+        }
+      }
+      const int key0 = tk0 + 2 * qd;
+      float mx = m_lo;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          sc[j][e] = (key0 + j * 8 + e < k1) ? sc[j][e] * sl2 : -INFINITY;
+          mx = fmaxf(mx, sc[j][e]);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float c_lo = exp2f(m_lo - mx);  // (the tile's first key is inside the range: mx is finite)
+      m_lo = mx;
+      float ps = 0.f;
+      uint32_t pa[4][4];  // P as A fragments; the rows g + 8 of the tile are unused (zero q rows): their P is 0
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float p0 = exp2f(sc[j][0] - m_lo), p1 = exp2f(sc[j][1] - m_lo);
+        ps += p0 + p1;
+        pa[j >> 1][(j & 1) * 2] = fa_pack(p0, p1);
+        pa[j >> 1][(j & 1) * 2 + 1] = 0u;
+      }
+      l_lo = l_lo * c_lo + ps;
+#pragma unroll
+      for (int d = 0; d < 8; ++d) {
+        o[d][0] *= c_lo;
+        o[d][1] *= c_lo;
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int d2 = 0; d2 < 4; ++d2) {
+          uint32_t vb[4];
+          fa_ldm4t(vb, &Vt[(t * 16 + ((lane >> 3) & 1) * 8 + (lane & 7)) * FA_LD + d2 * 16 + (lane >> 4) * 8]);
+          fa_mma(o[2 * d2], pa[t], vb[0], vb[1]);
+          fa_mma(o[2 * d2 + 1], pa[t], vb[2], vb[3]);
+        }
+    }
+    __syncthreads();  // the pass buffers are free for the next pass (and, after the last one, for the warps' partials)
+  }
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+  // the four warps' partials of row g (q-head h0 + g): [warp][g][AS_PW] floats over the K buffer
+  float* wp = reinterpret_cast<float*>(Ks);
+  if (g < gq) {
+    float* dst = wp + ((size_t)warp * 8 + g) * AS_PW;
+#pragma unroll
+    for (int d = 0; d < 8; ++d) {
+      dst[d * 8 + 2 * qd] = o[d][0];
+      dst[d * 8 + 2 * qd + 1] = o[d][1];
+    }
+    if (qd == 0) {
+      dst[64] = m_lo;
+      dst[65] = l_lo;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < gq * 64; i += 128) {
+    const int r = i >> 6, d = i & 63;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) M = fmaxf(M, wp[((size_t)w * 8 + r) * AS_PW + 64]);
+    float L = 0.f, O = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {  // warp order: deterministic (a warp without keys: exp2(-inf) = 0)
+      const float* src = wp + ((size_t)w * 8 + r) * AS_PW;
+      const float wgt = exp2f(src[64] - M);
+      L = fmaf(src[65], wgt, L);
+      O = fmaf(src[d], wgt, O);
+    }
+    float* pp = part + (((size_t)n * heads + h0 + r) * AS_SPLITS + z) * AS_PW;
+    pp[d] = O;
+    if (d == 0) {
+      pp[64] = M;
+      pp[65] = L;
+    }
   }
 }
 

@@ -45,6 +45,14 @@ for _ in range(4):
     tok, msk, pos = next_inputs(s, pos)
 torch.cuda.synchronize(); pm1.check_device_error()
 print("split attention ok")
+# 3b. row-batched decode at long context: 3 streams, 300-frame prompt (k_attn_split64_mma + k_attn_combine64), 2 frames
+pm3, _ = build_product(dict(spec, batch=3), batch=3)
+tok, msk, pos = syn.voice_prompt(3, 3, 20, 70, 30, seed=5, text_vocab=1000, device="cuda")
+for _ in range(3):
+    s = pm3.generate_frame(tok, msk, pos, 0.9, 50)
+    tok, msk, pos = next_inputs(s, pos)
+torch.cuda.synchronize(); pm3.check_device_error()
+print("long-context batched decode ok")
 # 4. Mimi: batched decode of 3 utterances x 4 frames (resident tail GEMM, fused final conv, batched transformer) + a stream
 codec = MimiCodec(max_frames=8); syn.init_mimi_weights(codec, 2024); codec.to(dev)
 codes = syn.hash_ints(3 * 32 * 4, 5, 4, 2048, device=dev).view(3, 32, 4)
