@@ -95,7 +95,10 @@ extern "C" const char* csm_last_error(void) { return g_err; }
 // ---------------------------------------------------------------------------------------------
 static const int PREFILL_CHUNK = 8;     // prompt frames per stream per small-row pass
 static const int PREFILL_TC_ROWS = 4096;  // rows per tensor-core prefill pass
-static const int PREFILL_TC_MIN = 64;     // prompt rows (B * (S-1)) from which the tcgen05 path is used
+// prompt rows (B * (S-1)) from which the row-batched path is used (skinny GEMMs up to 32 rows, tcgen05 beyond): a
+// 32-frame text prompt as four per-op passes of 8 rows cost 4.6 ms, and a serving loop with ragged admission pays that
+// nearly every round (config 5 with 32 lanes: 9.4 -> 8.0 s).  Up to 8 rows the per-op pass is one launch chain anyway.
+static const int PREFILL_TC_MIN = 9;
 static const int DECODE_TC_MIN = 16;      // streams from which a decode step runs on the tcgen05 GEMM
 static int skinny_max_rows() {  // rows up to which a linear layer runs on the skinny fragment-major GEMM (CSM_SKINNY_MAX_ROWS: experiments)
   static int v = -1;
@@ -1040,11 +1043,14 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
   }
   if (path == CSM_PATH_AUTO) path = (B == 1 && x->mega_ok) ? CSM_PATH_MEGA : CSM_PATH_GRAPH;
   if (path == CSM_PATH_MEGA && (B != 1 || !x->mega_ok)) return set_err(CSM_ERR_ARG, "megakernel path needs batch 1");
-  // prompt rows [0, S-1): tensor-core passes when there is a real contraction (>= 64 rows), else
-  // small-row passes of up to PREFILL_CHUNK frames per stream
+  // prompt rows [0, S-1): row-batched passes (skinny / tcgen05 GEMMs, tiled attention) from PREFILL_TC_MIN rows on,
+  // else per-op small-row passes of up to PREFILL_CHUNK frames per stream
   int prefill_path = opts ? opts->prefill : 0;
   if (prefill_path == CSM_PREFILL_AUTO)
-    prefill_path = ((long long)B * (S - 1) >= PREFILL_TC_MIN && x->cfg.backbone.dim % 64 == 0) ? CSM_PREFILL_TENSOR : CSM_PREFILL_SMALL_ROW;
+  {
+    static const int tc_min = getenv("CSM_PREFILL_TC_MIN") ? atoi(getenv("CSM_PREFILL_TC_MIN")) : PREFILL_TC_MIN;
+    prefill_path = ((long long)B * (S - 1) >= tc_min && x->cfg.backbone.dim % 64 == 0) ? CSM_PREFILL_TENSOR : CSM_PREFILL_SMALL_ROW;
+  }
   const int per_pass = prefill_path == CSM_PREFILL_TENSOR ? (PREFILL_TC_ROWS / B > 0 ? PREFILL_TC_ROWS / B : 1) : PREFILL_CHUNK;
   for (int s0 = 0; s0 < S - 1; s0 += per_pass) {
     const int chunk = (S - 1 - s0) < per_pass ? (S - 1 - s0) : per_pass;
