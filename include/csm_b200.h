@@ -273,6 +273,10 @@ typedef struct csm_phase_info {
   int32_t nb, K, rows, R, G, rot, ldx, ldo, split_row, attn_prologue, has_qkv_table;
   int32_t x_src[2], resid_src[2], q_src, logits_src;
   uint64_t t_x, t_out, t_out2, t_q, t_kv, t_logits, t_next; /* byte offsets of the tagged vectors (0: unused) */
+  /* ordering of the depth decoder's plain KV-cache rows: before this phase every CTA releases (1) / acquires (2)
+   * through done words tagged with phase done_src; pos_mode 0 = depth decoder (cache rows [0, pos0) were written
+   * in earlier codebook steps of the same launch), 1 = backbone (rows of earlier launches) */
+  int32_t kv_sync, done_src, pos0, pos_mode;
 } csm_phase_info;
 int32_t csm_debug_phase_table(const csm_config *cfg, int32_t n_ctas, int32_t with_qkv_table, csm_phase_info *out,
                               int32_t max_phases);

@@ -142,6 +142,7 @@ struct csm_ctx {
   bf16* f_heads;  // fragment-major audio heads [C-1][Vf][Dd]
   int Vf;         // audio vocab rounded up to 16 rows (fragment-major row groups)
   uint32_t* t_logits;  // tagged logits [Vf]
+  uint32_t* t_done;    // tagged per-CTA "KV rows released" words (mega::kv_step_sync)
   char* tagged_base;   // all tagged words live in [tagged_base, tagged_base + tagged_bytes): zeroed at create
   size_t tagged_bytes;
   bf16* proj_table;  // projection(audio_embeddings[cb*V + tok]) for cb < C-1: [(C-1)*V][Dd]
@@ -284,6 +285,7 @@ static size_t carve_all(csm_ctx* x, char* base) {
   carve_tagged(cv, x->bb);
   carve_tagged(cv, x->dec);
   x->t_logits = cv.take<uint32_t>((size_t)x->Vf);
+  x->t_done = cv.take<uint32_t>(1024);  // one word per CTA (kv_step_sync)
   cv.off = (cv.off + 255) & ~(size_t)255;
   x->tagged_base = base ? base + t0 : nullptr;
   x->tagged_bytes = cv.off - t0;
@@ -657,6 +659,11 @@ static void build_mega_phases(csm_ctx* x, MegaBuild& mb) {
     for (int l = 0; l < c.decoder.layers; ++l)
       stack_phases(x, x->dec, x->mega_Rdec, l, nb, mega::POS_FIXED, pos0, true, mb, dsrc, (x->mega_keep >> (4 * (l & 7))) & 15,
                    (x->qkv_table_ok && i >= 2 && l == 0) ? dsrc[0] : -1);
+    // KV rows of steps <= i are read from the cache in step i + 1: released after the last layer's gate/up phase
+    // (= before its down phase), acquired before the sampling phase (mega::kv_step_sync; flags sit on the NEXT phase)
+    const bool kv_step = i + 1 < C && mb.ncta <= 1024;
+    const int igu = (int)mb.v.size() - 2;
+    if (kv_step) { mb.v[igu + 1].kv_sync = 1; mb.v[igu + 1].done_src = igu; mb.v[igu + 1].t_done = x->t_done; }
     mega::Phase h = gemv_phase_desc(mb, x->f_heads + (size_t)(i - 1) * x->Vf * Dd, x->Vf, Dd, x->mega_Rh,
                                     x->dec.t_h + (size_t)(nb - 1) * Dd, Dd, 1, EPI_PLAIN, x->dec.norm, eps, x->t_logits, x->Vf);
     h.x_src[0] = h.x_src[1] = dsrc[nb - 1];
@@ -665,6 +672,7 @@ static void build_mega_phases(csm_ctx* x, MegaBuild& mb) {
     mb.v.push_back(h);
     const int is = (int)mb.v.size();
     mb.v.push_back(sample(i, ih, (i + 1 < C) ? x->dec.t_h : nullptr));
+    if (kv_step) { mb.v[is].kv_sync = 2; mb.v[is].done_src = igu; mb.v[is].t_done = x->t_done; }
     dsrc[0] = is;
   }
 }
@@ -1138,6 +1146,7 @@ extern "C" int32_t csm_debug_phase_table(const csm_config* cfg, int32_t n_ctas, 
     o.q_src = ph.q_src; o.logits_src = ph.logits_src;
     o.t_x = off(ph.t_x); o.t_out = off(ph.t_out); o.t_out2 = off(ph.t_out2); o.t_q = off(ph.t_q); o.t_kv = off(ph.t_kv);
     o.t_logits = off(ph.t_logits); o.t_next = off(ph.t_next);
+    o.kv_sync = ph.kv_sync; o.done_src = ph.done_src; o.pos0 = ph.pos0; o.pos_mode = ph.pos_mode;
   }
   return n;
 }

@@ -33,6 +33,9 @@ namespace mega {
 
 constexpr int NW = 8;                 // warps per CTA
 constexpr int NCT = NW * 32;          // consumer threads per CTA
+#ifndef MEGA_KV_FENCE
+#define MEGA_KV_FENCE 24  /* bit 3: release / acquire once per codebook step (kv_step_sync), bit 4: as st.release / ld.acquire instead of fence + relaxed access; measurement variants: 0 = none, bit 0: fence in every QKV epilogue, bit 1: in every attn_prefetch, bit 2: in the sampling phase's gather */
+#endif
 constexpr int NTHREADS = NCT + 32;    // + one producer warp that feeds the weight rings
 #ifndef MEGA_SLOTS
 #define MEGA_SLOTS 4
@@ -107,6 +110,11 @@ struct __align__(16) Phase {
   int keep;  // this matrix is loaded with the L2 evict-last policy
   int TV;    // EMBED: text vocabulary (range check of the text column)
   int rope_len;  // EMBED: rows of the backbone RoPE table (range check of input_pos)
+  // ordering of the depth decoder's plain KV rows, once per codebook step (MEGA_KV_FENCE bit 3, see kv_fence):
+  // before this phase every CTA ... kv_sync 1: releases its rows (done word t_done[cta] tagged with phase done_src);
+  // 2: acquires (polls all CTAs' done words for the tag of phase done_src)
+  int kv_sync, done_src;
+  uint32_t* t_done;
 };
 static_assert(sizeof(Phase) % 16 == 0, "Phase must be copyable in 16-byte units");
 
@@ -249,12 +257,18 @@ __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1
 // tag per frame, no ordering assumed at all) was built and measured too and is slower still (+0.5 ms: its
 // reads cannot be asynchronous).  tests/test_gpu_stress.py runs 2000+ frames against the per-op kernels, which
 // have a kernel boundary between every write and read.  (The backbone cache is read by the NEXT launch.)
-#ifndef MEGA_KV_FENCE
-#define MEGA_KV_FENCE 0  /* bit 0: QKV-epilogue writers, bit 1: readers (attn_prefetch), bit 2: sampling-phase writers */
-#endif
 template <int WHO>
 __device__ __forceinline__ void kv_fence() {
   if ((MEGA_KV_FENCE) & WHO) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+
+__device__ __forceinline__ uint4 lda4(const uint32_t* p) {
+  uint4 v;
+  asm volatile("ld.acquire.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // ---- tagged activations ------------------------------------------------------------------------------
@@ -281,8 +295,15 @@ __device__ __forceinline__ uint32_t ldv1(const uint32_t* p) {
   asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void stv4(uint32_t* p, const uint4& v) { __stcg(reinterpret_cast<uint4*>(p), v); }
-__device__ __forceinline__ void stv2(uint32_t* p, const uint2& v) { __stcg(reinterpret_cast<uint2*>(p), v); }
+// Tagged words are written with st.relaxed.gpu and polled with ld.volatile (= relaxed, system scope): both sides are
+// strong operations in the PTX memory model, so the hand-off itself is race-free word by word (every word carries its
+// own tag).  Same SASS as a .cg store (STG.E.STRONG.GPU): the qualifier costs nothing.
+__device__ __forceinline__ void stv4(uint32_t* p, const uint4& v) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void stv2(uint32_t* p, const uint2& v) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
 __device__ __forceinline__ bool fresh4(const uint4& v, uint32_t tag) {
   return ((((v.x ^ tag) | (v.y ^ tag)) | ((v.z ^ tag) | (v.w ^ tag))) & 0xffff0000u) == 0;
 }
@@ -311,7 +332,7 @@ __device__ __forceinline__ float tval(uint32_t w) { return __uint_as_float(w << 
 __device__ __forceinline__ void rep_st1(uint32_t* p, int rs, uint32_t v) {
 #pragma unroll
   for (int r = 0; r < REP; ++r)
-    if (r == 0 || rs) __stcg(p + (size_t)r * rs, v);
+    if (r == 0 || rs) st_relaxed_gpu(p + (size_t)r * rs, v);
 }
 __device__ __forceinline__ void rep_st2(uint32_t* p, int rs, const uint2& v) {
 #pragma unroll
@@ -1466,6 +1487,47 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
 }
 
 // ---- the kernel ------------------------------------------------------------------------------------
+// Ordering of the depth decoder's plain KV rows, once per codebook step (MEGA_KV_FENCE bit 3).  Called by every CTA --
+// with or without work in the phase -- after the CTA barrier that ends the phase BEFORE one flagged kv_sync (the flag
+// sits on the next descriptor because that one stays put until this warp passes the next barrier):
+//  1 (before the last layer's down phase of step i, i.e. after its gate/up phase: every KV row of steps <= i that
+//    this CTA wrote -- QKV epilogues, the sampling phase's table gather -- precedes the barrier): ONE thread runs the
+//    release pattern  fence.acq_rel.gpu ; st.relaxed.gpu done[cta] = tag(done_src).  The fence is cumulative over
+//    the other threads' stores through the barrier.  Off the critical path: the down phase starts by waiting
+//    > 1.5 us for the gate/up words of the other CTAs.
+//  2 (before the sampling phase of step i, two phases later): the last warp runs the acquire pattern  ld.volatile
+//    done[all CTAs] until they carry that tag ; fence.acq_rel.gpu.  The words were stored ~10 us earlier, so this is
+//    one L2 round trip, and only ONE CTA works in the sampling phase.  Every attn_prefetch of step i + 1 comes after
+//    the barrier that ends the sampling phase, i.e. after this fence in causality order, and reads rows of
+//    steps <= i only (the row of step i + 1 travels as tagged words).
+// Release -> observed done word -> acquire is a direct synchronizes-with edge between EVERY writer CTA and EVERY
+// reader CTA; no chain of relaxed hand-offs is relied on.
+__device__ __forceinline__ void kv_step_sync(const Phase& ph, const Ctx& c) {
+  constexpr bool FUSED = ((MEGA_KV_FENCE) & 16) != 0;  // st.release / ld.acquire instead of fence + relaxed access
+  const uint32_t dtag = tag_of(c.seq, ph.done_src);
+  if (ph.kv_sync == 1) {
+    if (c.tid == NCT - 1) {
+      if (FUSED) {
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ph.t_done + blockIdx.x), "r"(dtag) : "memory");
+      } else {
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        st_relaxed_gpu(ph.t_done + blockIdx.x, dtag);
+      }
+      if (blockIdx.x == gridDim.x - 1)  // pad to whole 16-byte units for the pollers
+        for (unsigned q = gridDim.x; (q & 3u) != 0; ++q) st_relaxed_gpu(ph.t_done + q, dtag);
+    }
+  } else if (c.warp == NW - 1) {
+    for (unsigned q = c.lane * 4; q < gridDim.x; q += 128) {
+      uint4 v = FUSED ? lda4(ph.t_done + q) : ldv4(ph.t_done + q);
+      for (unsigned spin = 0; !fresh4(v, dtag); ++spin) {
+        if (give_up(c.sync, spin, 0x40b)) break;
+        v = FUSED ? lda4(ph.t_done + q) : ldv4(ph.t_done + q);
+      }
+    }
+    if (!FUSED) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1)
 k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* __restrict__ P, Sync* sync,
              unsigned long long* __restrict__ trace /* optional [ncta][nphases][16]: 4 globaltimer ns + 12 clock64 marks, thread 0 of every CTA */,
@@ -1540,7 +1602,8 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
     // end of phase inside the CTA: shared activations / partial sums may be overwritten from here on
     csync<NCT, CBAR>();
     if (p + 1 < nphases) {
-      const Phase& nx = phbuf[(p + 1) & 1];
+      const Phase& nx = phbuf[(p + 1) & 1];  // stable until this warp passes the NEXT phase's barrier (ph is not: the others re-stage it)
+      if (((MEGA_KV_FENCE) & 8) && nx.kv_sync) kv_step_sync(nx, c);
       if (nx.type == PH_GEMV && nx.attn_prologue) {
         const int cl = local_cta(blockIdx.x, gridDim.x, nx.rot);
         if (nx.gq + (cl < nx.gr ? 1 : 0) > 0) attn_prefetch(nx, c);

@@ -40,7 +40,8 @@ class PhaseInfo(C.Structure):
     _fields_ = ([(n, C.c_int32) for n in ("type", "epi", "nb", "K", "rows", "R", "G", "rot", "ldx", "ldo", "split_row",
                                            "attn_prologue", "has_qkv_table")]
                 + [("x_src", C.c_int32 * 2), ("resid_src", C.c_int32 * 2), ("q_src", C.c_int32), ("logits_src", C.c_int32)]
-                + [(n, C.c_uint64) for n in ("t_x", "t_out", "t_out2", "t_q", "t_kv", "t_logits", "t_next")])
+                + [(n, C.c_uint64) for n in ("t_x", "t_out", "t_out2", "t_q", "t_kv", "t_logits", "t_next")]
+                + [(n, C.c_int32) for n in ("kv_sync", "done_src", "pos0", "pos_mode")])
 
 
 class LayerWeights(C.Structure):

@@ -3,6 +3,10 @@
   * no vector is rewritten sooner than two phases after it was written (a consumer of phase p's words
     may still be reading them while phase p+1 runs; seeing a word of phase p+1 proves phase p is over);
   * the consumer of a vector comes after its producer.
+  * the depth decoder's PLAIN cache rows (written by a QKV epilogue or the sampling phase's table gather, read by
+    other CTAs in later codebook steps of the same launch): between every writer and every reader there is a release
+    (all CTAs, after the writer phase) and an acquire (all CTAs, on that release's done words, a whole phase before
+    the reader's prefetch) -- mega::kv_step_sync.
 No GPU needed: csm_debug_phase_table builds the table against an imaginary workspace."""
 import ctypes as C
 
@@ -104,3 +108,48 @@ def test_tagged_hand_off_invariants(tiny, ncta, qkv):
             assert x.R in (8, 16) and x.K % 256 == 0
             if ncta >= 132:
                 assert -(-x.G // ncta) <= 8
+
+
+@pytest.mark.parametrize("tiny", [True, False])
+@pytest.mark.parametrize("ncta", [148, 16])
+@pytest.mark.parametrize("qkv", [0, 1])
+def test_plain_kv_rows_are_released_and_acquired(tiny, ncta, qkv):
+    """Flags sit on the NEXT phase: kv_sync on phase f runs after the barrier that ends phase f - 1, in every CTA.
+    A reader phase p prefetches its cached rows after the barrier that ends phase p - 1."""
+    cfg = _cfg(tiny)
+    ph = _table(cfg, ncta, qkv)
+    first_dec = 1 + 5 * cfg.backbone.layers + 2
+    releases = {}           # done_src -> flagged phase
+    acquired_release = -1   # flagged phase of the release that the latest acquire observed
+    acquire_at = -1
+    writers_before_step = -1  # last phase that wrote plain rows the current step reads from the cache
+    last_writer = -1
+    readers = 0
+    for p, x in enumerate(ph):
+        if x.kv_sync == 1:
+            assert x.done_src not in releases, "done-word tags must be unique within a frame"
+            assert 0 <= x.done_src < p
+            releases[x.done_src] = p
+        elif x.kv_sync == 2:
+            assert x.done_src in releases and releases[x.done_src] < p, (p, "acquire without an earlier release")
+            acquired_release, acquire_at = releases[x.done_src], p
+        else:
+            assert x.kv_sync == 0
+        if p < first_dec:
+            continue
+        if x.type == SAMPLE:
+            # rows written up to here (this phase's own gather excluded: its row travels as tagged words in the next
+            # step and is read from the cache only in the step after) are what the next step reads from the cache
+            writers_before_step = last_writer
+            if x.has_qkv_table:
+                last_writer = p
+        elif x.type == GEMV and x.epi == ROPE_KV and x.pos_mode == 0:
+            last_writer = p
+        if x.type == GEMV and x.attn_prologue and x.pos_mode == 0 and x.pos0 > 0:
+            readers += 1
+            assert writers_before_step >= 0
+            # release runs after phase (flag - 1): every writer phase must be <= flag - 1
+            assert acquired_release > writers_before_step, (p, "reads rows of phase", writers_before_step, "released at", acquired_release)
+            # the acquiring warp and the prefetching threads are ordered by the barrier ending phase acquire_at
+            assert acquire_at < p, (p, "acquire at", acquire_at)
+    assert readers == (cfg.codebooks - 2) * cfg.decoder.layers

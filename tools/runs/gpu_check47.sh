@@ -1,9 +1,20 @@
 #!/bin/bash
-# short prompts (9 .. 63 rows) through the row-batched path (skinny / tcgen05 GEMMs) instead of the per-op small-row passes
-T=${1:-r2pf}
+# final tree of round 2 (KV rows released / acquired once per codebook step by default): what the driver runs at round
+# end (GPU tests, smoke, both bench arms), launch list + one ncu --set full capture of the megakernel, and the headline of
+# the unfenced build (-DMEGA_KV_FENCE=0) on the same box for the record
+set -u
 mkdir -p gpurun_out
-CSM_PREFILL_TC_MIN=9 timeout 900 python -m pytest tests -q -m gpu > gpurun_out/${T}_tests.log 2>&1
-tail -6 gpurun_out/${T}_tests.log
-for k in 9 64; do
-  CSM_PREFILL_TC_MIN=$k timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_bench_min$k.json 2> gpurun_out/${T}_bench$k.err
-done
+T=${1:-r2fin6}
+( time python -m pytest tests -m gpu -x -q ) > gpurun_out/${T}_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/${T}_tests.log
+grep -E "passed|failed|rc=|real" gpurun_out/${T}_tests.log | tail -4
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/${T}_smoke.log; tail -2 gpurun_out/${T}_smoke.log
+( time python bench.py --impl reference --steps 20 --warmup 5 ) > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_bench_reference.err
+tail -c 300 gpurun_out/${T}_bench_reference.json
+( time python bench.py ) > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
+tail -4 gpurun_out/${T}_bench.err; head -c 700 gpurun_out/${T}_bench.json; echo
+CSM_B200_LIB=$PWD/sesameai-tts_b200/lib/libcsm_b200_f0.so timeout 120 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-secondary > gpurun_out/${T}_bench_unfenced.json 2> gpurun_out/${T}_bench_unfenced.err
+timeout 120 python bench.py --steps 100 --warmup 5 --no-cpu-baseline --no-secondary > gpurun_out/${T}_bench_headline.json 2> gpurun_out/${T}_bench_headline.err
+head -c 200 gpurun_out/${T}_bench_unfenced.json; echo; head -c 200 gpurun_out/${T}_bench_headline.json; echo
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name regex:'k_frame_mega|k_mega_prepare|k_gemv|k_skinny|k_embed|k_attn|k_sample|k_set_|k_rmsnorm|k_rope|k_gemm' -s 100 -c 400 --csv --log-file gpurun_out/${T}_bench_launches.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/${T}_ncu_bench.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_frame_mega -s 10 -c 1 -o gpurun_out/${T}_mega python bench.py --steps 12 --warmup 3 --no-cpu-baseline --no-secondary > gpurun_out/${T}_ncu_mega.log 2>&1
+ls -la gpurun_out/${T}_mega.ncu-rep
