@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/csm_b200.h"
+#include "nvtx_ranges.h"
 #include "lm_kernels.cuh"
 #include "mega.cuh"
 #include "gemm_tc.cuh"
@@ -826,6 +827,7 @@ extern "C" int32_t csm_create(const csm_config* cfg, const csm_weights* w, int32
   *out = nullptr;
   if (!valid_cfg(cfg)) return set_err(CSM_ERR_ARG, "unsupported csm_config (head_dim must be 64/128, dims multiples of 256)");
   if (!w || !workspace || max_batch < 1) return set_err(CSM_ERR_ARG, "null weights/workspace or max_batch < 1");
+  NvtxRange nvtx_create("csm.create");
   int ndev = 0;
   CU_TRY(cudaGetDeviceCount(&ndev));
   if (ndev < 1) return set_err(CSM_ERR_CUDA, "no CUDA device (libcsm_b200 has no CPU fallback)");
@@ -1000,6 +1002,7 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
   if (!tokens || !tokens_mask || !input_pos || !out || B < 1 || S < 1) return set_err(CSM_ERR_ARG, "bad tokens/mask/pos/out");
   if (B > x->max_batch) return set_err(CSM_ERR_STATE, "batch size exceeds the batch the caches were set up for");
   if (!(temperature > 0.f) || topk < 1) return set_err(CSM_ERR_ARG, "temperature must be > 0 and topk >= 1");
+  NvtxRange nvtx_frame("csm.generate_frame");
   cudaStream_t st = (cudaStream_t)stream;
   // cache lanes of the batch rows: identity for the reference's lock-step batch, any distinct lanes for a
   // continuous-batching caller; every lane keeps its own length
@@ -1061,6 +1064,7 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
   }
   const int per_pass = prefill_path == CSM_PREFILL_TENSOR ? (PREFILL_TC_ROWS / B > 0 ? PREFILL_TC_ROWS / B : 1) : PREFILL_CHUNK;
   for (int s0 = 0; s0 < S - 1; s0 += per_pass) {
+    NvtxRange nvtx_prefill("csm.prefill");
     const int chunk = (S - 1 - s0) < per_pass ? (S - 1 - s0) : per_pass;
     p.s0 = s0;
     launch_k(k_set_params, dim3(1), dim3(1), 0, st, x->d_params, p, s0 == 0 ? x->d_sync : nullptr); COUNT_LAUNCH();
@@ -1075,11 +1079,13 @@ extern "C" int32_t csm_generate_frame(csm_ctx* x, const int64_t* tokens, const u
   // last row + frame tail: persistent megakernel (batch 1) or the captured per-op graph
   p.s0 = S - 1;
   if (path == CSM_PATH_MEGA) {
+    NvtxRange nvtx_mega("csm.decode.mega");
     int rc = launch_mega(x, p, st);
     if (rc != CSM_OK) return rc;
     advance();
     return CSM_OK;
   }
+  NvtxRange nvtx_graph("csm.decode.graph");
   launch_k(k_set_params, dim3(1), dim3(1), 0, st, x->d_params, p, S == 1 ? x->d_sync : nullptr); COUNT_LAUNCH();
   CU_TRY(cudaGetLastError());
   if (path == CSM_PATH_DIRECT) {

@@ -246,17 +246,15 @@ __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1
 
 // ---- ordering of the plain KV-cache rows --------------------------------------------------------------
 // The depth decoder's cache rows are written as plain bf16 (a QKV epilogue, or the sampling phase's table
-// gather) and read by OTHER CTAs in later codebook steps of the SAME launch (attn_prefetch): stores that go
-// straight to L2 (the point of coherence; L1 is write-through and the readers use cp.async.cg, which bypasses
-// L1), read back >= 16 phases = tens of microseconds later.  The tagged hand-off words do not FORMALLY order
-// those plain stores; -DMEGA_KV_FENCE=7 adds the release fence after the writers' stores and the acquire fence
-// before the readers' loads that do (release -> chain of tagged words -> acquire at gpu scope).  Measured on
-// B200 (profiles/r2_kv_fence_variants.txt): writers +0.105 ms, readers +0.156 ms, sampling-phase writers
-// +0.039 ms per frame -- 7 % of the frame for an ordering the hardware provides anyway by a margin of four orders
-// of magnitude (a store reaches L2 in < 1 us), so the default build leaves them out; a tagged-word cache (one
-// tag per frame, no ordering assumed at all) was built and measured too and is slower still (+0.5 ms: its
-// reads cannot be asynchronous).  tests/test_gpu_stress.py runs 2000+ frames against the per-op kernels, which
-// have a kernel boundary between every write and read.  (The backbone cache is read by the NEXT launch.)
+// gather) and read by OTHER CTAs in later codebook steps of the SAME launch (attn_prefetch, cp.async.cg).  The
+// tagged hand-off words do not order those plain stores.  The default build orders them once per codebook step
+// (kv_step_sync below: a release by every CTA after the last layer's gate/up phase, an acquire by every CTA before
+// the sampling phase; +2.2 % of a frame).  Measured alternatives (profiles/r2_kv_fence_variants.txt), kept as
+// compile-time variants: bits 0-2 put fence.acq_rel.gpu into every QKV epilogue / attn_prefetch / sampling-phase
+// gather (+0.105 / +0.156 / +0.039 ms per frame, together +7.4 %); -DMEGA_KV_FENCE=0 orders nothing (the hardware
+// does deliver the rows -- a store reaches L2, the point of coherence, in < 1 us and the readers come >= 16 phases
+// later -- but nothing in the PTX memory model says so); a tagged-word cache was built and measured too (+17 %: its
+// reads cannot be asynchronous).  (The backbone cache is read by the NEXT launch.)
 template <int WHO>
 __device__ __forceinline__ void kv_fence() {
   if ((MEGA_KV_FENCE) & WHO) asm volatile("fence.acq_rel.gpu;" ::: "memory");

@@ -7,6 +7,7 @@
 #include <new>
 
 #include "../../include/csm_b200.h"
+#include "nvtx_ranges.h"
 #include "mimi_kernels.cuh"
 #include "mimi_tc.cuh"
 
@@ -578,6 +579,7 @@ static int rvq_search(mimi_ctx* x, int T, int K, int64_t* codes /*[K, T]*/, cuda
 extern "C" int32_t mimi_encode(mimi_ctx* x, const float* wav, int32_t B, int64_t Lin, int32_t K, int64_t* codes, void* stream) {
   if (!x) return csm_set_error(CSM_ERR_STATE, "mimi_encode: null context");
   if (!wav || !codes || B < 1 || Lin < 1 || K < 1 || K > 32) return csm_set_error(CSM_ERR_ARG, "mimi_encode: bad arguments");
+  NvtxRange nvtx_enc("mimi.encode");
   const long long T = (Lin + 1919) / 1920, Lp = T * 1920;
   if (T > x->max_frames) return csm_set_error(CSM_ERR_OVERFLOW, "mimi_encode: more frames than the codec was created for");
   cudaStream_t st = (cudaStream_t)stream;
@@ -835,6 +837,7 @@ static int decode_batch_tc(mimi_ctx* x, const int64_t* codes, int B, int K, int 
 extern "C" int32_t mimi_decode(mimi_ctx* x, const int64_t* codes, int32_t B, int32_t K, int32_t T, float* out, void* stream) {
   if (!x) return csm_set_error(CSM_ERR_STATE, "mimi_decode: null context");
   if (!codes || !out || B < 1 || K < 1 || K > 32 || T < 1) return csm_set_error(CSM_ERR_ARG, "mimi_decode: bad arguments");
+  NvtxRange nvtx_dec("mimi.decode");
   cudaStream_t st = (cudaStream_t)stream;
   const StateLayout SL = state_layout();
   static const bool batch_on = !(getenv("MIMI_BATCH") && getenv("MIMI_BATCH")[0] == '0');  // measurement aid
@@ -878,6 +881,7 @@ extern "C" void mimi_stream_destroy(mimi_stream* s) { delete s; }
 extern "C" int32_t mimi_decode_stream(mimi_stream* s, const int64_t* codes, int32_t K, int32_t T, float* out, void* stream) {
   if (!s) return csm_set_error(CSM_ERR_STATE, "mimi_decode_stream: null stream");
   if (!codes || !out || K < 1 || K > 32 || T < 1) return csm_set_error(CSM_ERR_ARG, "mimi_decode_stream: bad arguments");
+  NvtxRange nvtx_decs("mimi.decode_stream");
   cudaStream_t st = (cudaStream_t)stream;
   for (int t0 = 0; t0 < T; t0 += s->x->max_frames) {
     const int n = T - t0 < s->x->max_frames ? T - t0 : s->x->max_frames;

@@ -3,6 +3,7 @@
 #include <stdint.h>
 
 #include "../../include/csm_b200.h"
+#include "nvtx_ranges.h"
 #include "post_kernels.cuh"
 
 int csm_set_error(int code, const char* msg);  // api.cu
@@ -49,6 +50,7 @@ extern "C" int32_t csm_post_resample(const float* x, int64_t n, int32_t orig_fre
                                      size_t workspace_bytes, void* stream) {
   Rs r;
   if (!x || !y || n < 1 || !rs_params(orig_freq, new_freq, &r)) return csm_set_error(CSM_ERR_ARG, "csm_post_resample: bad arguments");
+  NvtxRange nvtx_rs("csm.post.resample");
   cudaStream_t st = (cudaStream_t)stream;
   const long long n_out = csm_post_resample_len(n, orig_freq, new_freq);
   if (r.of == r.nf) {
@@ -74,6 +76,7 @@ extern "C" int32_t csm_post_pcm16_segment(const float* audio, int64_t n, int64_t
     return csm_set_error(CSM_ERR_ARG, "csm_post_pcm16_segment: bad arguments");
   const long long total = start_silence + n + end_silence;
   if (fade_in > total || fade_out > total) return csm_set_error(CSM_ERR_ARG, "csm_post_pcm16_segment: fade longer than the segment");
+  NvtxRange nvtx_pcm("csm.post.pcm16");
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMemsetAsync(scratch4, 0, 4, st);
   if (e != cudaSuccess) return csm_set_error(CSM_ERR_CUDA, cudaGetErrorString(e));
