@@ -737,6 +737,10 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
                : "r"(smem_u32(p)));
 }
 
+#ifndef MEGA_PV_UNROLL
+#define MEGA_PV_UNROLL 2  /* P.V tiles of a warp in flight together (measured: 1 -> 2.954, 2 -> 2.943, 4 -> 2.946 ms per frame) */
+#endif
+constexpr int PV_UNROLL = MEGA_PV_UNROLL;
 __device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
   const int heads = ph.heads, kvn = ph.kv_heads, nb = ph.nb;
   const int gsh = ph.grp_shift, grp = 1 << gsh;  // heads per kv head (a power of two)
@@ -835,11 +839,14 @@ __device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
   csync<NCT, CBAR>();
   CK(7);
   {
-    // softmax rows: (kv head, column); lane == key
+    // softmax rows: (kv head, column); lane == key.  The kvn * ncols live rows are dealt round-robin over the warps
+    // (one row per warp for a one-row step: 2 kv heads x 4 heads of the group)
+    const int csh = gsh + nb - 1;  // log2(ncols): nb is 1 or 2, grp a power of two
 #pragma unroll
     for (int rr = 0; rr < 2; ++rr) {
-      const int row = c.warp * 2 + rr, kvh = row >> 3, col = row & 7;
-      if (kvh < kvn && col < ncols) {
+      const int rv = c.warp + rr * NW;
+      if (rv < (kvn << csh)) {
+        const int kvh = rv >> csh, col = rv & (ncols - 1), row = kvh * 8 + col;
         const int nkeys = ph.pos0 + (col >> gsh) + 1;
         const bool own = c.lane < nkeys;
         const float sc = own ? S[row * 32 + c.lane] : -INFINITY;
@@ -855,9 +862,10 @@ __device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
   CK(8);
   {
     // P.V: tiles of 8 output dims; A = P (columns as rows, 8 of 16 used), B = V^T by ldmatrix.trans
-    const int tiles = kvn * 16, per = tiles / NW;
-#pragma unroll 1
-    for (int i = 0; i < per; ++i) {
+    const int tiles = kvn * 16, per = tiles / NW;  // <= 4 (kvn <= 2)
+#pragma unroll PV_UNROLL
+    for (int i = 0; i < 4; ++i) {
+      if (i >= per) break;
       const int t = c.warp * per + i, kvh = t >> 4, n0 = (t & 15) * 8;
       uint32_t vb[4];
       ldmatrix_x4_trans(vb, c.xs + A_VOFF + (kvh * 32 + c.lane) * A_VS + n0);
@@ -1490,12 +1498,12 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
 // sits on the next descriptor because that one stays put until this warp passes the next barrier):
 //  1 (before the last layer's down phase of step i, i.e. after its gate/up phase: every KV row of steps <= i that
 //    this CTA wrote -- QKV epilogues, the sampling phase's table gather -- precedes the barrier): ONE thread runs the
-//    release pattern  fence.acq_rel.gpu ; st.relaxed.gpu done[cta] = tag(done_src).  The fence is cumulative over
-//    the other threads' stores through the barrier.  Off the critical path: the down phase starts by waiting
-//    > 1.5 us for the gate/up words of the other CTAs.
-//  2 (before the sampling phase of step i, two phases later): the last warp runs the acquire pattern  ld.volatile
-//    done[all CTAs] until they carry that tag ; fence.acq_rel.gpu.  The words were stored ~10 us earlier, so this is
-//    one L2 round trip, and only ONE CTA works in the sampling phase.  Every attn_prefetch of step i + 1 comes after
+//    release  st.release.gpu done[cta] = tag(done_src)  (bit 4 clear: fence.acq_rel.gpu ; st.relaxed.gpu -- same
+//    cost).  The release is cumulative over the other threads' stores through the barrier.  Measured: 0.75 us in that
+//    down phase (the thread's warp joins the phase late).
+//  2 (before the sampling phase of step i, two phases later): the last warp runs the acquire  ld.acquire.gpu
+//    done[all CTAs] until they carry that tag  (bit 4 clear: ld.volatile ... ; fence.acq_rel.gpu).  The words were
+//    stored ~10 us earlier, so this is one L2 round trip, and only ONE CTA works in the sampling phase (+0.45 us there).  Every attn_prefetch of step i + 1 comes after
 //    the barrier that ends the sampling phase, i.e. after this fence in causality order, and reads rows of
 //    steps <= i only (the row of step i + 1 travels as tagged words).
 // Release -> observed done word -> acquire is a direct synchronizes-with edge between EVERY writer CTA and EVERY
