@@ -655,8 +655,10 @@ static void build_mega_phases(csm_ctx* x, MegaBuild& mb) {
   const int is0 = (int)mb.v.size();
   mb.v.push_back(sample(0, ih0, x->dec.t_h + Dd));
   int dsrc[2] = {ih0, is0};
+  int kv_prev = -1;  // done_src of the previous codebook step's release / acquire
   for (int i = 1; i < C; ++i) {
     const int nb = (i == 1) ? 2 : 1, pos0 = (i == 1) ? 0 : i;
+    const int ifirst = (int)mb.v.size();  // the step's first phase
     for (int l = 0; l < c.decoder.layers; ++l)
       stack_phases(x, x->dec, x->mega_Rdec, l, nb, mega::POS_FIXED, pos0, true, mb, dsrc, (x->mega_keep >> (4 * (l & 7))) & 15,
                    (x->qkv_table_ok && i >= 2 && l == 0) ? dsrc[0] : -1);
@@ -664,7 +666,8 @@ static void build_mega_phases(csm_ctx* x, MegaBuild& mb) {
     // (= before its down phase), acquired before the sampling phase (mega::kv_step_sync; flags sit on the NEXT phase)
     const bool kv_step = i + 1 < C && mb.ncta <= 1024;
     const int igu = (int)mb.v.size() - 2;
-    if (kv_step) { mb.v[igu + 1].kv_sync = 1; mb.v[igu + 1].done_src = igu; mb.v[igu + 1].t_done = x->t_done; }
+    if (kv_prev >= 0) { mb.v[ifirst].kv_sync = 3; mb.v[ifirst].done_src = kv_prev; mb.v[ifirst].t_done = x->t_done; }
+    if (kv_step) { mb.v[igu + 1].kv_sync = 1 | (kv_prev << 8); mb.v[igu + 1].done_src = igu; mb.v[igu + 1].t_done = x->t_done; }
     mega::Phase h = gemv_phase_desc(mb, x->f_heads + (size_t)(i - 1) * x->Vf * Dd, x->Vf, Dd, x->mega_Rh,
                                     x->dec.t_h + (size_t)(nb - 1) * Dd, Dd, 1, EPI_PLAIN, x->dec.norm, eps, x->t_logits, x->Vf);
     h.x_src[0] = h.x_src[1] = dsrc[nb - 1];
@@ -673,7 +676,8 @@ static void build_mega_phases(csm_ctx* x, MegaBuild& mb) {
     mb.v.push_back(h);
     const int is = (int)mb.v.size();
     mb.v.push_back(sample(i, ih, (i + 1 < C) ? x->dec.t_h : nullptr));
-    if (kv_step) { mb.v[is].kv_sync = 2; mb.v[is].done_src = igu; mb.v[is].t_done = x->t_done; }
+    if (kv_step) { mb.v[is].kv_sync = 2 | (igu << 8); mb.v[is].done_src = igu; mb.v[is].t_done = x->t_done; }
+    kv_prev = kv_step ? igu : -1;
     dsrc[0] = is;
   }
 }
@@ -766,6 +770,7 @@ static int setup_mega(csm_ctx* x, cudaStream_t st) {
   std::vector<mega::Phase>& v = mb.v;
   if ((int)v.size() != mega_phase_count(x->cfg, x->qkv_table_ok)) return set_err(CSM_ERR_ARG, "internal: phase count mismatch");
   memset(&x->pf_table, 0, sizeof(x->pf_table));
+  x->pf_table.t_done = x->t_done;
   for (const mega::Phase& ph : v) {
     if (ph.type != mega::PH_GEMV) continue;
     if (x->pf_table.n >= mega::MAX_GEMV) return CSM_OK;  // too deep for the parameter-space table: per-op path only
@@ -1152,7 +1157,7 @@ extern "C" int32_t csm_debug_phase_table(const csm_config* cfg, int32_t n_ctas, 
     o.q_src = ph.q_src; o.logits_src = ph.logits_src;
     o.t_x = off(ph.t_x); o.t_out = off(ph.t_out); o.t_out2 = off(ph.t_out2); o.t_q = off(ph.t_q); o.t_kv = off(ph.t_kv);
     o.t_logits = off(ph.t_logits); o.t_next = off(ph.t_next);
-    o.kv_sync = ph.kv_sync; o.done_src = ph.done_src; o.pos0 = ph.pos0; o.pos_mode = ph.pos_mode;
+    o.kv_sync = ph.kv_sync & 255; o.done_src = ph.done_src; o.pos0 = ph.pos0; o.pos_mode = ph.pos_mode;
   }
   return n;
 }

@@ -34,8 +34,9 @@ namespace mega {
 constexpr int NW = 8;                 // warps per CTA
 constexpr int NCT = NW * 32;          // consumer threads per CTA
 #ifndef MEGA_KV_FENCE
-#define MEGA_KV_FENCE 24  /* bit 3: release / acquire once per codebook step (kv_step_sync), bit 4: as st.release / ld.acquire instead of fence + relaxed access; measurement variants: 0 = none, bit 0: fence in every QKV epilogue, bit 1: in every attn_prefetch, bit 2: in the sampling phase's gather */
+#define MEGA_KV_FENCE 32  /* bit 5: release / acquire once per codebook step, gpu-scope half on the producer warp (kv_producer_poll); inline variants: bit 3: release / acquire once per codebook step (kv_step_sync), bit 4: as st.release / ld.acquire instead of fence + relaxed access; measurement variants: 0 = none, bit 0: fence in every QKV epilogue, bit 1: in every attn_prefetch, bit 2: in the sampling phase's gather */
 #endif
+constexpr bool KV_PROD = ((MEGA_KV_FENCE) & 32) != 0;  // bit 5: the release / acquire runs on the producer warp (kv_producer_poll)
 constexpr int NTHREADS = NCT + 32;    // + one producer warp that feeds the weight rings
 #ifndef MEGA_SLOTS
 #define MEGA_SLOTS 4
@@ -111,8 +112,9 @@ struct __align__(16) Phase {
   int TV;    // EMBED: text vocabulary (range check of the text column)
   int rope_len;  // EMBED: rows of the backbone RoPE table (range check of input_pos)
   // ordering of the depth decoder's plain KV rows, once per codebook step (MEGA_KV_FENCE bit 3, see kv_fence):
-  // before this phase every CTA ... kv_sync 1: releases its rows (done word t_done[cta] tagged with phase done_src);
-  // 2: acquires (polls all CTAs' done words for the tag of phase done_src)
+  // before this phase every CTA ... kv_sync & 255 = 1: releases its rows (done word t_done[cta] tagged with phase
+  // done_src); 2: acquires (polls all CTAs' done words for the tag of phase done_src); 3: (producer-warp variant only)
+  // waits until the acquire for done_src is acknowledged.  kv_sync >> 8 = done_src of the previous request (-1: none)
   int kv_sync, done_src;
   uint32_t* t_done;
 };
@@ -128,7 +130,8 @@ struct PfDesc {
 static_assert(sizeof(PfDesc) == 24, "PfDesc layout");
 struct PfTable {
   int n;
-  int pad_[3];
+  int pad_;
+  uint32_t* t_done;  // per-CTA done words of the KV ordering (kv_producer_poll)
   PfDesc d[MAX_GEMV];
 };
 
@@ -264,6 +267,14 @@ __device__ __forceinline__ uint4 lda4(const uint32_t* p) {
   uint4 v;
   asm volatile("ld.acquire.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
+}
+__device__ __forceinline__ uint32_t lds_acquire_cta(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_release_cta(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_relaxed_gpu(uint32_t* p, uint32_t v) {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -406,8 +417,39 @@ __device__ __forceinline__ const unsigned char* cursor_src(const Cursor& k, cons
   return reinterpret_cast<const unsigned char*>(d.W) + (size_t)k.g * d.group_bytes + (size_t)lane * tb + (size_t)k.ch * chunk;
 }
 
+// KV ordering on the producer warp (MEGA_KV_FENCE bit 5): consumer thread NCT-1 posts a request word
+// {tag of done_src | type} in shared memory (st.release.cta after the phase's end barrier); the producer warp looks
+// at the word once per ring step and in its wait loop, and runs the gpu-scope half there -- type 1: st.release.gpu
+// done[cta] = tag (cumulative over the consumers' cache stores through barrier -> release.cta -> acquire.cta);
+// type 2: ld.acquire.gpu of every CTA's done word until it carries the tag -- then acknowledges the request in a second
+// shared word (st.release.cta), which the consumers read (ld.acquire.cta) before the next step's attn_prefetch.
+// A stall of this warp is absorbed by the weight rings (a warp's four slots hold its whole slice of a down phase).
+__device__ __forceinline__ void kv_producer_poll(uint32_t& last, uint32_t* kv, uint32_t* done, Sync* sync, int lane) {
+  const uint32_t r = lds_acquire_cta(&kv[0]);  // same word in every lane: warp-uniform
+  if (r == last) return;
+  last = r;
+  if ((r & 3u) == 3u) return;  // the consumers have run their last phase: nothing to do, nothing to acknowledge
+  const uint32_t dtag = r & 0xffff0000u;
+  if ((r & 3u) == 1u) {
+    if (lane == 0) {
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(done + blockIdx.x), "r"(dtag) : "memory");
+      if (blockIdx.x == gridDim.x - 1)  // pad to whole 16-byte units for the pollers
+        for (unsigned q = gridDim.x; (q & 3u) != 0; ++q) st_relaxed_gpu(done + q, dtag);
+    }
+  } else {
+    for (unsigned q = lane * 4; q < gridDim.x; q += 128) {
+      uint4 v = lda4(done + q);
+      for (unsigned spin = 0; !fresh4(v, dtag); ++spin) {
+        if (give_up(sync, spin, 0x40b)) break;
+        v = lda4(done + q);
+      }
+    }
+  }
+  __syncwarp();
+  if (lane == 0) sts_release_cta(&kv[1], r);
+}
 __device__ __forceinline__ void producer_loop(const PfDesc* tab, int ntab, unsigned char* ring, uint64_t* full, uint64_t* empty,
-                                              Sync* sync, int lane) {
+                                              Sync* sync, int lane, uint32_t* kv, uint32_t* done) {
   const int cta = blockIdx.x, ncta = gridDim.x;
   // Weights that are used once per frame stream through L2 evict-first.  The depth decoder's 222 MB are
   // used 31 times per frame: the matrices marked "keep" are loaded evict-last, so that part of them
@@ -418,7 +460,9 @@ __device__ __forceinline__ void producer_loop(const PfDesc* tab, int ntab, unsig
   cursor_seek(k, tab, ntab, cta, ncta);
   k2 = k;
   unsigned ahead = 0;  // ring steps by which the L2 cursor k2 leads the ring cursor k
+  uint32_t kv_last = 0;
   for (unsigned issued = 0; cursor_valid(k, ntab); ++issued) {
+    if (KV_PROD) kv_producer_poll(kv_last, kv, done, sync, lane);
     const int slot = issued % SLOTS;
     uint64_t* eb = &empty[(lane < NW ? lane : 0) * SLOTS + slot];
     const uint32_t parity = ((issued / SLOTS) & 1) ^ 1;
@@ -430,6 +474,7 @@ __device__ __forceinline__ void producer_loop(const PfDesc* tab, int ntab, unsig
       const bool ok = lane >= NW || (L2_AHEAD > 0 ? mbar_test(eb, parity) : mbar_try(eb, parity));
       if (__all_sync(0xffffffffu, ok)) break;
       if (__any_sync(0xffffffffu, give_up(sync, spin, 0x100, 1u << 26))) break;  // warp-uniform exit
+      if (KV_PROD) kv_producer_poll(kv_last, kv, done, sync, lane);
       if (L2_AHEAD > 0 && ahead < SLOTS + L2_AHEAD && cursor_valid(k2, ntab)) {
         if (ahead >= SLOTS && lane < NW) {  // the first SLOTS steps ahead are in the ring (or on their way) already
           int chunk;
@@ -453,6 +498,12 @@ __device__ __forceinline__ void producer_loop(const PfDesc* tab, int ntab, unsig
     if (ahead > 0) --ahead;
     else k2 = k;
   }
+  // a CTA whose last chunk goes out early (no groups in the frame's last phases) still has requests to serve
+  if (KV_PROD)
+    for (unsigned spin = 0; (kv_last & 3u) != 3u; ++spin) {
+      kv_producer_poll(kv_last, kv, done, sync, lane);
+      if (__any_sync(0xffffffffu, give_up(sync, spin, 0x40f, 1u << 26))) break;
+    }
 }
 
 #define CK(i) do { if (c.trp) c.trp[i] = clock64(); } while (0)
@@ -1511,7 +1562,7 @@ __device__ __forceinline__ void sample_phase(const Phase& ph, Ctx& c) {
 __device__ __forceinline__ void kv_step_sync(const Phase& ph, const Ctx& c) {
   constexpr bool FUSED = ((MEGA_KV_FENCE) & 16) != 0;  // st.release / ld.acquire instead of fence + relaxed access
   const uint32_t dtag = tag_of(c.seq, ph.done_src);
-  if (ph.kv_sync == 1) {
+  if ((ph.kv_sync & 255) == 1) {
     if (c.tid == NCT - 1) {
       if (FUSED) {
         asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ph.t_done + blockIdx.x), "r"(dtag) : "memory");
@@ -1522,7 +1573,7 @@ __device__ __forceinline__ void kv_step_sync(const Phase& ph, const Ctx& c) {
       if (blockIdx.x == gridDim.x - 1)  // pad to whole 16-byte units for the pollers
         for (unsigned q = gridDim.x; (q & 3u) != 0; ++q) st_relaxed_gpu(ph.t_done + q, dtag);
     }
-  } else if (c.warp == NW - 1) {
+  } else if ((ph.kv_sync & 255) == 2 && c.warp == NW - 1) {
     for (unsigned q = c.lane * 4; q < gridDim.x; q += 128) {
       uint4 v = FUSED ? lda4(ph.t_done + q) : ldv4(ph.t_done + q);
       for (unsigned spin = 0; !fresh4(v, dtag); ++spin) {
@@ -1531,6 +1582,23 @@ __device__ __forceinline__ void kv_step_sync(const Phase& ph, const Ctx& c) {
       }
     }
     if (!FUSED) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  }
+}
+
+// Consumer side of the producer-warp variant (kv_producer_poll).  kv_sync = type | previous request's done_src << 8:
+// type 1 / 2: thread NCT-1 posts the request (after checking that the previous one was acknowledged: long done);
+// type 3 (the next step's first phase): every thread waits for the acknowledgement of the step's acquire.
+__device__ __forceinline__ void kv_post(const Phase& nx, const Ctx& c, uint32_t* kvw) {
+  const int type = nx.kv_sync & 255, prev_src = nx.kv_sync >> 8;
+  const uint32_t dtag = tag_of(c.seq, nx.done_src);
+  if (type == 3) {
+    for (unsigned spin = 0; lds_acquire_cta(&kvw[1]) != (dtag | 2u); ++spin)
+      if (give_up(c.sync, spin, 0x40d)) break;
+  } else if (c.tid == NCT - 1) {
+    const uint32_t prev = type == 2 ? (dtag | 1u) : (prev_src >= 0 ? (tag_of(c.seq, prev_src) | 2u) : 0u);
+    for (unsigned spin = 0; lds_acquire_cta(&kvw[1]) != prev; ++spin)
+      if (give_up(c.sync, spin, 0x40e)) break;
+    sts_release_cta(&kvw[0], dtag | (uint32_t)type);
   }
 }
 
@@ -1548,10 +1616,12 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
   uint64_t* empty = full + NW * SLOTS;                                     // [NW*SLOTS]
   float* scratch = reinterpret_cast<float*>(empty + NW * SLOTS);           // [34]
   int* iscratch = reinterpret_cast<int*>(scratch + 34);                    // [40]
-  static_assert(2 * sizeof(Phase) + 2 * NW * SLOTS * 8 + 34 * 4 + 40 * 4 <= SMEM_MISC, "misc region too small");
+  uint32_t* kvw = reinterpret_cast<uint32_t*>(iscratch + 40);              // [2] KV ordering on the producer warp: request, acknowledgement
+  static_assert(2 * sizeof(Phase) + 2 * NW * SLOTS * 8 + 34 * 4 + 40 * 4 + 2 * 4 <= SMEM_MISC, "misc region too small");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2 * NW * SLOTS; ++i) mbar_init(&full[i], 1);  // full[] and empty[] are contiguous
+    kvw[0] = kvw[1] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -1561,7 +1631,7 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
   __syncthreads();
 
   if (threadIdx.x >= NCT) {  // producer warp: feeds the eight weight rings for the whole frame, then retires
-    producer_loop(tab.d, tab.n, ring, full, empty, sync, threadIdx.x - NCT);  // the schedule is read from parameter space: only this warp walks it
+    producer_loop(tab.d, tab.n, ring, full, empty, sync, threadIdx.x - NCT, kvw, tab.t_done);  // the schedule is read from parameter space: only this warp walks it
     return;
   }
 
@@ -1610,12 +1680,14 @@ k_frame_mega(const Phase* __restrict__ phases, int nphases, const FrameParams* _
     if (p + 1 < nphases) {
       const Phase& nx = phbuf[(p + 1) & 1];  // stable until this warp passes the NEXT phase's barrier (ph is not: the others re-stage it)
       if (((MEGA_KV_FENCE) & 8) && nx.kv_sync) kv_step_sync(nx, c);
+      if (KV_PROD && nx.kv_sync) kv_post(nx, c, kvw);
       if (nx.type == PH_GEMV && nx.attn_prologue) {
         const int cl = local_cta(blockIdx.x, gridDim.x, nx.rot);
         if (nx.gq + (cl < nx.gr ? 1 : 0) > 0) attn_prefetch(nx, c);
       }
     }
   }
+  if (KV_PROD && c.tid == NCT - 1) sts_release_cta(&kvw[0], 3u);  // lets the producer warp retire
 }
 
 }  // namespace mega

@@ -122,6 +122,7 @@ def test_plain_kv_rows_are_released_and_acquired(tiny, ncta, qkv):
     releases = {}           # done_src -> flagged phase
     acquired_release = -1   # flagged phase of the release that the latest acquire observed
     acquire_at = -1
+    waited_at = -1          # phase flagged with the wait for the latest acquire's acknowledgement
     writers_before_step = -1  # last phase that wrote plain rows the current step reads from the cache
     last_writer = -1
     readers = 0
@@ -133,6 +134,11 @@ def test_plain_kv_rows_are_released_and_acquired(tiny, ncta, qkv):
         elif x.kv_sync == 2:
             assert x.done_src in releases and releases[x.done_src] < p, (p, "acquire without an earlier release")
             acquired_release, acquire_at = releases[x.done_src], p
+        elif x.kv_sync == 3:
+            # producer-warp variant: every consumer thread waits here for the acknowledgement of that acquire, right
+            # before its own prefetch of phase p's cached rows
+            assert acquire_at >= 0 and ph[acquire_at].done_src == x.done_src and acquire_at < p
+            waited_at = p
         else:
             assert x.kv_sync == 0
         if p < first_dec:
@@ -152,4 +158,6 @@ def test_plain_kv_rows_are_released_and_acquired(tiny, ncta, qkv):
             assert acquired_release > writers_before_step, (p, "reads rows of phase", writers_before_step, "released at", acquired_release)
             # the acquiring warp and the prefetching threads are ordered by the barrier ending phase acquire_at
             assert acquire_at < p, (p, "acquire at", acquire_at)
+            # producer-warp variant: the wait for that acquire's acknowledgement sits at or before the reader
+            assert acquire_at < waited_at <= p, (p, "wait at", waited_at)
     assert readers == (cfg.codebooks - 2) * cfg.decoder.layers
