@@ -250,10 +250,11 @@ __device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1
 // ---- ordering of the plain KV-cache rows --------------------------------------------------------------
 // The depth decoder's cache rows are written as plain bf16 (a QKV epilogue, or the sampling phase's table
 // gather) and read by OTHER CTAs in later codebook steps of the SAME launch (attn_prefetch, cp.async.cg).  The
-// tagged hand-off words do not order those plain stores.  The default build orders them once per codebook step
-// (kv_step_sync below: a release by every CTA after the last layer's gate/up phase, an acquire by every CTA before
-// the sampling phase; +2.2 % of a frame).  Measured alternatives (profiles/r2_kv_fence_variants.txt), kept as
-// compile-time variants: bits 0-2 put fence.acq_rel.gpu into every QKV epilogue / attn_prefetch / sampling-phase
+// tagged hand-off words do not order those plain stores.  The default build orders them once per codebook step: a
+// release by every CTA after the last layer's gate/up phase, an acquire by every CTA before the sampling phase, the
+// gpu-scope instructions issued by the producer warp (kv_producer_poll / kv_post below; +2.3 % of a frame).  Measured
+// alternatives (profiles/r2_kv_fence_variants.txt), kept as compile-time variants: bits 3-4 run the same protocol
+// inline in the consumer warps (kv_step_sync; +3.1 %: its code spills at the 168-register cap); bits 0-2 put fence.acq_rel.gpu into every QKV epilogue / attn_prefetch / sampling-phase
 // gather (+0.105 / +0.156 / +0.039 ms per frame, together +7.4 %); -DMEGA_KV_FENCE=0 orders nothing (the hardware
 // does deliver the rows -- a store reaches L2, the point of coherence, in < 1 us and the readers come >= 16 phases
 // later -- but nothing in the PTX memory model says so); a tagged-word cache was built and measured too (+17 %: its
