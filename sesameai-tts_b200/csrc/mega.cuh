@@ -425,11 +425,23 @@ __device__ __forceinline__ const unsigned char* cursor_src(const Cursor& k, cons
 // type 2: ld.acquire.gpu of every CTA's done word until it carries the tag -- then acknowledges the request in a second
 // shared word (st.release.cta), which the consumers read (ld.acquire.cta) before the next step's attn_prefetch.
 // A stall of this warp is absorbed by the weight rings (a warp's four slots hold its whole slice of a down phase).
+#ifndef MEGA_KV_SERVE_NOINLINE
+#define MEGA_KV_SERVE_NOINLINE 0  /* 1: one out-of-line copy of the request handler for the producer loop's three call sites */
+#endif
+#if MEGA_KV_SERVE_NOINLINE
+#define KV_SERVE_ATTR __noinline__
+#else
+#define KV_SERVE_ATTR __forceinline__
+#endif
+__device__ KV_SERVE_ATTR void kv_producer_serve(uint32_t r, uint32_t* kv, uint32_t* done, Sync* sync, int lane);
 __device__ __forceinline__ void kv_producer_poll(uint32_t& last, uint32_t* kv, uint32_t* done, Sync* sync, int lane) {
   const uint32_t r = lds_acquire_cta(&kv[0]);  // same word in every lane: warp-uniform
   if (r == last) return;
   last = r;
   if ((r & 3u) == 3u) return;  // the consumers have run their last phase: nothing to do, nothing to acknowledge
+  kv_producer_serve(r, kv, done, sync, lane);
+}
+__device__ KV_SERVE_ATTR void kv_producer_serve(uint32_t r, uint32_t* kv, uint32_t* done, Sync* sync, int lane) {
   const uint32_t dtag = r & 0xffff0000u;
   if ((r & 3u) == 1u) {
     if (lane == 0) {
@@ -790,7 +802,7 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* 
 }
 
 #ifndef MEGA_PV_UNROLL
-#define MEGA_PV_UNROLL 2  /* P.V tiles of a warp in flight together (measured: 1 -> 2.954, 2 -> 2.943, 4 -> 2.946 ms per frame) */
+#define MEGA_PV_UNROLL 4  /* P.V tiles of a warp in flight together (final tree, ms per frame: 1 -> 2.953, 2 -> 2.943, 4 -> 2.930; tools/runs/gpu_check52.sh) */
 #endif
 constexpr int PV_UNROLL = MEGA_PV_UNROLL;
 __device__ __forceinline__ void attn_small_into_x(const Phase& ph, Ctx& c) {
