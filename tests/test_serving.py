@@ -157,3 +157,21 @@ def test_serve_sharded_two_gloo_ranks():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_throwaway_warm_up_server_leaves_the_next_server_untouched():
+    """bench.py config 5 decodes two frames of every request on a throwaway server before the timed job (first-use
+    costs of the process belong to the service's start-up): the pattern must not disturb the server that follows on
+    the same model, and two-frame budgets must retire cleanly."""
+    n = 13
+    budgets = [5 + (r * 2) % 4 for r in range(n)]
+    eos = {3: 2}
+    fm = FakeModel(eos)
+    reqs = _requests(n, budgets)
+    warm = LaneGroups(fm, 1, 8, 0.9, 50, max_frames=16)
+    got_w = warm.run([Request(q.rid, q.tokens, q.mask, 2) for q in reqs])
+    assert sorted(got_w) == list(range(n)) and all(got_w[r].shape[0] <= 2 for r in range(n))
+    del warm
+    got = LaneGroups(fm, 1, 8, 0.9, 50, max_frames=16).run(reqs)
+    for r in range(n):
+        assert torch.equal(got[r], _expected(r, eos.get(r, -1), budgets[r])), r
